@@ -1,0 +1,171 @@
+/*
+ * magi_attn.h - C-ABI of the B200-native MAGI-1 attention hot path (libmagi_attn.so).
+ *
+ * Plain pointers and sizes only: no torch types cross this boundary. Every entry point is asynchronous on the
+ * `stream` it is given (a cudaStream_t passed as void*), never synchronises the device, never allocates persistent
+ * device memory, and is CUDA-graph capturable. All return an int status: 0 = ok, non-zero = error (the message is
+ * available from magi_last_error(), thread-local).
+ *
+ * The reference (samiazirar/MAGI-1) has no FFI of its own: the "operator API" of this path is a set of Python call
+ * sites inside inference/model/dit/dit_module.py. Each entry point below names the call site(s) it replaces.
+ * INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ *
+ * Layout conventions (reference: dit_module.py:953-996, 1023-1066):
+ *   q / out : (tokens, Hq, 128) bf16, explicit token/head strides in elements, innermost dim contiguous
+ *   k / v   : (tokens, Hkv, 128) bf16 with explicit strides, so the reference's packed KV tensor
+ *             (tokens, Hkv, 256) = [K(128) | V(128)] (dit_module.py:996) is consumed in place:
+ *             k = base, v = base + 128, token_stride = Hkv*256, head_stride = 256.
+ *   GQA     : q head h reads kv head h / (Hq / Hkv) (flash-attn convention).
+ */
+#ifndef MAGI_ATTN_H_
+#define MAGI_ATTN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MAGI_API __attribute__((visibility("default")))
+#else
+#define MAGI_API
+#endif
+
+#define MAGI_HEAD_DIM 128
+#define MAGI_ROPE_DIM 96
+
+/* A (tokens, heads, 128) bf16 view. Strides are in elements. */
+typedef struct magi_view {
+  const void* ptr;
+  int64_t tokens;
+  int64_t token_stride;
+  int64_t head_stride;
+} magi_view;
+
+/*
+ * Range-masked ("chunk-causal") attention forward.
+ * Replaces: flex_flash_attn_func      dit_module.py:1032-1043, 1074-1085, 1111-1122
+ *           flash_attn_func loop      dit_module.py:1046-1065, 1087-1095
+ *           flash_attn_varlen_func    dit_module.py:1124-1133   (give cu_seqlens_* instead of *_ranges)
+ *           torch.cat/chunk of cache  dit_module.py:914-931, 945-946 (two-segment K/V source, no copy)
+ *
+ * For each i < n_ranges, query rows [q_ranges[i][0], q_ranges[i][1]) attend densely (non-causally) to key rows
+ * [k_ranges[i][0], k_ranges[i][1]) of the *concatenation* seg_a ++ seg_b. seg_a is the KV-cache prefix, seg_b the
+ * new tokens of this forward; either may be empty (tokens == 0). Query ranges must be disjoint (the reference passes
+ * disable_fwd_atomic_reduction=True, dit_module.py:1042). Rows covered by no range are left untouched.
+ * A range with an empty key interval yields out = 0, lse = -inf.
+ *
+ * Exactly one of {q_ranges,k_ranges} / {cu_seqlens_q,cu_seqlens_k} must be non-NULL; all are int32 DEVICE pointers
+ * ((n,2) row-major, resp. n+1 entries). lse is (total_q, Hq) fp32 natural-log, may be NULL.
+ */
+typedef struct magi_attn_args {
+  magi_view q;
+  magi_view k_a, v_a; /* segment A: KV-cache prefix (tokens may be 0) */
+  magi_view k_b, v_b; /* segment B: new tokens                         */
+  void* out;
+  int64_t out_token_stride, out_head_stride;
+  float* lse;
+  const int32_t* q_ranges;
+  const int32_t* k_ranges;
+  const int32_t* cu_seqlens_q;
+  const int32_t* cu_seqlens_k;
+  int32_t n_ranges;
+  int32_t num_heads_q, num_heads_kv, head_dim;
+  float softmax_scale; /* <= 0 selects 1/sqrt(head_dim) (reference passes softmax_scale=None) */
+  void* workspace;     /* >= magi_attn_workspace_bytes(n_ranges) bytes of device memory        */
+  size_t workspace_bytes;
+  int32_t num_sms;     /* 0 = all SMs of the current device                                    */
+} magi_attn_args;
+
+MAGI_API size_t magi_attn_workspace_bytes(int32_t n_ranges);
+MAGI_API int magi_attn_fwd(const magi_attn_args* args, void* stream);
+
+/*
+ * Fused QK-LayerNorm(+1p) + RoPE-96 + layout prologue.
+ * Replaces: get_q / get_k / get_v / get_kv   dit_module.py:953-996 (7 eager kernels per tensor)
+ *           FusedLayerNorm.forward           dit_module.py:355-357
+ *           flash_attn rotary (Triton)       dit_module.py:961, 978
+ *           KV-cache slice-assign            dit_module.py:918-929 (append fused: second store target)
+ *
+ * x_q / x_k / x_v are the bf16 projection outputs, (rows, H*128) row-major with rows = (sq b) flattened.
+ * LayerNorm runs in fp32 over 128 with gamma = (w + 1) if zero_centered_gamma else w, bias b, eps; weights are
+ * fp32 (the reference promotes q/k_layernorm to fp32, dit_model.py:621-633) or bf16 (ln_dtype = 1; the +1 is
+ * then rounded to bf16 like the reference's `self.weight + 1` in bf16).
+ * RoPE is the non-interleaved (NeoX) rotation of dims [0,48) with [48,96) in fp32 by sin/cos (seq, 48) fp32,
+ * row r uses table row r / batch; dims [96,128) pass through. One rounding to bf16 at the end.
+ * Passing sin == NULL skips RoPE (cross-attention q/k, dit_module.py:1005-1021).
+ *
+ * q_out: (rows, Hq, 128) with q_out strides. kv_out: packed (rows, Hkv, 256) rows, K at +0 and V at +128, with
+ * kv_out_token_stride (elements). If cache != NULL, rows [0, cache_rows) are ALSO stored to
+ * cache + (cache_row_offset + r) * cache_token_stride (the KV-cache append; cache_rows excludes the last chunk
+ * when distill_nearly_clean_chunk, dit_module.py:921-925).
+ * Head remap for Ulysses: if head_perm_cp > 1 the outputs are written in all-to-all SEND layout
+ * "(cp seq) hn hd" (context_parallel.py:396): output row = (h / (H/cp)) * rows + r, head = h % (H/cp).
+ */
+typedef struct magi_prologue_args {
+  const void* x_q; /* may be NULL (kv only)  */
+  const void* x_k; /* may be NULL (q only)   */
+  const void* x_v; /* may be NULL            */
+  int64_t rows;
+  int64_t xq_row_stride, xk_row_stride, xv_row_stride; /* elements */
+  int32_t num_heads_q, num_heads_kv;
+  int32_t batch; /* rope row = r / batch */
+  const void* ln_q_w;
+  const void* ln_q_b;
+  const void* ln_k_w;
+  const void* ln_k_b;
+  int32_t ln_dtype; /* 0 = fp32, 1 = bf16 */
+  float eps;
+  int32_t zero_centered_gamma;
+  const float* sin; /* (rows / batch, 48) or NULL */
+  const float* cos;
+  void* q_out;
+  int64_t q_out_token_stride, q_out_head_stride;
+  void* kv_out;
+  int64_t kv_out_token_stride, kv_out_head_stride; /* head stride normally 256 */
+  void* cache;
+  int64_t cache_token_stride, cache_head_stride;
+  int64_t cache_row_offset, cache_rows;
+  int32_t head_perm_cp; /* 0/1 = identity */
+} magi_prologue_args;
+
+MAGI_API int magi_qk_norm_rope_fwd(const magi_prologue_args* args, void* stream);
+
+/*
+ * Copy packed KV rows into the cache slot: cache[row_offset : row_offset + rows] = kv[0 : rows].
+ * Replaces dit_module.py:929 when the new KV arrives from the Ulysses all-to-all rather than the prologue.
+ */
+MAGI_API int magi_kv_cache_append(void* cache, int64_t cache_token_stride, const void* kv, int64_t kv_token_stride,
+                         int64_t row_offset, int64_t rows, int64_t row_elems, void* stream);
+
+/*
+ * Merge two partial attention results over disjoint key sets (ring-KV exchange step):
+ *   lse = log(exp(lse_a) + exp(lse_b)); out = out_a * exp(lse_a - lse) + out_b * exp(lse_b - lse)
+ * out_a/lse_a are updated in place. (rows, heads, 128) bf16 contiguous-innermost with token/head strides.
+ * New capability (no reference call site; SURVEY.md section 2.2 "ring attention: no").
+ */
+MAGI_API int magi_lse_merge(void* out_a, float* lse_a, const void* out_b, const float* lse_b, int64_t rows, int32_t heads,
+                   int64_t a_token_stride, int64_t a_head_stride, int64_t b_token_stride, int64_t b_head_stride,
+                   void* stream);
+
+/*
+ * Head<->sequence re-layout used around the Ulysses all-to-all.
+ *   mode 0: "seq (cp hn) hd -> (cp seq) hn hd"  (context_parallel.py:396, send side of all_to_all_input_split)
+ *   mode 1: "(cp seq) hn hd -> seq (cp hn) hd"  (context_parallel.py:596, after all_to_all_output_split)
+ * kv_repeat > 1 replicates each head kv_repeat times first (context_parallel.py:393-394).
+ */
+MAGI_API int magi_ulysses_relayout(void* dst, const void* src, int64_t seq, int32_t heads, int32_t head_elems, int32_t cp,
+                          int32_t kv_repeat, int32_t mode, void* stream);
+
+/* Diagnostics */
+MAGI_API const char* magi_last_error(void);
+MAGI_API const char* magi_build_info(void);
+/* Number of kernel launches issued by this library in this process (all threads). */
+MAGI_API uint64_t magi_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAGI_ATTN_H_ */

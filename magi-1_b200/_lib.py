@@ -1,0 +1,154 @@
+"""ctypes binding of libmagi_attn.so (the C-ABI declared in include/magi_attn.h).
+
+The shared library is the product; this module only mirrors its structs. There is no fallback: if the library is
+missing or was not built, importing the compute entry points raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmagi_attn.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+# Every symbol include/magi_attn.h declares (checked by tests/test_abi.py against the header text).
+EXPORTS = (
+    "magi_attn_workspace_bytes",
+    "magi_attn_fwd",
+    "magi_qk_norm_rope_fwd",
+    "magi_kv_cache_append",
+    "magi_lse_merge",
+    "magi_ulysses_relayout",
+    "magi_last_error",
+    "magi_build_info",
+    "magi_launch_count",
+)
+
+
+class MagiView(C.Structure):
+    _fields_ = [
+        ("ptr", C.c_void_p),
+        ("tokens", C.c_int64),
+        ("token_stride", C.c_int64),
+        ("head_stride", C.c_int64),
+    ]
+
+
+class MagiAttnArgs(C.Structure):
+    _fields_ = [
+        ("q", MagiView),
+        ("k_a", MagiView),
+        ("v_a", MagiView),
+        ("k_b", MagiView),
+        ("v_b", MagiView),
+        ("out", C.c_void_p),
+        ("out_token_stride", C.c_int64),
+        ("out_head_stride", C.c_int64),
+        ("lse", C.c_void_p),
+        ("q_ranges", C.c_void_p),
+        ("k_ranges", C.c_void_p),
+        ("cu_seqlens_q", C.c_void_p),
+        ("cu_seqlens_k", C.c_void_p),
+        ("n_ranges", C.c_int32),
+        ("num_heads_q", C.c_int32),
+        ("num_heads_kv", C.c_int32),
+        ("head_dim", C.c_int32),
+        ("softmax_scale", C.c_float),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_size_t),
+        ("num_sms", C.c_int32),
+    ]
+
+
+class MagiPrologueArgs(C.Structure):
+    _fields_ = [
+        ("x_q", C.c_void_p),
+        ("x_k", C.c_void_p),
+        ("x_v", C.c_void_p),
+        ("rows", C.c_int64),
+        ("xq_row_stride", C.c_int64),
+        ("xk_row_stride", C.c_int64),
+        ("xv_row_stride", C.c_int64),
+        ("num_heads_q", C.c_int32),
+        ("num_heads_kv", C.c_int32),
+        ("batch", C.c_int32),
+        ("ln_q_w", C.c_void_p),
+        ("ln_q_b", C.c_void_p),
+        ("ln_k_w", C.c_void_p),
+        ("ln_k_b", C.c_void_p),
+        ("ln_dtype", C.c_int32),
+        ("eps", C.c_float),
+        ("zero_centered_gamma", C.c_int32),
+        ("sin", C.c_void_p),
+        ("cos", C.c_void_p),
+        ("q_out", C.c_void_p),
+        ("q_out_token_stride", C.c_int64),
+        ("q_out_head_stride", C.c_int64),
+        ("kv_out", C.c_void_p),
+        ("kv_out_token_stride", C.c_int64),
+        ("kv_out_head_stride", C.c_int64),
+        ("cache", C.c_void_p),
+        ("cache_token_stride", C.c_int64),
+        ("cache_head_stride", C.c_int64),
+        ("cache_row_offset", C.c_int64),
+        ("cache_rows", C.c_int64),
+        ("head_perm_cp", C.c_int32),
+    ]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile libmagi_attn.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    if force:
+        subprocess.run(["make", "-C", CSRC_DIR, "clean"], check=True, capture_output=not verbose)
+    r = subprocess.run(["make", "-C", CSRC_DIR, "-j4"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libmagi_attn.so failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (once). Raises if it has not been built: there is no CPU or eager fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C magi-1_b200/csrc`). This package has no fallback path."
+        )
+    L = C.CDLL(LIB_PATH)
+    L.magi_attn_workspace_bytes.restype = C.c_size_t
+    L.magi_attn_workspace_bytes.argtypes = [C.c_int32]
+    L.magi_attn_fwd.restype = C.c_int
+    L.magi_attn_fwd.argtypes = [C.POINTER(MagiAttnArgs), C.c_void_p]
+    L.magi_qk_norm_rope_fwd.restype = C.c_int
+    L.magi_qk_norm_rope_fwd.argtypes = [C.POINTER(MagiPrologueArgs), C.c_void_p]
+    L.magi_kv_cache_append.restype = C.c_int
+    L.magi_kv_cache_append.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                       C.c_void_p]
+    L.magi_lse_merge.restype = C.c_int
+    L.magi_lse_merge.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64,
+                                 C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
+    L.magi_ulysses_relayout.restype = C.c_int
+    L.magi_ulysses_relayout.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_void_p]
+    L.magi_last_error.restype = C.c_char_p
+    L.magi_build_info.restype = C.c_char_p
+    L.magi_launch_count.restype = C.c_uint64
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().magi_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what}: {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().magi_launch_count())

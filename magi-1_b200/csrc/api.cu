@@ -1,0 +1,300 @@
+// extern "C" boundary of libmagi_attn.so (declared in include/magi_attn.h): argument checking, TMA tensor-map
+// encoding, launches. No torch types, no device synchronisation, no persistent device allocations.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/magi_attn.h"
+#include "attn_fwd.cuh"
+#include "prologue.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+#define MAGI_CHECK(cond, ...) \
+  do {                        \
+    if (!(cond)) return fail(__VA_ARGS__); \
+  } while (0)
+
+#define MAGI_CUDA(expr)                                                                      \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(e__));    \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// libcuda is resolved at run time through the runtime API so the library loads on machines without a driver
+// (the CPU-only symbol-export test) and carries no link-time dependency on libcuda.so.1.
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// (tokens, heads, 128) bf16 view -> 3-D tensor map {128, heads, tokens}, box {64, 1, 128}, 128B swizzle.
+// Rows past `tokens` are zero-filled by the TMA unit, which is what makes ragged range edges safe.
+int make_view_map(CUtensorMap* m, const magi_view& v, int heads, const char* what) {
+  EncodeTiledFn enc = get_encode_fn();
+  MAGI_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  const bool empty = v.tokens <= 0 || v.ptr == nullptr;
+  void* base = empty ? nullptr : const_cast<void*>(v.ptr);
+  cuuint64_t dims[3] = {128, (cuuint64_t)heads, (cuuint64_t)(empty ? 1 : v.tokens)};
+  cuuint64_t strides[2] = {(cuuint64_t)(empty ? 256 : v.head_stride * 2), (cuuint64_t)(empty ? 256 * heads : v.token_stride * 2)};
+  if (empty) return 2;  // never read by the kernel (no tiles are scheduled on it); caller substitutes another map
+  MAGI_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "%s: pointer must be 16-byte aligned", what);
+  MAGI_CHECK(v.head_stride % 8 == 0 && v.token_stride % 8 == 0, "%s: strides must be multiples of 8 elements", what);
+  MAGI_CHECK(v.head_stride >= 128, "%s: head stride < 128", what);
+  cuuint32_t box[3] = {64, 1, 128};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MAGI_CHECK(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled failed (CUresult %d)", what, (int)r);
+  return 0;
+}
+
+int device_sm_count(int* out) {
+  static int cached[64] = {0};
+  int dev = 0;
+  MAGI_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && cached[dev] > 0) { *out = cached[dev]; return 0; }
+  int n = 0;
+  MAGI_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  if (dev < 64) cached[dev] = n;
+  *out = n;
+  return 0;
+}
+
+int grid_for(int64_t work_threads, int threads, int* grid) {
+  int sms = 0;
+  if (int rc = device_sm_count(&sms)) return rc;
+  int64_t blocks = (work_threads + threads - 1) / threads;
+  const int64_t cap = (int64_t)sms * 8;  // 8 resident 256-thread CTAs per SM; grid-stride beyond that
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  *grid = (int)blocks;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* magi_last_error(void) { return g_err; }
+
+const char* magi_build_info(void) {
+  return "magi_attn sm_100a tcgen05/TMEM/TMA; built " __DATE__ " " __TIME__
+#ifdef __CUDACC_VER_MAJOR__
+         "; nvcc "
+#endif
+         ;
+}
+
+uint64_t magi_launch_count(void) { return g_launches.load(); }
+
+size_t magi_attn_workspace_bytes(int32_t n_ranges) {
+  if (n_ranges < 0) n_ranges = 0;
+  return magi::attn_workspace_ints(n_ranges) * sizeof(int);
+}
+
+int magi_attn_fwd(const magi_attn_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MAGI_CHECK(a != nullptr, "args is NULL");
+  MAGI_CHECK(a->head_dim == MAGI_HEAD_DIM, "head_dim must be 128 (got %d)", a->head_dim);
+  MAGI_CHECK(a->num_heads_q > 0 && a->num_heads_kv > 0 && a->num_heads_q % a->num_heads_kv == 0,
+             "num_heads_q (%d) must be a positive multiple of num_heads_kv (%d)", a->num_heads_q, a->num_heads_kv);
+  MAGI_CHECK(a->n_ranges >= 0, "n_ranges < 0");
+  const bool by_ranges = a->q_ranges != nullptr && a->k_ranges != nullptr;
+  const bool by_cu = a->cu_seqlens_q != nullptr && a->cu_seqlens_k != nullptr;
+  MAGI_CHECK(by_ranges != by_cu, "give exactly one of (q_ranges,k_ranges) or (cu_seqlens_q,cu_seqlens_k)");
+  MAGI_CHECK(a->out != nullptr, "out is NULL");
+  MAGI_CHECK((reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && a->out_token_stride % 8 == 0 &&
+                 a->out_head_stride % 8 == 0,
+             "out must be 16-byte aligned with strides that are multiples of 8 elements");
+  MAGI_CHECK(a->q.tokens >= 0 && a->k_a.tokens >= 0 && a->k_b.tokens >= 0, "negative token count");
+  MAGI_CHECK(a->k_a.tokens == a->v_a.tokens && a->k_b.tokens == a->v_b.tokens, "k/v token counts differ");
+  MAGI_CHECK(a->q.tokens < (1ll << 31) && a->k_a.tokens + a->k_b.tokens < (1ll << 31), "token counts exceed int32");
+  if (a->n_ranges == 0 || a->q.tokens == 0) return 0;
+  MAGI_CHECK(a->q.ptr != nullptr, "q is NULL");
+  MAGI_CHECK(a->workspace != nullptr && a->workspace_bytes >= magi_attn_workspace_bytes(a->n_ranges),
+             "workspace too small: need %zu bytes", magi_attn_workspace_bytes(a->n_ranges));
+  MAGI_CHECK((reinterpret_cast<uintptr_t>(a->workspace) & 15) == 0, "workspace must be 16-byte aligned");
+
+  CUtensorMap tm_q, tm_ka, tm_va, tm_kb, tm_vb;
+  int rc = make_view_map(&tm_q, a->q, a->num_heads_q, "q");
+  if (rc) return rc == 2 ? fail("q is empty") : rc;
+  int rka = make_view_map(&tm_ka, a->k_a, a->num_heads_kv, "k_a");
+  if (rka == 1) return 1;
+  int rva = make_view_map(&tm_va, a->v_a, a->num_heads_kv, "v_a");
+  if (rva == 1) return 1;
+  int rkb = make_view_map(&tm_kb, a->k_b, a->num_heads_kv, "k_b");
+  if (rkb == 1) return 1;
+  int rvb = make_view_map(&tm_vb, a->v_b, a->num_heads_kv, "v_b");
+  if (rvb == 1) return 1;
+  MAGI_CHECK(rka == rva && rkb == rvb, "k and v of a segment must both be present or both be empty");
+  // an empty segment is never read by the kernel; give it any valid descriptor
+  if (rka == 2) { tm_ka = rkb == 0 ? tm_kb : tm_q; tm_va = rkb == 0 ? tm_vb : tm_q; }
+  if (rkb == 2) { tm_kb = rka == 0 ? tm_ka : tm_q; tm_vb = rka == 0 ? tm_va : tm_q; }
+
+  const int len_a = rka == 2 ? 0 : (int)a->k_a.tokens;
+  const int len_b = rkb == 2 ? 0 : (int)a->k_b.tokens;
+  int* ws = reinterpret_cast<int*>(a->workspace);
+
+  MAGI_CUDA(magi::attn_setup_launch(a->q_ranges, a->k_ranges, a->cu_seqlens_q, a->cu_seqlens_k, a->n_ranges,
+                                    a->num_heads_q, (int)a->q.tokens, len_a + len_b, ws, stream));
+  g_launches++;
+
+  magi::AttnKernelParams p;
+  p.out = a->out;
+  p.out_token_stride = a->out_token_stride;
+  p.out_head_stride = a->out_head_stride;
+  p.lse = a->lse;
+  p.work = ws;
+  p.Hq = a->num_heads_q;
+  p.Hkv = a->num_heads_kv;
+  p.len_a = len_a;
+  const float scale = a->softmax_scale > 0.f ? a->softmax_scale : 0.08838834764831845f;  // 1/sqrt(128)
+  p.scale_log2 = scale * 1.4426950408889634f;
+
+  int sms = a->num_sms;
+  if (sms <= 0) { if (int r2 = device_sm_count(&sms)) return r2; }
+  const CUtensorMap maps[5] = {tm_q, tm_ka, tm_va, tm_kb, tm_vb};
+  MAGI_CUDA(magi::attn_fwd_launch(maps, p, sms, stream));
+  g_launches++;
+  return 0;
+}
+
+int magi_qk_norm_rope_fwd(const magi_prologue_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MAGI_CHECK(a != nullptr, "args is NULL");
+  MAGI_CHECK(a->rows >= 0, "rows < 0");
+  MAGI_CHECK(a->x_q != nullptr || a->x_k != nullptr || a->x_v != nullptr, "no input tensor");
+  MAGI_CHECK(a->ln_dtype == 0 || a->ln_dtype == 1, "ln_dtype must be 0 (fp32) or 1 (bf16)");
+  MAGI_CHECK(a->batch >= 1, "batch must be >= 1");
+  if (a->x_q) {
+    MAGI_CHECK(a->q_out && a->ln_q_w && a->ln_q_b, "q path needs q_out, ln_q_w, ln_q_b");
+    MAGI_CHECK(a->num_heads_q > 0 && a->xq_row_stride % 8 == 0 && a->q_out_token_stride % 8 == 0 &&
+                   a->q_out_head_stride % 8 == 0,
+               "q strides must be multiples of 8 elements");
+  }
+  if (a->x_k) MAGI_CHECK(a->kv_out && a->ln_k_w && a->ln_k_b, "k path needs kv_out, ln_k_w, ln_k_b");
+  if (a->x_v) MAGI_CHECK(a->kv_out, "v path needs kv_out");
+  if (a->x_k || a->x_v)
+    MAGI_CHECK(a->num_heads_kv > 0 && a->xk_row_stride % 8 == 0 && a->xv_row_stride % 8 == 0 &&
+                   a->kv_out_token_stride % 8 == 0 && a->kv_out_head_stride % 8 == 0,
+               "kv strides must be multiples of 8 elements");
+  if (a->cache)
+    MAGI_CHECK(a->cache_token_stride % 8 == 0 && a->cache_head_stride % 8 == 0 && a->cache_rows >= 0 &&
+                   a->cache_rows <= a->rows && a->cache_row_offset >= 0,
+               "bad cache arguments");
+  const int cp = a->head_perm_cp > 1 ? a->head_perm_cp : 1;
+  if (cp > 1) {
+    MAGI_CHECK(a->cache == nullptr, "cache append is not available together with head_perm_cp (cache holds post-all-to-all heads)");
+    if (a->x_q) MAGI_CHECK(a->num_heads_q % cp == 0, "num_heads_q %% cp != 0");
+    if (a->x_k || a->x_v)
+      MAGI_CHECK(a->num_heads_kv % cp == 0 || cp % a->num_heads_kv == 0, "num_heads_kv and cp are not compatible");
+  }
+  MAGI_CHECK((a->sin == nullptr) == (a->cos == nullptr), "sin and cos must both be given or both be NULL");
+  if (a->rows == 0) return 0;
+
+  magi::PrologueParams p;
+  p.x_q = a->x_q; p.x_k = a->x_k; p.x_v = a->x_v;
+  p.rows = a->rows;
+  p.xq_row_stride = a->xq_row_stride; p.xk_row_stride = a->xk_row_stride; p.xv_row_stride = a->xv_row_stride;
+  p.Hq = a->num_heads_q; p.Hkv = a->num_heads_kv; p.batch = a->batch;
+  p.ln_q_w = a->ln_q_w; p.ln_q_b = a->ln_q_b; p.ln_k_w = a->ln_k_w; p.ln_k_b = a->ln_k_b;
+  p.eps = a->eps; p.zero_centered_gamma = a->zero_centered_gamma;
+  p.sin = a->sin; p.cos = a->cos;
+  p.q_out = a->q_out; p.q_out_token_stride = a->q_out_token_stride; p.q_out_head_stride = a->q_out_head_stride;
+  p.kv_out = a->kv_out; p.kv_out_token_stride = a->kv_out_token_stride; p.kv_out_head_stride = a->kv_out_head_stride;
+  p.cache = a->cache; p.cache_token_stride = a->cache_token_stride; p.cache_head_stride = a->cache_head_stride;
+  p.cache_row_offset = a->cache_row_offset; p.cache_rows = a->cache_rows;
+  p.head_perm_cp = cp;
+
+  const int per_row = (a->x_q ? a->num_heads_q : 0) + (a->x_k ? a->num_heads_kv : 0) + (a->x_v ? a->num_heads_kv : 0);
+  int grid = 1;
+  if (int rc = grid_for(a->rows * per_row * 16, 256, &grid)) return rc;
+  MAGI_CUDA(magi::prologue_launch(p, a->ln_dtype == 1, grid, stream));
+  g_launches++;
+  return 0;
+}
+
+int magi_kv_cache_append(void* cache, int64_t cache_token_stride, const void* kv, int64_t kv_token_stride,
+                         int64_t row_offset, int64_t rows, int64_t row_elems, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MAGI_CHECK(rows >= 0 && row_offset >= 0, "negative rows/offset");
+  if (rows == 0) return 0;
+  MAGI_CHECK(cache && kv, "NULL pointer");
+  MAGI_CHECK(row_elems > 0 && row_elems % 8 == 0 && cache_token_stride % 8 == 0 && kv_token_stride % 8 == 0,
+             "row_elems and strides must be multiples of 8 elements");
+  MAGI_CHECK(((reinterpret_cast<uintptr_t>(cache) | reinterpret_cast<uintptr_t>(kv)) & 15) == 0,
+             "pointers must be 16-byte aligned");
+  int grid = 1;
+  if (int rc = grid_for(rows * (row_elems / 8), 256, &grid)) return rc;
+  MAGI_CUDA(magi::kv_append_launch(cache, cache_token_stride, kv, kv_token_stride, row_offset, rows,
+                                   (int)(row_elems / 8), grid, stream));
+  g_launches++;
+  return 0;
+}
+
+int magi_lse_merge(void* out_a, float* lse_a, const void* out_b, const float* lse_b, int64_t rows, int32_t heads,
+                   int64_t a_ts, int64_t a_hs, int64_t b_ts, int64_t b_hs, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MAGI_CHECK(rows >= 0 && heads > 0, "bad shape");
+  if (rows == 0) return 0;
+  MAGI_CHECK(out_a && lse_a && out_b && lse_b, "NULL pointer");
+  MAGI_CHECK(a_ts % 8 == 0 && a_hs % 8 == 0 && b_ts % 8 == 0 && b_hs % 8 == 0,
+             "strides must be multiples of 8 elements");
+  int grid = 1;
+  if (int rc = grid_for(rows * heads * 16, 256, &grid)) return rc;
+  MAGI_CUDA(magi::lse_merge_launch(out_a, lse_a, out_b, lse_b, rows, heads, a_ts, a_hs, b_ts, b_hs, grid, stream));
+  g_launches++;
+  return 0;
+}
+
+int magi_ulysses_relayout(void* dst, const void* src, int64_t seq, int32_t heads, int32_t head_elems, int32_t cp,
+                          int32_t kv_repeat, int32_t mode, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MAGI_CHECK(seq >= 0 && heads > 0 && cp >= 1 && kv_repeat >= 1, "bad shape");
+  MAGI_CHECK(mode == 0 || mode == 1, "mode must be 0 or 1");
+  MAGI_CHECK(head_elems > 0 && head_elems % 8 == 0, "head_elems must be a multiple of 8");
+  if (seq == 0) return 0;
+  MAGI_CHECK(dst && src, "NULL pointer");
+  int hn;
+  if (mode == 0) {
+    MAGI_CHECK((heads * kv_repeat) % cp == 0, "heads * kv_repeat must be divisible by cp");
+    hn = heads * kv_repeat / cp;
+  } else {
+    MAGI_CHECK(kv_repeat == 1, "kv_repeat only applies to mode 0");
+    hn = heads;  // per-rank heads
+  }
+  int grid = 1;
+  if (int rc = grid_for(seq * cp * hn * (head_elems / 8), 256, &grid)) return rc;
+  MAGI_CUDA(magi::ulysses_relayout_launch(dst, src, seq, hn, head_elems / 8, cp, kv_repeat, mode, grid, stream));
+  g_launches++;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,482 @@
+// Range-masked (chunk-causal) attention forward for sm_100a: tcgen05.mma with accumulators in TMEM,
+// TMA-staged Q/K/V tiles, register online softmax, block-sparse skipping of masked chunk tiles by construction
+// (only the (q-range x k-range) rectangles are ever enumerated), two-segment K/V source (KV cache ++ new tokens).
+//
+// Reference semantics being replaced (samiazirar/MAGI-1):
+//   core_attention / full_attention / cross_attention, inference/model/dit/dit_module.py:1023-1136
+//   _full_adjust_key_and_value's torch.cat + chunk().contiguous(), dit_module.py:914-946
+//
+// CTA = 384 threads, persistent (one per SM), one work item = 256 query rows x 1 query head x one range:
+//   warps 0-3   softmax warpgroup 0 : rows [0,128)   of the item, owns S0/P0/O0 in TMEM
+//   warps 4-7   softmax warpgroup 1 : rows [128,256) of the item, owns S1/P1/O1 in TMEM
+//   warp  8     tcgen05.mma issuer (one lane) + TMEM allocator
+//   warp  9     TMA producer (one lane)
+//   warps 10-11 idle (keep warpgroup granularity)
+// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P_t (bf16) aliases the first 64 columns of S_t.
+// One thread owns one query row (tcgen05.ld 32x32b), so row max / row sum need no cross-thread reduction.
+#include <math.h>
+#include <stdio.h>
+
+#include "attn_fwd.cuh"
+#include "common.cuh"
+
+namespace magi {
+
+namespace {
+
+constexpr int kTileM = 128;               // query rows per softmax warpgroup
+constexpr int kPairM = 2 * kTileM;        // query rows per work item
+constexpr int kTileN = 128;               // keys per K/V tile
+constexpr int kStages = 4;                // K/V smem ring depth (tiles; K and V alternate)
+constexpr int kBlkBytes = 128 * 64 * 2;   // one 64-column (128 B wide) swizzle block of a 128-row tile
+constexpr int kTileBytes = 2 * kBlkBytes; // 128 x 128 bf16
+constexpr int kThreads = 384;
+constexpr uint32_t kIdescQK = make_idesc_bf16(128, 128, 0, 0);
+constexpr uint32_t kIdescPV = make_idesc_bf16(128, 128, 0, 1);
+constexpr float kRescaleThreshold = 8.0f; // log2 units: lazily rescale O only when the row max grew by > 2^8
+
+struct Barriers {
+  uint64_t q_full, q_empty;
+  uint64_t kv_full[kStages], kv_empty[kStages];
+  uint64_t s_full[2], p_full[2], o_full[2], o_free[2];
+  uint32_t tmem_base;
+};
+
+constexpr int kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct Item {
+  int q_begin, q_end;  // query rows of this item's range
+  int qrow0;           // first query row of the 256-row item
+  int h, hkv;
+  int ka0, ka1;        // key rows in segment A (cache), [ka0, ka1)
+  int kb0, kb1;        // key rows in segment B (new tokens), segment-local
+  int nt_a, nt;        // K/V tiles in segment A, total
+};
+
+__device__ __forceinline__ bool decode_item(const int* __restrict__ ws, int item, int Hq, int group, int len_a,
+                                            Item& it) {
+  const int n = ws[1];
+  const int* prefix = ws + 4;
+  const int* rq0 = prefix + (n + 1);
+  const int* rq1 = rq0 + n;
+  const int* rk0 = rq1 + n;
+  const int* rk1 = rk0 + n;
+  // largest r with prefix[r] <= item
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (prefix[mid] <= item) lo = mid; else hi = mid - 1;
+  }
+  const int r = lo;
+  const int local = item - prefix[r];
+  it.q_begin = rq0[r];
+  it.q_end = rq1[r];
+  const int nqt = (it.q_end - it.q_begin + kPairM - 1) / kPairM;
+  // order inside a range: kv head (outer), q tile, q head within the GQA group (inner) -> neighbours share K/V in L2
+  const int per_kv = nqt * group;
+  it.hkv = local / per_kv;
+  const int rem = local - it.hkv * per_kv;
+  const int qt = rem / group;
+  it.h = it.hkv * group + (rem - qt * group);
+  it.qrow0 = it.q_begin + qt * kPairM;
+  const int k0 = rk0[r], k1 = rk1[r];
+  it.ka0 = min(k0, len_a);
+  it.ka1 = min(k1, len_a);
+  it.kb0 = max(k0, len_a) - len_a;
+  it.kb1 = max(k1, len_a) - len_a;
+  it.nt_a = (it.ka1 - it.ka0 + kTileN - 1) / kTileN;
+  it.nt = it.nt_a + (it.kb1 - it.kb0 + kTileN - 1) / kTileN;
+  return true;
+}
+
+__device__ __forceinline__ void tile_info(const Item& it, int j, int& seg, int& row0, int& nvalid) {
+  if (j < it.nt_a) {
+    seg = 0;
+    row0 = it.ka0 + j * kTileN;
+    nvalid = min(kTileN, it.ka1 - row0);
+  } else {
+    seg = 1;
+    row0 = it.kb0 + (j - it.nt_a) * kTileN;
+    nvalid = min(kTileN, it.kb1 - row0);
+  }
+}
+
+// S[128 x 128] = Q[128 x 128(hd)] * K[128 x 128(hd)]^T ; both operands K-major, 128B-swizzled, two 64-wide blocks.
+__device__ __forceinline__ void issue_qk(uint32_t d_tmem, uint32_t q_addr, uint32_t k_addr) {
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const uint32_t off = (ks >> 2) * kBlkBytes + (ks & 3) * 32;
+    const uint64_t a = make_smem_desc_sw128(q_addr + off, 16, 1024);
+    const uint64_t b = make_smem_desc_sw128(k_addr + off, 16, 1024);
+    mma_ss(d_tmem, a, b, kIdescQK, ks > 0 ? 1u : 0u);
+  }
+}
+
+// O[128 x 128(hd)] (+)= P[128 x 128(keys)] * V[128(keys) x 128(hd)] ; P from TMEM (bf16, 2 per column),
+// V is MN-major (head_dim contiguous): 8-key groups 1024 B apart (SBO), 64-wide hd blocks kBlkBytes apart (LBO).
+__device__ __forceinline__ void issue_pv(uint32_t d_tmem, uint32_t p_tmem, uint32_t v_addr, uint32_t accumulate) {
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const uint64_t b = make_smem_desc_sw128(v_addr + ks * 2048, kBlkBytes, 1024);
+    mma_ts(d_tmem, p_tmem + ks * 8, b, kIdescPV, (accumulate | (ks > 0)) ? 1u : 0u);
+  }
+}
+
+}  // namespace
+
+__global__ void attn_setup_kernel(const int* __restrict__ q_ranges, const int* __restrict__ k_ranges,
+                                  const int* __restrict__ cu_q, const int* __restrict__ cu_k, int n, int Hq,
+                                  int total_q, int total_k, int* __restrict__ ws) {
+  int* prefix = ws + 4;
+  int* rq0 = prefix + (n + 1);
+  int* rq1 = rq0 + n;
+  int* rk0 = rq1 + n;
+  int* rk1 = rk0 + n;
+  auto load = [&](int i, int& q0, int& q1, int& k0, int& k1) {
+    if (q_ranges != nullptr) {
+      q0 = q_ranges[2 * i]; q1 = q_ranges[2 * i + 1];
+      k0 = k_ranges[2 * i]; k1 = k_ranges[2 * i + 1];
+    } else {
+      q0 = cu_q[i]; q1 = cu_q[i + 1];
+      k0 = cu_k[i]; k1 = cu_k[i + 1];
+    }
+    q0 = max(0, min(q0, total_q)); q1 = max(q0, min(q1, total_q));
+    k0 = max(0, min(k0, total_k)); k1 = max(k0, min(k1, total_k));
+  };
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int q0, q1, k0, k1;
+    load(i, q0, q1, k0, k1);
+    const int lk = k1 - k0;
+    int rank = 0;  // longest-key-range first (LPT order for the persistent CTAs)
+    for (int j = 0; j < n; ++j) {
+      int a0, a1, b0, b1;
+      load(j, a0, a1, b0, b1);
+      const int lj = b1 - b0;
+      rank += (lj > lk) || (lj == lk && j < i);
+    }
+    rq0[rank] = q0; rq1[rank] = q1; rk0[rank] = k0; rk1[rank] = k1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int i = 0; i < n; ++i) {
+      prefix[i] = acc;
+      acc += ((rq1[i] - rq0[i] + kPairM - 1) / kPairM) * Hq;
+    }
+    prefix[n] = acc;
+    ws[0] = acc;
+    ws[1] = n;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_ka,
+                const __grid_constant__ CUtensorMap tm_va, const __grid_constant__ CUtensorMap tm_kb,
+                const __grid_constant__ CUtensorMap tm_vb, const AttnKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_q = smem;                    // 2 tiles
+  uint8_t* smem_kv = smem + 2 * kTileBytes;  // kStages tiles
+  Barriers* bar = reinterpret_cast<Barriers*>(smem + (2 + kStages) * kTileBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int group = p.Hq / p.Hkv;
+  const int* __restrict__ ws = p.work;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar->q_full, 1);
+    mbar_init(&bar->q_empty, 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&bar->kv_full[s], 1);
+      mbar_init(&bar->kv_empty[s], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&bar->s_full[t], 1);
+      mbar_init(&bar->p_full[t], kTileM);
+      mbar_init(&bar->o_full[t], 1);
+      mbar_init(&bar->o_free[t], kTileM);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8) {
+    tmem_alloc(&bar->tmem_base, 512);
+    tmem_relinquish();
+  }
+  if (warp == 9 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_ka);
+    tma_prefetch_desc(&tm_va);
+    tma_prefetch_desc(&tm_kb);
+    tma_prefetch_desc(&tm_vb);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bar->tmem_base;
+  const int total_items = ws[0];
+
+  if (warp < 8) {
+    // ====================================================================== softmax warpgroups
+    const int t = warp >> 2;
+    const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem_base + lane_sel + t * 128;
+    const uint32_t tO = tmem_base + lane_sel + 256 + t * 128;
+    const int row_in_item = t * kTileM + (warp & 3) * 32 + lane;
+    uint32_t s_phase = 0, o_phase = 0;
+    const float scale_log2 = p.scale_log2;
+    __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(p.out);
+
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      Item it;
+      decode_item(ws, item, p.Hq, group, p.len_a, it);
+      const int row = it.qrow0 + row_in_item;
+      const bool row_valid = row < it.q_end;
+      float m = -INFINITY, l = 0.f;
+
+      for (int j = 0; j < it.nt; ++j) {
+        int seg, krow0, nvalid;
+        tile_info(it, j, seg, krow0, nvalid);
+        mbar_wait(&bar->s_full[t], s_phase);
+        s_phase ^= 1;
+        tc_fence_after();
+
+        uint32_t sr[128];
+        MAGI_TMEM_LD32(tS + 0, sr, 0);
+        MAGI_TMEM_LD32(tS + 32, sr, 32);
+        MAGI_TMEM_LD32(tS + 64, sr, 64);
+        MAGI_TMEM_LD32(tS + 96, sr, 96);
+        tmem_wait_ld();
+
+        if (nvalid < kTileN) {
+#pragma unroll
+          for (int c = 0; c < 128; ++c)
+            if (c >= nvalid) sr[c] = 0xff800000u;  // -inf
+        }
+        float mx0 = __uint_as_float(sr[0]), mx1 = __uint_as_float(sr[1]);
+        float mx2 = __uint_as_float(sr[2]), mx3 = __uint_as_float(sr[3]);
+#pragma unroll
+        for (int c = 4; c < 128; c += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(sr[c + 0]));
+          mx1 = fmaxf(mx1, __uint_as_float(sr[c + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(sr[c + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(sr[c + 3]));
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+
+        bool need = false;
+        float alpha = 1.f;
+        if (j == 0) {
+          m = mx;
+        } else if ((mx - m) * scale_log2 > kRescaleThreshold) {
+          need = true;
+          alpha = ex2_approx((m - mx) * scale_log2);
+          m = mx;
+        }
+        const float neg_m = -m * scale_log2;
+
+        float sum0 = 0.f, sum1 = 0.f;
+        uint32_t pr[64];
+#pragma unroll
+        for (int c = 0; c < 128; c += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c]), scale_log2, neg_m));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sr[c + 1]), scale_log2, neg_m));
+          sum0 += p0;
+          sum1 += p1;
+          pr[c >> 1] = pack_bf16x2(p0, p1);
+        }
+        l = l * alpha + (sum0 + sum1);
+
+        MAGI_TMEM_ST32(tS + 0, pr, 0);
+        MAGI_TMEM_ST32(tS + 32, pr, 32);
+
+        if (__any_sync(0xffffffffu, need)) {
+          // rare: this row's running max jumped by more than 2^8 -> bring O back into range before P*V accumulates
+#pragma unroll 1
+          for (int c = 0; c < 128; c += 32) {
+            uint32_t orr[32];
+            MAGI_TMEM_LD32(tO + c, orr, 0);
+            tmem_wait_ld();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) orr[k] = __float_as_uint(__uint_as_float(orr[k]) * alpha);
+            MAGI_TMEM_ST32(tO + c, orr, 0);
+          }
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&bar->p_full[t]);
+      }
+
+      // ------------------------------------------------------------------ epilogue for this row
+      __nv_bfloat16* orow = out + static_cast<int64_t>(row) * p.out_token_stride +
+                            static_cast<int64_t>(it.h) * p.out_head_stride;
+      if (it.nt > 0) {
+        mbar_wait(&bar->o_full[t], o_phase);
+        o_phase ^= 1;
+        tc_fence_after();
+        const float inv_l = 1.f / l;
+#pragma unroll 1
+        for (int c = 0; c < 128; c += 32) {
+          uint32_t orr[32];
+          MAGI_TMEM_LD32(tO + c, orr, 0);
+          tmem_wait_ld();
+          if (row_valid) {
+#pragma unroll
+            for (int k = 0; k < 32; k += 8) {
+              uint4 v;
+              v.x = pack_bf16x2(__uint_as_float(orr[k + 0]) * inv_l, __uint_as_float(orr[k + 1]) * inv_l);
+              v.y = pack_bf16x2(__uint_as_float(orr[k + 2]) * inv_l, __uint_as_float(orr[k + 3]) * inv_l);
+              v.z = pack_bf16x2(__uint_as_float(orr[k + 4]) * inv_l, __uint_as_float(orr[k + 5]) * inv_l);
+              v.w = pack_bf16x2(__uint_as_float(orr[k + 6]) * inv_l, __uint_as_float(orr[k + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(orow + c + k) = v;
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&bar->o_free[t]);
+        if (row_valid && p.lse != nullptr)
+          p.lse[static_cast<int64_t>(row) * p.Hq + it.h] = (m * scale_log2 + log2f(l)) * 0.6931471805599453f;
+      } else if (row_valid) {
+        // empty key interval: zeros / -inf (flash-attn convention for seqlen_k == 0)
+#pragma unroll
+        for (int c = 0; c < 128; c += 8) *reinterpret_cast<uint4*>(orow + c) = make_uint4(0, 0, 0, 0);
+        if (p.lse != nullptr) p.lse[static_cast<int64_t>(row) * p.Hq + it.h] = -INFINITY;
+      }
+    }
+  } else if (warp == 8) {
+    // ====================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t tS0 = tmem_base, tS1 = tmem_base + 128, tO0 = tmem_base + 256, tO1 = tmem_base + 384;
+      const uint32_t q0_addr = smem_u32(smem_q), q1_addr = smem_u32(smem_q + kTileBytes);
+      const uint32_t kv_addr = smem_u32(smem_kv);
+      uint32_t stage = 0, phase = 0;  // kv ring (consumer side)
+      uint32_t p_phase0 = 0, p_phase1 = 0;
+      uint32_t item_cnt = 0;
+      auto advance = [&]() {
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      };
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        Item it;
+        decode_item(ws, item, p.Hq, group, p.len_a, it);
+        if (it.nt == 0) continue;
+        const int nt = it.nt;
+        mbar_wait(&bar->q_full, item_cnt & 1);
+        // K_0 -> S0(0), S1(0)
+        mbar_wait(&bar->kv_full[stage], phase);
+        tc_fence_after();
+        uint32_t kst = stage;
+        advance();
+        issue_qk(tS0, q0_addr, kv_addr + kst * kTileBytes);
+        tc_commit(&bar->s_full[0]);
+        issue_qk(tS1, q1_addr, kv_addr + kst * kTileBytes);
+        tc_commit(&bar->s_full[1]);
+        tc_commit(&bar->kv_empty[kst]);
+        if (nt == 1) tc_commit(&bar->q_empty);
+        // V_0 -> O0 = P0(0) V_0
+        mbar_wait(&bar->kv_full[stage], phase);
+        uint32_t vst = stage;
+        advance();
+        mbar_wait(&bar->o_free[0], (item_cnt & 1) ^ 1);
+        mbar_wait(&bar->p_full[0], p_phase0);
+        p_phase0 ^= 1;
+        tc_fence_after();
+        issue_pv(tO0, tS0, kv_addr + vst * kTileBytes, 0);
+        for (int i = 1; i < nt; ++i) {
+          // K_i -> S0(i)   (P0(i-1) already consumed by the in-order PV0(i-1))
+          mbar_wait(&bar->kv_full[stage], phase);
+          tc_fence_after();
+          kst = stage;
+          advance();
+          issue_qk(tS0, q0_addr, kv_addr + kst * kTileBytes);
+          tc_commit(&bar->s_full[0]);
+          // O1 (+)= P1(i-1) V_{i-1}
+          if (i == 1) mbar_wait(&bar->o_free[1], (item_cnt & 1) ^ 1);
+          mbar_wait(&bar->p_full[1], p_phase1);
+          p_phase1 ^= 1;
+          tc_fence_after();
+          issue_pv(tO1, tS1, kv_addr + vst * kTileBytes, i > 1 ? 1u : 0u);
+          tc_commit(&bar->kv_empty[vst]);
+          // S1(i)
+          issue_qk(tS1, q1_addr, kv_addr + kst * kTileBytes);
+          tc_commit(&bar->s_full[1]);
+          tc_commit(&bar->kv_empty[kst]);
+          if (i == nt - 1) tc_commit(&bar->q_empty);
+          // V_i -> O0 += P0(i) V_i
+          mbar_wait(&bar->kv_full[stage], phase);
+          vst = stage;
+          advance();
+          mbar_wait(&bar->p_full[0], p_phase0);
+          p_phase0 ^= 1;
+          tc_fence_after();
+          issue_pv(tO0, tS0, kv_addr + vst * kTileBytes, 1);
+        }
+        tc_commit(&bar->o_full[0]);
+        // O1 (+)= P1(nt-1) V_{nt-1}
+        if (nt == 1) mbar_wait(&bar->o_free[1], (item_cnt & 1) ^ 1);
+        mbar_wait(&bar->p_full[1], p_phase1);
+        p_phase1 ^= 1;
+        tc_fence_after();
+        issue_pv(tO1, tS1, kv_addr + vst * kTileBytes, nt > 1 ? 1u : 0u);
+        tc_commit(&bar->kv_empty[vst]);
+        tc_commit(&bar->o_full[1]);
+        ++item_cnt;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ====================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;  // kv ring (producer side)
+      uint32_t item_cnt = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        Item it;
+        decode_item(ws, item, p.Hq, group, p.len_a, it);
+        if (it.nt == 0) continue;
+        mbar_wait(&bar->q_empty, (item_cnt & 1) ^ 1);
+        mbar_expect_tx(&bar->q_full, 2 * kTileBytes);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          tma_load_3d(smem_q + t * kTileBytes, &tm_q, &bar->q_full, 0, it.h, it.qrow0 + t * kTileM);
+          tma_load_3d(smem_q + t * kTileBytes + kBlkBytes, &tm_q, &bar->q_full, 64, it.h, it.qrow0 + t * kTileM);
+        }
+        for (int j = 0; j < it.nt; ++j) {
+          int seg, krow0, nvalid;
+          tile_info(it, j, seg, krow0, nvalid);
+          const CUtensorMap* mk = seg == 0 ? &tm_ka : &tm_kb;
+          const CUtensorMap* mv = seg == 0 ? &tm_va : &tm_vb;
+#pragma unroll
+          for (int kv = 0; kv < 2; ++kv) {
+            const CUtensorMap* mm = kv == 0 ? mk : mv;
+            mbar_wait(&bar->kv_empty[stage], phase ^ 1);
+            mbar_expect_tx(&bar->kv_full[stage], kTileBytes);
+            uint8_t* dst = smem_kv + stage * kTileBytes;
+            tma_load_3d(dst, mm, &bar->kv_full[stage], 0, it.hkv, krow0);
+            tma_load_3d(dst + kBlkBytes, mm, &bar->kv_full[stage], 64, it.hkv, krow0);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+        ++item_cnt;
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+cudaError_t attn_setup_launch(const int* q_ranges, const int* k_ranges, const int* cu_q, const int* cu_k, int n,
+                              int Hq, int total_q, int total_k, int* ws, cudaStream_t stream) {
+  attn_setup_kernel<<<1, 128, 0, stream>>>(q_ranges, k_ranges, cu_q, cu_k, n, Hq, total_q, total_k, ws);
+  return cudaGetLastError();
+}
+
+cudaError_t attn_fwd_launch(const CUtensorMap* maps, const AttnKernelParams& p, int num_ctas, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e != cudaSuccess) return e;
+  attn_fwd_kernel<<<num_ctas, kThreads, kSmemBytes, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  return cudaGetLastError();
+}
+
+}  // namespace magi

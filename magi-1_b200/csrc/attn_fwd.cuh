@@ -1,0 +1,28 @@
+// Kernel-side parameter block and host launchers of the range-masked attention kernel (see attn_fwd.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace magi {
+
+struct AttnKernelParams {
+  void* out;
+  int64_t out_token_stride, out_head_stride;  // elements
+  float* lse;                                 // (total_q, Hq) or nullptr
+  const int* work;                            // produced by the setup kernel
+  int Hq, Hkv;
+  int len_a;                                  // rows of K/V segment A (KV-cache prefix)
+  float scale_log2;                           // softmax_scale * log2(e)
+};
+
+// workspace ints: [total_items, n, 0, 0][prefix n+1][q0 n][q1 n][k0 n][k1 n]
+inline size_t attn_workspace_ints(int n) { return 4 + (size_t)(n + 1) + 4 * (size_t)n; }
+
+// Builds the LPT-ordered work list on the device from (q_ranges,k_ranges) or (cu_q,cu_k); no host sync.
+cudaError_t attn_setup_launch(const int* q_ranges, const int* k_ranges, const int* cu_q, const int* cu_k, int n,
+                              int Hq, int total_q, int total_k, int* ws, cudaStream_t stream);
+// maps: {q, k_a, v_a, k_b, v_b}
+cudaError_t attn_fwd_launch(const CUtensorMap* maps, const AttnKernelParams& p, int num_ctas, cudaStream_t stream);
+
+}  // namespace magi

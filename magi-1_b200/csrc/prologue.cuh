@@ -1,0 +1,32 @@
+// Kernel-side parameter block of the fused prologue and declarations of the memory-bound helper kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace magi {
+
+struct PrologueParams {
+  const void* x_q; const void* x_k; const void* x_v;
+  int64_t rows;
+  int64_t xq_row_stride, xk_row_stride, xv_row_stride;
+  int Hq, Hkv, batch;
+  const void* ln_q_w; const void* ln_q_b; const void* ln_k_w; const void* ln_k_b;
+  float eps;
+  int zero_centered_gamma;
+  const float* sin; const float* cos;
+  void* q_out; int64_t q_out_token_stride, q_out_head_stride;
+  void* kv_out; int64_t kv_out_token_stride, kv_out_head_stride;
+  void* cache; int64_t cache_token_stride, cache_head_stride, cache_row_offset, cache_rows;
+  int head_perm_cp;
+};
+
+cudaError_t prologue_launch(const PrologueParams& p, bool ln_bf16, int grid, cudaStream_t stream);
+cudaError_t kv_append_launch(void* cache, int64_t cache_stride, const void* kv, int64_t kv_stride, int64_t row_offset,
+                             int64_t rows, int row_vecs, int grid, cudaStream_t stream);
+cudaError_t lse_merge_launch(void* out_a, float* lse_a, const void* out_b, const float* lse_b, int64_t rows, int heads,
+                             int64_t a_ts, int64_t a_hs, int64_t b_ts, int64_t b_hs, int grid, cudaStream_t stream);
+cudaError_t ulysses_relayout_launch(void* dst, const void* src, int64_t seq, int hn, int head_vecs, int cp, int rep,
+                                    int mode, int grid, cudaStream_t stream);
+
+}  // namespace magi

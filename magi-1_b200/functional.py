@@ -1,0 +1,387 @@
+"""Drop-in attention functions with the call signatures the reference uses inside
+inference/model/dit/dit_module.py, backed by libmagi_attn.so (hand-written sm_100a kernels) through ctypes.
+
+    flex_flash_attn_func    <- magi_attention.functional.flex_flash_attn_func   (dit_module.py:1032, 1074, 1111)
+    flash_attn_func         <- flash_attn.flash_attn_func                       (dit_module.py:1062, 1090)
+    flash_attn_varlen_func  <- flash_attn.flash_attn_varlen_func                (dit_module.py:1124)
+    attn_ranges             two-segment (KV cache ++ new tokens) form of the same kernel: what
+                            _full_adjust_key_and_value + core_attention compute without the torch.cat / chunk copies
+                            (dit_module.py:914-946, 1023-1066)
+    qk_norm_rope            get_q / get_k / get_v / get_kv / get_xqkv fused      (dit_module.py:953-1021)
+    kv_cache_append, lse_merge, ulysses_relayout : helpers around the context-parallel exchange
+
+No CPU fallback: every function requires CUDA tensors and the built extension.
+"""
+import ctypes as C
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import MagiAttnArgs, MagiPrologueArgs, MagiView
+
+HEAD_DIM = 128
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_thd(x: torch.Tensor, name: str) -> None:
+    if not x.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (this package has no CPU path)")
+    if x.dtype != torch.bfloat16:
+        raise ValueError(f"{name} must be bfloat16, got {x.dtype}")
+    if x.dim() != 3 or x.shape[-1] != HEAD_DIM:
+        raise ValueError(f"{name} must have shape (tokens, heads, 128), got {tuple(x.shape)}")
+    if x.shape[0] > 0 and x.stride(-1) != 1:
+        raise ValueError(f"{name} must be contiguous in the last dimension")
+
+
+def _view(x: Optional[torch.Tensor]) -> MagiView:
+    if x is None or x.shape[0] == 0:
+        return MagiView(None, 0, 0, 0)
+    return MagiView(x.data_ptr(), x.shape[0], x.stride(0), x.stride(1))
+
+
+def _ranges_arg(r: torch.Tensor, name: str) -> torch.Tensor:
+    if not r.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor")
+    if r.dtype != torch.int32:
+        r = r.to(torch.int32)
+    return r.contiguous()
+
+
+def attn_ranges(
+    q: torch.Tensor,
+    k_new: Optional[torch.Tensor],
+    v_new: Optional[torch.Tensor],
+    q_ranges: Optional[torch.Tensor] = None,
+    k_ranges: Optional[torch.Tensor] = None,
+    k_cache: Optional[torch.Tensor] = None,
+    v_cache: Optional[torch.Tensor] = None,
+    cu_seqlens_q: Optional[torch.Tensor] = None,
+    cu_seqlens_k: Optional[torch.Tensor] = None,
+    softmax_scale: Optional[float] = None,
+    out: Optional[torch.Tensor] = None,
+    return_lse: bool = True,
+    zero_fill: bool = False,
+    num_sms: int = 0,
+) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Range-masked attention over keys = concat(k_cache, k_new) without materialising the concatenation.
+
+    q (Tq, Hq, 128), k_*/v_* (T*, Hkv, 128) bf16 views (any token/head strides that are multiples of 8: the packed
+    `(T, Hkv, 256)` KV tensor of the reference is passed as `kv[..., :128]`, `kv[..., 128:]`).
+    Ranges are int32 CUDA tensors of shape (n, 2) in the coordinate system of the concatenation
+    (dit_module.py:914-931), or cu_seqlens of n+1 entries. Returns (out (Tq, Hq, 128) bf16, lse (Tq, Hq) fp32).
+    """
+    _check_thd(q, "q")
+    Hq = q.shape[1]
+    segs = []
+    for k_, v_, nm in ((k_cache, v_cache, "cache"), (k_new, v_new, "new")):
+        if (k_ is None) != (v_ is None):
+            raise ValueError(f"k_{nm} and v_{nm} must both be given or both be None")
+        if k_ is not None:
+            _check_thd(k_, f"k_{nm}")
+            _check_thd(v_, f"v_{nm}")
+            if k_.shape != v_.shape:
+                raise ValueError(f"k_{nm} and v_{nm} shapes differ")
+        segs.append((k_, v_))
+    ref = segs[1][0] if segs[1][0] is not None else segs[0][0]
+    if ref is None:
+        raise ValueError("no keys given")
+    Hkv = ref.shape[1]
+    for k_, _ in segs:
+        if k_ is not None and k_.shape[1] != Hkv:
+            raise ValueError("cache and new keys have different head counts")
+    if Hq % Hkv != 0:
+        raise ValueError(f"num_heads_q ({Hq}) must be a multiple of num_heads_kv ({Hkv})")
+    by_ranges = q_ranges is not None and k_ranges is not None
+    by_cu = cu_seqlens_q is not None and cu_seqlens_k is not None
+    if by_ranges == by_cu:
+        raise ValueError("give exactly one of (q_ranges, k_ranges) or (cu_seqlens_q, cu_seqlens_k)")
+    if by_ranges:
+        q_ranges = _ranges_arg(q_ranges, "q_ranges")
+        k_ranges = _ranges_arg(k_ranges, "k_ranges")
+        if q_ranges.shape != k_ranges.shape or q_ranges.dim() != 2 or q_ranges.shape[1] != 2:
+            raise ValueError("q_ranges and k_ranges must both have shape (n, 2)")
+        n = q_ranges.shape[0]
+    else:
+        cu_seqlens_q = _ranges_arg(cu_seqlens_q, "cu_seqlens_q")
+        cu_seqlens_k = _ranges_arg(cu_seqlens_k, "cu_seqlens_k")
+        if cu_seqlens_q.shape != cu_seqlens_k.shape or cu_seqlens_q.dim() != 1:
+            raise ValueError("cu_seqlens_q and cu_seqlens_k must be 1-D and of equal length")
+        n = cu_seqlens_q.shape[0] - 1
+
+    Tq = q.shape[0]
+    if out is None:
+        out = (torch.zeros if zero_fill else torch.empty)((Tq, Hq, HEAD_DIM), dtype=torch.bfloat16, device=q.device)
+    else:
+        _check_thd(out, "out")
+        if out.shape != q.shape:
+            raise ValueError("out must have the shape of q")
+    lse = None
+    if return_lse:
+        lse = torch.full((Tq, Hq), float("-inf"), dtype=torch.float32, device=q.device) if zero_fill else torch.empty(
+            (Tq, Hq), dtype=torch.float32, device=q.device)
+    if n <= 0 or Tq == 0:
+        return out, lse
+
+    L = _lib.lib()
+    ws_bytes = L.magi_attn_workspace_bytes(n)
+    ws = torch.empty((ws_bytes + 3) // 4, dtype=torch.int32, device=q.device)
+    a = MagiAttnArgs()
+    a.q = _view(q)
+    a.k_a, a.v_a = _view(segs[0][0]), _view(segs[0][1])
+    a.k_b, a.v_b = _view(segs[1][0]), _view(segs[1][1])
+    a.out = out.data_ptr()
+    a.out_token_stride, a.out_head_stride = out.stride(0), out.stride(1)
+    a.lse = lse.data_ptr() if lse is not None else None
+    a.q_ranges = q_ranges.data_ptr() if by_ranges else None
+    a.k_ranges = k_ranges.data_ptr() if by_ranges else None
+    a.cu_seqlens_q = cu_seqlens_q.data_ptr() if by_cu else None
+    a.cu_seqlens_k = cu_seqlens_k.data_ptr() if by_cu else None
+    a.n_ranges = n
+    a.num_heads_q, a.num_heads_kv, a.head_dim = Hq, Hkv, HEAD_DIM
+    a.softmax_scale = float(softmax_scale) if softmax_scale is not None else -1.0
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 4
+    a.num_sms = num_sms
+    with torch.cuda.device(q.device):
+        _lib.check(L.magi_attn_fwd(C.byref(a), _stream()), "magi_attn_fwd")
+    return out, lse
+
+
+def flex_flash_attn_func(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    q_ranges: torch.Tensor,
+    k_ranges: torch.Tensor,
+    max_seqlen_q: Optional[int] = None,
+    max_seqlen_k: Optional[int] = None,
+    softmax_scale: Optional[float] = None,
+    deterministic: bool = False,
+    disable_fwd_atomic_reduction: bool = True,
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Same call as MagiAttention's `flex_flash_attn_func` at dit_module.py:1032-1043.
+
+    Query ranges must be disjoint (the only mode the reference uses: disable_fwd_atomic_reduction=True); the kernel is
+    deterministic by construction (no atomics, fixed summation order), so `deterministic` is accepted and ignored.
+    Rows covered by no range come back as zeros with lse = -inf.
+    """
+    if not disable_fwd_atomic_reduction:
+        raise ValueError("overlapping q_ranges (disable_fwd_atomic_reduction=False) are not supported")
+    out, lse = attn_ranges(q, k, v, q_ranges, k_ranges, softmax_scale=softmax_scale, zero_fill=True)
+    return out, lse
+
+
+def flash_attn_func(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    dropout_p: float = 0.0,
+    softmax_scale: Optional[float] = None,
+    causal: bool = False,
+    deterministic: bool = False,
+) -> torch.Tensor:
+    """Same call as `flash_attn.flash_attn_func` at dit_module.py:1062/1090: (b, s, h, 128) dense, non-causal, GQA."""
+    if dropout_p != 0.0 or causal:
+        raise ValueError("only dropout_p=0, causal=False are supported (what the reference uses)")
+    if q.dim() != 4:
+        raise ValueError("q must be (batch, seqlen, heads, 128)")
+    b, sq = q.shape[0], q.shape[1]
+    sk = k.shape[1]
+    qf = q.reshape(b * sq, q.shape[2], q.shape[3])
+    kf = k.reshape(b * sk, k.shape[2], k.shape[3])
+    vf = v.reshape(b * sk, v.shape[2], v.shape[3])
+    cu_q = torch.arange(0, (b + 1) * sq, sq, dtype=torch.int32, device=q.device) if sq > 0 else torch.zeros(
+        b + 1, dtype=torch.int32, device=q.device)
+    cu_k = torch.arange(0, (b + 1) * sk, sk, dtype=torch.int32, device=q.device) if sk > 0 else torch.zeros(
+        b + 1, dtype=torch.int32, device=q.device)
+    out, _ = attn_ranges(qf, kf, vf, cu_seqlens_q=cu_q, cu_seqlens_k=cu_k, softmax_scale=softmax_scale,
+                         return_lse=False)
+    return out.view(b, sq, q.shape[2], q.shape[3])
+
+
+def flash_attn_varlen_func(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    cu_seqlens_q: torch.Tensor,
+    cu_seqlens_k: torch.Tensor,
+    max_seqlen_q: Optional[int] = None,
+    max_seqlen_k: Optional[int] = None,
+    dropout_p: float = 0.0,
+    softmax_scale: Optional[float] = None,
+    causal: bool = False,
+    deterministic: bool = False,
+) -> torch.Tensor:
+    """Same call as `flash_attn.flash_attn_varlen_func` at dit_module.py:1124-1133 (cross-attention)."""
+    if dropout_p != 0.0 or causal:
+        raise ValueError("only dropout_p=0, causal=False are supported (what the reference uses)")
+    out, _ = attn_ranges(q, k, v, cu_seqlens_q=cu_seqlens_q, cu_seqlens_k=cu_seqlens_k, softmax_scale=softmax_scale,
+                         return_lse=False, zero_fill=True)
+    return out
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return t.data_ptr() if t is not None else None
+
+
+def qk_norm_rope(
+    x_q: Optional[torch.Tensor],
+    x_k: Optional[torch.Tensor],
+    x_v: Optional[torch.Tensor],
+    num_heads_q: int,
+    num_heads_kv: int,
+    ln_q: Optional[Tuple[torch.Tensor, torch.Tensor]],
+    ln_k: Optional[Tuple[torch.Tensor, torch.Tensor]],
+    sin: Optional[torch.Tensor],
+    cos: Optional[torch.Tensor],
+    batch: int = 1,
+    eps: float = 1e-6,
+    zero_centered_gamma: bool = True,
+    q_out: Optional[torch.Tensor] = None,
+    kv_out: Optional[torch.Tensor] = None,
+    cache: Optional[torch.Tensor] = None,
+    cache_row_offset: int = 0,
+    cache_rows: int = 0,
+    head_perm_cp: int = 1,
+) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """Fused per-head LayerNorm(w+1, b) -> NeoX RoPE on 96 of 128 dims -> bf16, writing q in attention layout and
+    [K|V] packed (rows, Hkv, 256), optionally also appending to the KV cache (dit_module.py:953-996, 918-929).
+
+    x_* are the projection outputs (rows, H*128) bf16 (rows = "(sq b)" flattened; any row stride that is a multiple
+    of 8). ln_* = (weight, bias), both fp32 (self-attention, dit_model.py:621-633) or both bf16 (cross-attention).
+    sin/cos: (rows // batch, 48) fp32, or None to skip RoPE (dit_module.py:1005-1021).
+    With head_perm_cp = cp > 1 the outputs are laid out "(cp seq) hn hd", i.e. ready to be the all-to-all send buffer
+    (context_parallel.py:393-396), including KV-head replication when cp > Hkv.
+    """
+    ref = next(t for t in (x_q, x_k, x_v) if t is not None)
+    dev = ref.device
+    rows = ref.shape[0]
+    for t, nm, H in ((x_q, "x_q", num_heads_q), (x_k, "x_k", num_heads_kv), (x_v, "x_v", num_heads_kv)):
+        if t is None:
+            continue
+        if not t.is_cuda or t.dtype != torch.bfloat16:
+            raise ValueError(f"{nm} must be a CUDA bfloat16 tensor")
+        if t.dim() != 2 or t.shape[0] != rows or t.shape[1] != H * HEAD_DIM or t.stride(1) != 1:
+            raise ValueError(f"{nm} must be (rows, {H}*128) with a contiguous last dim, got {tuple(t.shape)}")
+    cp = max(1, head_perm_cp)
+    ln_dtype = None
+    for ln, nm in ((ln_q, "ln_q"), (ln_k, "ln_k")):
+        if ln is None:
+            continue
+        w, b = ln
+        if w.dtype != b.dtype or w.dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError(f"{nm} weight/bias must both be fp32 or both bf16")
+        if ln_dtype is not None and ln_dtype != w.dtype:
+            raise ValueError("ln_q and ln_k must have the same dtype")
+        ln_dtype = w.dtype
+        if w.numel() != HEAD_DIM or b.numel() != HEAD_DIM or not w.is_contiguous() or not b.is_contiguous():
+            raise ValueError(f"{nm} weight/bias must be contiguous with 128 elements")
+    if (sin is None) != (cos is None):
+        raise ValueError("sin and cos must both be given or both be None")
+    if sin is not None:
+        if sin.dtype != torch.float32 or cos.dtype != torch.float32:
+            raise ValueError("sin/cos must be fp32")
+        if rows % batch != 0 or sin.shape != (rows // batch, 48) or cos.shape != sin.shape:
+            raise ValueError(f"sin/cos must have shape ({rows // max(batch, 1)}, 48), got {tuple(sin.shape)}")
+        sin, cos = sin.contiguous(), cos.contiguous()
+
+    if x_q is not None and q_out is None:
+        q_out = torch.empty((rows * cp, num_heads_q // cp, HEAD_DIM), dtype=torch.bfloat16, device=dev)
+    if (x_k is not None or x_v is not None) and kv_out is None:
+        hn_kv = max(1, num_heads_kv // cp) if cp > 1 else num_heads_kv
+        kv_out = torch.empty((rows * cp, hn_kv, 2 * HEAD_DIM), dtype=torch.bfloat16, device=dev)
+
+    a = MagiPrologueArgs()
+    a.x_q, a.x_k, a.x_v = _ptr(x_q), _ptr(x_k), _ptr(x_v)
+    a.rows = rows
+    a.xq_row_stride = x_q.stride(0) if x_q is not None else 0
+    a.xk_row_stride = x_k.stride(0) if x_k is not None else 0
+    a.xv_row_stride = x_v.stride(0) if x_v is not None else 0
+    a.num_heads_q, a.num_heads_kv, a.batch = num_heads_q, num_heads_kv, batch
+    a.ln_q_w, a.ln_q_b = (_ptr(ln_q[0]), _ptr(ln_q[1])) if ln_q is not None else (None, None)
+    a.ln_k_w, a.ln_k_b = (_ptr(ln_k[0]), _ptr(ln_k[1])) if ln_k is not None else (None, None)
+    a.ln_dtype = 1 if ln_dtype == torch.bfloat16 else 0
+    a.eps = eps
+    a.zero_centered_gamma = 1 if zero_centered_gamma else 0
+    a.sin, a.cos = _ptr(sin), _ptr(cos)
+    if q_out is not None:
+        a.q_out = q_out.data_ptr()
+        a.q_out_token_stride, a.q_out_head_stride = q_out.stride(0), q_out.stride(1)
+    if kv_out is not None:
+        a.kv_out = kv_out.data_ptr()
+        a.kv_out_token_stride, a.kv_out_head_stride = kv_out.stride(0), kv_out.stride(1)
+    if cache is not None and cache_rows > 0:
+        if cache.dtype != torch.bfloat16 or cache.dim() != 3 or cache.shape[2] != 2 * HEAD_DIM or cache.stride(2) != 1:
+            raise ValueError("cache must be (max_tokens, Hkv, 256) bf16")
+        if cache_row_offset + cache_rows > cache.shape[0]:
+            raise ValueError("KV-cache append out of bounds")  # dit_module.py:927
+        a.cache = cache.data_ptr()
+        a.cache_token_stride, a.cache_head_stride = cache.stride(0), cache.stride(1)
+        a.cache_row_offset, a.cache_rows = cache_row_offset, cache_rows
+    a.head_perm_cp = cp
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().magi_qk_norm_rope_fwd(C.byref(a), _stream()), "magi_qk_norm_rope_fwd")
+    return q_out, kv_out
+
+
+def kv_cache_append(cache: torch.Tensor, kv: torch.Tensor, row_offset: int, rows: Optional[int] = None) -> None:
+    """cache[row_offset : row_offset + rows] = kv[:rows] for packed (tokens, Hkv, 256) bf16 tensors
+    (dit_module.py:929, used when the new KV comes out of the Ulysses all-to-all)."""
+    rows = kv.shape[0] if rows is None else rows
+    if rows == 0:
+        return
+    if cache.dtype != torch.bfloat16 or kv.dtype != torch.bfloat16 or not cache.is_cuda or not kv.is_cuda:
+        raise ValueError("cache and kv must be CUDA bfloat16 tensors")
+    if cache.shape[1:] != kv.shape[1:] or not kv[0].is_contiguous() or not cache[0].is_contiguous():
+        raise ValueError("cache and kv rows must have the same contiguous shape")
+    if row_offset + rows > cache.shape[0]:
+        raise ValueError("KV-cache append out of bounds")
+    row_elems = kv[0].numel()
+    with torch.cuda.device(cache.device):
+        _lib.check(_lib.lib().magi_kv_cache_append(cache.data_ptr(), cache.stride(0), kv.data_ptr(), kv.stride(0),
+                                                   row_offset, rows, row_elems, _stream()), "magi_kv_cache_append")
+
+
+def lse_merge(out_a: torch.Tensor, lse_a: torch.Tensor, out_b: torch.Tensor, lse_b: torch.Tensor) -> None:
+    """In place: (out_a, lse_a) <- softmax-merge of two partial attention results over disjoint key sets."""
+    _check_thd(out_a, "out_a")
+    _check_thd(out_b, "out_b")
+    if out_a.shape != out_b.shape or lse_a.shape != out_a.shape[:2] or lse_b.shape != lse_a.shape:
+        raise ValueError("shape mismatch")
+    if lse_a.dtype != torch.float32 or lse_b.dtype != torch.float32 or not lse_a.is_contiguous() or not lse_b.is_contiguous():
+        raise ValueError("lse tensors must be contiguous fp32")
+    with torch.cuda.device(out_a.device):
+        _lib.check(_lib.lib().magi_lse_merge(out_a.data_ptr(), lse_a.data_ptr(), out_b.data_ptr(), lse_b.data_ptr(),
+                                             out_a.shape[0], out_a.shape[1], out_a.stride(0), out_a.stride(1),
+                                             out_b.stride(0), out_b.stride(1), _stream()), "magi_lse_merge")
+
+
+def ulysses_relayout(src: torch.Tensor, cp: int, mode: int, kv_repeat: int = 1,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """mode 0: "seq (cp hn) hd -> (cp seq) hn hd" (with optional head replication); mode 1: the inverse
+    "(cp seq) hn hd -> seq (cp hn) hd" (context_parallel.py:393-396, 596)."""
+    if not src.is_cuda or src.dtype != torch.bfloat16 or src.dim() != 3 or not src.is_contiguous():
+        raise ValueError("src must be a contiguous CUDA bfloat16 tensor (tokens, heads, head_elems)")
+    T, H, E = src.shape
+    if mode == 0:
+        hn = H * kv_repeat // cp
+        shape = (T * cp, hn, E)
+        seq, heads = T, H
+    else:
+        if T % cp != 0:
+            raise ValueError("token count must be divisible by cp")
+        shape = (T // cp, H * cp, E)
+        seq, heads = T // cp, H
+    if out is None:
+        out = torch.empty(shape, dtype=src.dtype, device=src.device)
+    elif tuple(out.shape) != shape or not out.is_contiguous():
+        raise ValueError(f"out must be contiguous with shape {shape}")
+    with torch.cuda.device(src.device):
+        _lib.check(_lib.lib().magi_ulysses_relayout(out.data_ptr(), src.data_ptr(), seq, heads, E, cp, kv_repeat, mode,
+                                                    _stream()), "magi_ulysses_relayout")
+    return out

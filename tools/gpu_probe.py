@@ -1,0 +1,210 @@
+"""Bring-up probe for the B200 box: runs each case in its own subprocess (a trap or watchdog in one case must not
+take the others down), prints one line per case. Usage: python tools/gpu_probe.py [case ...]"""
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def ref_attn(q, k, v, q_ranges, k_ranges, scale=None):
+    """fp32 torch reference on the GPU (probe only; the tests use oracle/)."""
+    import torch
+    Tq, Hq, D = q.shape
+    Hkv = k.shape[1]
+    g = Hq // Hkv
+    scale = scale or D ** -0.5
+    out = torch.zeros(Tq, Hq, D, dtype=torch.float32, device=q.device)
+    lse = torch.full((Tq, Hq), float("-inf"), dtype=torch.float32, device=q.device)
+    for (q0, q1), (k0, k1) in zip(q_ranges, k_ranges):
+        if q1 <= q0:
+            continue
+        if k1 <= k0:
+            continue
+        qq = q[q0:q1].float().permute(1, 0, 2)  # H, Lq, D
+        kk = k[k0:k1].float().repeat_interleave(g, dim=1).permute(1, 0, 2)
+        vv = v[k0:k1].float().repeat_interleave(g, dim=1).permute(1, 0, 2)
+        s = torch.matmul(qq, kk.transpose(1, 2)) * scale
+        lse[q0:q1] = torch.logsumexp(s, dim=-1).permute(1, 0)
+        p = torch.softmax(s, dim=-1)
+        out[q0:q1] = torch.matmul(p, vv).permute(1, 0, 2)
+    return out, lse
+
+
+def run_attn_case(name, Tq, Tk, Hq, Hkv, q_ranges, k_ranges, cache_len=0, packed=True, mode="rand", seed=0):
+    import torch
+    import magi_b200.functional as F
+    torch.manual_seed(seed)
+    dev = "cuda"
+    q = torch.randn(Tq, Hq, 128, device=dev, dtype=torch.bfloat16)
+    if packed:
+        kv = torch.randn(Tk, Hkv, 256, device=dev, dtype=torch.bfloat16)
+        k, v = kv[..., :128], kv[..., 128:]
+    else:
+        k = torch.randn(Tk, Hkv, 128, device=dev, dtype=torch.bfloat16)
+        v = torch.randn(Tk, Hkv, 128, device=dev, dtype=torch.bfloat16)
+    if mode == "v_eye":      # out rows = softmax probabilities of the first 128 keys -> isolates Q K^T
+        v.zero_()
+        for j in range(min(Tk, 128)):
+            v[j, :, j] = 1
+    elif mode == "k_zero":   # uniform P -> out = mean over keys of V -> isolates V's head_dim ordering
+        k.zero_()
+    elif mode == "onehot":   # P ~ one-hot(i) -> out_i = V_i -> isolates key ordering of P V
+        q.zero_(); k.zero_()
+        for j in range(min(Tk, Tq, 128)):
+            q[j, :, j] = 16
+            k[j, :, j] = 16
+    qr = torch.tensor(q_ranges, dtype=torch.int32, device=dev).reshape(-1, 2)
+    kr = torch.tensor(k_ranges, dtype=torch.int32, device=dev).reshape(-1, 2)
+    if cache_len > 0:
+        kc, vc, kn, vn = k[:cache_len], v[:cache_len], k[cache_len:], v[cache_len:]
+    else:
+        kc = vc = None
+        kn, vn = k, v
+    out, lse = F.attn_ranges(q, kn, vn, qr, kr, k_cache=kc, v_cache=vc, zero_fill=True)
+    torch.cuda.synchronize()
+    ro, rl = ref_attn(q, k, v, q_ranges, k_ranges)
+    err = (out.float() - ro).abs().max().item()
+    fin = torch.isfinite(rl)
+    lerr = (lse[fin] - rl[fin]).abs().max().item() if fin.any() else 0.0
+    rel = ((out.float() - ro).norm() / ro.norm().clamp_min(1e-9)).item()
+    ok = err < 2e-2 and lerr < 1e-2
+    print(f"[{name}] max_abs={err:.3e} rel_l2={rel:.3e} lse_err={lerr:.3e} -> {'OK' if ok else 'FAIL'}", flush=True)
+    if not ok:
+        d = (out.float() - ro).abs()
+        bad = (d > 2e-2).nonzero()
+        print(f"    bad elements: {bad.shape[0]} of {d.numel()}; first: {bad[:6].tolist()}")
+        print(f"    out[0,0,:8]={out[0,0,:8].float().tolist()}\n    ref[0,0,:8]={ro[0,0,:8].tolist()}")
+        r = min(Tq - 1, 130)
+        print(f"    out[{r},0,:8]={out[r,0,:8].float().tolist()}\n    ref[{r},0,:8]={ro[r,0,:8].tolist()}")
+    return ok
+
+
+def bench_attn(name, clip, nchunks_q, k_chunks, Hq, Hkv, iters=5):
+    """k_chunks[i] = (start_chunk, end_chunk) for q chunk i; keys laid out as all chunks up to max end."""
+    import torch
+    import magi_b200.functional as F
+    dev = "cuda"
+    Tq = clip * nchunks_q
+    Tk = clip * max(e for _, e in k_chunks)
+    q = torch.randn(Tq, Hq, 128, device=dev, dtype=torch.bfloat16)
+    kv = torch.randn(Tk, Hkv, 256, device=dev, dtype=torch.bfloat16)
+    qr = torch.tensor([[i * clip, (i + 1) * clip] for i in range(nchunks_q)], dtype=torch.int32, device=dev)
+    kr = torch.tensor([[s * clip, e * clip] for s, e in k_chunks], dtype=torch.int32, device=dev)
+    flops = 4 * 128 * Hq * sum(clip * (e - s) * clip for s, e in k_chunks)
+    for _ in range(3):
+        F.attn_ranges(q, kv[..., :128], kv[..., 128:], qr, kr)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    ev[0].record()
+    for i in range(iters):
+        F.attn_ranges(q, kv[..., :128], kv[..., 128:], qr, kr)
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    ts = [ev[i].elapsed_time(ev[i + 1]) for i in range(iters)]
+    best = min(ts)
+    print(f"[{name}] {flops/1e12:.2f} TFLOP  best {best:.3f} ms -> {flops/best/1e9:.1f} TFLOP/s  (all: "
+          + ", ".join(f"{t:.2f}" for t in ts) + ")", flush=True)
+
+
+CASES = {}
+
+
+def case(fn):
+    CASES[fn.__name__] = fn
+    return fn
+
+
+@case
+def a_veye_1tile():
+    return run_attn_case("v=I 1 tile", 256, 128, 1, 1, [[0, 256]], [[0, 128]], mode="v_eye", packed=False)
+
+
+@case
+def b_kzero_1tile():
+    return run_attn_case("k=0 1 tile", 256, 128, 1, 1, [[0, 256]], [[0, 128]], mode="k_zero", packed=False)
+
+
+@case
+def c_onehot_1tile():
+    return run_attn_case("onehot 1 tile", 256, 128, 1, 1, [[0, 256]], [[0, 128]], mode="onehot", packed=False)
+
+
+@case
+def d_rand_1tile():
+    return run_attn_case("rand 1 tile", 256, 128, 1, 1, [[0, 256]], [[0, 128]], packed=False)
+
+
+@case
+def e_rand_4tiles():
+    return run_attn_case("rand 4 tiles", 256, 512, 1, 1, [[0, 256]], [[0, 512]], packed=False)
+
+
+@case
+def f_rand_packed_gqa():
+    return run_attn_case("packed gqa 1536", 1536, 1536, 6, 2, [[0, 1536]], [[0, 1536]])
+
+
+@case
+def g_ragged_ranges():
+    return run_attn_case("ragged 3 ranges", 1000, 1300, 3, 1, [[0, 300], [300, 650], [650, 1000]],
+                         [[0, 333], [100, 1300], [900, 1001]])
+
+
+@case
+def h_two_segments():
+    return run_attn_case("cache+new", 700, 1500, 6, 2, [[0, 350], [350, 700]], [[0, 1150], [200, 1500]], cache_len=800)
+
+
+@case
+def i_empty_k_and_gap():
+    return run_attn_case("empty k + uncovered rows", 600, 400, 2, 2, [[0, 200], [300, 600]], [[50, 50], [0, 400]])
+
+
+@case
+def j_many_items():
+    # more items than SMs, several per CTA, unequal lengths -> exercises barrier phases across items
+    qr = [[i * 520, (i + 1) * 520] for i in range(6)]
+    kr = [[0, (i + 1) * 520] for i in range(6)]
+    return run_attn_case("6 chunks x 24 heads", 3120, 3120, 24, 8, qr, kr)
+
+
+@case
+def p_bench_cfg2():
+    bench_attn("cfg2 peak: 4 ranges K=1..4 x 9360, 24/8 heads", 9360, 4, [(0, 1), (0, 2), (0, 3), (0, 4)], 24, 8)
+    return True
+
+
+@case
+def q_bench_single():
+    bench_attn("1 range 9360x37440, 24/8 heads", 9360, 1, [(0, 4)], 24, 8)
+    return True
+
+
+def main():
+    names = sys.argv[1:] or sorted(CASES)
+    if len(names) == 1 and names[0].startswith("--run="):
+        n = names[0][6:]
+        ok = CASES[n]()
+        sys.exit(0 if ok else 1)
+    results = {}
+    for n in names:
+        t0 = time.time()
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), f"--run={n}"], timeout=180,
+                               capture_output=True, text=True)
+            out = (r.stdout + r.stderr).strip()
+            tail = "\n".join(out.splitlines()[-14:])
+            print(tail, flush=True)
+            results[n] = r.returncode
+        except subprocess.TimeoutExpired:
+            print(f"[{n}] TIMEOUT", flush=True)
+            results[n] = -9
+        print(f"  ({n}: rc={results[n]}, {time.time()-t0:.1f}s)", flush=True)
+    print("SUMMARY", results)
+
+
+if __name__ == "__main__":
+    main()
