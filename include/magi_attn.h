@@ -89,7 +89,7 @@ MAGI_API int magi_attn_fwd(const magi_attn_args* args, void* stream);
  *           flash_attn rotary (Triton)       dit_module.py:961, 978
  *           KV-cache slice-assign            dit_module.py:918-929 (append fused: second store target)
  *
- * x_q / x_k / x_v are the bf16 projection outputs, (rows, H*128) row-major with rows = (sq b) flattened.
+ * x_q / x_k / x_v are the bf16 projection outputs, (rows, H, 128) with explicit row/head strides, rows = (sq b).
  * LayerNorm runs in fp32 over 128 with gamma = (w + 1) if zero_centered_gamma else w, bias b, eps; weights are
  * fp32 (the reference promotes q/k_layernorm to fp32, dit_model.py:621-633) or bf16 (ln_dtype = 1; the +1 is
  * then rounded to bf16 like the reference's `self.weight + 1` in bf16).
@@ -109,7 +109,10 @@ typedef struct magi_prologue_args {
   const void* x_k; /* may be NULL (q only)   */
   const void* x_v; /* may be NULL            */
   int64_t rows;
-  int64_t xq_row_stride, xk_row_stride, xv_row_stride; /* elements */
+  int64_t xq_row_stride, xk_row_stride, xv_row_stride;    /* elements */
+  int64_t xq_head_stride, xk_head_stride, xv_head_stride; /* elements; 0 selects 128 (dense heads). 256 reads K and
+                                                             V out of a packed (rows, Hkv, 256) projection
+                                                             (linear_kv_xattn, dit_module.py:1015-1018) */
   int32_t num_heads_q, num_heads_kv;
   int32_t batch; /* rope row = r / batch */
   const void* ln_q_w;
@@ -153,11 +156,17 @@ MAGI_API int magi_lse_merge(void* out_a, float* lse_a, const void* out_b, const 
 /*
  * Head<->sequence re-layout used around the Ulysses all-to-all.
  *   mode 0: "seq (cp hn) hd -> (cp seq) hn hd"  (context_parallel.py:396, send side of all_to_all_input_split)
- *   mode 1: "(cp seq) hn hd -> seq (cp hn) hd"  (context_parallel.py:596, after all_to_all_output_split)
- * kv_repeat > 1 replicates each head kv_repeat times first (context_parallel.py:393-394).
+ *           kv_repeat > 1 replicates each source head kv_repeat times first (context_parallel.py:393-394);
+ *           `heads` = source heads.
+ *   mode 1: "(cp seq) hn hd -> seq (cp hn) hd"  (context_parallel.py:596, after all_to_all_output_split);
+ *           `heads` = hn of src. The destination may be wider: dst row = (cp, dst_heads_total, hd) and this call
+ *           fills heads [dst_head_offset, dst_head_offset + hn) of every cp block, so the per-head-group outputs of
+ *           the overlapped pipeline (context_parallel.py:584-594) land in place without a torch.cat.
+ *           dst_heads_total = 0 selects hn (dense).
  */
-MAGI_API int magi_ulysses_relayout(void* dst, const void* src, int64_t seq, int32_t heads, int32_t head_elems, int32_t cp,
-                          int32_t kv_repeat, int32_t mode, void* stream);
+MAGI_API int magi_ulysses_relayout(void* dst, const void* src, int64_t seq, int32_t heads, int32_t head_elems,
+                                   int32_t cp, int32_t kv_repeat, int32_t mode, int32_t dst_heads_total,
+                                   int32_t dst_head_offset, void* stream);
 
 /* Diagnostics */
 MAGI_API const char* magi_last_error(void);

@@ -69,6 +69,9 @@ class MagiPrologueArgs(C.Structure):
         ("xq_row_stride", C.c_int64),
         ("xk_row_stride", C.c_int64),
         ("xv_row_stride", C.c_int64),
+        ("xq_head_stride", C.c_int64),
+        ("xk_head_stride", C.c_int64),
+        ("xv_head_stride", C.c_int64),
         ("num_heads_q", C.c_int32),
         ("num_heads_kv", C.c_int32),
         ("batch", C.c_int32),
@@ -136,7 +139,7 @@ def lib() -> C.CDLL:
                                  C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
     L.magi_ulysses_relayout.restype = C.c_int
     L.magi_ulysses_relayout.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                        C.c_int32, C.c_void_p]
+                                        C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     L.magi_last_error.restype = C.c_char_p
     L.magi_build_info.restype = C.c_char_p
     L.magi_launch_count.restype = C.c_uint64

@@ -1,0 +1,321 @@
+"""Drop-in `FullyParallelAttention` for the reference's DiT block (inference/model/dit/dit_module.py:776-1246):
+same constructor `(model_config, engine_config, layer_number)`, same sub-module / parameter names (so reference
+state_dicts load: `linear_qkv.{layer_norm,q,qx,k,v}`, `linear_kv_xattn`, `linear_proj`, `q_layernorm`,
+`q_layernorm_xattn`, `k_layernorm`, `k_layernorm_xattn`), same `forward(hidden_states, key_value_states,
+inference_params, rotary_pos_emb, meta_args) -> (core_attn_out, xattn_out)`.
+
+What runs where
+  * LayerNorm(hidden) and the q/qx/k/v, kv_xattn projections are plain torch/cuBLAS GEMMs (outside the hot path,
+    SURVEY.md section 2.3 K11).
+  * everything between the projections and the two attention outputs is hand-written CUDA behind the C-ABI:
+    fused per-head LayerNorm(+1p) + RoPE + packing + KV-cache append (one kernel instead of ~15 eager ones),
+    range-masked tcgen05 attention reading the KV cache in place (no torch.cat / chunk().contiguous()),
+    varlen cross-attention on the same kernel.
+"""
+import math
+from functools import partial
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import context_parallel as cpm
+from . import functional as F
+from . import parallel_state as mpu
+from .common import EngineConfig, InferenceParams, ModelConfig, ModelMetaArgs, PackedCrossAttnParams, divide
+
+
+class HeadLayerNorm(nn.Module):
+    """Parameter holder for the per-head LayerNorm (FusedLayerNorm, dit_module.py:323-357). The arithmetic is fused
+    into the prologue kernel; `weight`/`bias` keep the reference's names, shapes and (torch.empty) initialisation."""
+
+    def __init__(self, model_config: ModelConfig, hidden_size: int):
+        super().__init__()
+        self.zero_centered_gamma = model_config.apply_layernorm_1p
+        self.eps = model_config.layernorm_epsilon
+        self.weight = nn.Parameter(torch.empty(hidden_size, dtype=model_config.params_dtype))
+        self.bias = nn.Parameter(torch.empty(hidden_size, dtype=model_config.params_dtype))
+
+
+class CustomLayerNormLinear(nn.Module):
+    """dit_module.py:390-425 (bf16 linears; the fp8 variants are outside the hot path)."""
+
+    def __init__(self, input_size, output_size_q, output_size_kv, layer_number, model_config, engine_config):
+        super().__init__()
+        if engine_config.fp8_quant:
+            raise NotImplementedError("fp8_quant projections are outside the hot path of this build")
+        self.layer_norm = nn.LayerNorm(input_size, eps=model_config.layernorm_epsilon, dtype=model_config.params_dtype)
+        self.layer_number = layer_number
+        for name, size in {"q": output_size_q, "qx": output_size_q, "k": output_size_kv, "v": output_size_kv}.items():
+            setattr(self, name, nn.Linear(input_size, size, bias=False, dtype=model_config.params_dtype))
+
+    def forward_ln(self, hidden_states):
+        return self.layer_norm(hidden_states)
+
+    def forward_q(self, x):
+        return self.q(x)
+
+    def forward_qx(self, x):
+        return self.qx(x)
+
+    def forward_k(self, x):
+        return self.k(x)
+
+    def forward_v(self, x):
+        return self.v(x)
+
+
+class FullyParallelAttention(nn.Module):
+    def __init__(self, model_config: ModelConfig, engine_config: EngineConfig, layer_number: int):
+        super().__init__()
+        self.model_config = model_config
+        self.engine_config = engine_config
+        self.layer_number = layer_number
+        hd = model_config.kv_channels
+        if hd != F.HEAD_DIM:
+            raise ValueError(f"kv_channels must be {F.HEAD_DIM}")
+        self.hidden_size_per_attention_head = hd
+        self.query_projection_size = hd * model_config.num_attention_heads
+        self.kv_projection_size = hd * model_config.num_query_groups
+        world_size = mpu.get_tp_world_size(with_context_parallel=True)
+        groups = model_config.num_query_groups
+        if engine_config.cp_strategy == "cp_ring_kv":
+            self.num_query_groups_per_partition = groups   # ring-KV keeps all heads (and a replicated cache)
+        elif world_size > groups and world_size % groups == 0:   # dit_module.py:794-798
+            self.num_query_groups_per_partition = 1
+        else:
+            self.num_query_groups_per_partition = divide(groups, world_size)
+
+        self.linear_qkv = CustomLayerNormLinear(model_config.hidden_size, self.query_projection_size,
+                                                self.kv_projection_size, layer_number, model_config, engine_config)
+        self.linear_kv_xattn = nn.Linear(int(model_config.hidden_size * model_config.xattn_cond_hidden_ratio),
+                                         2 * self.kv_projection_size, dtype=model_config.params_dtype, bias=False)
+        self.linear_proj = nn.Linear(2 * self.query_projection_size, model_config.hidden_size,
+                                     dtype=model_config.params_dtype, bias=False)
+        self.q_layernorm = HeadLayerNorm(model_config, hd)
+        self.q_layernorm_xattn = HeadLayerNorm(model_config, hd)
+        self.k_layernorm = HeadLayerNorm(model_config, hd)
+        self.k_layernorm_xattn = HeadLayerNorm(model_config, hd)
+
+    # ------------------------------------------------------------------ KV cache (dit_module.py:800-819, 891-946)
+    def _allocate_key_and_value_memory(self, sequence_length, batch_size, dtype, device):
+        if self.engine_config.kv_offload:
+            raise NotImplementedError("kv_offload is a 'next' row (SURVEY.md section 8f-3); the cache lives in HBM")
+        return torch.empty(sequence_length * batch_size, self.num_query_groups_per_partition,
+                           2 * self.hidden_size_per_attention_head, dtype=dtype, device=device)
+
+    def _cache(self, inference_params: InferenceParams, dtype, device):
+        d = inference_params.key_value_memory_dict
+        if self.layer_number not in d:
+            d[self.layer_number] = self._allocate_key_and_value_memory(
+                inference_params.max_sequence_length, inference_params.max_batch_size, dtype, device)
+        return d[self.layer_number]
+
+    @staticmethod
+    def _uses_cache(inference_params, meta_args: ModelMetaArgs) -> bool:
+        """dit_module.py:936-943."""
+        return inference_params is not None and (
+            meta_args.extract_prefix_video_feature or meta_args.fwd_extra_1st_chunk or meta_args.slice_point > 0)
+
+    def _cache_plan(self, inference_params, meta_args, new_rows: int, dtype, device):
+        """(cache, sequence_start, rows_to_append) following dit_module.py:914-929."""
+        if not self._uses_cache(inference_params, meta_args):
+            return None, 0, 0
+        cache = self._cache(inference_params, dtype, device)
+        bs = inference_params.max_batch_size
+        start = meta_args.slice_point * meta_args.clip_token_nums * bs
+        rows = 0
+        if inference_params.update_kv_cache:
+            rows = new_rows - meta_args.clip_token_nums * bs if meta_args.distill_nearly_clean_chunk else new_rows
+            assert start + rows <= cache.size(0)   # dit_module.py:927
+        return cache, start, rows
+
+    # ------------------------------------------------------------------ pieces
+    def _project(self, mixed):
+        sq, b, _ = mixed.shape
+        x = mixed.reshape(sq * b, -1)
+        return (self.linear_qkv.forward_q(x), self.linear_qkv.forward_k(x), self.linear_qkv.forward_v(x))
+
+    def _ln(self, mod: HeadLayerNorm):
+        return (mod.weight, mod.bias)
+
+    def core_attention(self, query, k_new, v_new, bs: int, meta_args: ModelMetaArgs, k_cache=None, v_cache=None,
+                       out=None):
+        """dit_module.py:1023-1066 on "(sq b)"-ordered rows. bs > 1 only occurs with one range shared by all batch
+        rows (dit_module.py:1048-1061): each batch row is a strided view, no transposes or copies."""
+        p = meta_args.core_attn_params
+        if out is None:
+            out = torch.empty_like(query)
+        if bs == 1:
+            F.attn_ranges(query, k_new, v_new, p.q_range, p.k_range, k_cache=k_cache, v_cache=v_cache, out=out,
+                          return_lse=False)
+            return out
+        assert not (bs > 1 and meta_args.denoising_range_num > 1)
+        assert k_cache is None
+
+        def row(x, i):
+            return x.unflatten(0, (-1, bs))[:, i]
+
+        for i in range(bs):
+            F.attn_ranges(row(query, i), row(k_new, i), row(v_new, i), p.q_range[:1], p.k_range[:1], out=row(out, i),
+                          return_lse=False)
+        return out
+
+    def cross_attention(self, mixed_qqkv, key_value_states, cross_attn_params: PackedCrossAttnParams):
+        """get_xqkv + cross_attention, dit_module.py:1005-1021, 1098-1136. Returns (sq, b, Hq*128)."""
+        sq, b, _ = mixed_qqkv.shape
+        Hq, Hkv = self.model_config.num_attention_heads, self.model_config.num_query_groups
+        eps, z = self.model_config.layernorm_epsilon, self.model_config.apply_layernorm_1p
+        qx = self.linear_qkv.forward_qx(mixed_qqkv.reshape(sq * b, -1))                 # rows in (sq b) order
+        kvx = torch.nn.functional.linear(key_value_states, self.linear_kv_xattn.weight)  # (ytot, Hkv*256)
+        kvx = kvx.view(key_value_states.shape[0], Hkv, 2 * F.HEAD_DIM)
+        # text K: LayerNorm (bf16 params, no RoPE); V: copy -> packed (ytot, Hkv, 256)
+        _, kv_x = F.qk_norm_rope(None, kvx[..., :F.HEAD_DIM], kvx[..., F.HEAD_DIM:], Hq, Hkv, None,
+                                 self._ln(self.k_layernorm_xattn), None, None, eps=eps, zero_centered_gamma=z)
+        out = torch.empty((sq, b, Hq, F.HEAD_DIM), dtype=qx.dtype, device=qx.device)
+        # q_ranges / kv_ranges (the flex_flash_attn_func arguments, dit_module.py:1111-1122) rather than cu_seqlens:
+        # they stay valid when a caption segment is empty and after the per-rank rewrite under context parallelism
+        n = cross_attn_params.q_ranges.shape[0]
+        per_b = n // b
+        for i in range(b):
+            # "(sq b) -> (b sq)": batch row i is a strided view of the projection output
+            q_i, _ = F.qk_norm_rope(qx.view(sq, b, Hq, F.HEAD_DIM)[:, i], None, None, Hq, Hkv,
+                                    self._ln(self.q_layernorm_xattn), None, None, None, eps=eps,
+                                    zero_centered_gamma=z)
+            qr = cross_attn_params.q_ranges[i * per_b:(i + 1) * per_b]
+            if i > 0:
+                qr = qr - i * sq
+            kr = cross_attn_params.kv_ranges[i * per_b:(i + 1) * per_b]
+            F.attn_ranges(q_i, kv_x[..., :F.HEAD_DIM], kv_x[..., F.HEAD_DIM:], qr, kr, out=out[:, i],
+                          return_lse=False)
+        return out.view(sq, b, Hq * F.HEAD_DIM)
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, hidden_states: torch.Tensor, key_value_states: torch.Tensor,
+                inference_params: Optional[InferenceParams], rotary_pos_emb: torch.Tensor, meta_args: ModelMetaArgs):
+        assert rotary_pos_emb is not None, "FullyParallelAttention needs rotary_pos_emb"
+        sin_emb, cos_emb = rotary_pos_emb.tensor_split(2, -1)   # dit_module.py:1147: table is [sin | cos]
+        sq, batch_size, _ = hidden_states.shape
+        Hq, Hkv = self.model_config.num_attention_heads, self.model_config.num_query_groups
+        eps, z = self.model_config.layernorm_epsilon, self.model_config.apply_layernorm_1p
+        mixed_qqkv = self.linear_qkv.forward_ln(hidden_states)
+        strategy = self.engine_config.cp_strategy
+        rows = sq * batch_size
+        dev, dt = hidden_states.device, hidden_states.dtype
+
+        if strategy == "none":
+            assert self.engine_config.cp_size == 1
+            xq, xk, xv = self._project(mixed_qqkv)
+            cache, start, app = self._cache_plan(inference_params, meta_args, rows, dt, dev)
+            query, kv_new = F.qk_norm_rope(xq, xk, xv, Hq, Hkv, self._ln(self.q_layernorm), self._ln(self.k_layernorm),
+                                           sin_emb, cos_emb, batch=batch_size, eps=eps, zero_centered_gamma=z,
+                                           cache=cache if app > 0 else None, cache_row_offset=start, cache_rows=app)
+            kc = vc = None
+            if cache is not None and start > 0:
+                kc, vc = cache[:start, :, :F.HEAD_DIM], cache[:start, :, F.HEAD_DIM:]
+            core = self.core_attention(query, kv_new[..., :F.HEAD_DIM], kv_new[..., F.HEAD_DIM:], batch_size,
+                                       meta_args, kc, vc)
+            core_attn_out = core.view(sq, batch_size, Hq * F.HEAD_DIM)
+            xattn_out = self.cross_attention(mixed_qqkv, key_value_states, meta_args.cross_attn_params)
+
+        elif strategy == "cp_ulysses":
+            core_attn_out, xattn_out = self._forward_ulysses(mixed_qqkv, key_value_states, inference_params, sin_emb,
+                                                             cos_emb, meta_args)
+        elif strategy == "cp_ring_kv":
+            core_attn_out, xattn_out = self._forward_ring(mixed_qqkv, key_value_states, inference_params, sin_emb,
+                                                          cos_emb, meta_args)
+        elif strategy == "cp_shuffle_overlap":
+            raise NotImplementedError("cp_shuffle_overlap (CSO, 'for 4090 or older') is not part of this build")
+        else:
+            raise ValueError(f"Unsupported cp_strategy: {strategy}")   # dit_module.py:1244
+        return core_attn_out, xattn_out
+
+    # ------------------------------------------------------------------ Ulysses (dit_module.py:1175-1205)
+    def _forward_ulysses(self, mixed_qqkv, key_value_states, inference_params, sin_emb, cos_emb, meta_args):
+        sq, b, _ = mixed_qqkv.shape
+        cp = self.engine_config.cp_size
+        Hq, Hkv = self.model_config.num_attention_heads, self.model_config.num_query_groups
+        eps, z = self.model_config.layernorm_epsilon, self.model_config.apply_layernorm_1p
+        rows = sq * b
+        dev, dt = mixed_qqkv.device, mixed_qqkv.dtype
+        split = [x * b for x in meta_args.cp_split_sizes]   # dit_module.py:1150
+        total_rows = sum(split)
+        x2d = mixed_qqkv.reshape(rows, -1)
+        cache, start, app = self._cache_plan(inference_params, meta_args, total_rows, dt, dev)
+        hkv_loc = self.num_query_groups_per_partition
+        # the KV all-to-all lands straight in the cache slot when every received row is to be cached
+        direct = cache is not None and app == total_rows
+        kv_recv = cache[start:start + total_rows] if direct else None
+
+        def get_kv():
+            _, kv = F.qk_norm_rope(None, self.linear_qkv.forward_k(x2d), self.linear_qkv.forward_v(x2d), Hq, Hkv, None,
+                                   self._ln(self.k_layernorm), sin_emb, cos_emb, batch=b, eps=eps,
+                                   zero_centered_gamma=z, head_perm_cp=cp)
+            return kv
+
+        def get_q():
+            q, _ = F.qk_norm_rope(self.linear_qkv.forward_q(x2d), None, None, Hq, Hkv, self._ln(self.q_layernorm), None,
+                                  sin_emb, cos_emb, batch=b, eps=eps, zero_centered_gamma=z, head_perm_cp=cp)
+            return q
+
+        def kv_cache_func(kv):
+            if cache is not None and app > 0 and not direct:
+                F.kv_cache_append(cache, kv, start, app)
+            if cache is not None and start > 0:
+                self._kc, self._vc = cache[:start, :, :F.HEAD_DIM], cache[:start, :, F.HEAD_DIM:]
+            else:
+                self._kc = self._vc = None
+            return kv[..., :F.HEAD_DIM], kv[..., F.HEAD_DIM:]
+
+        def core(q, k, v, out, kv_heads):
+            kc = vc = None
+            if self._kc is not None:   # same kv-head slice of the cache as of the new tokens
+                kc, vc = self._kc[:, kv_heads[0]:kv_heads[1]], self._vc[:, kv_heads[0]:kv_heads[1]]
+            return self.core_attention(q, k, v, b, meta_args, kc, vc, out=out)
+
+        def relayout_out(recv, cp_, result, q_head, lo):
+            F.ulysses_relayout(recv, cp_, 1, out=result, dst_heads_total=q_head, dst_head_offset=lo)
+
+        kv = get_kv()
+        kv, h_kv = cpm.all_to_all_input_split(kv, split, send_layout=True, out=kv_recv)
+        query = get_q()
+        query, h_q = cpm.all_to_all_input_split(query, split, send_layout=True)
+        h_kv.wait()
+        key, value = kv_cache_func(kv)
+        h_q.wait()
+        out = cpm.UlyssesScheduler.get_attn_and_xattn_base(
+            query, key, value, core, partial(self.cross_attention, mixed_qqkv, key_value_states,
+                                             meta_args.cross_attn_params),
+            self.engine_config.ulysses_overlap_degree, b, cp, split, relayout_out=relayout_out)
+        self._kc = self._vc = None
+        return out
+
+    # ------------------------------------------------------------------ ring-KV (new)
+    def _forward_ring(self, mixed_qqkv, key_value_states, inference_params, sin_emb, cos_emb, meta_args):
+        sq, b, _ = mixed_qqkv.shape
+        if b != 1:
+            raise NotImplementedError("cp_ring_kv supports batch size 1 (the 3-CFG uncond pass uses cp_ulysses)")
+        Hq, Hkv = self.model_config.num_attention_heads, self.model_config.num_query_groups
+        eps, z = self.model_config.layernorm_epsilon, self.model_config.apply_layernorm_1p
+        dev, dt = mixed_qqkv.device, mixed_qqkv.dtype
+        total_rows = sum(meta_args.cp_split_sizes)
+        cache, start, app = self._cache_plan(inference_params, meta_args, total_rows, dt, dev)
+        xq, xk, xv = self._project(mixed_qqkv)
+        query, kv_local = F.qk_norm_rope(xq, xk, xv, Hq, Hkv, self._ln(self.q_layernorm), self._ln(self.k_layernorm),
+                                         sin_emb, cos_emb, batch=1, eps=eps, zero_centered_gamma=z)
+        p = meta_args.core_attn_params
+
+        def attn(q, blk, cache_prefix, qr, kr):
+            t = lambda a: torch.as_tensor(a, dtype=torch.int32).to(dev, non_blocking=True)
+            kc = vc = None
+            if cache_prefix is not None:
+                kc, vc = cache_prefix[..., :F.HEAD_DIM], cache_prefix[..., F.HEAD_DIM:]
+            return F.attn_ranges(q, blk[..., :F.HEAD_DIM], blk[..., F.HEAD_DIM:], t(qr), t(kr), k_cache=kc, v_cache=vc,
+                                 zero_fill=True)
+
+        out, _ = cpm.RingKVScheduler.run(query, kv_local, cache, p.np_q_range, p.np_k_range, start, app,
+                                         meta_args.cp_split_sizes, attn, F.lse_merge, F.kv_cache_append)
+        core_attn_out = out.view(sq, 1, Hq * F.HEAD_DIM)
+        xattn_out = self.cross_attention(mixed_qqkv, key_value_states, meta_args.cross_attn_params)
+        return core_attn_out, xattn_out

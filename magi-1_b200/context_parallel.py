@@ -1,0 +1,375 @@
+"""Context-parallel hooks of the hot path, same names / argument meaning as the reference's
+inference/infra/parallelism/context_parallel.py, re-designed for one NVSwitch domain:
+
+  * the all-to-all SEND buffers are produced directly by the fused prologue kernel (`head_perm_cp`), so the
+    `repeat_interleave` + `rearrange().contiguous()` staging of context_parallel.py:393-396 disappears;
+  * the KV all-to-all can land directly in the KV-cache slot (the cache stores post-all-to-all heads,
+    dit_module.py:794-819), so the append copy of dit_module.py:929 disappears;
+  * the receive-side "(cp sq) hn hd -> sq (cp hn hd)" of context_parallel.py:596 is one re-layout kernel writing each
+    head group in place (no torch.cat of groups);
+  * a ring-KV exchange (`RingKVScheduler`) is added: K/V blocks rotate over NVLink with point-to-point send/recv,
+    double-buffered against the per-step attention, partial results merged by log-sum-exp.
+
+Collectives go through torch.distributed (NCCL on the GPU box). Everything that computes is injected as a callable
+(attention, re-layout, merge), exactly as the reference's UlyssesScheduler takes callables
+(context_parallel.py:452-597): the product wires in the CUDA kernels, the CPU (gloo) tests wire in test doubles.
+The cp_shuffle_overlap (CSO) strategy of the reference ("for 4090 or older", context_parallel.py:324) is not built.
+"""
+from typing import Callable, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import parallel_state as mpu
+from .common import ModelMetaArgs, PackedCoreAttnParams, PackedCrossAttnParams
+
+
+class FakeHandle:
+    """context_parallel.py:89-94."""
+
+    def wait(self):
+        pass
+
+
+#####################################################
+# Common primitives
+#####################################################
+def scatter_to_context_parallel_region(input_, cp_split_sizes, cp_shuffle_num=1, cp_pad_size=0):
+    """context_parallel.py:29-53 (contiguous split; no communication, the input is replicated)."""
+    world_size = mpu.get_cp_world_size()
+    if world_size == 1:
+        return input_
+    if cp_shuffle_num != 1 or cp_pad_size != 0:
+        raise NotImplementedError("cp_shuffle_overlap (CSO) is not part of this build")
+    rank = mpu.get_cp_rank()
+    dim_offset = sum(cp_split_sizes[:rank])
+    return input_[dim_offset:dim_offset + cp_split_sizes[rank]].contiguous()
+
+
+def gather_from_context_parallel_region(input_, cp_split_sizes, cp_shuffle_num=1, cp_pad_size=0):
+    """context_parallel.py:56-86: all-gather of uneven sequence shards along dim 0."""
+    world_size = mpu.get_cp_world_size()
+    if world_size == 1:
+        return input_
+    if cp_shuffle_num != 1 or cp_pad_size != 0:
+        raise NotImplementedError("cp_shuffle_overlap (CSO) is not part of this build")
+    input_ = input_.contiguous()
+    dim_size = list(input_.size())
+    dim_size[0] = sum(cp_split_sizes)
+    output = torch.empty(dim_size, dtype=input_.dtype, device=input_.device)
+    outputs = list(torch.split(output, cp_split_sizes, dim=0))
+    dist.all_gather(outputs, input_, group=mpu.get_cp_group())
+    return output
+
+
+#####################################################
+# Context-parallel pre/post processing
+#####################################################
+def ulysses_split_sizes(seq_len: int, cp_size: int) -> List[int]:
+    """context_parallel.py:240-242: S // cp (+1 on the first S % cp ranks)."""
+    sizes = [seq_len // cp_size] * cp_size
+    for i in range(seq_len % cp_size):
+        sizes[i] += 1
+    return sizes
+
+
+def cp_update_cross_attn_qkv_range(cross_attn_params: PackedCrossAttnParams, batch_size: int,
+                                   cp_split_sizes: List[int], device, cp_shuffle_num: int = 1, cp_pad_size: int = 0):
+    """context_parallel.py:134-224: intersect every cross-attention q segment with this rank's sequence shard and
+    rebase to shard-local rows; text K/V are replicated so kv ranges are only filtered."""
+    if cp_shuffle_num != 1 or cp_pad_size != 0:
+        raise NotImplementedError("cp_shuffle_overlap (CSO) is not part of this build")
+    cp_rank = mpu.get_cp_rank()
+    # host-side interval arithmetic (a handful of segments); one D2H read per forward, like the reference's
+    # boolean-mask indexing at context_parallel.py:182-190
+    cu_q = cross_attn_params.cu_seqlens_q.detach().cpu().numpy().astype(np.int64)
+    cu_k = cross_attn_params.cu_seqlens_kv.detach().cpu().numpy().astype(np.int64)
+    bounds = np.concatenate([[0], np.cumsum(np.asarray(cp_split_sizes, dtype=np.int64))])
+    total = int(bounds[-1])
+    qs, qe = cu_q[:-1], cu_q[1:]
+    xq, xk = [], []
+    for i in range(batch_size):
+        s, e = bounds[cp_rank] + i * total, bounds[cp_rank + 1] + i * total
+        st, en = np.maximum(s, qs), np.minimum(e, qe)
+        m = st < en
+        part = np.stack([st[m], en[m]], axis=1)
+        part = part - part[:, 0].min()
+        xq.append(part)
+        xk.append(np.stack([cu_k[:-1][m], cu_k[1:][m]], axis=1))
+    offs = np.concatenate([[0], np.cumsum([r[-1, -1] for r in xq])[:-1]])
+    q_ranges = np.concatenate([r + int(o) for r, o in zip(xq, offs)], axis=0)
+    k_ranges = np.concatenate(xk, axis=0)
+    cu_q_new, cu_k_new = np.unique(q_ranges), np.unique(k_ranges)
+    assert cu_q_new.shape == cu_k_new.shape, f"cu_seqlens_q {cu_q_new.shape} vs cu_seqlens_k {cu_k_new.shape}"
+
+    def t(a):
+        return torch.as_tensor(a.astype(np.int32), device=device)
+
+    return PackedCrossAttnParams(q_ranges=t(q_ranges), kv_ranges=t(k_ranges), cu_seqlens_q=t(cu_q_new),
+                                 cu_seqlens_kv=t(cu_k_new), max_seqlen_q=cp_split_sizes[cp_rank],
+                                 max_seqlen_kv=cross_attn_params.max_seqlen_kv)
+
+
+def cp_ulysses_process(cp_size: int, x: torch.Tensor, condition_map: torch.Tensor, rope: torch.Tensor,
+                       xattn_mask_for_cuda_graph: Union[torch.Tensor, None], cross_attn_params: PackedCrossAttnParams):
+    """context_parallel.py:227-254."""
+    seq_len, N, D = x.shape
+    assert seq_len == rope.size(0), f"seq_len: {seq_len} != rope.size(0): {rope.size(0)}"
+    assert condition_map.size(0) == seq_len, f"condition_map.size(0): {condition_map.size(0)} != seq_len: {seq_len}"
+    if xattn_mask_for_cuda_graph is not None:
+        raise NotImplementedError("xattn_mask_for_cuda_graph is hard-wired to None in the reference (dit_model.py:210)")
+    cp_split_sizes = ulysses_split_sizes(seq_len, cp_size)
+    x = scatter_to_context_parallel_region(x, cp_split_sizes)
+    condition_map = scatter_to_context_parallel_region(condition_map, cp_split_sizes)
+    rope = scatter_to_context_parallel_region(rope, cp_split_sizes)
+    cross_attn_params = cp_update_cross_attn_qkv_range(cross_attn_params, N, cp_split_sizes, x.device)
+    return x, condition_map, rope, cp_split_sizes, cross_attn_params
+
+
+def cp_pre_process(cp_size: int, cp_strategy: str, x: torch.Tensor, condition_map: torch.Tensor, rope: torch.Tensor,
+                   xattn_mask_for_cuda_graph, ardf_meta: dict, core_attn_params: PackedCoreAttnParams,
+                   cross_attn_params: PackedCrossAttnParams):
+    """context_parallel.py:308-361. Returns (x, condition_map, rope, cp_pad_size, cp_split_sizes, core_attn_params,
+    cross_attn_params). `cp_ring_kv` (new) shards the sequence exactly like `cp_ulysses`."""
+    if cp_size == 1:
+        return x, condition_map, rope, None, None, core_attn_params, cross_attn_params
+    if cp_strategy in ("cp_ulysses", "cp_ring_kv"):
+        x, condition_map, rope, cp_split_sizes, cross_attn_params = cp_ulysses_process(
+            cp_size, x, condition_map, rope, xattn_mask_for_cuda_graph, cross_attn_params)
+        return x, condition_map, rope, 0, cp_split_sizes, core_attn_params, cross_attn_params
+    if cp_strategy == "cp_shuffle_overlap":
+        raise NotImplementedError("cp_shuffle_overlap (CSO, 'for 4090 or older') is not part of this build")
+    raise ValueError(f"Invalid CP strategy: {cp_strategy}, expected cp_ulysses or cp_ring_kv")
+
+
+def cp_post_process(cp_size: int, cp_strategy: str, x: torch.Tensor, meta_args: ModelMetaArgs) -> torch.Tensor:
+    """context_parallel.py:364-375."""
+    if cp_size == 1:
+        return x
+    if cp_strategy in ("cp_ulysses", "cp_ring_kv"):
+        return gather_from_context_parallel_region(x, meta_args.cp_split_sizes)
+    raise ValueError(f"Invalid CP strategy: {cp_strategy}, expected cp_ulysses or cp_ring_kv")
+
+
+#####################################################
+# Ulysses all-to-all
+#####################################################
+def all_to_all_input_split(tensor: torch.Tensor, cp_split_sizes: List[int], relayout: Optional[Callable] = None,
+                           send_layout: bool = False, out: Optional[torch.Tensor] = None):
+    """context_parallel.py:381-401: scatter heads / gather sequence. tensor (seq, cp*hn, hd) -> (sum(sizes), hn, hd).
+    send_layout=True means `tensor` already is "(cp seq) hn hd" (written by the prologue kernel): nothing is staged.
+    Otherwise `relayout(tensor, cp, kv_repeat)` must produce it. `out` lets the result land in a caller-owned
+    contiguous buffer (e.g. the KV-cache slot)."""
+    cp = mpu.get_cp_world_size()
+    if cp == 1:
+        return tensor, FakeHandle()
+    assert cp_split_sizes is not None
+    if not send_layout:
+        _, hn, _ = tensor.shape
+        rep = cp // hn if (cp % hn == 0 and cp != hn) else 1
+        tensor = relayout(tensor, cp, rep)
+    assert tensor.is_contiguous()
+    if out is None:
+        out = torch.empty([sum(cp_split_sizes), *tensor.shape[1:]], device=tensor.device, dtype=tensor.dtype)
+    else:
+        assert out.is_contiguous() and out.shape[0] == sum(cp_split_sizes) and out.shape[1:] == tensor.shape[1:]
+    handle = dist.all_to_all_single(out, tensor, output_split_sizes=list(cp_split_sizes), group=mpu.get_cp_group(),
+                                    async_op=True)
+    return out, handle
+
+
+def all_to_all_output_split(tensor: torch.Tensor, cp_split_sizes: List[int]):
+    """context_parallel.py:404-423: scatter sequence / gather heads. (sum(sizes), hn, hd) -> (cp * local, hn, hd)."""
+    cp = mpu.get_cp_world_size()
+    if cp == 1:
+        return tensor, FakeHandle()
+    assert cp_split_sizes is not None and tensor.is_contiguous()
+    out = torch.empty([cp_split_sizes[mpu.get_cp_rank()] * cp, *tensor.shape[1:]], device=tensor.device,
+                      dtype=tensor.dtype)
+    handle = dist.all_to_all_single(out, tensor, input_split_sizes=list(cp_split_sizes), group=mpu.get_cp_group(),
+                                    async_op=True)
+    return out, handle
+
+
+def head_groups(q_heads: int, kv_heads: int, overlap_degree: int) -> List[Tuple[int, int, int, int]]:
+    """Split the local heads into `overlap_degree` CONTIGUOUS groups (q_lo, q_hi, kv_lo, kv_hi) for the
+    attention / all-to-all pipeline of context_parallel.py:565-589. overlap_degree == -1 selects q_heads // kv_heads.
+    Unlike the reference's GQA branch (context_parallel.py:574-578), whose reshape/chunk permutes the head order of
+    the concatenated output when kv_heads > 1, groups here are contiguous head slices, so the result is identical to
+    overlap_degree == 1 for every degree."""
+    if overlap_degree == -1:
+        overlap_degree = q_heads // kv_heads
+    if overlap_degree < 1 or overlap_degree > q_heads:
+        raise ValueError(f"overlap_degree {overlap_degree} out of range for {q_heads} heads")
+    g = q_heads // kv_heads
+    if overlap_degree == 1:
+        return [(0, q_heads, 0, kv_heads)]
+    if kv_heads % overlap_degree == 0:   # whole kv heads per group
+        kpg = kv_heads // overlap_degree
+        return [(i * kpg * g, (i + 1) * kpg * g, i * kpg, (i + 1) * kpg) for i in range(overlap_degree)]
+    if overlap_degree % kv_heads == 0 and g % (overlap_degree // kv_heads) == 0:  # several groups per kv head
+        per = overlap_degree // kv_heads
+        qpg = g // per
+        return [(i * qpg, (i + 1) * qpg, i // per, i // per + 1) for i in range(overlap_degree)]
+    raise ValueError(f"cannot split {q_heads} q heads / {kv_heads} kv heads into {overlap_degree} contiguous groups")
+
+
+class UlyssesScheduler:
+    """context_parallel.py:452-597, callable-based like the reference. Differences: see module docstring."""
+
+    @staticmethod
+    def get_attn_and_xattn_with_fused_kv_comm(get_q_func: Callable, get_kv_func: Callable, kv_cache_func: Callable,
+                                              core_attn_func: Callable, cross_attn_func: Callable,
+                                              overlap_degree: int, batch_size: int, cp_size: int,
+                                              cp_split_sizes: List[int] = None, *, relayout_in: Callable = None,
+                                              relayout_out: Callable = None, send_layout: bool = False,
+                                              kv_recv_buffer: Optional[torch.Tensor] = None):
+        """context_parallel.py:503-527. get_kv_func() -> packed kv; get_q_func() -> q; kv_cache_func(kv) -> (key,
+        value) views; core_attn_func(q_group, key_group, value_group, out=..., kv_heads=(lo, hi)) -> out;
+        cross_attn_func() -> xattn_out."""
+        kv = get_kv_func()
+        kv, handle_kv = all_to_all_input_split(kv, cp_split_sizes, relayout_in, send_layout, out=kv_recv_buffer)
+        query = get_q_func()
+        query, handle_q = all_to_all_input_split(query, cp_split_sizes, relayout_in, send_layout)
+        handle_kv.wait()
+        key, value = kv_cache_func(kv)
+        handle_q.wait()
+        return UlyssesScheduler.get_attn_and_xattn_base(query, key, value, core_attn_func, cross_attn_func,
+                                                        overlap_degree, batch_size, cp_size, cp_split_sizes,
+                                                        relayout_out=relayout_out)
+
+    @staticmethod
+    def get_attn_and_xattn_base(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, core_attn_func: Callable,
+                                cross_attn_func: Callable, overlap_degree: int, batch_size: int, cp_size: int,
+                                cp_split_sizes: List[int] = None, *, relayout_out: Callable = None):
+        """context_parallel.py:550-597: attention of head group g overlaps the output all-to-all of group g-1; the
+        cross-attention (local tokens, all heads, no communication) overlaps the last one."""
+        q_seq, q_head, q_hidden = query.shape
+        kv_head = key.shape[1]
+        groups = head_groups(q_head, kv_head, overlap_degree)
+        local = cp_split_sizes[mpu.get_cp_rank()] if cp_split_sizes is not None else q_seq
+        result = torch.empty((local, cp_size * q_head, q_hidden), dtype=query.dtype, device=query.device)
+        pending = None
+        for (q_lo, q_hi, k_lo, k_hi) in groups:
+            o = torch.empty((q_seq, q_hi - q_lo, q_hidden), dtype=query.dtype, device=query.device)
+            core_attn_func(query[:, q_lo:q_hi], key[:, k_lo:k_hi], value[:, k_lo:k_hi], out=o, kv_heads=(k_lo, k_hi))
+            if pending is not None:
+                recv, handle, lo = pending
+                handle.wait()
+                relayout_out(recv, cp_size, result, q_head, lo)
+            recv, handle = all_to_all_output_split(o, cp_split_sizes)
+            pending = (recv, handle, q_lo)
+        xattn_out = cross_attn_func()
+        recv, handle, lo = pending
+        handle.wait()
+        relayout_out(recv, cp_size, result, q_head, lo)
+        # "(cp sq b) hn hd -> sq b (cp hn hd)"
+        core_attn_out = result.view(local // batch_size, batch_size, cp_size * q_head * q_hidden)
+        return core_attn_out, xattn_out
+
+
+#####################################################
+# Ring-KV exchange (new capability)
+#####################################################
+def ring_step_ranges(np_q_range: np.ndarray, np_k_range: np.ndarray, seq_start: int, q_off: int, q_len: int,
+                     blk_off: int, blk_len: int, with_cache: bool):
+    """Host-side interval arithmetic for one ring step.
+
+    Global coordinates: new-token row g of this forward has key coordinate seq_start + g (dit_module.py:914-931);
+    this rank owns query rows [q_off, q_off + q_len) of the new tokens; the visiting K/V block holds new-token rows
+    [blk_off, blk_off + blk_len). Returns (q_ranges, k_ranges) for the attention call of this step, q rows local to
+    the rank's shard, k rows in the coordinate system concat(cache[0:seq_start] if with_cache else [], block).
+    Rectangles with an empty intersection are dropped (their rows keep out = 0, lse = -inf for the merge)."""
+    qs, ks = [], []
+    base = seq_start if with_cache else 0
+    for (q0, q1), (k0, k1) in zip(np.asarray(np_q_range).reshape(-1, 2), np.asarray(np_k_range).reshape(-1, 2)):
+        a, b = max(int(q0), q_off), min(int(q1), q_off + q_len)
+        if a >= b:
+            continue
+        nb0 = max(int(k0), seq_start + blk_off)
+        nb1 = min(int(k1), seq_start + blk_off + blk_len)
+        lo = hi = None
+        if nb0 < nb1:   # part of the range inside the visiting block
+            lo, hi = base + nb0 - (seq_start + blk_off), base + nb1 - (seq_start + blk_off)
+        if with_cache and int(k0) < seq_start:   # part of the range inside the cache prefix
+            c0, c1 = int(k0), min(int(k1), seq_start)
+            if lo is None:
+                lo, hi = c0, c1
+            else:
+                # contiguous by construction: a range that reaches the cache and this block covers [seq_start,
+                # seq_start + blk_off) entirely, which is only non-empty for blocks other than the first
+                assert c1 == seq_start and nb0 == seq_start + blk_off
+                if blk_off != 0:
+                    raise AssertionError("cache part must be folded into the step whose block starts at row 0 "
+                                         "or handled as a separate rectangle")
+                lo = c0
+        if lo is None:
+            continue
+        qs.append([a - q_off, b - q_off])
+        ks.append([lo, hi])
+    return (np.asarray(qs, dtype=np.int32).reshape(-1, 2), np.asarray(ks, dtype=np.int32).reshape(-1, 2))
+
+
+class RingKVScheduler:
+    """Sequence-sharded attention: every rank keeps its contiguous query shard with ALL heads; the packed K/V blocks
+    of the new tokens travel around the ring (cp - 1 point-to-point steps, next transfer in flight while the current
+    block is attended), partial results are merged with their log-sum-exp. The KV cache of clean chunks is kept
+    replicated (full heads, full sequence) on every rank: each visiting block is appended as it passes, which at
+    24B / 720p / 8 chunks is 34 GB of the 180 GB per GPU and means cached chunks are never re-communicated.
+    Oracle: the single-GPU result; the reference has no ring attention."""
+
+    @staticmethod
+    def run(query: torch.Tensor, kv_local: torch.Tensor, cache: Optional[torch.Tensor], np_q_range: np.ndarray,
+            np_k_range: np.ndarray, seq_start: int, cache_rows_limit: int, cp_split_sizes: Sequence[int],
+            attn_func: Callable, merge_func: Callable, append_func: Optional[Callable]):
+        """query (S_loc, Hq, 128); kv_local packed (S_loc, Hkv, 256); cache packed (max_seq, Hkv, 256) or None.
+        attn_func(q, kv_block, cache_prefix_or_None, q_ranges, k_ranges) -> (out, lse) with uncovered rows 0 / -inf;
+        merge_func(out_a, lse_a, out_b, lse_b) merges in place into a; append_func(cache, block, row_offset, rows).
+        cache_rows_limit: number of leading new-token rows that go to the cache (0 = no update)."""
+        cp = mpu.get_cp_world_size()
+        rank = mpu.get_cp_rank()
+        group = mpu.get_cp_group()
+        offs = np.concatenate([[0], np.cumsum(np.asarray(cp_split_sizes, dtype=np.int64))]).astype(np.int64)
+        q_off, q_len = int(offs[rank]), int(cp_split_sizes[rank])
+        max_len = int(max(cp_split_sizes))
+        nxt, prv = mpu.cp_global_rank((rank + 1) % cp), mpu.cp_global_rank((rank - 1) % cp)
+        bufs = [torch.empty((max_len,) + tuple(kv_local.shape[1:]), dtype=kv_local.dtype, device=kv_local.device)
+                for _ in range(2)] if cp > 1 else []
+        cur = kv_local
+        out = lse = None
+        for step in range(cp):
+            src = (rank - step) % cp
+            blk_off, blk_len = int(offs[src]), int(cp_split_sizes[src])
+            reqs = None
+            if step + 1 < cp:
+                # forward the block we hold to the next rank while we attend to it
+                send = cur if cur.shape[0] == max_len else torch.nn.functional.pad(
+                    cur, [0, 0] * (cur.dim() - 1) + [0, max_len - cur.shape[0]])
+                ops = [dist.P2POp(dist.isend, send.contiguous(), nxt, group=group),
+                       dist.P2POp(dist.irecv, bufs[step % 2], prv, group=group)]
+                reqs = dist.batch_isend_irecv(ops)
+            blk = cur[:blk_len]
+            if cache is not None and append_func is not None and cache_rows_limit > blk_off:
+                append_func(cache, blk, seq_start + blk_off, min(blk_len, cache_rows_limit - blk_off))
+            # the cache prefix joins the step whose block starts at new-token row 0 (contiguous coordinates)
+            with_cache = cache is not None and seq_start > 0 and blk_off == 0
+            qr, kr = ring_step_ranges(np_q_range, np_k_range, seq_start, q_off, q_len, blk_off, blk_len, with_cache)
+            if cache is not None and seq_start > 0 and blk_off != 0:
+                # ranges that reach into the cache but whose new-token part does not touch this block are covered
+                # in the blk_off == 0 step; nothing to do here
+                pass
+            if qr.shape[0] > 0:
+                o, l = attn_func(query, blk, cache[:seq_start] if with_cache else None, qr, kr)
+                if out is None:
+                    out, lse = o, l
+                else:
+                    merge_func(out, lse, o, l)
+            if reqs is not None:
+                for r in reqs:
+                    r.wait()
+                cur = bufs[step % 2]
+        if out is None:
+            out = torch.zeros_like(query)
+            lse = torch.full(query.shape[:2], float("-inf"), dtype=torch.float32, device=query.device)
+        return out, lse

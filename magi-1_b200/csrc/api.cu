@@ -199,6 +199,9 @@ int magi_qk_norm_rope_fwd(const magi_prologue_args* a, void* stream_) {
                    a->q_out_head_stride % 8 == 0,
                "q strides must be multiples of 8 elements");
   }
+  MAGI_CHECK(a->xq_head_stride % 8 == 0 && a->xk_head_stride % 8 == 0 && a->xv_head_stride % 8 == 0 &&
+                 a->xq_head_stride >= 0 && a->xk_head_stride >= 0 && a->xv_head_stride >= 0,
+             "input head strides must be non-negative multiples of 8 elements");
   if (a->x_k) MAGI_CHECK(a->kv_out && a->ln_k_w && a->ln_k_b, "k path needs kv_out, ln_k_w, ln_k_b");
   if (a->x_v) MAGI_CHECK(a->kv_out, "v path needs kv_out");
   if (a->x_k || a->x_v)
@@ -223,6 +226,9 @@ int magi_qk_norm_rope_fwd(const magi_prologue_args* a, void* stream_) {
   p.x_q = a->x_q; p.x_k = a->x_k; p.x_v = a->x_v;
   p.rows = a->rows;
   p.xq_row_stride = a->xq_row_stride; p.xk_row_stride = a->xk_row_stride; p.xv_row_stride = a->xv_row_stride;
+  p.xq_head_stride = a->xq_head_stride > 0 ? a->xq_head_stride : 128;
+  p.xk_head_stride = a->xk_head_stride > 0 ? a->xk_head_stride : 128;
+  p.xv_head_stride = a->xv_head_stride > 0 ? a->xv_head_stride : 128;
   p.Hq = a->num_heads_q; p.Hkv = a->num_heads_kv; p.batch = a->batch;
   p.ln_q_w = a->ln_q_w; p.ln_q_b = a->ln_q_b; p.ln_k_w = a->ln_k_w; p.ln_k_b = a->ln_k_b;
   p.eps = a->eps; p.zero_centered_gamma = a->zero_centered_gamma;
@@ -275,7 +281,8 @@ int magi_lse_merge(void* out_a, float* lse_a, const void* out_b, const float* ls
 }
 
 int magi_ulysses_relayout(void* dst, const void* src, int64_t seq, int32_t heads, int32_t head_elems, int32_t cp,
-                          int32_t kv_repeat, int32_t mode, void* stream_) {
+                          int32_t kv_repeat, int32_t mode, int32_t dst_heads_total, int32_t dst_head_offset,
+                          void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MAGI_CHECK(seq >= 0 && heads > 0 && cp >= 1 && kv_repeat >= 1, "bad shape");
   MAGI_CHECK(mode == 0 || mode == 1, "mode must be 0 or 1");
@@ -290,9 +297,13 @@ int magi_ulysses_relayout(void* dst, const void* src, int64_t seq, int32_t heads
     MAGI_CHECK(kv_repeat == 1, "kv_repeat only applies to mode 0");
     hn = heads;  // per-rank heads
   }
+  if (dst_heads_total <= 0) dst_heads_total = hn;
+  MAGI_CHECK(mode == 1 || (dst_heads_total == hn && dst_head_offset == 0), "dst head window only applies to mode 1");
+  MAGI_CHECK(dst_head_offset >= 0 && dst_head_offset + hn <= dst_heads_total, "dst head window out of range");
   int grid = 1;
   if (int rc = grid_for(seq * cp * hn * (head_elems / 8), 256, &grid)) return rc;
-  MAGI_CUDA(magi::ulysses_relayout_launch(dst, src, seq, hn, head_elems / 8, cp, kv_repeat, mode, grid, stream));
+  MAGI_CUDA(magi::ulysses_relayout_launch(dst, src, seq, hn, head_elems / 8, cp, kv_repeat, mode,
+                                          dst_heads_total, dst_head_offset, grid, stream));
   g_launches++;
   return 0;
 }

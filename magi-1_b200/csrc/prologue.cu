@@ -102,8 +102,9 @@ __global__ void __launch_bounds__(256) prologue_kernel(const PrologueParams p) {
         type == 0 ? reinterpret_cast<const __nv_bfloat16*>(p.x_q) + r * p.xq_row_stride
                   : type == 1 ? reinterpret_cast<const __nv_bfloat16*>(p.x_k) + r * p.xk_row_stride
                               : reinterpret_cast<const __nv_bfloat16*>(p.x_v) + r * p.xv_row_stride;
+    const int64_t hstride = type == 0 ? p.xq_head_stride : type == 1 ? p.xk_head_stride : p.xv_head_stride;
     uint4 raw = make_uint4(0, 0, 0, 0);
-    if (valid) raw = ld_stream(src + h * 128 + sub * 8);
+    if (valid) raw = ld_stream(src + h * hstride + sub * 8);
     float v[8];
     unpack8(raw, v);
 
@@ -243,7 +244,8 @@ __global__ void __launch_bounds__(256) lse_merge_kernel(__nv_bfloat16* __restric
 // mode 1: dst[s, c*hn + hl, :] = src[(c, s), hl, :]           "(cp seq) hn hd -> seq (cp hn) hd"
 __global__ void __launch_bounds__(256) ulysses_relayout_kernel(__nv_bfloat16* __restrict__ dst,
                                                                const __nv_bfloat16* __restrict__ src, int64_t seq,
-                                                               int hn, int head_vecs, int cp, int rep, int mode) {
+                                                               int hn, int head_vecs, int cp, int rep, int mode,
+                                                               int dst_hn, int dst_off) {
   const int64_t total = seq * cp * hn * head_vecs;
   const int src_heads = cp * hn / rep;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(256) ulysses_relayout_kernel(__nv_bfloat16* __
       const int c = static_cast<int>(t % cp);
       const int64_t s = t / cp;
       const uint4 v = ld_stream(src + (((static_cast<int64_t>(c) * seq + s) * hn + hl) * head_vecs + e) * 8);
-      *reinterpret_cast<uint4*>(dst + i * 8) = v;
+      *reinterpret_cast<uint4*>(dst + (((s * cp + c) * dst_hn + dst_off + hl) * head_vecs + e) * 8) = v;
     }
   }
 }
@@ -287,10 +289,10 @@ cudaError_t lse_merge_launch(void* out_a, float* lse_a, const void* out_b, const
   return cudaGetLastError();
 }
 cudaError_t ulysses_relayout_launch(void* dst, const void* src, int64_t seq, int hn, int head_vecs, int cp, int rep,
-                                    int mode, int grid, cudaStream_t stream) {
+                                    int mode, int dst_hn, int dst_off, int grid, cudaStream_t stream) {
   ulysses_relayout_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(dst),
                                                     reinterpret_cast<const __nv_bfloat16*>(src), seq, hn, head_vecs,
-                                                    cp, rep, mode);
+                                                    cp, rep, mode, dst_hn, dst_off);
   return cudaGetLastError();
 }
 

@@ -10,6 +10,7 @@ struct PrologueParams {
   const void* x_q; const void* x_k; const void* x_v;
   int64_t rows;
   int64_t xq_row_stride, xk_row_stride, xv_row_stride;
+  int64_t xq_head_stride, xk_head_stride, xv_head_stride;
   int Hq, Hkv, batch;
   const void* ln_q_w; const void* ln_q_b; const void* ln_k_w; const void* ln_k_b;
   float eps;
@@ -27,6 +28,6 @@ cudaError_t kv_append_launch(void* cache, int64_t cache_stride, const void* kv, 
 cudaError_t lse_merge_launch(void* out_a, float* lse_a, const void* out_b, const float* lse_b, int64_t rows, int heads,
                              int64_t a_ts, int64_t a_hs, int64_t b_ts, int64_t b_hs, int grid, cudaStream_t stream);
 cudaError_t ulysses_relayout_launch(void* dst, const void* src, int64_t seq, int hn, int head_vecs, int cp, int rep,
-                                    int mode, int grid, cudaStream_t stream);
+                                    int mode, int dst_hn, int dst_off, int grid, cudaStream_t stream);
 
 }  // namespace magi

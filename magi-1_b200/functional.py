@@ -252,8 +252,8 @@ def qk_norm_rope(
     """Fused per-head LayerNorm(w+1, b) -> NeoX RoPE on 96 of 128 dims -> bf16, writing q in attention layout and
     [K|V] packed (rows, Hkv, 256), optionally also appending to the KV cache (dit_module.py:953-996, 918-929).
 
-    x_* are the projection outputs (rows, H*128) bf16 (rows = "(sq b)" flattened; any row stride that is a multiple
-    of 8). ln_* = (weight, bias), both fp32 (self-attention, dit_model.py:621-633) or both bf16 (cross-attention).
+    x_* are the projection outputs, (rows, H*128) or strided (rows, H, 128) bf16 views (rows = "(sq b)" flattened;
+    strides multiples of 8). ln_* = (weight, bias), both fp32 (self-attention, dit_model.py:621-633) or both bf16 (cross-attention).
     sin/cos: (rows // batch, 48) fp32, or None to skip RoPE (dit_module.py:1005-1021).
     With head_perm_cp = cp > 1 the outputs are laid out "(cp seq) hn hd", i.e. ready to be the all-to-all send buffer
     (context_parallel.py:393-396), including KV-head replication when cp > Hkv.
@@ -266,8 +266,11 @@ def qk_norm_rope(
             continue
         if not t.is_cuda or t.dtype != torch.bfloat16:
             raise ValueError(f"{nm} must be a CUDA bfloat16 tensor")
-        if t.dim() != 2 or t.shape[0] != rows or t.shape[1] != H * HEAD_DIM or t.stride(1) != 1:
-            raise ValueError(f"{nm} must be (rows, {H}*128) with a contiguous last dim, got {tuple(t.shape)}")
+        ok2 = t.dim() == 2 and t.shape == (rows, H * HEAD_DIM) and t.stride(1) == 1
+        ok3 = t.dim() == 3 and t.shape == (rows, H, HEAD_DIM) and t.stride(2) == 1
+        if not (ok2 or ok3):
+            raise ValueError(f"{nm} must be (rows, {H}*128) or (rows, {H}, 128) with a contiguous last dim, "
+                             f"got {tuple(t.shape)}")
     cp = max(1, head_perm_cp)
     ln_dtype = None
     for ln, nm in ((ln_q, "ln_q"), (ln_k, "ln_k")):
@@ -302,6 +305,9 @@ def qk_norm_rope(
     a.xq_row_stride = x_q.stride(0) if x_q is not None else 0
     a.xk_row_stride = x_k.stride(0) if x_k is not None else 0
     a.xv_row_stride = x_v.stride(0) if x_v is not None else 0
+    a.xq_head_stride = x_q.stride(1) if x_q is not None and x_q.dim() == 3 else HEAD_DIM
+    a.xk_head_stride = x_k.stride(1) if x_k is not None and x_k.dim() == 3 else HEAD_DIM
+    a.xv_head_stride = x_v.stride(1) if x_v is not None and x_v.dim() == 3 else HEAD_DIM
     a.num_heads_q, a.num_heads_kv, a.batch = num_heads_q, num_heads_kv, batch
     a.ln_q_w, a.ln_q_b = (_ptr(ln_q[0]), _ptr(ln_q[1])) if ln_q is not None else (None, None)
     a.ln_k_w, a.ln_k_b = (_ptr(ln_k[0]), _ptr(ln_k[1])) if ln_k is not None else (None, None)
@@ -361,10 +367,11 @@ def lse_merge(out_a: torch.Tensor, lse_a: torch.Tensor, out_b: torch.Tensor, lse
                                              out_b.stride(0), out_b.stride(1), _stream()), "magi_lse_merge")
 
 
-def ulysses_relayout(src: torch.Tensor, cp: int, mode: int, kv_repeat: int = 1,
-                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def ulysses_relayout(src: torch.Tensor, cp: int, mode: int, kv_repeat: int = 1, out: Optional[torch.Tensor] = None,
+                     dst_heads_total: int = 0, dst_head_offset: int = 0) -> torch.Tensor:
     """mode 0: "seq (cp hn) hd -> (cp seq) hn hd" (with optional head replication); mode 1: the inverse
-    "(cp seq) hn hd -> seq (cp hn) hd" (context_parallel.py:393-396, 596)."""
+    "(cp seq) hn hd -> seq (cp hn) hd" (context_parallel.py:393-396, 596). In mode 1 `out` may be a wider
+    (seq, cp * dst_heads_total, hd) tensor of which heads [dst_head_offset, +hn) of every cp block are filled."""
     if not src.is_cuda or src.dtype != torch.bfloat16 or src.dim() != 3 or not src.is_contiguous():
         raise ValueError("src must be a contiguous CUDA bfloat16 tensor (tokens, heads, head_elems)")
     T, H, E = src.shape
@@ -375,7 +382,8 @@ def ulysses_relayout(src: torch.Tensor, cp: int, mode: int, kv_repeat: int = 1,
     else:
         if T % cp != 0:
             raise ValueError("token count must be divisible by cp")
-        shape = (T // cp, H * cp, E)
+        total = dst_heads_total if dst_heads_total > 0 else H
+        shape = (T // cp, total * cp, E)
         seq, heads = T // cp, H
     if out is None:
         out = torch.empty(shape, dtype=src.dtype, device=src.device)
@@ -383,5 +391,6 @@ def ulysses_relayout(src: torch.Tensor, cp: int, mode: int, kv_repeat: int = 1,
         raise ValueError(f"out must be contiguous with shape {shape}")
     with torch.cuda.device(src.device):
         _lib.check(_lib.lib().magi_ulysses_relayout(out.data_ptr(), src.data_ptr(), seq, heads, E, cp, kv_repeat, mode,
-                                                    _stream()), "magi_ulysses_relayout")
+                                                    dst_heads_total, dst_head_offset, _stream()),
+                   "magi_ulysses_relayout")
     return out

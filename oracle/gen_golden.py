@@ -1,0 +1,343 @@
+"""Generates tests/golden/*.npz by EXECUTING THE REFERENCE'S OWN PYTHON CODE (imported from /root/reference) on CPU
+in the authoring container. Test infrastructure only; /root/reference does not exist on the GPU box, so the
+fixtures are committed and this script is only re-run by hand:
+
+    python oracle/gen_golden.py            # writes tests/golden/
+
+The reference's orchestration code runs unmodified (FullyParallelAttention.forward, get_q/get_k/get_kv/get_xqkv,
+adjust_key_and_value_for_inference, core_attention's fallback loop, cross_attention, cp_ulysses_process,
+cp_update_cross_attn_qkv_range, all_to_all_input/output_split, UlyssesScheduler, generate_sequences, the kv-range
+generators). Only its third-party CUDA-only kernels are substituted by their published math so that it can run
+without a GPU:
+  * flash_attn.layers.rotary.apply_rotary_emb (Triton)  -> flash-attn's own `apply_rotary_emb_torch`
+  * flash_attn_func / flash_attn_varlen_func (CUDA)     -> fp32 softmax(QK^T/sqrt(d))V with GQA, output cast to bf16
+  * torch.cuda.current_device / Tensor.cuda / get_device_capability -> CPU stand-ins
+"""
+import math
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+warnings.filterwarnings("ignore")
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+# ------------------------------------------------------------------ third-party stand-ins (published math)
+def sdpa_math(q, k, v):
+    """flash_attn_func semantics: (b, s, h, d), non-causal, softmax_scale = 1/sqrt(d), GQA. fp32 math, bf16 out."""
+    b, sq, hq, d = q.shape
+    hk = k.shape[2]
+    g = hq // hk
+    qf = q.float().permute(0, 2, 1, 3)
+    kf = k.float().repeat_interleave(g, dim=2).permute(0, 2, 1, 3)
+    vf = v.float().repeat_interleave(g, dim=2).permute(0, 2, 1, 3)
+    s = torch.matmul(qf, kf.transpose(-1, -2)) / math.sqrt(d)
+    p = torch.softmax(s, dim=-1)
+    return torch.matmul(p, vf).permute(0, 2, 1, 3).to(q.dtype).contiguous()
+
+
+def flash_attn_func_cpu(q, k, v, deterministic=False, **kw):
+    return sdpa_math(q, k, v)
+
+
+def flash_attn_varlen_func_cpu(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k, deterministic=False,
+                               **kw):
+    out = torch.zeros_like(q)
+    cq, ck = cu_seqlens_q.tolist(), cu_seqlens_k.tolist()
+    for i in range(len(cq) - 1):
+        if cq[i + 1] > cq[i] and ck[i + 1] > ck[i]:
+            out[cq[i]:cq[i + 1]] = sdpa_math(q[None, cq[i]:cq[i + 1]], k[None, ck[i]:ck[i + 1]],
+                                             v[None, ck[i]:ck[i + 1]])[0]
+    return out
+
+
+def install_patches():
+    sys.path.insert(0, REF)
+    torch.cuda.current_device = lambda: "cpu"
+    torch.cuda.get_device_capability = lambda *a, **k: (8, 0)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    import inference.model.dit.dit_module as dm
+    from flash_attn.layers.rotary import apply_rotary_emb_torch
+    dm.flash_apply_rotary_emb = lambda x, cos, sin: apply_rotary_emb_torch(x, cos, sin)
+    dm.flash_attn_func = flash_attn_func_cpu
+    dm.flash_attn_varlen_func = flash_attn_varlen_func_cpu
+    dm.flex_attention = None
+    return dm
+
+
+def init_dist(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from inference.infra.distributed import parallel_state as mpu
+    mpu.initialize_model_parallel(cp_size=world, pp_size=1, nccl_communicator_config_path=None,
+                                  distributed_timeout_minutes=10, order="tp-cp-pp-dp")
+    return mpu
+
+
+def make_configs(cp_size=1, cp_strategy="none", hidden=128, hq=4, hkv=2):
+    from inference.common.config import EngineConfig, ModelConfig
+    mc = ModelConfig(model_name="videodit_ardf", num_layers=4, hidden_size=hidden, ffn_hidden_size=4 * hidden,
+                     num_attention_heads=hq, num_query_groups=hkv, kv_channels=128, layernorm_epsilon=1e-6,
+                     apply_layernorm_1p=True, params_dtype=torch.bfloat16, xattn_cond_hidden_ratio=1.0)
+    ec = EngineConfig(cp_size=cp_size, cp_strategy=cp_strategy, ulysses_overlap_degree=1)
+    return mc, ec
+
+
+def build_attention(dm, mc, ec, seed):
+    """Reference module with explicit initialisation (its LayerNorm params are torch.empty, dit_module.py:352-353)
+    and the precision promotion of dit_model.py:621-633 applied."""
+    torch.manual_seed(seed)
+    attn = dm.FullyParallelAttention(mc, ec, layer_number=1)
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p_ in attn.named_parameters():
+            if "layernorm" in name or "layer_norm" in name:
+                p_.copy_((torch.randn(p_.shape, generator=g) * (0.2 if "layernorm" in name else 0.02)).to(p_.dtype))
+                if name.endswith("layer_norm.weight"):
+                    p_.add_(1.0)
+            else:
+                p_.copy_((torch.randn(p_.shape, generator=g) * (1.0 / math.sqrt(p_.shape[-1]))).to(p_.dtype))
+    for name, sub in attn.named_modules():
+        if "_xattn" in name:
+            continue
+        if "q_layernorm" in name or "k_layernorm" in name:
+            sub.float()
+    return attn.eval()
+
+
+def pk(t):
+    """bf16 tensors are stored as their raw 16-bit patterns (uint16) to keep the fixtures small; tests/golden_io.py
+    turns them back into fp32 values. Everything else is stored as is."""
+    if isinstance(t, torch.Tensor):
+        if t.dtype == torch.bfloat16:
+            return t.contiguous().view(torch.int16).numpy().view(np.uint16)
+        return t.detach().numpy()
+    return np.asarray(t)
+
+
+def state_to_np(attn):
+    return {"w." + k_: pk(v_) for k_, v_ in attn.state_dict().items()}
+
+
+def meta(dm_common, clip, slice_point, dn, bs, k_range, y_index, fwd_extra=False, distill_ncc=False,
+         cp_split_sizes=None, cross_override=None):
+    from inference.common import ModelMetaArgs, PackedCoreAttnParams, PackedCrossAttnParams
+    cu_q = torch.tensor([0] + [clip] * (dn * bs), dtype=torch.int64).cumsum(0).to(torch.int32)
+    cu_k = torch.tensor([0] + list(y_index), dtype=torch.int64).cumsum(0).to(torch.int32)
+    q_range = torch.stack([cu_q[:-1], cu_q[1:]], 1)
+    k_range = torch.tensor(k_range, dtype=torch.int32)
+    flat = torch.unique(k_range, sorted=True)
+    core = PackedCoreAttnParams(q_range=q_range, k_range=k_range, np_q_range=q_range.numpy(),
+                                np_k_range=k_range.numpy(), max_seqlen_q=clip,
+                                max_seqlen_k=int(flat[-1] - flat[0]))
+    cross = cross_override or PackedCrossAttnParams(
+        q_ranges=q_range, kv_ranges=torch.stack([cu_k[:-1], cu_k[1:]], 1), cu_seqlens_q=cu_q, cu_seqlens_kv=cu_k,
+        max_seqlen_q=clip, max_seqlen_kv=800)
+    return ModelMetaArgs(H=0, W=0, cp_pad_size=0, cp_split_sizes=cp_split_sizes, slice_point=slice_point,
+                         denoising_range_num=dn, range_num=slice_point + dn, extract_prefix_video_feature=False,
+                         fwd_extra_1st_chunk=fwd_extra, distill_nearly_clean_chunk=distill_ncc, clip_token_nums=clip,
+                         enable_cuda_graph=False, core_attn_params=core, cross_attn_params=cross)
+
+
+def rope_for(dm, T_total, H, W, keep_T):
+    """The reference's own table builder on CPU (dit_module.py:670-717 via the dit_model.py:163-166 recipe)."""
+    bands = dm.freq_bands(16, temperature=10000.0, step=1, device="cpu")
+    rescale = math.sqrt((H * W) / (16 * 16))
+    sin, cos = dm.build_rotary_pos_embed([T_total, H, W], bands=bands, dim=128, in_pixels=False,
+                                         ref_feat_shape=[T_total, H / rescale, W / rescale], device="cpu")
+    rope = torch.cat([sin, cos], -1)
+    return rope[-(keep_T * H * W):].contiguous()
+
+
+# ------------------------------------------------------------------ scenario 1: single rank, KV-cache sequence
+def gen_single_rank():
+    dm = install_patches()
+    init_dist(0, 1, 29541)
+    from inference.common import InferenceParams
+    mc, ec = make_configs()
+    attn = build_attention(dm, mc, ec, seed=1234)
+    H = W = 4
+    frames = 3                    # latent frames per chunk -> clip = 48 tokens
+    clip = frames * H * W
+    hidden = mc.hidden_size
+    g = torch.Generator().manual_seed(7)
+    fx = dict(state_to_np(attn))
+    fx["clip"] = np.array(clip)
+    inf = InferenceParams(max_batch_size=1, max_sequence_length=4 * clip)
+
+    def run(tag, slice_point, dn, k_chunks, y_index, update, fwd_extra=False, distill_ncc=False, bs=1, params=inf):
+        S = dn * clip
+        hs = torch.randn(S, bs, hidden, generator=g).to(torch.bfloat16)
+        ytot = int(sum(y_index))
+        kvs = torch.randn(ytot, hidden, generator=g).to(torch.bfloat16)
+        rope = rope_for(dm, (slice_point + dn) * frames, H, W, dn * frames)
+        k_range = [[s * clip, e * clip] for s, e in k_chunks]
+        m = meta(dm, clip, slice_point, dn, bs, k_range, y_index, fwd_extra, distill_ncc)
+        if params is not None:
+            params.update_kv_cache = update
+        with torch.no_grad():
+            core, xattn = attn(hs, kvs, params, rope, m)
+            mixed = attn.linear_qkv.forward_ln(hs)
+            sin_emb, cos_emb = rope.tensor_split(2, -1)
+            q = attn.get_q(mixed, cos_emb, sin_emb)
+            kv = attn.get_kv(mixed, cos_emb, sin_emb)
+            xq, xk, xv = attn.get_xqkv(mixed, kvs)
+            lin = {n: getattr(attn.linear_qkv, "forward_" + n)(mixed) for n in ("q", "qx", "k", "v")}
+        fx.update({
+            f"{tag}.hidden_states": pk(hs), f"{tag}.key_value_states": pk(kvs),
+            f"{tag}.rope": pk(rope), f"{tag}.k_range": np.array(k_range, dtype=np.int32),
+            f"{tag}.q_range": m.core_attn_params.np_q_range, f"{tag}.y_index": np.array(y_index),
+            f"{tag}.meta": np.array([slice_point, dn, bs, int(update), int(fwd_extra), int(distill_ncc),
+                                     int(params is not None)]),
+            f"{tag}.lin_q": pk(lin["q"]), f"{tag}.lin_qx": pk(lin["qx"]),
+            f"{tag}.lin_k": pk(lin["k"]), f"{tag}.lin_v": pk(lin["v"]),
+            f"{tag}.q": pk(q), f"{tag}.kv": pk(kv), f"{tag}.xq": pk(xq), f"{tag}.xk": pk(xk), f"{tag}.xv": pk(xv),
+            f"{tag}.core_attn_out": pk(core), f"{tag}.xattn_out": pk(xattn),
+        })
+        if params is not None and 1 in params.key_value_memory_dict:
+            fx[f"{tag}.cache_after"] = pk(params.key_value_memory_dict[1]).copy()
+
+    # the reference allocates the cache with torch.empty on first use (dit_module.py:905-912): make it deterministic
+    inf.key_value_memory_dict[1] = torch.zeros(4 * clip, 2, 256, dtype=torch.bfloat16)
+    # step A: 2 chunks denoising from scratch (no cache involvement: slice_point == 0, no extra chunk)
+    run("A", 0, 2, [(0, 1), (0, 2)], [50, 50], update=True)
+    # step B: first chunk finished -> re-forward it clean and cache it (fwd_extra_1st_chunk), 2 more in flight
+    run("B", 0, 3, [(0, 1), (0, 2), (1, 3)], [0, 37, 61], update=True, fwd_extra=True)
+    # step C: window advanced: chunks 1,2 in flight reading cached chunk 0 (3-CFG pass A: update_kv_cache False)
+    run("C", 1, 2, [(0, 2), (1, 3)], [33, 90], update=False)
+    # step D: same state, update True, distill extra self-only range appended (dit_model.py:544-566)
+    run("D", 1, 3, [(0, 2), (1, 3), (3, 4)], [33, 90, 33], update=True, distill_ncc=True)
+    # step E: 3-CFG uncond pass: chunks on the batch dim, no inference params (dit_model.py:470-491)
+    run("E", 0, 1, [(0, 1)], [50, 50], update=False, bs=2, params=None)
+    np.savez_compressed(os.path.join(OUT, "attention_single_rank.npz"), **fx)
+    print("single-rank fixture:", len(fx), "arrays")
+    dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------ scenario 2: range / schedule generators
+def gen_ranges():
+    sys.path.insert(0, REF)
+    for name in ("ffmpeg", "diffusers", "timm", "imageio", "cv2", "av"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    fx = {}
+    # `inference.pipeline.__init__` pulls in ffmpeg/diffusers/timm (absent here); register the package without
+    # running it and stub the one sibling module video_generate.py imports names from (prompt text handling only).
+    import importlib.util
+    import inference  # noqa: F401
+    pkg = types.ModuleType("inference.pipeline")
+    pkg.__path__ = [os.path.join(REF, "inference/pipeline")]
+    sys.modules["inference.pipeline"] = pkg
+    pp = types.ModuleType("inference.pipeline.prompt_process")
+    pp.get_negative_special_token_keys = pp.get_special_token_keys = pp.pad_special_token = lambda *a, **k: None
+    sys.modules["inference.pipeline.prompt_process"] = pp
+    spec = importlib.util.spec_from_file_location("inference.pipeline.video_generate",
+                                                  os.path.join(REF, "inference/pipeline/video_generate.py"))
+    vg = importlib.util.module_from_spec(spec)
+    sys.modules["inference.pipeline.video_generate"] = vg
+    spec.loader.exec_module(vg)
+    cases = [(8, 8, 0), (8, 4, 0), (8, 4, 2), (8, 1, 0), (4, 4, 0), (5, 4, 1), (1, 4, 0)]
+    for i, (cn, ws, off) in enumerate(cases):
+        cs, ce, ts, te = vg.generate_sequences(cn, ws, off)
+        fx[f"seq{i}.args"] = np.array([cn, ws, off])
+        fx[f"seq{i}.out"] = np.array([cs, ce, ts, te])
+    # kv-range generators are methods of SampleTransport; call them unbound on a minimal stand-in
+    ti = types.SimpleNamespace(num_steps=64)
+    fake = types.SimpleNamespace(
+        device="cpu", transport_inputs=[ti],
+        get_batch_size_and_chunk_token_nums=lambda infer_idx: (fake_bs[0], 9360))
+    fake_bs = [1]
+    kcases = [(0, 4, [0, 16, 32, 48], 1), (2, 3, [64, 20, 3], 1), (1, 4, [64, 47, 31, 15], 1), (0, 2, [10, 0], 2),
+              (3, 1, [63], 1)]
+    for i, (sp, dn, steps, bs) in enumerate(kcases):
+        fake_bs[0] = bs
+        r = vg.SampleTransport.generate_noise2clean_kvrange(fake, 0, sp, dn, [5, 4, 3, 2], 1, steps)
+        d = vg.SampleTransport.generate_default_kvrange(fake, 0, sp, dn)
+        fx[f"kv{i}.args"] = np.array([sp, dn, bs] + steps)
+        fx[f"kv{i}.noise2clean"] = r.numpy()
+        fx[f"kv{i}.default"] = d.numpy()
+    np.savez_compressed(os.path.join(OUT, "ranges.npz"), **fx)
+    print("range fixture:", len(fx), "arrays")
+
+
+# ------------------------------------------------------------------ scenario 3: 2- and 4-rank Ulysses on gloo
+def _cp_worker(rank, world, port, out_path, hq, hkv):
+    dm = install_patches()
+    init_dist(rank, world, port)
+    import inference.infra.parallelism.context_parallel as cpm
+    from inference.common import PackedCrossAttnParams
+    mc, ec = make_configs(cp_size=world, cp_strategy="cp_ulysses", hq=hq, hkv=hkv)
+    attn = build_attention(dm, mc, ec, seed=99)   # same seed on all ranks -> replicated weights
+    H = W = 4
+    frames = 3
+    clip = frames * H * W + 3 * 0
+    dn, sp, bs = 3, 0, 1
+    S = dn * clip + 0
+    g = torch.Generator().manual_seed(5)
+    hs_full = torch.randn(S, bs, mc.hidden_size, generator=g).to(torch.bfloat16)
+    y_index = [41, 50, 77]
+    kvs = torch.randn(sum(y_index), mc.hidden_size, generator=g).to(torch.bfloat16)
+    rope_full = rope_for(dm, dn * frames, H, W, dn * frames)
+    k_range = [[0, clip], [0, 2 * clip], [clip, 3 * clip]]
+    m_full = meta(dm, clip, sp, dn, bs, k_range, y_index)
+    cond_map = torch.arange(S).reshape(S, 1) // clip
+    x, cmap, rope, split_sizes, cross = cpm.cp_ulysses_process(world, hs_full, cond_map, rope_full, None,
+                                                               m_full.cross_attn_params)
+    m = meta(dm, clip, sp, dn, bs, k_range, y_index, cp_split_sizes=split_sizes, cross_override=cross)
+    with torch.no_grad():
+        core, xattn = attn(x, kvs, None, rope, m)
+        # raw movement primitives on a recognisable tensor
+        probe = (torch.arange(x.shape[0] * hq * 4, dtype=torch.float32).reshape(x.shape[0], hq, 4) + 1000 * rank)
+        probe = probe.to(torch.bfloat16).contiguous()
+        a2a_in, h = cpm.all_to_all_input_split(probe, split_sizes)
+        h.wait()
+        a2a_out, h = cpm.all_to_all_output_split(a2a_in.contiguous(), split_sizes)
+        h.wait()
+        kvprobe = (torch.arange(x.shape[0] * hkv * 4, dtype=torch.float32).reshape(x.shape[0], hkv, 4) + 500 * rank)
+        kvprobe = kvprobe.to(torch.bfloat16).contiguous()
+        kv_in, h = cpm.all_to_all_input_split(kvprobe, split_sizes)
+        h.wait()
+        gathered = cpm.gather_from_context_parallel_region(core.float().contiguous(), split_sizes)
+    fx = {
+        "split_sizes": np.array(split_sizes), "x_local": pk(x), "rope_local": pk(rope),
+        "cross.q_ranges": pk(cross.q_ranges), "cross.kv_ranges": pk(cross.kv_ranges),
+        "cross.cu_seqlens_q": pk(cross.cu_seqlens_q), "cross.cu_seqlens_kv": pk(cross.cu_seqlens_kv),
+        "cross.max_seqlen_q": np.array(cross.max_seqlen_q),
+        "core_attn_out": pk(core), "xattn_out": pk(xattn),
+        "probe": pk(probe), "a2a_in": pk(a2a_in), "a2a_out": pk(a2a_out),
+        "kvprobe": pk(kvprobe), "kv_in": pk(kv_in), "gathered": pk(gathered.to(torch.bfloat16)),
+    }
+    if rank == 0:
+        fx.update(state_to_np(attn))
+        fx.update({"hidden_states": pk(hs_full), "key_value_states": pk(kvs),
+                   "rope": pk(rope_full), "k_range": np.array(k_range, dtype=np.int32),
+                   "y_index": np.array(y_index), "clip": np.array(clip), "heads": np.array([hq, hkv])})
+    np.savez_compressed(out_path.format(rank=rank), **fx)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def gen_cp(world, port, hq, hkv, tag):
+    path = os.path.join(OUT, f"ulysses_{tag}_rank{{rank}}.npz")
+    mp.spawn(_cp_worker, args=(world, port, path, hq, hkv), nprocs=world, join=True)
+    print(f"ulysses cp={world} fixture written ({tag})")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "ranges"):
+        gen_ranges()
+    if which in ("all", "cp2"):
+        gen_cp(2, 29551, 4, 2, "cp2")
+    if which in ("all", "cp4"):
+        gen_cp(4, 29561, 8, 2, "cp4")   # cp > Hkv: exercises KV-head replication (context_parallel.py:393-394)
+    if which in ("all", "single"):
+        gen_single_rank()

@@ -1,0 +1,379 @@
+"""ORACLE - test infrastructure only. CPU (numpy, fp32) restatement of the reference's algorithm for the hot path.
+
+Nothing in the product (`magi-1_b200/`) imports this module. Only `tests/`, `__graft_entry__.smoke()` and the
+`cpu_baseline` / `--impl reference` legs of `bench.py` may use it, and only as the checker / reported baseline.
+
+Reference: samiazirar/MAGI-1 (file:line relative to /root/reference). Third-party arithmetic that is NOT under
+/root/reference and is restated here from its published definition:
+  * flash-attn (pinned `flash-attn==2.4.2`, requirements.txt:20): `flash_attn_func`, `flash_attn_varlen_func` =
+    softmax(Q K^T / sqrt(d)) V per (batch|segment, head) with GQA head mapping h -> h // (Hq/Hkv);
+    `flash_attn.layers.rotary.apply_rotary_emb` = non-interleaved rotation (its own `apply_rotary_emb_torch`).
+  * MagiAttention `flex_flash_attn_func` (unpinned, Dockerfile:17-19): for each i, rows q_ranges[i] attend densely
+    to k_ranges[i]; with disjoint q ranges this equals the reference's own fallback loop, dit_module.py:1046-1065.
+
+Parity pinning: the reference ships no tests or golden vectors for this path, so this oracle is
+pinned against outputs of the reference's own Python code executed in the authoring container
+(oracle/gen_golden.py -> tests/golden/*.npz; tests/test_oracle_golden.py).
+"""
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+F32 = np.float32
+
+
+# ----------------------------------------------------------------------------------------------- bf16 helpers
+def bf16_round(x: np.ndarray) -> np.ndarray:
+    """Round fp32 -> bf16 (round-to-nearest-even) and return as fp32 (what `.to(torch.bfloat16)` does)."""
+    x = np.ascontiguousarray(x, dtype=F32)
+    u = x.view(np.uint32).astype(np.uint64)
+    rounded = ((u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000).astype(np.uint32)
+    out = rounded.view(F32).copy()
+    nan = np.isnan(x)
+    out[nan] = np.nan
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- prologue
+def layer_norm(x: np.ndarray, weight: np.ndarray, bias: np.ndarray, eps: float = 1e-6,
+               zero_centered_gamma: bool = True, weight_is_bf16: bool = False) -> np.ndarray:
+    """FusedLayerNorm.forward, dit_module.py:355-357: F.layer_norm(x, (128,), weight + 1, bias, eps), biased variance.
+    With bf16 parameters (the `_xattn` norms, dit_model.py:626-627) `weight + 1` is itself rounded to bf16."""
+    x = x.astype(F32)
+    w = weight.astype(F32)
+    if zero_centered_gamma:
+        w = w + F32(1.0)
+        if weight_is_bf16:
+            w = bf16_round(w)
+    mean = x.mean(axis=-1, keepdims=True, dtype=F32)
+    d = x - mean
+    var = (d * d).mean(axis=-1, keepdims=True, dtype=F32)
+    rstd = F32(1.0) / np.sqrt(var + F32(eps))
+    return (d * rstd * w + bias.astype(F32)).astype(F32)
+
+
+def apply_rotary_neox(x: np.ndarray, cos: np.ndarray, sin: np.ndarray) -> np.ndarray:
+    """flash_attn.layers.rotary.apply_rotary_emb (non-interleaved), called at dit_module.py:961, 978.
+    x (..., S, H, D), cos/sin (S, R/2); rotates dims [0, R/2) with [R/2, R); dims >= R pass through."""
+    half = cos.shape[-1]
+    x1, x2, rest = x[..., :half], x[..., half:2 * half], x[..., 2 * half:]
+    c = cos[:, None, :].astype(F32)
+    s = sin[:, None, :].astype(F32)
+    o1 = x1 * c - x2 * s
+    o2 = x2 * c + x1 * s
+    return np.concatenate([o1, o2, rest], axis=-1).astype(F32)
+
+
+def get_q_or_k(x_lin: np.ndarray, num_heads: int, ln_w: np.ndarray, ln_b: np.ndarray, sin: np.ndarray,
+               cos: np.ndarray, eps: float = 1e-6, zero_centered_gamma: bool = True) -> np.ndarray:
+    """get_q / get_k, dit_module.py:953-980. x_lin: (sq, b, H*128) holding bf16 values (projection output).
+    fp32 LayerNorm -> transpose to (b, sq, H, 128) -> fp32 RoPE -> one rounding to bf16 -> "(sq b) hn hd"."""
+    sq, b, _ = x_lin.shape
+    x = x_lin.reshape(sq, b, num_heads, 128).astype(F32)
+    x = layer_norm(x, ln_w, ln_b, eps, zero_centered_gamma)
+    x = np.transpose(x, (1, 0, 2, 3))  # b sq hn hd
+    x = apply_rotary_neox(x, cos, sin)
+    x = bf16_round(x)
+    return np.ascontiguousarray(np.transpose(x, (1, 0, 2, 3))).reshape(sq * b, num_heads, 128)
+
+
+def get_v(x_lin: np.ndarray, num_heads: int) -> np.ndarray:
+    """get_v, dit_module.py:987-989: pure re-layout "sq b (hn hd) -> (sq b) hn hd"."""
+    sq, b, _ = x_lin.shape
+    return x_lin.reshape(sq * b, num_heads, 128).astype(F32)
+
+
+def get_kv(xk_lin, xv_lin, num_heads_kv, ln_w, ln_b, sin, cos, eps=1e-6, zero_centered_gamma=True) -> np.ndarray:
+    """get_kv, dit_module.py:991-996: cat([k, v], -1) -> (sq*b, Hkv, 256)."""
+    k = get_q_or_k(xk_lin, num_heads_kv, ln_w, ln_b, sin, cos, eps, zero_centered_gamma)
+    v = get_v(xv_lin, num_heads_kv)
+    return np.concatenate([k, v], axis=-1)
+
+
+def xattn_layer_norm(x: np.ndarray, ln_w_bf16: np.ndarray, ln_b_bf16: np.ndarray, eps: float = 1e-6,
+                     zero_centered_gamma: bool = True) -> np.ndarray:
+    """q_layernorm_xattn / k_layernorm_xattn inside get_xqkv, dit_module.py:1008, 1020: bf16 tensor, bf16 parameters,
+    ATen computes in fp32 and rounds the result to bf16. No RoPE on the cross-attention path."""
+    return bf16_round(layer_norm(x, ln_w_bf16, ln_b_bf16, eps, zero_centered_gamma, weight_is_bf16=True))
+
+
+# ----------------------------------------------------------------------------------------------- KV cache
+def full_adjust_key_and_value(cache: np.ndarray, key_and_value: np.ndarray, slice_point: int, clip_token_nums: int,
+                              max_batch_size: int, update_kv_cache: bool,
+                              distill_nearly_clean_chunk: bool) -> np.ndarray:
+    """_full_adjust_key_and_value, dit_module.py:891-931. `cache` (max_seq*max_bs, Hkv, 256) is updated IN PLACE.
+    Returns cat(cache[:sequence_start], key_and_value)."""
+    sequence_start = slice_point * clip_token_nums * max_batch_size
+    prefix = cache[:sequence_start].copy()
+    if update_kv_cache:
+        total = key_and_value.shape[0]
+        clip_size = total - clip_token_nums * max_batch_size if distill_nearly_clean_chunk else total
+        sequence_end = sequence_start + clip_size
+        assert sequence_end <= cache.shape[0]  # dit_module.py:927
+        cache[sequence_start:sequence_end] = key_and_value[:clip_size]
+    return np.concatenate([prefix, key_and_value], axis=0)
+
+
+def adjust_key_and_value_for_inference(key_and_value, cache, has_inference_params, slice_point, clip_token_nums,
+                                       max_batch_size, update_kv_cache, extract_prefix_video_feature,
+                                       fwd_extra_1st_chunk, distill_nearly_clean_chunk):
+    """adjust_key_and_value_for_inference, dit_module.py:933-946. Returns (key, value)."""
+    if has_inference_params and (extract_prefix_video_feature or fwd_extra_1st_chunk or slice_point > 0):
+        key_and_value = full_adjust_key_and_value(cache, key_and_value, slice_point, clip_token_nums, max_batch_size,
+                                                  update_kv_cache, distill_nearly_clean_chunk)
+    return key_and_value[..., :128].copy(), key_and_value[..., 128:].copy()
+
+
+# ----------------------------------------------------------------------------------------------- attention
+def _attend(q: np.ndarray, k: np.ndarray, v: np.ndarray, scale: float) -> Tuple[np.ndarray, np.ndarray]:
+    """softmax(q k^T * scale) v for q (Lq, Hq, D), k/v (Lk, Hkv, D) with GQA; fp32. Returns (out, lse)."""
+    Lq, Hq, D = q.shape
+    Lk, Hkv, _ = k.shape
+    g = Hq // Hkv
+    out = np.zeros((Lq, Hq, D), dtype=F32)
+    lse = np.full((Lq, Hq), -np.inf, dtype=F32)
+    if Lk == 0 or Lq == 0:
+        return out, lse
+    for h in range(Hq):
+        s = (q[:, h, :].astype(F32) @ k[:, h // g, :].astype(F32).T) * F32(scale)
+        m = s.max(axis=-1, keepdims=True)
+        p = np.exp(s - m)
+        l = p.sum(axis=-1, keepdims=True, dtype=F32)
+        out[:, h, :] = (p / l) @ v[:, h // g, :].astype(F32)
+        lse[:, h] = (m + np.log(l))[:, 0]
+    return out, lse
+
+
+def attn_ranges(q, k, v, q_ranges, k_ranges, softmax_scale: Optional[float] = None,
+                round_output: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+    """Range-masked attention = the reference's fallback loop, dit_module.py:1052-1065 (bs == 1), which is also the
+    contract of flex_flash_attn_func with disjoint q ranges (dit_module.py:1032-1043).
+    q (Tq, Hq, 128), k/v (Tk, Hkv, 128); ranges (n, 2). Uncovered rows: out 0, lse -inf."""
+    D = q.shape[-1]
+    scale = softmax_scale if softmax_scale is not None else 1.0 / math.sqrt(D)
+    out = np.zeros(q.shape, dtype=F32)
+    lse = np.full(q.shape[:2], -np.inf, dtype=F32)
+    for (q0, q1), (k0, k1) in zip(np.asarray(q_ranges).reshape(-1, 2), np.asarray(k_ranges).reshape(-1, 2)):
+        q0, q1, k0, k1 = int(q0), int(q1), int(k0), int(k1)
+        if q1 <= q0:
+            continue
+        o, l = _attend(q[q0:q1], k[k0:k1], v[k0:k1], scale)
+        out[q0:q1] = o
+        lse[q0:q1] = l
+    return (bf16_round(out) if round_output else out), lse
+
+
+def core_attention(query, key, value, bs: int, np_q_range, np_k_range, denoising_range_num: int) -> np.ndarray:
+    """core_attention, dit_module.py:1023-1066 (fallback branch). query (sq*b, Hq, 128) in "(sq b)" order.
+    Returns (sq*b, Hq, 128) in "(sq b)" order, bf16-rounded."""
+    assert not (bs > 1 and denoising_range_num > 1)  # dit_module.py:1048
+    Hq = query.shape[1]
+    qb = np.transpose(query.reshape(-1, bs, Hq, 128), (1, 0, 2, 3))               # b sq hn hd
+    kb = np.transpose(key.reshape(-1, bs, key.shape[1], 128), (1, 0, 2, 3))
+    vb = np.transpose(value.reshape(-1, bs, value.shape[1], 128), (1, 0, 2, 3))
+    outs = []
+    for i in range(denoising_range_num):
+        j = i if bs == 1 else 0
+        q0, q1 = int(np_q_range[j, 0]), int(np_q_range[j, 1])
+        k0, k1 = int(np_k_range[j, 0]), int(np_k_range[j, 1])
+        per_b = []
+        for b in range(bs):
+            o, _ = _attend(qb[b, q0:q1], kb[b, k0:k1], vb[b, k0:k1], 1.0 / math.sqrt(128))
+            per_b.append(bf16_round(o))
+        o = np.stack(per_b, axis=0)                                               # b sq h d
+        outs.append(np.transpose(o, (1, 0, 2, 3)).reshape(-1, Hq, 128))           # (sq b) h d
+    return np.concatenate(outs, axis=0)
+
+
+def attn_varlen(q, k, v, cu_seqlens_q, cu_seqlens_k, softmax_scale: Optional[float] = None) -> np.ndarray:
+    """flash_attn_varlen_func as used by cross_attention, dit_module.py:1124-1133: segment i of q attends to segment
+    i of k. A zero-length key segment yields zeros."""
+    cu_q = np.asarray(cu_seqlens_q).astype(np.int64)
+    cu_k = np.asarray(cu_seqlens_k).astype(np.int64)
+    qr = np.stack([cu_q[:-1], cu_q[1:]], axis=1)
+    kr = np.stack([cu_k[:-1], cu_k[1:]], axis=1)
+    out, _ = attn_ranges(q, k, v, qr, kr, softmax_scale)
+    return out
+
+
+def lse_merge(out_a, lse_a, out_b, lse_b) -> Tuple[np.ndarray, np.ndarray]:
+    """Merge of two partial softmax-attention results over disjoint key sets (ring-KV step; new capability, the
+    reference has no ring attention). Mathematical identity: softmax over the union."""
+    mx = np.maximum(lse_a, lse_b)
+    safe = np.where(np.isfinite(mx), mx, 0.0)
+    ea, eb = np.exp(lse_a - safe), np.exp(lse_b - safe)
+    den = ea + eb
+    ok = den > 0
+    wa = np.where(ok, ea / np.where(ok, den, 1), 0.0).astype(F32)
+    wb = np.where(ok, eb / np.where(ok, den, 1), 0.0).astype(F32)
+    out = out_a.astype(F32) * wa[..., None] + out_b.astype(F32) * wb[..., None]
+    lse = np.where(ok, safe + np.log(np.where(ok, den, 1)), -np.inf).astype(F32)
+    return bf16_round(out), lse
+
+
+# ----------------------------------------------------------------------------------------------- ranges / schedule
+def generate_sequences(chunk_num: int, window_size: int, chunk_offset: int):
+    """generate_sequences, inference/pipeline/video_generate.py:164-180."""
+    start_index = chunk_offset
+    end_index = chunk_num + window_size - 1
+    clip_start = [max(chunk_offset, i - window_size + 1) for i in range(start_index, end_index)]
+    clip_end = [min(chunk_num, i + 1) for i in range(start_index, end_index)]
+    t_start = [max(0, i - chunk_num + 1) for i in range(start_index, end_index)]
+    t_end = [min(window_size, i - chunk_offset + 1) if i - chunk_offset < window_size else window_size
+             for i in range(start_index, end_index)]
+    return clip_start, clip_end, t_start, t_end
+
+
+def generate_default_kvrange(slice_point: int, denoising_range_num: int, batch_size: int,
+                             chunk_token_nums: int) -> np.ndarray:
+    """generate_default_kvrange, video_generate.py:454-465."""
+    range_num = slice_point + denoising_range_num
+    rows = []
+    for i in range(batch_size):
+        for j in range(denoising_range_num):
+            rows.append([i * range_num, slice_point + 1 + j + i * range_num])
+    return (np.asarray(rows, dtype=np.int32) * chunk_token_nums).astype(np.int32)
+
+
+def generate_noise2clean_kvrange(slice_point: int, denoising_range_num: int, noise2clean_kvrange: Sequence[int],
+                                 clean_chunk_kvrange: int, denoise_step_of_each_chunk: Sequence[int], num_steps: int,
+                                 batch_size: int, chunk_token_nums: int) -> np.ndarray:
+    """generate_noise2clean_kvrange, video_generate.py:467-508."""
+    assert len(denoise_step_of_each_chunk) == denoising_range_num and len(noise2clean_kvrange) > 0
+    if clean_chunk_kvrange == -1:
+        clean_chunk_kvrange = noise2clean_kvrange[-1]
+    assert num_steps % len(noise2clean_kvrange) == 0
+    per_stage = num_steps // len(noise2clean_kvrange)
+    widths = [clean_chunk_kvrange if s == num_steps else noise2clean_kvrange[s // per_stage]
+              for s in denoise_step_of_each_chunk]
+    range_num = slice_point + denoising_range_num
+    rows = []
+    for i in range(batch_size):
+        base = i * range_num
+        for j in range(denoising_range_num):
+            end = slice_point + j + 1
+            start = max(0, end - widths[j])
+            rows.append([(base + start) * chunk_token_nums, (base + end) * chunk_token_nums])
+    return np.asarray(rows, dtype=np.int32)
+
+
+def core_q_ranges(clip_token_nums: int, denoising_range_num: int, batch_size: int) -> np.ndarray:
+    """q_range construction, dit_model.py:220-246: consecutive clips of clip_token_nums."""
+    cu = np.arange(0, denoising_range_num * batch_size + 1, dtype=np.int64) * clip_token_nums
+    return np.stack([cu[:-1], cu[1:]], axis=1).astype(np.int32)
+
+
+def cross_attn_params(clip_token_nums: int, denoising_range_num: int, batch_size: int, y_index: Sequence[int]):
+    """cu_seqlens / ranges of the cross-attention, dit_model.py:215-241. y_index = valid caption tokens per
+    (batch x chunk). Returns dict(q_ranges, kv_ranges, cu_seqlens_q, cu_seqlens_kv)."""
+    cu_q = np.concatenate([[0], np.full(denoising_range_num * batch_size, clip_token_nums)]).cumsum().astype(np.int32)
+    cu_k = np.concatenate([[0], np.asarray(y_index)]).cumsum().astype(np.int32)
+    return dict(q_ranges=np.stack([cu_q[:-1], cu_q[1:]], 1), kv_ranges=np.stack([cu_k[:-1], cu_k[1:]], 1),
+                cu_seqlens_q=cu_q, cu_seqlens_kv=cu_k)
+
+
+def max_seqlen_k(kv_range: np.ndarray) -> int:
+    """dit_model.py:247-248: unique(kv_range)[-1] - unique(kv_range)[0]."""
+    u = np.unique(kv_range)
+    return int(u[-1] - u[0])
+
+
+# ----------------------------------------------------------------------------------------------- context parallel
+def cp_split_sizes(seq_len: int, cp_size: int) -> List[int]:
+    """cp_ulysses_process Part1, context_parallel.py:240-242."""
+    sizes = [seq_len // cp_size] * cp_size
+    for i in range(seq_len % cp_size):
+        sizes[i] += 1
+    return sizes
+
+
+def scatter_to_cp_region(x: np.ndarray, split_sizes: Sequence[int], rank: int) -> np.ndarray:
+    """scatter_to_context_parallel_region (cp_shuffle_num == 1), context_parallel.py:50-52."""
+    off = sum(split_sizes[:rank])
+    return x[off:off + split_sizes[rank]].copy()
+
+
+def cp_update_cross_attn_qkv_range(cu_seqlens_q, cu_seqlens_k, batch_size: int, split_sizes: Sequence[int],
+                                   cp_rank: int):
+    """cp_update_cross_attn_qkv_range (cp_shuffle_num == 1, cp_pad_size == 0), context_parallel.py:134-224.
+    Returns dict(q_ranges, kv_ranges, cu_seqlens_q, cu_seqlens_kv, max_seqlen_q)."""
+    sizes = np.asarray(split_sizes, dtype=np.int64)
+    bounds = np.concatenate([[0], sizes.cumsum()])
+    total = int(bounds[-1])
+    cu_q = np.asarray(cu_seqlens_q, dtype=np.int64)
+    cu_k = np.asarray(cu_seqlens_k, dtype=np.int64)
+    qs, qe = cu_q[:-1], cu_q[1:]
+    xq, xk = [], []
+    for i in range(batch_size):
+        b = bounds + i * total
+        s, e = b[cp_rank], b[cp_rank + 1]
+        st, en = np.maximum(s, qs), np.minimum(e, qe)
+        m = st < en
+        part_q = np.stack([st[m], en[m]], axis=1)
+        part_q = part_q - part_q[:, 0].min()
+        xq.append(part_q)
+        xk.append(np.stack([cu_k[:-1][m], cu_k[1:][m]], axis=1))
+    offs = np.concatenate([[0], np.cumsum([r[-1, -1] for r in xq])[:-1]])
+    q_ranges = np.concatenate([r + int(o) for r, o in zip(xq, offs)], axis=0).astype(np.int32)
+    k_ranges = np.concatenate(xk, axis=0).astype(np.int32)
+    return dict(q_ranges=q_ranges, kv_ranges=k_ranges, cu_seqlens_q=np.unique(q_ranges).astype(np.int32),
+                cu_seqlens_kv=np.unique(k_ranges).astype(np.int32), max_seqlen_q=int(split_sizes[cp_rank]))
+
+
+def ulysses_input_split(per_rank: List[np.ndarray], split_sizes: Sequence[int]) -> List[np.ndarray]:
+    """all_to_all_input_split as index math, context_parallel.py:381-401. per_rank[r]: (seq_r, H, hd) with
+    seq_r == split_sizes[r]. Returns per-rank (sum(split_sizes), H/cp, hd): all tokens, local heads.
+    KV heads are replicated when cp % H == 0 and cp != H (context_parallel.py:393-394)."""
+    cp = len(per_rank)
+    outs = []
+    for dst in range(cp):
+        blocks = []
+        for src in range(cp):
+            t = per_rank[src]
+            hn = t.shape[1]
+            if cp % hn == 0 and cp != hn:
+                t = np.repeat(t, cp // hn, axis=1)
+            hl = t.shape[1] // cp
+            blocks.append(t[:, dst * hl:(dst + 1) * hl])
+        outs.append(np.concatenate(blocks, axis=0))
+    return outs
+
+
+def ulysses_output_split(per_rank: List[np.ndarray], split_sizes: Sequence[int]) -> List[np.ndarray]:
+    """all_to_all_output_split followed by "(cp sq) hn hd -> sq (cp hn) hd", context_parallel.py:404-423, 596
+    (batch folded into sq). per_rank[r]: (sum(split_sizes), hn, hd). Returns per-rank (split_sizes[r], cp*hn, hd)."""
+    cp = len(per_rank)
+    bounds = np.concatenate([[0], np.cumsum(split_sizes)])
+    outs = []
+    for dst in range(cp):
+        s, e = int(bounds[dst]), int(bounds[dst + 1])
+        outs.append(np.concatenate([per_rank[src][s:e] for src in range(cp)], axis=1))
+    return outs
+
+
+# ----------------------------------------------------------------------------------------------- RoPE table
+def rope_table(T_total: int, H: int, W: int, bands: Optional[np.ndarray] = None, keep_last_T: Optional[int] = None):
+    """LearnableRotaryEmbeddingCat.get_embed as used at dit_model.py:163-166 (in_pixels=False, dim=128):
+    bands = 1/10000^(arange(16)/16) (dit_module.py:591-596); t = arange, h/w centred (dit_module.py:644-647) and
+    rescaled x/(f-1)*(r-1) with r = H/sqrt(HW/256) (dit_module.py:648-659, dit_model.py:163-164).
+    Returns (sin, cos), each (rows, 48); rows = last keep_last_T*H*W rows (dit_model.py:166)."""
+    if bands is None:
+        bands = (1.0 / (10000.0 ** (np.arange(16, dtype=F32) / F32(16)))).astype(F32)
+    rescale = math.sqrt((H * W) / (16 * 16))
+    feat = [T_total, H, W]
+    ref = [T_total, H / rescale, W / rescale]
+    t = [np.arange(s, dtype=F32) for s in feat]
+    t[1] = t[1] - F32((feat[1] - 1) / 2)
+    t[2] = t[2] - F32((feat[2] - 1) / 2)
+    tr = []
+    for x, f, r in zip(t, feat, ref):
+        tr.append(x if f == 1 else (x / F32(f - 1) * F32(r - 1)).astype(F32))
+    grid = np.stack(np.meshgrid(*tr, indexing="ij"), axis=-1)[..., None].astype(F32)  # T H W 3 1
+    pos = grid * bands.astype(F32)                                                    # T H W 3 16
+    sin = np.sin(pos).reshape(T_total * H * W, -1).astype(F32)
+    cos = np.cos(pos).reshape(T_total * H * W, -1).astype(F32)
+    if keep_last_T is not None:
+        n = keep_last_T * H * W
+        sin, cos = sin[-n:], cos[-n:]
+    return sin, cos

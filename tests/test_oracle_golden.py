@@ -1,0 +1,235 @@
+"""Pins the CPU oracle (oracle/magi_oracle.py) against fixtures produced by the reference's own Python code
+(oracle/gen_golden.py, run in the authoring container). CPU only."""
+import numpy as np
+import pytest
+
+import magi_oracle as O
+from golden_io import Golden, f32
+
+BF16_ULP = 2.0 ** -7  # upper bound of the relative spacing of bf16 (8 significand bits)
+
+
+def close_bf16(a, b, ulps=1.0, atol=1e-6):
+    """|a - b| within `ulps` bf16 ulp of the larger magnitude (both sides hold bf16-rounded values)."""
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    tol = np.maximum(np.abs(a), np.abs(b)) * BF16_ULP * ulps + atol
+    bad = np.abs(a - b) > tol
+    return not bad.any(), float(np.abs(a - b).max()), int(bad.sum())
+
+
+@pytest.fixture(scope="module")
+def g():
+    return Golden("attention_single_rank.npz")
+
+
+STEPS = ["A", "B", "C", "D", "E"]
+
+
+def _meta(g, s):
+    sp, dn, bs, upd, extra, ncc, has_inf = [int(x) for x in g[f"{s}.meta"]]
+    return dict(slice_point=sp, dn=dn, bs=bs, update=bool(upd), fwd_extra=bool(extra), distill_ncc=bool(ncc),
+                has_inf=bool(has_inf))
+
+
+@pytest.mark.parametrize("s", STEPS)
+def test_prologue_q_kv_match_reference(g, s):
+    """get_q / get_kv (dit_module.py:953-996) incl. fp32 LayerNorm(+1p), NeoX RoPE on 96 dims, bf16 rounding."""
+    rope = g[f"{s}.rope"]
+    sin, cos = rope[:, :48], rope[:, 48:]
+    Hq, Hkv = g[f"{s}.q"].shape[1], g[f"{s}.kv"].shape[1]
+    q = O.get_q_or_k(g[f"{s}.lin_q"], Hq, g["w.q_layernorm.weight"], g["w.q_layernorm.bias"], sin, cos)
+    kv = O.get_kv(g[f"{s}.lin_k"], g[f"{s}.lin_v"], Hkv, g["w.k_layernorm.weight"], g["w.k_layernorm.bias"], sin, cos)
+    ok, err, nbad = close_bf16(q, g[f"{s}.q"])
+    assert ok, f"q: max err {err}, {nbad} elements beyond 1 bf16 ulp"
+    ok, err, nbad = close_bf16(kv, g[f"{s}.kv"])
+    assert ok, f"kv: max err {err}, {nbad} elements beyond 1 bf16 ulp"
+    # V half is a pure re-layout: bit exact
+    assert np.array_equal(kv[..., 128:], g[f"{s}.kv"][..., 128:])
+
+
+@pytest.mark.parametrize("s", STEPS)
+def test_xattn_layernorms_match_reference(g, s):
+    """get_xqkv (dit_module.py:1005-1021): bf16-parameter LayerNorms, "(sq b) -> (b sq)" re-layout, no RoPE."""
+    m = _meta(g, s)
+    lin_qx = g[f"{s}.lin_qx"]                                     # (sq, b, Hq*128)
+    sq, b, _ = lin_qx.shape
+    Hq = g[f"{s}.xq"].shape[1]
+    x = np.transpose(lin_qx.reshape(sq, b, Hq, 128), (1, 0, 2, 3)).reshape(b * sq, Hq, 128)
+    xq = O.xattn_layer_norm(x, g["w.q_layernorm_xattn.weight"], g["w.q_layernorm_xattn.bias"])
+    ok, err, nbad = close_bf16(xq, g[f"{s}.xq"])
+    assert ok, f"xq: max err {err}, {nbad} bad"
+    # text K: linear_kv_xattn -> (ytot, Hkv, 256) -> K half -> LayerNorm
+    kvs = g[f"{s}.key_value_states"]
+    if kvs.shape[0] == 0:
+        return
+    w = g["w.linear_kv_xattn.weight"]
+    mixed = O.bf16_round(kvs @ w.T)                               # bf16 GEMM output (fp32 accumulate)
+    Hkv = g[f"{s}.xk"].shape[1]
+    mixed = mixed.reshape(kvs.shape[0], Hkv, 256)
+    xk = O.xattn_layer_norm(mixed[..., :128], g["w.k_layernorm_xattn.weight"], g["w.k_layernorm_xattn.bias"])
+    # the GEMM accumulation order differs between numpy and ATen: allow a couple of ulps through the LayerNorm
+    ok, err, nbad = close_bf16(xk, g[f"{s}.xk"], ulps=4.0, atol=2e-2)
+    assert ok, f"xk: max err {err}, {nbad} bad"
+
+
+def test_kv_cache_sequence_and_core_attention(g):
+    """Replays steps A-D through the oracle's KV-cache restatement (dit_module.py:891-946) and range attention
+    (dit_module.py:1046-1065) and compares cache contents and core_attn_out with the reference's."""
+    clip = int(g["clip"])
+    cache = np.zeros((4 * clip, 2, 256), dtype=np.float32)
+    for s in ["A", "B", "C", "D"]:
+        m = _meta(g, s)
+        kv_new = g[f"{s}.kv"]
+        key, value = O.adjust_key_and_value_for_inference(
+            kv_new, cache, m["has_inf"], m["slice_point"], clip, 1, m["update"], False, m["fwd_extra"],
+            m["distill_ncc"])
+        if f"{s}.cache_after" in g:
+            assert np.array_equal(cache, g[f"{s}.cache_after"]), f"step {s}: cache contents differ"
+        out = O.core_attention(g[f"{s}.q"], key, value, m["bs"], g[f"{s}.q_range"], g[f"{s}.k_range"], m["dn"])
+        ref = g[f"{s}.core_attn_out"].reshape(out.shape)
+        ok, err, nbad = close_bf16(out, ref, ulps=2.0, atol=2e-3)
+        assert ok, f"step {s}: core_attn_out max err {err}, {nbad} bad"
+
+
+def test_core_attention_batched_uncond_pass(g):
+    """Step E: bs = 2, one range, no inference params (3-CFG uncond pass, dit_model.py:470-491)."""
+    m = _meta(g, "E")
+    kv = g["E.kv"]
+    out = O.core_attention(g["E.q"], kv[..., :128], kv[..., 128:], m["bs"], g["E.q_range"], g["E.k_range"], m["dn"])
+    ok, err, nbad = close_bf16(out, g["E.core_attn_out"].reshape(out.shape), ulps=2.0, atol=2e-3)
+    assert ok, f"max err {err}, {nbad} bad"
+
+
+@pytest.mark.parametrize("s", STEPS)
+def test_cross_attention_matches_reference(g, s):
+    """cross_attention (dit_module.py:1098-1136) incl. a zero-length caption segment (step B) -> zeros."""
+    m = _meta(g, s)
+    xq, xk, xv = g[f"{s}.xq"], g[f"{s}.xk"], g[f"{s}.xv"]
+    clip = int(g["clip"])
+    p = O.cross_attn_params(clip, m["dn"], m["bs"], g[f"{s}.y_index"])
+    out = O.attn_varlen(xq, xk, xv, p["cu_seqlens_q"], p["cu_seqlens_kv"])           # (b sq) hn hd
+    sq = xq.shape[0] // m["bs"]
+    out = np.transpose(out.reshape(m["bs"], sq, -1), (1, 0, 2))                       # sq b (hn hd)
+    ok, err, nbad = close_bf16(out, g[f"{s}.xattn_out"], ulps=2.0, atol=2e-3)
+    assert ok, f"step {s}: xattn_out max err {err}, {nbad} bad"
+    if s == "B":   # first chunk has no caption tokens
+        assert np.all(g["B.xattn_out"][:clip] == 0) and np.all(out[:clip] == 0)
+
+
+def test_rope_table_matches_reference_builder(g):
+    """The reference's build_rotary_pos_embed (dit_module.py:599-717) with the dit_model.py:163-166 recipe."""
+    for s, (T_total, keep) in {"A": (6, 6), "C": (9, 6), "D": (12, 9)}.items():
+        sin, cos = O.rope_table(T_total, 4, 4, keep_last_T=keep)
+        rope = g[f"{s}.rope"]
+        np.testing.assert_allclose(sin, rope[:, :48], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(cos, rope[:, 48:], rtol=0, atol=2e-6)
+
+
+# ----------------------------------------------------------------------------------------------- ranges / schedule
+def test_generate_sequences_and_kv_ranges():
+    r = Golden("ranges.npz")
+    i = 0
+    while f"seq{i}.args" in r:
+        cn, ws, off = [int(x) for x in r[f"seq{i}.args"]]
+        got = np.array(O.generate_sequences(cn, ws, off))
+        assert np.array_equal(got, r[f"seq{i}.out"]), (cn, ws, off)
+        i += 1
+    assert i >= 5
+    i = 0
+    while f"kv{i}.args" in r:
+        a = [int(x) for x in r[f"kv{i}.args"]]
+        sp, dn, bs, steps = a[0], a[1], a[2], a[3:]
+        n2c = O.generate_noise2clean_kvrange(sp, dn, [5, 4, 3, 2], 1, steps, 64, bs, 9360)
+        assert np.array_equal(n2c, r[f"kv{i}.noise2clean"]), a
+        assert np.array_equal(O.generate_default_kvrange(sp, dn, bs, 9360), r[f"kv{i}.default"]), a
+        i += 1
+    assert i >= 4
+
+
+def test_reference_examples_in_comments():
+    """The worked examples in the reference's own comments, video_generate.py:139-161."""
+    assert O.generate_sequences(8, 4, 0)[0] == [0, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7]
+    assert O.generate_sequences(8, 4, 0)[1] == [1, 2, 3, 4, 5, 6, 7, 8, 8, 8, 8]
+    assert O.generate_sequences(8, 4, 2)[3] == [1, 2, 3, 4, 4, 4, 4, 4, 4]
+    assert O.generate_sequences(8, 1, 0)[2] == [0] * 8
+
+
+# ----------------------------------------------------------------------------------------------- context parallel
+@pytest.mark.parametrize("tag,cp", [("cp2", 2), ("cp4", 4)])
+def test_ulysses_movement_and_range_rewrite(tag, cp):
+    ranks = [Golden(f"ulysses_{tag}_rank{r}.npz") for r in range(cp)]
+    r0 = ranks[0]
+    clip = int(r0["clip"])
+    S = r0["hidden_states"].shape[0]
+    sizes = O.cp_split_sizes(S, cp)
+    for r, gr in enumerate(ranks):
+        assert list(gr["split_sizes"]) == sizes
+        # scatter (context_parallel.py:29-53)
+        assert np.array_equal(O.scatter_to_cp_region(r0["hidden_states"], sizes, r), gr["x_local"])
+        assert np.array_equal(O.scatter_to_cp_region(r0["rope"], sizes, r), gr["rope_local"])
+        # per-rank cross-attention ranges (context_parallel.py:134-224)
+        full = O.cross_attn_params(clip, 3, 1, r0["y_index"])
+        got = O.cp_update_cross_attn_qkv_range(full["cu_seqlens_q"], full["cu_seqlens_kv"], 1, sizes, r)
+        assert np.array_equal(got["q_ranges"], gr["cross.q_ranges"])
+        assert np.array_equal(got["kv_ranges"], gr["cross.kv_ranges"])
+        assert np.array_equal(got["cu_seqlens_q"], gr["cross.cu_seqlens_q"])
+        assert np.array_equal(got["cu_seqlens_kv"], gr["cross.cu_seqlens_kv"])
+        assert got["max_seqlen_q"] == int(gr["cross.max_seqlen_q"])
+    # all-to-all movement as index math (context_parallel.py:381-423, 596)
+    a_in = O.ulysses_input_split([gr["probe"] for gr in ranks], sizes)
+    kv_in = O.ulysses_input_split([gr["kvprobe"] for gr in ranks], sizes)
+    for r, gr in enumerate(ranks):
+        assert np.array_equal(a_in[r], gr["a2a_in"])
+        assert np.array_equal(kv_in[r], gr["kv_in"])       # cp4: Hkv=2 < cp -> replicated heads
+    back = O.ulysses_output_split(a_in, sizes)
+    for r, gr in enumerate(ranks):
+        hn = gr["a2a_in"].shape[1]
+        ref = gr["a2a_out"].reshape(cp, sizes[r], hn, -1).transpose(1, 0, 2, 3).reshape(sizes[r], cp * hn, -1)
+        assert np.array_equal(back[r], ref)
+        assert np.array_equal(back[r], gr["probe"])         # round trip restores the local tensor
+
+
+@pytest.mark.parametrize("tag,cp", [("cp2", 2), ("cp4", 4)])
+def test_ulysses_attention_equals_single_rank_oracle(tag, cp):
+    """O3: the reference's cp_ulysses forward (gloo, its own scheduler) == single-rank math on the gathered input."""
+    ranks = [Golden(f"ulysses_{tag}_rank{r}.npz") for r in range(cp)]
+    r0 = ranks[0]
+    Hq, Hkv = [int(x) for x in r0["heads"]]
+    clip = int(r0["clip"])
+    hs = r0["hidden_states"]                                      # (S, 1, hidden)
+    S = hs.shape[0]
+
+    def ln(x, w, b):
+        return O.bf16_round(O.layer_norm(x, w, b, 1e-6, zero_centered_gamma=False))
+
+    mixed = ln(hs, r0["w.linear_qkv.layer_norm.weight"], r0["w.linear_qkv.layer_norm.bias"])
+    lin = {n: O.bf16_round(mixed @ r0[f"w.linear_qkv.{n}.weight"].T) for n in ("q", "k", "v")}
+    rope = r0["rope"]
+    sin, cos = rope[:, :48], rope[:, 48:]
+    q = O.get_q_or_k(lin["q"], Hq, r0["w.q_layernorm.weight"], r0["w.q_layernorm.bias"], sin, cos)
+    kv = O.get_kv(lin["k"], lin["v"], Hkv, r0["w.k_layernorm.weight"], r0["w.k_layernorm.bias"], sin, cos)
+    q_range = O.core_q_ranges(clip, 3, 1)
+    out = O.core_attention(q, kv[..., :128], kv[..., 128:], 1, q_range, r0["k_range"], 3).reshape(S, 1, -1)
+    gathered = np.concatenate([gr["core_attn_out"] for gr in ranks], axis=0)
+    assert np.array_equal(ranks[0]["gathered"], gathered)        # gather_from_context_parallel_region
+    # projections were recomputed with numpy GEMMs: tolerance covers bf16 re-rounding of the GEMM outputs
+    err = np.abs(out - gathered).max()
+    rel = np.linalg.norm(out - gathered) / np.linalg.norm(gathered)
+    assert err < 6e-2 and rel < 1.5e-2, (err, rel)
+
+
+def test_lse_merge_is_softmax_over_union():
+    rng = np.random.default_rng(0)
+    q = rng.standard_normal((40, 4, 128)).astype(np.float32)
+    k = rng.standard_normal((90, 2, 128)).astype(np.float32)
+    v = rng.standard_normal((90, 2, 128)).astype(np.float32)
+    full, lse = O.attn_ranges(q, k, v, [[0, 40]], [[0, 90]], round_output=False)
+    a, la = O.attn_ranges(q, k, v, [[0, 40]], [[0, 33]], round_output=False)
+    b, lb = O.attn_ranges(q, k, v, [[0, 40]], [[33, 90]], round_output=False)
+    m, lm = O.lse_merge(a, la, b, lb)
+    np.testing.assert_allclose(lm, lse, atol=1e-5)
+    np.testing.assert_allclose(m, O.bf16_round(full), atol=1e-2)
+    # empty partner is a no-op
+    e, le = O.attn_ranges(q, k, v, [[0, 40]], [[5, 5]], round_output=False)
+    m2, lm2 = O.lse_merge(a, la, e, le)
+    np.testing.assert_allclose(lm2, la, atol=0)
