@@ -8,7 +8,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmagi_attn.so")
+# MAGI_ATTN_LIB selects another build of the same library (kernel tuning variants, tools/bench_variants.py)
+LIB_PATH = os.environ.get("MAGI_ATTN_LIB") or os.path.join(_HERE, "libmagi_attn.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 # Every symbol include/magi_attn.h declares (checked by tests/test_abi.py against the header text).

@@ -239,9 +239,8 @@ int magi_qk_norm_rope_fwd(const magi_prologue_args* a, void* stream_) {
   p.cache_row_offset = a->cache_row_offset; p.cache_rows = a->cache_rows;
   p.head_perm_cp = cp;
 
-  const int per_row = (a->x_q ? a->num_heads_q : 0) + (a->x_k ? a->num_heads_kv : 0) + (a->x_v ? a->num_heads_kv : 0);
   int grid = 1;
-  if (int rc = grid_for(a->rows * per_row * 16, 256, &grid)) return rc;
+  if (int rc = grid_for(a->rows * 32, 256, &grid)) return rc;   // one warp per row, grid-stride
   MAGI_CUDA(magi::prologue_launch(p, a->ln_dtype == 1, grid, stream));
   g_launches++;
   return 0;

@@ -34,6 +34,16 @@ constexpr int kThreads = 384;
 constexpr uint32_t kIdescQK = make_idesc_bf16(128, 128, 0, 0);
 constexpr uint32_t kIdescPV = make_idesc_bf16(128, 128, 0, 1);
 constexpr float kRescaleThreshold = 8.0f; // log2 units: lazily rescale O only when the row max grew by > 2^8
+#ifndef MAGI_EMU_MOD
+#define MAGI_EMU_MOD 4                    // every MAGI_EMU_MOD-th column pair takes the polynomial exp2 (0 = never)
+#endif
+#ifndef MAGI_SOFTMAX_REGS
+#define MAGI_SOFTMAX_REGS 208   // 256 softmax threads x 208 + 128 issuer/producer/idle threads x 96 = 64 K registers
+#endif
+#ifndef MAGI_AUX_REGS
+#define MAGI_AUX_REGS 96
+#endif
+constexpr int kEmuMod = MAGI_EMU_MOD;
 
 struct Barriers {
   uint64_t q_full, q_empty;
@@ -101,24 +111,27 @@ __device__ __forceinline__ void tile_info(const Item& it, int j, int& seg, int& 
   }
 }
 
+// Descriptors differ only in their 14-bit start-address field, so the issuer keeps one base descriptor per operand
+// and adds a compile-time constant (in 16-byte units) per MMA.
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) { return make_smem_desc_sw128(addr, 16, 1024); }
+__device__ __forceinline__ uint64_t desc_v(uint32_t addr) { return make_smem_desc_sw128(addr, kBlkBytes, 1024); }
+
 // S[128 x 128] = Q[128 x 128(hd)] * K[128 x 128(hd)]^T ; both operands K-major, 128B-swizzled, two 64-wide blocks.
-__device__ __forceinline__ void issue_qk(uint32_t d_tmem, uint32_t q_addr, uint32_t k_addr) {
+__device__ __forceinline__ void issue_qk(uint32_t d_tmem, uint64_t q_desc, uint64_t k_desc) {
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks) {
-    const uint32_t off = (ks >> 2) * kBlkBytes + (ks & 3) * 32;
-    const uint64_t a = make_smem_desc_sw128(q_addr + off, 16, 1024);
-    const uint64_t b = make_smem_desc_sw128(k_addr + off, 16, 1024);
-    mma_ss(d_tmem, a, b, kIdescQK, ks > 0 ? 1u : 0u);
+    const uint64_t off = static_cast<uint64_t>(((ks >> 2) * kBlkBytes + (ks & 3) * 32) >> 4);
+    mma_ss(d_tmem, q_desc + off, k_desc + off, kIdescQK, ks > 0 ? 1u : 0u);
   }
 }
 
 // O[128 x 128(hd)] (+)= P[128 x 128(keys)] * V[128(keys) x 128(hd)] ; P from TMEM (bf16, 2 per column),
 // V is MN-major (head_dim contiguous): 8-key groups 1024 B apart (SBO), 64-wide hd blocks kBlkBytes apart (LBO).
-__device__ __forceinline__ void issue_pv(uint32_t d_tmem, uint32_t p_tmem, uint32_t v_addr, uint32_t accumulate) {
+__device__ __forceinline__ void issue_pv(uint32_t d_tmem, uint32_t p_tmem, uint64_t v_desc, uint32_t accumulate) {
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks) {
-    const uint64_t b = make_smem_desc_sw128(v_addr + ks * 2048, kBlkBytes, 1024);
-    mma_ts(d_tmem, p_tmem + ks * 8, b, kIdescPV, (accumulate | (ks > 0)) ? 1u : 0u);
+    mma_ts(d_tmem, p_tmem + ks * 8, v_desc + static_cast<uint64_t>((ks * 2048) >> 4), kIdescPV,
+           (accumulate | (ks > 0)) ? 1u : 0u);
   }
 }
 
@@ -193,9 +206,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&bar->s_full[t], 1);
-      mbar_init(&bar->p_full[t], kTileM);
+      mbar_init(&bar->p_full[t], kTileM / 32);   // one arrival per softmax warp
       mbar_init(&bar->o_full[t], 1);
-      mbar_init(&bar->o_free[t], kTileM);
+      mbar_init(&bar->o_free[t], kTileM / 32);
     }
     fence_barrier_init();
   }
@@ -218,6 +231,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   if (warp < 8) {
     // ====================================================================== softmax warpgroups
+    setmaxnreg_inc<MAGI_SOFTMAX_REGS>();
     const int t = warp >> 2;
     const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t tS = tmem_base + lane_sel + t * 128;
@@ -253,14 +267,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           for (int c = 0; c < 128; ++c)
             if (c >= nvalid) sr[c] = 0xff800000u;  // -inf
         }
-        float mx0 = __uint_as_float(sr[0]), mx1 = __uint_as_float(sr[1]);
-        float mx2 = __uint_as_float(sr[2]), mx3 = __uint_as_float(sr[3]);
+        float mx0 = fmax3(__uint_as_float(sr[0]), __uint_as_float(sr[1]), __uint_as_float(sr[2]));
+        float mx1 = fmax3(__uint_as_float(sr[3]), __uint_as_float(sr[4]), __uint_as_float(sr[5]));
+        float mx2 = fmaxf(__uint_as_float(sr[6]), __uint_as_float(sr[7]));
+        float mx3 = mx2;
 #pragma unroll
-        for (int c = 4; c < 128; c += 4) {
-          mx0 = fmaxf(mx0, __uint_as_float(sr[c + 0]));
-          mx1 = fmaxf(mx1, __uint_as_float(sr[c + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(sr[c + 2]));
-          mx3 = fmaxf(mx3, __uint_as_float(sr[c + 3]));
+        for (int c = 8; c < 128; c += 8) {
+          mx0 = fmax3(mx0, __uint_as_float(sr[c + 0]), __uint_as_float(sr[c + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3]));
+          mx2 = fmax3(mx2, __uint_as_float(sr[c + 4]), __uint_as_float(sr[c + 5]));
+          mx3 = fmax3(mx3, __uint_as_float(sr[c + 6]), __uint_as_float(sr[c + 7]));
         }
         const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
 
@@ -274,21 +290,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           m = mx;
         }
         const float neg_m = -m * scale_log2;
+        const uint64_t scale2 = pack_f2(scale_log2, scale_log2);
+        const uint64_t negm2 = pack_f2(neg_m, neg_m);
 
-        float sum0 = 0.f, sum1 = 0.f;
-        uint32_t pr[64];
+        uint64_t sum_a = pack_f2(0.f, 0.f), sum_b = sum_a;
+        // P overwrites S in place, in registers (pair k of a 64-column half lands in slot k of that half) and in
+        // TMEM; each half is stored as soon as it is complete so the store overlaps the second half's math.
 #pragma unroll
-        for (int c = 0; c < 128; c += 2) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c]), scale_log2, neg_m));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(sr[c + 1]), scale_log2, neg_m));
-          sum0 += p0;
-          sum1 += p1;
-          pr[c >> 1] = pack_bf16x2(p0, p1);
+        for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+          for (int c = 64 * hf; c < 64 * hf + 64; c += 2) {
+            const uint64_t x2 = ffma2(pack_f2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), scale2, negm2);
+            float x0, x1, p0, p1;
+            unpack_f2(x2, x0, x1);
+            const int pair = c >> 1;
+            if (kEmuMod > 0 && (pair % (kEmuMod > 0 ? kEmuMod : 1)) == (kEmuMod > 0 ? kEmuMod : 1) - 1) {
+              ex2_poly2(x0, x1, p0, p1);
+            } else {
+              p0 = ex2_approx(x0);
+              p1 = ex2_approx(x1);
+            }
+            const uint64_t p2 = pack_f2(p0, p1);
+            if (pair & 1) sum_b = fadd2(sum_b, p2); else sum_a = fadd2(sum_a, p2);
+            sr[64 * hf + ((c - 64 * hf) >> 1)] = pack_bf16x2(p0, p1);
+          }
+          MAGI_TMEM_ST32(tS + 32 * hf, sr, 64 * hf);
         }
-        l = l * alpha + (sum0 + sum1);
-
-        MAGI_TMEM_ST32(tS + 0, pr, 0);
-        MAGI_TMEM_ST32(tS + 32, pr, 32);
+        float s0, s1;
+        unpack_f2(fadd2(sum_a, sum_b), s0, s1);
+        l = l * alpha + (s0 + s1);
 
         if (__any_sync(0xffffffffu, need)) {
           // rare: this row's running max jumped by more than 2^8 -> bring O back into range before P*V accumulates
@@ -304,7 +334,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(&bar->p_full[t]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar->p_full[t]);
       }
 
       // ------------------------------------------------------------------ epilogue for this row
@@ -333,7 +364,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           }
         }
         tc_fence_before();
-        mbar_arrive(&bar->o_free[t]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar->o_free[t]);
         if (row_valid && p.lse != nullptr)
           p.lse[static_cast<int64_t>(row) * p.Hq + it.h] = (m * scale_log2 + log2f(l)) * 0.6931471805599453f;
       } else if (row_valid) {
@@ -345,9 +377,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
   } else if (warp == 8) {
     // ====================================================================== MMA issuer
+    setmaxnreg_dec<MAGI_AUX_REGS>();
     if (lane == 0) {
       const uint32_t tS0 = tmem_base, tS1 = tmem_base + 128, tO0 = tmem_base + 256, tO1 = tmem_base + 384;
-      const uint32_t q0_addr = smem_u32(smem_q), q1_addr = smem_u32(smem_q + kTileBytes);
+      const uint64_t q0_desc = desc_kmajor(smem_u32(smem_q)), q1_desc = desc_kmajor(smem_u32(smem_q + kTileBytes));
       const uint32_t kv_addr = smem_u32(smem_kv);
       uint32_t stage = 0, phase = 0;  // kv ring (consumer side)
       uint32_t p_phase0 = 0, p_phase1 = 0;
@@ -366,9 +399,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_fence_after();
         uint32_t kst = stage;
         advance();
-        issue_qk(tS0, q0_addr, kv_addr + kst * kTileBytes);
+        issue_qk(tS0, q0_desc, desc_kmajor(kv_addr + kst * kTileBytes));
         tc_commit(&bar->s_full[0]);
-        issue_qk(tS1, q1_addr, kv_addr + kst * kTileBytes);
+        issue_qk(tS1, q1_desc, desc_kmajor(kv_addr + kst * kTileBytes));
         tc_commit(&bar->s_full[1]);
         tc_commit(&bar->kv_empty[kst]);
         if (nt == 1) tc_commit(&bar->q_empty);
@@ -380,24 +413,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_wait(&bar->p_full[0], p_phase0);
         p_phase0 ^= 1;
         tc_fence_after();
-        issue_pv(tO0, tS0, kv_addr + vst * kTileBytes, 0);
+        issue_pv(tO0, tS0, desc_v(kv_addr + vst * kTileBytes), 0);
         for (int i = 1; i < nt; ++i) {
           // K_i -> S0(i)   (P0(i-1) already consumed by the in-order PV0(i-1))
           mbar_wait(&bar->kv_full[stage], phase);
           tc_fence_after();
           kst = stage;
           advance();
-          issue_qk(tS0, q0_addr, kv_addr + kst * kTileBytes);
+          issue_qk(tS0, q0_desc, desc_kmajor(kv_addr + kst * kTileBytes));
           tc_commit(&bar->s_full[0]);
           // O1 (+)= P1(i-1) V_{i-1}
           if (i == 1) mbar_wait(&bar->o_free[1], (item_cnt & 1) ^ 1);
           mbar_wait(&bar->p_full[1], p_phase1);
           p_phase1 ^= 1;
           tc_fence_after();
-          issue_pv(tO1, tS1, kv_addr + vst * kTileBytes, i > 1 ? 1u : 0u);
+          issue_pv(tO1, tS1, desc_v(kv_addr + vst * kTileBytes), i > 1 ? 1u : 0u);
           tc_commit(&bar->kv_empty[vst]);
           // S1(i)
-          issue_qk(tS1, q1_addr, kv_addr + kst * kTileBytes);
+          issue_qk(tS1, q1_desc, desc_kmajor(kv_addr + kst * kTileBytes));
           tc_commit(&bar->s_full[1]);
           tc_commit(&bar->kv_empty[kst]);
           if (i == nt - 1) tc_commit(&bar->q_empty);
@@ -408,7 +441,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           mbar_wait(&bar->p_full[0], p_phase0);
           p_phase0 ^= 1;
           tc_fence_after();
-          issue_pv(tO0, tS0, kv_addr + vst * kTileBytes, 1);
+          issue_pv(tO0, tS0, desc_v(kv_addr + vst * kTileBytes), 1);
         }
         tc_commit(&bar->o_full[0]);
         // O1 (+)= P1(nt-1) V_{nt-1}
@@ -416,7 +449,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_wait(&bar->p_full[1], p_phase1);
         p_phase1 ^= 1;
         tc_fence_after();
-        issue_pv(tO1, tS1, kv_addr + vst * kTileBytes, nt > 1 ? 1u : 0u);
+        issue_pv(tO1, tS1, desc_v(kv_addr + vst * kTileBytes), nt > 1 ? 1u : 0u);
         tc_commit(&bar->kv_empty[vst]);
         tc_commit(&bar->o_full[1]);
         ++item_cnt;
@@ -425,6 +458,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     __syncwarp();
   } else if (warp == 9) {
     // ====================================================================== TMA producer
+    setmaxnreg_dec<MAGI_AUX_REGS>();
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;  // kv ring (producer side)
       uint32_t item_cnt = 0;
@@ -459,6 +493,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
     }
     __syncwarp();
+  } else {
+    setmaxnreg_dec<MAGI_AUX_REGS>();   // idle warps of the third warpgroup (setmaxnreg is warpgroup-collective)
   }
 
   tc_fence_before();

@@ -204,6 +204,71 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// ---------------------------------------------------------------- packed fp32x2 math (sm_100: FFMA2 / FADD2 / FMNMX3)
+__device__ __forceinline__ uint64_t pack_f2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fsub2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2_rm(uint64_t a, uint64_t b) {  // round toward -inf
+  uint64_t d;
+  asm("add.rm.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// 2^x for a pair on the FMA/ALU pipes instead of the MUFU (Cody-Waite split + degree-3 polynomial on [0,1);
+// max relative error ~9e-5, well below the bf16 rounding of P). Valid for x in [-127, 127]; smaller x clamp to 2^-127.
+__device__ __forceinline__ void ex2_poly2(float x0, float x1, float& y0, float& y1) {
+  const float kMagic = 12582912.f;  // 2^23 + 2^22: adding it leaves floor(x) in the low mantissa bits
+  x0 = fmaxf(x0, -127.f);
+  x1 = fmaxf(x1, -127.f);
+  const uint64_t x = pack_f2(x0, x1);
+  const uint64_t magic = pack_f2(kMagic, kMagic);
+  const uint64_t xr = fadd2_rm(x, magic);
+  const uint64_t fl = fsub2(xr, magic);        // floor(x)
+  const uint64_t f = fsub2(x, fl);             // x - floor(x) in [0, 1)
+  uint64_t pz = ffma2(pack_f2(0.077119089663028717f, 0.077119089663028717f), f,
+                      pack_f2(0.227564394474029541f, 0.227564394474029541f));
+  pz = ffma2(pz, f, pack_f2(0.695146143436431885f, 0.695146143436431885f));
+  pz = ffma2(pz, f, pack_f2(1.0f, 1.0f));
+  float p0, p1, r0, r1;
+  unpack_f2(pz, p0, p1);
+  unpack_f2(xr, r0, r1);
+  y0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+  y1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
+}
+
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // pack two fp32 into bf16x2 (lo -> bits [0,16), hi -> bits [16,32)), round-to-nearest-even
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;

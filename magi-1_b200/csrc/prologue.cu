@@ -76,120 +76,132 @@ __device__ __forceinline__ void load_affine(const void* w, const void* b, int su
 
 }  // namespace
 
+// One warp owns one row (token): it streams that row's q heads, then k heads, then v heads, two heads per step (one
+// per half-warp, 16 lanes x 16 B = one 256-byte vector) and kUnroll steps in flight, so every lane keeps kUnroll
+// independent 16-byte loads outstanding. sin/cos of the row and the LayerNorm affine of the current tensor live in
+// registers for the whole row.
 template <bool kLnBf16>
-__global__ void __launch_bounds__(256) prologue_kernel(const PrologueParams p) {
+__global__ void __launch_bounds__(256, 3) prologue_kernel(const PrologueParams p) {
+  constexpr int kUnroll = 4;
   const int lane = threadIdx.x & 31;
   const int sub = lane & 15;   // 16-byte slot inside the 128-element vector
-  const int half = lane >> 4;  // which of the warp's two units
+  const int half = lane >> 4;  // which of the two heads of a step
   const int64_t warps_total = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   const int64_t warp_id = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int nq = p.x_q ? p.Hq : 0, nk = p.x_k ? p.Hkv : 0, nv = p.x_v ? p.Hkv : 0;
-  const int per_row = nq + nk + nv;
-  const int64_t units = p.rows * per_row;
   const int cp = p.head_perm_cp > 1 ? p.head_perm_cp : 1;
+  const bool rope = p.sin != nullptr;
+  const int partner = sub < 6 ? lane + 6 : (sub < 12 ? lane - 6 : lane);
+  const int dsub = sub < 6 ? sub : sub - 6;
 
-  for (int64_t base = warp_id * 2; base < units; base += warps_total * 2) {
-    const int64_t u = base + half;
-    const bool valid = u < units;
-    const int64_t r = valid ? u / per_row : 0;
-    const int hh = valid ? static_cast<int>(u - r * per_row) : 0;
-    int type, h;  // 0 = q, 1 = k, 2 = v
-    if (hh < nq) { type = 0; h = hh; }
-    else if (hh < nq + nk) { type = 1; h = hh - nq; }
-    else { type = 2; h = hh - nq - nk; }
-
-    const __nv_bfloat16* src =
-        type == 0 ? reinterpret_cast<const __nv_bfloat16*>(p.x_q) + r * p.xq_row_stride
-                  : type == 1 ? reinterpret_cast<const __nv_bfloat16*>(p.x_k) + r * p.xk_row_stride
-                              : reinterpret_cast<const __nv_bfloat16*>(p.x_v) + r * p.xv_row_stride;
-    const int64_t hstride = type == 0 ? p.xq_head_stride : type == 1 ? p.xk_head_stride : p.xv_head_stride;
-    uint4 raw = make_uint4(0, 0, 0, 0);
-    if (valid) raw = ld_stream(src + h * hstride + sub * 8);
-    float v[8];
-    unpack8(raw, v);
-
-    // ---- LayerNorm over 128 in fp32 (all lanes take part in the shuffles; V lanes discard the result)
-    float s = 0.f;
+  for (int64_t r = warp_id; r < p.rows; r += warps_total) {
+    float cs[8], sn[8];
+    if (rope && sub < 12) {
+      const int64_t trow = r / p.batch;
+      const float4* pc = reinterpret_cast<const float4*>(p.cos + trow * 48 + dsub * 8);
+      const float4* ps = reinterpret_cast<const float4*>(p.sin + trow * 48 + dsub * 8);
+      const float4 c0 = pc[0], c1 = pc[1], s0 = ps[0], s1 = ps[1];
+      cs[0] = c0.x; cs[1] = c0.y; cs[2] = c0.z; cs[3] = c0.w; cs[4] = c1.x; cs[5] = c1.y; cs[6] = c1.z; cs[7] = c1.w;
+      sn[0] = s0.x; sn[1] = s0.y; sn[2] = s0.z; sn[3] = s0.w; sn[4] = s1.x; sn[5] = s1.y; sn[6] = s1.z; sn[7] = s1.w;
+      if (sub < 6) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += v[i];
-    const float mean = half_warp_sum(s) * (1.0f / 128.0f);
-    float d[8], sq = 0.f;
+        for (int i = 0; i < 8; ++i) sn[i] = -sn[i];   // first half: x1*cos - x2*sin ; second half: x2*cos + x1*sin
+      }
+    } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { d[i] = v[i] - mean; sq += d[i] * d[i]; }
-    const float var = half_warp_sum(sq) * (1.0f / 128.0f);
-    const float rstd = 1.0f / sqrtf(var + p.eps);
-    float y[8];
-    if (type != 2) {
+      for (int i = 0; i < 8; ++i) { cs[i] = 1.f; sn[i] = 0.f; }
+    }
+
+#pragma unroll 1
+    for (int type = 0; type < 3; ++type) {  // 0 = q, 1 = k, 2 = v
+      const void* xbase = type == 0 ? p.x_q : type == 1 ? p.x_k : p.x_v;
+      if (xbase == nullptr) continue;
+      const int H = type == 0 ? p.Hq : p.Hkv;
+      const int64_t rstride = type == 0 ? p.xq_row_stride : type == 1 ? p.xk_row_stride : p.xv_row_stride;
+      const int64_t hstride = type == 0 ? p.xq_head_stride : type == 1 ? p.xk_head_stride : p.xv_head_stride;
+      const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(xbase) + r * rstride + sub * 8;
       float wf[8], bf[8];
-      load_affine<kLnBf16>(type == 0 ? p.ln_q_w : p.ln_k_w, type == 0 ? p.ln_q_b : p.ln_k_b, sub,
-                           p.zero_centered_gamma != 0, wf, bf);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] = d[i] * rstd * wf[i] + bf[i];
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] = v[i];
-    }
+      if (type != 2)
+        load_affine<kLnBf16>(type == 0 ? p.ln_q_w : p.ln_k_w, type == 0 ? p.ln_q_b : p.ln_k_b, sub,
+                             p.zero_centered_gamma != 0, wf, bf);
 
-    // ---- NeoX RoPE on dims [0,48) x [48,96): slots 0-5 pair with slots 6-11 (same half-warp)
-    if (p.sin != nullptr) {
-      const int partner = sub < 6 ? lane + 6 : (sub < 12 ? lane - 6 : lane);
-      float o[8];
+      for (int h0 = 0; h0 < H; h0 += 2 * kUnroll) {
+        uint4 raw[kUnroll];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = __shfl_sync(0xffffffffu, y[i], partner);
-      if (type != 2 && sub < 12) {
-        const int dsub = sub < 6 ? sub : sub - 6;
-        const int64_t trow = r / p.batch;
-        const float4* pc = reinterpret_cast<const float4*>(p.cos + trow * 48 + dsub * 8);
-        const float4* ps = reinterpret_cast<const float4*>(p.sin + trow * 48 + dsub * 8);
-        const float4 c0 = pc[0], c1 = pc[1], s0 = ps[0], s1 = ps[1];
-        const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-        const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-        if (sub < 6) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) y[i] = y[i] * cs[i] - o[i] * sn[i];
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) y[i] = y[i] * cs[i] + o[i] * sn[i];
+        for (int u = 0; u < kUnroll; ++u) {
+          const int h = h0 + 2 * u + half;
+          raw[u] = make_uint4(0, 0, 0, 0);
+          if (h < H) raw[u] = ld_stream(src + h * hstride);
         }
-      }
-    }
-    if (!valid) continue;
-    const uint4 packed = type == 2 ? raw : pack8(y);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int h = h0 + 2 * u + half;
+          if (h0 + 2 * u >= H) break;   // warp-uniform: both halves are past the last head
+          const bool valid = h < H;
+          uint4 packed = raw[u];
+          if (type != 2) {
+            float v[8];
+            unpack8(raw[u], v);
+            // ---- LayerNorm over 128 in fp32
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s += v[i];
+            const float mean = half_warp_sum(s) * (1.0f / 128.0f);
+            float sq = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { v[i] -= mean; sq += v[i] * v[i]; }
+            const float var = half_warp_sum(sq) * (1.0f / 128.0f);
+            const float rstd = 1.0f / sqrtf(var + p.eps);
+            float y[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) y[i] = v[i] * rstd * wf[i] + bf[i];
+            // ---- NeoX RoPE on dims [0,48) x [48,96): slots 0-5 pair with slots 6-11 of the same half-warp
+            if (rope) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float o = __shfl_sync(0xffffffffu, y[i], partner);
+                y[i] = y[i] * cs[i] + o * sn[i];
+              }
+            }
+            packed = pack8(y);
+          }
+          if (!valid) continue;
 
-    // ---- stores: attention (or all-to-all send) layout, plus the fused KV-cache append
-    if (type == 0) {
-      const int hn = p.Hq / cp;
-      const int64_t drow = static_cast<int64_t>(h / hn) * p.rows + r;
-      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.q_out) + drow * p.q_out_token_stride +
-                           static_cast<int64_t>(h % hn) * p.q_out_head_stride + sub * 8;
-      *reinterpret_cast<uint4*>(dst) = packed;
-    } else {
-      const int col = (type == 2 ? 128 : 0) + sub * 8;
-      if (cp > p.Hkv) {
-        // fewer kv heads than ranks: replicate (repeat_interleave, context_parallel.py:393-394)
-        const int rep = cp / p.Hkv;
-        for (int c = h * rep; c < (h + 1) * rep; ++c) {
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.kv_out) +
-                               (static_cast<int64_t>(c) * p.rows + r) * p.kv_out_token_stride + col;
-          *reinterpret_cast<uint4*>(dst) = packed;
+          // ---- stores: attention (or all-to-all send) layout, plus the fused KV-cache append
+          if (type == 0) {
+            const int hn = p.Hq / cp;
+            const int64_t drow = static_cast<int64_t>(h / hn) * p.rows + r;
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.q_out) + drow * p.q_out_token_stride +
+                                 static_cast<int64_t>(h % hn) * p.q_out_head_stride + sub * 8;
+            *reinterpret_cast<uint4*>(dst) = packed;
+          } else {
+            const int col = (type == 2 ? 128 : 0) + sub * 8;
+            if (cp > p.Hkv) {
+              // fewer kv heads than ranks: replicate (repeat_interleave, context_parallel.py:393-394)
+              const int rep = cp / p.Hkv;
+              for (int c = h * rep; c < (h + 1) * rep; ++c) {
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.kv_out) +
+                                     (static_cast<int64_t>(c) * p.rows + r) * p.kv_out_token_stride + col;
+                *reinterpret_cast<uint4*>(dst) = packed;
+              }
+            } else {
+              const int hn = p.Hkv / cp;
+              const int64_t drow = static_cast<int64_t>(h / hn) * p.rows + r;
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.kv_out) + drow * p.kv_out_token_stride +
+                                   static_cast<int64_t>(h % hn) * p.kv_out_head_stride + col;
+              *reinterpret_cast<uint4*>(dst) = packed;
+            }
+            if (p.cache != nullptr && r < p.cache_rows) {
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.cache) +
+                                   (p.cache_row_offset + r) * p.cache_token_stride +
+                                   static_cast<int64_t>(h) * p.cache_head_stride + col;
+              *reinterpret_cast<uint4*>(dst) = packed;
+            }
+          }
         }
-      } else {
-        const int hn = p.Hkv / cp;
-        const int64_t drow = static_cast<int64_t>(h / hn) * p.rows + r;
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.kv_out) + drow * p.kv_out_token_stride +
-                             static_cast<int64_t>(h % hn) * p.kv_out_head_stride + col;
-        *reinterpret_cast<uint4*>(dst) = packed;
-      }
-      if (p.cache != nullptr && r < p.cache_rows) {
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.cache) +
-                             (p.cache_row_offset + r) * p.cache_token_stride +
-                             static_cast<int64_t>(h) * p.cache_head_stride + col;
-        *reinterpret_cast<uint4*>(dst) = packed;
       }
     }
   }
 }
-
 
 // cache[row_offset + r, :] = kv[r, :]   (row_elems bf16 per row, multiple of 8)
 __global__ void __launch_bounds__(256) kv_append_kernel(__nv_bfloat16* __restrict__ cache, int64_t cache_stride,

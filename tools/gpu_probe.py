@@ -183,6 +183,40 @@ def q_bench_single():
     return True
 
 
+@case
+def r_bench_prologue():
+    """cfg2 shapes: 37440 rows x (24 q + 8 k + 8 v heads), KV-cache append of all rows."""
+    import torch
+    import magi_b200.functional as F
+    dev = "cuda"
+    S, Hq, Hkv = 37440, 24, 8
+    xq = torch.randn(S, Hq * 128, device=dev, dtype=torch.bfloat16)
+    xk = torch.randn(S, Hkv * 128, device=dev, dtype=torch.bfloat16)
+    xv = torch.randn(S, Hkv * 128, device=dev, dtype=torch.bfloat16)
+    ln = [torch.randn(128, device=dev) * 0.1 for _ in range(4)]
+    sin, cos = torch.randn(S, 48, device=dev), torch.randn(S, 48, device=dev)
+    cache = torch.empty(S, Hkv, 256, device=dev, dtype=torch.bfloat16)
+    q = torch.empty(S, Hq, 128, device=dev, dtype=torch.bfloat16)
+    kv = torch.empty(S, Hkv, 256, device=dev, dtype=torch.bfloat16)
+    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+    def run(cache_rows):
+        F.qk_norm_rope(xq, xk, xv, Hq, Hkv, (ln[0], ln[1]), (ln[2], ln[3]), sin, cos, q_out=q, kv_out=kv,
+                       cache=cache, cache_row_offset=0, cache_rows=cache_rows)
+    for cache_rows, nm in ((S, "with cache append"), (0, "no cache append")):
+        byts = S * (Hq + 2 * Hkv) * 128 * 4 + S * 96 * 4 + (cache_rows * Hkv * 256 * 2)
+        ts = []
+        for _ in range(6):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); run(cache_rows); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        best = min(ts[1:])
+        print(f"[prologue {nm}] {byts/1e6:.0f} MB  best {best*1e3:.1f} us -> {byts/best/1e6:.0f} GB/s (L2 flushed; all: "
+              + ", ".join(f"{t*1e3:.0f}" for t in ts) + ")", flush=True)
+    return True
+
+
 def main():
     names = sys.argv[1:] or sorted(CASES)
     if len(names) == 1 and names[0].startswith("--run="):
