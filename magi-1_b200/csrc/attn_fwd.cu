@@ -38,11 +38,15 @@ constexpr float kRescaleThreshold = 8.0f; // log2 units: lazily rescale O only w
 #define MAGI_EMU_MOD 4                    // every MAGI_EMU_MOD-th column pair takes the polynomial exp2 (0 = never)
 #endif
 #ifndef MAGI_SOFTMAX_REGS
-#define MAGI_SOFTMAX_REGS 208   // 256 softmax threads x 208 + 128 issuer/producer/idle threads x 96 = 64 K registers
+#define MAGI_SOFTMAX_REGS 208   // 256 softmax threads x 208 + 128 issuer/producer/idle threads x 88 = 384 x 168
 #endif
 #ifndef MAGI_AUX_REGS
-#define MAGI_AUX_REGS 96
+#define MAGI_AUX_REGS 88
 #endif
+// setmaxnreg only moves registers inside the pool the CTA was launched with (384 threads x 168 registers): asking
+// for more blocks the second softmax warpgroup forever.
+static_assert(256 * MAGI_SOFTMAX_REGS + 128 * MAGI_AUX_REGS <= 384 * 168, "register pool of the CTA exceeded");
+static_assert(MAGI_SOFTMAX_REGS % 8 == 0 && MAGI_AUX_REGS % 8 == 0, "setmaxnreg takes multiples of 8");
 constexpr int kEmuMod = MAGI_EMU_MOD;
 
 struct Barriers {

@@ -1,0 +1,122 @@
+"""Multi-GPU parity of the context-parallel paths with the real kernels (run on the GPU box):
+
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29700 tools/cp_check.py
+
+Every rank builds the same FullyParallelAttention weights and the same full-sequence inputs, runs the cp_ulysses and
+cp_ring_kv forwards on its shard through a KV-cache sequence (cache fill, window advance, update on/off, distill extra
+range), all-gathers the outputs and compares them with the single-GPU (cp_strategy="none") forward computed locally
+(oracle O3 of SURVEY.md section 8c). Ulysses must be bit-identical (same kernels, same per-head inputs); ring-KV is
+bounded by one bf16 rounding per merge step."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    import magi_b200  # noqa: F401
+    from magi_b200 import context_parallel as cpm
+    from magi_b200 import parallel_state as mpu
+    from magi_b200.attention import FullyParallelAttention
+    from magi_b200.common import (EngineConfig, InferenceParams, ModelConfig, ModelMetaArgs, PackedCoreAttnParams,
+                                  PackedCrossAttnParams)
+    mpu.initialize_model_parallel(cp_size=world)
+
+    Hq, Hkv, hidden, clip = 24, 8, 512, 1111       # 1111: shards and tiles are ragged everywhere
+    mc = ModelConfig(num_layers=4, hidden_size=hidden, num_attention_heads=Hq, num_query_groups=Hkv)
+
+    def build(strategy, cp):
+        torch.manual_seed(1234)
+        m = FullyParallelAttention(mc, EngineConfig(cp_size=cp, cp_strategy=strategy, ulysses_overlap_degree=overlap),
+                                   layer_number=1)
+        g = torch.Generator().manual_seed(99)
+        with torch.no_grad():
+            for n, p in m.named_parameters():
+                if "layernorm" in n:
+                    p.copy_((torch.randn(p.shape, generator=g) * 0.2).to(p.dtype))
+                elif n.endswith("layer_norm.weight"):
+                    p.fill_(1.0)
+                elif n.endswith("layer_norm.bias"):
+                    p.zero_()
+                else:
+                    p.copy_((torch.randn(p.shape, generator=g) / p.shape[-1] ** 0.5).to(p.dtype))
+        for n_ in ("q_layernorm", "k_layernorm"):
+            getattr(m, n_).float()
+        return m.to(dev).eval()
+
+    i32 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.int32), device=dev)
+
+    def meta(sp, dn, k_chunks, y_index, extra=False, ncc=False, split=None, cross=None):
+        q_range = np.array([[i * clip, (i + 1) * clip] for i in range(dn)], dtype=np.int32)
+        k_range = np.array([[s * clip, e * clip] for s, e in k_chunks], dtype=np.int32)
+        cu_k = np.concatenate([[0], np.cumsum(y_index)]).astype(np.int32)
+        core = PackedCoreAttnParams(i32(q_range), i32(k_range), q_range, k_range, clip, int(k_range.max() - k_range.min()))
+        if cross is None:
+            cu_q = np.arange(dn + 1, dtype=np.int32) * clip
+            cross = PackedCrossAttnParams(i32(np.stack([cu_q[:-1], cu_q[1:]], 1)), i32(np.stack([cu_k[:-1], cu_k[1:]], 1)),
+                                          i32(cu_q), i32(cu_k), clip, 800)
+        return ModelMetaArgs(H=1, W=1, cp_pad_size=0, cp_split_sizes=split, slice_point=sp, denoising_range_num=dn,
+                             range_num=sp + dn, extract_prefix_video_feature=False, fwd_extra_1st_chunk=extra,
+                             distill_nearly_clean_chunk=ncc, clip_token_nums=clip, enable_cuda_graph=False,
+                             core_attn_params=core, cross_attn_params=cross)
+
+    steps = [  # (slice_point, dn, k ranges in chunks, caption tokens, update, fwd_extra, distill_ncc)
+        (0, 2, [(0, 1), (0, 2)], [50, 61], True, False, False),
+        (0, 3, [(0, 1), (0, 2), (1, 3)], [0, 37, 300], True, True, False),
+        (1, 2, [(0, 2), (1, 3)], [33, 90], False, False, False),
+        (1, 3, [(0, 2), (1, 3), (3, 4)], [33, 90, 33], True, False, True),
+    ]
+    results = {}
+    for strategy in ("cp_ulysses", "cp_ring_kv"):
+        for overlap in ((1, 3) if strategy == "cp_ulysses" and (Hq // world) % 3 == 0 else (1,)):
+            ref_m, cp_m = build("none", 1), build(strategy, world)
+            inf_ref = InferenceParams(1, 5 * clip)
+            inf_cp = InferenceParams(1, 5 * clip)
+            worst = {"core": 0.0, "xattn": 0.0}
+            g = torch.Generator().manual_seed(5)
+            for (sp, dn, kc, yi, upd, extra, ncc) in steps:
+                S = dn * clip
+                hs = torch.randn(S, 1, hidden, generator=g).to(torch.bfloat16).to(dev)
+                kvs = torch.randn(sum(yi), hidden, generator=g).to(torch.bfloat16).to(dev)
+                ang = torch.rand(S, 48, generator=g) * 6.28
+                rope = torch.cat([torch.sin(ang), torch.cos(ang)], -1).to(dev)
+                m_full = meta(sp, dn, kc, yi, extra, ncc)
+                inf_ref.update_kv_cache = inf_cp.update_kv_cache = upd
+                ref_core, ref_x = ref_m(hs, kvs, inf_ref, rope, m_full)
+                cond = torch.zeros(S, 1, device=dev)
+                x, _, rope_l, pad, split, _, cross_l = cpm.cp_pre_process(world, strategy, hs, cond, rope, None, {},
+                                                                           m_full.core_attn_params,
+                                                                           m_full.cross_attn_params)
+                m_cp = meta(sp, dn, kc, yi, extra, ncc, split=split, cross=cross_l)
+                core, xo = cp_m(x, kvs, inf_cp, rope_l, m_cp)
+                core = cpm.gather_from_context_parallel_region(core.contiguous(), split)
+                xo = cpm.gather_from_context_parallel_region(xo.contiguous(), split)
+                worst["core"] = max(worst["core"], (core.float() - ref_core.float()).abs().max().item())
+                worst["xattn"] = max(worst["xattn"], (xo.float() - ref_x.float()).abs().max().item())
+            results[f"{strategy}/overlap{overlap}"] = worst
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        ok = True
+        for k, w in results.items():
+            bound = 0.0 if k.startswith("cp_ulysses") else 2.5e-2
+            good = w["core"] <= bound and w["xattn"] == 0.0
+            ok &= good
+            print(f"[cp_check N={world}] {k}: core max_abs {w['core']:.3e} (bound {bound}) xattn max_abs "
+                  f"{w['xattn']:.3e} -> {'OK' if good else 'FAIL'}", flush=True)
+        print("CP_CHECK", "PASS" if ok else "FAIL", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    overlap = 1
+    main()
