@@ -245,7 +245,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const float scale_log2 = p.scale_log2;
     __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(p.out);
 
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+    for (int round = 0; round * static_cast<int>(gridDim.x) < total_items; ++round) {
+      // items are sorted longest-first; CTAs walk them boustrophedon (0..G-1, G-1..0, ...) so that the CTA that drew
+      // the longest item of one round draws the shortest of the next: static LPT-like balance without atomics
+      const int item = round * static_cast<int>(gridDim.x) +
+                       ((round & 1) ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x)
+                                    : static_cast<int>(blockIdx.x));
+      if (item >= total_items) continue;
       Item it;
       decode_item(ws, item, p.Hq, group, p.len_a, it);
       const int row = it.qrow0 + row_in_item;
@@ -392,7 +398,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       auto advance = [&]() {
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       };
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      for (int round = 0; round * static_cast<int>(gridDim.x) < total_items; ++round) {
+      // items are sorted longest-first; CTAs walk them boustrophedon (0..G-1, G-1..0, ...) so that the CTA that drew
+      // the longest item of one round draws the shortest of the next: static LPT-like balance without atomics
+      const int item = round * static_cast<int>(gridDim.x) +
+                       ((round & 1) ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x)
+                                    : static_cast<int>(blockIdx.x));
+      if (item >= total_items) continue;
         Item it;
         decode_item(ws, item, p.Hq, group, p.len_a, it);
         if (it.nt == 0) continue;
@@ -466,7 +478,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;  // kv ring (producer side)
       uint32_t item_cnt = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      for (int round = 0; round * static_cast<int>(gridDim.x) < total_items; ++round) {
+      // items are sorted longest-first; CTAs walk them boustrophedon (0..G-1, G-1..0, ...) so that the CTA that drew
+      // the longest item of one round draws the shortest of the next: static LPT-like balance without atomics
+      const int item = round * static_cast<int>(gridDim.x) +
+                       ((round & 1) ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x)
+                                    : static_cast<int>(blockIdx.x));
+      if (item >= total_items) continue;
         Item it;
         decode_item(ws, item, p.Hq, group, p.len_a, it);
         if (it.nt == 0) continue;

@@ -49,66 +49,64 @@ __device__ __forceinline__ float half_warp_sum(float x) {
   return x;
 }
 
-template <bool kLnBf16>
-__device__ __forceinline__ void load_affine(const void* w, const void* b, int sub, bool plus1, float* wf, float* bf) {
-  if constexpr (kLnBf16) {
-    uint4 uw = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(w) + sub * 8);
-    uint4 ub = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(b) + sub * 8);
-    unpack8(uw, wf);
-    unpack8(ub, bf);
-    if (plus1) {
-      // the reference computes `self.weight + 1` in the parameter dtype: round the sum back to bf16
-#pragma unroll
-      for (int i = 0; i < 8; ++i) wf[i] = __bfloat162float(__float2bfloat16_rn(wf[i] + 1.0f));
-    }
+}  // namespace
+
+#ifndef MAGI_PRO_UNROLL
+#define MAGI_PRO_UNROLL 4
+#endif
+#ifndef MAGI_PRO_BLOCKS
+#define MAGI_PRO_BLOCKS 3
+#endif
+
+__device__ __forceinline__ uint2 ld_8(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void unpack4(const uint2& u, float* v) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+template <bool kBf16>
+__device__ __forceinline__ void load4(const void* base, int off, float* v) {
+  if constexpr (kBf16) {
+    unpack4(*reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + off), v);
   } else {
-    const float4* pw = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(w) + sub * 8);
-    const float4* pb = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(b) + sub * 8);
-    const float4 w0 = pw[0], w1 = pw[1], b0 = pb[0], b1 = pb[1];
-    wf[0] = w0.x; wf[1] = w0.y; wf[2] = w0.z; wf[3] = w0.w; wf[4] = w1.x; wf[5] = w1.y; wf[6] = w1.z; wf[7] = w1.w;
-    bf[0] = b0.x; bf[1] = b0.y; bf[2] = b0.z; bf[3] = b0.w; bf[4] = b1.x; bf[5] = b1.y; bf[6] = b1.z; bf[7] = b1.w;
-    if (plus1) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) wf[i] += 1.0f;
-    }
+    const float4 f = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
   }
 }
 
-}  // namespace
-
 // One warp owns one row (token): it streams that row's q heads, then k heads, then v heads, two heads per step (one
-// per half-warp, 16 lanes x 16 B = one 256-byte vector) and kUnroll steps in flight, so every lane keeps kUnroll
-// independent 16-byte loads outstanding. sin/cos of the row and the LayerNorm affine of the current tensor live in
-// registers for the whole row.
+// per half-warp) and MAGI_PRO_UNROLL steps in flight. Inside a half-warp, lane s < 12 holds elements [4s, 4s+4) and
+// [48+4s, 48+4s+4) of the 128-element head vector - the two RoPE partners of the non-interleaved rotation sit in the
+// same lane, so the rotation needs no shuffles - and lanes 12..15 hold the pass-through dims [96, 128).
+// sin/cos of the row and the LayerNorm affine of the current tensor stay in registers for the whole row.
 template <bool kLnBf16>
-__global__ void __launch_bounds__(256, 3) prologue_kernel(const PrologueParams p) {
-  constexpr int kUnroll = 4;
+__global__ void __launch_bounds__(256, MAGI_PRO_BLOCKS) prologue_kernel(const PrologueParams p) {
+  constexpr int kUnroll = MAGI_PRO_UNROLL;
   const int lane = threadIdx.x & 31;
-  const int sub = lane & 15;   // 16-byte slot inside the 128-element vector
+  const int sub = lane & 15;
   const int half = lane >> 4;  // which of the two heads of a step
+  const int off0 = sub < 12 ? 4 * sub : 96 + 8 * (sub - 12);
+  const int off1 = sub < 12 ? 48 + 4 * sub : off0 + 4;
   const int64_t warps_total = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   const int64_t warp_id = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int cp = p.head_perm_cp > 1 ? p.head_perm_cp : 1;
-  const bool rope = p.sin != nullptr;
-  const int partner = sub < 6 ? lane + 6 : (sub < 12 ? lane - 6 : lane);
-  const int dsub = sub < 6 ? sub : sub - 6;
+  const bool rope = p.sin != nullptr && sub < 12;
 
   for (int64_t r = warp_id; r < p.rows; r += warps_total) {
-    float cs[8], sn[8];
-    if (rope && sub < 12) {
+    float cs[4], sn[4];
+    if (rope) {
       const int64_t trow = r / p.batch;
-      const float4* pc = reinterpret_cast<const float4*>(p.cos + trow * 48 + dsub * 8);
-      const float4* ps = reinterpret_cast<const float4*>(p.sin + trow * 48 + dsub * 8);
-      const float4 c0 = pc[0], c1 = pc[1], s0 = ps[0], s1 = ps[1];
-      cs[0] = c0.x; cs[1] = c0.y; cs[2] = c0.z; cs[3] = c0.w; cs[4] = c1.x; cs[5] = c1.y; cs[6] = c1.z; cs[7] = c1.w;
-      sn[0] = s0.x; sn[1] = s0.y; sn[2] = s0.z; sn[3] = s0.w; sn[4] = s1.x; sn[5] = s1.y; sn[6] = s1.z; sn[7] = s1.w;
-      if (sub < 6) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sn[i] = -sn[i];   // first half: x1*cos - x2*sin ; second half: x2*cos + x1*sin
-      }
+      const float4 c = *reinterpret_cast<const float4*>(p.cos + trow * 48 + 4 * sub);
+      const float4 s4 = *reinterpret_cast<const float4*>(p.sin + trow * 48 + 4 * sub);
+      cs[0] = c.x; cs[1] = c.y; cs[2] = c.z; cs[3] = c.w;
+      sn[0] = s4.x; sn[1] = s4.y; sn[2] = s4.z; sn[3] = s4.w;
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { cs[i] = 1.f; sn[i] = 0.f; }
+      for (int i = 0; i < 4; ++i) { cs[i] = 1.f; sn[i] = 0.f; }
     }
 
 #pragma unroll 1
@@ -118,30 +116,45 @@ __global__ void __launch_bounds__(256, 3) prologue_kernel(const PrologueParams p
       const int H = type == 0 ? p.Hq : p.Hkv;
       const int64_t rstride = type == 0 ? p.xq_row_stride : type == 1 ? p.xk_row_stride : p.xv_row_stride;
       const int64_t hstride = type == 0 ? p.xq_head_stride : type == 1 ? p.xk_head_stride : p.xv_head_stride;
-      const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(xbase) + r * rstride + sub * 8;
+      const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(xbase) + r * rstride;
       float wf[8], bf[8];
-      if (type != 2)
-        load_affine<kLnBf16>(type == 0 ? p.ln_q_w : p.ln_k_w, type == 0 ? p.ln_q_b : p.ln_k_b, sub,
-                             p.zero_centered_gamma != 0, wf, bf);
+      if (type != 2) {
+        const void* w = type == 0 ? p.ln_q_w : p.ln_k_w;
+        const void* b = type == 0 ? p.ln_q_b : p.ln_k_b;
+        load4<kLnBf16>(w, off0, wf); load4<kLnBf16>(w, off1, wf + 4);
+        load4<kLnBf16>(b, off0, bf); load4<kLnBf16>(b, off1, bf + 4);
+        if (p.zero_centered_gamma != 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            // bf16 parameters: the reference computes `self.weight + 1` in bf16, i.e. rounds the sum
+            wf[i] = kLnBf16 ? __bfloat162float(__float2bfloat16_rn(wf[i] + 1.0f)) : wf[i] + 1.0f;
+          }
+        }
+      }
 
       for (int h0 = 0; h0 < H; h0 += 2 * kUnroll) {
-        uint4 raw[kUnroll];
+        uint2 ra[kUnroll], rb[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
           const int h = h0 + 2 * u + half;
-          raw[u] = make_uint4(0, 0, 0, 0);
-          if (h < H) raw[u] = ld_stream(src + h * hstride);
+          ra[u] = make_uint2(0, 0);
+          rb[u] = make_uint2(0, 0);
+          if (h < H) {
+            ra[u] = ld_8(src + h * hstride + off0);
+            rb[u] = ld_8(src + h * hstride + off1);
+          }
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
           const int h = h0 + 2 * u + half;
           if (h0 + 2 * u >= H) break;   // warp-uniform: both halves are past the last head
           const bool valid = h < H;
-          uint4 packed = raw[u];
+          uint2 pa = ra[u], pb = rb[u];
           if (type != 2) {
             float v[8];
-            unpack8(raw[u], v);
-            // ---- LayerNorm over 128 in fp32
+            unpack4(ra[u], v);
+            unpack4(rb[u], v + 4);
+            // ---- LayerNorm over 128 in fp32 (two-pass, biased variance)
             float s = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) s += v[i];
@@ -154,48 +167,47 @@ __global__ void __launch_bounds__(256, 3) prologue_kernel(const PrologueParams p
             float y[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) y[i] = v[i] * rstd * wf[i] + bf[i];
-            // ---- NeoX RoPE on dims [0,48) x [48,96): slots 0-5 pair with slots 6-11 of the same half-warp
+            // ---- NeoX RoPE: (x1, x2) -> (x1 cos - x2 sin, x2 cos + x1 sin); identity on lanes 12..15 (cos 1, sin 0)
             if (rope) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float o = __shfl_sync(0xffffffffu, y[i], partner);
-                y[i] = y[i] * cs[i] + o * sn[i];
+              for (int i = 0; i < 4; ++i) {
+                const float x1 = y[i], x2 = y[4 + i];
+                y[i] = x1 * cs[i] - x2 * sn[i];
+                y[4 + i] = x2 * cs[i] + x1 * sn[i];
               }
             }
-            packed = pack8(y);
+            pa = make_uint2(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]));
+            pb = make_uint2(pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
           }
           if (!valid) continue;
 
           // ---- stores: attention (or all-to-all send) layout, plus the fused KV-cache append
+          auto store = [&](__nv_bfloat16* dst) {
+            *reinterpret_cast<uint2*>(dst + off0) = pa;
+            *reinterpret_cast<uint2*>(dst + off1) = pb;
+          };
           if (type == 0) {
             const int hn = p.Hq / cp;
             const int64_t drow = static_cast<int64_t>(h / hn) * p.rows + r;
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.q_out) + drow * p.q_out_token_stride +
-                                 static_cast<int64_t>(h % hn) * p.q_out_head_stride + sub * 8;
-            *reinterpret_cast<uint4*>(dst) = packed;
+            store(reinterpret_cast<__nv_bfloat16*>(p.q_out) + drow * p.q_out_token_stride +
+                  static_cast<int64_t>(h % hn) * p.q_out_head_stride);
           } else {
-            const int col = (type == 2 ? 128 : 0) + sub * 8;
+            const int col = type == 2 ? 128 : 0;
             if (cp > p.Hkv) {
               // fewer kv heads than ranks: replicate (repeat_interleave, context_parallel.py:393-394)
               const int rep = cp / p.Hkv;
-              for (int c = h * rep; c < (h + 1) * rep; ++c) {
-                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.kv_out) +
-                                     (static_cast<int64_t>(c) * p.rows + r) * p.kv_out_token_stride + col;
-                *reinterpret_cast<uint4*>(dst) = packed;
-              }
+              for (int c = h * rep; c < (h + 1) * rep; ++c)
+                store(reinterpret_cast<__nv_bfloat16*>(p.kv_out) +
+                      (static_cast<int64_t>(c) * p.rows + r) * p.kv_out_token_stride + col);
             } else {
               const int hn = p.Hkv / cp;
               const int64_t drow = static_cast<int64_t>(h / hn) * p.rows + r;
-              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.kv_out) + drow * p.kv_out_token_stride +
-                                   static_cast<int64_t>(h % hn) * p.kv_out_head_stride + col;
-              *reinterpret_cast<uint4*>(dst) = packed;
+              store(reinterpret_cast<__nv_bfloat16*>(p.kv_out) + drow * p.kv_out_token_stride +
+                    static_cast<int64_t>(h % hn) * p.kv_out_head_stride + col);
             }
-            if (p.cache != nullptr && r < p.cache_rows) {
-              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.cache) +
-                                   (p.cache_row_offset + r) * p.cache_token_stride +
-                                   static_cast<int64_t>(h) * p.cache_head_stride + col;
-              *reinterpret_cast<uint4*>(dst) = packed;
-            }
+            if (p.cache != nullptr && r < p.cache_rows)
+              store(reinterpret_cast<__nv_bfloat16*>(p.cache) + (p.cache_row_offset + r) * p.cache_token_stride +
+                    static_cast<int64_t>(h) * p.cache_head_stride + col);
           }
         }
       }
