@@ -379,14 +379,15 @@ def main():
     e2e = None
     if not args.no_e2e:
         host_in = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in hp.inputs.items()}
-        host_out = [torch.empty(hp.core_out.shape, dtype=torch.bfloat16, pin_memory=True) for _ in range(2)]
+        host_out = [torch.empty(hp.core_out.numel(), dtype=torch.bfloat16, pin_memory=True),
+                    torch.empty(hp.x_out.numel(), dtype=torch.bfloat16, pin_memory=True)]
 
         def e2e_step():
             for k, v in host_in.items():
                 hp.inputs[k].copy_(v, non_blocking=True)
             hp.step()
-            host_out[0].copy_(hp.core_out.reshape(host_out[0].shape), non_blocking=True)
-            host_out[1].copy_(hp.x_out, non_blocking=True)
+            host_out[0].copy_(hp.core_out.reshape(-1), non_blocking=True)
+            host_out[1].copy_(hp.x_out.reshape(-1), non_blocking=True)
 
         for _ in range(2):
             e2e_step()

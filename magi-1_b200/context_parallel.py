@@ -100,8 +100,11 @@ def cp_update_cross_attn_qkv_range(cross_attn_params: PackedCrossAttnParams, bat
     offs = np.concatenate([[0], np.cumsum([r[-1, -1] for r in xq])[:-1]])
     q_ranges = np.concatenate([r + int(o) for r, o in zip(xq, offs)], axis=0)
     k_ranges = np.concatenate(xk, axis=0)
-    cu_q_new, cu_k_new = np.unique(q_ranges), np.unique(k_ranges)
-    assert cu_q_new.shape == cu_k_new.shape, f"cu_seqlens_q {cu_q_new.shape} vs cu_seqlens_k {cu_k_new.shape}"
+    # the reference derives cu_seqlens with torch.unique (context_parallel.py:211-215) and asserts equal lengths, which
+    # trips on an empty caption segment; the kernels here consume q_ranges / kv_ranges, so cu_seqlens are rebuilt
+    # segment by segment instead and stay well-formed in that case
+    cu_q_new = np.concatenate([q_ranges[:1, 0], q_ranges[:, 1]])
+    cu_k_new = np.concatenate([k_ranges[:1, 0], k_ranges[:, 1]])
 
     def t(a):
         return torch.as_tensor(a.astype(np.int32), device=device)

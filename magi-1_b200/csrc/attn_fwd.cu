@@ -49,6 +49,15 @@ static_assert(256 * MAGI_SOFTMAX_REGS + 128 * MAGI_AUX_REGS <= 384 * 168, "regis
 static_assert(MAGI_SOFTMAX_REGS % 8 == 0 && MAGI_AUX_REGS % 8 == 0, "setmaxnreg takes multiples of 8");
 constexpr int kEmuMod = MAGI_EMU_MOD;
 
+#ifdef MAGI_TRACE
+// Debug build only: clock64 stamps of CTA 0 (warp 0 of each softmax warpgroup, and the MMA issuer), first 512 tiles.
+__device__ long long g_trace[3][512][8];
+#define TRACE(who, idx, slot) \
+  do { if (blockIdx.x == 0 && (idx) < 512) g_trace[who][idx][slot] = clock64(); } while (0)
+#else
+#define TRACE(who, idx, slot) do {} while (0)
+#endif
+
 struct Barriers {
   uint64_t q_full, q_empty;
   uint64_t kv_full[kStages], kv_empty[kStages];
@@ -261,9 +270,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       for (int j = 0; j < it.nt; ++j) {
         int seg, krow0, nvalid;
         tile_info(it, j, seg, krow0, nvalid);
+        const bool tr = (warp & 3) == 0 && lane == 0 && item == 0;
+        if (tr) TRACE(t, j, 0);
         mbar_wait(&bar->s_full[t], s_phase);
         s_phase ^= 1;
         tc_fence_after();
+        if (tr) TRACE(t, j, 1);
 
         uint32_t sr[128];
         MAGI_TMEM_LD32(tS + 0, sr, 0);
@@ -271,6 +283,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         MAGI_TMEM_LD32(tS + 64, sr, 64);
         MAGI_TMEM_LD32(tS + 96, sr, 96);
         tmem_wait_ld();
+        if (tr) TRACE(t, j, 2);
 
         if (nvalid < kTileN) {
 #pragma unroll
@@ -299,6 +312,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           alpha = ex2_approx((m - mx) * scale_log2);
           m = mx;
         }
+        if (tr) TRACE(t, j, 3);
         const float neg_m = -m * scale_log2;
         const uint64_t scale2 = pack_f2(scale_log2, scale_log2);
         const uint64_t negm2 = pack_f2(neg_m, neg_m);
@@ -342,10 +356,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             MAGI_TMEM_ST32(tO + c, orr, 0);
           }
         }
+        if (tr) TRACE(t, j, 4);
         tmem_wait_st();
+        if (tr) TRACE(t, j, 5);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar->p_full[t]);
+        if (tr) TRACE(t, j, 6);
       }
 
       // ------------------------------------------------------------------ epilogue for this row
@@ -436,13 +453,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tc_fence_after();
           kst = stage;
           advance();
+          if (item == 0) TRACE(2, i, 0);
           issue_qk(tS0, q0_desc, desc_kmajor(kv_addr + kst * kTileBytes));
           tc_commit(&bar->s_full[0]);
+          if (item == 0) TRACE(2, i, 1);
           // O1 (+)= P1(i-1) V_{i-1}
           if (i == 1) mbar_wait(&bar->o_free[1], (item_cnt & 1) ^ 1);
           mbar_wait(&bar->p_full[1], p_phase1);
           p_phase1 ^= 1;
           tc_fence_after();
+          if (item == 0) TRACE(2, i, 2);
           issue_pv(tO1, tS1, desc_v(kv_addr + vst * kTileBytes), i > 1 ? 1u : 0u);
           tc_commit(&bar->kv_empty[vst]);
           // S1(i)
@@ -450,14 +470,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tc_commit(&bar->s_full[1]);
           tc_commit(&bar->kv_empty[kst]);
           if (i == nt - 1) tc_commit(&bar->q_empty);
+          if (item == 0) TRACE(2, i, 3);
           // V_i -> O0 += P0(i) V_i
           mbar_wait(&bar->kv_full[stage], phase);
+          if (item == 0) TRACE(2, i, 4);
           vst = stage;
           advance();
           mbar_wait(&bar->p_full[0], p_phase0);
           p_phase0 ^= 1;
           tc_fence_after();
+          if (item == 0) TRACE(2, i, 5);
           issue_pv(tO0, tS0, desc_v(kv_addr + vst * kTileBytes), 1);
+          if (item == 0) TRACE(2, i, 6);
         }
         tc_commit(&bar->o_full[0]);
         // O1 (+)= P1(nt-1) V_{nt-1}
@@ -523,6 +547,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
+
+#ifdef MAGI_TRACE
+extern "C" __attribute__((visibility("default"))) int magi_debug_read_trace(long long* host, size_t bytes) {
+  return (int)cudaMemcpyFromSymbol(host, g_trace, bytes < sizeof(g_trace) ? bytes : sizeof(g_trace));
+}
+#endif
 
 cudaError_t attn_setup_launch(const int* q_ranges, const int* k_ranges, const int* cu_q, const int* cu_k, int n,
                               int Hq, int total_q, int total_k, int* ws, cudaStream_t stream) {
