@@ -77,11 +77,15 @@ class FullyParallelAttention(nn.Module):
         self.hidden_size_per_attention_head = hd
         self.query_projection_size = hd * model_config.num_attention_heads
         self.kv_projection_size = hd * model_config.num_query_groups
-        world_size = mpu.get_tp_world_size(with_context_parallel=True)
+        # dit_module.py:794-798 takes the tp-cp world size from parallel_state; with cp_strategy "none" the reference
+        # asserts cp_size == 1 (dit_module.py:1167), so the engine config is authoritative here
+        world_size = 1 if engine_config.cp_strategy == "none" else engine_config.cp_size
+        if engine_config.cp_strategy != "none" and mpu.get_cp_group() is not None:
+            assert world_size == mpu.get_cp_world_size(), "engine_config.cp_size != context-parallel group size"
         groups = model_config.num_query_groups
         if engine_config.cp_strategy == "cp_ring_kv":
             self.num_query_groups_per_partition = groups   # ring-KV keeps all heads (and a replicated cache)
-        elif world_size > groups and world_size % groups == 0:   # dit_module.py:794-798
+        elif world_size > groups and world_size % groups == 0:
             self.num_query_groups_per_partition = 1
         else:
             self.num_query_groups_per_partition = divide(groups, world_size)

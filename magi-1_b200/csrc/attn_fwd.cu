@@ -404,141 +404,161 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
   } else if (warp == 8) {
     // ====================================================================== MMA issuer
+    // The whole warp runs the loop (waits included) so that everything feeding the MMAs is warp-uniform; only the
+    // tcgen05.mma / tcgen05.commit instructions themselves are issued by the elected lane.
     setmaxnreg_dec<MAGI_AUX_REGS>();
-    if (lane == 0) {
-      const uint32_t tS0 = tmem_base, tS1 = tmem_base + 128, tO0 = tmem_base + 256, tO1 = tmem_base + 384;
-      const uint64_t q0_desc = desc_kmajor(smem_u32(smem_q)), q1_desc = desc_kmajor(smem_u32(smem_q + kTileBytes));
-      const uint32_t kv_addr = smem_u32(smem_kv);
-      uint32_t stage = 0, phase = 0;  // kv ring (consumer side)
-      uint32_t p_phase0 = 0, p_phase1 = 0;
-      uint32_t item_cnt = 0;
-      auto advance = [&]() {
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
-      };
-      for (int round = 0; round * static_cast<int>(gridDim.x) < total_items; ++round) {
-      // items are sorted longest-first; CTAs walk them boustrophedon (0..G-1, G-1..0, ...) so that the CTA that drew
-      // the longest item of one round draws the shortest of the next: static LPT-like balance without atomics
+    const uint32_t tb = uniform(tmem_base);
+    const uint32_t tS0 = tb, tS1 = tb + 128, tO0 = tb + 256, tO1 = tb + 384;
+    const uint64_t q0_desc = desc_kmajor(smem_u32(smem_q)), q1_desc = desc_kmajor(smem_u32(smem_q + kTileBytes));
+    const uint32_t kv_addr = smem_u32(smem_kv);
+    uint32_t stage = 0, phase = 0;  // kv ring (consumer side)
+    uint32_t p_phase0 = 0, p_phase1 = 0;
+    uint32_t item_cnt = 0;
+    auto advance = [&]() {
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    };
+    for (int round = 0; round * static_cast<int>(gridDim.x) < total_items; ++round) {
       const int item = round * static_cast<int>(gridDim.x) +
                        ((round & 1) ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x)
                                     : static_cast<int>(blockIdx.x));
       if (item >= total_items) continue;
-        Item it;
-        decode_item(ws, item, p.Hq, group, p.len_a, it);
-        if (it.nt == 0) continue;
-        const int nt = it.nt;
-        mbar_wait(&bar->q_full, item_cnt & 1);
-        // K_0 -> S0(0), S1(0)
-        mbar_wait(&bar->kv_full[stage], phase);
-        tc_fence_after();
-        uint32_t kst = stage;
-        advance();
-        issue_qk(tS0, q0_desc, desc_kmajor(kv_addr + kst * kTileBytes));
+      Item it;
+      decode_item(ws, item, p.Hq, group, p.len_a, it);
+      const int nt = uniform(it.nt);
+      if (nt == 0) continue;
+      const uint32_t o_free_parity = (item_cnt & 1) ^ 1;
+      mbar_wait(&bar->q_full, item_cnt & 1);
+      // K_0 -> S0(0), S1(0)
+      mbar_wait(&bar->kv_full[stage], phase);
+      tc_fence_after();
+      uint32_t kst = stage;
+      advance();
+      if (elect_one()) {
+        const uint64_t kd = desc_kmajor(kv_addr + kst * kTileBytes);
+        issue_qk(tS0, q0_desc, kd);
         tc_commit(&bar->s_full[0]);
-        issue_qk(tS1, q1_desc, desc_kmajor(kv_addr + kst * kTileBytes));
+        issue_qk(tS1, q1_desc, kd);
         tc_commit(&bar->s_full[1]);
         tc_commit(&bar->kv_empty[kst]);
         if (nt == 1) tc_commit(&bar->q_empty);
-        // V_0 -> O0 = P0(0) V_0
+      }
+      __syncwarp();
+      // V_0 -> O0 = P0(0) V_0
+      mbar_wait(&bar->kv_full[stage], phase);
+      uint32_t vst = stage;
+      advance();
+      mbar_wait(&bar->o_free[0], o_free_parity);
+      mbar_wait(&bar->p_full[0], p_phase0);
+      p_phase0 ^= 1;
+      tc_fence_after();
+      if (elect_one()) issue_pv(tO0, tS0, desc_v(kv_addr + vst * kTileBytes), 0);
+      __syncwarp();
+      for (int i = 1; i < nt; ++i) {
+        // K_i -> S0(i)   (P0(i-1) already consumed by the in-order PV0(i-1))
         mbar_wait(&bar->kv_full[stage], phase);
-        uint32_t vst = stage;
-        advance();
-        mbar_wait(&bar->o_free[0], (item_cnt & 1) ^ 1);
-        mbar_wait(&bar->p_full[0], p_phase0);
-        p_phase0 ^= 1;
         tc_fence_after();
-        issue_pv(tO0, tS0, desc_v(kv_addr + vst * kTileBytes), 0);
-        for (int i = 1; i < nt; ++i) {
-          // K_i -> S0(i)   (P0(i-1) already consumed by the in-order PV0(i-1))
-          mbar_wait(&bar->kv_full[stage], phase);
-          tc_fence_after();
-          kst = stage;
-          advance();
-          if (item == 0) TRACE(2, i, 0);
+        kst = stage;
+        advance();
+        const bool tr = item == 0;
+        if (elect_one()) {
+          if (tr) TRACE(2, i, 0);
           issue_qk(tS0, q0_desc, desc_kmajor(kv_addr + kst * kTileBytes));
           tc_commit(&bar->s_full[0]);
-          if (item == 0) TRACE(2, i, 1);
-          // O1 (+)= P1(i-1) V_{i-1}
-          if (i == 1) mbar_wait(&bar->o_free[1], (item_cnt & 1) ^ 1);
-          mbar_wait(&bar->p_full[1], p_phase1);
-          p_phase1 ^= 1;
-          tc_fence_after();
-          if (item == 0) TRACE(2, i, 2);
+          if (tr) TRACE(2, i, 1);
+        }
+        __syncwarp();
+        // O1 (+)= P1(i-1) V_{i-1} ; S1(i)
+        if (i == 1) mbar_wait(&bar->o_free[1], o_free_parity);
+        mbar_wait(&bar->p_full[1], p_phase1);
+        p_phase1 ^= 1;
+        tc_fence_after();
+        if (elect_one()) {
+          if (tr) TRACE(2, i, 2);
           issue_pv(tO1, tS1, desc_v(kv_addr + vst * kTileBytes), i > 1 ? 1u : 0u);
           tc_commit(&bar->kv_empty[vst]);
-          // S1(i)
           issue_qk(tS1, q1_desc, desc_kmajor(kv_addr + kst * kTileBytes));
           tc_commit(&bar->s_full[1]);
           tc_commit(&bar->kv_empty[kst]);
           if (i == nt - 1) tc_commit(&bar->q_empty);
-          if (item == 0) TRACE(2, i, 3);
-          // V_i -> O0 += P0(i) V_i
-          mbar_wait(&bar->kv_full[stage], phase);
-          if (item == 0) TRACE(2, i, 4);
-          vst = stage;
-          advance();
-          mbar_wait(&bar->p_full[0], p_phase0);
-          p_phase0 ^= 1;
-          tc_fence_after();
-          if (item == 0) TRACE(2, i, 5);
-          issue_pv(tO0, tS0, desc_v(kv_addr + vst * kTileBytes), 1);
-          if (item == 0) TRACE(2, i, 6);
+          if (tr) TRACE(2, i, 3);
         }
-        tc_commit(&bar->o_full[0]);
-        // O1 (+)= P1(nt-1) V_{nt-1}
-        if (nt == 1) mbar_wait(&bar->o_free[1], (item_cnt & 1) ^ 1);
-        mbar_wait(&bar->p_full[1], p_phase1);
-        p_phase1 ^= 1;
+        __syncwarp();
+        // V_i -> O0 += P0(i) V_i
+        mbar_wait(&bar->kv_full[stage], phase);
+        vst = stage;
+        advance();
+        if (tr && lane == 0) TRACE(2, i, 4);
+        mbar_wait(&bar->p_full[0], p_phase0);
+        p_phase0 ^= 1;
         tc_fence_after();
+        if (elect_one()) {
+          if (tr) TRACE(2, i, 5);
+          issue_pv(tO0, tS0, desc_v(kv_addr + vst * kTileBytes), 1);
+          if (tr) TRACE(2, i, 6);
+        }
+        __syncwarp();
+      }
+      // O1 (+)= P1(nt-1) V_{nt-1}
+      if (nt == 1) mbar_wait(&bar->o_free[1], o_free_parity);
+      mbar_wait(&bar->p_full[1], p_phase1);
+      p_phase1 ^= 1;
+      tc_fence_after();
+      if (elect_one()) {
+        tc_commit(&bar->o_full[0]);   // everything up to PV0(nt-1)
         issue_pv(tO1, tS1, desc_v(kv_addr + vst * kTileBytes), nt > 1 ? 1u : 0u);
         tc_commit(&bar->kv_empty[vst]);
         tc_commit(&bar->o_full[1]);
-        ++item_cnt;
       }
+      __syncwarp();
+      ++item_cnt;
     }
-    __syncwarp();
   } else if (warp == 9) {
-    // ====================================================================== TMA producer
+    // ====================================================================== TMA producer (same structure)
     setmaxnreg_dec<MAGI_AUX_REGS>();
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;  // kv ring (producer side)
-      uint32_t item_cnt = 0;
-      for (int round = 0; round * static_cast<int>(gridDim.x) < total_items; ++round) {
-      // items are sorted longest-first; CTAs walk them boustrophedon (0..G-1, G-1..0, ...) so that the CTA that drew
-      // the longest item of one round draws the shortest of the next: static LPT-like balance without atomics
+    uint32_t stage = 0, phase = 0;  // kv ring (producer side)
+    uint32_t item_cnt = 0;
+    for (int round = 0; round * static_cast<int>(gridDim.x) < total_items; ++round) {
       const int item = round * static_cast<int>(gridDim.x) +
                        ((round & 1) ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x)
                                     : static_cast<int>(blockIdx.x));
       if (item >= total_items) continue;
-        Item it;
-        decode_item(ws, item, p.Hq, group, p.len_a, it);
-        if (it.nt == 0) continue;
-        mbar_wait(&bar->q_empty, (item_cnt & 1) ^ 1);
+      Item it;
+      decode_item(ws, item, p.Hq, group, p.len_a, it);
+      it.nt = uniform(it.nt); it.nt_a = uniform(it.nt_a);
+      it.h = uniform(it.h); it.hkv = uniform(it.hkv); it.qrow0 = uniform(it.qrow0);
+      it.ka0 = uniform(it.ka0); it.ka1 = uniform(it.ka1); it.kb0 = uniform(it.kb0); it.kb1 = uniform(it.kb1);
+      if (it.nt == 0) continue;
+      mbar_wait(&bar->q_empty, (item_cnt & 1) ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&bar->q_full, 2 * kTileBytes);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           tma_load_3d(smem_q + t * kTileBytes, &tm_q, &bar->q_full, 0, it.h, it.qrow0 + t * kTileM);
           tma_load_3d(smem_q + t * kTileBytes + kBlkBytes, &tm_q, &bar->q_full, 64, it.h, it.qrow0 + t * kTileM);
         }
-        for (int j = 0; j < it.nt; ++j) {
-          int seg, krow0, nvalid;
-          tile_info(it, j, seg, krow0, nvalid);
-          const CUtensorMap* mk = seg == 0 ? &tm_ka : &tm_kb;
-          const CUtensorMap* mv = seg == 0 ? &tm_va : &tm_vb;
+      }
+      __syncwarp();
+      for (int j = 0; j < it.nt; ++j) {
+        int seg, krow0, nvalid;
+        tile_info(it, j, seg, krow0, nvalid);
+        const CUtensorMap* mk = seg == 0 ? &tm_ka : &tm_kb;
+        const CUtensorMap* mv = seg == 0 ? &tm_va : &tm_vb;
 #pragma unroll
-          for (int kv = 0; kv < 2; ++kv) {
-            const CUtensorMap* mm = kv == 0 ? mk : mv;
-            mbar_wait(&bar->kv_empty[stage], phase ^ 1);
+        for (int kv = 0; kv < 2; ++kv) {
+          const CUtensorMap* mm = kv == 0 ? mk : mv;
+          mbar_wait(&bar->kv_empty[stage], phase ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(&bar->kv_full[stage], kTileBytes);
             uint8_t* dst = smem_kv + stage * kTileBytes;
             tma_load_3d(dst, mm, &bar->kv_full[stage], 0, it.hkv, krow0);
             tma_load_3d(dst + kBlkBytes, mm, &bar->kv_full[stage], 64, it.hkv, krow0);
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        ++item_cnt;
       }
+      ++item_cnt;
     }
-    __syncwarp();
   } else {
     setmaxnreg_dec<MAGI_AUX_REGS>();   // idle warps of the third warpgroup (setmaxnreg is warpgroup-collective)
   }

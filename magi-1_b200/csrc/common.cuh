@@ -23,6 +23,23 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   return t;
 }
 
+// One lane of a fully converged warp (the same lane every time for the same mask). Single-lane tcgen05 / TMA issue
+// must sit behind this (not behind `lane == 0` around a whole loop): operands computed in convergent code stay in
+// uniform registers, otherwise ptxas wraps every UTCHMMA / UTMALDG in a per-lane "waterfall" loop of R2UR moves.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
