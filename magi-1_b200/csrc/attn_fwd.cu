@@ -61,7 +61,7 @@ __device__ long long g_trace[3][512][8];
 struct Barriers {
   uint64_t q_full, q_empty;
   uint64_t kv_full[kStages], kv_empty[kStages];
-  uint64_t s_full[2], p_full[2], o_full[2], o_free[2];
+  uint64_t s_full[2], p_half[2][2], o_full[2], o_free[2];
   uint32_t tmem_base;
 };
 
@@ -140,11 +140,13 @@ __device__ __forceinline__ void issue_qk(uint32_t d_tmem, uint64_t q_desc, uint6
 
 // O[128 x 128(hd)] (+)= P[128 x 128(keys)] * V[128(keys) x 128(hd)] ; P from TMEM (bf16, 2 per column),
 // V is MN-major (head_dim contiguous): 8-key groups 1024 B apart (SBO), 64-wide hd blocks kBlkBytes apart (LBO).
-__device__ __forceinline__ void issue_pv(uint32_t d_tmem, uint32_t p_tmem, uint64_t v_desc, uint32_t accumulate) {
+// `half` selects keys [64 half, 64 half + 64) of the tile (k-steps 4 half .. 4 half + 3).
+__device__ __forceinline__ void issue_pv(uint32_t d_tmem, uint32_t p_tmem, uint64_t v_desc, uint32_t accumulate,
+                                         int half) {
 #pragma unroll
-  for (int ks = 0; ks < 8; ++ks) {
+  for (int ks = 4 * half; ks < 4 * half + 4; ++ks) {
     mma_ts(d_tmem, p_tmem + ks * 8, v_desc + static_cast<uint64_t>((ks * 2048) >> 4), kIdescPV,
-           (accumulate | (ks > 0)) ? 1u : 0u);
+           (accumulate | (ks > 0)) ? 1u : 0u);   // only k-step 0 of a fresh accumulator overwrites
   }
 }
 
@@ -219,7 +221,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&bar->s_full[t], 1);
-      mbar_init(&bar->p_full[t], kTileM / 32);   // one arrival per softmax warp
+      mbar_init(&bar->p_half[t][0], kTileM / 32);   // one arrival per softmax warp, per 64-key half of P
+      mbar_init(&bar->p_half[t][1], kTileM / 32);
       mbar_init(&bar->o_full[t], 1);
       mbar_init(&bar->o_free[t], kTileM / 32);
     }
@@ -278,56 +281,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (tr) TRACE(t, j, 1);
 
         uint32_t sr[128];
-        MAGI_TMEM_LD32(tS + 0, sr, 0);
-        MAGI_TMEM_LD32(tS + 32, sr, 32);
-        MAGI_TMEM_LD32(tS + 64, sr, 64);
-        MAGI_TMEM_LD32(tS + 96, sr, 96);
-        tmem_wait_ld();
+        auto load_s = [&]() {
+          MAGI_TMEM_LD32(tS + 0, sr, 0);
+          MAGI_TMEM_LD32(tS + 32, sr, 32);
+          MAGI_TMEM_LD32(tS + 64, sr, 64);
+          MAGI_TMEM_LD32(tS + 96, sr, 96);
+          tmem_wait_ld();
+          if (nvalid < kTileN) {
+#pragma unroll
+            for (int c = 0; c < 128; ++c)
+              if (c >= nvalid) sr[c] = 0xff800000u;  // -inf
+          }
+        };
+        load_s();
         if (tr) TRACE(t, j, 2);
 
-        if (nvalid < kTileN) {
-#pragma unroll
-          for (int c = 0; c < 128; ++c)
-            if (c >= nvalid) sr[c] = 0xff800000u;  // -inf
-        }
-        float mx0 = fmax3(__uint_as_float(sr[0]), __uint_as_float(sr[1]), __uint_as_float(sr[2]));
-        float mx1 = fmax3(__uint_as_float(sr[3]), __uint_as_float(sr[4]), __uint_as_float(sr[5]));
-        float mx2 = fmaxf(__uint_as_float(sr[6]), __uint_as_float(sr[7]));
-        float mx3 = mx2;
-#pragma unroll
-        for (int c = 8; c < 128; c += 8) {
-          mx0 = fmax3(mx0, __uint_as_float(sr[c + 0]), __uint_as_float(sr[c + 1]));
-          mx1 = fmax3(mx1, __uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3]));
-          mx2 = fmax3(mx2, __uint_as_float(sr[c + 4]), __uint_as_float(sr[c + 5]));
-          mx3 = fmax3(mx3, __uint_as_float(sr[c + 6]), __uint_as_float(sr[c + 7]));
-        }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-
-        bool need = false;
-        float alpha = 1.f;
-        if (j == 0) {
-          m = mx;
-        } else if ((mx - m) * scale_log2 > kRescaleThreshold) {
-          need = true;
-          alpha = ex2_approx((m - mx) * scale_log2);
-          m = mx;
-        }
-        if (tr) TRACE(t, j, 3);
-        const float neg_m = -m * scale_log2;
-        const uint64_t scale2 = pack_f2(scale_log2, scale_log2);
-        const uint64_t negm2 = pack_f2(neg_m, neg_m);
-
-        uint64_t sum_a = pack_f2(0.f, 0.f), sum_b = sum_a;
-        // P overwrites S in place, in registers (pair k of a 64-column half lands in slot k of that half) and in
-        // TMEM; each half is stored as soon as it is complete so the store overlaps the second half's math.
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
+        // Row max over the 128 scores: 64 x FMNMX3 in four chains. For j > 0 it is NOT on the critical path: P is
+        // computed optimistically against the running max m while the chains run on the ALU pipe next to it; only
+        // if some row's max grew by more than 2^8 (rare) is the tile redone with the new max.
+        float mxa, mxb, mxc, mxd;
+        auto max_step = [&](int k) {   // k = 0..31: consumes columns 4k .. 4k+3
+          const float a0 = __uint_as_float(sr[4 * k]), a1 = __uint_as_float(sr[4 * k + 1]);
+          const float a2 = __uint_as_float(sr[4 * k + 2]), a3 = __uint_as_float(sr[4 * k + 3]);
+          if (k == 0) { mxa = fmaxf(a0, a1); mxb = fmaxf(a2, a3); mxc = mxa; mxd = mxb; }
+          else if (k & 1) { mxc = fmax3(mxc, a0, a1); mxd = fmax3(mxd, a2, a3); }
+          else { mxa = fmax3(mxa, a0, a1); mxb = fmax3(mxb, a2, a3); }
+        };
+        uint64_t sum_a, sum_b;
+        // columns [64 hf, 64 hf + 64) -> packed bf16 P in sr[64 hf .. 64 hf + 32) (in place), row sums accumulated
+        auto half = [&](const int hf, const uint64_t scale2, const uint64_t negm2, const bool with_max) {
 #pragma unroll
           for (int c = 64 * hf; c < 64 * hf + 64; c += 2) {
+            const int pair = c >> 1;
+            if (with_max) max_step(pair - 32 * hf);   // 32 steps cover all 128 columns during the first half
             const uint64_t x2 = ffma2(pack_f2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), scale2, negm2);
             float x0, x1, p0, p1;
             unpack_f2(x2, x0, x1);
-            const int pair = c >> 1;
             if (kEmuMod > 0 && (pair % (kEmuMod > 0 ? kEmuMod : 1)) == (kEmuMod > 0 ? kEmuMod : 1) - 1) {
               ex2_poly2(x0, x1, p0, p1);
             } else {
@@ -338,30 +327,68 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             if (pair & 1) sum_b = fadd2(sum_b, p2); else sum_a = fadd2(sum_a, p2);
             sr[64 * hf + ((c - 64 * hf) >> 1)] = pack_bf16x2(p0, p1);
           }
-          MAGI_TMEM_ST32(tS + 32 * hf, sr, 64 * hf);
+        };
+
+        float alpha = 1.f;
+        bool need = false;
+        const uint64_t scale2 = pack_f2(scale_log2, scale_log2);
+        sum_a = pack_f2(0.f, 0.f);
+        sum_b = sum_a;
+        if (j == 0) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) max_step(k);
+          m = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
+          if (tr) TRACE(t, j, 3);
+          const float neg_m = -m * scale_log2;
+          half(0, scale2, pack_f2(neg_m, neg_m), false);
+        } else {
+          if (tr) TRACE(t, j, 3);
+          const float neg_m = -m * scale_log2;
+          half(0, scale2, pack_f2(neg_m, neg_m), true);
+          const float mx = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
+          need = (mx - m) * scale_log2 > kRescaleThreshold;
+          if (__any_sync(0xffffffffu, need)) {
+            // rare: redo the first half against the new max and bring O back into range before P*V accumulates
+            if (need) {
+              alpha = ex2_approx((m - mx) * scale_log2);
+              m = mx;
+            }
+            load_s();
+            sum_a = pack_f2(0.f, 0.f);
+            sum_b = sum_a;
+            const float neg_m2 = -m * scale_log2;
+            half(0, scale2, pack_f2(neg_m2, neg_m2), false);
+#pragma unroll 1
+            for (int c = 0; c < 128; c += 32) {
+              uint32_t orr[32];
+              MAGI_TMEM_LD32(tO + c, orr, 0);
+              tmem_wait_ld();
+#pragma unroll
+              for (int k = 0; k < 32; ++k) orr[k] = __float_as_uint(__uint_as_float(orr[k]) * alpha);
+              MAGI_TMEM_ST32(tO + c, orr, 0);
+            }
+          }
         }
+        // first 64 keys of P are final: hand them to the MMA issuer so P*V starts while the second half is computed
+        MAGI_TMEM_ST32(tS, sr, 0);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar->p_half[t][0]);
+        if (tr) TRACE(t, j, 4);
+        {
+          const float neg_m = -m * scale_log2;
+          half(1, scale2, pack_f2(neg_m, neg_m), false);
+        }
+        MAGI_TMEM_ST32(tS + 32, sr, 64);
         float s0, s1;
         unpack_f2(fadd2(sum_a, sum_b), s0, s1);
         l = l * alpha + (s0 + s1);
-
-        if (__any_sync(0xffffffffu, need)) {
-          // rare: this row's running max jumped by more than 2^8 -> bring O back into range before P*V accumulates
-#pragma unroll 1
-          for (int c = 0; c < 128; c += 32) {
-            uint32_t orr[32];
-            MAGI_TMEM_LD32(tO + c, orr, 0);
-            tmem_wait_ld();
-#pragma unroll
-            for (int k = 0; k < 32; ++k) orr[k] = __float_as_uint(__uint_as_float(orr[k]) * alpha);
-            MAGI_TMEM_ST32(tO + c, orr, 0);
-          }
-        }
-        if (tr) TRACE(t, j, 4);
         tmem_wait_st();
         if (tr) TRACE(t, j, 5);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar->p_full[t]);
+        if (lane == 0) mbar_arrive(&bar->p_half[t][1]);
         if (tr) TRACE(t, j, 6);
       }
 
@@ -417,6 +444,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     auto advance = [&]() {
       if (++stage == kStages) { stage = 0; phase ^= 1; }
     };
+    // O_t (+)= P_t V in two 64-key halves, each issued as soon as the softmax warpgroup has published that half of P
+    auto pv = [&](uint32_t tO, uint32_t tS, int t, uint32_t& ph, uint32_t vst_, uint32_t acc) {
+      const uint64_t vd = desc_v(kv_addr + vst_ * kTileBytes);
+      mbar_wait(&bar->p_half[t][0], ph);
+      tc_fence_after();
+      if (elect_one()) issue_pv(tO, tS, vd, acc, 0);
+      __syncwarp();
+      mbar_wait(&bar->p_half[t][1], ph);
+      tc_fence_after();
+      if (elect_one()) issue_pv(tO, tS, vd, acc, 1);
+      __syncwarp();
+      ph ^= 1;
+    };
     for (int round = 0; round * static_cast<int>(gridDim.x) < total_items; ++round) {
       const int item = round * static_cast<int>(gridDim.x) +
                        ((round & 1) ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x)
@@ -448,11 +488,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       uint32_t vst = stage;
       advance();
       mbar_wait(&bar->o_free[0], o_free_parity);
-      mbar_wait(&bar->p_full[0], p_phase0);
-      p_phase0 ^= 1;
-      tc_fence_after();
-      if (elect_one()) issue_pv(tO0, tS0, desc_v(kv_addr + vst * kTileBytes), 0);
-      __syncwarp();
+      pv(tO0, tS0, 0, p_phase0, vst, 0);
       for (int i = 1; i < nt; ++i) {
         // K_i -> S0(i)   (P0(i-1) already consumed by the in-order PV0(i-1))
         mbar_wait(&bar->kv_full[stage], phase);
@@ -469,12 +505,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         __syncwarp();
         // O1 (+)= P1(i-1) V_{i-1} ; S1(i)
         if (i == 1) mbar_wait(&bar->o_free[1], o_free_parity);
-        mbar_wait(&bar->p_full[1], p_phase1);
-        p_phase1 ^= 1;
-        tc_fence_after();
+        if (tr && lane == 0) TRACE(2, i, 2);
+        pv(tO1, tS1, 1, p_phase1, vst, i > 1 ? 1u : 0u);
         if (elect_one()) {
-          if (tr) TRACE(2, i, 2);
-          issue_pv(tO1, tS1, desc_v(kv_addr + vst * kTileBytes), i > 1 ? 1u : 0u);
           tc_commit(&bar->kv_empty[vst]);
           issue_qk(tS1, q1_desc, desc_kmajor(kv_addr + kst * kTileBytes));
           tc_commit(&bar->s_full[1]);
@@ -488,24 +521,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         vst = stage;
         advance();
         if (tr && lane == 0) TRACE(2, i, 4);
-        mbar_wait(&bar->p_full[0], p_phase0);
-        p_phase0 ^= 1;
-        tc_fence_after();
-        if (elect_one()) {
-          if (tr) TRACE(2, i, 5);
-          issue_pv(tO0, tS0, desc_v(kv_addr + vst * kTileBytes), 1);
-          if (tr) TRACE(2, i, 6);
-        }
-        __syncwarp();
+        pv(tO0, tS0, 0, p_phase0, vst, 1);
+        if (tr && lane == 0) { TRACE(2, i, 5); TRACE(2, i, 6); }
       }
       // O1 (+)= P1(nt-1) V_{nt-1}
       if (nt == 1) mbar_wait(&bar->o_free[1], o_free_parity);
-      mbar_wait(&bar->p_full[1], p_phase1);
-      p_phase1 ^= 1;
-      tc_fence_after();
+      if (elect_one()) tc_commit(&bar->o_full[0]);   // everything up to PV0(nt-1)
+      __syncwarp();
+      pv(tO1, tS1, 1, p_phase1, vst, nt > 1 ? 1u : 0u);
       if (elect_one()) {
-        tc_commit(&bar->o_full[0]);   // everything up to PV0(nt-1)
-        issue_pv(tO1, tS1, desc_v(kv_addr + vst * kTileBytes), nt > 1 ? 1u : 0u);
         tc_commit(&bar->kv_empty[vst]);
         tc_commit(&bar->o_full[1]);
       }

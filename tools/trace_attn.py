@@ -27,12 +27,12 @@ assert rc == 0, rc
 lo, hi = 20, 280   # steady state tiles of item 0 (293 tiles)
 for t in (0, 1):
     b = buf[t, lo:hi].astype(np.float64)
-    names = ["wait S", "tcgen05.ld S", "row max", "exp+pack+st issue", "wait::st", "fence+arrive"]
+    names = ["wait S", "tcgen05.ld S", "(max, j=0 only)", "half0 exp+st+arrive", "half1 exp+st+wait", "arrive"]
     d = [b[:, i + 1] - b[:, i] for i in range(6)]
     period = np.diff(b[:, 0]).mean()
     print(f"softmax WG{t}: period {period:.0f} cyc | " + " | ".join(f"{n} {x.mean():.0f}" for n, x in zip(names, d)))
 m = buf[2, lo:hi].astype(np.float64)
-names = ["issue S0+commit", "wait P1", "issue PV1,S1,commits", "wait V", "wait P0", "issue PV0"]
+names = ["issue S0+commit", "wait o_free", "PV1 (waits+issue), S1, commits", "wait V", "PV0 (waits+issue)", "-"]
 d = [m[:, i + 1] - m[:, i] for i in range(6)]
 period = np.diff(m[:, 0]).mean()
 loop = m[1:, 0] - m[:-1, 6]
