@@ -35,7 +35,7 @@ constexpr uint32_t kIdescQK = make_idesc_bf16(128, 128, 0, 0);
 constexpr uint32_t kIdescPV = make_idesc_bf16(128, 128, 0, 1);
 constexpr float kRescaleThreshold = 8.0f; // log2 units: lazily rescale O only when the row max grew by > 2^8
 #ifndef MAGI_EMU_MOD
-#define MAGI_EMU_MOD 4                    // every MAGI_EMU_MOD-th column pair takes the polynomial exp2 (0 = never)
+#define MAGI_EMU_MOD 3                    // every MAGI_EMU_MOD-th column pair takes the polynomial exp2 (0 = never)
 #endif
 #ifndef MAGI_SOFTMAX_REGS
 #define MAGI_SOFTMAX_REGS 208   // 256 softmax threads x 208 + 128 issuer/producer/idle threads x 88 = 384 x 168

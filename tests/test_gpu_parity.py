@@ -123,6 +123,32 @@ def test_attn_random_range_sets_vs_oracle(F, seed):
     check_attn(out, ref, f"seed {seed}: n={n} Hq={Hq} Hkv={Hkv} Tq={Tq} Tk={Tk} cache={cache_len}")
 
 
+def test_running_max_jumps_take_the_rescale_path(F):
+    """Later key tiles carry much larger scores, so the running row max grows by far more than 2^8 between tiles:
+    exercises the lazy-rescale branch (redo of the optimistic first half, O rescale in TMEM) that N(0,1) data never
+    reaches; some rows jump, others (zero queries) do not."""
+    Tq, Tk, Hq, Hkv = 300, 1100, 4, 2
+    q, k, v = rnd((Tq, Hq, 128), 1), rnd((Tk, Hkv, 128), 2), rnd((Tk, Hkv, 128), 3)
+    ramp = np.ones(Tk, dtype=np.float32)
+    ramp[256:384] = 6.0
+    ramp[640:700] = 14.0
+    ramp[1000:] = 0.25
+    k = O.bf16_round(k * ramp[:, None, None])
+    q[::7] = 0.0            # rows whose scores stay flat
+    qr, kr = [[0, 300]], [[0, 1100]]
+    ref, ref_lse = O.attn_ranges(q, k, v, qr, kr, round_output=False)
+    out, lse = F.attn_ranges(bf(q), bf(k), bf(v), i32(qr), i32(kr))
+    check_attn(out, ref, "growing max")
+    assert np.abs(lse.cpu().numpy() - ref_lse).max() < 2e-3
+    # decreasing scores (max set by the first tile, later tiles underflow towards 0) as the mirror case
+    k2 = O.bf16_round(k[::-1].copy())
+    v2 = np.ascontiguousarray(v[::-1])
+    ref2, _ = O.attn_ranges(q, k2, v2, qr, kr, round_output=False)
+    out2, _ = F.attn_ranges(bf(q), bf(k2), bf(v2), i32(qr), i32(kr))
+    check_attn(out2, ref2, "shrinking max")
+    assert np.abs(ref - ref2).max() < 1e-4   # permutation invariance of the oracle itself
+
+
 def test_drop_in_signatures(F):
     """flash_attn_func / flash_attn_varlen_func / flex_flash_attn_func call shapes of dit_module.py:1032-1133."""
     q, k, v = rnd((2, 200, 6, 128), 3), rnd((2, 333, 2, 128), 4), rnd((2, 333, 2, 128), 5)
