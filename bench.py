@@ -329,6 +329,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
         from magi_b200 import parallel_state as mpu
         mpu.initialize_model_parallel(cp_size=world)

@@ -77,7 +77,9 @@ def main():
     ]
     results = {}
     for strategy in ("cp_ulysses", "cp_ring_kv"):
-        for overlap in ((1, 3) if strategy == "cp_ulysses" and (Hq // world) % 3 == 0 else (1,)):
+        kv_loc = max(1, Hkv // world)
+        second = kv_loc if kv_loc > 1 else 3      # whole kv heads per group, or 3 q-head groups in the MQA case
+        for overlap in ((1, second) if strategy == "cp_ulysses" else (1,)):
             ref_m, cp_m = build("none", 1), build(strategy, world)
             inf_ref = InferenceParams(1, 5 * clip)
             inf_cp = InferenceParams(1, 5 * clip)
