@@ -30,7 +30,16 @@ constexpr int kTileN = 128;               // keys per K/V tile
 constexpr int kStages = 4;                // K/V smem ring depth (tiles; K and V alternate)
 constexpr int kBlkBytes = 128 * 64 * 2;   // one 64-column (128 B wide) swizzle block of a 128-row tile
 constexpr int kTileBytes = 2 * kBlkBytes; // 128 x 128 bf16
-constexpr int kThreads = 384;
+#ifndef MAGI_COL_SPLIT
+#define MAGI_COL_SPLIT 1   // 1: one thread owns a whole 128-column row of S_t; 2: two threads (two warps) share it
+#endif
+constexpr int kSplit = MAGI_COL_SPLIT;
+static_assert(kSplit == 1 || kSplit == 2, "MAGI_COL_SPLIT must be 1 or 2");
+constexpr int kCols = 128 / kSplit;              // S columns per softmax thread
+constexpr int kSoftmaxWarps = 8 * kSplit;
+constexpr int kMmaWarp = kSoftmaxWarps;          // tcgen05 issuer + TMEM allocator
+constexpr int kTmaWarp = kSoftmaxWarps + 1;
+constexpr int kThreads = kSplit == 1 ? 384 : 576;   // 12 warps (3 warpgroups, setmaxnreg) or 18 warps (112 regs each)
 constexpr uint32_t kIdescQK = make_idesc_bf16(128, 128, 0, 0);
 constexpr uint32_t kIdescPV = make_idesc_bf16(128, 128, 0, 1);
 constexpr float kRescaleThreshold = 8.0f; // log2 units: lazily rescale O only when the row max grew by > 2^8
@@ -45,7 +54,8 @@ constexpr float kRescaleThreshold = 8.0f; // log2 units: lazily rescale O only w
 #endif
 // setmaxnreg only moves registers inside the pool the CTA was launched with (384 threads x 168 registers): asking
 // for more blocks the second softmax warpgroup forever.
-static_assert(256 * MAGI_SOFTMAX_REGS + 128 * MAGI_AUX_REGS <= 384 * 168, "register pool of the CTA exceeded");
+static_assert(kSplit != 1 || 256 * MAGI_SOFTMAX_REGS + 128 * MAGI_AUX_REGS <= 384 * 168,
+              "register pool of the CTA exceeded");
 static_assert(MAGI_SOFTMAX_REGS % 8 == 0 && MAGI_AUX_REGS % 8 == 0, "setmaxnreg takes multiples of 8");
 constexpr int kEmuMod = MAGI_EMU_MOD;
 
@@ -63,9 +73,11 @@ struct Barriers {
   uint64_t kv_full[kStages], kv_empty[kStages];
   uint64_t s_full[2], p_half[2][2], o_full[2], o_free[2];
   uint32_t tmem_base;
+  float xch[2][2][2][128];   // [parity][q tile][column half][row]: per-tile row-max exchange (kSplit == 2)
+  float xl[2][2][128];       // [q tile][column half][row]: row-sum exchange at the end of an item (kSplit == 2)
 };
 
-constexpr int kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 1024 /*align slack*/ + sizeof(Barriers);
 
 struct Item {
   int q_begin, q_end;  // query rows of this item's range
@@ -145,7 +157,8 @@ __device__ __forceinline__ void issue_pv(uint32_t d_tmem, uint32_t p_tmem, uint6
                                          int half) {
 #pragma unroll
   for (int ks = 4 * half; ks < 4 * half + 4; ++ks) {
-    mma_ts(d_tmem, p_tmem + ks * 8, v_desc + static_cast<uint64_t>((ks * 2048) >> 4), kIdescPV,
+    // P half h (keys [64h, 64h+64), bf16) sits in columns [64h, 64h+32) of S_t: over the S columns its writer read
+    mma_ts(d_tmem, p_tmem + 64 * half + (ks - 4 * half) * 8, v_desc + static_cast<uint64_t>((ks * 2048) >> 4), kIdescPV,
            (accumulate | (ks > 0)) ? 1u : 0u);   // only k-step 0 of a fresh accumulator overwrites
   }
 }
@@ -224,15 +237,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_init(&bar->p_half[t][0], kTileM / 32);   // one arrival per softmax warp, per 64-key half of P
       mbar_init(&bar->p_half[t][1], kTileM / 32);
       mbar_init(&bar->o_full[t], 1);
-      mbar_init(&bar->o_free[t], kTileM / 32);
+      mbar_init(&bar->o_free[t], kSplit * kTileM / 32);
     }
     fence_barrier_init();
   }
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     tmem_alloc(&bar->tmem_base, 512);
     tmem_relinquish();
   }
-  if (warp == 9 && lane == 0) {
+  if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_ka);
     tma_prefetch_desc(&tm_va);
@@ -245,17 +258,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const uint32_t tmem_base = bar->tmem_base;
   const int total_items = ws[0];
 
-  if (warp < 8) {
+  if (warp < kSoftmaxWarps) {
     // ====================================================================== softmax warpgroups
-    setmaxnreg_inc<MAGI_SOFTMAX_REGS>();
-    const int t = warp >> 2;
-    const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tS = tmem_base + lane_sel + t * 128;
-    const uint32_t tO = tmem_base + lane_sel + 256 + t * 128;
-    const int row_in_item = t * kTileM + (warp & 3) * 32 + lane;
+    if constexpr (kSplit == 1) setmaxnreg_inc<MAGI_SOFTMAX_REGS>();
+    const int grp = warp >> 2;                 // warpgroup index
+    const int t = grp / kSplit;                // which 128-row query tile of the item
+    const int ch = grp % kSplit;               // which column half of S_t / O_t this thread owns (kSplit == 2)
+    const int quarter = warp & 3;              // TMEM lane quarter this warp may access
+    const int rowq = quarter * 32 + lane;
+    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tS = tmem_base + lane_sel + t * 128;          // S_t (and P_t)
+    const uint32_t tSc = tS + ch * kCols;                        // this thread's S columns
+    const uint32_t tO = tmem_base + lane_sel + 256 + t * 128 + ch * kCols;   // this thread's O columns
+    const int row_in_item = t * kTileM + rowq;
+    const int pair_bar = 1 + t * 4 + quarter;  // named barrier shared by the two warps that split a row (kSplit == 2)
     uint32_t s_phase = 0, o_phase = 0;
     const float scale_log2 = p.scale_log2;
     __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(p.out);
+    auto pair_max = [&](float v, int par) -> float {   // max over the two threads that share this row
+      if constexpr (kSplit == 1) return v;
+      bar->xch[par][t][ch][rowq] = v;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      return fmaxf(v, bar->xch[par][t][ch ^ 1][rowq]);
+    };
 
     for (int round = 0; round * static_cast<int>(gridDim.x) < total_items; ++round) {
       // items are sorted longest-first; CTAs walk them boustrophedon (0..G-1, G-1..0, ...) so that the CTA that drew
@@ -268,39 +293,37 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       decode_item(ws, item, p.Hq, group, p.len_a, it);
       const int row = it.qrow0 + row_in_item;
       const bool row_valid = row < it.q_end;
-      float m = -INFINITY, l = 0.f;
+      float m = -INFINITY, l = 0.f;   // running max of the row (shared by its threads), this thread's partial row sum
 
       for (int j = 0; j < it.nt; ++j) {
         int seg, krow0, nvalid;
         tile_info(it, j, seg, krow0, nvalid);
-        const bool tr = (warp & 3) == 0 && lane == 0 && item == 0;
+        const bool tr = quarter == 0 && lane == 0 && item == 0 && ch == 0;
         if (tr) TRACE(t, j, 0);
         mbar_wait(&bar->s_full[t], s_phase);
         s_phase ^= 1;
         tc_fence_after();
         if (tr) TRACE(t, j, 1);
 
-        uint32_t sr[128];
+        uint32_t sr[kCols];
         auto load_s = [&]() {
-          MAGI_TMEM_LD32(tS + 0, sr, 0);
-          MAGI_TMEM_LD32(tS + 32, sr, 32);
-          MAGI_TMEM_LD32(tS + 64, sr, 64);
-          MAGI_TMEM_LD32(tS + 96, sr, 96);
+#pragma unroll
+          for (int c0 = 0; c0 < kCols; c0 += 32) MAGI_TMEM_LD32(tSc + c0, sr, c0);
           tmem_wait_ld();
           if (nvalid < kTileN) {
 #pragma unroll
-            for (int c = 0; c < 128; ++c)
-              if (c >= nvalid) sr[c] = 0xff800000u;  // -inf
+            for (int c = 0; c < kCols; ++c)
+              if (ch * kCols + c >= nvalid) sr[c] = 0xff800000u;  // -inf
           }
         };
         load_s();
         if (tr) TRACE(t, j, 2);
 
-        // Row max over the 128 scores: 64 x FMNMX3 in four chains. For j > 0 it is NOT on the critical path: P is
+        // Row max over this thread's scores: FMNMX3 in four chains. For j > 0 it is NOT on the critical path: P is
         // computed optimistically against the running max m while the chains run on the ALU pipe next to it; only
         // if some row's max grew by more than 2^8 (rare) is the tile redone with the new max.
         float mxa, mxb, mxc, mxd;
-        auto max_step = [&](int k) {   // k = 0..31: consumes columns 4k .. 4k+3
+        auto max_step = [&](int k) {   // k = 0 .. kCols/4 - 1: consumes columns 4k .. 4k+3
           const float a0 = __uint_as_float(sr[4 * k]), a1 = __uint_as_float(sr[4 * k + 1]);
           const float a2 = __uint_as_float(sr[4 * k + 2]), a3 = __uint_as_float(sr[4 * k + 3]);
           if (k == 0) { mxa = fmaxf(a0, a1); mxb = fmaxf(a2, a3); mxc = mxa; mxd = mxb; }
@@ -308,12 +331,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           else { mxa = fmax3(mxa, a0, a1); mxb = fmax3(mxb, a2, a3); }
         };
         uint64_t sum_a, sum_b;
-        // columns [64 hf, 64 hf + 64) -> packed bf16 P in sr[64 hf .. 64 hf + 32) (in place), row sums accumulated
-        auto half = [&](const int hf, const uint64_t scale2, const uint64_t negm2, const bool with_max) {
+        // local columns [64 hl, 64 hl + 64) -> packed bf16 P in sr[64 hl .. 64 hl + 32) (in place), row sums accumulated
+        auto half = [&](const int hl, const uint64_t scale2, const uint64_t negm2, const bool with_max) {
 #pragma unroll
-          for (int c = 64 * hf; c < 64 * hf + 64; c += 2) {
+          for (int c = 64 * hl; c < 64 * hl + 64; c += 2) {
             const int pair = c >> 1;
-            if (with_max) max_step(pair - 32 * hf);   // 32 steps cover all 128 columns during the first half
+            // all kCols columns are covered by max steps during the first local half
+            if (with_max) {
+              if constexpr (kSplit == 1) max_step(pair);
+              else if ((pair & 1) == 0) max_step(pair >> 1);
+            }
             const uint64_t x2 = ffma2(pack_f2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), scale2, negm2);
             float x0, x1, p0, p1;
             unpack_f2(x2, x0, x1);
@@ -325,8 +352,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
             const uint64_t p2 = pack_f2(p0, p1);
             if (pair & 1) sum_b = fadd2(sum_b, p2); else sum_a = fadd2(sum_a, p2);
-            sr[64 * hf + ((c - 64 * hf) >> 1)] = pack_bf16x2(p0, p1);
+            sr[64 * hl + ((c - 64 * hl) >> 1)] = pack_bf16x2(p0, p1);
           }
+        };
+        auto local_max = [&]() { return fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd)); };
+        // publish the P half whose keys are [64 hg, 64 hg + 64) from local registers sr[64 hl ..]
+        auto publish = [&](int hl, int hg) {
+          MAGI_TMEM_ST32(tS + 64 * hg, sr, 64 * hl);
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar->p_half[t][hg]);
         };
 
         float alpha = 1.f;
@@ -336,8 +372,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         sum_b = sum_a;
         if (j == 0) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) max_step(k);
-          m = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
+          for (int k = 0; k < kCols / 4; ++k) max_step(k);
+          m = pair_max(local_max(), j & 1);
           if (tr) TRACE(t, j, 3);
           const float neg_m = -m * scale_log2;
           half(0, scale2, pack_f2(neg_m, neg_m), false);
@@ -345,10 +381,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           if (tr) TRACE(t, j, 3);
           const float neg_m = -m * scale_log2;
           half(0, scale2, pack_f2(neg_m, neg_m), true);
-          const float mx = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
+          const float mx = pair_max(local_max(), j & 1);
           need = (mx - m) * scale_log2 > kRescaleThreshold;
           if (__any_sync(0xffffffffu, need)) {
-            // rare: redo the first half against the new max and bring O back into range before P*V accumulates
+            // rare: redo the first half against the new max and bring O back into range before P*V accumulates.
+            // Both threads of a row see the same mx, hence take the same decision.
             if (need) {
               alpha = ex2_approx((m - mx) * scale_log2);
               m = mx;
@@ -359,7 +396,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             const float neg_m2 = -m * scale_log2;
             half(0, scale2, pack_f2(neg_m2, neg_m2), false);
 #pragma unroll 1
-            for (int c = 0; c < 128; c += 32) {
+            for (int c = 0; c < kCols; c += 32) {
               uint32_t orr[32];
               MAGI_TMEM_LD32(tO + c, orr, 0);
               tmem_wait_ld();
@@ -369,39 +406,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
           }
         }
-        // first 64 keys of P are final: hand them to the MMA issuer so P*V starts while the second half is computed
-        MAGI_TMEM_ST32(tS, sr, 0);
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar->p_half[t][0]);
+        // the first 64 keys this thread owns are final: hand them to the MMA issuer so that P*V starts early
+        publish(0, kSplit == 1 ? 0 : ch);
         if (tr) TRACE(t, j, 4);
-        {
+        if constexpr (kSplit == 1) {
           const float neg_m = -m * scale_log2;
           half(1, scale2, pack_f2(neg_m, neg_m), false);
+          if (tr) TRACE(t, j, 5);
+          publish(1, 1);
         }
-        MAGI_TMEM_ST32(tS + 32, sr, 64);
         float s0, s1;
         unpack_f2(fadd2(sum_a, sum_b), s0, s1);
         l = l * alpha + (s0 + s1);
-        tmem_wait_st();
-        if (tr) TRACE(t, j, 5);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar->p_half[t][1]);
         if (tr) TRACE(t, j, 6);
       }
 
       // ------------------------------------------------------------------ epilogue for this row
       __nv_bfloat16* orow = out + static_cast<int64_t>(row) * p.out_token_stride +
-                            static_cast<int64_t>(it.h) * p.out_head_stride;
+                            static_cast<int64_t>(it.h) * p.out_head_stride + ch * kCols;
       if (it.nt > 0) {
+        if constexpr (kSplit == 2) {   // total row sum = sum of the two column halves
+          bar->xl[t][ch][rowq] = l;
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+          l += bar->xl[t][ch ^ 1][rowq];
+        }
         mbar_wait(&bar->o_full[t], o_phase);
         o_phase ^= 1;
         tc_fence_after();
         const float inv_l = 1.f / l;
 #pragma unroll 1
-        for (int c = 0; c < 128; c += 32) {
+        for (int c = 0; c < kCols; c += 32) {
           uint32_t orr[32];
           MAGI_TMEM_LD32(tO + c, orr, 0);
           tmem_wait_ld();
@@ -420,20 +454,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar->o_free[t]);
-        if (row_valid && p.lse != nullptr)
+        if (row_valid && ch == 0 && p.lse != nullptr)
           p.lse[static_cast<int64_t>(row) * p.Hq + it.h] = (m * scale_log2 + log2f(l)) * 0.6931471805599453f;
       } else if (row_valid) {
         // empty key interval: zeros / -inf (flash-attn convention for seqlen_k == 0)
 #pragma unroll
-        for (int c = 0; c < 128; c += 8) *reinterpret_cast<uint4*>(orow + c) = make_uint4(0, 0, 0, 0);
-        if (p.lse != nullptr) p.lse[static_cast<int64_t>(row) * p.Hq + it.h] = -INFINITY;
+        for (int c = 0; c < kCols; c += 8) *reinterpret_cast<uint4*>(orow + c) = make_uint4(0, 0, 0, 0);
+        if (ch == 0 && p.lse != nullptr) p.lse[static_cast<int64_t>(row) * p.Hq + it.h] = -INFINITY;
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // ====================================================================== MMA issuer
     // The whole warp runs the loop (waits included) so that everything feeding the MMAs is warp-uniform; only the
     // tcgen05.mma / tcgen05.commit instructions themselves are issued by the elected lane.
-    setmaxnreg_dec<MAGI_AUX_REGS>();
+    if constexpr (kSplit == 1) setmaxnreg_dec<MAGI_AUX_REGS>();
     const uint32_t tb = uniform(tmem_base);
     const uint32_t tS0 = tb, tS1 = tb + 128, tO0 = tb + 256, tO1 = tb + 384;
     const uint64_t q0_desc = desc_kmajor(smem_u32(smem_q)), q1_desc = desc_kmajor(smem_u32(smem_q + kTileBytes));
@@ -536,9 +570,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       __syncwarp();
       ++item_cnt;
     }
-  } else if (warp == 9) {
+  } else if (warp == kTmaWarp) {
     // ====================================================================== TMA producer (same structure)
-    setmaxnreg_dec<MAGI_AUX_REGS>();
+    if constexpr (kSplit == 1) setmaxnreg_dec<MAGI_AUX_REGS>();
     uint32_t stage = 0, phase = 0;  // kv ring (producer side)
     uint32_t item_cnt = 0;
     for (int round = 0; round * static_cast<int>(gridDim.x) < total_items; ++round) {
@@ -584,12 +618,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       ++item_cnt;
     }
   } else {
-    setmaxnreg_dec<MAGI_AUX_REGS>();   // idle warps of the third warpgroup (setmaxnreg is warpgroup-collective)
+    if constexpr (kSplit == 1) setmaxnreg_dec<MAGI_AUX_REGS>();   // idle warps (setmaxnreg is warpgroup-collective)
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 512);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
 }
 
 #ifdef MAGI_TRACE
