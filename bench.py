@@ -51,6 +51,13 @@ def attn_flops(w):
     return self_f, cross_f
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE self-attention launch of the named workload, from the committed
+# `ncu --set full` capture (profiles/r01_ncu_final_raw.csv: 623.07 MB read + 199.84 MB written). The algorithmic
+# minimum (q + out + packed kv once) is 230 + 230 + 153 = 613 MB: K/V re-reads by the 3 query heads of a GQA group and by
+# the 37 query tiles of a chunk are served by L2.
+NCU_TRAFFIC_BYTES = {"cfg2": 822909440}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -428,7 +435,8 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "magi::attn_fwd_kernel (self-attention launch)",
                          "achieved": round(achieved, 1), "peak": peaks["sustained"], "unit": "TFLOP/s",
-                         "frac": round(achieved / peaks["sustained"], 3), "traffic": None,
+                         "frac": round(achieved / peaks["sustained"], 3),
+                         "traffic": NCU_TRAFFIC_BYTES.get(args.workload) if world == 1 else None,
                          "peak_source": peaks["source"] + ", sustained (kernel timed inside a long step); burst "
                                         f"{peaks['burst']} -> frac {achieved / peaks['burst']:.3f}",
                          "flops_per_launch": launch_flops, "avg_launch_ms": round(attn_avg_ms, 4),
