@@ -27,7 +27,10 @@ namespace {
 constexpr int kTileM = 128;               // query rows per softmax warpgroup
 constexpr int kPairM = 2 * kTileM;        // query rows per work item
 constexpr int kTileN = 128;               // keys per K/V tile
-constexpr int kStages = 4;                // K/V smem ring depth (tiles; K and V alternate)
+#ifndef MAGI_KV_STAGES
+#define MAGI_KV_STAGES 4
+#endif
+constexpr int kStages = MAGI_KV_STAGES;   // K/V smem ring depth (tiles; K and V alternate)
 constexpr int kBlkBytes = 128 * 64 * 2;   // one 64-column (128 B wide) swizzle block of a 128-row tile
 constexpr int kTileBytes = 2 * kBlkBytes; // 128 x 128 bf16
 #ifndef MAGI_COL_SPLIT
@@ -73,8 +76,9 @@ struct Barriers {
   uint64_t kv_full[kStages], kv_empty[kStages];
   uint64_t s_full[2], p_half[2][2], o_full[2], o_free[2];
   uint32_t tmem_base;
-  float xch[2][2][2][128];   // [parity][q tile][column half][row]: per-tile row-max exchange (kSplit == 2)
-  float xl[2][2][128];       // [q tile][column half][row]: row-sum exchange at the end of an item (kSplit == 2)
+  // exchange buffers of the two threads that share a row (only with MAGI_COL_SPLIT == 2)
+  float xch[kSplit == 2 ? 2 : 1][2][2][kSplit == 2 ? 128 : 1];   // [parity][q tile][column half][row]: row max
+  float xl[2][2][kSplit == 2 ? 128 : 1];                         // [q tile][column half][row]: row sum
 };
 
 constexpr int kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 1024 /*align slack*/ + sizeof(Barriers);
@@ -481,11 +485,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // O_t (+)= P_t V in two 64-key halves, each issued as soon as the softmax warpgroup has published that half of P
     auto pv = [&](uint32_t tO, uint32_t tS, int t, uint32_t& ph, uint32_t vst_, uint32_t acc) {
       const uint64_t vd = desc_v(kv_addr + vst_ * kTileBytes);
-      mbar_wait(&bar->p_half[t][0], ph);
+      mbar_wait_warp(&bar->p_half[t][0], ph);
       tc_fence_after();
       if (elect_one()) issue_pv(tO, tS, vd, acc, 0);
       __syncwarp();
-      mbar_wait(&bar->p_half[t][1], ph);
+      mbar_wait_warp(&bar->p_half[t][1], ph);
       tc_fence_after();
       if (elect_one()) issue_pv(tO, tS, vd, acc, 1);
       __syncwarp();
@@ -501,9 +505,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const int nt = uniform(it.nt);
       if (nt == 0) continue;
       const uint32_t o_free_parity = (item_cnt & 1) ^ 1;
-      mbar_wait(&bar->q_full, item_cnt & 1);
+      mbar_wait_warp(&bar->q_full, item_cnt & 1);
       // K_0 -> S0(0), S1(0)
-      mbar_wait(&bar->kv_full[stage], phase);
+      mbar_wait_warp(&bar->kv_full[stage], phase);
       tc_fence_after();
       uint32_t kst = stage;
       advance();
@@ -518,14 +522,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
       __syncwarp();
       // V_0 -> O0 = P0(0) V_0
-      mbar_wait(&bar->kv_full[stage], phase);
+      mbar_wait_warp(&bar->kv_full[stage], phase);
       uint32_t vst = stage;
       advance();
-      mbar_wait(&bar->o_free[0], o_free_parity);
+      mbar_wait_warp(&bar->o_free[0], o_free_parity);
       pv(tO0, tS0, 0, p_phase0, vst, 0);
       for (int i = 1; i < nt; ++i) {
         // K_i -> S0(i)   (P0(i-1) already consumed by the in-order PV0(i-1))
-        mbar_wait(&bar->kv_full[stage], phase);
+        mbar_wait_warp(&bar->kv_full[stage], phase);
         tc_fence_after();
         kst = stage;
         advance();
@@ -538,7 +542,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         __syncwarp();
         // O1 (+)= P1(i-1) V_{i-1} ; S1(i)
-        if (i == 1) mbar_wait(&bar->o_free[1], o_free_parity);
+        if (i == 1) mbar_wait_warp(&bar->o_free[1], o_free_parity);
         if (tr && lane == 0) TRACE(2, i, 2);
         pv(tO1, tS1, 1, p_phase1, vst, i > 1 ? 1u : 0u);
         if (elect_one()) {
@@ -551,7 +555,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         __syncwarp();
         // V_i -> O0 += P0(i) V_i
-        mbar_wait(&bar->kv_full[stage], phase);
+        mbar_wait_warp(&bar->kv_full[stage], phase);
         vst = stage;
         advance();
         if (tr && lane == 0) TRACE(2, i, 4);
@@ -559,7 +563,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (tr && lane == 0) { TRACE(2, i, 5); TRACE(2, i, 6); }
       }
       // O1 (+)= P1(nt-1) V_{nt-1}
-      if (nt == 1) mbar_wait(&bar->o_free[1], o_free_parity);
+      if (nt == 1) mbar_wait_warp(&bar->o_free[1], o_free_parity);
       if (elect_one()) tc_commit(&bar->o_full[0]);   // everything up to PV0(nt-1)
       __syncwarp();
       pv(tO1, tS1, 1, p_phase1, vst, nt > 1 ? 1u : 0u);
@@ -586,7 +590,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       it.h = uniform(it.h); it.hkv = uniform(it.hkv); it.qrow0 = uniform(it.qrow0);
       it.ka0 = uniform(it.ka0); it.ka1 = uniform(it.ka1); it.kb0 = uniform(it.kb0); it.kb1 = uniform(it.kb1);
       if (it.nt == 0) continue;
-      mbar_wait(&bar->q_empty, (item_cnt & 1) ^ 1);
+      mbar_wait_warp(&bar->q_empty, (item_cnt & 1) ^ 1);
       if (elect_one()) {
         mbar_expect_tx(&bar->q_full, 2 * kTileBytes);
 #pragma unroll
@@ -604,7 +608,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
         for (int kv = 0; kv < 2; ++kv) {
           const CUtensorMap* mm = kv == 0 ? mk : mv;
-          mbar_wait(&bar->kv_empty[stage], phase ^ 1);
+          mbar_wait_warp(&bar->kv_empty[stage], phase ^ 1);
           if (elect_one()) {
             mbar_expect_tx(&bar->kv_full[stage], kTileBytes);
             uint8_t* dst = smem_kv + stage * kTileBytes;

@@ -88,6 +88,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Whole-warp wait where only one lane polls (the issuer / producer warps share their scheduler with softmax warps:
+// 32 polling lanes cost the same issue slots as one, but a failed try_wait re-issues less often from one lane).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+#ifdef MAGI_POLL_ONE_LANE
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+#else
+  mbar_wait(bar, parity);
+#endif
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
