@@ -77,6 +77,13 @@ typedef struct magi_attn_args {
   void* workspace;     /* >= magi_attn_workspace_bytes(n_ranges) bytes of device memory        */
   size_t workspace_bytes;
   int32_t num_sms;     /* 0 = all SMs of the current device                                    */
+  /* Optional grouped output addressing (0 = off): head h is stored at
+   *   out + row * out_token_stride + (h / out_group_heads) * out_group_stride + (h % out_group_heads) * out_head_stride
+   * which lets self- and cross-attention write straight into the out-projection input of the reference,
+   * "sq b (n hn hd) -> sq b (hn n hd)", n = 2, hn = 8 (attn_linear_proj, dit_module.py:1332-1338): no cat, no
+   * rearrange copy. */
+  int32_t out_group_heads;
+  int64_t out_group_stride;
 } magi_attn_args;
 
 MAGI_API size_t magi_attn_workspace_bytes(int32_t n_ranges);

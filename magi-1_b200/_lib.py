@@ -58,6 +58,8 @@ class MagiAttnArgs(C.Structure):
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_size_t),
         ("num_sms", C.c_int32),
+        ("out_group_heads", C.c_int32),
+        ("out_group_stride", C.c_int64),
     ]
 
 

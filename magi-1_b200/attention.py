@@ -143,30 +143,39 @@ class FullyParallelAttention(nn.Module):
     def _ln(self, mod: HeadLayerNorm):
         return (mod.weight, mod.bias)
 
+    PROJ_GROUPS = 8   # "hn=8 is hardcoded to align with TP8 training and TP1 inference", dit_module.py:1337
+
     def core_attention(self, query, k_new, v_new, bs: int, meta_args: ModelMetaArgs, k_cache=None, v_cache=None,
-                       out=None):
+                       out=None, proj_buf=None):
         """dit_module.py:1023-1066 on "(sq b)"-ordered rows. bs > 1 only occurs with one range shared by all batch
-        rows (dit_module.py:1048-1061): each batch row is a strided view, no transposes or copies."""
+        rows (dit_module.py:1048-1061): each batch row is a strided view, no transposes or copies.
+        proj_buf: (sq*b, 2*Hq*128) out-projection input to write into (slot n = 0) instead of `out`."""
         p = meta_args.core_attn_params
-        if out is None:
+        if out is None and proj_buf is None:
             out = torch.empty_like(query)
-        if bs == 1:
-            F.attn_ranges(query, k_new, v_new, p.q_range, p.k_range, k_cache=k_cache, v_cache=v_cache, out=out,
-                          return_lse=False)
-            return out
-        assert not (bs > 1 and meta_args.denoising_range_num > 1)
-        assert k_cache is None
 
         def row(x, i):
             return x.unflatten(0, (-1, bs))[:, i]
 
+        def dest(i=None):
+            if proj_buf is not None:
+                return dict(proj_input=(proj_buf if i is None else row(proj_buf, i), 0, self.PROJ_GROUPS))
+            return dict(out=out if i is None else row(out, i))
+
+        if bs == 1:
+            F.attn_ranges(query, k_new, v_new, p.q_range, p.k_range, k_cache=k_cache, v_cache=v_cache,
+                          return_lse=False, **dest())
+            return out
+        assert not (bs > 1 and meta_args.denoising_range_num > 1)
+        assert k_cache is None
         for i in range(bs):
-            F.attn_ranges(row(query, i), row(k_new, i), row(v_new, i), p.q_range[:1], p.k_range[:1], out=row(out, i),
-                          return_lse=False)
+            F.attn_ranges(row(query, i), row(k_new, i), row(v_new, i), p.q_range[:1], p.k_range[:1],
+                          return_lse=False, **dest(i))
         return out
 
-    def cross_attention(self, mixed_qqkv, key_value_states, cross_attn_params: PackedCrossAttnParams):
-        """get_xqkv + cross_attention, dit_module.py:1005-1021, 1098-1136. Returns (sq, b, Hq*128)."""
+    def cross_attention(self, mixed_qqkv, key_value_states, cross_attn_params: PackedCrossAttnParams, proj_buf=None):
+        """get_xqkv + cross_attention, dit_module.py:1005-1021, 1098-1136. Returns (sq, b, Hq*128), or writes slot
+        n = 1 of the out-projection input `proj_buf` (sq*b, 2*Hq*128) and returns None."""
         sq, b, _ = mixed_qqkv.shape
         Hq, Hkv = self.model_config.num_attention_heads, self.model_config.num_query_groups
         eps, z = self.model_config.layernorm_epsilon, self.model_config.apply_layernorm_1p
@@ -176,7 +185,7 @@ class FullyParallelAttention(nn.Module):
         # text K: LayerNorm (bf16 params, no RoPE); V: copy -> packed (ytot, Hkv, 256)
         _, kv_x = F.qk_norm_rope(None, kvx[..., :F.HEAD_DIM], kvx[..., F.HEAD_DIM:], Hq, Hkv, None,
                                  self._ln(self.k_layernorm_xattn), None, None, eps=eps, zero_centered_gamma=z)
-        out = torch.empty((sq, b, Hq, F.HEAD_DIM), dtype=qx.dtype, device=qx.device)
+        out = None if proj_buf is not None else torch.empty((sq, b, Hq, F.HEAD_DIM), dtype=qx.dtype, device=qx.device)
         # q_ranges / kv_ranges (the flex_flash_attn_func arguments, dit_module.py:1111-1122) rather than cu_seqlens:
         # they stay valid when a caption segment is empty and after the per-rank rewrite under context parallelism
         n = cross_attn_params.q_ranges.shape[0]
@@ -190,14 +199,31 @@ class FullyParallelAttention(nn.Module):
             if i > 0:
                 qr = qr - i * sq
             kr = cross_attn_params.kv_ranges[i * per_b:(i + 1) * per_b]
-            F.attn_ranges(q_i, kv_x[..., :F.HEAD_DIM], kv_x[..., F.HEAD_DIM:], qr, kr, out=out[:, i],
-                          return_lse=False)
-        return out.view(sq, b, Hq * F.HEAD_DIM)
+            if proj_buf is not None:
+                dst = dict(proj_input=(proj_buf.view(sq, b, -1)[:, i], 1, self.PROJ_GROUPS))
+            else:
+                dst = dict(out=out[:, i])
+            F.attn_ranges(q_i, kv_x[..., :F.HEAD_DIM], kv_x[..., F.HEAD_DIM:], qr, kr, return_lse=False, **dst)
+        return None if proj_buf is not None else out.view(sq, b, Hq * F.HEAD_DIM)
 
     # ------------------------------------------------------------------ forward
+    @staticmethod
+    def attn_linear_proj_input(core_attn_out: torch.Tensor, cross_attn_out: torch.Tensor) -> torch.Tensor:
+        """What the reference builds before linear_proj (attn_linear_proj, dit_module.py:1332-1338): the torch
+        cat + rearrange that `forward(..., fused_proj_input=True)` makes unnecessary. Kept for callers that use the
+        two-output interface and as the checker of the fused layout."""
+        sq, b, w = core_attn_out.shape
+        x = torch.stack([core_attn_out, cross_attn_out], dim=2)                       # sq b n (hn hd)
+        x = x.view(sq, b, 2, FullyParallelAttention.PROJ_GROUPS, w // FullyParallelAttention.PROJ_GROUPS)
+        return x.transpose(2, 3).reshape(sq, b, 2 * w)                                # sq b (hn n hd)
+
     @torch.no_grad()
     def forward(self, hidden_states: torch.Tensor, key_value_states: torch.Tensor,
-                inference_params: Optional[InferenceParams], rotary_pos_emb: torch.Tensor, meta_args: ModelMetaArgs):
+                inference_params: Optional[InferenceParams], rotary_pos_emb: torch.Tensor, meta_args: ModelMetaArgs,
+                fused_proj_input: bool = False):
+        """Returns (core_attn_out, xattn_out) like the reference. With fused_proj_input=True (cp_strategy "none") both
+        attention kernels write straight into the out-projection input "sq b (hn n hd)" and that single tensor is
+        returned instead (no torch.cat, no rearrange copy)."""
         assert rotary_pos_emb is not None, "FullyParallelAttention needs rotary_pos_emb"
         sin_emb, cos_emb = rotary_pos_emb.tensor_split(2, -1)   # dit_module.py:1147: table is [sin | cos]
         sq, batch_size, _ = hidden_states.shape
@@ -218,11 +244,19 @@ class FullyParallelAttention(nn.Module):
             kc = vc = None
             if cache is not None and start > 0:
                 kc, vc = cache[:start, :, :F.HEAD_DIM], cache[:start, :, F.HEAD_DIM:]
+            if fused_proj_input:
+                buf = torch.empty((rows, 2 * Hq * F.HEAD_DIM), dtype=dt, device=dev)
+                self.core_attention(query, kv_new[..., :F.HEAD_DIM], kv_new[..., F.HEAD_DIM:], batch_size, meta_args,
+                                    kc, vc, proj_buf=buf)
+                self.cross_attention(mixed_qqkv, key_value_states, meta_args.cross_attn_params, proj_buf=buf)
+                return buf.view(sq, batch_size, 2 * Hq * F.HEAD_DIM)
             core = self.core_attention(query, kv_new[..., :F.HEAD_DIM], kv_new[..., F.HEAD_DIM:], batch_size,
                                        meta_args, kc, vc)
             core_attn_out = core.view(sq, batch_size, Hq * F.HEAD_DIM)
             xattn_out = self.cross_attention(mixed_qqkv, key_value_states, meta_args.cross_attn_params)
 
+        elif fused_proj_input:
+            raise NotImplementedError("fused_proj_input is available with cp_strategy 'none'")
         elif strategy == "cp_ulysses":
             core_attn_out, xattn_out = self._forward_ulysses(mixed_qqkv, key_value_states, inference_params, sin_emb,
                                                              cos_emb, meta_args)

@@ -177,6 +177,11 @@ int magi_attn_fwd(const magi_attn_args* a, void* stream_) {
   p.len_a = len_a;
   const float scale = a->softmax_scale > 0.f ? a->softmax_scale : 0.08838834764831845f;  // 1/sqrt(128)
   p.scale_log2 = scale * 1.4426950408889634f;
+  MAGI_CHECK(a->out_group_heads >= 0 && (a->out_group_heads == 0 || (a->num_heads_q % a->out_group_heads == 0 &&
+                                                                    a->out_group_stride % 8 == 0)),
+             "out_group_heads must divide num_heads_q and out_group_stride must be a multiple of 8 elements");
+  p.out_group_heads = a->out_group_heads;
+  p.out_group_stride = a->out_group_stride;
 
   int sms = a->num_sms;
   if (sms <= 0) { if (int r2 = device_sm_count(&sms)) return r2; }

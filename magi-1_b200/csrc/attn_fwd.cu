@@ -426,8 +426,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
 
       // ------------------------------------------------------------------ epilogue for this row
-      __nv_bfloat16* orow = out + static_cast<int64_t>(row) * p.out_token_stride +
-                            static_cast<int64_t>(it.h) * p.out_head_stride + ch * kCols;
+      const int64_t head_off =
+          p.out_group_heads > 0
+              ? static_cast<int64_t>(it.h / p.out_group_heads) * p.out_group_stride +
+                    static_cast<int64_t>(it.h % p.out_group_heads) * p.out_head_stride
+              : static_cast<int64_t>(it.h) * p.out_head_stride;
+      __nv_bfloat16* orow = out + static_cast<int64_t>(row) * p.out_token_stride + head_off + ch * kCols;
       if (it.nt > 0) {
         if constexpr (kSplit == 2) {   // total row sum = sum of the two column halves
           bar->xl[t][ch][rowq] = l;

@@ -14,6 +14,8 @@ struct AttnKernelParams {
   int Hq, Hkv;
   int len_a;                                  // rows of K/V segment A (KV-cache prefix)
   float scale_log2;                           // softmax_scale * log2(e)
+  int out_group_heads;                        // 0 = plain head stride; else grouped output addressing (magi_attn.h)
+  int64_t out_group_stride;
 };
 
 // workspace ints: [total_items, n, 0, 0][prefix n+1][q0 n][q1 n][k0 n][k1 n]

@@ -68,8 +68,13 @@ def attn_ranges(
     return_lse: bool = True,
     zero_fill: bool = False,
     num_sms: int = 0,
+    proj_input: Optional[Tuple[torch.Tensor, int, int]] = None,
 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Range-masked attention over keys = concat(k_cache, k_new) without materialising the concatenation.
+
+    proj_input = (buffer, n, hn): instead of a (Tq, Hq, 128) tensor, write the result straight into the reference's
+    out-projection input `buffer` (Tq, 2 * Hq * 128), laid out "(hn n hd)" with n = 0 for self-attention and n = 1
+    for cross-attention and hn = 8 head groups (attn_linear_proj, dit_module.py:1332-1338). Returns (buffer, lse).
 
     q (Tq, Hq, 128), k_*/v_* (T*, Hkv, 128) bf16 views (any token/head strides that are multiples of 8: the packed
     `(T, Hkv, 256)` KV tensor of the reference is passed as `kv[..., :128]`, `kv[..., 128:]`).
@@ -115,12 +120,28 @@ def attn_ranges(
         n = cu_seqlens_q.shape[0] - 1
 
     Tq = q.shape[0]
-    if out is None:
+    group_heads = group_stride = 0
+    if proj_input is not None:
+        buf, n_src, hn = proj_input
+        if out is not None:
+            raise ValueError("give either out or proj_input")
+        if (not buf.is_cuda or buf.dtype != torch.bfloat16 or buf.dim() != 2 or buf.shape != (Tq, 2 * Hq * HEAD_DIM)
+                or buf.stride(1) != 1 or Hq % hn != 0 or n_src not in (0, 1)):
+            raise ValueError(f"proj_input buffer must be a CUDA bf16 tensor ({Tq}, {2 * Hq * HEAD_DIM}); hn must divide Hq")
+        group_heads = Hq // hn
+        group_stride = 2 * group_heads * HEAD_DIM
+        out_ptr = buf.data_ptr() + n_src * group_heads * HEAD_DIM * 2
+        out_ts, out_hs = buf.stride(0), HEAD_DIM
+    elif out is None:
         out = (torch.zeros if zero_fill else torch.empty)((Tq, Hq, HEAD_DIM), dtype=torch.bfloat16, device=q.device)
     else:
         _check_thd(out, "out")
         if out.shape != q.shape:
             raise ValueError("out must have the shape of q")
+    if proj_input is None:
+        out_ptr, out_ts, out_hs = out.data_ptr(), out.stride(0), out.stride(1)
+    else:
+        out = proj_input[0]
     lse = None
     if return_lse:
         lse = torch.full((Tq, Hq), float("-inf"), dtype=torch.float32, device=q.device) if zero_fill else torch.empty(
@@ -135,8 +156,9 @@ def attn_ranges(
     a.q = _view(q)
     a.k_a, a.v_a = _view(segs[0][0]), _view(segs[0][1])
     a.k_b, a.v_b = _view(segs[1][0]), _view(segs[1][1])
-    a.out = out.data_ptr()
-    a.out_token_stride, a.out_head_stride = out.stride(0), out.stride(1)
+    a.out = out_ptr
+    a.out_token_stride, a.out_head_stride = out_ts, out_hs
+    a.out_group_heads, a.out_group_stride = group_heads, group_stride
     a.lse = lse.data_ptr() if lse is not None else None
     a.q_ranges = q_ranges.data_ptr() if by_ranges else None
     a.k_ranges = k_ranges.data_ptr() if by_ranges else None

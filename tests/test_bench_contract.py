@@ -1,0 +1,36 @@
+"""bench.py contract checks that run without a GPU: the reference arm (the oracle port timed on the host cores) prints
+exactly one JSON line with the keys the driver reads, and the FLOP accounting follows SURVEY.md section 8(d)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1",
+                        "--steps", "1", "--warmup", "0", "--ref-budget", "0.2"], capture_output=True, text=True,
+                       timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "chunk_causal_attn_tflops" and d["unit"] == "TFLOP/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_flop_accounting_matches_survey():
+    sys.path.insert(0, ROOT)
+    import bench
+    w = bench.WORKLOADS["cfg2"]
+    self_f, cross_f = bench.attn_flops(w)
+    # 4 * hd * Hq * sum_i Lq_i * Lk_i with k = 1..4 chunks of 9360: 10.77 TFLOP per layer
+    assert self_f == 4 * 128 * 24 * 9360 * 9360 * (1 + 2 + 3 + 4)
+    assert abs(self_f / 1e12 - 10.77) < 0.01
+    assert cross_f == 4 * 128 * 24 * 9360 * (50 + 512 + 512 + 512)
+    w4 = bench.WORKLOADS["cfg4"]
+    assert abs(bench.attn_flops(w4)[0] / 1e12 - 172.0) < 0.1

@@ -347,6 +347,91 @@ def test_full_attention_block_matches_reference_golden():
             assert x_out[:clip].abs().sum() == 0   # zero caption tokens -> zeros (dit_module.py:1124 semantics)
 
 
+def test_fused_out_projection_input_layout():
+    """both attention kernels write straight into the reference's out-projection input
+    "sq b (n hn hd) -> sq b (hn n hd)", n = 2, hn = 8 (attn_linear_proj, dit_module.py:1332-1338). Must equal
+    cat + rearrange of the two separate outputs bit for bit (batch 1 and the batched uncond pass)."""
+    from magi_b200.attention import FullyParallelAttention
+    from magi_b200.common import (EngineConfig, InferenceParams, ModelConfig, ModelMetaArgs, PackedCoreAttnParams,
+                                  PackedCrossAttnParams)
+    torch.manual_seed(0)
+    Hq, Hkv, hidden, clip = 16, 8, 256, 150
+    mc = ModelConfig(num_layers=2, hidden_size=hidden, num_attention_heads=Hq, num_query_groups=Hkv)
+    attn = FullyParallelAttention(mc, EngineConfig(), layer_number=0)
+    with torch.no_grad():
+        for n_, p_ in attn.named_parameters():
+            p_.copy_((torch.randn(p_.shape) * (0.2 if "layernorm" in n_ else p_.shape[-1] ** -0.5)).to(p_.dtype))
+    for n_ in ("q_layernorm", "k_layernorm"):
+        getattr(attn, n_).float()
+    attn = attn.cuda().eval()
+    for bs, dn in ((1, 3), (2, 1)):
+        S = dn * clip
+        y_index = [40, 77, 13][:dn * bs] if bs == 1 else [40, 77]
+        p = O.cross_attn_params(clip, dn, bs, y_index)
+        q_range = O.core_q_ranges(clip, dn, bs)
+        k_range = np.array([[0, (i + 1) * clip] for i in range(dn)], dtype=np.int32) if bs == 1 else q_range[:1].copy()
+        core = PackedCoreAttnParams(i32(q_range), i32(k_range), q_range, k_range, clip, O.max_seqlen_k(k_range))
+        cross = PackedCrossAttnParams(i32(p["q_ranges"]), i32(p["kv_ranges"]), i32(p["cu_seqlens_q"]),
+                                      i32(p["cu_seqlens_kv"]), clip, 800)
+        meta = ModelMetaArgs(H=1, W=1, cp_pad_size=None, cp_split_sizes=None, slice_point=0, denoising_range_num=dn,
+                             range_num=dn, extract_prefix_video_feature=False, fwd_extra_1st_chunk=False,
+                             distill_nearly_clean_chunk=False, clip_token_nums=clip, enable_cuda_graph=False,
+                             core_attn_params=core, cross_attn_params=cross)
+        hs = torch.randn(S, bs, hidden, device="cuda").to(torch.bfloat16)
+        kvs = torch.randn(sum(y_index), hidden, device="cuda").to(torch.bfloat16)
+        ang = torch.rand(S, 48, device="cuda") * 6.28
+        rope = torch.cat([torch.sin(ang), torch.cos(ang)], -1)
+        inf = InferenceParams(1, 4 * clip) if bs == 1 else None
+        core_out, x_out = attn(hs, kvs, inf, rope, meta)
+        fused = attn(hs, kvs, inf, rope, meta, fused_proj_input=True)
+        ref = FullyParallelAttention.attn_linear_proj_input(core_out, x_out)
+        # the reference's own expression of the same re-layout
+        from einops import rearrange
+        ref2 = rearrange(torch.cat([core_out, x_out], dim=2), "sq b (n hn hd) -> sq b (hn n hd)", n=2, hn=8)
+        assert torch.equal(ref, ref2)
+        assert fused.shape == ref.shape and torch.equal(fused, ref), f"bs={bs}"
+
+
+def test_hot_path_is_cuda_graph_capturable(F):
+    """include/magi_attn.h promises no host reads of the ranges, no device sync and no hidden state: the prologue +
+    range attention sequence is captured into a CUDA graph once and replayed on new inputs (same buffers)."""
+    S, Hq, Hkv = 700, 6, 2
+    xq = torch.zeros(S, Hq * 128, device="cuda", dtype=torch.bfloat16)
+    xk = torch.zeros(S, Hkv * 128, device="cuda", dtype=torch.bfloat16)
+    xv = torch.zeros(S, Hkv * 128, device="cuda", dtype=torch.bfloat16)
+    ln = [torch.randn(128, device="cuda") * 0.2 for _ in range(4)]
+    ang = torch.rand(S, 48, device="cuda") * 6.28
+    sin, cos = torch.sin(ang), torch.cos(ang)
+    qr, kr = i32([[0, 350], [350, 700]]), i32([[0, 350], [100, 700]])
+    cache = torch.zeros(S, Hkv, 256, device="cuda", dtype=torch.bfloat16)
+
+    def run():
+        q, kv = F.qk_norm_rope(xq, xk, xv, Hq, Hkv, (ln[0], ln[1]), (ln[2], ln[3]), sin, cos, cache=cache,
+                               cache_row_offset=0, cache_rows=S)
+        return F.attn_ranges(q, kv[..., :128], kv[..., 128:], qr, kr)
+
+    def fill(seed):
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        for t in (xq, xk, xv):
+            t.copy_(torch.randn(t.shape, device="cuda", generator=g).to(torch.bfloat16))
+
+    fill(1)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        run()                                  # warm-up outside capture
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out_g, lse_g = run()
+    for seed in (2, 3):
+        fill(seed)
+        graph.replay()
+        torch.cuda.synchronize()
+        out_e, lse_e = run()                   # eager on the same inputs
+        assert torch.equal(out_g, out_e) and torch.equal(lse_g, lse_e), f"replay {seed}"
+        assert torch.equal(cache, torch.cat([cache[..., :128], xv.view(S, Hkv, 128)], -1))
+
+
 # ------------------------------------------------------------------------------------------ full-size properties
 CLIP = 9360   # 480x832, BASELINE.json configs[1]
 
