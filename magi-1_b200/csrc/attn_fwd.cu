@@ -27,9 +27,13 @@ namespace {
 constexpr int kTileM = 128;               // query rows per softmax warpgroup
 constexpr int kPairM = 2 * kTileM;        // query rows per work item
 constexpr int kTileN = 128;               // keys per K/V tile
-#ifndef MAGI_KV_STAGES
-#define MAGI_KV_STAGES 4
+#ifndef MAGI_Q_STAGES
+#define MAGI_Q_STAGES 1     // 2: the next item's Q tiles are prefetched while the current item runs (short-K items)
 #endif
+#ifndef MAGI_KV_STAGES
+#define MAGI_KV_STAGES (MAGI_Q_STAGES == 1 ? 4 : 3)   // smem: (2 * Q stages + KV stages) * 32 KB <= 224 KB
+#endif
+constexpr int kQStages = MAGI_Q_STAGES;
 constexpr int kStages = MAGI_KV_STAGES;   // K/V smem ring depth (tiles; K and V alternate)
 constexpr int kBlkBytes = 128 * 64 * 2;   // one 64-column (128 B wide) swizzle block of a 128-row tile
 constexpr int kTileBytes = 2 * kBlkBytes; // 128 x 128 bf16
@@ -72,7 +76,7 @@ __device__ long long g_trace[3][512][8];
 #endif
 
 struct Barriers {
-  uint64_t q_full, q_empty;
+  uint64_t q_full[kQStages], q_empty[kQStages];
   uint64_t kv_full[kStages], kv_empty[kStages];
   uint64_t s_full[2], p_half[2][2], o_full[2], o_free[2];
   uint32_t tmem_base;
@@ -81,7 +85,8 @@ struct Barriers {
   float xl[2][2][kSplit == 2 ? 128 : 1];                         // [q tile][column half][row]: row sum
 };
 
-constexpr int kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 1024 /*align slack*/ + sizeof(Barriers);
+constexpr int kSmemBytes = (2 * kQStages + kStages) * kTileBytes + 1024 /*align slack*/ + sizeof(Barriers);
+static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 
 struct Item {
   int q_begin, q_end;  // query rows of this item's range
@@ -220,9 +225,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 const __grid_constant__ CUtensorMap tm_vb, const AttnKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_q = smem;                    // 2 tiles
-  uint8_t* smem_kv = smem + 2 * kTileBytes;  // kStages tiles
-  Barriers* bar = reinterpret_cast<Barriers*>(smem + (2 + kStages) * kTileBytes);
+  uint8_t* smem_q = smem;                               // kQStages x 2 tiles
+  uint8_t* smem_kv = smem + 2 * kQStages * kTileBytes;  // kStages tiles
+  Barriers* bar = reinterpret_cast<Barriers*>(smem + (2 * kQStages + kStages) * kTileBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -230,8 +235,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int* __restrict__ ws = p.work;
 
   if (threadIdx.x == 0) {
-    mbar_init(&bar->q_full, 1);
-    mbar_init(&bar->q_empty, 1);
+    for (int s = 0; s < kQStages; ++s) {
+      mbar_init(&bar->q_full[s], 1);
+      mbar_init(&bar->q_empty[s], 1);
+    }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&bar->kv_full[s], 1);
       mbar_init(&bar->kv_empty[s], 1);
@@ -478,7 +485,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if constexpr (kSplit == 1) setmaxnreg_dec<MAGI_AUX_REGS>();
     const uint32_t tb = uniform(tmem_base);
     const uint32_t tS0 = tb, tS1 = tb + 128, tO0 = tb + 256, tO1 = tb + 384;
-    const uint64_t q0_desc = desc_kmajor(smem_u32(smem_q)), q1_desc = desc_kmajor(smem_u32(smem_q + kTileBytes));
+    const uint64_t q_desc_base = desc_kmajor(smem_u32(smem_q));
     const uint32_t kv_addr = smem_u32(smem_kv);
     uint32_t stage = 0, phase = 0;  // kv ring (consumer side)
     uint32_t p_phase0 = 0, p_phase1 = 0;
@@ -509,7 +516,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const int nt = uniform(it.nt);
       if (nt == 0) continue;
       const uint32_t o_free_parity = (item_cnt & 1) ^ 1;
-      mbar_wait_warp(&bar->q_full, item_cnt & 1);
+      const uint32_t qs = item_cnt % kQStages;                       // Q stage of this item
+      const uint64_t q0_desc = q_desc_base + static_cast<uint64_t>((qs * 2 * kTileBytes) >> 4);
+      const uint64_t q1_desc = q0_desc + static_cast<uint64_t>(kTileBytes >> 4);
+      mbar_wait_warp(&bar->q_full[qs], (item_cnt / kQStages) & 1);
       // K_0 -> S0(0), S1(0)
       mbar_wait_warp(&bar->kv_full[stage], phase);
       tc_fence_after();
@@ -522,7 +532,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         issue_qk(tS1, q1_desc, kd);
         tc_commit(&bar->s_full[1]);
         tc_commit(&bar->kv_empty[kst]);
-        if (nt == 1) tc_commit(&bar->q_empty);
+        if (nt == 1) tc_commit(&bar->q_empty[qs]);
       }
       __syncwarp();
       // V_0 -> O0 = P0(0) V_0
@@ -554,7 +564,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           issue_qk(tS1, q1_desc, desc_kmajor(kv_addr + kst * kTileBytes));
           tc_commit(&bar->s_full[1]);
           tc_commit(&bar->kv_empty[kst]);
-          if (i == nt - 1) tc_commit(&bar->q_empty);
+          if (i == nt - 1) tc_commit(&bar->q_empty[qs]);
           if (tr) TRACE(2, i, 3);
         }
         __syncwarp();
@@ -594,13 +604,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       it.h = uniform(it.h); it.hkv = uniform(it.hkv); it.qrow0 = uniform(it.qrow0);
       it.ka0 = uniform(it.ka0); it.ka1 = uniform(it.ka1); it.kb0 = uniform(it.kb0); it.kb1 = uniform(it.kb1);
       if (it.nt == 0) continue;
-      mbar_wait_warp(&bar->q_empty, (item_cnt & 1) ^ 1);
+      const uint32_t qs = item_cnt % kQStages;
+      mbar_wait_warp(&bar->q_empty[qs], ((item_cnt / kQStages) & 1) ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(&bar->q_full, 2 * kTileBytes);
+        uint8_t* qdst = smem_q + qs * 2 * kTileBytes;
+        mbar_expect_tx(&bar->q_full[qs], 2 * kTileBytes);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-          tma_load_3d(smem_q + t * kTileBytes, &tm_q, &bar->q_full, 0, it.h, it.qrow0 + t * kTileM);
-          tma_load_3d(smem_q + t * kTileBytes + kBlkBytes, &tm_q, &bar->q_full, 64, it.h, it.qrow0 + t * kTileM);
+          tma_load_3d(qdst + t * kTileBytes, &tm_q, &bar->q_full[qs], 0, it.h, it.qrow0 + t * kTileM);
+          tma_load_3d(qdst + t * kTileBytes + kBlkBytes, &tm_q, &bar->q_full[qs], 64, it.h, it.qrow0 + t * kTileM);
         }
       }
       __syncwarp();

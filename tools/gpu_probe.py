@@ -184,6 +184,44 @@ def q_bench_single():
 
 
 @case
+def s_bench_cross():
+    """cross-attention of the cfg2 state: 4 q segments of 9360 rows x caption segments of 50/512/512/512 tokens,
+    and the cfg1 self-attention (1536 x 1536): both dominated by per-item overheads, not by the tile loop."""
+    import torch
+    import magi_b200.functional as F
+    dev = "cuda"
+    clip, Hq, Hkv = 9360, 24, 8
+    text = [50, 512, 512, 512]
+    q = torch.randn(4 * clip, Hq, 128, device=dev, dtype=torch.bfloat16)
+    kv = torch.randn(sum(text), Hkv, 256, device=dev, dtype=torch.bfloat16)
+    cu_q = torch.tensor([i * clip for i in range(5)], dtype=torch.int32, device=dev)
+    cu_k = torch.tensor([0, 50, 562, 1074, 1586], dtype=torch.int32, device=dev)
+    out = torch.empty_like(q)
+    q1 = torch.randn(1536, Hq, 128, device=dev, dtype=torch.bfloat16)
+    kv1 = torch.randn(1536, Hkv, 256, device=dev, dtype=torch.bfloat16)
+    r1 = torch.tensor([[0, 1536]], dtype=torch.int32, device=dev)
+    o1 = torch.empty_like(q1)
+    cases = [("cross-attn cfg2", 4 * 128 * Hq * clip * sum(text),
+              lambda: F.attn_ranges(q, kv[..., :128], kv[..., 128:], cu_seqlens_q=cu_q, cu_seqlens_k=cu_k, out=out,
+                                    return_lse=False)),
+             ("self-attn cfg1 1536x1536", 4 * 128 * Hq * 1536 * 1536,
+              lambda: F.attn_ranges(q1, kv1[..., :128], kv1[..., 128:], r1, r1, out=o1, return_lse=False))]
+    for nm, flops, fn in cases:
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        best = min(ts)
+        print(f"[{nm}] {flops/1e12:.3f} TFLOP  best {best*1e3:.1f} us -> {flops/best/1e9:.1f} TFLOP/s", flush=True)
+    return True
+
+
+@case
 def r_bench_prologue():
     """cfg2 shapes: 37440 rows x (24 q + 8 k + 8 v heads), KV-cache append of all rows."""
     import torch
