@@ -9,10 +9,11 @@
 // CTA = 384 threads, persistent (one per SM), one work item = 256 query rows x 1 query head x one range:
 //   warps 0-3   softmax warpgroup 0 : rows [0,128)   of the item, owns S0/P0/O0 in TMEM
 //   warps 4-7   softmax warpgroup 1 : rows [128,256) of the item, owns S1/P1/O1 in TMEM
-//   warp  8     tcgen05.mma issuer (one lane) + TMEM allocator
-//   warp  9     TMA producer (one lane)
+//   warp  8     tcgen05.mma issuer (warp-uniform loop, elect.sync around the issue) + TMEM allocator
+//   warp  9     TMA producer (same structure)
 //   warps 10-11 idle (keep warpgroup granularity)
-// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P_t (bf16) aliases the first 64 columns of S_t.
+// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P_t (bf16) is written in place over S_t in two
+// 64-key halves (columns [0,32) and [64,96) of S_t).
 // One thread owns one query row (tcgen05.ld 32x32b), so row max / row sum need no cross-thread reduction.
 #include <math.h>
 #include <stdio.h>
