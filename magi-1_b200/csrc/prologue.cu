@@ -132,6 +132,18 @@ __global__ void __launch_bounds__(256, MAGI_PRO_BLOCKS) prologue_kernel(const Pr
         }
       }
 
+      // destination bases of this (row, tensor): q_out, or the K / V half of the packed kv row (and of the cache row)
+      __nv_bfloat16* out_base = type == 0 ? reinterpret_cast<__nv_bfloat16*>(p.q_out)
+                                          : reinterpret_cast<__nv_bfloat16*>(p.kv_out) + (type == 2 ? 128 : 0);
+      const int64_t out_tstride = type == 0 ? p.q_out_token_stride : p.kv_out_token_stride;
+      const int64_t out_hstride = type == 0 ? p.q_out_head_stride : p.kv_out_head_stride;
+      __nv_bfloat16* out_row = out_base + r * out_tstride;
+      __nv_bfloat16* cache_row =
+          (type != 0 && p.cache != nullptr && r < p.cache_rows)
+              ? reinterpret_cast<__nv_bfloat16*>(p.cache) + (p.cache_row_offset + r) * p.cache_token_stride +
+                    (type == 2 ? 128 : 0)
+              : nullptr;
+
       for (int h0 = 0; h0 < H; h0 += 2 * kUnroll) {
         uint2 ra[kUnroll], rb[kUnroll];
 #pragma unroll
@@ -163,7 +175,7 @@ __global__ void __launch_bounds__(256, MAGI_PRO_BLOCKS) prologue_kernel(const Pr
 #pragma unroll
             for (int i = 0; i < 8; ++i) { v[i] -= mean; sq += v[i] * v[i]; }
             const float var = half_warp_sum(sq) * (1.0f / 128.0f);
-            const float rstd = 1.0f / sqrtf(var + p.eps);
+            const float rstd = rsqrtf(var + p.eps);   // MUFU.RSQ (2 ulp in fp32: invisible after the bf16 rounding)
             float y[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) y[i] = v[i] * rstd * wf[i] + bf[i];
@@ -181,33 +193,29 @@ __global__ void __launch_bounds__(256, MAGI_PRO_BLOCKS) prologue_kernel(const Pr
           }
           if (!valid) continue;
 
-          // ---- stores: attention (or all-to-all send) layout, plus the fused KV-cache append
+          // ---- stores: attention (or all-to-all send) layout, plus the fused KV-cache append.
+          // Row bases were hoisted out of the head loop; without head permutation (cp == 1) a head costs one
+          // multiply-add per target - no integer divisions on the common path.
           auto store = [&](__nv_bfloat16* dst) {
             *reinterpret_cast<uint2*>(dst + off0) = pa;
             *reinterpret_cast<uint2*>(dst + off1) = pb;
           };
-          if (type == 0) {
+          if (cp == 1) {
+            store(out_row + h * out_hstride);
+            if (cache_row != nullptr) store(cache_row + h * p.cache_head_stride);
+          } else if (type == 0) {
             const int hn = p.Hq / cp;
-            const int64_t drow = static_cast<int64_t>(h / hn) * p.rows + r;
-            store(reinterpret_cast<__nv_bfloat16*>(p.q_out) + drow * p.q_out_token_stride +
-                  static_cast<int64_t>(h % hn) * p.q_out_head_stride);
+            store(out_base + (static_cast<int64_t>(h / hn) * p.rows + r) * out_tstride +
+                  static_cast<int64_t>(h % hn) * out_hstride);
+          } else if (cp > p.Hkv) {
+            // fewer kv heads than ranks: replicate (repeat_interleave, context_parallel.py:393-394)
+            const int rep = cp / p.Hkv;
+            for (int c = h * rep; c < (h + 1) * rep; ++c)
+              store(out_base + (static_cast<int64_t>(c) * p.rows + r) * out_tstride);
           } else {
-            const int col = type == 2 ? 128 : 0;
-            if (cp > p.Hkv) {
-              // fewer kv heads than ranks: replicate (repeat_interleave, context_parallel.py:393-394)
-              const int rep = cp / p.Hkv;
-              for (int c = h * rep; c < (h + 1) * rep; ++c)
-                store(reinterpret_cast<__nv_bfloat16*>(p.kv_out) +
-                      (static_cast<int64_t>(c) * p.rows + r) * p.kv_out_token_stride + col);
-            } else {
-              const int hn = p.Hkv / cp;
-              const int64_t drow = static_cast<int64_t>(h / hn) * p.rows + r;
-              store(reinterpret_cast<__nv_bfloat16*>(p.kv_out) + drow * p.kv_out_token_stride +
-                    static_cast<int64_t>(h % hn) * p.kv_out_head_stride + col);
-            }
-            if (p.cache != nullptr && r < p.cache_rows)
-              store(reinterpret_cast<__nv_bfloat16*>(p.cache) + (p.cache_row_offset + r) * p.cache_token_stride +
-                    static_cast<int64_t>(h) * p.cache_head_stride + col);
+            const int hn = p.Hkv / cp;
+            store(out_base + (static_cast<int64_t>(h / hn) * p.rows + r) * out_tstride +
+                  static_cast<int64_t>(h % hn) * out_hstride);
           }
         }
       }
