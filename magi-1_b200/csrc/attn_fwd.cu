@@ -11,15 +11,9 @@
 //   warps 4-7   softmax warpgroup 1 : rows [128,256) of the item, owns S1/P1/O1 in TMEM
 //   warp  8     tcgen05.mma issuer (warp-uniform loop, elect.sync around the issue) + TMEM allocator
 //   warp  9     TMA producer (same structure)
-//   warps 10-11 idle (keep warpgroup granularity for setmaxnreg)
-// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512).
-//
-// The pipeline unit is a 64-key HALF of a K/V tile. S_t is two independent 64-column buffers S_t,a | S_t,b; the
-// softmax warpgroup turns S_t,h into bf16 P_t,h in place (first 32 columns of that half) and publishes it; the issuer
-// runs   ... PV_t,a(i) ; S_t,a(i+1) ; PV_t,b(i) ; S_t,b(i+1) ...   so the next scores of one half are produced while the
-// warpgroup is still exponentiating the other half: the softmax warps never wait for the tensor core and the
-// S -> softmax -> P*V -> S dependency chain of a whole tile (which bounded the first versions at ~60 % tensor-pipe
-// utilisation) is cut in two overlapping halves.
+//   warps 10-11 idle (keep warpgroup granularity)
+// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P_t (bf16) is written in place over S_t in two
+// 64-key halves (columns [0,32) and [64,96) of S_t).
 // One thread owns one query row (tcgen05.ld 32x32b), so row max / row sum need no cross-thread reduction.
 #include <math.h>
 #include <stdio.h>
@@ -34,7 +28,6 @@ namespace {
 constexpr int kTileM = 128;               // query rows per softmax warpgroup
 constexpr int kPairM = 2 * kTileM;        // query rows per work item
 constexpr int kTileN = 128;               // keys per K/V tile
-constexpr int kHalfN = 64;                // keys per pipeline unit
 #ifndef MAGI_Q_STAGES
 #define MAGI_Q_STAGES 1     // 2: the next item's Q tiles are prefetched while the current item runs (short-K items)
 #endif
@@ -45,12 +38,18 @@ constexpr int kQStages = MAGI_Q_STAGES;
 constexpr int kStages = MAGI_KV_STAGES;   // K/V smem ring depth (tiles; K and V alternate)
 constexpr int kBlkBytes = 128 * 64 * 2;   // one 64-column (128 B wide) swizzle block of a 128-row tile
 constexpr int kTileBytes = 2 * kBlkBytes; // 128 x 128 bf16
-constexpr int kSoftmaxWarps = 8;
-constexpr int kMmaWarp = 8;               // tcgen05 issuer + TMEM allocator
-constexpr int kTmaWarp = 9;
-constexpr int kThreads = 384;
-constexpr uint32_t kIdescQK = make_idesc_bf16(128, kHalfN, 0, 0);   // S_t,h = Q_t (128 x 128) . K_h^T (128 x 64)
-constexpr uint32_t kIdescPV = make_idesc_bf16(128, 128, 0, 1);      // O_t += P_t,h (128 x 64) . V_h (64 x 128)
+#ifndef MAGI_COL_SPLIT
+#define MAGI_COL_SPLIT 1   // 1: one thread owns a whole 128-column row of S_t; 2: two threads (two warps) share it
+#endif
+constexpr int kSplit = MAGI_COL_SPLIT;
+static_assert(kSplit == 1 || kSplit == 2, "MAGI_COL_SPLIT must be 1 or 2");
+constexpr int kCols = 128 / kSplit;              // S columns per softmax thread
+constexpr int kSoftmaxWarps = 8 * kSplit;
+constexpr int kMmaWarp = kSoftmaxWarps;          // tcgen05 issuer + TMEM allocator
+constexpr int kTmaWarp = kSoftmaxWarps + 1;
+constexpr int kThreads = kSplit == 1 ? 384 : 576;   // 12 warps (3 warpgroups, setmaxnreg) or 18 warps (112 regs each)
+constexpr uint32_t kIdescQK = make_idesc_bf16(128, 128, 0, 0);
+constexpr uint32_t kIdescPV = make_idesc_bf16(128, 128, 0, 1);
 constexpr float kRescaleThreshold = 8.0f; // log2 units: lazily rescale O only when the row max grew by > 2^8
 #ifndef MAGI_EMU_MOD
 #define MAGI_EMU_MOD 3                    // every MAGI_EMU_MOD-th column pair takes the polynomial exp2 (0 = never)
@@ -63,12 +62,13 @@ constexpr float kRescaleThreshold = 8.0f; // log2 units: lazily rescale O only w
 #endif
 // setmaxnreg only moves registers inside the pool the CTA was launched with (384 threads x 168 registers): asking
 // for more blocks the second softmax warpgroup forever.
-static_assert(256 * MAGI_SOFTMAX_REGS + 128 * MAGI_AUX_REGS <= 384 * 168, "register pool of the CTA exceeded");
+static_assert(kSplit != 1 || 256 * MAGI_SOFTMAX_REGS + 128 * MAGI_AUX_REGS <= 384 * 168,
+              "register pool of the CTA exceeded");
 static_assert(MAGI_SOFTMAX_REGS % 8 == 0 && MAGI_AUX_REGS % 8 == 0, "setmaxnreg takes multiples of 8");
 constexpr int kEmuMod = MAGI_EMU_MOD;
 
 #ifdef MAGI_TRACE
-// Debug build only: clock64 stamps of CTA 0 (warp 0 of each softmax warpgroup, and the MMA issuer), first 512 units.
+// Debug build only: clock64 stamps of CTA 0 (warp 0 of each softmax warpgroup, and the MMA issuer), first 512 tiles.
 __device__ long long g_trace[3][512][8];
 #define TRACE(who, idx, slot) \
   do { if (blockIdx.x == 0 && (idx) < 512) g_trace[who][idx][slot] = clock64(); } while (0)
@@ -79,10 +79,11 @@ __device__ long long g_trace[3][512][8];
 struct Barriers {
   uint64_t q_full[kQStages], q_empty[kQStages];
   uint64_t kv_full[kStages], kv_empty[kStages];
-  uint64_t s_full[2][2];   // [q tile][key half]: S_t,h written (and every earlier MMA of the issuer complete)
-  uint64_t p_full[2][2];   // [q tile][key half]: P_t,h published by the softmax warpgroup
-  uint64_t o_free[2];      // O_t drained by the epilogue: the next item may overwrite it
+  uint64_t s_full[2], p_half[2][2], o_full[2], o_free[2];
   uint32_t tmem_base;
+  // exchange buffers of the two threads that share a row (only with MAGI_COL_SPLIT == 2)
+  float xch[kSplit == 2 ? 2 : 1][2][2][kSplit == 2 ? 128 : 1];   // [parity][q tile][column half][row]: row max
+  float xl[2][2][kSplit == 2 ? 128 : 1];                         // [q tile][column half][row]: row sum
 };
 
 constexpr int kSmemBytes = (2 * kQStages + kStages) * kTileBytes + 1024 /*align slack*/ + sizeof(Barriers);
@@ -150,24 +151,25 @@ __device__ __forceinline__ void tile_info(const Item& it, int j, int& seg, int& 
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) { return make_smem_desc_sw128(addr, 16, 1024); }
 __device__ __forceinline__ uint64_t desc_v(uint32_t addr) { return make_smem_desc_sw128(addr, kBlkBytes, 1024); }
 
-// S_t,h [128 x 64] = Q_t [128 x 128(hd)] . K[64h .. 64h+64)[128(hd)]^T ; both operands K-major, 128B-swizzled, two
-// 64-wide hd blocks; key row 64h starts 64 * 128 B into each block.
-__device__ __forceinline__ void issue_qk(uint32_t d_tmem, uint64_t q_desc, uint64_t k_desc, int h) {
+// S[128 x 128] = Q[128 x 128(hd)] * K[128 x 128(hd)]^T ; both operands K-major, 128B-swizzled, two 64-wide blocks.
+__device__ __forceinline__ void issue_qk(uint32_t d_tmem, uint64_t q_desc, uint64_t k_desc) {
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks) {
     const uint64_t off = static_cast<uint64_t>(((ks >> 2) * kBlkBytes + (ks & 3) * 32) >> 4);
-    mma_ss(d_tmem, q_desc + off, k_desc + off + static_cast<uint64_t>((h * kHalfN * 128) >> 4), kIdescQK,
-           ks > 0 ? 1u : 0u);
+    mma_ss(d_tmem, q_desc + off, k_desc + off, kIdescQK, ks > 0 ? 1u : 0u);
   }
 }
 
-// O_t [128 x 128(hd)] (+)= P_t,h [128 x 64(keys)] . V[64h .. 64h+64)[128(hd)] ; P from TMEM (bf16, 2 per column),
+// O[128 x 128(hd)] (+)= P[128 x 128(keys)] * V[128(keys) x 128(hd)] ; P from TMEM (bf16, 2 per column),
 // V is MN-major (head_dim contiguous): 8-key groups 1024 B apart (SBO), 64-wide hd blocks kBlkBytes apart (LBO).
-__device__ __forceinline__ void issue_pv(uint32_t d_tmem, uint32_t p_tmem, uint64_t v_desc, uint32_t accumulate, int h) {
+// `half` selects keys [64 half, 64 half + 64) of the tile (k-steps 4 half .. 4 half + 3).
+__device__ __forceinline__ void issue_pv(uint32_t d_tmem, uint32_t p_tmem, uint64_t v_desc, uint32_t accumulate,
+                                         int half) {
 #pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    mma_ts(d_tmem, p_tmem + ks * 8, v_desc + static_cast<uint64_t>(((4 * h + ks) * 2048) >> 4), kIdescPV,
-           (accumulate | (ks > 0)) ? 1u : 0u);
+  for (int ks = 4 * half; ks < 4 * half + 4; ++ks) {
+    // P half h (keys [64h, 64h+64), bf16) sits in columns [64h, 64h+32) of S_t: over the S columns its writer read
+    mma_ts(d_tmem, p_tmem + 64 * half + (ks - 4 * half) * 8, v_desc + static_cast<uint64_t>((ks * 2048) >> 4), kIdescPV,
+           (accumulate | (ks > 0)) ? 1u : 0u);   // only k-step 0 of a fresh accumulator overwrites
   }
 }
 
@@ -243,11 +245,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_init(&bar->kv_empty[s], 1);
     }
     for (int t = 0; t < 2; ++t) {
-      for (int h = 0; h < 2; ++h) {
-        mbar_init(&bar->s_full[t][h], 1);
-        mbar_init(&bar->p_full[t][h], kTileM / 32);   // one arrival per softmax warp
-      }
-      mbar_init(&bar->o_free[t], kTileM / 32);
+      mbar_init(&bar->s_full[t], 1);
+      mbar_init(&bar->p_half[t][0], kTileM / 32);   // one arrival per softmax warp, per 64-key half of P
+      mbar_init(&bar->p_half[t][1], kTileM / 32);
+      mbar_init(&bar->o_full[t], 1);
+      mbar_init(&bar->o_free[t], kSplit * kTileM / 32);
     }
     fence_barrier_init();
   }
@@ -268,74 +270,75 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const uint32_t tmem_base = bar->tmem_base;
   const int total_items = ws[0];
 
-  // items are sorted longest-first; CTAs walk them boustrophedon (0..G-1, G-1..0, ...) so that the CTA that drew the
-  // longest item of one round draws the shortest of the next: static LPT-like balance without atomics
-  auto item_of_round = [&](int round) {
-    return round * static_cast<int>(gridDim.x) + ((round & 1) ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x)
-                                                              : static_cast<int>(blockIdx.x));
-  };
-
   if (warp < kSoftmaxWarps) {
     // ====================================================================== softmax warpgroups
-    setmaxnreg_inc<MAGI_SOFTMAX_REGS>();
-    const int t = warp >> 2;                   // which 128-row query tile of the item
+    if constexpr (kSplit == 1) setmaxnreg_inc<MAGI_SOFTMAX_REGS>();
+    const int grp = warp >> 2;                 // warpgroup index
+    const int t = grp / kSplit;                // which 128-row query tile of the item
+    const int ch = grp % kSplit;               // which column half of S_t / O_t this thread owns (kSplit == 2)
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
+    const int rowq = quarter * 32 + lane;
     const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t tS = tmem_base + lane_sel + t * 128;          // S_t,a | S_t,b
-    const uint32_t tO = tmem_base + lane_sel + 256 + t * 128;    // O_t
-    const int row_in_item = t * kTileM + quarter * 32 + lane;
-    uint32_t s_phase[2] = {0, 0};
+    const uint32_t tS = tmem_base + lane_sel + t * 128;          // S_t (and P_t)
+    const uint32_t tSc = tS + ch * kCols;                        // this thread's S columns
+    const uint32_t tO = tmem_base + lane_sel + 256 + t * 128 + ch * kCols;   // this thread's O columns
+    const int row_in_item = t * kTileM + rowq;
+    const int pair_bar = 1 + t * 4 + quarter;  // named barrier shared by the two warps that split a row (kSplit == 2)
+    uint32_t s_phase = 0, o_phase = 0;
     const float scale_log2 = p.scale_log2;
-    const uint64_t scale2 = pack_f2(scale_log2, scale_log2);
     __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(p.out);
+    auto pair_max = [&](float v, int par) -> float {   // max over the two threads that share this row
+      if constexpr (kSplit == 1) return v;
+      bar->xch[par][t][ch][rowq] = v;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      return fmaxf(v, bar->xch[par][t][ch ^ 1][rowq]);
+    };
 
     for (int round = 0; round * static_cast<int>(gridDim.x) < total_items; ++round) {
-      const int item = item_of_round(round);
+      // items are sorted longest-first; CTAs walk them boustrophedon (0..G-1, G-1..0, ...) so that the CTA that drew
+      // the longest item of one round draws the shortest of the next: static LPT-like balance without atomics
+      const int item = round * static_cast<int>(gridDim.x) +
+                       ((round & 1) ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x)
+                                    : static_cast<int>(blockIdx.x));
       if (item >= total_items) continue;
       Item it;
       decode_item(ws, item, p.Hq, group, p.len_a, it);
       const int row = it.qrow0 + row_in_item;
       const bool row_valid = row < it.q_end;
-      float m = -INFINITY, l = 0.f;   // running (lazily updated) row max, row sum
-      bool pre_waited[2] = {false, false};   // s_full[t][h] of the NEXT unit of half h already consumed (rare path)
-      const int units = 2 * it.nt;
+      float m = -INFINITY, l = 0.f;   // running max of the row (shared by its threads), this thread's partial row sum
 
-      for (int u = 0; u < units; ++u) {
-        const int j = u >> 1, h = u & 1;
+      for (int j = 0; j < it.nt; ++j) {
         int seg, krow0, nvalid;
         tile_info(it, j, seg, krow0, nvalid);
-        const int nv = nvalid - kHalfN * h;    // valid columns of this half (<= 0: fully masked, >= 64: full)
-        const bool tr = quarter == 0 && lane == 0 && item == 0;
-        if (tr) TRACE(t, u, 0);
-        if (!pre_waited[h]) {
-          mbar_wait(&bar->s_full[t][h], s_phase[h]);
-          s_phase[h] ^= 1;
-        }
-        pre_waited[h] = false;
+        const bool tr = quarter == 0 && lane == 0 && item == 0 && ch == 0;
+        if (tr) TRACE(t, j, 0);
+        mbar_wait(&bar->s_full[t], s_phase);
+        s_phase ^= 1;
         tc_fence_after();
-        if (tr) TRACE(t, u, 1);
+        if (tr) TRACE(t, j, 1);
 
-        uint32_t sr[kHalfN];
+        uint32_t sr[kCols];
         auto load_s = [&]() {
-          MAGI_TMEM_LD32(tS + kHalfN * h, sr, 0);
-          MAGI_TMEM_LD32(tS + kHalfN * h + 32, sr, 32);
+#pragma unroll
+          for (int c0 = 0; c0 < kCols; c0 += 32) MAGI_TMEM_LD32(tSc + c0, sr, c0);
           tmem_wait_ld();
-          if (nv < kHalfN) {
-            // Only the last key tile of a segment is partial (the asm keeps this block a real, skipped branch).
+          if (nvalid < kTileN) {
+            // Only the last key tile of a segment is partial. The empty volatile asm keeps ptxas from if-converting
+            // this block into 128 ISETP+SEL pairs executed on EVERY tile (a third of the loop's instructions).
             asm volatile("" ::: "memory");
 #pragma unroll
-            for (int c = 0; c < kHalfN; ++c)
-              if (c >= nv) sr[c] = 0xff800000u;  // -inf
+            for (int c = 0; c < kCols; ++c)
+              if (ch * kCols + c >= nvalid) sr[c] = 0xff800000u;  // -inf
           }
         };
         load_s();
-        if (tr) TRACE(t, u, 2);
+        if (tr) TRACE(t, j, 2);
 
-        // Row max over the 64 scores: FMNMX3 in four chains. Except for the first unit it is NOT on the critical
-        // path: P is computed optimistically against the running max m while the chains run on the ALU pipe next to
-        // it; only if some row's max grew by more than 2^8 (rare) is the unit redone with the new max.
+        // Row max over this thread's scores: FMNMX3 in four chains. For j > 0 it is NOT on the critical path: P is
+        // computed optimistically against the running max m while the chains run on the ALU pipe next to it; only
+        // if some row's max grew by more than 2^8 (rare) is the tile redone with the new max.
         float mxa, mxb, mxc, mxd;
-        auto max_step = [&](int k) {   // k = 0..15: consumes columns 4k .. 4k+3
+        auto max_step = [&](int k) {   // k = 0 .. kCols/4 - 1: consumes columns 4k .. 4k+3
           const float a0 = __uint_as_float(sr[4 * k]), a1 = __uint_as_float(sr[4 * k + 1]);
           const float a2 = __uint_as_float(sr[4 * k + 2]), a3 = __uint_as_float(sr[4 * k + 3]);
           if (k == 0) { mxa = fmaxf(a0, a1); mxb = fmaxf(a2, a3); mxc = mxa; mxd = mxb; }
@@ -343,12 +346,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           else { mxa = fmax3(mxa, a0, a1); mxb = fmax3(mxb, a2, a3); }
         };
         uint64_t sum_a, sum_b;
-        // 64 scores -> 32 packed bf16x2 probabilities in sr[0..32) (in place), row sums accumulated
-        auto exps = [&](const uint64_t negm2, const bool with_max) {
+        // local columns [64 hl, 64 hl + 64) -> packed bf16 P in sr[64 hl .. 64 hl + 32) (in place), row sums accumulated
+        auto half = [&](const int hl, const uint64_t scale2, const uint64_t negm2, const bool with_max) {
 #pragma unroll
-          for (int c = 0; c < kHalfN; c += 2) {
+          for (int c = 64 * hl; c < 64 * hl + 64; c += 2) {
             const int pair = c >> 1;
-            if (with_max && (pair & 1) == 0) max_step(pair >> 1);
+            // all kCols columns are covered by max steps during the first local half
+            if (with_max) {
+              if constexpr (kSplit == 1) max_step(pair);
+              else if ((pair & 1) == 0) max_step(pair >> 1);
+            }
             const uint64_t x2 = ffma2(pack_f2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), scale2, negm2);
             float x0, x1, p0, p1;
             unpack_f2(x2, x0, x1);
@@ -360,38 +367,40 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
             const uint64_t p2 = pack_f2(p0, p1);
             if (pair & 1) sum_b = fadd2(sum_b, p2); else sum_a = fadd2(sum_a, p2);
-            sr[pair] = pack_bf16x2(p0, p1);
+            sr[64 * hl + ((c - 64 * hl) >> 1)] = pack_bf16x2(p0, p1);
           }
         };
         auto local_max = [&]() { return fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd)); };
+        // publish the P half whose keys are [64 hg, 64 hg + 64) from local registers sr[64 hl ..]
+        auto publish = [&](int hl, int hg) {
+          MAGI_TMEM_ST32(tS + 64 * hg, sr, 64 * hl);
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar->p_half[t][hg]);
+        };
 
         float alpha = 1.f;
+        bool need = false;
+        const uint64_t scale2 = pack_f2(scale_log2, scale_log2);
         sum_a = pack_f2(0.f, 0.f);
         sum_b = sum_a;
-        if (u == 0) {
+        if (j == 0) {
 #pragma unroll
-          for (int k = 0; k < kHalfN / 4; ++k) max_step(k);
-          m = local_max();              // at least one column of the first unit is valid
-          if (tr) TRACE(t, u, 3);
+          for (int k = 0; k < kCols / 4; ++k) max_step(k);
+          m = pair_max(local_max(), j & 1);
+          if (tr) TRACE(t, j, 3);
           const float neg_m = -m * scale_log2;
-          exps(pack_f2(neg_m, neg_m), false);
+          half(0, scale2, pack_f2(neg_m, neg_m), false);
         } else {
-          if (tr) TRACE(t, u, 3);
+          if (tr) TRACE(t, j, 3);
           const float neg_m = -m * scale_log2;
-          exps(pack_f2(neg_m, neg_m), true);
-          const float mx = local_max();
-          const bool need = (mx - m) * scale_log2 > kRescaleThreshold;
+          half(0, scale2, pack_f2(neg_m, neg_m), true);
+          const float mx = pair_max(local_max(), j & 1);
+          need = (mx - m) * scale_log2 > kRescaleThreshold;
           if (__any_sync(0xffffffffu, need)) {
-            // Rare: redo this unit against the new max and bring O back into range before P*V accumulates. O_t may
-            // still be the target of the previous unit's P*V: its completion is covered by the commit on
-            // s_full[t][h^1] that follows it (the next scores of the other half, or the end-of-item marker), which
-            // the issuer produces without needing this unit - so it is safe to wait for it here, early.
-            if (!pre_waited[h ^ 1]) {
-              mbar_wait(&bar->s_full[t][h ^ 1], s_phase[h ^ 1]);
-              s_phase[h ^ 1] ^= 1;
-              pre_waited[h ^ 1] = true;
-            }
-            tc_fence_after();
+            // rare: redo the first half against the new max and bring O back into range before P*V accumulates.
+            // Both threads of a row see the same mx, hence take the same decision.
             if (need) {
               alpha = ex2_approx((m - mx) * scale_log2);
               m = mx;
@@ -400,9 +409,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             sum_a = pack_f2(0.f, 0.f);
             sum_b = sum_a;
             const float neg_m2 = -m * scale_log2;
-            exps(pack_f2(neg_m2, neg_m2), false);
+            half(0, scale2, pack_f2(neg_m2, neg_m2), false);
 #pragma unroll 1
-            for (int c = 0; c < 128; c += 32) {
+            for (int c = 0; c < kCols; c += 32) {
               uint32_t orr[32];
               MAGI_TMEM_LD32(tO + c, orr, 0);
               tmem_wait_ld();
@@ -412,16 +421,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
           }
         }
-        // publish P_t,h (32 bf16x2 columns over the first half of S_t,h)
-        MAGI_TMEM_ST32(tS + kHalfN * h, sr, 0);
+        // the first 64 keys this thread owns are final: hand them to the MMA issuer so that P*V starts early
+        publish(0, kSplit == 1 ? 0 : ch);
+        if (tr) TRACE(t, j, 4);
+        if constexpr (kSplit == 1) {
+          const float neg_m = -m * scale_log2;
+          half(1, scale2, pack_f2(neg_m, neg_m), false);
+          if (tr) TRACE(t, j, 5);
+          publish(1, 1);
+        }
         float s0, s1;
         unpack_f2(fadd2(sum_a, sum_b), s0, s1);
         l = l * alpha + (s0 + s1);
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar->p_full[t][h]);
-        if (tr) TRACE(t, u, 4);
+        if (tr) TRACE(t, j, 6);
       }
 
       // ------------------------------------------------------------------ epilogue for this row
@@ -430,20 +442,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               ? static_cast<int64_t>(it.h / p.out_group_heads) * p.out_group_stride +
                     static_cast<int64_t>(it.h % p.out_group_heads) * p.out_head_stride
               : static_cast<int64_t>(it.h) * p.out_head_stride;
-      __nv_bfloat16* orow = out + static_cast<int64_t>(row) * p.out_token_stride + head_off;
+      __nv_bfloat16* orow = out + static_cast<int64_t>(row) * p.out_token_stride + head_off + ch * kCols;
       if (it.nt > 0) {
-        // the issuer commits s_full[t][h] once more after the last P*V of each half: O_t is complete
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (!pre_waited[h]) {
-            mbar_wait(&bar->s_full[t][h], s_phase[h]);
-            s_phase[h] ^= 1;
-          }
+        if constexpr (kSplit == 2) {   // total row sum = sum of the two column halves
+          bar->xl[t][ch][rowq] = l;
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+          l += bar->xl[t][ch ^ 1][rowq];
         }
+        mbar_wait(&bar->o_full[t], o_phase);
+        o_phase ^= 1;
         tc_fence_after();
         const float inv_l = 1.f / l;
 #pragma unroll 1
-        for (int c = 0; c < 128; c += 32) {
+        for (int c = 0; c < kCols; c += 32) {
           uint32_t orr[32];
           MAGI_TMEM_LD32(tO + c, orr, 0);
           tmem_wait_ld();
@@ -462,31 +473,47 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar->o_free[t]);
-        if (row_valid && p.lse != nullptr)
+        if (row_valid && ch == 0 && p.lse != nullptr)
           p.lse[static_cast<int64_t>(row) * p.Hq + it.h] = (m * scale_log2 + log2f(l)) * 0.6931471805599453f;
       } else if (row_valid) {
         // empty key interval: zeros / -inf (flash-attn convention for seqlen_k == 0)
 #pragma unroll
-        for (int c = 0; c < 128; c += 8) *reinterpret_cast<uint4*>(orow + c) = make_uint4(0, 0, 0, 0);
-        if (p.lse != nullptr) p.lse[static_cast<int64_t>(row) * p.Hq + it.h] = -INFINITY;
+        for (int c = 0; c < kCols; c += 8) *reinterpret_cast<uint4*>(orow + c) = make_uint4(0, 0, 0, 0);
+        if (ch == 0 && p.lse != nullptr) p.lse[static_cast<int64_t>(row) * p.Hq + it.h] = -INFINITY;
       }
     }
   } else if (warp == kMmaWarp) {
     // ====================================================================== MMA issuer
     // The whole warp runs the loop (waits included) so that everything feeding the MMAs is warp-uniform; only the
     // tcgen05.mma / tcgen05.commit instructions themselves are issued by the elected lane.
-    setmaxnreg_dec<MAGI_AUX_REGS>();
+    if constexpr (kSplit == 1) setmaxnreg_dec<MAGI_AUX_REGS>();
     const uint32_t tb = uniform(tmem_base);
+    const uint32_t tS0 = tb, tS1 = tb + 128, tO0 = tb + 256, tO1 = tb + 384;
     const uint64_t q_desc_base = desc_kmajor(smem_u32(smem_q));
     const uint32_t kv_addr = smem_u32(smem_kv);
     uint32_t stage = 0, phase = 0;  // kv ring (consumer side)
-    uint32_t p_phase[2][2] = {{0, 0}, {0, 0}};
+    uint32_t p_phase0 = 0, p_phase1 = 0;
     uint32_t item_cnt = 0;
     auto advance = [&]() {
       if (++stage == kStages) { stage = 0; phase ^= 1; }
     };
+    // O_t (+)= P_t V in two 64-key halves, each issued as soon as the softmax warpgroup has published that half of P
+    auto pv = [&](uint32_t tO, uint32_t tS, int t, uint32_t& ph, uint32_t vst_, uint32_t acc) {
+      const uint64_t vd = desc_v(kv_addr + vst_ * kTileBytes);
+      mbar_wait_warp(&bar->p_half[t][0], ph);
+      tc_fence_after();
+      if (elect_one()) issue_pv(tO, tS, vd, acc, 0);
+      __syncwarp();
+      mbar_wait_warp(&bar->p_half[t][1], ph);
+      tc_fence_after();
+      if (elect_one()) issue_pv(tO, tS, vd, acc, 1);
+      __syncwarp();
+      ph ^= 1;
+    };
     for (int round = 0; round * static_cast<int>(gridDim.x) < total_items; ++round) {
-      const int item = item_of_round(round);
+      const int item = round * static_cast<int>(gridDim.x) +
+                       ((round & 1) ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x)
+                                    : static_cast<int>(blockIdx.x));
       if (item >= total_items) continue;
       Item it;
       decode_item(ws, item, p.Hq, group, p.len_a, it);
@@ -494,81 +521,86 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (nt == 0) continue;
       const uint32_t o_free_parity = (item_cnt & 1) ^ 1;
       const uint32_t qs = item_cnt % kQStages;                       // Q stage of this item
-      const uint64_t q_desc0 = q_desc_base + static_cast<uint64_t>((qs * 2 * kTileBytes) >> 4);
-      const bool tr = item == 0;
+      const uint64_t q0_desc = q_desc_base + static_cast<uint64_t>((qs * 2 * kTileBytes) >> 4);
+      const uint64_t q1_desc = q0_desc + static_cast<uint64_t>(kTileBytes >> 4);
       mbar_wait_warp(&bar->q_full[qs], (item_cnt / kQStages) & 1);
-      // K_0 -> S_t,h(0) for both query tiles and both key halves
+      // K_0 -> S0(0), S1(0)
       mbar_wait_warp(&bar->kv_full[stage], phase);
       tc_fence_after();
       uint32_t kst = stage;
       advance();
       if (elect_one()) {
         const uint64_t kd = desc_kmajor(kv_addr + kst * kTileBytes);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            issue_qk(tb + t * 128 + kHalfN * h, q_desc0 + static_cast<uint64_t>((t * kTileBytes) >> 4), kd, h);
-            tc_commit(&bar->s_full[t][h]);
-          }
-        }
+        issue_qk(tS0, q0_desc, kd);
+        tc_commit(&bar->s_full[0]);
+        issue_qk(tS1, q1_desc, kd);
+        tc_commit(&bar->s_full[1]);
         tc_commit(&bar->kv_empty[kst]);
         if (nt == 1) tc_commit(&bar->q_empty[qs]);
       }
       __syncwarp();
-      for (int i = 0; i < nt; ++i) {
-        const bool last = i == nt - 1;
-        // V_i, and K_{i+1} for the next scores
+      // V_0 -> O0 = P0(0) V_0
+      mbar_wait_warp(&bar->kv_full[stage], phase);
+      uint32_t vst = stage;
+      advance();
+      mbar_wait_warp(&bar->o_free[0], o_free_parity);
+      pv(tO0, tS0, 0, p_phase0, vst, 0);
+      for (int i = 1; i < nt; ++i) {
+        // K_i -> S0(i)   (P0(i-1) already consumed by the in-order PV0(i-1))
         mbar_wait_warp(&bar->kv_full[stage], phase);
-        const uint32_t vst = stage;
+        tc_fence_after();
+        kst = stage;
         advance();
-        if (!last) {
-          mbar_wait_warp(&bar->kv_full[stage], phase);
-          kst = stage;
-          advance();
-        }
-        const uint64_t vd = desc_v(kv_addr + vst * kTileBytes);
-        const uint64_t kd = desc_kmajor(kv_addr + kst * kTileBytes);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            // O_t (+)= P_t,h(i) V_h(i) as soon as that half of P is published, then the next scores of the same half
-            if (i == 0 && h == 0) mbar_wait_warp(&bar->o_free[t], o_free_parity);
-            if (tr && lane == 0) TRACE(2, 4 * i + 2 * h + t, 0);
-            mbar_wait_warp(&bar->p_full[t][h], p_phase[t][h]);
-            p_phase[t][h] ^= 1;
-            tc_fence_after();
-            if (tr && lane == 0) TRACE(2, 4 * i + 2 * h + t, 1);
-            if (elect_one()) {
-              issue_pv(tb + 256 + t * 128, tb + t * 128 + kHalfN * h, vd, (i > 0 || h > 0) ? 1u : 0u, h);
-              if (!last)
-                issue_qk(tb + t * 128 + kHalfN * h, q_desc0 + static_cast<uint64_t>((t * kTileBytes) >> 4), kd, h);
-              // next scores of this half - or, after the last tile, the end-of-item marker: O_t complete up to here
-              tc_commit(&bar->s_full[t][h]);
-            }
-            __syncwarp();
-            if (tr && lane == 0) TRACE(2, 4 * i + 2 * h + t, 2);
-          }
-        }
+        const bool tr = item == 0;
         if (elect_one()) {
-          tc_commit(&bar->kv_empty[vst]);
-          if (!last) {
-            tc_commit(&bar->kv_empty[kst]);
-            if (i == nt - 2) tc_commit(&bar->q_empty[qs]);
-          }
+          if (tr) TRACE(2, i, 0);
+          issue_qk(tS0, q0_desc, desc_kmajor(kv_addr + kst * kTileBytes));
+          tc_commit(&bar->s_full[0]);
+          if (tr) TRACE(2, i, 1);
         }
         __syncwarp();
+        // O1 (+)= P1(i-1) V_{i-1} ; S1(i)
+        if (i == 1) mbar_wait_warp(&bar->o_free[1], o_free_parity);
+        if (tr && lane == 0) TRACE(2, i, 2);
+        pv(tO1, tS1, 1, p_phase1, vst, i > 1 ? 1u : 0u);
+        if (elect_one()) {
+          tc_commit(&bar->kv_empty[vst]);
+          issue_qk(tS1, q1_desc, desc_kmajor(kv_addr + kst * kTileBytes));
+          tc_commit(&bar->s_full[1]);
+          tc_commit(&bar->kv_empty[kst]);
+          if (i == nt - 1) tc_commit(&bar->q_empty[qs]);
+          if (tr) TRACE(2, i, 3);
+        }
+        __syncwarp();
+        // V_i -> O0 += P0(i) V_i
+        mbar_wait_warp(&bar->kv_full[stage], phase);
+        vst = stage;
+        advance();
+        if (tr && lane == 0) TRACE(2, i, 4);
+        pv(tO0, tS0, 0, p_phase0, vst, 1);
+        if (tr && lane == 0) { TRACE(2, i, 5); TRACE(2, i, 6); }
       }
+      // O1 (+)= P1(nt-1) V_{nt-1}
+      if (nt == 1) mbar_wait_warp(&bar->o_free[1], o_free_parity);
+      if (elect_one()) tc_commit(&bar->o_full[0]);   // everything up to PV0(nt-1)
+      __syncwarp();
+      pv(tO1, tS1, 1, p_phase1, vst, nt > 1 ? 1u : 0u);
+      if (elect_one()) {
+        tc_commit(&bar->kv_empty[vst]);
+        tc_commit(&bar->o_full[1]);
+      }
+      __syncwarp();
       ++item_cnt;
     }
   } else if (warp == kTmaWarp) {
     // ====================================================================== TMA producer (same structure)
-    setmaxnreg_dec<MAGI_AUX_REGS>();
+    if constexpr (kSplit == 1) setmaxnreg_dec<MAGI_AUX_REGS>();
     uint32_t stage = 0, phase = 0;  // kv ring (producer side)
     uint32_t item_cnt = 0;
     for (int round = 0; round * static_cast<int>(gridDim.x) < total_items; ++round) {
-      const int item = item_of_round(round);
+      const int item = round * static_cast<int>(gridDim.x) +
+                       ((round & 1) ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x)
+                                    : static_cast<int>(blockIdx.x));
       if (item >= total_items) continue;
       Item it;
       decode_item(ws, item, p.Hq, group, p.len_a, it);
@@ -610,7 +642,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       ++item_cnt;
     }
   } else {
-    setmaxnreg_dec<MAGI_AUX_REGS>();   // idle warps of the third warpgroup (setmaxnreg is warpgroup-collective)
+    if constexpr (kSplit == 1) setmaxnreg_dec<MAGI_AUX_REGS>();   // idle warps (setmaxnreg is warpgroup-collective)
   }
 
   tc_fence_before();

@@ -24,18 +24,21 @@ buf = np.zeros((3, 512, 8), dtype=np.int64)
 L = _lib.lib()
 rc = L.magi_debug_read_trace(buf.ctypes.data_as(C.c_void_p), C.c_size_t(buf.nbytes))
 assert rc == 0, rc
-lo, hi = 40, 560 - 40   # steady-state units of item 0 (293 tiles = 586 half-tile units; the trace keeps 512)
-hi = min(hi, 500)
+lo, hi = 20, 280   # steady state tiles of item 0 (293 tiles)
 for t in (0, 1):
     b = buf[t, lo:hi].astype(np.float64)
-    names = ["wait S_h", "tcgen05.ld", "(max, unit 0 only)", "exp2 + pack + st + arrive"]
-    d = [b[:, i + 1] - b[:, i] for i in range(4)]
+    names = ["wait S", "tcgen05.ld S", "(max, j=0 only)", "half0 exp+st+arrive", "half1 exp+st+wait", "arrive"]
+    d = [b[:, i + 1] - b[:, i] for i in range(6)]
     period = np.diff(b[:, 0]).mean()
-    print(f"softmax WG{t}: unit period {period:.0f} cyc (x2 per tile) | " + " | ".join(f"{n} {x.mean():.0f}" for n, x in zip(names, d)))
+    print(f"softmax WG{t}: period {period:.0f} cyc | " + " | ".join(f"{n} {x.mean():.0f}" for n, x in zip(names, d)))
 m = buf[2, lo:hi].astype(np.float64)
-names = ["wait P_t,h", "issue PV + S(next) + commit"]
-d = [m[:, i + 1] - m[:, i] for i in range(2)]
+names = ["issue S0+commit", "wait o_free", "PV1 (waits+issue), S1, commits", "wait V", "PV0 (waits+issue)", "-"]
+d = [m[:, i + 1] - m[:, i] for i in range(6)]
 period = np.diff(m[:, 0]).mean()
-gap = m[1:, 0] - m[:-1, 2]
-print(f"MMA issuer : per (tile, half, q-tile) step {period:.0f} cyc (x4 per tile pair) | "
-      + " | ".join(f"{n} {x.mean():.0f}" for n, x in zip(names, d)) + f" | between steps (K/V waits) {gap.mean():.0f}")
+loop = m[1:, 0] - m[:-1, 6]
+print(f"MMA issuer : period {period:.0f} cyc | " + " | ".join(f"{n} {x.mean():.0f}" for n, x in zip(names, d))
+      + f" | wait K (loop top) {loop.mean():.0f}")
+# latency from S0 issue (MMA stamp 1) to softmax WG0 seeing it (softmax stamp 1) and from arrive to MMA wake
+s0 = buf[0, lo:hi].astype(np.float64)
+print(f"S0 commit issued -> softmax0 woke: {(s0[:, 1] - m[:, 1]).mean():.0f} cyc ; softmax0 arrive -> MMA past wait P0: "
+      f"{(m[:, 5] - s0[:, 6]).mean():.0f} cyc")
