@@ -195,14 +195,21 @@ class HotPath:
             self.attn_events.append((e0, e1))
         self.cross(inp)
 
-    def cross(self, inp):
+    def cross_prepare(self, inp):
         F, w = self.F, self.w
         xq, _ = F.qk_norm_rope(inp["qx"], None, None, w["Hq"], w["Hkv"], self.lnx["q"], None, None, None)
         tkv = inp["text_kv"]
         _, xkv = F.qk_norm_rope(None, tkv[..., :128], tkv[..., 128:], w["Hq"], w["Hkv"], None, self.lnx["k"], None,
                                 None)
-        F.attn_ranges(xq, xkv[..., :128], xkv[..., 128:], self.x_q_ranges, self.x_k_ranges, out=self.x_out,
-                      return_lse=False)
+        return xq, xkv
+
+    def cross_attend(self, prepared):
+        xq, xkv = prepared
+        self.F.attn_ranges(xq, xkv[..., :128], xkv[..., 128:], self.x_q_ranges, self.x_k_ranges, out=self.x_out,
+                           return_lse=False)
+
+    def cross(self, inp):
+        self.cross_attend(self.cross_prepare(inp))
 
     # -- one layer, Ulysses context parallel (dit_module.py:1175-1205 / context_parallel.py:503-597)
     def layer_cp(self, l, timed_events=False):
@@ -217,6 +224,7 @@ class HotPath:
         q_send, _ = F.qk_norm_rope(inp["xq"], None, None, w["Hq"], w["Hkv"], self.ln["q"], None, inp["sin"],
                                    inp["cos"], head_perm_cp=cp)
         q, h_q = cpm.all_to_all_input_split(q_send, self.split, send_layout=True)
+        x_prepared = self.cross_prepare(inp)   # overlaps the two input all-to-alls
         h_kv.wait()
         h_q.wait()
         kc = vc = None
@@ -239,7 +247,7 @@ class HotPath:
             F.ulysses_relayout(recv, cp_, 1, out=result, dst_heads_total=q_head, dst_head_offset=lo)
 
         core_out, _ = cpm.UlyssesScheduler.get_attn_and_xattn_base(
-            q, kv[..., :128], kv[..., 128:], core, lambda: self.cross(inp), self.ulysses_overlap_degree, 1, cp,
+            q, kv[..., :128], kv[..., 128:], core, lambda: self.cross_attend(x_prepared), self.ulysses_overlap_degree, 1, cp,
             self.split, relayout_out=relayout_out)
         self.core_out = core_out
 

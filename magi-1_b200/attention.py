@@ -173,9 +173,10 @@ class FullyParallelAttention(nn.Module):
                           return_lse=False, **dest(i))
         return out
 
-    def cross_attention(self, mixed_qqkv, key_value_states, cross_attn_params: PackedCrossAttnParams, proj_buf=None):
-        """get_xqkv + cross_attention, dit_module.py:1005-1021, 1098-1136. Returns (sq, b, Hq*128), or writes slot
-        n = 1 of the out-projection input `proj_buf` (sq*b, 2*Hq*128) and returns None."""
+    def cross_attention_prepare(self, mixed_qqkv, key_value_states):
+        """get_xqkv, dit_module.py:1005-1021: qx / text-kv projections + the two bf16 LayerNorms (no RoPE). Split from
+        the attention itself so that, under context parallelism, this half can overlap the input all-to-alls and the
+        attention half the output all-to-all."""
         sq, b, _ = mixed_qqkv.shape
         Hq, Hkv = self.model_config.num_attention_heads, self.model_config.num_query_groups
         eps, z = self.model_config.layernorm_epsilon, self.model_config.apply_layernorm_1p
@@ -185,16 +186,27 @@ class FullyParallelAttention(nn.Module):
         # text K: LayerNorm (bf16 params, no RoPE); V: copy -> packed (ytot, Hkv, 256)
         _, kv_x = F.qk_norm_rope(None, kvx[..., :F.HEAD_DIM], kvx[..., F.HEAD_DIM:], Hq, Hkv, None,
                                  self._ln(self.k_layernorm_xattn), None, None, eps=eps, zero_centered_gamma=z)
-        out = None if proj_buf is not None else torch.empty((sq, b, Hq, F.HEAD_DIM), dtype=qx.dtype, device=qx.device)
-        # q_ranges / kv_ranges (the flex_flash_attn_func arguments, dit_module.py:1111-1122) rather than cu_seqlens:
-        # they stay valid when a caption segment is empty and after the per-rank rewrite under context parallelism
-        n = cross_attn_params.q_ranges.shape[0]
-        per_b = n // b
+        q_rows = []
         for i in range(b):
             # "(sq b) -> (b sq)": batch row i is a strided view of the projection output
             q_i, _ = F.qk_norm_rope(qx.view(sq, b, Hq, F.HEAD_DIM)[:, i], None, None, Hq, Hkv,
                                     self._ln(self.q_layernorm_xattn), None, None, None, eps=eps,
                                     zero_centered_gamma=z)
+            q_rows.append(q_i)
+        return q_rows, kv_x
+
+    def cross_attention_attend(self, prepared, shape, cross_attn_params: PackedCrossAttnParams, proj_buf=None):
+        """cross_attention, dit_module.py:1098-1136, on the tensors of cross_attention_prepare."""
+        q_rows, kv_x = prepared
+        sq, b = shape
+        Hq = self.model_config.num_attention_heads
+        out = None if proj_buf is not None else torch.empty((sq, b, Hq, F.HEAD_DIM), dtype=kv_x.dtype,
+                                                            device=kv_x.device)
+        # q_ranges / kv_ranges (the flex_flash_attn_func arguments, dit_module.py:1111-1122) rather than cu_seqlens:
+        # they stay valid when a caption segment is empty and after the per-rank rewrite under context parallelism
+        n = cross_attn_params.q_ranges.shape[0]
+        per_b = n // b
+        for i in range(b):
             qr = cross_attn_params.q_ranges[i * per_b:(i + 1) * per_b]
             if i > 0:
                 qr = qr - i * sq
@@ -203,10 +215,15 @@ class FullyParallelAttention(nn.Module):
                 dst = dict(proj_input=(proj_buf.view(sq, b, -1)[:, i], 1, self.PROJ_GROUPS))
             else:
                 dst = dict(out=out[:, i])
-            F.attn_ranges(q_i, kv_x[..., :F.HEAD_DIM], kv_x[..., F.HEAD_DIM:], qr, kr, return_lse=False, **dst)
+            F.attn_ranges(q_rows[i], kv_x[..., :F.HEAD_DIM], kv_x[..., F.HEAD_DIM:], qr, kr, return_lse=False, **dst)
         return None if proj_buf is not None else out.view(sq, b, Hq * F.HEAD_DIM)
 
-    # ------------------------------------------------------------------ forward
+    def cross_attention(self, mixed_qqkv, key_value_states, cross_attn_params: PackedCrossAttnParams, proj_buf=None):
+        """get_xqkv + cross_attention, dit_module.py:1005-1021, 1098-1136. Returns (sq, b, Hq*128), or writes slot
+        n = 1 of the out-projection input `proj_buf` (sq*b, 2*Hq*128) and returns None."""
+        prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states)
+        return self.cross_attention_attend(prepared, mixed_qqkv.shape[:2], cross_attn_params, proj_buf)
+
     @staticmethod
     def attn_linear_proj_input(core_attn_out: torch.Tensor, cross_attn_out: torch.Tensor) -> torch.Tensor:
         """What the reference builds before linear_proj (attn_linear_proj, dit_module.py:1332-1338): the torch
@@ -319,11 +336,14 @@ class FullyParallelAttention(nn.Module):
         kv, h_kv = cpm.all_to_all_input_split(kv, split, send_layout=True, out=kv_recv)
         query = get_q()
         query, h_q = cpm.all_to_all_input_split(query, split, send_layout=True)
+        # the cross-attention needs no communication (context_parallel.py:591): its projections + norms run under the
+        # two input all-to-alls, its attention under the (last) output all-to-all
+        x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states)
         h_kv.wait()
         key, value = kv_cache_func(kv)
         h_q.wait()
         out = cpm.UlyssesScheduler.get_attn_and_xattn_base(
-            query, key, value, core, partial(self.cross_attention, mixed_qqkv, key_value_states,
+            query, key, value, core, partial(self.cross_attention_attend, x_prepared, (sq, b),
                                              meta_args.cross_attn_params),
             self.engine_config.ulysses_overlap_degree, b, cp, split, relayout_out=relayout_out)
         self._kc = self._vc = None

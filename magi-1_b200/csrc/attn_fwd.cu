@@ -271,7 +271,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   }
   {
     const int n = p.work[1];
+#ifdef MAGI_NO_WORK_CACHE
+    if (false) {
+#else
     if (n <= kMaxCachedRanges) {
+#endif
       for (int i = threadIdx.x; i < 4 + 5 * n + 1; i += blockDim.x) bar->work[i] = p.work[i];
       ws = bar->work;
     }
