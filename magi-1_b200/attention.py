@@ -145,6 +145,82 @@ class FullyParallelAttention(nn.Module):
 
     PROJ_GROUPS = 8   # "hn=8 is hardcoded to align with TP8 training and TP1 inference", dit_module.py:1337
 
+    # ------------------------------------------------------------------ reference-named pieces (dit_module.py:953-1021)
+    # The reference hands these to UlyssesScheduler / CSOHelper as callables; they are kept under the same names and
+    # argument meaning. Each one is a single launch of the fused prologue kernel.
+    def get_q(self, mixed_qqkv: torch.Tensor, cos_emb: torch.Tensor, sin_emb: torch.Tensor, head_perm_cp: int = 1):
+        """dit_module.py:953-963: [sq, b, hidden] -> [(sq b), hn, hd], LayerNorm(+1p) + RoPE in fp32, bf16 out."""
+        sq, b, _ = mixed_qqkv.shape
+        q, _ = F.qk_norm_rope(self.linear_qkv.forward_q(mixed_qqkv.reshape(sq * b, -1)), None, None,
+                              self.model_config.num_attention_heads, self.model_config.num_query_groups,
+                              self._ln(self.q_layernorm), None, sin_emb, cos_emb, batch=b,
+                              eps=self.model_config.layernorm_epsilon,
+                              zero_centered_gamma=self.model_config.apply_layernorm_1p, head_perm_cp=head_perm_cp)
+        return q
+
+    def get_kv(self, mixed_qqkv: torch.Tensor, cos_emb: torch.Tensor, sin_emb: torch.Tensor, head_perm_cp: int = 1):
+        """dit_module.py:991-996 (get_k + get_v + cat): packed [(sq b), hn, 2 * hd] = [K | V]."""
+        sq, b, _ = mixed_qqkv.shape
+        x = mixed_qqkv.reshape(sq * b, -1)
+        _, kv = F.qk_norm_rope(None, self.linear_qkv.forward_k(x), self.linear_qkv.forward_v(x),
+                               self.model_config.num_attention_heads, self.model_config.num_query_groups, None,
+                               self._ln(self.k_layernorm), sin_emb, cos_emb, batch=b,
+                               eps=self.model_config.layernorm_epsilon,
+                               zero_centered_gamma=self.model_config.apply_layernorm_1p, head_perm_cp=head_perm_cp)
+        return kv
+
+    def get_k(self, mixed_qqkv, cos_emb, sin_emb):
+        """dit_module.py:970-980 (a view of the packed result)."""
+        return self.get_kv(mixed_qqkv, cos_emb, sin_emb)[..., :F.HEAD_DIM]
+
+    def get_v(self, mixed_qqkv):
+        """dit_module.py:987-989: pure re-layout of the projection output."""
+        sq, b, _ = mixed_qqkv.shape
+        return self.linear_qkv.forward_v(mixed_qqkv.reshape(sq * b, -1)).view(sq * b, -1, F.HEAD_DIM)
+
+    def get_qkv(self, mixed_qqkv, cos_emb, sin_emb):
+        """dit_module.py:998-1003: one prologue launch for all three."""
+        sq, b, _ = mixed_qqkv.shape
+        x = mixed_qqkv.reshape(sq * b, -1)
+        q, kv = F.qk_norm_rope(self.linear_qkv.forward_q(x), self.linear_qkv.forward_k(x), self.linear_qkv.forward_v(x),
+                               self.model_config.num_attention_heads, self.model_config.num_query_groups,
+                               self._ln(self.q_layernorm), self._ln(self.k_layernorm), sin_emb, cos_emb, batch=b,
+                               eps=self.model_config.layernorm_epsilon,
+                               zero_centered_gamma=self.model_config.apply_layernorm_1p)
+        return q, kv[..., :F.HEAD_DIM], kv[..., F.HEAD_DIM:]
+
+    def get_xqkv(self, mixed_qqkv, key_value_states):
+        """dit_module.py:1005-1021: (query_xattn [(b sq), hn, hd], key_xattn, value_xattn [ytot, hn, hd])."""
+        q_rows, kv_x = self.cross_attention_prepare(mixed_qqkv, key_value_states)
+        q = q_rows[0] if len(q_rows) == 1 else torch.cat(q_rows, dim=0)
+        return q, kv_x[..., :F.HEAD_DIM], kv_x[..., F.HEAD_DIM:]
+
+    def adjust_key_and_value_for_inference(self, key_and_value, inference_params, meta_args):
+        """dit_module.py:933-946, for callers that want the reference's materialised (key, value): performs the cache
+        append and returns views of `cat(cache prefix, new)`. The fast paths of this class never call it - they hand
+        the cache prefix and the new tokens to the kernel as two segments and skip the concatenation."""
+        if inference_params is None:
+            return key_and_value[..., :F.HEAD_DIM], key_and_value[..., F.HEAD_DIM:]
+        cache, start, app = self._cache_plan(inference_params, meta_args, key_and_value.shape[0], key_and_value.dtype,
+                                             key_and_value.device)
+        if cache is not None:
+            if app > 0:
+                F.kv_cache_append(cache, key_and_value, start, app)
+            if start > 0:
+                key_and_value = torch.cat([cache[:start], key_and_value], dim=0)
+        return key_and_value[..., :F.HEAD_DIM], key_and_value[..., F.HEAD_DIM:]
+
+    def full_attention(self, bs: int, meta_args: ModelMetaArgs, q, k, v, i: int, out=None):
+        """dit_module.py:1068-1096 (the cp_shuffle_overlap entry): q is already sliced to denoising range i, k / v are
+        the full key / value sequence; rows attend to k_range[i]."""
+        assert bs == 1   # dit_module.py:1070
+        p = meta_args.core_attn_params
+        if out is None:
+            out = torch.empty_like(q)
+        q_range = p.q_range[i:i + 1] - p.q_range[i, 0]          # rebased to the slice (dit_module.py:1072)
+        F.attn_ranges(q, k, v, q_range, p.k_range[i:i + 1], out=out, return_lse=False)
+        return out
+
     def core_attention(self, query, k_new, v_new, bs: int, meta_args: ModelMetaArgs, k_cache=None, v_cache=None,
                        out=None, proj_buf=None):
         """dit_module.py:1023-1066 on "(sq b)"-ordered rows. bs > 1 only occurs with one range shared by all batch

@@ -84,12 +84,7 @@ struct Barriers {
   // exchange buffers of the two threads that share a row (only with MAGI_COL_SPLIT == 2)
   float xch[kSplit == 2 ? 2 : 1][2][2][kSplit == 2 ? 128 : 1];   // [parity][q tile][column half][row]: row max
   float xl[2][2][kSplit == 2 ? 128 : 1];                         // [q tile][column half][row]: row sum
-  // copy of the work list (header, prefix sums, sorted ranges) when it has at most kMaxCachedRanges ranges: every
-  // role decodes one item per work item with a chain of dependent loads, which from global memory costs microseconds
-  // - noticeable for cross-attention items that are only 1-4 key tiles long
-  int work[4 + 5 * 64 + 1];
 };
-constexpr int kMaxCachedRanges = 64;
 
 constexpr int kSmemBytes = (2 * kQStages + kStages) * kTileBytes + 1024 /*align slack*/ + sizeof(Barriers);
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
@@ -238,7 +233,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int group = p.Hq / p.Hkv;
-  const int* ws = p.work;   // re-pointed at the shared-memory copy below when it fits
+  const int* __restrict__ ws = p.work;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kQStages; ++s) {
@@ -268,17 +263,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tma_prefetch_desc(&tm_va);
     tma_prefetch_desc(&tm_kb);
     tma_prefetch_desc(&tm_vb);
-  }
-  {
-    const int n = p.work[1];
-#ifdef MAGI_NO_WORK_CACHE
-    if (false) {
-#else
-    if (n <= kMaxCachedRanges) {
-#endif
-      for (int i = threadIdx.x; i < 4 + 5 * n + 1; i += blockDim.x) bar->work[i] = p.work[i];
-      ws = bar->work;
-    }
   }
   tc_fence_before();
   __syncthreads();

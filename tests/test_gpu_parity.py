@@ -347,6 +347,62 @@ def test_full_attention_block_matches_reference_golden():
             assert x_out[:clip].abs().sum() == 0   # zero caption tokens -> zeros (dit_module.py:1124 semantics)
 
 
+def test_reference_named_pieces_match_golden():
+    """get_q / get_kv / get_qkv / get_xqkv / adjust_key_and_value_for_inference / full_attention keep the reference's
+    names and argument meaning (dit_module.py:933-1096); their outputs are compared with what the reference's own
+    methods produced on the same weights and inputs (golden step C: slice_point 1, cache from steps A-B)."""
+    from magi_b200.common import InferenceParams, ModelMetaArgs, PackedCoreAttnParams
+    g = Golden("attention_single_rank.npz")
+    attn = _build_module(g)
+    clip = int(g["clip"])
+    s = "C"
+    hs = g.torch(f"{s}.hidden_states", "cuda")
+    rope = g.torch(f"{s}.rope", "cuda")
+    sin_emb, cos_emb = rope.tensor_split(2, -1)
+    mixed = attn.linear_qkv.forward_ln(hs)
+
+    def close(a, ref, ulps=6.0, atol=3e-2):   # cuBLAS vs ATen-CPU GEMM feeding a LayerNorm: a few bf16 ulps
+        a = a.float().cpu().numpy()
+        tol = np.maximum(np.abs(a), np.abs(ref)) * 2.0 ** -7 * ulps + atol
+        assert a.shape == ref.shape and (np.abs(a - ref) <= tol).all(), float(np.abs(a - ref).max())
+
+    q = attn.get_q(mixed, cos_emb, sin_emb)
+    kv = attn.get_kv(mixed, cos_emb, sin_emb)
+    close(q, g[f"{s}.q"])
+    close(kv, g[f"{s}.kv"])
+    q2, k2, v2 = attn.get_qkv(mixed, cos_emb, sin_emb)
+    assert torch.equal(q2, q) and torch.equal(k2, kv[..., :128]) and torch.equal(v2, kv[..., 128:])
+    assert torch.equal(attn.get_k(mixed, cos_emb, sin_emb), kv[..., :128])
+    assert torch.equal(attn.get_v(mixed), kv[..., 128:])
+    xq, xk, xv = attn.get_xqkv(mixed, g.torch(f"{s}.key_value_states", "cuda"))
+    close(xq, g[f"{s}.xq"])
+    close(xk, g[f"{s}.xk"])
+    close(xv, g[f"{s}.xv"], ulps=2.0, atol=2e-2)
+    # KV cache: replay the reference's cache contents of step B, then the reference's adjust_key_and_value call of C
+    sp, dn = 1, 2
+    inf = InferenceParams(1, 4 * clip)
+    inf.key_value_memory_dict[1] = g.torch("B.cache_after", "cuda").clone()
+    inf.update_kv_cache = False
+    k_range, q_range = g.raw(f"{s}.k_range"), g.raw(f"{s}.q_range")
+    meta = ModelMetaArgs(H=4, W=4, cp_pad_size=None, cp_split_sizes=None, slice_point=sp, denoising_range_num=dn,
+                         range_num=sp + dn, extract_prefix_video_feature=False, fwd_extra_1st_chunk=False,
+                         distill_nearly_clean_chunk=False, clip_token_nums=clip, enable_cuda_graph=False,
+                         core_attn_params=PackedCoreAttnParams(i32(q_range), i32(k_range), q_range, k_range, clip,
+                                                               O.max_seqlen_k(k_range)), cross_attn_params=None)
+    kv_ref = g.torch(f"{s}.kv", "cuda")                       # the reference's own new-token K|V
+    key, value = attn.adjust_key_and_value_for_inference(kv_ref, inf, meta)
+    assert key.shape[0] == sp * clip + dn * clip
+    assert torch.equal(key[:sp * clip], inf.key_value_memory_dict[1][:sp * clip, :, :128])
+    assert torch.equal(value[sp * clip:], kv_ref[..., 128:])
+    assert torch.equal(inf.key_value_memory_dict[1], g.torch("C.cache_after", "cuda"))   # update_kv_cache False
+    # full_attention(i) on the reference's q / materialised k, v == rows of the reference's core_attn_out
+    q_ref = g.torch(f"{s}.q", "cuda")
+    ref_core = g[f"{s}.core_attn_out"].reshape(dn * clip, -1, 128)
+    for i in range(dn):
+        o = attn.full_attention(1, meta, q_ref[i * clip:(i + 1) * clip], key, value, i)
+        check_attn(o, ref_core[i * clip:(i + 1) * clip], f"full_attention range {i}")
+
+
 def test_fused_out_projection_input_layout():
     """both attention kernels write straight into the reference's out-projection input
     "sq b (n hn hd) -> sq b (hn n hd)", n = 2, hn = 8 (attn_linear_proj, dit_module.py:1332-1338). Must equal
