@@ -175,6 +175,16 @@ MAGI_API int magi_ulysses_relayout(void* dst, const void* src, int64_t seq, int3
                                    int32_t cp, int32_t kv_repeat, int32_t mode, int32_t dst_heads_total,
                                    int32_t dst_head_offset, void* stream);
 
+/*
+ * CSO (cp_shuffle_overlap) receive side: un-shuffle and un-pad the key/value sequence after its all-to-all,
+ *   "(cp dn spb) hn nhd -> dn (cp spb) hn nhd" [:, :clip] flattened   (dit_module.py:1215-1224: rearrange + slice +
+ *   .contiguous()), as one gather that can write straight into the KV-cache slot:
+ *   dst[d * clip + t, :] = src[((t / spb) * dn + d) * spb + t % spb, :]   for d < dn, t < clip <= cp * spb.
+ * Rows are row_elems bf16 (multiple of 8), token strides in elements.
+ */
+MAGI_API int magi_cso_unshuffle(void* dst, int64_t dst_token_stride, const void* src, int64_t src_token_stride,
+                                int32_t cp, int32_t dn, int64_t spb, int64_t clip, int64_t row_elems, void* stream);
+
 /* Diagnostics */
 MAGI_API const char* magi_last_error(void);
 MAGI_API const char* magi_build_info(void);

@@ -20,6 +20,7 @@ EXPORTS = (
     "magi_kv_cache_append",
     "magi_lse_merge",
     "magi_ulysses_relayout",
+    "magi_cso_unshuffle",
     "magi_last_error",
     "magi_build_info",
     "magi_launch_count",
@@ -143,6 +144,9 @@ def lib() -> C.CDLL:
     L.magi_ulysses_relayout.restype = C.c_int
     L.magi_ulysses_relayout.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    L.magi_cso_unshuffle.restype = C.c_int
+    L.magi_cso_unshuffle.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64,
+                                     C.c_int64, C.c_int64, C.c_void_p]
     L.magi_last_error.restype = C.c_char_p
     L.magi_build_info.restype = C.c_char_p
     L.magi_launch_count.restype = C.c_uint64

@@ -210,15 +210,17 @@ class FullyParallelAttention(nn.Module):
                 key_and_value = torch.cat([cache[:start], key_and_value], dim=0)
         return key_and_value[..., :F.HEAD_DIM], key_and_value[..., F.HEAD_DIM:]
 
-    def full_attention(self, bs: int, meta_args: ModelMetaArgs, q, k, v, i: int, out=None):
+    def full_attention(self, bs: int, meta_args: ModelMetaArgs, q, k, v, i: int, out=None, k_cache=None, v_cache=None):
         """dit_module.py:1068-1096 (the cp_shuffle_overlap entry): q is already sliced to denoising range i, k / v are
-        the full key / value sequence; rows attend to k_range[i]."""
+        the full key / value sequence (or, with k_cache / v_cache, the new tokens that follow the cache prefix); rows
+        attend to k_range[i]."""
         assert bs == 1   # dit_module.py:1070
         p = meta_args.core_attn_params
         if out is None:
-            out = torch.empty_like(q)
-        q_range = p.q_range[i:i + 1] - p.q_range[i, 0]          # rebased to the slice (dit_module.py:1072)
-        F.attn_ranges(q, k, v, q_range, p.k_range[i:i + 1], out=out, return_lse=False)
+            out = torch.empty((q.shape[0], q.shape[1], F.HEAD_DIM), dtype=q.dtype, device=q.device)
+        q_range = p.q_range[i:i + 1] - p.q_range[i, :1]         # rebased to the slice (dit_module.py:1072)
+        F.attn_ranges(q, k, v, q_range, p.k_range[i:i + 1], k_cache=k_cache, v_cache=v_cache, out=out,
+                      return_lse=False)
         return out
 
     def core_attention(self, query, k_new, v_new, bs: int, meta_args: ModelMetaArgs, k_cache=None, v_cache=None,
@@ -357,7 +359,8 @@ class FullyParallelAttention(nn.Module):
             core_attn_out, xattn_out = self._forward_ring(mixed_qqkv, key_value_states, inference_params, sin_emb,
                                                           cos_emb, meta_args)
         elif strategy == "cp_shuffle_overlap":
-            raise NotImplementedError("cp_shuffle_overlap (CSO, 'for 4090 or older') is not part of this build")
+            core_attn_out, xattn_out = self._forward_cso(mixed_qqkv, key_value_states, inference_params, sin_emb,
+                                                         cos_emb, meta_args)
         else:
             raise ValueError(f"Unsupported cp_strategy: {strategy}")   # dit_module.py:1244
         return core_attn_out, xattn_out
@@ -424,6 +427,67 @@ class FullyParallelAttention(nn.Module):
             self.engine_config.ulysses_overlap_degree, b, cp, split, relayout_out=relayout_out)
         self._kc = self._vc = None
         return out
+
+    # ------------------------------------------------------------------ CSO (dit_module.py:1207-1242)
+    def _forward_cso(self, mixed_qqkv, key_value_states, inference_params, sin_emb, cos_emb, meta_args):
+        """cp_shuffle_overlap: every rank holds the same slice of every (padded) chunk; K/V are exchanged once
+        (head-sharded, un-shuffled and un-padded on arrival, straight into the KV-cache slot when all of it is
+        cached), then chunk i's attention overlaps the query all-to-all of chunk i+1 and the output all-to-all of
+        chunk i-1."""
+        sq, b, _ = mixed_qqkv.shape
+        assert b == 1                                       # dit_module.py:1070
+        cp, dn = self.engine_config.cp_size, meta_args.denoising_range_num
+        Hq, Hkv = self.model_config.num_attention_heads, self.model_config.num_query_groups
+        eps, z = self.model_config.layernorm_epsilon, self.model_config.apply_layernorm_1p
+        dev, dt = mixed_qqkv.device, mixed_qqkv.dtype
+        split = [x * b for x in meta_args.cp_split_sizes]   # dit_module.py:1150
+        rows = sq * b
+        spb = divide(rows, dn)
+        clip = meta_args.clip_token_nums
+        hq_loc, hkv_loc = divide(Hq, cp), self.num_query_groups_per_partition
+        x2d = mixed_qqkv.reshape(rows, -1)
+
+        # K/V: prologue writes the all-to-all send layout "(cp spb) hn hd" (with KV-head replication when cp > Hkv)
+        _, kv = F.qk_norm_rope(None, self.linear_qkv.forward_k(x2d), self.linear_qkv.forward_v(x2d), Hq, Hkv, None,
+                               self._ln(self.k_layernorm), sin_emb, cos_emb, batch=b, eps=eps, zero_centered_gamma=z,
+                               head_perm_cp=cp)
+        kv_recv, handle_kv = cpm.cso_communication(kv, cp, split, "kv", send_layout=True)
+
+        # Q: one send buffer per chunk, "(dn cp spb) hn hd", written in place by the prologue (one launch per chunk)
+        xq = self.linear_qkv.forward_q(x2d)
+        q_send = torch.empty((dn * cp * spb, hq_loc, F.HEAD_DIM), dtype=dt, device=dev)
+        for d in range(dn):
+            F.qk_norm_rope(xq[d * spb:(d + 1) * spb], None, None, Hq, Hkv, self._ln(self.q_layernorm), None,
+                           sin_emb[d * spb:(d + 1) * spb], cos_emb[d * spb:(d + 1) * spb], batch=b, eps=eps,
+                           zero_centered_gamma=z, head_perm_cp=cp, q_out=q_send[d * cp * spb:(d + 1) * cp * spb])
+        helper = cpm.CSOHelper(dn, cp, split)
+        query, handle_q = helper.split_query_for_overlap(q_send, send_layout=True)
+        # the cross-attention needs no communication: its projections + norms run under the input all-to-alls
+        x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states)
+
+        handle_kv.wait()
+        total_rows = dn * clip
+        cache, start, app = self._cache_plan(inference_params, meta_args, total_rows, dt, dev)
+        if cache is not None and app == total_rows:        # un-shuffle straight into the cache slot
+            kv_new = F.cso_unshuffle(kv_recv, cp, dn, clip, out=cache[start:start + total_rows])
+        else:
+            kv_new = F.cso_unshuffle(kv_recv, cp, dn, clip)
+            if cache is not None and app > 0:
+                F.kv_cache_append(cache, kv_new, start, app)
+        kc = vc = None
+        if cache is not None and start > 0:
+            kc, vc = cache[:start, :, :F.HEAD_DIM], cache[:start, :, F.HEAD_DIM:]
+
+        handle_q.wait()
+        outs, handle_attn = helper.overlap(partial(self.full_attention, b, meta_args, k_cache=kc, v_cache=vc), query,
+                                           kv_new[..., :F.HEAD_DIM], kv_new[..., F.HEAD_DIM:])
+        xattn_out = self.cross_attention_attend(x_prepared, (sq, b), meta_args.cross_attn_params)
+        handle_attn.wait()
+        # "(dn cp sq b) hn hd -> (dn sq) b (cp hn hd)": one re-layout per chunk, written in place
+        result = torch.empty((rows, Hq, F.HEAD_DIM), dtype=dt, device=dev)
+        for d, o in enumerate(outs):
+            F.ulysses_relayout(o, cp, 1, out=result[d * spb:(d + 1) * spb])
+        return result.view(sq, b, Hq * F.HEAD_DIM), xattn_out
 
     # ------------------------------------------------------------------ ring-KV (new)
     def _forward_ring(self, mixed_qqkv, key_value_states, inference_params, sin_emb, cos_emb, meta_args):

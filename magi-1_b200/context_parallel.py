@@ -13,8 +13,12 @@ inference/infra/parallelism/context_parallel.py, re-designed for one NVSwitch do
 Collectives go through torch.distributed (NCCL on the GPU box). Everything that computes is injected as a callable
 (attention, re-layout, merge), exactly as the reference's UlyssesScheduler takes callables
 (context_parallel.py:452-597): the product wires in the CUDA kernels, the CPU (gloo) tests wire in test doubles.
-The cp_shuffle_overlap (CSO) strategy of the reference ("for 4090 or older", context_parallel.py:324) is not built.
+The cp_shuffle_overlap (CSO) strategy (context_parallel.py:257-305, 603-664) is built with the same entry points
+(`cp_shuffle_overlap_process`, `cso_communication`, `CSOHelper`); on NVSwitch the fused "[q(i+1) | o(i-1)]" message of
+the reference (one torch.concat + one chunk copy per step) is sent as two back-to-back all-to-alls instead, so no
+staging copy is made.
 """
+import math
 from typing import Callable, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -22,7 +26,7 @@ import torch
 import torch.distributed as dist
 
 from . import parallel_state as mpu
-from .common import ModelMetaArgs, PackedCoreAttnParams, PackedCrossAttnParams
+from .common import ModelMetaArgs, PackedCoreAttnParams, PackedCrossAttnParams, divide
 
 
 class FakeHandle:
@@ -40,10 +44,23 @@ def scatter_to_context_parallel_region(input_, cp_split_sizes, cp_shuffle_num=1,
     world_size = mpu.get_cp_world_size()
     if world_size == 1:
         return input_
-    if cp_shuffle_num != 1 or cp_pad_size != 0:
-        raise NotImplementedError("cp_shuffle_overlap (CSO) is not part of this build")
     rank = mpu.get_cp_rank()
+    if cp_shuffle_num > 1:
+        # CSO: every one of the cp_shuffle_num chunks is zero-padded to a multiple of cp and split on its own, so a
+        # rank holds the same slice of every chunk (context_parallel.py:40-48)
+        pad = divide(cp_pad_size, cp_shuffle_num)
+        sizes = [divide(s, cp_shuffle_num) for s in cp_split_sizes]
+        lo = sum(sizes[:rank])
+        n = sizes[rank]
+        chunk = divide(input_.shape[0], cp_shuffle_num)
+        out = input_.new_zeros((cp_shuffle_num, n) + tuple(input_.shape[1:]))
+        valid = max(0, min(lo + n, chunk) - lo)      # rows of the slice that are not padding
+        if valid > 0:
+            out[:, :valid] = input_.unflatten(0, (cp_shuffle_num, chunk))[:, lo:lo + valid]
+        return out.flatten(0, 1)
     dim_offset = sum(cp_split_sizes[:rank])
+    if cp_pad_size:
+        input_ = torch.nn.functional.pad(input_, [0, 0] * (input_.dim() - 1) + [0, cp_pad_size])
     return input_[dim_offset:dim_offset + cp_split_sizes[rank]].contiguous()
 
 
@@ -52,14 +69,22 @@ def gather_from_context_parallel_region(input_, cp_split_sizes, cp_shuffle_num=1
     world_size = mpu.get_cp_world_size()
     if world_size == 1:
         return input_
-    if cp_shuffle_num != 1 or cp_pad_size != 0:
-        raise NotImplementedError("cp_shuffle_overlap (CSO) is not part of this build")
     input_ = input_.contiguous()
     dim_size = list(input_.size())
     dim_size[0] = sum(cp_split_sizes)
     output = torch.empty(dim_size, dtype=input_.dtype, device=input_.device)
     outputs = list(torch.split(output, cp_split_sizes, dim=0))
     dist.all_gather(outputs, input_, group=mpu.get_cp_group())
+    if cp_shuffle_num > 1:
+        # CSO (context_parallel.py:74-84): "(cp dn spb) -> (dn cp spb)", then drop every chunk's zero padding.
+        # Equal shards (cp_shuffle_overlap_process pads to make them so): one permuted view, one copy.
+        spb = divide(cp_split_sizes[0], cp_shuffle_num)
+        assert all(s == cp_split_sizes[0] for s in cp_split_sizes)
+        keep = spb * world_size - divide(cp_pad_size, cp_shuffle_num)
+        v = output.unflatten(0, (world_size, cp_shuffle_num, spb)).transpose(0, 1).flatten(1, 2)
+        return v[:, :keep].flatten(0, 1)
+    if cp_pad_size:
+        return output[:dim_size[0] - cp_pad_size]
     return output
 
 
@@ -78,25 +103,33 @@ def cp_update_cross_attn_qkv_range(cross_attn_params: PackedCrossAttnParams, bat
                                    cp_split_sizes: List[int], device, cp_shuffle_num: int = 1, cp_pad_size: int = 0):
     """context_parallel.py:134-224: intersect every cross-attention q segment with this rank's sequence shard and
     rebase to shard-local rows; text K/V are replicated so kv ranges are only filtered."""
-    if cp_shuffle_num != 1 or cp_pad_size != 0:
-        raise NotImplementedError("cp_shuffle_overlap (CSO) is not part of this build")
     cp_rank = mpu.get_cp_rank()
+    seq_len_cur_rank = cp_split_sizes[cp_rank]
     # host-side interval arithmetic (a handful of segments); one D2H read per forward, like the reference's
     # boolean-mask indexing at context_parallel.py:182-190
     cu_q = cross_attn_params.cu_seqlens_q.detach().cpu().numpy().astype(np.int64)
     cu_k = cross_attn_params.cu_seqlens_kv.detach().cpu().numpy().astype(np.int64)
-    bounds = np.concatenate([[0], np.cumsum(np.asarray(cp_split_sizes, dtype=np.int64))])
+    # CSO: every q segment (one chunk) grows by the chunk's zero padding (context_parallel.py:164-167)
+    cu_q = cu_q + np.arange(cu_q.shape[0], dtype=np.int64) * divide(cp_pad_size, cp_shuffle_num)
+    sizes = [divide(x, cp_shuffle_num) for x in cp_split_sizes]
+    bounds = np.concatenate([[0], np.cumsum(np.asarray(sizes, dtype=np.int64))])
     total = int(bounds[-1])
     qs, qe = cu_q[:-1], cu_q[1:]
     xq, xk = [], []
     for i in range(batch_size):
-        s, e = bounds[cp_rank] + i * total, bounds[cp_rank + 1] + i * total
-        st, en = np.maximum(s, qs), np.minimum(e, qe)
-        m = st < en
-        part = np.stack([st[m], en[m]], axis=1)
-        part = part - part[:, 0].min()
-        xq.append(part)
-        xk.append(np.stack([cu_k[:-1][m], cu_k[1:][m]], axis=1))
+        inner_q, inner_k = [], []
+        for j in range(cp_shuffle_num):
+            off = (i * cp_shuffle_num + j) * total
+            s, e = bounds[cp_rank] + off, bounds[cp_rank + 1] + off
+            st, en = np.maximum(s, qs), np.minimum(e, qe)
+            m = st < en
+            part = np.stack([st[m], en[m]], axis=1)
+            part = part - part[:, 0].min()
+            inner_q.append(part)
+            inner_k.append(np.stack([cu_k[:-1][m], cu_k[1:][m]], axis=1))
+        ioffs = np.concatenate([[0], np.cumsum([r[-1, -1] for r in inner_q])[:-1]])
+        xq.append(np.concatenate([r + int(o) for r, o in zip(inner_q, ioffs)], axis=0))
+        xk.append(np.concatenate(inner_k, axis=0))
     offs = np.concatenate([[0], np.cumsum([r[-1, -1] for r in xq])[:-1]])
     q_ranges = np.concatenate([r + int(o) for r, o in zip(xq, offs)], axis=0)
     k_ranges = np.concatenate(xk, axis=0)
@@ -110,7 +143,7 @@ def cp_update_cross_attn_qkv_range(cross_attn_params: PackedCrossAttnParams, bat
         return torch.as_tensor(a.astype(np.int32), device=device)
 
     return PackedCrossAttnParams(q_ranges=t(q_ranges), kv_ranges=t(k_ranges), cu_seqlens_q=t(cu_q_new),
-                                 cu_seqlens_kv=t(cu_k_new), max_seqlen_q=cp_split_sizes[cp_rank],
+                                 cu_seqlens_kv=t(cu_k_new), max_seqlen_q=seq_len_cur_rank,
                                  max_seqlen_kv=cross_attn_params.max_seqlen_kv)
 
 
@@ -130,6 +163,41 @@ def cp_ulysses_process(cp_size: int, x: torch.Tensor, condition_map: torch.Tenso
     return x, condition_map, rope, cp_split_sizes, cross_attn_params
 
 
+def cp_shuffle_overlap_process(cp_size: int, x: torch.Tensor, condition_map: torch.Tensor, rope: torch.Tensor,
+                               xattn_mask_for_cuda_graph: Union[torch.Tensor, None], ardf_meta: dict,
+                               core_attn_params: PackedCoreAttnParams, cross_attn_params: PackedCrossAttnParams):
+    """context_parallel.py:257-305: every denoising chunk is padded to a multiple of cp and split across the ranks on
+    its own (load balance under the chunk-causal mask); q ranges are rescaled to the padded chunk length, k ranges
+    stay in unpadded coordinates (the key/value sequence is un-padded again after its all-to-all)."""
+    seq_len, N, D = x.shape
+    assert seq_len == rope.size(0), f"seq_len: {seq_len} != rope.size(0): {rope.size(0)}"
+    assert condition_map.size(0) == seq_len, f"condition_map.size(0): {condition_map.size(0)} != seq_len: {seq_len}"
+    if xattn_mask_for_cuda_graph is not None:
+        raise NotImplementedError("xattn_mask_for_cuda_graph is hard-wired to None in the reference (dit_model.py:210)")
+    cp_shuffle_num = ardf_meta["denoising_range_num"]
+    chunk = divide(seq_len, cp_shuffle_num)
+    cp_pad_size = 0
+    if chunk % cp_size != 0:
+        cp_pad_size = (cp_size - chunk % cp_size) * cp_shuffle_num
+    cp_split_sizes = [(seq_len + cp_pad_size) // cp_size] * cp_size
+    x = scatter_to_context_parallel_region(x, cp_split_sizes, cp_shuffle_num, cp_pad_size)
+    condition_map = scatter_to_context_parallel_region(condition_map, cp_split_sizes, cp_shuffle_num, cp_pad_size)
+    rope = scatter_to_context_parallel_region(rope, cp_split_sizes, cp_shuffle_num, cp_pad_size)
+    g = math.gcd(seq_len, seq_len + cp_pad_size)
+    _sq, _psq = seq_len // g, (seq_len + cp_pad_size) // g
+    q_range = ardf_meta["q_range"] * _psq // _sq
+    np_q_range = (core_attn_params.np_q_range.astype(np.int64) * _psq // _sq).astype(np.int32) \
+        if core_attn_params is not None and core_attn_params.np_q_range is not None else q_range.cpu().numpy()
+    np_k_range = core_attn_params.np_k_range if core_attn_params is not None and \
+        core_attn_params.np_k_range is not None else ardf_meta["k_range"].cpu().numpy()
+    core_attn_params = PackedCoreAttnParams(
+        q_range=q_range, k_range=ardf_meta["k_range"], np_q_range=np_q_range, np_k_range=np_k_range,
+        max_seqlen_q=ardf_meta["max_seqlen_q"] * _psq // _sq, max_seqlen_k=ardf_meta["max_seqlen_k"])
+    cross_attn_params = cp_update_cross_attn_qkv_range(cross_attn_params, N, cp_split_sizes, x.device, cp_shuffle_num,
+                                                       cp_pad_size)
+    return x, condition_map, rope, cp_pad_size, cp_split_sizes, core_attn_params, cross_attn_params
+
+
 def cp_pre_process(cp_size: int, cp_strategy: str, x: torch.Tensor, condition_map: torch.Tensor, rope: torch.Tensor,
                    xattn_mask_for_cuda_graph, ardf_meta: dict, core_attn_params: PackedCoreAttnParams,
                    cross_attn_params: PackedCrossAttnParams):
@@ -142,17 +210,21 @@ def cp_pre_process(cp_size: int, cp_strategy: str, x: torch.Tensor, condition_ma
             cp_size, x, condition_map, rope, xattn_mask_for_cuda_graph, cross_attn_params)
         return x, condition_map, rope, 0, cp_split_sizes, core_attn_params, cross_attn_params
     if cp_strategy == "cp_shuffle_overlap":
-        raise NotImplementedError("cp_shuffle_overlap (CSO, 'for 4090 or older') is not part of this build")
-    raise ValueError(f"Invalid CP strategy: {cp_strategy}, expected cp_ulysses or cp_ring_kv")
+        return cp_shuffle_overlap_process(cp_size, x, condition_map, rope, xattn_mask_for_cuda_graph, ardf_meta,
+                                          core_attn_params, cross_attn_params)
+    raise ValueError(f"Invalid CP strategy: {cp_strategy}, expected cp_ulysses, cp_shuffle_overlap or cp_ring_kv")
 
 
 def cp_post_process(cp_size: int, cp_strategy: str, x: torch.Tensor, meta_args: ModelMetaArgs) -> torch.Tensor:
     """context_parallel.py:364-375."""
     if cp_size == 1:
         return x
+    if cp_strategy == "cp_shuffle_overlap":
+        return gather_from_context_parallel_region(x, meta_args.cp_split_sizes, meta_args.denoising_range_num,
+                                                   meta_args.cp_pad_size)
     if cp_strategy in ("cp_ulysses", "cp_ring_kv"):
         return gather_from_context_parallel_region(x, meta_args.cp_split_sizes)
-    raise ValueError(f"Invalid CP strategy: {cp_strategy}, expected cp_ulysses or cp_ring_kv")
+    raise ValueError(f"Invalid CP strategy: {cp_strategy}, expected cp_ulysses, cp_shuffle_overlap or cp_ring_kv")
 
 
 #####################################################
@@ -270,6 +342,90 @@ class UlyssesScheduler:
         # "(cp sq b) hn hd -> sq b (cp hn hd)"
         core_attn_out = result.view(local // batch_size, batch_size, cp_size * q_head * q_hidden)
         return core_attn_out, xattn_out
+
+
+#####################################################
+# CSO (context shuffle overlap) attention pipeline
+#####################################################
+def cso_communication(input: torch.Tensor, cp_world_size: int, cp_split_sizes: List[int], comm_type: str = None, *,
+                      relayout: Optional[Callable] = None, send_layout: bool = False):
+    """context_parallel.py:603-621: equal-split all-to-all along dim 0. comm_type "kv": the packed K/V tensor
+    "spb (cp hn) hd" is first brought to send layout "(cp spb) hn hd" (with KV-head replication when cp > hn) by
+    `relayout(tensor, cp, rep)`, or already is (send_layout=True: the prologue kernel wrote it that way)."""
+    if cp_world_size == 1:
+        return input, FakeHandle()
+    assert cp_split_sizes is not None
+    if comm_type == "kv" and not send_layout:
+        _, hn, _ = input.shape
+        rep = divide(cp_world_size, hn) if (cp_world_size % hn == 0 and cp_world_size != hn) else 1
+        input = relayout(input, cp_world_size, rep)
+    assert input.is_contiguous()
+    output = torch.empty(input.shape, device=input.device, dtype=input.dtype)
+    handle = dist.all_to_all_single(output, input, input_split_sizes=list(cp_split_sizes), group=mpu.get_cp_group(),
+                                    async_op=True)
+    return output, handle
+
+
+def cso_unshuffle_rows(cp: int, dn: int, spb: int, clip: int) -> np.ndarray:
+    """Row gather of "(cp dn spb) -> dn (cp spb)" followed by [:, :clip] (dit_module.py:1215-1224): source row of every
+    row of the un-padded, chunk-ordered key/value sequence inside the all-to-all receive buffer."""
+    t = np.arange(clip, dtype=np.int64)
+    c, s = t // spb, t % spb
+    d = np.arange(dn, dtype=np.int64)[:, None]
+    return ((c[None, :] * dn + d) * spb + s[None, :]).reshape(-1)
+
+
+class CSOHelper:
+    """context_parallel.py:624-664. Chunk i's attention runs while chunk i+1's queries arrive and chunk i-1's outputs
+    leave. The reference concatenates q(i+1) and o(i-1) into one message and splits it again on arrival (two copies
+    per step); here they are two all-to-alls issued back to back, which on NVSwitch costs one more launch and no
+    copy. Entry points, argument meaning and the returned (core_attn_outs, handle_attn) are the reference's."""
+
+    def __init__(self, cp_shuffle_num, cp_world_size, cp_split_sizes):
+        self.cp_shuffle_num = cp_shuffle_num
+        self.cp_world_size = cp_world_size
+        self.cp_split_sizes = [divide(x, self.cp_shuffle_num) for x in cp_split_sizes]
+
+    def split_query_for_overlap(self, query, *, relayout: Optional[Callable] = None, send_layout: bool = False):
+        """query "(dn spb) (cp hn) hd" -> dn send buffers "(cp spb) hn hd"; chunk 0's all-to-all is started.
+        send_layout=True: `query` already is "(dn cp spb) hn hd" (written that way by the prologue kernel)."""
+        dn, cp = self.cp_shuffle_num, self.cp_world_size
+        if not send_layout and cp > 1:
+            t, h, d = query.shape
+            if relayout is not None:
+                query = torch.cat([relayout(c, cp, 1) for c in torch.chunk(query, dn, dim=0)], dim=0)
+            else:
+                query = query.view(dn, t // dn, cp, h // cp, d).permute(0, 2, 1, 3, 4).reshape(t * cp, h // cp, d)
+        querys = list(torch.chunk(query, dn, dim=0))
+        querys[0], handle_q = cso_communication(querys[0], cp, self.cp_split_sizes)
+        return querys, handle_q
+
+    def overlap(self, fattn, qs, k, v):
+        """fattn(q, k, v, i) -> o. Returns ([o_0 .. o_{dn-1}] each "(cp sq b) hn hd", handle of the last one)."""
+        dn, cp = self.cp_shuffle_num, self.cp_world_size
+        outs = []
+        pending_q = pending_o = None
+        o = None
+        for i in range(dn):
+            q = qs[0] if i == 0 else None
+            if i > 0:
+                recv_q, h = pending_q
+                h.wait()
+                q = recv_q
+            # issue before this chunk's attention: queries of the next chunk, outputs of the previous one
+            if i + 1 < dn:
+                pending_q = cso_communication(qs[i + 1], cp, self.cp_split_sizes)
+            if pending_o is not None:
+                pending_o[1].wait()
+            if i > 0:
+                pending_o = cso_communication(o, cp, self.cp_split_sizes)
+                outs.append(pending_o[0])
+            o = fattn(q, k, v, i)
+        if pending_o is not None:
+            pending_o[1].wait()
+        last_o, handle_attn = cso_communication(o, cp, self.cp_split_sizes)
+        outs.append(last_o)
+        return outs, handle_attn
 
 
 #####################################################

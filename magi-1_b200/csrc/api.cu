@@ -312,4 +312,23 @@ int magi_ulysses_relayout(void* dst, const void* src, int64_t seq, int32_t heads
   return 0;
 }
 
+int magi_cso_unshuffle(void* dst, int64_t dst_token_stride, const void* src, int64_t src_token_stride, int32_t cp,
+                       int32_t dn, int64_t spb, int64_t clip, int64_t row_elems, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MAGI_CHECK(cp >= 1 && dn >= 1 && spb >= 0 && clip >= 0, "bad shape");
+  MAGI_CHECK(clip <= spb * cp, "clip must not exceed cp * spb (the padded chunk length)");
+  if (clip == 0) return 0;
+  MAGI_CHECK(dst && src, "NULL pointer");
+  MAGI_CHECK(row_elems > 0 && row_elems % 8 == 0 && dst_token_stride % 8 == 0 && src_token_stride % 8 == 0,
+             "row_elems and strides must be multiples of 8 elements");
+  MAGI_CHECK(((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0,
+             "pointers must be 16-byte aligned");
+  int grid = 1;
+  if (int rc = grid_for(dn * clip * (row_elems / 8), 256, &grid)) return rc;
+  MAGI_CUDA(magi::cso_unshuffle_launch(dst, dst_token_stride, src, src_token_stride, dn, spb, clip,
+                                       (int)(row_elems / 8), grid, stream));
+  g_launches++;
+  return 0;
+}
+
 }  // extern "C"

@@ -301,6 +301,31 @@ __global__ void __launch_bounds__(256) ulysses_relayout_kernel(__nv_bfloat16* __
   }
 }
 
+// CSO receive side: dst[d * clip + t, :] = src[((t / spb) * dn + d) * spb + t % spb, :] for t < clip, i.e.
+// "(cp dn spb) -> dn (cp spb)" followed by dropping every chunk's zero padding (dit_module.py:1215-1224).
+__global__ void __launch_bounds__(256) cso_unshuffle_kernel(__nv_bfloat16* __restrict__ dst, int64_t dst_stride,
+                                                            const __nv_bfloat16* __restrict__ src, int64_t src_stride,
+                                                            int dn, int64_t spb, int64_t clip, int row_vecs) {
+  const int64_t total = static_cast<int64_t>(dn) * clip * row_vecs;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / row_vecs;
+    const int c8 = static_cast<int>(i - r * row_vecs);
+    const int64_t d = r / clip, t = r - d * clip;
+    const int64_t c = t / spb, s = t - c * spb;
+    const uint4 v = ld_stream(src + ((c * dn + d) * spb + s) * src_stride + c8 * 8);
+    *reinterpret_cast<uint4*>(dst + r * dst_stride + c8 * 8) = v;
+  }
+}
+
+cudaError_t cso_unshuffle_launch(void* dst, int64_t dst_stride, const void* src, int64_t src_stride, int dn,
+                                 int64_t spb, int64_t clip, int row_vecs, int grid, cudaStream_t stream) {
+  cso_unshuffle_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(dst), dst_stride,
+                                                 reinterpret_cast<const __nv_bfloat16*>(src), src_stride, dn, spb,
+                                                 clip, row_vecs);
+  return cudaGetLastError();
+}
+
 cudaError_t prologue_launch(const PrologueParams& p, bool ln_bf16, int grid, cudaStream_t stream) {
   if (ln_bf16) prologue_kernel<true><<<grid, 256, 0, stream>>>(p);
   else prologue_kernel<false><<<grid, 256, 0, stream>>>(p);

@@ -29,5 +29,7 @@ cudaError_t lse_merge_launch(void* out_a, float* lse_a, const void* out_b, const
                              int64_t a_ts, int64_t a_hs, int64_t b_ts, int64_t b_hs, int grid, cudaStream_t stream);
 cudaError_t ulysses_relayout_launch(void* dst, const void* src, int64_t seq, int hn, int head_vecs, int cp, int rep,
                                     int mode, int dst_hn, int dst_off, int grid, cudaStream_t stream);
+cudaError_t cso_unshuffle_launch(void* dst, int64_t dst_stride, const void* src, int64_t src_stride, int dn,
+                                 int64_t spb, int64_t clip, int row_vecs, int grid, cudaStream_t stream);
 
 }  // namespace magi

@@ -375,6 +375,29 @@ def kv_cache_append(cache: torch.Tensor, kv: torch.Tensor, row_offset: int, rows
                                                    row_offset, rows, row_elems, _stream()), "magi_kv_cache_append")
 
 
+def cso_unshuffle(recv: torch.Tensor, cp: int, dn: int, clip: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """"(cp dn spb) hn nhd -> dn (cp spb) hn nhd"[:, :clip] flattened (dit_module.py:1215-1224) as one gather kernel;
+    `out` (dn * clip rows, any token stride) may be the KV-cache slot."""
+    if not recv.is_cuda or recv.dtype != torch.bfloat16 or recv.dim() != 3 or not recv.is_contiguous():
+        raise ValueError("recv must be a contiguous CUDA bfloat16 tensor (tokens, heads, head_elems)")
+    if recv.shape[0] % (cp * dn) != 0:
+        raise ValueError("recv rows must be divisible by cp * dn")
+    spb = recv.shape[0] // (cp * dn)
+    if clip > cp * spb:
+        raise ValueError("clip exceeds the padded chunk length")
+    if out is None:
+        out = torch.empty((dn * clip,) + tuple(recv.shape[1:]), dtype=recv.dtype, device=recv.device)
+    elif out.shape != (dn * clip,) + tuple(recv.shape[1:]) or out.dtype != recv.dtype or (
+            out.shape[0] > 0 and not out[0].is_contiguous()):
+        raise ValueError("out must be (dn * clip, heads, head_elems) bf16 with contiguous rows")
+    if out.shape[0] == 0:
+        return out
+    with torch.cuda.device(recv.device):
+        _lib.check(_lib.lib().magi_cso_unshuffle(out.data_ptr(), out.stride(0), recv.data_ptr(), recv.stride(0), cp, dn,
+                                                 spb, clip, recv[0].numel(), _stream()), "magi_cso_unshuffle")
+    return out
+
+
 def lse_merge(out_a: torch.Tensor, lse_a: torch.Tensor, out_b: torch.Tensor, lse_b: torch.Tensor) -> None:
     """In place: (out_a, lse_a) <- softmax-merge of two partial attention results over disjoint key sets."""
     _check_thd(out_a, "out_a")

@@ -330,6 +330,62 @@ def gen_cp(world, port, hq, hkv, tag):
     print(f"ulysses cp={world} fixture written ({tag})")
 
 
+# ------------------------------------------------------------------ scenario 4: cp_shuffle_overlap (CSO) on gloo
+def _cso_worker(rank, world, port, out_path):
+    dm = install_patches()
+    init_dist(rank, world, port)
+    import inference.infra.parallelism.context_parallel as cpm
+    mc, ec = make_configs(cp_size=world, cp_strategy="cp_shuffle_overlap", hq=4, hkv=2)
+    attn = build_attention(dm, mc, ec, seed=77)
+    H, W, frames = 3, 5, 3
+    clip = frames * H * W                 # 45: odd, so every chunk is padded by one row for cp = 2
+    dn, sp, bs = 3, 0, 1
+    S = dn * clip
+    g = torch.Generator().manual_seed(11)
+    hs_full = torch.randn(S, bs, mc.hidden_size, generator=g).to(torch.bfloat16)
+    y_index = [41, 50, 77]
+    kvs = torch.randn(sum(y_index), mc.hidden_size, generator=g).to(torch.bfloat16)
+    rope_full = rope_for(dm, dn * frames, H, W, dn * frames)
+    k_range = [[0, clip], [0, 2 * clip], [clip, 3 * clip]]
+    m_full = meta(dm, clip, sp, dn, bs, k_range, y_index)
+    cond_map = torch.arange(S).reshape(S, 1) // clip
+    cp_ = m_full.core_attn_params
+    ardf_meta = dict(clip_token_nums=clip, slice_point=sp, range_num=sp + dn, denoising_range_num=dn,
+                     q_range=cp_.q_range, k_range=cp_.k_range, max_seqlen_q=clip, max_seqlen_k=cp_.max_seqlen_k)
+    (x, cmap, rope, pad, split, core_p, cross) = cpm.cp_pre_process(
+        world, "cp_shuffle_overlap", hs_full, cond_map, rope_full, None, ardf_meta, cp_, m_full.cross_attn_params)
+    from inference.common import ModelMetaArgs
+    m = ModelMetaArgs(H=0, W=0, cp_pad_size=pad, cp_split_sizes=split, slice_point=sp, denoising_range_num=dn,
+                      range_num=sp + dn, extract_prefix_video_feature=False, fwd_extra_1st_chunk=False,
+                      distill_nearly_clean_chunk=False, clip_token_nums=clip, enable_cuda_graph=False,
+                      core_attn_params=core_p, cross_attn_params=cross)
+    with torch.no_grad():
+        core, xattn = attn(x, kvs, None, rope, m)
+        gathered = cpm.cp_post_process(world, "cp_shuffle_overlap", core.float().contiguous(), m)
+    fx = {
+        "split_sizes": np.array(split), "pad": np.array(pad), "x_local": pk(x), "rope_local": pk(rope),
+        "cond_local": pk(cmap), "core.q_range": pk(core_p.q_range), "core.k_range": pk(core_p.k_range),
+        "core.max_seqlen_q": np.array(core_p.max_seqlen_q),
+        "cross.q_ranges": pk(cross.q_ranges), "cross.kv_ranges": pk(cross.kv_ranges),
+        "cross.max_seqlen_q": np.array(cross.max_seqlen_q),
+        "core_attn_out": pk(core), "xattn_out": pk(xattn), "gathered": pk(gathered.to(torch.bfloat16)),
+    }
+    if rank == 0:
+        fx.update(state_to_np(attn))
+        fx.update({"hidden_states": pk(hs_full), "key_value_states": pk(kvs), "rope": pk(rope_full),
+                   "k_range": np.array(k_range, dtype=np.int32), "y_index": np.array(y_index), "clip": np.array(clip),
+                   "heads": np.array([4, 2])})
+    np.savez_compressed(out_path.format(rank=rank), **fx)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def gen_cso(world, port):
+    path = os.path.join(OUT, f"cso_cp{world}_rank{{rank}}.npz")
+    mp.spawn(_cso_worker, args=(world, port, path), nprocs=world, join=True)
+    print(f"cso cp={world} fixture written")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -339,5 +395,7 @@ if __name__ == "__main__":
         gen_cp(2, 29551, 4, 2, "cp2")
     if which in ("all", "cp4"):
         gen_cp(4, 29561, 8, 2, "cp4")   # cp > Hkv: exercises KV-head replication (context_parallel.py:393-394)
+    if which in ("all", "cso"):
+        gen_cso(2, 29571)
     if which in ("all", "single"):
         gen_single_rank()

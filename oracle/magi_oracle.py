@@ -352,6 +352,92 @@ def ulysses_output_split(per_rank: List[np.ndarray], split_sizes: Sequence[int])
     return outs
 
 
+# ----------------------------------------------------------------------------------------------- CSO (cp_shuffle_overlap)
+def cso_pad_and_split(seq_len: int, cp_shuffle_num: int, cp_size: int) -> Tuple[int, List[int]]:
+    """cp_shuffle_overlap_process Part1, context_parallel.py:271-275."""
+    assert seq_len % cp_shuffle_num == 0
+    chunk = seq_len // cp_shuffle_num
+    pad = 0 if chunk % cp_size == 0 else (cp_size - chunk % cp_size) * cp_shuffle_num
+    return pad, [(seq_len + pad) // cp_size] * cp_size
+
+
+def cso_scatter(x: np.ndarray, split_sizes: Sequence[int], cp_shuffle_num: int, cp_pad_size: int, rank: int):
+    """scatter_to_context_parallel_region with cp_shuffle_num > 1, context_parallel.py:40-48: every chunk is
+    zero-padded and split on its own; a rank keeps the same slice of every chunk."""
+    pad = cp_pad_size // cp_shuffle_num
+    sizes = [s // cp_shuffle_num for s in split_sizes]
+    off = sum(sizes[:rank])
+    outs = []
+    for c in np.split(x, cp_shuffle_num, axis=0):
+        c = np.concatenate([c, np.zeros((pad,) + c.shape[1:], dtype=c.dtype)], axis=0)
+        outs.append(c[off:off + sizes[rank]])
+    return np.concatenate(outs, axis=0)
+
+
+def cso_gather(per_rank: List[np.ndarray], cp_shuffle_num: int, cp_pad_size: int) -> np.ndarray:
+    """gather_from_context_parallel_region with cp_shuffle_num > 1, context_parallel.py:74-84."""
+    pad = cp_pad_size // cp_shuffle_num
+    chunks = [np.split(o, cp_shuffle_num, axis=0) for o in per_rank]
+    outs = []
+    for i in range(cp_shuffle_num):
+        c = np.concatenate([ch[i] for ch in chunks], axis=0)
+        outs.append(c[:c.shape[0] - pad])
+    return np.concatenate(outs, axis=0)
+
+
+def cso_update_cross_attn_qkv_range(cu_seqlens_q, cu_seqlens_k, batch_size: int, split_sizes: Sequence[int],
+                                    cp_rank: int, cp_shuffle_num: int, cp_pad_size: int):
+    """cp_update_cross_attn_qkv_range with cp_shuffle_num > 1, context_parallel.py:134-224."""
+    sizes = np.asarray([s // cp_shuffle_num for s in split_sizes], dtype=np.int64)
+    bounds = np.concatenate([[0], sizes.cumsum()])
+    total = int(bounds[-1])
+    cu_q = np.asarray(cu_seqlens_q, dtype=np.int64)
+    cu_q = cu_q + np.arange(cu_q.shape[0]) * (cp_pad_size // cp_shuffle_num)      # :164-167
+    cu_k = np.asarray(cu_seqlens_k, dtype=np.int64)
+    qs, qe = cu_q[:-1], cu_q[1:]
+    xq, xk = [], []
+    for i in range(batch_size):
+        iq, ik = [], []
+        for j in range(cp_shuffle_num):
+            b = bounds + (i * cp_shuffle_num + j) * total
+            st, en = np.maximum(b[cp_rank], qs), np.minimum(b[cp_rank + 1], qe)
+            m = st < en
+            part = np.stack([st[m], en[m]], axis=1)
+            iq.append(part - part[:, 0].min())
+            ik.append(np.stack([cu_k[:-1][m], cu_k[1:][m]], axis=1))
+        ioffs = np.concatenate([[0], np.cumsum([r[-1, -1] for r in iq])[:-1]])
+        xq.append(np.concatenate([r + int(o) for r, o in zip(iq, ioffs)], axis=0))
+        xk.append(np.concatenate(ik, axis=0))
+    offs = np.concatenate([[0], np.cumsum([r[-1, -1] for r in xq])[:-1]])
+    q_ranges = np.concatenate([r + int(o) for r, o in zip(xq, offs)], axis=0).astype(np.int32)
+    k_ranges = np.concatenate(xk, axis=0).astype(np.int32)
+    return dict(q_ranges=q_ranges, kv_ranges=k_ranges, max_seqlen_q=int(split_sizes[cp_rank]))
+
+
+def cso_core_attention(q_per_rank: List[np.ndarray], kv_per_rank: List[np.ndarray], cp_shuffle_num: int,
+                       clip_token_nums: int, np_k_range: np.ndarray, cache_prefix: Optional[np.ndarray] = None):
+    """The cp_shuffle_overlap branch of FullyParallelAttention.forward as index math (dit_module.py:1207-1242 with
+    cso_communication / CSOHelper, context_parallel.py:603-664), all ranks simulated in one process, heads kept
+    together (the head all-to-alls only move data).
+    q_per_rank[r] (dn * spb, Hq, 128), kv_per_rank[r] (dn * spb, Hkv, 256): rank r's slice of every padded chunk.
+    The key/value sequence is re-assembled chunk by chunk and un-padded (dit_module.py:1215-1224), optionally
+    preceded by the KV-cache prefix; the padded query chunk i (all ranks' slices, rank-major) attends k_range[i]
+    (full_attention, dit_module.py:1068-1096). Returns per-rank outputs (dn * spb, Hq, 128)."""
+    cp, dn = len(q_per_rank), cp_shuffle_num
+    spb = q_per_rank[0].shape[0] // dn
+    kv = np.concatenate([np.concatenate([kv_per_rank[r][d * spb:(d + 1) * spb] for r in range(cp)], axis=0)
+                         [:clip_token_nums] for d in range(dn)], axis=0)
+    if cache_prefix is not None:
+        kv = np.concatenate([cache_prefix, kv], axis=0)
+    outs = [np.zeros_like(q) for q in q_per_rank]
+    for d in range(dn):
+        q = np.concatenate([q_per_rank[r][d * spb:(d + 1) * spb] for r in range(cp)], axis=0)
+        o, _ = attn_ranges(q, kv[..., :128], kv[..., 128:], np.array([[0, q.shape[0]]]), np.asarray(np_k_range)[d:d + 1])
+        for r in range(cp):
+            outs[r][d * spb:(d + 1) * spb] = o[r * spb:(r + 1) * spb]
+    return outs
+
+
 # ----------------------------------------------------------------------------------------------- RoPE table
 def rope_table(T_total: int, H: int, W: int, bands: Optional[np.ndarray] = None, keep_last_T: Optional[int] = None):
     """LearnableRotaryEmbeddingCat.get_embed as used at dit_model.py:163-166 (in_pixels=False, dim=128):

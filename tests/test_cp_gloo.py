@@ -131,6 +131,91 @@ def _ulysses_worker(rank, world, port, tag, overlap, errq):
             dist.destroy_process_group()
 
 
+def _cso_worker(rank, world, port, errq):
+    try:
+        _setup(rank, world, port)
+        import magi_oracle as O
+        from golden_io import Golden
+        from magi_b200 import context_parallel as cpm
+        from magi_b200.common import PackedCoreAttnParams, PackedCrossAttnParams
+        g0 = Golden(f"cso_cp{world}_rank0.npz")
+        gr = Golden(f"cso_cp{world}_rank{rank}.npz")
+        Hq, Hkv = [int(x) for x in g0["heads"]]
+        clip, dn = int(g0["clip"]), 3
+        hs, rope = g0.torch("hidden_states"), g0.torch("rope")
+        S = hs.shape[0]
+        i32 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.int32))
+        full = O.cross_attn_params(clip, dn, 1, g0["y_index"])
+        cross = PackedCrossAttnParams(q_ranges=i32(full["q_ranges"]), kv_ranges=i32(full["kv_ranges"]),
+                                      cu_seqlens_q=i32(full["cu_seqlens_q"]), cu_seqlens_kv=i32(full["cu_seqlens_kv"]),
+                                      max_seqlen_q=clip, max_seqlen_kv=800)
+        q_range, k_range = O.core_q_ranges(clip, dn, 1), g0.raw("k_range")
+        core = PackedCoreAttnParams(q_range=i32(q_range), k_range=i32(k_range), np_q_range=q_range, np_k_range=k_range,
+                                    max_seqlen_q=clip, max_seqlen_k=3 * clip)
+        ardf = dict(clip_token_nums=clip, slice_point=0, range_num=dn, denoising_range_num=dn, q_range=core.q_range,
+                    k_range=core.k_range, max_seqlen_q=clip, max_seqlen_k=core.max_seqlen_k)
+        cond_map = torch.arange(S).reshape(S, 1) // clip
+        x, cmap, rope_l, pad, split, core_l, cross_l = cpm.cp_pre_process(world, "cp_shuffle_overlap", hs, cond_map,
+                                                                          rope, None, ardf, core, cross)
+        # (1) pre-process == the reference's cp_shuffle_overlap_process on the same inputs
+        assert pad == int(gr["pad"]) and split == [int(v) for v in gr["split_sizes"]]
+        assert torch.equal(x, gr.torch("x_local")) and torch.equal(rope_l, gr.torch("rope_local"))
+        assert torch.equal(cmap, gr.torch("cond_local"))
+        assert np.array_equal(core_l.q_range.numpy(), gr.raw("core.q_range"))
+        assert np.array_equal(core_l.np_q_range, gr.raw("core.q_range"))
+        assert np.array_equal(core_l.k_range.numpy(), gr.raw("core.k_range"))
+        assert core_l.max_seqlen_q == int(gr["core.max_seqlen_q"])
+        assert np.array_equal(cross_l.q_ranges.numpy(), gr.raw("cross.q_ranges"))
+        assert np.array_equal(cross_l.kv_ranges.numpy(), gr.raw("cross.kv_ranges"))
+        assert cross_l.max_seqlen_q == int(gr["cross.max_seqlen_q"])
+        # (2) the CSO pipeline (cso_communication + CSOHelper) with oracle compute == the reference's per-rank output
+        w = lambda n: g0[f"w.{n}"]
+        mixed = O.bf16_round(O.layer_norm(t2n(x), w("linear_qkv.layer_norm.weight"), w("linear_qkv.layer_norm.bias"),
+                                          1e-6, zero_centered_gamma=False))
+        lin = {n: O.bf16_round(mixed @ w(f"linear_qkv.{n}.weight").T) for n in ("q", "k", "v")}
+        sin, cos = t2n(rope_l)[:, :48], t2n(rope_l)[:, 48:]
+        q = n2t(O.get_q_or_k(lin["q"], Hq, w("q_layernorm.weight"), w("q_layernorm.bias"), sin, cos))
+        kv = n2t(O.get_kv(lin["k"], lin["v"], Hkv, w("k_layernorm.weight"), w("k_layernorm.bias"), sin, cos))
+        kv_recv, h_kv = cpm.cso_communication(kv, world, split, "kv", relayout=relayout_in)
+        helper = cpm.CSOHelper(dn, world, split)
+        query, h_q = helper.split_query_for_overlap(q, relayout=relayout_in)
+        assert len(query) == dn
+        h_kv.wait()
+        spb = split[rank] // dn
+        idx = torch.from_numpy(cpm.cso_unshuffle_rows(world, dn, spb, clip))
+        kv_full = kv_recv.index_select(0, idx)
+        assert tuple(kv_full.shape) == (dn * clip, Hkv // world, 256)
+        h_q.wait()
+        calls = []
+
+        def fattn(qi, k, v, i):
+            calls.append(i)
+            o, _ = O.attn_ranges(t2n(qi), t2n(k), t2n(v), np.array([[0, qi.shape[0]]]), core_l.np_k_range[i:i + 1])
+            return n2t(o)
+
+        outs, h = helper.overlap(fattn, query, kv_full[..., :128], kv_full[..., 128:])
+        h.wait()
+        assert calls == list(range(dn)) and len(outs) == dn
+        result = torch.empty(split[rank], Hq, 128, dtype=torch.bfloat16)
+        for d, o in enumerate(outs):
+            relayout_out(o, world, result[d * spb:(d + 1) * spb], Hq // world, 0)
+        core_out = result.view(split[rank], 1, Hq * 128)
+        ref = gr["core_attn_out"]
+        err = np.abs(t2n(core_out) - ref).max()
+        rel = np.linalg.norm(t2n(core_out) - ref) / np.linalg.norm(ref)
+        assert err < 6e-2 and rel < 1.5e-2, (err, rel)
+        # (3) post-process gather (un-shuffle + un-pad) == reference's
+        meta = type("M", (), {"cp_split_sizes": split, "denoising_range_num": dn, "cp_pad_size": pad})()
+        gathered = cpm.cp_post_process(world, "cp_shuffle_overlap", gr.torch("core_attn_out").float(), meta)
+        assert torch.equal(gathered.to(torch.bfloat16), g0.torch("gathered"))
+        dist.barrier()
+    except Exception:
+        errq.put(f"rank {rank}:\n{traceback.format_exc()}")
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
 def _ring_worker(rank, world, port, errq):
     try:
         _setup(rank, world, port)
@@ -210,6 +295,19 @@ def _spawn(fn, world, args):
 @pytest.mark.parametrize("tag,world,overlap,port", [("cp2", 2, 1, 29611), ("cp2", 2, 2, 29612), ("cp4", 4, 1, 29613)])
 def test_ulysses_pipeline_matches_reference(tag, world, overlap, port):
     _spawn(_ulysses_worker, world, (port, tag, overlap))
+
+
+def test_cso_pipeline_matches_reference():
+    _spawn(_cso_worker, 2, (29631,))
+
+
+def test_cso_unshuffle_rows_is_the_reference_rearrange():
+    """"(cp dn sqb) -> dn (cp sqb)"[:, :clip] flattened (dit_module.py:1215-1224)."""
+    from magi_b200.context_parallel import cso_unshuffle_rows
+    cp, dn, spb, clip = 4, 3, 5, 18
+    src = torch.arange(cp * dn * spb)
+    exp = src.view(cp, dn, spb).permute(1, 0, 2).reshape(dn, cp * spb)[:, :clip].flatten()
+    assert np.array_equal(cso_unshuffle_rows(cp, dn, spb, clip), exp.numpy())
 
 
 @pytest.mark.parametrize("world,port", [(2, 29621), (3, 29622)])

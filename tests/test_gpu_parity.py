@@ -299,6 +299,34 @@ def _build_module(g, cp_strategy="none"):
     return attn.cuda().eval()
 
 
+def test_cso_unshuffle_and_full_attention(F):
+    """CSO pieces with the real kernels: the receive-side gather "(cp dn spb) -> dn (cp spb)"[:, :clip]
+    (dit_module.py:1215-1224) is bit exact and can land in the KV-cache slot; full_attention on the padded query
+    chunk (dit_module.py:1068-1096) matches the oracle's cso_core_attention."""
+    cp, dn, clip, Hq, Hkv = 4, 3, 203, 4, 2
+    spb = -(-clip // cp)
+    recv = bf(rnd((cp * dn * spb, Hkv, 256), 41))
+    exp = recv.view(cp, dn, spb, Hkv, 256).permute(1, 0, 2, 3, 4).reshape(dn, cp * spb, Hkv, 256)[:, :clip].flatten(0, 1)
+    got = F.cso_unshuffle(recv, cp, dn, clip)
+    assert torch.equal(got, exp)
+    cache = torch.zeros(5 * clip, Hkv, 256, dtype=torch.bfloat16, device="cuda")
+    F.cso_unshuffle(recv, cp, dn, clip, out=cache[clip:clip + dn * clip])
+    assert torch.equal(cache[clip:clip + dn * clip], exp) and not cache[:clip].any() and not cache[(dn + 1) * clip:].any()
+    # per-rank slices of every padded chunk -> oracle (all ranks simulated) vs kernel (one launch per chunk)
+    qs = [rnd((dn * spb, Hq, 128), 50 + r) for r in range(cp)]
+    kvs = [rnd((dn * spb, Hkv, 256), 60 + r) for r in range(cp)]
+    k_range = np.array([[0, clip], [0, 2 * clip], [clip, 3 * clip]], dtype=np.int32)
+    ref = O.cso_core_attention(qs, kvs, dn, clip, k_range)
+    kv_full = np.concatenate([np.concatenate([kvs[r][d * spb:(d + 1) * spb] for r in range(cp)], 0)[:clip]
+                              for d in range(dn)], 0)
+    kv_dev = bf(kv_full)
+    for d in range(dn):
+        q = bf(np.concatenate([qs[r][d * spb:(d + 1) * spb] for r in range(cp)], 0))
+        out, _ = F.attn_ranges(q, kv_dev[..., :128], kv_dev[..., 128:], i32([[0, cp * spb]]), i32(k_range[d:d + 1]))
+        exp_o = np.concatenate([ref[r][d * spb:(d + 1) * spb] for r in range(cp)], 0)
+        check_attn(out, exp_o, f"cso chunk {d}")
+
+
 def test_full_attention_block_matches_reference_golden():
     """The drop-in FullyParallelAttention replays the reference's own forward sequence (steps A-E of
     oracle/gen_golden.py: KV-cache fill, fwd_extra_1st_chunk, update_kv_cache False/True, distill extra range,

@@ -2,10 +2,10 @@
 
     torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29700 tools/cp_check.py
 
-Every rank builds the same FullyParallelAttention weights and the same full-sequence inputs, runs the cp_ulysses and
+Every rank builds the same FullyParallelAttention weights and the same full-sequence inputs, runs the cp_ulysses, cp_shuffle_overlap and
 cp_ring_kv forwards on its shard through a KV-cache sequence (cache fill, window advance, update on/off, distill extra
 range), all-gathers the outputs and compares them with the single-GPU (cp_strategy="none") forward computed locally
-(oracle O3 of SURVEY.md section 8c). Ulysses must be bit-identical (same kernels, same per-head inputs); ring-KV is
+(oracle O3 of SURVEY.md section 8c). Ulysses and cp_shuffle_overlap must be bit-identical (same kernels, same per-head inputs); ring-KV is
 bounded by one bf16 rounding per merge step."""
 import os
 import sys
@@ -76,7 +76,7 @@ def main():
         (1, 3, [(0, 2), (1, 3), (3, 4)], [33, 90, 33], True, False, True),
     ]
     results = {}
-    for strategy in ("cp_ulysses", "cp_ring_kv"):
+    for strategy in ("cp_ulysses", "cp_shuffle_overlap", "cp_ring_kv"):
         kv_loc = max(1, Hkv // world)
         second = kv_loc if kv_loc > 1 else 3      # whole kv heads per group, or 3 q-head groups in the MQA case
         for overlap in ((1, second) if strategy == "cp_ulysses" else (1,)):
@@ -95,13 +95,18 @@ def main():
                 inf_ref.update_kv_cache = inf_cp.update_kv_cache = upd
                 ref_core, ref_x = ref_m(hs, kvs, inf_ref, rope, m_full)
                 cond = torch.zeros(S, 1, device=dev)
-                x, _, rope_l, pad, split, _, cross_l = cpm.cp_pre_process(world, strategy, hs, cond, rope, None, {},
-                                                                           m_full.core_attn_params,
-                                                                           m_full.cross_attn_params)
+                cp_ = m_full.core_attn_params
+                ardf = dict(denoising_range_num=dn, q_range=cp_.q_range, k_range=cp_.k_range, max_seqlen_q=clip,
+                            max_seqlen_k=cp_.max_seqlen_k)
+                x, _, rope_l, pad, split, core_l, cross_l = cpm.cp_pre_process(world, strategy, hs, cond, rope, None,
+                                                                                ardf, cp_, m_full.cross_attn_params)
                 m_cp = meta(sp, dn, kc, yi, extra, ncc, split=split, cross=cross_l)
+                if strategy == "cp_shuffle_overlap":   # padded q ranges, per-chunk shards (context_parallel.py:283-296)
+                    import dataclasses
+                    m_cp = dataclasses.replace(m_cp, cp_pad_size=pad, core_attn_params=core_l)
                 core, xo = cp_m(x, kvs, inf_cp, rope_l, m_cp)
-                core = cpm.gather_from_context_parallel_region(core.contiguous(), split)
-                xo = cpm.gather_from_context_parallel_region(xo.contiguous(), split)
+                core = cpm.cp_post_process(world, strategy, core.contiguous(), m_cp)
+                xo = cpm.cp_post_process(world, strategy, xo.contiguous(), m_cp)
                 worst["core"] = max(worst["core"], (core.float() - ref_core.float()).abs().max().item())
                 worst["xattn"] = max(worst["xattn"], (xo.float() - ref_x.float()).abs().max().item())
             results[f"{strategy}/overlap{overlap}"] = worst
@@ -110,7 +115,7 @@ def main():
     if rank == 0:
         ok = True
         for k, w in results.items():
-            bound = 0.0 if k.startswith("cp_ulysses") else 2.5e-2
+            bound = 2.5e-2 if k.startswith("cp_ring_kv") else 0.0
             good = w["core"] <= bound and w["xattn"] == 0.0
             ok &= good
             print(f"[cp_check N={world}] {k}: core max_abs {w['core']:.3e} (bound {bound}) xattn max_abs "
