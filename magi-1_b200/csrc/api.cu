@@ -225,6 +225,13 @@ int magi_qk_norm_rope_fwd(const magi_prologue_args* a, void* stream_) {
       MAGI_CHECK(a->num_heads_kv % cp == 0 || cp % a->num_heads_kv == 0, "num_heads_kv and cp are not compatible");
   }
   MAGI_CHECK((a->sin == nullptr) == (a->cos == nullptr), "sin and cos must both be given or both be NULL");
+  MAGI_CHECK(((reinterpret_cast<uintptr_t>(a->x_q) | reinterpret_cast<uintptr_t>(a->x_k) |
+               reinterpret_cast<uintptr_t>(a->x_v) | reinterpret_cast<uintptr_t>(a->q_out) |
+               reinterpret_cast<uintptr_t>(a->kv_out) | reinterpret_cast<uintptr_t>(a->cache) |
+               reinterpret_cast<uintptr_t>(a->sin) | reinterpret_cast<uintptr_t>(a->cos) |
+               reinterpret_cast<uintptr_t>(a->ln_q_w) | reinterpret_cast<uintptr_t>(a->ln_q_b) |
+               reinterpret_cast<uintptr_t>(a->ln_k_w) | reinterpret_cast<uintptr_t>(a->ln_k_b)) & 15) == 0,
+             "all pointers must be 16-byte aligned");
   if (a->rows == 0) return 0;
 
   magi::PrologueParams p;
@@ -244,9 +251,12 @@ int magi_qk_norm_rope_fwd(const magi_prologue_args* a, void* stream_) {
   p.cache_row_offset = a->cache_row_offset; p.cache_rows = a->cache_rows;
   p.head_perm_cp = cp;
 
-  int grid = 1;
-  if (int rc = grid_for(a->rows * 32, 256, &grid)) return rc;   // one warp per row, grid-stride
-  MAGI_CUDA(magi::prologue_launch(p, a->ln_dtype == 1, grid, stream));
+  int64_t units = 0;
+  magi::prologue_units(p, &units);
+  MAGI_CHECK(units < (int64_t)0x7fffffff, "too many rows for one prologue launch");
+  int sms = 0;
+  if (int rc = device_sm_count(&sms)) return rc;
+  MAGI_CUDA(magi::prologue_launch(p, a->ln_dtype == 1, sms, stream));
   g_launches++;
   return 0;
 }

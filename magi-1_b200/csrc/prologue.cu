@@ -52,169 +52,490 @@ __device__ __forceinline__ float half_warp_sum(float x) {
 }  // namespace
 
 #ifndef MAGI_PRO_UNROLL
-#define MAGI_PRO_UNROLL 4
+#define MAGI_PRO_UNROLL 3
 #endif
 #ifndef MAGI_PRO_BLOCKS
-#define MAGI_PRO_BLOCKS 3
+#define MAGI_PRO_BLOCKS 2
 #endif
 
-__device__ __forceinline__ uint2 ld_8(const void* p) {
-  uint2 r;
-  asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
-  return r;
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
 }
-__device__ __forceinline__ void unpack4(const uint2& u, float* v) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-  const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
-  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+// two bf16 in one 32-bit word -> packed (lo, hi) fp32 pair: one shift, one mask
+__device__ __forceinline__ uint64_t bf2_to_f2(uint32_t u) {
+  return pack_f2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
+__device__ __forceinline__ uint32_t f2_to_bf2(uint64_t v) {
+  float lo, hi;
+  unpack_f2(v, lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float quarter_warp_sum(float x) {   // over the 8 lanes that share one head vector
+  x += __shfl_xor_sync(0xffffffffu, x, 4);
+  x += __shfl_xor_sync(0xffffffffu, x, 2);
+  x += __shfl_xor_sync(0xffffffffu, x, 1);
+  return x;
+}
+// 8 consecutive parameters (fp32 or bf16) starting at element `off` -> 4 packed fp32 pairs
 template <bool kBf16>
-__device__ __forceinline__ void load4(const void* base, int off, float* v) {
+__device__ __forceinline__ void load_param8(const void* base, int off, uint64_t* v) {
   if constexpr (kBf16) {
-    unpack4(*reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + off), v);
+    const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + off);
+    v[0] = bf2_to_f2(u.x); v[1] = bf2_to_f2(u.y); v[2] = bf2_to_f2(u.z); v[3] = bf2_to_f2(u.w);
   } else {
-    const float4 f = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
-    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+    const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off + 4);
+    v[0] = pack_f2(a.x, a.y); v[1] = pack_f2(a.z, a.w); v[2] = pack_f2(b.x, b.y); v[3] = pack_f2(b.z, b.w);
   }
 }
 
-// One warp owns one row (token): it streams that row's q heads, then k heads, then v heads, two heads per step (one
-// per half-warp) and MAGI_PRO_UNROLL steps in flight. Inside a half-warp, lane s < 12 holds elements [4s, 4s+4) and
-// [48+4s, 48+4s+4) of the 128-element head vector - the two RoPE partners of the non-interleaved rotation sit in the
-// same lane, so the rotation needs no shuffles - and lanes 12..15 hold the pass-through dims [96, 128).
-// sin/cos of the row and the LayerNorm affine of the current tensor stay in registers for the whole row.
-template <bool kLnBf16>
+// Work decomposition. A unit is (tensor, row, group of 4 * kUnroll heads); units are numbered tensor-major (all q
+// units, then k, then v) and dealt round-robin to the resident warps, so every warp streams through q, then k, then v
+// and reloads the LayerNorm affine (kept in registers as packed fp32 pairs) at most twice.
+// Inside a unit, 8 lanes own one 128-element head vector (4 heads per warp step, kUnroll steps = 8 * kUnroll
+// independent 16-byte loads per lane pair in flight): lane s < 6 holds elements [8s, 8s+8) and [48+8s, 48+8s+8) -
+// the two partners of the non-interleaved RoPE rotation sit in the same lane, so the rotation needs no shuffles -
+// and lanes 6, 7 hold the pass-through dims [96, 128). Every load/store instruction moves whole 32-byte sectors.
+// All fp32 arithmetic is packed (add/mul/fma.f32x2): the previous kernel was issue-bound (ncu: 65 % issue-active at
+// 3.7 TB/s, two thirds of its instructions integer address math), not bandwidth-bound.
+template <bool kLnBf16, bool kPerm>
 __global__ void __launch_bounds__(256, MAGI_PRO_BLOCKS) prologue_kernel(const PrologueParams p) {
   constexpr int kUnroll = MAGI_PRO_UNROLL;
+  constexpr int kHeadsPerUnit = 4 * kUnroll;
   const int lane = threadIdx.x & 31;
-  const int sub = lane & 15;
-  const int half = lane >> 4;  // which of the two heads of a step
-  const int off0 = sub < 12 ? 4 * sub : 96 + 8 * (sub - 12);
-  const int off1 = sub < 12 ? 48 + 4 * sub : off0 + 4;
-  const int64_t warps_total = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  const int64_t warp_id = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int cp = p.head_perm_cp > 1 ? p.head_perm_cp : 1;
-  const bool rope = p.sin != nullptr && sub < 12;
+  const int s = lane & 7;
+  const int j = lane >> 3;
+  const int e0 = s < 6 ? 8 * s : 96 + 8 * (s - 6);        // lane 6: [96,104)+[112,120), lane 7: [104,112)+[120,128)
+  const int e1 = s < 6 ? 48 + 8 * s : 112 + 8 * (s - 6);
+  const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const bool rot = p.sin != nullptr && s < 6;
+  const uint32_t rows = static_cast<uint32_t>(p.rows);
+  const uint32_t upr_q = (p.Hq + kHeadsPerUnit - 1) / kHeadsPerUnit;
+  const uint32_t upr_kv = (p.Hkv + kHeadsPerUnit - 1) / kHeadsPerUnit;
+  const uint32_t n_q = p.x_q != nullptr ? rows * upr_q : 0u;
+  const uint32_t n_k = p.x_k != nullptr ? rows * upr_kv : 0u;
+  const uint32_t n_v = p.x_v != nullptr ? rows * upr_kv : 0u;
+  const uint32_t total = n_q + n_k + n_v;
 
-  for (int64_t r = warp_id; r < p.rows; r += warps_total) {
-    float cs[4], sn[4];
-    if (rope) {
-      const int64_t trow = r / p.batch;
-      const float4 c = *reinterpret_cast<const float4*>(p.cos + trow * 48 + 4 * sub);
-      const float4 s4 = *reinterpret_cast<const float4*>(p.sin + trow * 48 + 4 * sub);
-      cs[0] = c.x; cs[1] = c.y; cs[2] = c.z; cs[3] = c.w;
-      sn[0] = s4.x; sn[1] = s4.y; sn[2] = s4.z; sn[3] = s4.w;
-    } else {
+  int cur_type = -1;
+  uint64_t w2[8], b2[8];
+  const uint64_t one2 = pack_f2(1.f, 1.f);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { cs[i] = 1.f; sn[i] = 0.f; }
-    }
+  for (int i = 0; i < 8; ++i) { w2[i] = one2; b2[i] = 0; }
 
 #pragma unroll 1
-    for (int type = 0; type < 3; ++type) {  // 0 = q, 1 = k, 2 = v
-      const void* xbase = type == 0 ? p.x_q : type == 1 ? p.x_k : p.x_v;
-      if (xbase == nullptr) continue;
-      const int H = type == 0 ? p.Hq : p.Hkv;
-      const int64_t rstride = type == 0 ? p.xq_row_stride : type == 1 ? p.xk_row_stride : p.xv_row_stride;
-      const int64_t hstride = type == 0 ? p.xq_head_stride : type == 1 ? p.xk_head_stride : p.xv_head_stride;
-      const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(xbase) + r * rstride;
-      float wf[8], bf[8];
+  for (uint32_t unit = warp_id; unit < total; unit += warps_total) {
+    const int type = unit < n_q ? 0 : (unit < n_q + n_k ? 1 : 2);   // 0 = q, 1 = k, 2 = v
+    const uint32_t local = unit - (type == 0 ? 0u : type == 1 ? n_q : n_q + n_k);
+    const uint32_t upr = type == 0 ? upr_q : upr_kv;
+    const uint32_t r = upr == 1 ? local : local / upr;
+    const int h_first = static_cast<int>(local - r * upr) * kHeadsPerUnit + j;
+    const int H = type == 0 ? p.Hq : p.Hkv;
+
+    if (type != cur_type) {
+      cur_type = type;
       if (type != 2) {
         const void* w = type == 0 ? p.ln_q_w : p.ln_k_w;
         const void* b = type == 0 ? p.ln_q_b : p.ln_k_b;
-        load4<kLnBf16>(w, off0, wf); load4<kLnBf16>(w, off1, wf + 4);
-        load4<kLnBf16>(b, off0, bf); load4<kLnBf16>(b, off1, bf + 4);
+        load_param8<kLnBf16>(w, e0, w2); load_param8<kLnBf16>(w, e1, w2 + 4);
+        load_param8<kLnBf16>(b, e0, b2); load_param8<kLnBf16>(b, e1, b2 + 4);
         if (p.zero_centered_gamma != 0) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
+            w2[i] = fadd2(w2[i], one2);
             // bf16 parameters: the reference computes `self.weight + 1` in bf16, i.e. rounds the sum
-            wf[i] = kLnBf16 ? __bfloat162float(__float2bfloat16_rn(wf[i] + 1.0f)) : wf[i] + 1.0f;
+            if constexpr (kLnBf16) w2[i] = bf2_to_f2(f2_to_bf2(w2[i]));
+          }
+        }
+      }
+    }
+
+    const int64_t rstride = type == 0 ? p.xq_row_stride : type == 1 ? p.xk_row_stride : p.xv_row_stride;
+    const int64_t hstride = type == 0 ? p.xq_head_stride : type == 1 ? p.xk_head_stride : p.xv_head_stride;
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(type == 0 ? p.x_q : type == 1 ? p.x_k : p.x_v) +
+                               r * rstride + h_first * hstride;
+    uint4 ra[kUnroll], rb[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      ra[u] = make_uint4(0, 0, 0, 0);
+      rb[u] = make_uint4(0, 0, 0, 0);
+      if (h_first + 4 * u < H) {
+        ra[u] = ld_stream(src + 4 * u * hstride + e0);
+        rb[u] = ld_stream(src + 4 * u * hstride + e1);
+      }
+    }
+
+    uint64_t cs2[4], sn2[4], nsn2[4];
+    if (type != 2 && rot) {
+      const uint32_t trow = p.batch == 1 ? r : r / static_cast<uint32_t>(p.batch);
+      const float4* c = reinterpret_cast<const float4*>(p.cos + static_cast<int64_t>(trow) * 48 + 8 * s);
+      const float4* sp = reinterpret_cast<const float4*>(p.sin + static_cast<int64_t>(trow) * 48 + 8 * s);
+      const float4 c0 = c[0], c1 = c[1], s0 = sp[0], s1 = sp[1];
+      cs2[0] = pack_f2(c0.x, c0.y); cs2[1] = pack_f2(c0.z, c0.w); cs2[2] = pack_f2(c1.x, c1.y); cs2[3] = pack_f2(c1.z, c1.w);
+      sn2[0] = pack_f2(s0.x, s0.y); sn2[1] = pack_f2(s0.z, s0.w); sn2[2] = pack_f2(s1.x, s1.y); sn2[3] = pack_f2(s1.z, s1.w);
+      nsn2[0] = pack_f2(-s0.x, -s0.y); nsn2[1] = pack_f2(-s0.z, -s0.w);
+      nsn2[2] = pack_f2(-s1.x, -s1.y); nsn2[3] = pack_f2(-s1.z, -s1.w);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { cs2[i] = one2; sn2[i] = 0; nsn2[i] = 0; }
+    }
+
+    // destination bases of this (row, tensor): q_out, or the K / V half of the packed kv row (and of the cache row)
+    __nv_bfloat16* out_base = type == 0 ? reinterpret_cast<__nv_bfloat16*>(p.q_out)
+                                        : reinterpret_cast<__nv_bfloat16*>(p.kv_out) + (type == 2 ? 128 : 0);
+    const int64_t out_tstride = type == 0 ? p.q_out_token_stride : p.kv_out_token_stride;
+    const int64_t out_hstride = type == 0 ? p.q_out_head_stride : p.kv_out_head_stride;
+    __nv_bfloat16* cache_row = nullptr;
+    if constexpr (!kPerm) {
+      if (type != 0 && p.cache != nullptr && static_cast<int64_t>(r) < p.cache_rows)
+        cache_row = reinterpret_cast<__nv_bfloat16*>(p.cache) + (p.cache_row_offset + r) * p.cache_token_stride +
+                    (type == 2 ? 128 : 0);
+    }
+
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int h = h_first + 4 * u;
+      if (h - j >= H) break;            // warp-uniform: the whole step is past the last head
+      uint4 pa = ra[u], pb = rb[u];
+      if (type != 2) {
+        uint64_t v[8];
+        v[0] = bf2_to_f2(pa.x); v[1] = bf2_to_f2(pa.y); v[2] = bf2_to_f2(pa.z); v[3] = bf2_to_f2(pa.w);
+        v[4] = bf2_to_f2(pb.x); v[5] = bf2_to_f2(pb.y); v[6] = bf2_to_f2(pb.z); v[7] = bf2_to_f2(pb.w);
+        // ---- LayerNorm over 128 in fp32 (two-pass, biased variance)
+        float lo, hi;
+        unpack_f2(fadd2(fadd2(fadd2(v[0], v[1]), fadd2(v[2], v[3])), fadd2(fadd2(v[4], v[5]), fadd2(v[6], v[7]))), lo, hi);
+        const float mean = quarter_warp_sum(lo + hi) * (1.0f / 128.0f);
+        const uint64_t mean2 = pack_f2(mean, mean);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = fsub2(v[i], mean2);
+        uint64_t sq_a = fmul2(v[0], v[0]), sq_b = fmul2(v[1], v[1]);
+#pragma unroll
+        for (int i = 2; i < 8; i += 2) { sq_a = ffma2(v[i], v[i], sq_a); sq_b = ffma2(v[i + 1], v[i + 1], sq_b); }
+        unpack_f2(fadd2(sq_a, sq_b), lo, hi);
+        const float var = quarter_warp_sum(lo + hi) * (1.0f / 128.0f);
+        const float rstd = rsqrtf(var + p.eps);   // MUFU.RSQ (2 ulp in fp32: invisible after the bf16 rounding)
+        const uint64_t rstd2 = pack_f2(rstd, rstd);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = ffma2(fmul2(v[i], rstd2), w2[i], b2[i]);
+        // ---- NeoX RoPE: (x1, x2) -> (x1 cos - x2 sin, x2 cos + x1 sin); identity on lanes 6, 7 (cos 1, sin 0)
+        if (rot) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint64_t x1 = v[i], x2 = v[4 + i];
+            v[i] = ffma2(x1, cs2[i], fmul2(x2, nsn2[i]));
+            v[4 + i] = ffma2(x2, cs2[i], fmul2(x1, sn2[i]));
+          }
+        }
+        pa = make_uint4(f2_to_bf2(v[0]), f2_to_bf2(v[1]), f2_to_bf2(v[2]), f2_to_bf2(v[3]));
+        pb = make_uint4(f2_to_bf2(v[4]), f2_to_bf2(v[5]), f2_to_bf2(v[6]), f2_to_bf2(v[7]));
+      }
+      if (h >= H) continue;
+
+      // ---- stores: attention (or all-to-all send) layout, plus the fused KV-cache append
+      auto store = [&](__nv_bfloat16* dst) {
+        *reinterpret_cast<uint4*>(dst + e0) = pa;
+        *reinterpret_cast<uint4*>(dst + e1) = pb;
+      };
+      if constexpr (!kPerm) {
+        store(out_base + r * out_tstride + h * out_hstride);
+        if (cache_row != nullptr) store(cache_row + h * p.cache_head_stride);
+      } else {
+        const int cp = p.head_perm_cp;
+        if (type == 0) {
+          const int hn = p.Hq / cp;
+          store(out_base + (static_cast<int64_t>(h / hn) * rows + r) * out_tstride +
+                static_cast<int64_t>(h % hn) * out_hstride);
+        } else if (cp > p.Hkv) {
+          // fewer kv heads than ranks: replicate (repeat_interleave, context_parallel.py:393-394)
+          const int rep = cp / p.Hkv;
+          for (int c = h * rep; c < (h + 1) * rep; ++c)
+            store(out_base + (static_cast<int64_t>(c) * rows + r) * out_tstride);
+        } else {
+          const int hn = p.Hkv / cp;
+          store(out_base + (static_cast<int64_t>(h / hn) * rows + r) * out_tstride +
+                static_cast<int64_t>(h % hn) * out_hstride);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Ring version (default): the same arithmetic, but the loads are taken off the compute warps. One producer warp per
+// CTA streams "super-units" (kGroup consecutive work units of one tensor; a unit = (row, group of 8 heads) = 2 KB)
+// into a shared-memory ring with cp.async.bulk - ONE 8 KB bulk copy per super-unit when the projection output is
+// dense, one copy per head otherwise - completing on an mbarrier per stage. kConsumers warps pick the units up
+// (warp w takes unit w % kGroup of every (w / kGroup)-th super-unit), read them with conflict-free LDS.128, normalise /
+// rotate in packed fp32 and store straight to global memory. The bytes in flight are set by the ring depth (stages x
+// 8 KB x CTAs per SM), not by the register budget of the compute warps: the register version above tops out at
+// 16 warps x 3 KB per SM (124 registers) and 78 % of the measured copy bandwidth. A first ring with one 2 KB copy
+// per barrier was producer-bound (~50 cycles of serial issue latency per copy; profiles/README.md).
+#ifndef MAGI_PRO_STAGES
+#define MAGI_PRO_STAGES 10
+#endif
+#ifndef MAGI_PRO_CONSUMERS
+#define MAGI_PRO_CONSUMERS 8
+#endif
+#ifndef MAGI_PRO_RING_BLOCKS
+#define MAGI_PRO_RING_BLOCKS 2
+#endif
+constexpr int kRingUnitHeads = 8;
+constexpr int kRingUnitBytes = kRingUnitHeads * 256;
+constexpr int kRingGroup = 4;                                  // units per super-unit (4 x 8 heads = 32 producer lanes)
+constexpr int kRingStageBytes = kRingGroup * kRingUnitBytes;
+constexpr int kRingStages = MAGI_PRO_STAGES;
+constexpr int kRingConsumers = MAGI_PRO_CONSUMERS;
+constexpr int kRingConsumerGroups = kRingConsumers / kRingGroup;
+static_assert(kRingConsumers % kRingGroup == 0, "consumer warps come in groups of kRingGroup");
+// Every use of a stage must be consumed by the SAME group of warps: an mbarrier parity wait can only tell the current
+// phase from the one before it, so a warp of another group arriving one use early would see "complete" spuriously
+// (found with 3 groups x 10 stages: unspecified launch failure from the watchdog trap).
+static_assert(kRingStages % kRingConsumerGroups == 0, "stages must be a multiple of the consumer groups");
+constexpr int kRingThreads = (kRingConsumers + 1) * 32;
+constexpr int kRingBarBytes = ((2 * kRingStages * 8 + 127) / 128) * 128;
+constexpr int kRingSmemBytes = kRingBarBytes + kRingStages * kRingStageBytes;
+
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+
+struct RingSuper {
+  int type;        // 0 = q, 1 = k, 2 = v
+  uint32_t u0;     // first unit (index inside the tensor's unit list)
+  int cnt;         // valid units (1..kRingGroup)
+};
+
+template <bool kLnBf16, bool kPerm>
+__global__ void __launch_bounds__(kRingThreads, MAGI_PRO_RING_BLOCKS) prologue_ring_kernel(const PrologueParams p) {
+  extern __shared__ __align__(128) uint8_t ring_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring_smem);
+  uint64_t* empty = full + kRingStages;
+  const uint32_t ring = smem_u32(ring_smem + kRingBarBytes);
+  const int lane = threadIdx.x & 31;
+  const int warp = uniform(static_cast<int>(threadIdx.x >> 5));
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRingStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kRingGroup); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  const uint32_t rows = static_cast<uint32_t>(p.rows);
+  const uint32_t upr_q = (p.Hq + kRingUnitHeads - 1) / kRingUnitHeads;
+  const uint32_t upr_kv = (p.Hkv + kRingUnitHeads - 1) / kRingUnitHeads;
+  const uint32_t n_q = p.x_q != nullptr ? rows * upr_q : 0u;
+  const uint32_t n_k = p.x_k != nullptr ? rows * upr_kv : 0u;
+  const uint32_t n_v = p.x_v != nullptr ? rows * upr_kv : 0u;
+  const uint32_t su_q = (n_q + kRingGroup - 1) / kRingGroup, su_k = (n_k + kRingGroup - 1) / kRingGroup;
+  const uint32_t su_v = (n_v + kRingGroup - 1) / kRingGroup;
+  const uint32_t total = su_q + su_k + su_v;
+  auto decode = [&](uint32_t su) {
+    RingSuper d;
+    d.type = su < su_q ? 0 : (su < su_q + su_k ? 1 : 2);
+    const uint32_t local = su - (d.type == 0 ? 0u : d.type == 1 ? su_q : su_q + su_k);
+    const uint32_t n = d.type == 0 ? n_q : d.type == 1 ? n_k : n_v;
+    d.u0 = local * kRingGroup;
+    d.cnt = static_cast<int>(min(static_cast<uint32_t>(kRingGroup), n - d.u0));
+    return d;
+  };
+
+  if (warp == kRingConsumers) {
+    // ------------------------------------------------------------------ producer
+    uint32_t m = 0;
+#pragma unroll 1
+    for (uint32_t su = blockIdx.x; su < total; su += gridDim.x, ++m) {
+      const uint32_t stage = m % kRingStages;
+      const uint32_t phase = (m / kRingStages) & 1u;
+      if (m >= kRingStages) mbar_wait(&empty[stage], phase ^ 1u);
+      const RingSuper d = decode(su);
+      const int H = d.type == 0 ? p.Hq : p.Hkv;
+      const uint32_t upr = d.type == 0 ? upr_q : upr_kv;
+      const int64_t rstride = d.type == 0 ? p.xq_row_stride : d.type == 1 ? p.xk_row_stride : p.xv_row_stride;
+      const int64_t hstride = d.type == 0 ? p.xq_head_stride : d.type == 1 ? p.xk_head_stride : p.xv_head_stride;
+      const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(d.type == 0 ? p.x_q : d.type == 1 ? p.x_k : p.x_v);
+      const uint32_t dst = ring + stage * kRingStageBytes;
+      if (hstride == 128 && rstride == static_cast<int64_t>(H) * 128 && (H % kRingUnitHeads) == 0) {
+        // dense projection output: the units of a super-unit are consecutive 2 KB pieces of one array
+        if (elect_one()) {
+          mbar_expect_tx(&full[stage], d.cnt * kRingUnitBytes);
+          bulk_g2s(dst, x + static_cast<int64_t>(d.u0) * (kRingUnitHeads * 128), d.cnt * kRingUnitBytes, &full[stage]);
+        }
+      } else {
+        // strided rows / heads (views, packed [K|V] projection of the cross-attention): lane = (unit, head)
+        const int sub = lane >> 3, hh = lane & 7;
+        const uint32_t u = d.u0 + sub;
+        const uint32_t r = upr == 1 ? u : u / upr;
+        const int head = static_cast<int>(u - r * upr) * kRingUnitHeads + hh;
+        const bool valid = sub < d.cnt && head < H;
+        const uint32_t nvalid = __popc(__ballot_sync(0xffffffffu, valid));
+        if (elect_one()) mbar_expect_tx(&full[stage], nvalid * 256);
+        __syncwarp();
+        if (valid) bulk_g2s(dst + lane * 256, x + r * rstride + head * hstride, 256, &full[stage]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ consumers
+    const int s = lane & 7;
+    const int j = lane >> 3;
+    const int sub = warp % kRingGroup;       // which unit of a super-unit this warp takes
+    const int grp = warp / kRingGroup;
+    // lane s < 6: elements [8s, 8s+8) and [48+8s, 48+8s+8) (RoPE partners in the same lane); lanes 6, 7: the
+    // pass-through dims, ordered so that both LDS.128 of a quarter-warp are bank-conflict free and every STG.128
+    // writes whole 32-byte sectors
+    const int e0 = s < 6 ? 8 * s : 112 + 8 * (s - 6);
+    const int e1 = s < 6 ? 48 + 8 * s : 96 + 8 * (s - 6);
+    const bool rot = p.sin != nullptr && s < 6;
+    const uint64_t one2 = pack_f2(1.f, 1.f);
+    int cur_type = -1;
+    uint64_t w2[8], b2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { w2[i] = one2; b2[i] = 0; }
+
+#pragma unroll 1
+    for (uint32_t m = grp;; m += kRingConsumerGroups) {
+      const uint64_t su64 = static_cast<uint64_t>(blockIdx.x) + static_cast<uint64_t>(m) * gridDim.x;
+      if (su64 >= total) break;
+      const RingSuper d = decode(static_cast<uint32_t>(su64));
+      const int type = d.type;
+      const uint32_t stage = m % kRingStages;
+      const uint32_t phase = (m / kRingStages) & 1u;
+      if (sub >= d.cnt) {                      // tail super-unit: nothing for this warp, keep the ring protocol going
+        mbar_wait(&full[stage], phase);
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        continue;
+      }
+      const uint32_t upr = type == 0 ? upr_q : upr_kv;
+      const uint32_t unit = d.u0 + sub;
+      const uint32_t r = upr == 1 ? unit : unit / upr;
+      const int h0 = static_cast<int>(unit - r * upr) * kRingUnitHeads;
+      const int H = type == 0 ? p.Hq : p.Hkv;
+
+      if (type != cur_type) {
+        cur_type = type;
+        if (type != 2) {
+          const void* w = type == 0 ? p.ln_q_w : p.ln_k_w;
+          const void* b = type == 0 ? p.ln_q_b : p.ln_k_b;
+          load_param8<kLnBf16>(w, e0, w2); load_param8<kLnBf16>(w, e1, w2 + 4);
+          load_param8<kLnBf16>(b, e0, b2); load_param8<kLnBf16>(b, e1, b2 + 4);
+          if (p.zero_centered_gamma != 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              w2[i] = fadd2(w2[i], one2);
+              // bf16 parameters: the reference computes `self.weight + 1` in bf16, i.e. rounds the sum
+              if constexpr (kLnBf16) w2[i] = bf2_to_f2(f2_to_bf2(w2[i]));
+            }
           }
         }
       }
 
-      // destination bases of this (row, tensor): q_out, or the K / V half of the packed kv row (and of the cache row)
+      // sin / cos of the row: issued here, consumed only after the LayerNorm of the first step (the packing below
+      // sits after the ring wait in program order, so the loads have the wait + LDS + LayerNorm time to land;
+      // ncu showed the warp parked on these loads when they were unpacked right away)
+      float4 c0 = make_float4(1.f, 1.f, 1.f, 1.f), c1 = c0, s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+      if (type != 2 && rot) {
+        const uint32_t trow = p.batch == 1 ? r : r / static_cast<uint32_t>(p.batch);
+        const float4* c = reinterpret_cast<const float4*>(p.cos + static_cast<int64_t>(trow) * 48 + 8 * s);
+        const float4* sp = reinterpret_cast<const float4*>(p.sin + static_cast<int64_t>(trow) * 48 + 8 * s);
+        c0 = __ldg(c); c1 = __ldg(c + 1); s0 = __ldg(sp); s1 = __ldg(sp + 1);
+      }
+
       __nv_bfloat16* out_base = type == 0 ? reinterpret_cast<__nv_bfloat16*>(p.q_out)
                                           : reinterpret_cast<__nv_bfloat16*>(p.kv_out) + (type == 2 ? 128 : 0);
       const int64_t out_tstride = type == 0 ? p.q_out_token_stride : p.kv_out_token_stride;
       const int64_t out_hstride = type == 0 ? p.q_out_head_stride : p.kv_out_head_stride;
-      __nv_bfloat16* out_row = out_base + r * out_tstride;
-      __nv_bfloat16* cache_row =
-          (type != 0 && p.cache != nullptr && r < p.cache_rows)
-              ? reinterpret_cast<__nv_bfloat16*>(p.cache) + (p.cache_row_offset + r) * p.cache_token_stride +
-                    (type == 2 ? 128 : 0)
-              : nullptr;
+      __nv_bfloat16* cache_row = nullptr;
+      if constexpr (!kPerm) {
+        if (type != 0 && p.cache != nullptr && static_cast<int64_t>(r) < p.cache_rows)
+          cache_row = reinterpret_cast<__nv_bfloat16*>(p.cache) + (p.cache_row_offset + r) * p.cache_token_stride +
+                      (type == 2 ? 128 : 0);
+      }
 
-      for (int h0 = 0; h0 < H; h0 += 2 * kUnroll) {
-        uint2 ra[kUnroll], rb[kUnroll];
+      mbar_wait(&full[stage], phase);
+      const uint32_t sbase = ring + stage * kRingStageBytes + sub * kRingUnitBytes + j * 256;
+      uint4 ra[2], rb[2];
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-          const int h = h0 + 2 * u + half;
-          ra[u] = make_uint2(0, 0);
-          rb[u] = make_uint2(0, 0);
-          if (h < H) {
-            ra[u] = ld_8(src + h * hstride + off0);
-            rb[u] = ld_8(src + h * hstride + off1);
-          }
-        }
+      for (int u = 0; u < 2; ++u) {
+        ra[u] = lds128(sbase + u * 1024 + e0 * 2);
+        rb[u] = lds128(sbase + u * 1024 + e1 * 2);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);   // the unit is in registers: hand the stage back to the producer
+
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-          const int h = h0 + 2 * u + half;
-          if (h0 + 2 * u >= H) break;   // warp-uniform: both halves are past the last head
-          const bool valid = h < H;
-          uint2 pa = ra[u], pb = rb[u];
-          if (type != 2) {
-            float v[8];
-            unpack4(ra[u], v);
-            unpack4(rb[u], v + 4);
-            // ---- LayerNorm over 128 in fp32 (two-pass, biased variance)
-            float s = 0.f;
+      for (int u = 0; u < 2; ++u) {
+        const int h = h0 + 4 * u + j;
+        if (h0 + 4 * u >= H) break;                // warp-uniform: the whole step is past the last head
+        uint4 pa = ra[u], pb = rb[u];
+        if (type != 2) {
+          uint64_t v[8];
+          v[0] = bf2_to_f2(pa.x); v[1] = bf2_to_f2(pa.y); v[2] = bf2_to_f2(pa.z); v[3] = bf2_to_f2(pa.w);
+          v[4] = bf2_to_f2(pb.x); v[5] = bf2_to_f2(pb.y); v[6] = bf2_to_f2(pb.z); v[7] = bf2_to_f2(pb.w);
+          // ---- LayerNorm over 128 in fp32 (two-pass, biased variance)
+          float lo, hi;
+          unpack_f2(fadd2(fadd2(fadd2(v[0], v[1]), fadd2(v[2], v[3])), fadd2(fadd2(v[4], v[5]), fadd2(v[6], v[7]))),
+                    lo, hi);
+          const float mean = quarter_warp_sum(lo + hi) * (1.0f / 128.0f);
+          const uint64_t mean2 = pack_f2(mean, mean);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) s += v[i];
-            const float mean = half_warp_sum(s) * (1.0f / 128.0f);
-            float sq = 0.f;
+          for (int i = 0; i < 8; ++i) v[i] = fsub2(v[i], mean2);
+          uint64_t sq_a = fmul2(v[0], v[0]), sq_b = fmul2(v[1], v[1]);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { v[i] -= mean; sq += v[i] * v[i]; }
-            const float var = half_warp_sum(sq) * (1.0f / 128.0f);
-            const float rstd = rsqrtf(var + p.eps);   // MUFU.RSQ (2 ulp in fp32: invisible after the bf16 rounding)
-            float y[8];
+          for (int i = 2; i < 8; i += 2) { sq_a = ffma2(v[i], v[i], sq_a); sq_b = ffma2(v[i + 1], v[i + 1], sq_b); }
+          unpack_f2(fadd2(sq_a, sq_b), lo, hi);
+          const float var = quarter_warp_sum(lo + hi) * (1.0f / 128.0f);
+          const float rstd = rsqrtf(var + p.eps);   // MUFU.RSQ (2 ulp in fp32: invisible after the bf16 rounding)
+          const uint64_t rstd2 = pack_f2(rstd, rstd);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) y[i] = v[i] * rstd * wf[i] + bf[i];
-            // ---- NeoX RoPE: (x1, x2) -> (x1 cos - x2 sin, x2 cos + x1 sin); identity on lanes 12..15 (cos 1, sin 0)
-            if (rope) {
+          for (int i = 0; i < 8; ++i) v[i] = ffma2(fmul2(v[i], rstd2), w2[i], b2[i]);
+          // ---- NeoX RoPE: (x1, x2) -> (x1 cos - x2 sin, x2 cos + x1 sin); identity on lanes 6, 7 (cos 1, sin 0)
+          if (rot) {
+            const uint64_t cs2[4] = {pack_f2(c0.x, c0.y), pack_f2(c0.z, c0.w), pack_f2(c1.x, c1.y), pack_f2(c1.z, c1.w)};
+            const uint64_t sn2[4] = {pack_f2(s0.x, s0.y), pack_f2(s0.z, s0.w), pack_f2(s1.x, s1.y), pack_f2(s1.z, s1.w)};
+            const uint64_t nsn2[4] = {pack_f2(-s0.x, -s0.y), pack_f2(-s0.z, -s0.w), pack_f2(-s1.x, -s1.y),
+                                      pack_f2(-s1.z, -s1.w)};
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float x1 = y[i], x2 = y[4 + i];
-                y[i] = x1 * cs[i] - x2 * sn[i];
-                y[4 + i] = x2 * cs[i] + x1 * sn[i];
-              }
+            for (int i = 0; i < 4; ++i) {
+              const uint64_t x1 = v[i], x2 = v[4 + i];
+              v[i] = ffma2(x1, cs2[i], fmul2(x2, nsn2[i]));
+              v[4 + i] = ffma2(x2, cs2[i], fmul2(x1, sn2[i]));
             }
-            pa = make_uint2(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]));
-            pb = make_uint2(pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
           }
-          if (!valid) continue;
+          pa = make_uint4(f2_to_bf2(v[0]), f2_to_bf2(v[1]), f2_to_bf2(v[2]), f2_to_bf2(v[3]));
+          pb = make_uint4(f2_to_bf2(v[4]), f2_to_bf2(v[5]), f2_to_bf2(v[6]), f2_to_bf2(v[7]));
+        }
+        if (h >= H) continue;
 
-          // ---- stores: attention (or all-to-all send) layout, plus the fused KV-cache append.
-          // Row bases were hoisted out of the head loop; without head permutation (cp == 1) a head costs one
-          // multiply-add per target - no integer divisions on the common path.
-          auto store = [&](__nv_bfloat16* dst) {
-            *reinterpret_cast<uint2*>(dst + off0) = pa;
-            *reinterpret_cast<uint2*>(dst + off1) = pb;
-          };
-          if (cp == 1) {
-            store(out_row + h * out_hstride);
-            if (cache_row != nullptr) store(cache_row + h * p.cache_head_stride);
-          } else if (type == 0) {
+        auto store = [&](__nv_bfloat16* dst) {
+          *reinterpret_cast<uint4*>(dst + e0) = pa;
+          *reinterpret_cast<uint4*>(dst + e1) = pb;
+        };
+        if constexpr (!kPerm) {
+          store(out_base + r * out_tstride + h * out_hstride);
+          if (cache_row != nullptr) store(cache_row + h * p.cache_head_stride);
+        } else {
+          const int cp = p.head_perm_cp;
+          if (type == 0) {
             const int hn = p.Hq / cp;
-            store(out_base + (static_cast<int64_t>(h / hn) * p.rows + r) * out_tstride +
+            store(out_base + (static_cast<int64_t>(h / hn) * rows + r) * out_tstride +
                   static_cast<int64_t>(h % hn) * out_hstride);
           } else if (cp > p.Hkv) {
             // fewer kv heads than ranks: replicate (repeat_interleave, context_parallel.py:393-394)
             const int rep = cp / p.Hkv;
             for (int c = h * rep; c < (h + 1) * rep; ++c)
-              store(out_base + (static_cast<int64_t>(c) * p.rows + r) * out_tstride);
+              store(out_base + (static_cast<int64_t>(c) * rows + r) * out_tstride);
           } else {
             const int hn = p.Hkv / cp;
-            store(out_base + (static_cast<int64_t>(h / hn) * p.rows + r) * out_tstride +
+            store(out_base + (static_cast<int64_t>(h / hn) * rows + r) * out_tstride +
                   static_cast<int64_t>(h % hn) * out_hstride);
           }
         }
@@ -326,10 +647,47 @@ cudaError_t cso_unshuffle_launch(void* dst, int64_t dst_stride, const void* src,
   return cudaGetLastError();
 }
 
-cudaError_t prologue_launch(const PrologueParams& p, bool ln_bf16, int grid, cudaStream_t stream) {
-  if (ln_bf16) prologue_kernel<true><<<grid, 256, 0, stream>>>(p);
-  else prologue_kernel<false><<<grid, 256, 0, stream>>>(p);
+#ifndef MAGI_PRO_RING
+#define MAGI_PRO_RING 1
+#endif
+int prologue_units(const PrologueParams& p, int64_t* units) {
+  constexpr int kHeadsPerUnit = MAGI_PRO_RING ? kRingUnitHeads : 4 * MAGI_PRO_UNROLL;
+  const int64_t upr_q = (p.Hq + kHeadsPerUnit - 1) / kHeadsPerUnit, upr_kv = (p.Hkv + kHeadsPerUnit - 1) / kHeadsPerUnit;
+  *units = p.rows * ((p.x_q ? upr_q : 0) + (p.x_k ? upr_kv : 0) + (p.x_v ? upr_kv : 0));
+  return MAGI_PRO_RING ? MAGI_PRO_RING_BLOCKS : MAGI_PRO_BLOCKS;
+}
+template <bool kLnBf16, bool kPerm>
+static cudaError_t prologue_launch_t(const PrologueParams& p, int64_t units, int sms, cudaStream_t stream) {
+#if MAGI_PRO_RING
+  static bool attr_set = false;   // per template instance; idempotent
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(prologue_ring_kernel<kLnBf16, kPerm>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kRingSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  // persistent: one CTA per resident slot; a CTA needs at least one unit
+  int64_t blocks = static_cast<int64_t>(sms) * MAGI_PRO_RING_BLOCKS;
+  const int64_t need = (units / kRingGroup + kRingConsumerGroups) / kRingConsumerGroups;
+  if (blocks > need) blocks = need;
+  if (blocks < 1) blocks = 1;
+  prologue_ring_kernel<kLnBf16, kPerm><<<static_cast<int>(blocks), kRingThreads, kRingSmemBytes, stream>>>(p);
+#else
+  int64_t blocks = (units + 7) / 8;
+  if (blocks > static_cast<int64_t>(sms) * MAGI_PRO_BLOCKS) blocks = static_cast<int64_t>(sms) * MAGI_PRO_BLOCKS;
+  if (blocks < 1) blocks = 1;
+  prologue_kernel<kLnBf16, kPerm><<<static_cast<int>(blocks), 256, 0, stream>>>(p);
+#endif
   return cudaGetLastError();
+}
+cudaError_t prologue_launch(const PrologueParams& p, bool ln_bf16, int sms, cudaStream_t stream) {
+  int64_t units = 0;
+  prologue_units(p, &units);
+  const bool perm = p.head_perm_cp > 1;
+  if (ln_bf16) return perm ? prologue_launch_t<true, true>(p, units, sms, stream)
+                           : prologue_launch_t<true, false>(p, units, sms, stream);
+  return perm ? prologue_launch_t<false, true>(p, units, sms, stream)
+              : prologue_launch_t<false, false>(p, units, sms, stream);
 }
 cudaError_t kv_append_launch(void* cache, int64_t cache_stride, const void* kv, int64_t kv_stride, int64_t row_offset,
                              int64_t rows, int row_vecs, int grid, cudaStream_t stream) {

@@ -22,7 +22,10 @@ struct PrologueParams {
   int head_perm_cp;
 };
 
-cudaError_t prologue_launch(const PrologueParams& p, bool ln_bf16, int grid, cudaStream_t stream);
+// number of work units of a launch (-> *units) and the resident 256-thread CTAs per SM the kernel is built for
+int prologue_units(const PrologueParams& p, int64_t* units);
+// persistent launch sized from the SM count
+cudaError_t prologue_launch(const PrologueParams& p, bool ln_bf16, int sms, cudaStream_t stream);
 cudaError_t kv_append_launch(void* cache, int64_t cache_stride, const void* kv, int64_t kv_stride, int64_t row_offset,
                              int64_t rows, int row_vecs, int grid, cudaStream_t stream);
 cudaError_t lse_merge_launch(void* out_a, float* lse_a, const void* out_b, const float* lse_b, int64_t rows, int heads,

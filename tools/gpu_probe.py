@@ -252,6 +252,27 @@ def r_bench_prologue():
         best = min(ts[1:])
         print(f"[prologue {nm}] {byts/1e6:.0f} MB  best {best*1e3:.1f} us -> {byts/best/1e6:.0f} GB/s (L2 flushed; all: "
               + ", ".join(f"{t*1e3:.0f}" for t in ts) + ")", flush=True)
+    # which part limits it: q alone (dense in, dense out, full arithmetic), k alone (arithmetic, 256-byte-strided
+    # writes), v alone (pure copy, 256-byte-strided writes), and a plain copy of the same size through torch
+    def timed(fn, byts, nm):
+        ts = []
+        for _ in range(6):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        best = min(ts[1:])
+        print(f"[prologue part: {nm}] {byts/1e6:.0f} MB  best {best*1e3:.1f} us -> {byts/best/1e6:.0f} GB/s", flush=True)
+    timed(lambda: F.qk_norm_rope(xq, None, None, Hq, Hkv, (ln[0], ln[1]), None, sin, cos, q_out=q),
+          S * Hq * 128 * 4 + S * 96 * 4, "q only")
+    timed(lambda: F.qk_norm_rope(None, xk, None, Hq, Hkv, None, (ln[2], ln[3]), sin, cos, kv_out=kv),
+          S * Hkv * 128 * 4 + S * 96 * 4, "k only")
+    timed(lambda: F.qk_norm_rope(None, None, xv, Hq, Hkv, None, None, None, None, kv_out=kv),
+          S * Hkv * 128 * 4, "v only")
+    timed(lambda: F.qk_norm_rope(xq, None, None, Hq, Hkv, (ln[0], ln[1]), None, None, None, q_out=q),
+          S * Hq * 128 * 4, "q only, no rope")
+    timed(lambda: q.view(-1).copy_(xq.view(-1)), S * Hq * 128 * 4, "torch copy of q")
     return True
 
 
