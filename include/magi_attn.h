@@ -185,6 +185,29 @@ MAGI_API int magi_ulysses_relayout(void* dst, const void* src, int64_t seq, int3
 MAGI_API int magi_cso_unshuffle(void* dst, int64_t dst_token_stride, const void* src, int64_t src_token_stride,
                                 int32_t cp, int32_t dn, int64_t spb, int64_t clip, int64_t row_elems, void* stream);
 
+/*
+ * Fused adaLN gating chain behind the attention path's output projection (and behind the MLP):
+ *   out[row, :] = bf16( LayerNorm_hidden( float(x[row, :]) * float(gate[cond_map[row], :]) ) * (ln_w + 1) + ln_b
+ *                       + float(residual[row, :]) )
+ * Replaces bias_modulate_add (dit_module.py:292-307): x.float(), residual.float(), gate.float(), the Triton
+ * range_mod kernel (:201-289), FusedLayerNorm post_norm (:355-357, fp32 parameters per dit_model.py:621-638), the
+ * residual add and the cast back, seven eager kernels in the reference.
+ * Rows are "(sq b)"-flattened; cond_map[row] indexes the rows of gate = gate.flatten(0, 1) (dit_model.py:204-206).
+ * x_dtype / gate_dtype: 0 = fp32, 1 = bf16. residual / out: bf16. hidden must be a multiple of 256 and at most
+ * 12288. Strides in elements; all pointers 16-byte aligned, row strides multiples of 8 elements.
+ */
+typedef struct MagiGatingArgs {
+  const void* x; int32_t x_dtype; int64_t x_row_stride;
+  const void* residual; int64_t residual_row_stride;
+  const void* cond_map; int32_t cond_map_is_int64; int64_t cond_map_stride;
+  const void* gate; int32_t gate_dtype; int64_t gate_row_stride; int64_t num_gates;
+  const float* ln_w; const float* ln_b;
+  float eps; int32_t zero_centered_gamma;
+  void* out; int64_t out_row_stride;
+  int64_t rows; int32_t hidden;
+} MagiGatingArgs;
+MAGI_API int magi_bias_modulate_add(const MagiGatingArgs* args, void* stream);
+
 /* Diagnostics */
 MAGI_API const char* magi_last_error(void);
 MAGI_API const char* magi_build_info(void);

@@ -21,6 +21,7 @@ EXPORTS = (
     "magi_lse_merge",
     "magi_ulysses_relayout",
     "magi_cso_unshuffle",
+    "magi_bias_modulate_add",
     "magi_last_error",
     "magi_build_info",
     "magi_launch_count",
@@ -103,6 +104,19 @@ class MagiPrologueArgs(C.Structure):
     ]
 
 
+class MagiGatingArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("x_dtype", C.c_int32), ("x_row_stride", C.c_int64),
+        ("residual", C.c_void_p), ("residual_row_stride", C.c_int64),
+        ("cond_map", C.c_void_p), ("cond_map_is_int64", C.c_int32), ("cond_map_stride", C.c_int64),
+        ("gate", C.c_void_p), ("gate_dtype", C.c_int32), ("gate_row_stride", C.c_int64), ("num_gates", C.c_int64),
+        ("ln_w", C.c_void_p), ("ln_b", C.c_void_p),
+        ("eps", C.c_float), ("zero_centered_gamma", C.c_int32),
+        ("out", C.c_void_p), ("out_row_stride", C.c_int64),
+        ("rows", C.c_int64), ("hidden", C.c_int32),
+    ]
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile libmagi_attn.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
     if force:
@@ -147,6 +161,8 @@ def lib() -> C.CDLL:
     L.magi_cso_unshuffle.restype = C.c_int
     L.magi_cso_unshuffle.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64,
                                      C.c_int64, C.c_int64, C.c_void_p]
+    L.magi_bias_modulate_add.restype = C.c_int
+    L.magi_bias_modulate_add.argtypes = [C.POINTER(MagiGatingArgs), C.c_void_p]
     L.magi_last_error.restype = C.c_char_p
     L.magi_build_info.restype = C.c_char_p
     L.magi_launch_count.restype = C.c_uint64

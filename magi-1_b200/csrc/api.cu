@@ -9,6 +9,7 @@
 #include "../../include/magi_attn.h"
 #include "attn_fwd.cuh"
 #include "prologue.cuh"
+#include "gating.cuh"
 
 namespace {
 
@@ -337,6 +338,39 @@ int magi_cso_unshuffle(void* dst, int64_t dst_token_stride, const void* src, int
   if (int rc = grid_for(dn * clip * (row_elems / 8), 256, &grid)) return rc;
   MAGI_CUDA(magi::cso_unshuffle_launch(dst, dst_token_stride, src, src_token_stride, dn, spb, clip,
                                        (int)(row_elems / 8), grid, stream));
+  g_launches++;
+  return 0;
+}
+
+int magi_bias_modulate_add(const MagiGatingArgs* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MAGI_CHECK(a != nullptr, "NULL args");
+  MAGI_CHECK(a->rows >= 0 && a->hidden > 0, "bad shape");
+  MAGI_CHECK(magi::gating_warps_per_row(a->hidden) > 0, "hidden must be a multiple of 256 (at most 12288)");
+  MAGI_CHECK((a->x_dtype == 0 || a->x_dtype == 1) && (a->gate_dtype == 0 || a->gate_dtype == 1),
+             "x_dtype / gate_dtype must be 0 (fp32) or 1 (bf16)");
+  if (a->rows == 0) return 0;
+  MAGI_CHECK(a->x && a->residual && a->cond_map && a->gate && a->ln_w && a->ln_b && a->out, "NULL pointer");
+  MAGI_CHECK(a->x_row_stride % 8 == 0 && a->residual_row_stride % 8 == 0 && a->out_row_stride % 8 == 0 &&
+                 a->gate_row_stride % 8 == 0,
+             "row strides must be multiples of 8 elements");
+  MAGI_CHECK(a->x_row_stride >= a->hidden && a->residual_row_stride >= a->hidden && a->out_row_stride >= a->hidden,
+             "row strides smaller than hidden");
+  MAGI_CHECK(((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->residual) |
+               reinterpret_cast<uintptr_t>(a->gate) | reinterpret_cast<uintptr_t>(a->ln_w) |
+               reinterpret_cast<uintptr_t>(a->ln_b) | reinterpret_cast<uintptr_t>(a->out)) & 15) == 0,
+             "pointers must be 16-byte aligned");
+  MAGI_CHECK(a->num_gates > 0 && a->cond_map_stride >= 1, "bad gate / cond_map description");
+  magi::GatingParams p;
+  p.x = a->x; p.residual = a->residual; p.cond_map = a->cond_map; p.gate = a->gate;
+  p.ln_w = a->ln_w; p.ln_b = a->ln_b; p.out = a->out;
+  p.rows = a->rows; p.hidden = a->hidden;
+  p.x_row_stride = a->x_row_stride; p.res_row_stride = a->residual_row_stride; p.out_row_stride = a->out_row_stride;
+  p.gate_row_stride = a->gate_row_stride; p.map_stride = a->cond_map_stride;
+  p.map_is_i64 = a->cond_map_is_int64; p.eps = a->eps; p.zero_centered_gamma = a->zero_centered_gamma;
+  int sms = 0;
+  if (int rc = device_sm_count(&sms)) return rc;
+  MAGI_CUDA(magi::gating_launch(p, a->x_dtype == 1, a->gate_dtype == 1, sms, stream));
   g_launches++;
   return 0;
 }

@@ -8,7 +8,8 @@ inference/model/dit/dit_module.py, backed by libmagi_attn.so (hand-written sm_10
                             _full_adjust_key_and_value + core_attention compute without the torch.cat / chunk copies
                             (dit_module.py:914-946, 1023-1066)
     qk_norm_rope            get_q / get_k / get_v / get_kv / get_xqkv fused      (dit_module.py:953-1021)
-    kv_cache_append, lse_merge, ulysses_relayout : helpers around the context-parallel exchange
+    kv_cache_append, lse_merge, ulysses_relayout, cso_unshuffle : helpers around the context-parallel exchange
+    bias_modulate_add       <- bias_modulate_add / range_mod_triton / post_norm    (dit_module.py:201-307)
 
 No CPU fallback: every function requires CUDA tensors and the built extension.
 """
@@ -19,7 +20,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import MagiAttnArgs, MagiPrologueArgs, MagiView
+from ._lib import MagiAttnArgs, MagiGatingArgs, MagiPrologueArgs, MagiView
 
 HEAD_DIM = 128
 
@@ -438,4 +439,60 @@ def ulysses_relayout(src: torch.Tensor, cp: int, mode: int, kv_repeat: int = 1, 
         _lib.check(_lib.lib().magi_ulysses_relayout(out.data_ptr(), src.data_ptr(), seq, heads, E, cp, kv_repeat, mode,
                                                     dst_heads_total, dst_head_offset, _stream()),
                    "magi_ulysses_relayout")
+    return out
+
+
+def bias_modulate_add(x: torch.Tensor, residual: torch.Tensor, condition_map: torch.Tensor, gate: torch.Tensor,
+                      post_norm, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Same call as the reference's `bias_modulate_add(x, residual, condition_map, gate, post_norm)`
+    (dit_module.py:292-307), one kernel instead of seven:
+        out = (post_norm(x.float() * gate.float()[condition_map]) + residual.float()).to(residual.dtype)
+
+    x (s, b, h) fp32 (the out-projection runs under fp32 autocast, dit_module.py:1343) or bf16 (MLP output);
+    residual (s, b, h) bf16; condition_map (s, b) int64/int32 indices into gate.flatten(0, 1); gate (b, dn, h) fp32 or
+    bf16; post_norm: a module with fp32 `weight`, `bias`, and `eps`, `zero_centered_gamma` attributes (FusedLayerNorm,
+    dit_module.py:323-357) or a tuple (weight, bias, eps, zero_centered_gamma)."""
+    if isinstance(post_norm, (tuple, list)):
+        w, b, eps, zcg = post_norm
+    else:
+        w, b, eps, zcg = post_norm.weight, post_norm.bias, post_norm.eps, post_norm.zero_centered_gamma
+    if not x.is_cuda:
+        raise ValueError("x must be a CUDA tensor (this package has no CPU path)")
+    if x.dtype not in (torch.float32, torch.bfloat16) or gate.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("x and gate must be fp32 or bf16")
+    if residual.dtype != torch.bfloat16 or residual.shape != x.shape:
+        raise ValueError("residual must be bf16 with the shape of x")
+    if w.dtype != torch.float32 or b.dtype != torch.float32:
+        raise ValueError("post_norm parameters must be fp32 (dit_model.py:621-638)")
+    h = x.shape[-1]
+    assert gate.shape[-1] == h   # dit_module.py:295
+    if w.numel() != h or b.numel() != h:
+        raise ValueError("post_norm parameters do not match the hidden size")
+    if condition_map.dtype not in (torch.int64, torch.int32) or condition_map.numel() != x.numel() // h:
+        raise ValueError("condition_map must be int32/int64 with one entry per row of x")
+    x2, r2 = x.reshape(-1, h), residual.reshape(-1, h)          # "(sq b)" rows; views for contiguous inputs
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    if r2.stride(1) != 1:
+        r2 = r2.contiguous()
+    cm = condition_map.reshape(-1)
+    g2 = gate.reshape(-1, h)
+    if g2.stride(1) != 1:
+        g2 = g2.contiguous()
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    elif out.shape != x.shape or out.dtype != torch.bfloat16 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous bf16 tensor with the shape of x")
+    a = MagiGatingArgs()
+    a.x, a.x_dtype, a.x_row_stride = x2.data_ptr(), 1 if x2.dtype == torch.bfloat16 else 0, x2.stride(0)
+    a.residual, a.residual_row_stride = r2.data_ptr(), r2.stride(0)
+    a.cond_map, a.cond_map_is_int64, a.cond_map_stride = cm.data_ptr(), 1 if cm.dtype == torch.int64 else 0, cm.stride(0)
+    a.gate, a.gate_dtype, a.gate_row_stride, a.num_gates = (g2.data_ptr(), 1 if g2.dtype == torch.bfloat16 else 0,
+                                                            g2.stride(0), g2.shape[0])
+    a.ln_w, a.ln_b = w.contiguous().data_ptr(), b.contiguous().data_ptr()
+    a.eps, a.zero_centered_gamma = float(eps), 1 if zcg else 0
+    a.out, a.out_row_stride = out.data_ptr(), h
+    a.rows, a.hidden = x2.shape[0], h
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().magi_bias_modulate_add(C.byref(a), _stream()), "magi_bias_modulate_add")
     return out

@@ -12,6 +12,8 @@ without a GPU:
   * flash_attn.layers.rotary.apply_rotary_emb (Triton)  -> flash-attn's own `apply_rotary_emb_torch`
   * flash_attn_func / flash_attn_varlen_func (CUDA)     -> fp32 softmax(QK^T/sqrt(d))V with GQA, output cast to bf16
   * torch.cuda.current_device / Tensor.cuda / get_device_capability -> CPU stand-ins
+  * range_mod_kernel_fwd (the reference's own Triton kernel, dit_module.py:201-241) -> the same row-gather multiply
+    in torch; its host wrapper range_mod_triton and bias_modulate_add run unmodified
 """
 import math
 import os
@@ -386,6 +388,48 @@ def gen_cso(world, port):
     print(f"cso cp={world} fixture written")
 
 
+# ------------------------------------------------------------------ scenario 5: adaLN gating chain (bias_modulate_add)
+class _RangeModGrid:
+    """Stand-in for `range_mod_kernel_fwd[(M,)](...)`: what the Triton program does for every row
+    (dit_module.py:218-241): y[row, :] = x[row, :] * gatings[map[row], :]."""
+
+    def __getitem__(self, grid):
+        def run(x, MAP, gatings, y, M, N, sxm, sxn, sgm, sgn, sym, syn, BLOCK_SIZE=None):
+            y.copy_(x * gatings[MAP.long()])
+        return run
+
+
+def gen_gating():
+    dm = install_patches()
+    dm.range_mod_kernel_fwd = _RangeModGrid()
+    torch.Tensor.is_cuda = property(lambda self: True)      # the wrapper asserts x.is_cuda (dit_module.py:252-254)
+    mc, _ = make_configs(hidden=512)
+    fx = {}
+    g = torch.Generator().manual_seed(2024)
+    for tag, (s_, b_, dn, xdt) in {"attn_b1": (3 * 29, 1, 3, torch.float32), "mlp_b1": (3 * 29, 1, 3, torch.bfloat16),
+                                  "attn_b2": (41, 2, 1, torch.float32)}.items():
+        h = mc.hidden_size
+        norm = dm.FusedLayerNorm(mc, h).float()
+        with torch.no_grad():
+            norm.weight.copy_(torch.randn(h, generator=g) * 0.1)
+            norm.bias.copy_(torch.randn(h, generator=g) * 0.1)
+        x = (torch.randn(s_, b_, h, generator=g) * 1.5).to(xdt)
+        residual = torch.randn(s_, b_, h, generator=g).to(torch.bfloat16)
+        cond = torch.randn(b_, dn, h, generator=g)
+        gate = dm.softcap(cond.to(torch.bfloat16), 1.0)                       # dit_module.py:1353-1355
+        cmap = torch.arange(b_ * dn).repeat_interleave(s_ // dn).reshape(b_, -1).transpose(0, 1).contiguous()
+        with torch.no_grad():
+            out = dm.bias_modulate_add(x, residual, cmap, gate, norm)
+        assert out.dtype == xdt
+        fx.update({f"{tag}.x": pk(x) if xdt == torch.bfloat16 else x.numpy(), f"{tag}.residual": pk(residual),
+                   f"{tag}.cmap": cmap.numpy(), f"{tag}.gate": pk(gate), f"{tag}.w": norm.weight.detach().numpy(),
+                   f"{tag}.b": norm.bias.detach().numpy(), f"{tag}.cond": cond.numpy(),
+                   f"{tag}.out": pk(out.to(torch.bfloat16)), f"{tag}.out_is_fp32": np.array(xdt == torch.float32)})
+    del torch.Tensor.is_cuda
+    np.savez_compressed(os.path.join(OUT, "gating.npz"), **fx)
+    print("gating fixture written")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -397,5 +441,7 @@ if __name__ == "__main__":
         gen_cp(4, 29561, 8, 2, "cp4")   # cp > Hkv: exercises KV-head replication (context_parallel.py:393-394)
     if which in ("all", "cso"):
         gen_cso(2, 29571)
+    if which in ("gating",):      # run on its own: it monkey-patches Tensor.is_cuda while it runs
+        gen_gating()
     if which in ("all", "single"):
         gen_single_rank()

@@ -438,6 +438,26 @@ def cso_core_attention(q_per_rank: List[np.ndarray], kv_per_rank: List[np.ndarra
     return outs
 
 
+# ----------------------------------------------------------------------------------------------- adaLN gating chain
+def softcap(x: np.ndarray, cap: float = 1.0) -> np.ndarray:
+    """dit_module.py:360-361 on a bf16 tensor: (cap * tanh(x.float() / cap)).to(bf16)."""
+    return bf16_round(F32(cap) * np.tanh(x.astype(F32) / F32(cap)))
+
+
+def bias_modulate_add(x: np.ndarray, residual: np.ndarray, condition_map: np.ndarray, gate: np.ndarray,
+                      ln_w: np.ndarray, ln_b: np.ndarray, eps: float = 1e-6, zero_centered_gamma: bool = True):
+    """bias_modulate_add, dit_module.py:292-307, with range_mod_triton (:244-289; the Triton program :201-241 is
+    y[row] = x[row] * gatings[map[row]]) and the fp32 FusedLayerNorm post_norm (:355-357).
+    x (s, b, h) holding fp32 (or bf16) values, residual (s, b, h) bf16 values, condition_map (s, b) indices into
+    gate.reshape(-1, h), gate (b, dn, h). Returns the bf16-rounded result the layer keeps
+    (`.to(params_dtype)`, dit_module.py:1359-1361)."""
+    h = x.shape[-1]
+    g = gate.reshape(-1, h).astype(F32)[np.asarray(condition_map).astype(np.int64)]     # (s, b, h)
+    t = x.astype(F32) * g
+    y = layer_norm(t, ln_w, ln_b, eps, zero_centered_gamma)
+    return bf16_round(y + residual.astype(F32))
+
+
 # ----------------------------------------------------------------------------------------------- RoPE table
 def rope_table(T_total: int, H: int, W: int, bands: Optional[np.ndarray] = None, keep_last_T: Optional[int] = None):
     """LearnableRotaryEmbeddingCat.get_embed as used at dit_model.py:163-166 (in_pixels=False, dim=128):

@@ -327,6 +327,46 @@ def test_cso_unshuffle_and_full_attention(F):
         check_attn(out, exp_o, f"cso chunk {d}")
 
 
+@pytest.mark.parametrize("tag", ["attn_b1", "mlp_b1", "attn_b2"])
+def test_bias_modulate_add_vs_reference_golden(F, tag):
+    """Fused adaLN gating chain kernel against the reference's bias_modulate_add output (tests/golden/gating.npz)
+    and the oracle: <= 1 bf16 ulp (fp32 LayerNorm summation order differs)."""
+    g = Golden("gating.npz")
+    x = g.torch(f"{tag}.x", "cuda")
+    res, gate = g.torch(f"{tag}.residual", "cuda"), g.torch(f"{tag}.gate", "cuda")
+    cmap = g.torch(f"{tag}.cmap", "cuda")
+    w, b = g.torch(f"{tag}.w", "cuda"), g.torch(f"{tag}.b", "cuda")
+    out = F.bias_modulate_add(x, res, cmap, gate, (w, b, 1e-6, True))
+    assert out.dtype == torch.bfloat16 and out.shape == x.shape
+    ref = g[f"{tag}.out"]
+    got = out.float().cpu().numpy()
+    tol = np.maximum(np.abs(ref), np.abs(got)) * 2.0 ** -7 + 1e-6
+    assert (np.abs(got - ref) <= tol).all(), float(np.abs(got - ref).max())
+    # int32 map, fp32 gate: same result
+    out2 = F.bias_modulate_add(x, res, cmap.to(torch.int32), gate.float(), (w, b, 1e-6, True))
+    assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("hidden,rows,xdt", [(3072, 1000, torch.float32), (6144, 517, torch.float32),
+                                             (3072, 333, torch.bfloat16), (256, 77, torch.float32),
+                                             (12288, 64, torch.bfloat16)])
+def test_bias_modulate_add_sizes_vs_oracle(F, hidden, rows, xdt):
+    """Model widths (4.5B: 3072 = one warp per row, 24B: 6144 = two warps per row) and the extremes of the supported
+    range against the oracle."""
+    gen = torch.Generator().manual_seed(hidden + rows)
+    x = (torch.randn(rows, 1, hidden, generator=gen) * 2).to(xdt)
+    res = torch.randn(rows, 1, hidden, generator=gen).to(torch.bfloat16)
+    gate = torch.tanh(torch.randn(1, 5, hidden, generator=gen)).to(torch.bfloat16)
+    cmap = torch.randint(0, 5, (rows, 1), generator=gen)
+    w, b = torch.randn(hidden, generator=gen) * 0.1, torch.randn(hidden, generator=gen) * 0.1
+    ref = O.bias_modulate_add(x.float().numpy(), res.float().numpy(), cmap.numpy(), gate.float().numpy(), w.numpy(),
+                              b.numpy())
+    out = F.bias_modulate_add(x.cuda(), res.cuda(), cmap.cuda(), gate.cuda(), (w.cuda(), b.cuda(), 1e-6, True))
+    got = out.float().cpu().numpy()
+    tol = np.maximum(np.abs(ref), np.abs(got)) * 2.0 ** -7 + 1e-6
+    assert (np.abs(got - ref) <= tol).all(), float(np.abs(got - ref).max())
+
+
 def test_full_attention_block_matches_reference_golden():
     """The drop-in FullyParallelAttention replays the reference's own forward sequence (steps A-E of
     oracle/gen_golden.py: KV-cache fill, fwd_extra_1st_chunk, update_kv_cache False/True, distill extra range,

@@ -261,6 +261,18 @@ def test_cso_matches_reference():
     assert np.array_equal(gathered, g0["gathered"])
 
 
+@pytest.mark.parametrize("tag", ["attn_b1", "mlp_b1", "attn_b2"])
+def test_bias_modulate_add_matches_reference(tag):
+    """adaLN gating chain (dit_module.py:201-307) against the reference's own bias_modulate_add run on CPU:
+    fp32 out-projection input (attention branch), bf16 MLP output, and the batched (b = 2, one range) pass."""
+    g = Golden("gating.npz")
+    out = O.bias_modulate_add(g[f"{tag}.x"], g[f"{tag}.residual"], g.raw(f"{tag}.cmap"), g[f"{tag}.gate"],
+                              g[f"{tag}.w"], g[f"{tag}.b"])
+    ok, err, nbad = close_bf16(out, g[f"{tag}.out"])
+    assert ok, f"max err {err}, {nbad} elements beyond 1 bf16 ulp"
+    assert np.array_equal(O.softcap(O.bf16_round(g[f"{tag}.cond"])), g[f"{tag}.gate"])
+
+
 def test_lse_merge_is_softmax_over_union():
     rng = np.random.default_rng(0)
     q = rng.standard_normal((40, 4, 128)).astype(np.float32)

@@ -276,6 +276,49 @@ def r_bench_prologue():
     return True
 
 
+@case
+def t_bench_gating():
+    """Fused adaLN gating chain (bias_modulate_add): cfg2 rows x 3072 (fp32 out-projection input and bf16 MLP output)
+    and the 24B width (6144, two warps per row)."""
+    import torch
+    import magi_b200.functional as F
+    dev = "cuda"
+    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+    for rows, h, xdt in ((37440, 3072, torch.float32), (37440, 3072, torch.bfloat16), (54000, 6144, torch.float32)):
+        x = torch.randn(rows, 1, h, device=dev, dtype=xdt)
+        res = torch.randn(rows, 1, h, device=dev, dtype=torch.bfloat16)
+        gate = torch.tanh(torch.randn(1, 4, h, device=dev)).to(torch.bfloat16)
+        cmap = (torch.arange(rows, device=dev) * 4 // rows).reshape(rows, 1)
+        w, b = torch.randn(h, device=dev) * 0.1, torch.randn(h, device=dev) * 0.1
+        out = torch.empty(rows, 1, h, device=dev, dtype=torch.bfloat16)
+        byts = rows * h * (x.element_size() + 2 + 2)
+        ts = []
+        for _ in range(6):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); F.bias_modulate_add(x, res, cmap, gate, (w, b, 1e-6, True), out=out); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        best = min(ts[1:])
+        print(f"[gating {rows}x{h} x={str(xdt)[6:]}] {byts/1e6:.0f} MB  best {best*1e3:.1f} us -> {byts/best/1e6:.0f} GB/s "
+              f"(L2 flushed; all: " + ", ".join(f"{t*1e3:.0f}" for t in ts) + ")", flush=True)
+        # the reference's eager chain on the same box (range_mod restated as an index-multiply: its Triton kernel
+        # is not importable here), for scale
+        def eager():
+            t = x.float() * gate.float().flatten(0, 1)[cmap.flatten()].view(rows, 1, h)
+            t = torch.nn.functional.layer_norm(t, (h,), w + 1, b, 1e-6)
+            return (t + res.float()).to(torch.bfloat16)
+        ts = []
+        for _ in range(4):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); eager(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        print(f"[gating eager torch chain, same shapes] best {min(ts[1:])*1e3:.1f} us", flush=True)
+    return True
+
+
 def main():
     names = sys.argv[1:] or sorted(CASES)
     if len(names) == 1 and names[0].startswith("--run="):
