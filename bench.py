@@ -118,14 +118,15 @@ class HotPath:
     """Synthetic inputs of one denoise forward's attention hot path, resident in HBM, and the per-layer launch
     sequence through the public API (magi_b200.functional -> C-ABI)."""
 
-    def __init__(self, w, device, cp=1, rank=0, seed=1234):
+    def __init__(self, w, device, cp=1, rank=0, seed=1234, fused=True):
         import torch
         import magi_b200.functional as F
         self.torch, self.F, self.w, self.cp, self.rank, self.dev = torch, F, w, cp, rank, device
+        self.fused = fused and cp > 1
         Hq, Hkv, clip = w["Hq"], w["Hkv"], w["clip"]
         self.S = clip * len(w["k_chunks"])
+        from magi_b200 import context_parallel as cpm
         if cp > 1:
-            from magi_b200 import context_parallel as cpm
             self.split = cpm.ulysses_split_sizes(self.S, cp)
         else:
             self.split = [self.S]
@@ -165,8 +166,21 @@ class HotPath:
         self.hq_loc = Hq // cp
         self.cache_rows = (sp + n) * clip
         self.start = sp * clip
-        self.caches = [torch.empty(self.cache_rows, self.hkv_loc, 256, dtype=torch.bfloat16, device=device)
-                       for _ in range(w["layers"])]
+        if self.fused:
+            # fused all-to-alls: caches and receive buffers live in symmetric (NVLink peer-mapped) memory
+            import torch.distributed._symmetric_memory as symm
+            from magi_b200 import parallel_state as mpu
+            self.caches, self.cache_ptrs = [], []
+            for _ in range(w["layers"]):
+                c = symm.empty((self.cache_rows, self.hkv_loc, 256), dtype=torch.bfloat16, device=device)
+                self.cache_ptrs.append([int(p_) for p_ in symm.rendezvous(c, mpu.get_cp_group().group_name).buffer_ptrs])
+                self.caches.append(c)
+            self.ws = cpm.UlyssesPeerWorkspace.get(mpu.get_cp_group(), self.S, max(self.split), self.hq_loc,
+                                                   self.hkv_loc, Hq, device)
+            self.row_off, self.bounds, self.head_off = cpm.fused_ulysses_plan(self.split, rank, Hq, cp)
+        else:
+            self.caches = [torch.empty(self.cache_rows, self.hkv_loc, 256, dtype=torch.bfloat16, device=device)
+                           for _ in range(w["layers"])]
         if sp > 0:
             for c in self.caches:
                 c[:self.start].normal_()
@@ -251,10 +265,39 @@ class HotPath:
             self.split, relayout_out=relayout_out)
         self.core_out = core_out
 
+    # -- one layer, Ulysses with both all-to-alls fused into the kernels' stores (FullyParallelAttention.
+    #    _forward_ulysses_fused): one prologue launch writes q and [K|V] into the owners' buffers (K/V straight into
+    #    the cache slot), the attention epilogue writes every output row into its owner's buffer; two barriers
+    def layer_cp_fused(self, l, timed_events=False):
+        F, w, inp, torch, cp = self.F, self.w, self.inputs, self.torch, self.cp
+        cache, ws = self.caches[l], self.ws
+        row_bytes = self.hkv_loc * 256 * 2
+        F.qk_norm_rope(inp["xq"], inp["xk"], inp["xv"], w["Hq"], w["Hkv"], self.ln["q"], self.ln["k"], inp["sin"],
+                       inp["cos"], head_perm_cp=cp, peer_q_out=ws.q_ptrs,
+                       peer_kv_out=[p_ + self.start * row_bytes for p_ in self.cache_ptrs[l]],
+                       peer_row_offset=self.row_off, peer_heads=(self.hq_loc, self.hkv_loc))
+        x_prepared = self.cross_prepare(inp)
+        ws.barrier()
+        kv = cache[self.start:self.start + self.S]
+        kc = vc = None
+        if self.start > 0:
+            kc, vc = cache[:self.start, :, :128], cache[:self.start, :, 128:]
+        if timed_events:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        F.attn_ranges(ws.q, kv[..., :128], kv[..., 128:], self.q_ranges, self.k_ranges, k_cache=kc, v_cache=vc,
+                      return_lse=False, peer_out=(ws.out_ptrs, self.bounds, self.head_off, w["Hq"]))
+        if timed_events:
+            e1.record()
+            self.attn_events.append((e0, e1))
+        self.cross_attend(x_prepared)
+        ws.barrier()
+        self.core_out = ws.out[:self.S_loc]
+
     ulysses_overlap_degree = 1
 
     def step(self, timed_events=False):
-        fn = self.layer_cp if self.cp > 1 else self.layer
+        fn = (self.layer_cp_fused if self.fused else self.layer_cp) if self.cp > 1 else self.layer
         for l in range(self.w["layers"]):
             fn(l, timed_events)
 
@@ -322,6 +365,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--overlap-degree", type=int, default=1)
+    ap.add_argument("--cp-mode", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: all-to-alls fused into the kernels' stores over NVLink peer memory, or NCCL calls")
     ap.add_argument("--ref-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -350,7 +395,7 @@ def main():
         mpu.initialize_model_parallel(cp_size=world)
     from magi_b200 import _lib
 
-    hp = HotPath(w, dev, cp=world, rank=rank)
+    hp = HotPath(w, dev, cp=world, rank=rank, fused=args.cp_mode == "fused")
     hp.ulysses_overlap_degree = args.overlap_degree
     self_f, cross_f = attn_flops(w)
     step_flops = (self_f + cross_f) * w["layers"]
@@ -429,7 +474,10 @@ def main():
             "steps": args.steps, "warmup": n_warm, "ms_per_step": round(ms_step, 3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": w["desc"], "name": args.workload,
-                       "parallelism": "none" if world == 1 else f"cp_ulysses{world} (overlap_degree {args.overlap_degree})",
+                       "parallelism": "none" if world == 1 else (
+                           f"cp_ulysses{world}, all-to-alls fused into the kernels' stores (NVLink peer memory), 2 barriers "
+                           f"per layer" if hp.fused else f"cp_ulysses{world}, NCCL all_to_all_single "
+                           f"(overlap_degree {args.overlap_degree})"),
                        "step": "attention hot path of one denoise forward over all layers: fused LN+RoPE prologue with "
                                "KV-cache append, range-masked self-attention, text cross-attention",
                        "tokens_q": hp.S, "layers": w["layers"],

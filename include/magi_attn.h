@@ -35,6 +35,7 @@ extern "C" {
 
 #define MAGI_HEAD_DIM 128
 #define MAGI_ROPE_DIM 96
+#define MAGI_MAX_PEERS 8 /* ranks of one context-parallel group (one NVSwitch box) */
 
 /* A (tokens, heads, 128) bf16 view. Strides are in elements. */
 typedef struct magi_view {
@@ -84,6 +85,17 @@ typedef struct magi_attn_args {
    * rearrange copy. */
   int32_t out_group_heads;
   int64_t out_group_stride;
+  /* Fused Ulysses output all-to-all (num_peers > 0): query row g (a row of ALL ranks' tokens) of local head h is
+   * stored straight into the output buffer of the rank rho that owns the row, peer_row_bounds[rho] <= g <
+   * peer_row_bounds[rho + 1], at
+   *   peer_out[rho] + (g - peer_row_bounds[rho]) * out_token_stride + (peer_head_offset + h) * out_head_stride
+   * i.e. all_to_all_output_split followed by "(cp sq) hn hd -> sq (cp hn) hd" (context_parallel.py:404-423, 596)
+   * performed by the epilogue's own stores over NVLink peer memory. `out` is then unused (may be NULL); rows outside
+   * every bound are dropped. The caller owns the cross-GPU synchronisation. */
+  int32_t num_peers;
+  int32_t peer_head_offset;
+  void* peer_out[MAGI_MAX_PEERS];
+  int64_t peer_row_bounds[MAGI_MAX_PEERS + 1];
 } magi_attn_args;
 
 MAGI_API size_t magi_attn_workspace_bytes(int32_t n_ranges);
@@ -139,6 +151,17 @@ typedef struct magi_prologue_args {
   int64_t cache_token_stride, cache_head_stride;
   int64_t cache_row_offset, cache_rows;
   int32_t head_perm_cp; /* 0/1 = identity */
+  /* Fused Ulysses input all-to-all (head_perm_cp > 1, num_peers == head_perm_cp): instead of one local send buffer,
+   * the slice of head group c is stored straight into rank c's RECEIVE buffer over NVLink peer memory,
+   *   peer_q_out[c]  + (peer_row_offset + r) * q_out_token_stride  + (h % hn) * q_out_head_stride
+   *   peer_kv_out[c] + (peer_row_offset + r) * kv_out_token_stride + (h % hn) * kv_out_head_stride (+128 for V)
+   * i.e. where all_to_all_input_split (context_parallel.py:381-401) would have delivered it; peer_row_offset is
+   * the sum of the split sizes of the ranks before this one. q_out / kv_out are then unused (may be NULL). The
+   * caller owns the cross-GPU synchronisation (all ranks' launches complete -> barrier -> consumers start). */
+  int32_t num_peers; /* 0 = off */
+  void* peer_q_out[MAGI_MAX_PEERS];
+  void* peer_kv_out[MAGI_MAX_PEERS];
+  int64_t peer_row_offset;
 } magi_prologue_args;
 
 MAGI_API int magi_qk_norm_rope_fwd(const magi_prologue_args* args, void* stream);

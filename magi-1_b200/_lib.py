@@ -28,6 +28,9 @@ EXPORTS = (
 )
 
 
+MAX_PEERS = 8   # MAGI_MAX_PEERS
+
+
 class MagiView(C.Structure):
     _fields_ = [
         ("ptr", C.c_void_p),
@@ -62,6 +65,10 @@ class MagiAttnArgs(C.Structure):
         ("num_sms", C.c_int32),
         ("out_group_heads", C.c_int32),
         ("out_group_stride", C.c_int64),
+        ("num_peers", C.c_int32),
+        ("peer_head_offset", C.c_int32),
+        ("peer_out", C.c_void_p * MAX_PEERS),
+        ("peer_row_bounds", C.c_int64 * (MAX_PEERS + 1)),
     ]
 
 
@@ -101,6 +108,10 @@ class MagiPrologueArgs(C.Structure):
         ("cache_row_offset", C.c_int64),
         ("cache_rows", C.c_int64),
         ("head_perm_cp", C.c_int32),
+        ("num_peers", C.c_int32),
+        ("peer_q_out", C.c_void_p * MAX_PEERS),
+        ("peer_kv_out", C.c_void_p * MAX_PEERS),
+        ("peer_row_offset", C.c_int64),
     ]
 
 

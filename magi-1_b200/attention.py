@@ -105,8 +105,23 @@ class FullyParallelAttention(nn.Module):
     def _allocate_key_and_value_memory(self, sequence_length, batch_size, dtype, device):
         if self.engine_config.kv_offload:
             raise NotImplementedError("kv_offload is a 'next' row (SURVEY.md section 8f-3); the cache lives in HBM")
-        return torch.empty(sequence_length * batch_size, self.num_query_groups_per_partition,
-                           2 * self.hidden_size_per_attention_head, dtype=dtype, device=device)
+        shape = (sequence_length * batch_size, self.num_query_groups_per_partition,
+                 2 * self.hidden_size_per_attention_head)
+        if self._fused_ulysses(batch_size, device):
+            # fused Ulysses: the cache lives in symmetric (NVLink peer-mapped) memory so that the other ranks'
+            # prologue kernels store their K/V rows straight into the cache slot. Collective: every rank of the
+            # group allocates its layer cache in the same forward.
+            import torch.distributed._symmetric_memory as symm
+            cache = symm.empty(shape, dtype=dtype, device=device)
+            self._cache_peer_ptrs = [int(p_) for p_ in symm.rendezvous(cache, mpu.get_cp_group().group_name).buffer_ptrs]
+            self._cache_peer_of = cache.data_ptr()
+            return cache
+        return torch.empty(shape, dtype=dtype, device=device)
+
+    def _fused_ulysses(self, batch_size, device) -> bool:
+        return (self.engine_config.cp_strategy == "cp_ulysses" and batch_size == 1
+                and getattr(self.engine_config, "cp_fused_all_to_all", False)
+                and cpm.UlyssesPeerWorkspace.available(mpu.get_cp_group(), device))
 
     def _cache(self, inference_params: InferenceParams, dtype, device):
         d = inference_params.key_value_memory_dict
@@ -353,8 +368,8 @@ class FullyParallelAttention(nn.Module):
         elif fused_proj_input:
             raise NotImplementedError("fused_proj_input is available with cp_strategy 'none'")
         elif strategy == "cp_ulysses":
-            core_attn_out, xattn_out = self._forward_ulysses(mixed_qqkv, key_value_states, inference_params, sin_emb,
-                                                             cos_emb, meta_args)
+            fwd = self._forward_ulysses_fused if self._fused_ulysses(batch_size, dev) else self._forward_ulysses
+            core_attn_out, xattn_out = fwd(mixed_qqkv, key_value_states, inference_params, sin_emb, cos_emb, meta_args)
         elif strategy == "cp_ring_kv":
             core_attn_out, xattn_out = self._forward_ring(mixed_qqkv, key_value_states, inference_params, sin_emb,
                                                           cos_emb, meta_args)
@@ -427,6 +442,53 @@ class FullyParallelAttention(nn.Module):
             self.engine_config.ulysses_overlap_degree, b, cp, split, relayout_out=relayout_out)
         self._kc = self._vc = None
         return out
+
+    # ------------------------------------------------------------------ Ulysses, all-to-alls fused into the kernels
+    def _forward_ulysses_fused(self, mixed_qqkv, key_value_states, inference_params, sin_emb, cos_emb, meta_args):
+        """dit_module.py:1175-1205 without NCCL on the data path: ONE prologue launch stores every head slice of q and
+        [K|V] straight into the owning rank's receive buffer, the attention epilogue stores every output row straight
+        into the buffer of the rank that owns the row (NVLink peer memory; include/magi_attn.h "peer" fields). Two
+        device-side barriers per layer replace three all-to-all calls and the re-layout kernel, and the transfers
+        overlap the kernels that issue them. Same values as _forward_ulysses (same kernels, same per-head inputs)."""
+        sq, b, _ = mixed_qqkv.shape
+        assert b == 1
+        cp, rank = self.engine_config.cp_size, mpu.get_cp_rank()
+        Hq, Hkv = self.model_config.num_attention_heads, self.model_config.num_query_groups
+        eps, z = self.model_config.layernorm_epsilon, self.model_config.apply_layernorm_1p
+        dev, dt = mixed_qqkv.device, mixed_qqkv.dtype
+        split = list(meta_args.cp_split_sizes)
+        total_rows = sum(split)
+        hq_loc, hkv_loc = divide(Hq, cp), self.num_query_groups_per_partition
+        ws = cpm.UlyssesPeerWorkspace.get(mpu.get_cp_group(), total_rows, max(split), hq_loc, hkv_loc, Hq, dev)
+        row_off, bounds, head_off = cpm.fused_ulysses_plan(split, rank, Hq, cp)
+        xq, xk, xv = self._project(mixed_qqkv)
+        cache, start, app = self._cache_plan(inference_params, meta_args, total_rows, dt, dev)
+        # when every row of this forward is cached, the peers store K/V straight into the cache slot
+        direct = (cache is not None and app == total_rows
+                  and getattr(self, "_cache_peer_of", None) == cache.data_ptr())
+        row_bytes = hkv_loc * 2 * F.HEAD_DIM * 2
+        kv_ptrs = [p_ + start * row_bytes for p_ in self._cache_peer_ptrs] if direct else ws.kv_ptrs
+        F.qk_norm_rope(xq, xk, xv, Hq, Hkv, self._ln(self.q_layernorm), self._ln(self.k_layernorm), sin_emb, cos_emb,
+                       batch=1, eps=eps, zero_centered_gamma=z, head_perm_cp=cp, peer_q_out=ws.q_ptrs,
+                       peer_kv_out=kv_ptrs, peer_row_offset=row_off, peer_heads=(hq_loc, hkv_loc))
+        # no communication in the cross-attention (context_parallel.py:591): its projections + norms are issued
+        # before the barrier, its attention before the second one
+        x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states)
+        ws.barrier()                                                     # A: every rank's q / kv rows have landed
+        kv = cache[start:start + total_rows] if direct else ws.kv
+        if cache is not None and app > 0 and not direct:
+            F.kv_cache_append(cache, kv, start, app)
+        kc = vc = None
+        if cache is not None and start > 0:
+            kc, vc = cache[:start, :, :F.HEAD_DIM], cache[:start, :, F.HEAD_DIM:]
+        p = meta_args.core_attn_params
+        F.attn_ranges(ws.q, kv[..., :F.HEAD_DIM], kv[..., F.HEAD_DIM:], p.q_range, p.k_range, k_cache=kc, v_cache=vc,
+                      return_lse=False, peer_out=(ws.out_ptrs, bounds, head_off, Hq))
+        xattn_out = self.cross_attention_attend(x_prepared, (sq, b), meta_args.cross_attn_params)
+        ws.barrier()                                                     # B: every rank's output rows have landed
+        # the workspace is reused by the next layer: hand out a private copy of this rank's rows
+        core_attn_out = ws.out[:split[rank]].reshape(sq, b, Hq * F.HEAD_DIM).clone()
+        return core_attn_out, xattn_out
 
     # ------------------------------------------------------------------ CSO (dit_module.py:1207-1242)
     def _forward_cso(self, mixed_qqkv, key_value_states, inference_params, sin_emb, cos_emb, meta_args):

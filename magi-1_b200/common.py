@@ -106,6 +106,9 @@ class EngineConfig:
     distill: bool = False
     kv_offload: bool = False
     enable_cuda_graph: bool = False
+    # new: under cp_ulysses, fuse both all-to-alls into the kernels' own stores over NVLink peer (symmetric) memory
+    # instead of calling NCCL (falls back to NCCL when symmetric memory is unavailable, e.g. gloo / CPU tests)
+    cp_fused_all_to_all: bool = True
 
 
 def divide(numerator: int, denominator: int) -> int:

@@ -345,6 +345,72 @@ class UlyssesScheduler:
 
 
 #####################################################
+# Ulysses with the all-to-alls fused into the kernels (NVLink peer memory)
+#####################################################
+class UlyssesPeerWorkspace:
+    """Receive buffers of the fused Ulysses path, allocated in symmetric memory (torch.distributed._symmetric_memory:
+    the same virtual layout on every rank of the group, peer-mapped over NVLink) and shared by all layers:
+
+        q   (total rows, Hq / cp, 128)     written by every rank's prologue kernel   (= all_to_all_input_split)
+        kv  (total rows, Hkv / cp, 256)    written by every rank's prologue kernel
+        out (max local rows, Hq, 128)      written by every rank's attention epilogue
+                                           (= all_to_all_output_split + "(cp sq) hn hd -> sq (cp hn) hd")
+
+    Two device-side barriers per layer order the exchange: A after the prologue (all q / kv rows have landed, and
+    every rank has consumed the previous layer's `out`), B after the attention (all `out` rows have landed, and every
+    rank is done reading q / kv). torch provides allocation, rendezvous and the barrier (plumbing); the data
+    movement is the kernels' own stores."""
+
+    _instances = {}
+
+    def __init__(self, group, total_rows: int, max_local_rows: int, hq_loc: int, hkv_loc: int, heads_q: int, device):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group
+
+        def alloc(shape):
+            t = symm.empty(shape, dtype=torch.bfloat16, device=device)
+            return t, symm.rendezvous(t, group.group_name)
+
+        self.q, self.h_q = alloc((total_rows, hq_loc, 128))
+        self.kv, self.h_kv = alloc((total_rows, hkv_loc, 256))
+        self.out, self.h_out = alloc((max_local_rows, heads_q, 128))
+        self.q_ptrs = [int(p) for p in self.h_q.buffer_ptrs]
+        self.kv_ptrs = [int(p) for p in self.h_kv.buffer_ptrs]
+        self.out_ptrs = [int(p) for p in self.h_out.buffer_ptrs]
+
+    def barrier(self) -> None:
+        """All ranks of the group, on the current stream, no host synchronisation."""
+        self.h_q.barrier(channel=0)
+
+    @classmethod
+    def get(cls, group, total_rows, max_local_rows, hq_loc, hkv_loc, heads_q, device):
+        key = (id(group), total_rows, max_local_rows, hq_loc, hkv_loc, heads_q, str(device))
+        ws = cls._instances.get(key)
+        if ws is None:     # collective: every rank reaches this with the same key at the same forward
+            ws = cls._instances[key] = cls(group, total_rows, max_local_rows, hq_loc, hkv_loc, heads_q, device)
+        return ws
+
+    @staticmethod
+    def available(group, device) -> bool:
+        if group is None or not dist.is_initialized() or torch.device(device).type != "cuda":
+            return False
+        try:
+            import torch.distributed._symmetric_memory as _symm  # noqa: F401
+            return dist.get_backend(group) == "nccl"
+        except Exception:
+            return False
+
+
+def fused_ulysses_plan(cp_split_sizes: Sequence[int], rank: int, heads_q: int, cp: int):
+    """Routing arguments of the fused path: (row offset of this rank's tokens in the receive buffers, row bounds of
+    every rank, head slot of this rank's heads in the owners' output rows)."""
+    bounds = [0]
+    for s_ in cp_split_sizes:
+        bounds.append(bounds[-1] + int(s_))
+    return bounds[rank], bounds, rank * divide(heads_q, cp)
+
+
+#####################################################
 # CSO (context shuffle overlap) attention pipeline
 #####################################################
 def cso_communication(input: torch.Tensor, cp_world_size: int, cp_split_sizes: List[int], comm_type: str = None, *,

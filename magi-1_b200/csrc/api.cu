@@ -130,7 +130,8 @@ int magi_attn_fwd(const magi_attn_args* a, void* stream_) {
   const bool by_ranges = a->q_ranges != nullptr && a->k_ranges != nullptr;
   const bool by_cu = a->cu_seqlens_q != nullptr && a->cu_seqlens_k != nullptr;
   MAGI_CHECK(by_ranges != by_cu, "give exactly one of (q_ranges,k_ranges) or (cu_seqlens_q,cu_seqlens_k)");
-  MAGI_CHECK(a->out != nullptr, "out is NULL");
+  MAGI_CHECK(a->out != nullptr || a->num_peers > 0, "out is NULL");
+  MAGI_CHECK(a->num_peers >= 0 && a->num_peers <= MAGI_MAX_PEERS, "num_peers out of range");
   MAGI_CHECK((reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && a->out_token_stride % 8 == 0 &&
                  a->out_head_stride % 8 == 0,
              "out must be 16-byte aligned with strides that are multiples of 8 elements");
@@ -183,6 +184,22 @@ int magi_attn_fwd(const magi_attn_args* a, void* stream_) {
              "out_group_heads must divide num_heads_q and out_group_stride must be a multiple of 8 elements");
   p.out_group_heads = a->out_group_heads;
   p.out_group_stride = a->out_group_stride;
+  p.num_peers = a->num_peers;
+  p.peer_head_offset = a->peer_head_offset;
+  for (int i = 0; i < 8; ++i) { p.peer_out[i] = nullptr; p.peer_bounds[i] = 0; }
+  p.peer_bounds[8] = 0;
+  if (a->num_peers > 0) {
+    MAGI_CHECK(a->out_group_heads == 0 && a->lse == nullptr, "peer output routing excludes grouped output and lse");
+    MAGI_CHECK(a->peer_head_offset >= 0, "negative peer_head_offset");
+    for (int i = 0; i < a->num_peers; ++i) {
+      MAGI_CHECK(a->peer_out[i] && (reinterpret_cast<uintptr_t>(a->peer_out[i]) & 15) == 0, "bad peer_out[%d]", i);
+      MAGI_CHECK(a->peer_row_bounds[i] <= a->peer_row_bounds[i + 1] && a->peer_row_bounds[i] >= 0,
+                 "peer_row_bounds must be non-decreasing");
+      p.peer_out[i] = a->peer_out[i];
+      p.peer_bounds[i] = a->peer_row_bounds[i];
+    }
+    p.peer_bounds[a->num_peers] = a->peer_row_bounds[a->num_peers];
+  }
 
   int sms = a->num_sms;
   if (sms <= 0) { if (int r2 = device_sm_count(&sms)) return r2; }
@@ -200,7 +217,7 @@ int magi_qk_norm_rope_fwd(const magi_prologue_args* a, void* stream_) {
   MAGI_CHECK(a->ln_dtype == 0 || a->ln_dtype == 1, "ln_dtype must be 0 (fp32) or 1 (bf16)");
   MAGI_CHECK(a->batch >= 1, "batch must be >= 1");
   if (a->x_q) {
-    MAGI_CHECK(a->q_out && a->ln_q_w && a->ln_q_b, "q path needs q_out, ln_q_w, ln_q_b");
+    MAGI_CHECK((a->q_out || a->num_peers > 0) && a->ln_q_w && a->ln_q_b, "q path needs q_out, ln_q_w, ln_q_b");
     MAGI_CHECK(a->num_heads_q > 0 && a->xq_row_stride % 8 == 0 && a->q_out_token_stride % 8 == 0 &&
                    a->q_out_head_stride % 8 == 0,
                "q strides must be multiples of 8 elements");
@@ -208,8 +225,8 @@ int magi_qk_norm_rope_fwd(const magi_prologue_args* a, void* stream_) {
   MAGI_CHECK(a->xq_head_stride % 8 == 0 && a->xk_head_stride % 8 == 0 && a->xv_head_stride % 8 == 0 &&
                  a->xq_head_stride >= 0 && a->xk_head_stride >= 0 && a->xv_head_stride >= 0,
              "input head strides must be non-negative multiples of 8 elements");
-  if (a->x_k) MAGI_CHECK(a->kv_out && a->ln_k_w && a->ln_k_b, "k path needs kv_out, ln_k_w, ln_k_b");
-  if (a->x_v) MAGI_CHECK(a->kv_out, "v path needs kv_out");
+  if (a->x_k) MAGI_CHECK((a->kv_out || a->num_peers > 0) && a->ln_k_w && a->ln_k_b, "k path needs kv_out, ln_k_w, ln_k_b");
+  if (a->x_v) MAGI_CHECK(a->kv_out || a->num_peers > 0, "v path needs kv_out");
   if (a->x_k || a->x_v)
     MAGI_CHECK(a->num_heads_kv > 0 && a->xk_row_stride % 8 == 0 && a->xv_row_stride % 8 == 0 &&
                    a->kv_out_token_stride % 8 == 0 && a->kv_out_head_stride % 8 == 0,
@@ -251,6 +268,22 @@ int magi_qk_norm_rope_fwd(const magi_prologue_args* a, void* stream_) {
   p.cache = a->cache; p.cache_token_stride = a->cache_token_stride; p.cache_head_stride = a->cache_head_stride;
   p.cache_row_offset = a->cache_row_offset; p.cache_rows = a->cache_rows;
   p.head_perm_cp = cp;
+  p.use_peers = 0;
+  p.peer_row_offset = 0;
+  for (int i = 0; i < 8; ++i) { p.peer_q[i] = nullptr; p.peer_kv[i] = nullptr; }
+  if (a->num_peers > 0) {
+    MAGI_CHECK(a->num_peers == cp && cp <= MAGI_MAX_PEERS, "num_peers must equal head_perm_cp (at most %d)", MAGI_MAX_PEERS);
+    MAGI_CHECK(a->peer_row_offset >= 0, "negative peer_row_offset");
+    for (int i = 0; i < cp; ++i) {
+      if (a->x_q) MAGI_CHECK(a->peer_q_out[i] && (reinterpret_cast<uintptr_t>(a->peer_q_out[i]) & 15) == 0, "bad peer_q_out[%d]", i);
+      if (a->x_k || a->x_v)
+        MAGI_CHECK(a->peer_kv_out[i] && (reinterpret_cast<uintptr_t>(a->peer_kv_out[i]) & 15) == 0, "bad peer_kv_out[%d]", i);
+      p.peer_q[i] = a->peer_q_out[i];
+      p.peer_kv[i] = a->peer_kv_out[i];
+    }
+    p.use_peers = 1;
+    p.peer_row_offset = a->peer_row_offset;
+  }
 
   int64_t units = 0;
   magi::prologue_units(p, &units);

@@ -443,6 +443,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     static_cast<int64_t>(it.h % p.out_group_heads) * p.out_head_stride
               : static_cast<int64_t>(it.h) * p.out_head_stride;
       __nv_bfloat16* orow = out + static_cast<int64_t>(row) * p.out_token_stride + head_off + ch * kCols;
+      bool store_ok = row_valid;
+      if (p.num_peers > 0) {
+        // fused output all-to-all: this row belongs to rank rho; store into ITS output buffer (NVLink peer memory)
+        // at the row's local index and this rank's head slot - the epilogue's stores are the transfer
+        int rho = -1;
+        for (int i = 0; i < p.num_peers; ++i)
+          if (row >= p.peer_bounds[i] && row < p.peer_bounds[i + 1]) rho = i;
+        store_ok = row_valid && rho >= 0;
+        if (store_ok)
+          orow = reinterpret_cast<__nv_bfloat16*>(p.peer_out[rho]) + (row - p.peer_bounds[rho]) * p.out_token_stride +
+                 static_cast<int64_t>(p.peer_head_offset + it.h) * p.out_head_stride + ch * kCols;
+      }
       if (it.nt > 0) {
         if constexpr (kSplit == 2) {   // total row sum = sum of the two column halves
           bar->xl[t][ch][rowq] = l;
@@ -458,7 +470,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           uint32_t orr[32];
           MAGI_TMEM_LD32(tO + c, orr, 0);
           tmem_wait_ld();
-          if (row_valid) {
+          if (store_ok) {
 #pragma unroll
             for (int k = 0; k < 32; k += 8) {
               uint4 v;
@@ -475,7 +487,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (lane == 0) mbar_arrive(&bar->o_free[t]);
         if (row_valid && ch == 0 && p.lse != nullptr)
           p.lse[static_cast<int64_t>(row) * p.Hq + it.h] = (m * scale_log2 + log2f(l)) * 0.6931471805599453f;
-      } else if (row_valid) {
+      } else if (store_ok) {
         // empty key interval: zeros / -inf (flash-attn convention for seqlen_k == 0)
 #pragma unroll
         for (int c = 0; c < kCols; c += 8) *reinterpret_cast<uint4*>(orow + c) = make_uint4(0, 0, 0, 0);

@@ -16,6 +16,11 @@ struct AttnKernelParams {
   float scale_log2;                           // softmax_scale * log2(e)
   int out_group_heads;                        // 0 = plain head stride; else grouped output addressing (magi_attn.h)
   int64_t out_group_stride;
+  // fused output all-to-all: row g of head h goes to peer_out[rho] (rho = owner of g), see magi_attn.h
+  int num_peers;
+  int peer_head_offset;
+  void* peer_out[8];
+  int64_t peer_bounds[9];
 };
 
 // workspace ints: [total_items, n, 0, 0][prefix n+1][q0 n][q1 n][k0 n][k1 n]

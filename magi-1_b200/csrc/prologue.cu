@@ -51,13 +51,6 @@ __device__ __forceinline__ float half_warp_sum(float x) {
 
 }  // namespace
 
-#ifndef MAGI_PRO_UNROLL
-#define MAGI_PRO_UNROLL 3
-#endif
-#ifndef MAGI_PRO_BLOCKS
-#define MAGI_PRO_BLOCKS 2
-#endif
-
 __device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -91,188 +84,17 @@ __device__ __forceinline__ void load_param8(const void* base, int off, uint64_t*
   }
 }
 
-// Work decomposition. A unit is (tensor, row, group of 4 * kUnroll heads); units are numbered tensor-major (all q
-// units, then k, then v) and dealt round-robin to the resident warps, so every warp streams through q, then k, then v
-// and reloads the LayerNorm affine (kept in registers as packed fp32 pairs) at most twice.
-// Inside a unit, 8 lanes own one 128-element head vector (4 heads per warp step, kUnroll steps = 8 * kUnroll
-// independent 16-byte loads per lane pair in flight): lane s < 6 holds elements [8s, 8s+8) and [48+8s, 48+8s+8) -
-// the two partners of the non-interleaved RoPE rotation sit in the same lane, so the rotation needs no shuffles -
-// and lanes 6, 7 hold the pass-through dims [96, 128). Every load/store instruction moves whole 32-byte sectors.
-// All fp32 arithmetic is packed (add/mul/fma.f32x2): the previous kernel was issue-bound (ncu: 65 % issue-active at
-// 3.7 TB/s, two thirds of its instructions integer address math), not bandwidth-bound.
-template <bool kLnBf16, bool kPerm>
-__global__ void __launch_bounds__(256, MAGI_PRO_BLOCKS) prologue_kernel(const PrologueParams p) {
-  constexpr int kUnroll = MAGI_PRO_UNROLL;
-  constexpr int kHeadsPerUnit = 4 * kUnroll;
-  const int lane = threadIdx.x & 31;
-  const int s = lane & 7;
-  const int j = lane >> 3;
-  const int e0 = s < 6 ? 8 * s : 96 + 8 * (s - 6);        // lane 6: [96,104)+[112,120), lane 7: [104,112)+[120,128)
-  const int e1 = s < 6 ? 48 + 8 * s : 112 + 8 * (s - 6);
-  const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const bool rot = p.sin != nullptr && s < 6;
-  const uint32_t rows = static_cast<uint32_t>(p.rows);
-  const uint32_t upr_q = (p.Hq + kHeadsPerUnit - 1) / kHeadsPerUnit;
-  const uint32_t upr_kv = (p.Hkv + kHeadsPerUnit - 1) / kHeadsPerUnit;
-  const uint32_t n_q = p.x_q != nullptr ? rows * upr_q : 0u;
-  const uint32_t n_k = p.x_k != nullptr ? rows * upr_kv : 0u;
-  const uint32_t n_v = p.x_v != nullptr ? rows * upr_kv : 0u;
-  const uint32_t total = n_q + n_k + n_v;
-
-  int cur_type = -1;
-  uint64_t w2[8], b2[8];
-  const uint64_t one2 = pack_f2(1.f, 1.f);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { w2[i] = one2; b2[i] = 0; }
-
-#pragma unroll 1
-  for (uint32_t unit = warp_id; unit < total; unit += warps_total) {
-    const int type = unit < n_q ? 0 : (unit < n_q + n_k ? 1 : 2);   // 0 = q, 1 = k, 2 = v
-    const uint32_t local = unit - (type == 0 ? 0u : type == 1 ? n_q : n_q + n_k);
-    const uint32_t upr = type == 0 ? upr_q : upr_kv;
-    const uint32_t r = upr == 1 ? local : local / upr;
-    const int h_first = static_cast<int>(local - r * upr) * kHeadsPerUnit + j;
-    const int H = type == 0 ? p.Hq : p.Hkv;
-
-    if (type != cur_type) {
-      cur_type = type;
-      if (type != 2) {
-        const void* w = type == 0 ? p.ln_q_w : p.ln_k_w;
-        const void* b = type == 0 ? p.ln_q_b : p.ln_k_b;
-        load_param8<kLnBf16>(w, e0, w2); load_param8<kLnBf16>(w, e1, w2 + 4);
-        load_param8<kLnBf16>(b, e0, b2); load_param8<kLnBf16>(b, e1, b2 + 4);
-        if (p.zero_centered_gamma != 0) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            w2[i] = fadd2(w2[i], one2);
-            // bf16 parameters: the reference computes `self.weight + 1` in bf16, i.e. rounds the sum
-            if constexpr (kLnBf16) w2[i] = bf2_to_f2(f2_to_bf2(w2[i]));
-          }
-        }
-      }
-    }
-
-    const int64_t rstride = type == 0 ? p.xq_row_stride : type == 1 ? p.xk_row_stride : p.xv_row_stride;
-    const int64_t hstride = type == 0 ? p.xq_head_stride : type == 1 ? p.xk_head_stride : p.xv_head_stride;
-    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(type == 0 ? p.x_q : type == 1 ? p.x_k : p.x_v) +
-                               r * rstride + h_first * hstride;
-    uint4 ra[kUnroll], rb[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      ra[u] = make_uint4(0, 0, 0, 0);
-      rb[u] = make_uint4(0, 0, 0, 0);
-      if (h_first + 4 * u < H) {
-        ra[u] = ld_stream(src + 4 * u * hstride + e0);
-        rb[u] = ld_stream(src + 4 * u * hstride + e1);
-      }
-    }
-
-    uint64_t cs2[4], sn2[4], nsn2[4];
-    if (type != 2 && rot) {
-      const uint32_t trow = p.batch == 1 ? r : r / static_cast<uint32_t>(p.batch);
-      const float4* c = reinterpret_cast<const float4*>(p.cos + static_cast<int64_t>(trow) * 48 + 8 * s);
-      const float4* sp = reinterpret_cast<const float4*>(p.sin + static_cast<int64_t>(trow) * 48 + 8 * s);
-      const float4 c0 = c[0], c1 = c[1], s0 = sp[0], s1 = sp[1];
-      cs2[0] = pack_f2(c0.x, c0.y); cs2[1] = pack_f2(c0.z, c0.w); cs2[2] = pack_f2(c1.x, c1.y); cs2[3] = pack_f2(c1.z, c1.w);
-      sn2[0] = pack_f2(s0.x, s0.y); sn2[1] = pack_f2(s0.z, s0.w); sn2[2] = pack_f2(s1.x, s1.y); sn2[3] = pack_f2(s1.z, s1.w);
-      nsn2[0] = pack_f2(-s0.x, -s0.y); nsn2[1] = pack_f2(-s0.z, -s0.w);
-      nsn2[2] = pack_f2(-s1.x, -s1.y); nsn2[3] = pack_f2(-s1.z, -s1.w);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { cs2[i] = one2; sn2[i] = 0; nsn2[i] = 0; }
-    }
-
-    // destination bases of this (row, tensor): q_out, or the K / V half of the packed kv row (and of the cache row)
-    __nv_bfloat16* out_base = type == 0 ? reinterpret_cast<__nv_bfloat16*>(p.q_out)
-                                        : reinterpret_cast<__nv_bfloat16*>(p.kv_out) + (type == 2 ? 128 : 0);
-    const int64_t out_tstride = type == 0 ? p.q_out_token_stride : p.kv_out_token_stride;
-    const int64_t out_hstride = type == 0 ? p.q_out_head_stride : p.kv_out_head_stride;
-    __nv_bfloat16* cache_row = nullptr;
-    if constexpr (!kPerm) {
-      if (type != 0 && p.cache != nullptr && static_cast<int64_t>(r) < p.cache_rows)
-        cache_row = reinterpret_cast<__nv_bfloat16*>(p.cache) + (p.cache_row_offset + r) * p.cache_token_stride +
-                    (type == 2 ? 128 : 0);
-    }
-
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int h = h_first + 4 * u;
-      if (h - j >= H) break;            // warp-uniform: the whole step is past the last head
-      uint4 pa = ra[u], pb = rb[u];
-      if (type != 2) {
-        uint64_t v[8];
-        v[0] = bf2_to_f2(pa.x); v[1] = bf2_to_f2(pa.y); v[2] = bf2_to_f2(pa.z); v[3] = bf2_to_f2(pa.w);
-        v[4] = bf2_to_f2(pb.x); v[5] = bf2_to_f2(pb.y); v[6] = bf2_to_f2(pb.z); v[7] = bf2_to_f2(pb.w);
-        // ---- LayerNorm over 128 in fp32 (two-pass, biased variance)
-        float lo, hi;
-        unpack_f2(fadd2(fadd2(fadd2(v[0], v[1]), fadd2(v[2], v[3])), fadd2(fadd2(v[4], v[5]), fadd2(v[6], v[7]))), lo, hi);
-        const float mean = quarter_warp_sum(lo + hi) * (1.0f / 128.0f);
-        const uint64_t mean2 = pack_f2(mean, mean);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = fsub2(v[i], mean2);
-        uint64_t sq_a = fmul2(v[0], v[0]), sq_b = fmul2(v[1], v[1]);
-#pragma unroll
-        for (int i = 2; i < 8; i += 2) { sq_a = ffma2(v[i], v[i], sq_a); sq_b = ffma2(v[i + 1], v[i + 1], sq_b); }
-        unpack_f2(fadd2(sq_a, sq_b), lo, hi);
-        const float var = quarter_warp_sum(lo + hi) * (1.0f / 128.0f);
-        const float rstd = rsqrtf(var + p.eps);   // MUFU.RSQ (2 ulp in fp32: invisible after the bf16 rounding)
-        const uint64_t rstd2 = pack_f2(rstd, rstd);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = ffma2(fmul2(v[i], rstd2), w2[i], b2[i]);
-        // ---- NeoX RoPE: (x1, x2) -> (x1 cos - x2 sin, x2 cos + x1 sin); identity on lanes 6, 7 (cos 1, sin 0)
-        if (rot) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint64_t x1 = v[i], x2 = v[4 + i];
-            v[i] = ffma2(x1, cs2[i], fmul2(x2, nsn2[i]));
-            v[4 + i] = ffma2(x2, cs2[i], fmul2(x1, sn2[i]));
-          }
-        }
-        pa = make_uint4(f2_to_bf2(v[0]), f2_to_bf2(v[1]), f2_to_bf2(v[2]), f2_to_bf2(v[3]));
-        pb = make_uint4(f2_to_bf2(v[4]), f2_to_bf2(v[5]), f2_to_bf2(v[6]), f2_to_bf2(v[7]));
-      }
-      if (h >= H) continue;
-
-      // ---- stores: attention (or all-to-all send) layout, plus the fused KV-cache append
-      auto store = [&](__nv_bfloat16* dst) {
-        *reinterpret_cast<uint4*>(dst + e0) = pa;
-        *reinterpret_cast<uint4*>(dst + e1) = pb;
-      };
-      if constexpr (!kPerm) {
-        store(out_base + r * out_tstride + h * out_hstride);
-        if (cache_row != nullptr) store(cache_row + h * p.cache_head_stride);
-      } else {
-        const int cp = p.head_perm_cp;
-        if (type == 0) {
-          const int hn = p.Hq / cp;
-          store(out_base + (static_cast<int64_t>(h / hn) * rows + r) * out_tstride +
-                static_cast<int64_t>(h % hn) * out_hstride);
-        } else if (cp > p.Hkv) {
-          // fewer kv heads than ranks: replicate (repeat_interleave, context_parallel.py:393-394)
-          const int rep = cp / p.Hkv;
-          for (int c = h * rep; c < (h + 1) * rep; ++c)
-            store(out_base + (static_cast<int64_t>(c) * rows + r) * out_tstride);
-        } else {
-          const int hn = p.Hkv / cp;
-          store(out_base + (static_cast<int64_t>(h / hn) * rows + r) * out_tstride +
-                static_cast<int64_t>(h % hn) * out_hstride);
-        }
-      }
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
-// Ring version (default): the same arithmetic, but the loads are taken off the compute warps. One producer warp per
+// Fused prologue. The loads are taken off the compute warps: one producer warp per
 // CTA streams "super-units" (kGroup consecutive work units of one tensor; a unit = (row, group of 8 heads) = 2 KB)
 // into a shared-memory ring with cp.async.bulk - ONE 8 KB bulk copy per super-unit when the projection output is
 // dense, one copy per head otherwise - completing on an mbarrier per stage. kConsumers warps pick the units up
 // (warp w takes unit w % kGroup of every (w / kGroup)-th super-unit), read them with conflict-free LDS.128, normalise /
 // rotate in packed fp32 and store straight to global memory. The bytes in flight are set by the ring depth (stages x
-// 8 KB x CTAs per SM), not by the register budget of the compute warps: the register version above tops out at
-// 16 warps x 3 KB per SM (124 registers) and 78 % of the measured copy bandwidth. A first ring with one 2 KB copy
-// per barrier was producer-bound (~50 cycles of serial issue latency per copy; profiles/README.md).
+// 8 KB x CTAs per SM), not by the register budget of the compute warps: a register-only version of the same math
+// topped out at 16 warps x 3 KB per SM (124 registers) and 78 % of the measured copy bandwidth, and a first ring with
+// one 2 KB copy per barrier was producer-bound (~50 cycles of serial issue latency per copy); profiles/README.md.
+// All fp32 arithmetic is packed (add/mul/fma.f32x2), 8 lanes own one head vector.
 #ifndef MAGI_PRO_STAGES
 #define MAGI_PRO_STAGES 10
 #endif
@@ -523,20 +345,27 @@ __global__ void __launch_bounds__(kRingThreads, MAGI_PRO_RING_BLOCKS) prologue_r
           store(out_base + r * out_tstride + h * out_hstride);
           if (cache_row != nullptr) store(cache_row + h * p.cache_head_stride);
         } else {
+          // all-to-all SEND layout "(cp seq) hn hd" in one local buffer, or - fused all-to-all - straight into the
+          // receive buffer of the rank that owns the head slice, at this rank's row offset (NVLink peer stores)
           const int cp = p.head_perm_cp;
+          auto dest = [&](int c) -> __nv_bfloat16* {
+            if (p.use_peers != 0) {
+              __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(type == 0 ? p.peer_q[c] : p.peer_kv[c]) +
+                                    (type == 2 ? 128 : 0);
+              return base + (p.peer_row_offset + r) * out_tstride;
+            }
+            return out_base + (static_cast<int64_t>(c) * rows + r) * out_tstride;
+          };
           if (type == 0) {
             const int hn = p.Hq / cp;
-            store(out_base + (static_cast<int64_t>(h / hn) * rows + r) * out_tstride +
-                  static_cast<int64_t>(h % hn) * out_hstride);
+            store(dest(h / hn) + static_cast<int64_t>(h % hn) * out_hstride);
           } else if (cp > p.Hkv) {
             // fewer kv heads than ranks: replicate (repeat_interleave, context_parallel.py:393-394)
             const int rep = cp / p.Hkv;
-            for (int c = h * rep; c < (h + 1) * rep; ++c)
-              store(out_base + (static_cast<int64_t>(c) * rows + r) * out_tstride);
+            for (int c = h * rep; c < (h + 1) * rep; ++c) store(dest(c));
           } else {
             const int hn = p.Hkv / cp;
-            store(out_base + (static_cast<int64_t>(h / hn) * rows + r) * out_tstride +
-                  static_cast<int64_t>(h % hn) * out_hstride);
+            store(dest(h / hn) + static_cast<int64_t>(h % hn) * out_hstride);
           }
         }
       }
@@ -647,18 +476,13 @@ cudaError_t cso_unshuffle_launch(void* dst, int64_t dst_stride, const void* src,
   return cudaGetLastError();
 }
 
-#ifndef MAGI_PRO_RING
-#define MAGI_PRO_RING 1
-#endif
 int prologue_units(const PrologueParams& p, int64_t* units) {
-  constexpr int kHeadsPerUnit = MAGI_PRO_RING ? kRingUnitHeads : 4 * MAGI_PRO_UNROLL;
-  const int64_t upr_q = (p.Hq + kHeadsPerUnit - 1) / kHeadsPerUnit, upr_kv = (p.Hkv + kHeadsPerUnit - 1) / kHeadsPerUnit;
+  const int64_t upr_q = (p.Hq + kRingUnitHeads - 1) / kRingUnitHeads, upr_kv = (p.Hkv + kRingUnitHeads - 1) / kRingUnitHeads;
   *units = p.rows * ((p.x_q ? upr_q : 0) + (p.x_k ? upr_kv : 0) + (p.x_v ? upr_kv : 0));
-  return MAGI_PRO_RING ? MAGI_PRO_RING_BLOCKS : MAGI_PRO_BLOCKS;
+  return MAGI_PRO_RING_BLOCKS;
 }
 template <bool kLnBf16, bool kPerm>
 static cudaError_t prologue_launch_t(const PrologueParams& p, int64_t units, int sms, cudaStream_t stream) {
-#if MAGI_PRO_RING
   static bool attr_set = false;   // per template instance; idempotent
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(prologue_ring_kernel<kLnBf16, kPerm>,
@@ -666,18 +490,12 @@ static cudaError_t prologue_launch_t(const PrologueParams& p, int64_t units, int
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  // persistent: one CTA per resident slot; a CTA needs at least one unit
+  // persistent: one CTA per resident slot; a CTA needs at least one super-unit per consumer group
   int64_t blocks = static_cast<int64_t>(sms) * MAGI_PRO_RING_BLOCKS;
   const int64_t need = (units / kRingGroup + kRingConsumerGroups) / kRingConsumerGroups;
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
   prologue_ring_kernel<kLnBf16, kPerm><<<static_cast<int>(blocks), kRingThreads, kRingSmemBytes, stream>>>(p);
-#else
-  int64_t blocks = (units + 7) / 8;
-  if (blocks > static_cast<int64_t>(sms) * MAGI_PRO_BLOCKS) blocks = static_cast<int64_t>(sms) * MAGI_PRO_BLOCKS;
-  if (blocks < 1) blocks = 1;
-  prologue_kernel<kLnBf16, kPerm><<<static_cast<int>(blocks), 256, 0, stream>>>(p);
-#endif
   return cudaGetLastError();
 }
 cudaError_t prologue_launch(const PrologueParams& p, bool ln_bf16, int sms, cudaStream_t stream) {

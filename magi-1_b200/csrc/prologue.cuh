@@ -20,6 +20,10 @@ struct PrologueParams {
   void* kv_out; int64_t kv_out_token_stride, kv_out_head_stride;
   void* cache; int64_t cache_token_stride, cache_head_stride, cache_row_offset, cache_rows;
   int head_perm_cp;
+  // fused all-to-all: per destination rank receive buffers (same strides as q_out / kv_out), this rank's row offset
+  int use_peers;
+  void* peer_q[8]; void* peer_kv[8];
+  int64_t peer_row_offset;
 };
 
 // number of work units of a launch (-> *units) and the resident 256-thread CTAs per SM the kernel is built for

@@ -15,7 +15,7 @@ No CPU fallback: every function requires CUDA tensors and the built extension.
 """
 import ctypes as C
 import math
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 
@@ -70,8 +70,14 @@ def attn_ranges(
     zero_fill: bool = False,
     num_sms: int = 0,
     proj_input: Optional[Tuple[torch.Tensor, int, int]] = None,
+    peer_out: Optional[Tuple[Sequence[int], Sequence[int], int, int]] = None,
 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Range-masked attention over keys = concat(k_cache, k_new) without materialising the concatenation.
+
+    peer_out = (pointers, row_bounds, head_offset, heads_total): fused Ulysses output all-to-all. Query row g of
+    local head h is stored into the (rows_rho, heads_total, 128) bf16 buffer at pointers[rho] of the rank rho with
+    row_bounds[rho] <= g < row_bounds[rho + 1], at row g - row_bounds[rho], head head_offset + h (NVLink peer
+    memory; include/magi_attn.h). Returns (None, None); the caller synchronises the ranks.
 
     proj_input = (buffer, n, hn): instead of a (Tq, Hq, 128) tensor, write the result straight into the reference's
     out-projection input `buffer` (Tq, 2 * Hq * 128), laid out "(hn n hd)" with n = 0 for self-attention and n = 1
@@ -133,16 +139,23 @@ def attn_ranges(
         group_stride = 2 * group_heads * HEAD_DIM
         out_ptr = buf.data_ptr() + n_src * group_heads * HEAD_DIM * 2
         out_ts, out_hs = buf.stride(0), HEAD_DIM
+    elif peer_out is not None:
+        if out is not None or return_lse:
+            raise ValueError("peer_out excludes out and return_lse")
+        ptrs, bounds, head_off, heads_total = peer_out
+        if len(ptrs) > _lib.MAX_PEERS or len(bounds) != len(ptrs) + 1:
+            raise ValueError("peer_out needs at most 8 pointers and one more row bound than pointers")
+        out_ptr, out_ts, out_hs = None, heads_total * HEAD_DIM, HEAD_DIM
     elif out is None:
         out = (torch.zeros if zero_fill else torch.empty)((Tq, Hq, HEAD_DIM), dtype=torch.bfloat16, device=q.device)
     else:
         _check_thd(out, "out")
         if out.shape != q.shape:
             raise ValueError("out must have the shape of q")
-    if proj_input is None:
-        out_ptr, out_ts, out_hs = out.data_ptr(), out.stride(0), out.stride(1)
-    else:
+    if proj_input is not None:
         out = proj_input[0]
+    elif peer_out is None:
+        out_ptr, out_ts, out_hs = out.data_ptr(), out.stride(0), out.stride(1)
     lse = None
     if return_lse:
         lse = torch.full((Tq, Hq), float("-inf"), dtype=torch.float32, device=q.device) if zero_fill else torch.empty(
@@ -170,6 +183,12 @@ def attn_ranges(
     a.softmax_scale = float(softmax_scale) if softmax_scale is not None else -1.0
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 4
     a.num_sms = num_sms
+    if peer_out is not None:
+        a.num_peers, a.peer_head_offset = len(ptrs), head_off
+        for i, ptr in enumerate(ptrs):
+            a.peer_out[i] = ptr
+        for i, b_ in enumerate(bounds):
+            a.peer_row_bounds[i] = int(b_)
     with torch.cuda.device(q.device):
         _lib.check(L.magi_attn_fwd(C.byref(a), _stream()), "magi_attn_fwd")
     return out, lse
@@ -271,6 +290,10 @@ def qk_norm_rope(
     cache_row_offset: int = 0,
     cache_rows: int = 0,
     head_perm_cp: int = 1,
+    peer_q_out: Optional[Sequence[int]] = None,
+    peer_kv_out: Optional[Sequence[int]] = None,
+    peer_row_offset: int = 0,
+    peer_heads: Optional[Tuple[int, int]] = None,
 ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """Fused per-head LayerNorm(w+1, b) -> NeoX RoPE on 96 of 128 dims -> bf16, writing q in attention layout and
     [K|V] packed (rows, Hkv, 256), optionally also appending to the KV cache (dit_module.py:953-996, 918-929).
@@ -280,6 +303,9 @@ def qk_norm_rope(
     sin/cos: (rows // batch, 48) fp32, or None to skip RoPE (dit_module.py:1005-1021).
     With head_perm_cp = cp > 1 the outputs are laid out "(cp seq) hn hd", i.e. ready to be the all-to-all send buffer
     (context_parallel.py:393-396), including KV-head replication when cp > Hkv.
+    With peer_q_out / peer_kv_out (head_perm_cp device pointers each) the all-to-all itself is fused: head slice c is
+    stored straight into rank c's receive buffer ((all rows, peer_heads[0], 128) resp. (all rows, peer_heads[1], 256))
+    at row peer_row_offset + r over NVLink peer memory (include/magi_attn.h); nothing is returned for that tensor.
     """
     ref = next(t for t in (x_q, x_k, x_v) if t is not None)
     dev = ref.device
@@ -316,9 +342,16 @@ def qk_norm_rope(
             raise ValueError(f"sin/cos must have shape ({rows // max(batch, 1)}, 48), got {tuple(sin.shape)}")
         sin, cos = sin.contiguous(), cos.contiguous()
 
-    if x_q is not None and q_out is None:
+    use_peers = peer_q_out is not None or peer_kv_out is not None
+    if use_peers:
+        if cp <= 1 or peer_heads is None:
+            raise ValueError("peer routing needs head_perm_cp > 1 and peer_heads")
+        if (x_q is not None and (peer_q_out is None or len(peer_q_out) != cp)) or (
+                (x_k is not None or x_v is not None) and (peer_kv_out is None or len(peer_kv_out) != cp)):
+            raise ValueError("peer pointer lists must have head_perm_cp entries")
+    if x_q is not None and q_out is None and not use_peers:
         q_out = torch.empty((rows * cp, num_heads_q // cp, HEAD_DIM), dtype=torch.bfloat16, device=dev)
-    if (x_k is not None or x_v is not None) and kv_out is None:
+    if (x_k is not None or x_v is not None) and kv_out is None and not use_peers:
         hn_kv = max(1, num_heads_kv // cp) if cp > 1 else num_heads_kv
         kv_out = torch.empty((rows * cp, hn_kv, 2 * HEAD_DIM), dtype=torch.bfloat16, device=dev)
 
@@ -353,6 +386,13 @@ def qk_norm_rope(
         a.cache_token_stride, a.cache_head_stride = cache.stride(0), cache.stride(1)
         a.cache_row_offset, a.cache_rows = cache_row_offset, cache_rows
     a.head_perm_cp = cp
+    if use_peers:
+        a.num_peers, a.peer_row_offset = cp, peer_row_offset
+        a.q_out_token_stride, a.q_out_head_stride = peer_heads[0] * HEAD_DIM, HEAD_DIM
+        a.kv_out_token_stride, a.kv_out_head_stride = peer_heads[1] * 2 * HEAD_DIM, 2 * HEAD_DIM
+        for i in range(cp):
+            a.peer_q_out[i] = peer_q_out[i] if peer_q_out is not None else None
+            a.peer_kv_out[i] = peer_kv_out[i] if peer_kv_out is not None else None
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().magi_qk_norm_rope_fwd(C.byref(a), _stream()), "magi_qk_norm_rope_fwd")
     return q_out, kv_out

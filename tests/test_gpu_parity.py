@@ -299,6 +299,47 @@ def _build_module(g, cp_strategy="none"):
     return attn.cuda().eval()
 
 
+@pytest.mark.parametrize("cp,Hq,Hkv", [(4, 8, 4), (4, 8, 2), (2, 6, 2), (8, 8, 1)])
+def test_fused_all_to_all_routing_on_virtual_ranks(F, cp, Hq, Hkv):
+    """The peer-memory routing of the fused Ulysses all-to-alls, exercised on ONE device: every "rank" is a set of
+    local buffers whose addresses are handed to the kernels as peer pointers. The prologue must deliver exactly what
+    all_to_all_input_split delivers (context_parallel.py:381-401, incl. KV-head replication), the attention
+    epilogue exactly all_to_all_output_split + "(cp sq) hn hd -> sq (cp hn) hd" (:404-423, 596): bit-exact against the
+    single-rank run of the same kernels."""
+    clip, dn = 150, 3
+    S = clip * dn
+    split = [S // cp + (1 if i < S % cp else 0) for i in range(cp)]
+    offs = np.concatenate([[0], np.cumsum(split)]).astype(np.int64)
+    xq, xk, xv = bf(rnd((S, Hq * 128), 1)), bf(rnd((S, Hkv * 128), 2)), bf(rnd((S, Hkv * 128), 3))
+    ln = [torch.from_numpy(rnd((128,), 10 + i, 0.2)).cuda() for i in range(4)]
+    ang = torch.from_numpy(rnd((S, 48), 20, 3.0))
+    sin, cos = torch.sin(ang).cuda(), torch.cos(ang).cuda()
+    q_ranges = i32([[i * clip, (i + 1) * clip] for i in range(dn)])
+    k_ranges = i32([[0, clip], [0, 2 * clip], [clip, 3 * clip]])
+    q_full, kv_full = F.qk_norm_rope(xq, xk, xv, Hq, Hkv, (ln[0], ln[1]), (ln[2], ln[3]), sin, cos)
+    out_full, _ = F.attn_ranges(q_full, kv_full[..., :128], kv_full[..., 128:], q_ranges, k_ranges)
+    hn, hkv_loc = Hq // cp, max(1, Hkv // cp)
+    recv_q = [torch.zeros(S, hn, 128, dtype=torch.bfloat16, device="cuda") for _ in range(cp)]
+    recv_kv = [torch.zeros(S, hkv_loc, 256, dtype=torch.bfloat16, device="cuda") for _ in range(cp)]
+    for me in range(cp):
+        sl = slice(int(offs[me]), int(offs[me + 1]))
+        F.qk_norm_rope(xq[sl], xk[sl], xv[sl], Hq, Hkv, (ln[0], ln[1]), (ln[2], ln[3]), sin[sl], cos[sl],
+                       head_perm_cp=cp, peer_q_out=[t.data_ptr() for t in recv_q],
+                       peer_kv_out=[t.data_ptr() for t in recv_kv], peer_row_offset=int(offs[me]),
+                       peer_heads=(hn, hkv_loc))
+    rep = cp // Hkv if cp > Hkv else 1
+    for c in range(cp):
+        assert torch.equal(recv_q[c], q_full[:, c * hn:(c + 1) * hn])
+        k_lo = c // rep if cp > Hkv else c * hkv_loc
+        assert torch.equal(recv_kv[c], kv_full[:, k_lo:k_lo + hkv_loc])
+    out_recv = [torch.zeros(split[r], Hq, 128, dtype=torch.bfloat16, device="cuda") for r in range(cp)]
+    for c in range(cp):
+        o, l = F.attn_ranges(recv_q[c], recv_kv[c][..., :128], recv_kv[c][..., 128:], q_ranges, k_ranges,
+                             return_lse=False, peer_out=([t.data_ptr() for t in out_recv], offs.tolist(), c * hn, Hq))
+        assert o is None and l is None
+    assert torch.equal(torch.cat(out_recv, 0), out_full)
+
+
 def test_cso_unshuffle_and_full_attention(F):
     """CSO pieces with the real kernels: the receive-side gather "(cp dn spb) -> dn (cp spb)"[:, :clip]
     (dit_module.py:1215-1224) is bit exact and can land in the KV-cache slot; full_attention on the padded query

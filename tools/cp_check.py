@@ -36,8 +36,8 @@ def main():
 
     def build(strategy, cp):
         torch.manual_seed(1234)
-        m = FullyParallelAttention(mc, EngineConfig(cp_size=cp, cp_strategy=strategy, ulysses_overlap_degree=overlap),
-                                   layer_number=1)
+        m = FullyParallelAttention(mc, EngineConfig(cp_size=cp, cp_strategy=strategy, ulysses_overlap_degree=overlap,
+                                                    cp_fused_all_to_all=fused), layer_number=1)
         g = torch.Generator().manual_seed(99)
         with torch.no_grad():
             for n, p in m.named_parameters():
@@ -79,7 +79,8 @@ def main():
     for strategy in ("cp_ulysses", "cp_shuffle_overlap", "cp_ring_kv"):
         kv_loc = max(1, Hkv // world)
         second = kv_loc if kv_loc > 1 else 3      # whole kv heads per group, or 3 q-head groups in the MQA case
-        for overlap in ((1, second) if strategy == "cp_ulysses" else (1,)):
+        # cp_ulysses: all-to-alls fused into the kernels (NVLink peer stores), then the NCCL path at two overlap degrees
+        for overlap, fused in (((1, True), (1, False), (second, False)) if strategy == "cp_ulysses" else ((1, False),)):
             ref_m, cp_m = build("none", 1), build(strategy, world)
             inf_ref = InferenceParams(1, 5 * clip)
             inf_cp = InferenceParams(1, 5 * clip)
@@ -109,7 +110,7 @@ def main():
                 xo = cpm.cp_post_process(world, strategy, xo.contiguous(), m_cp)
                 worst["core"] = max(worst["core"], (core.float() - ref_core.float()).abs().max().item())
                 worst["xattn"] = max(worst["xattn"], (xo.float() - ref_x.float()).abs().max().item())
-            results[f"{strategy}/overlap{overlap}"] = worst
+            results[f"{strategy}/{'fused-p2p' if fused else 'nccl'}/overlap{overlap}"] = worst
     torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:
@@ -125,5 +126,5 @@ def main():
 
 
 if __name__ == "__main__":
-    overlap = 1
+    overlap, fused = 1, False
     main()
