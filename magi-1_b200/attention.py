@@ -65,6 +65,89 @@ class CustomLayerNormLinear(nn.Module):
         return self.v(x)
 
 
+class KVOffload:
+    """kv_offload (config.py:106, dit_module.py:803-811, 914-929): the per-layer KV caches live in pinned host memory.
+    The reference copies the cache prefix to the GPU synchronously inside every layer's forward
+    (`inference_key_and_value_memory[:sequence_start].cuda()`) and slice-assigns the new rows back.
+    Here one manager per generation (kept on the InferenceParams) moves both directions on a copy stream:
+      * prefix(layer): the device copy of cache[:start]. While layer L computes, the prefix of layer L + 1 is already
+        on its way into the other of two staging buffers (the layers run in order, dit_module.py:1425-1440), so
+        after the first layer the H2D transfer is off the critical path;
+      * store(layer): the new rows go back device -> host asynchronously after the kernels that produced them;
+        any later read of that layer's cache waits for the write-back event."""
+
+    def __init__(self, device):
+        self.device = device
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.stage = [None, None]          # ping-pong device staging buffers (rows, Hkv, 256)
+        self.prefetched = {}               # layer -> (buffer index, rows, event)
+        self.written = {}                  # layer -> event of the last device -> host write-back
+        self.h2d_bytes = self.d2h_bytes = self.prefetch_hits = 0
+
+    @classmethod
+    def of(cls, inference_params: InferenceParams, device) -> "KVOffload":
+        st = getattr(inference_params, "kv_offload_state", None)
+        if st is None:
+            st = inference_params.kv_offload_state = cls(device)
+        return st
+
+    def _buffer(self, i: int, like: torch.Tensor, rows: int) -> torch.Tensor:
+        b = self.stage[i]
+        if b is None or b.shape[0] < rows or b.shape[1:] != like.shape[1:]:
+            b = self.stage[i] = torch.empty((max(rows, like.shape[0]),) + tuple(like.shape[1:]), dtype=like.dtype,
+                                            device=self.device)
+        return b
+
+    def _h2d(self, layer: int, cache: torch.Tensor, rows: int, buf_index: int, stream) -> torch.Tensor:
+        buf = self._buffer(buf_index, cache, rows)
+        with torch.cuda.stream(stream):
+            if layer in self.written:
+                stream.wait_event(self.written[layer])
+            buf[:rows].copy_(cache[:rows], non_blocking=True)
+        self.h2d_bytes += rows * cache[0].numel() * cache.element_size()
+        return buf
+
+    def prefix(self, layer: int, cache: torch.Tensor, rows: int, next_layer_cache: Optional[torch.Tensor]):
+        """Device view of cache[:rows] for `layer`, and kick the prefetch of the next layer's prefix."""
+        cur = torch.cuda.current_stream(self.device)
+        hit = self.prefetched.pop(layer, None)
+        if hit is not None and hit[1] == rows:
+            cur.wait_event(hit[2])
+            idx = hit[0]
+            buf = self.stage[idx]
+            self.prefetch_hits += 1
+        else:
+            idx = layer & 1
+            buf = self._h2d(layer, cache, rows, idx, cur)
+        if next_layer_cache is not None and rows > 0:
+            # the other staging buffer was last read by the previous layer's attention, which the compute stream has
+            # already been given: order the copy stream behind it
+            self.copy_stream.wait_stream(cur)
+            self._h2d(layer + 1, next_layer_cache, rows, idx ^ 1, self.copy_stream)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+            self.prefetched[layer + 1] = (idx ^ 1, rows, ev)
+        return buf[:rows]
+
+    def store(self, layer: int, cache: torch.Tensor, kv_new: torch.Tensor, row_offset: int, rows: int) -> None:
+        """cache[row_offset : row_offset + rows] = kv_new[:rows], device -> pinned host, asynchronously."""
+        if rows <= 0:
+            return
+        cur = torch.cuda.current_stream(self.device)
+        self.copy_stream.wait_stream(cur)
+        kv_new.record_stream(self.copy_stream)
+        with torch.cuda.stream(self.copy_stream):
+            cache[row_offset:row_offset + rows].copy_(kv_new[:rows], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(self.copy_stream)
+        self.written[layer] = ev
+        self.prefetched.pop(layer, None)   # a staged copy of this layer is stale now
+        self.d2h_bytes += rows * cache[0].numel() * cache.element_size()
+
+    def synchronize(self) -> None:
+        self.copy_stream.synchronize()
+
+
 class FullyParallelAttention(nn.Module):
     def __init__(self, model_config: ModelConfig, engine_config: EngineConfig, layer_number: int):
         super().__init__()
@@ -103,10 +186,11 @@ class FullyParallelAttention(nn.Module):
 
     # ------------------------------------------------------------------ KV cache (dit_module.py:800-819, 891-946)
     def _allocate_key_and_value_memory(self, sequence_length, batch_size, dtype, device):
-        if self.engine_config.kv_offload:
-            raise NotImplementedError("kv_offload is a 'next' row (SURVEY.md section 8f-3); the cache lives in HBM")
         shape = (sequence_length * batch_size, self.num_query_groups_per_partition,
                  2 * self.hidden_size_per_attention_head)
+        if self.engine_config.kv_offload:
+            # dit_module.py:803-811: the cache lives in pinned host memory; see KVOffload for how it is staged
+            return torch.empty(shape, dtype=dtype, device="cpu", pin_memory=True)
         if self._fused_ulysses(batch_size, device):
             # fused Ulysses: the cache lives in symmetric (NVLink peer-mapped) memory so that the other ranks'
             # prologue kernels store their K/V rows straight into the cache slot. Collective: every rank of the
@@ -119,7 +203,7 @@ class FullyParallelAttention(nn.Module):
         return torch.empty(shape, dtype=dtype, device=device)
 
     def _fused_ulysses(self, batch_size, device) -> bool:
-        return (self.engine_config.cp_strategy == "cp_ulysses" and batch_size == 1
+        return (self.engine_config.cp_strategy == "cp_ulysses" and batch_size == 1 and not self.engine_config.kv_offload
                 and getattr(self.engine_config, "cp_fused_all_to_all", False)
                 and cpm.UlyssesPeerWorkspace.available(mpu.get_cp_group(), device))
 
@@ -148,6 +232,13 @@ class FullyParallelAttention(nn.Module):
             rows = new_rows - meta_args.clip_token_nums * bs if meta_args.distill_nearly_clean_chunk else new_rows
             assert start + rows <= cache.size(0)   # dit_module.py:927
         return cache, start, rows
+
+    def _offload_views(self, inference_params, cache, start):
+        """kv_offload: device views (k, v) of the cache prefix cache[:start], staged through KVOffload."""
+        off = KVOffload.of(inference_params, torch.device("cuda", torch.cuda.current_device()))
+        nxt = inference_params.key_value_memory_dict.get(self.layer_number + 1)
+        pre = off.prefix(self.layer_number, cache, start, nxt)
+        return pre[..., :F.HEAD_DIM], pre[..., F.HEAD_DIM:]
 
     # ------------------------------------------------------------------ pieces
     def _project(self, mixed):
@@ -218,7 +309,14 @@ class FullyParallelAttention(nn.Module):
             return key_and_value[..., :F.HEAD_DIM], key_and_value[..., F.HEAD_DIM:]
         cache, start, app = self._cache_plan(inference_params, meta_args, key_and_value.shape[0], key_and_value.dtype,
                                              key_and_value.device)
-        if cache is not None:
+        if cache is not None and not cache.is_cuda:      # kv_offload
+            off = KVOffload.of(inference_params, key_and_value.device)
+            pre = off.prefix(self.layer_number, cache, start,
+                             inference_params.key_value_memory_dict.get(self.layer_number + 1)) if start > 0 else None
+            off.store(self.layer_number, cache, key_and_value, start, app)
+            if pre is not None:
+                key_and_value = torch.cat([pre, key_and_value], dim=0)
+        elif cache is not None:
             if app > 0:
                 F.kv_cache_append(cache, key_and_value, start, app)
             if start > 0:
@@ -348,12 +446,17 @@ class FullyParallelAttention(nn.Module):
             assert self.engine_config.cp_size == 1
             xq, xk, xv = self._project(mixed_qqkv)
             cache, start, app = self._cache_plan(inference_params, meta_args, rows, dt, dev)
+            offload = cache is not None and not cache.is_cuda
             query, kv_new = F.qk_norm_rope(xq, xk, xv, Hq, Hkv, self._ln(self.q_layernorm), self._ln(self.k_layernorm),
                                            sin_emb, cos_emb, batch=batch_size, eps=eps, zero_centered_gamma=z,
-                                           cache=cache if app > 0 else None, cache_row_offset=start, cache_rows=app)
+                                           cache=cache if app > 0 and not offload else None, cache_row_offset=start,
+                                           cache_rows=app)
             kc = vc = None
             if cache is not None and start > 0:
-                kc, vc = cache[:start, :, :F.HEAD_DIM], cache[:start, :, F.HEAD_DIM:]
+                kc, vc = (self._offload_views(inference_params, cache, start) if offload else
+                          (cache[:start, :, :F.HEAD_DIM], cache[:start, :, F.HEAD_DIM:]))
+            if offload:
+                KVOffload.of(inference_params, dev).store(self.layer_number, cache, kv_new, start, app)
             if fused_proj_input:
                 buf = torch.empty((rows, 2 * Hq * F.HEAD_DIM), dtype=dt, device=dev)
                 self.core_attention(query, kv_new[..., :F.HEAD_DIM], kv_new[..., F.HEAD_DIM:], batch_size, meta_args,
@@ -393,8 +496,9 @@ class FullyParallelAttention(nn.Module):
         x2d = mixed_qqkv.reshape(rows, -1)
         cache, start, app = self._cache_plan(inference_params, meta_args, total_rows, dt, dev)
         hkv_loc = self.num_query_groups_per_partition
+        offload = cache is not None and not cache.is_cuda
         # the KV all-to-all lands straight in the cache slot when every received row is to be cached
-        direct = cache is not None and app == total_rows
+        direct = cache is not None and app == total_rows and not offload
         kv_recv = cache[start:start + total_rows] if direct else None
 
         def get_kv():
@@ -409,10 +513,13 @@ class FullyParallelAttention(nn.Module):
             return q
 
         def kv_cache_func(kv):
-            if cache is not None and app > 0 and not direct:
+            if offload:
+                KVOffload.of(inference_params, dev).store(self.layer_number, cache, kv, start, app)
+            elif cache is not None and app > 0 and not direct:
                 F.kv_cache_append(cache, kv, start, app)
             if cache is not None and start > 0:
-                self._kc, self._vc = cache[:start, :, :F.HEAD_DIM], cache[:start, :, F.HEAD_DIM:]
+                self._kc, self._vc = (self._offload_views(inference_params, cache, start) if offload else
+                                      (cache[:start, :, :F.HEAD_DIM], cache[:start, :, F.HEAD_DIM:]))
             else:
                 self._kc = self._vc = None
             return kv[..., :F.HEAD_DIM], kv[..., F.HEAD_DIM:]
@@ -498,6 +605,8 @@ class FullyParallelAttention(nn.Module):
         chunk i-1."""
         sq, b, _ = mixed_qqkv.shape
         assert b == 1                                       # dit_module.py:1070
+        if self.engine_config.kv_offload:
+            raise NotImplementedError("kv_offload is available with cp_strategy 'none' and 'cp_ulysses'")
         cp, dn = self.engine_config.cp_size, meta_args.denoising_range_num
         Hq, Hkv = self.model_config.num_attention_heads, self.model_config.num_query_groups
         eps, z = self.model_config.layernorm_epsilon, self.model_config.apply_layernorm_1p
@@ -556,6 +665,8 @@ class FullyParallelAttention(nn.Module):
         sq, b, _ = mixed_qqkv.shape
         if b != 1:
             raise NotImplementedError("cp_ring_kv supports batch size 1 (the 3-CFG uncond pass uses cp_ulysses)")
+        if self.engine_config.kv_offload:
+            raise NotImplementedError("kv_offload is available with cp_strategy 'none' and 'cp_ulysses'")
         Hq, Hkv = self.model_config.num_attention_heads, self.model_config.num_query_groups
         eps, z = self.model_config.layernorm_epsilon, self.model_config.apply_layernorm_1p
         dev, dt = mixed_qqkv.device, mixed_qqkv.dtype

@@ -29,7 +29,7 @@ constexpr int kTileM = 128;               // query rows per softmax warpgroup
 constexpr int kPairM = 2 * kTileM;        // query rows per work item
 constexpr int kTileN = 128;               // keys per K/V tile
 #ifndef MAGI_Q_STAGES
-#define MAGI_Q_STAGES 1     // 2: the next item's Q tiles are prefetched while the current item runs (short-K items)
+#define MAGI_Q_STAGES 2     // the next item's Q tiles are prefetched while the current item runs (1 = single buffer, 4 KV stages)
 #endif
 #ifndef MAGI_KV_STAGES
 #define MAGI_KV_STAGES (MAGI_Q_STAGES == 1 ? 4 : 3)   // smem: (2 * Q stages + KV stages) * 32 KB <= 224 KB

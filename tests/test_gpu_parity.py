@@ -456,6 +456,66 @@ def test_full_attention_block_matches_reference_golden():
             assert x_out[:clip].abs().sum() == 0   # zero caption tokens -> zeros (dit_module.py:1124 semantics)
 
 
+def test_kv_offload_matches_resident_cache():
+    """kv_offload (dit_module.py:803-811, 914-929): caches in pinned host memory, prefix staged to the device (the next
+    layer's prefix prefetched on a copy stream), new rows written back asynchronously. Two layers replay the golden
+    step sequence with and without offload: outputs and cache contents must be bit-identical."""
+    from magi_b200.attention import KVOffload
+    from magi_b200.common import InferenceParams, ModelMetaArgs, PackedCoreAttnParams, PackedCrossAttnParams
+    g = Golden("attention_single_rank.npz")
+    clip = int(g["clip"])
+
+    def run(offload):
+        layers = []
+        for ln_ in (1, 2):
+            m = _build_module(g)
+            m.layer_number = ln_
+            m.engine_config.kv_offload = offload
+            layers.append(m)
+        inf = InferenceParams(max_batch_size=1, max_sequence_length=4 * clip)
+        outs = []
+        for rep in range(2):                      # second pass: every layer's cache exists -> prefetch path
+            for s in ["A", "B", "C", "D"]:
+                sp, dn, bs, upd, extra, ncc, has_inf = [int(x) for x in g[f"{s}.meta"]]
+                if not has_inf or bs != 1:
+                    continue
+                p = O.cross_attn_params(clip, dn, bs, g[f"{s}.y_index"])
+                q_range, k_range = g.raw(f"{s}.q_range"), g.raw(f"{s}.k_range")
+                core = PackedCoreAttnParams(q_range=i32(q_range), k_range=i32(k_range), np_q_range=q_range,
+                                            np_k_range=k_range, max_seqlen_q=clip, max_seqlen_k=O.max_seqlen_k(k_range))
+                cross = PackedCrossAttnParams(q_ranges=i32(p["q_ranges"]), kv_ranges=i32(p["kv_ranges"]),
+                                              cu_seqlens_q=i32(p["cu_seqlens_q"]), cu_seqlens_kv=i32(p["cu_seqlens_kv"]),
+                                              max_seqlen_q=clip, max_seqlen_kv=800)
+                meta = ModelMetaArgs(H=4, W=4, cp_pad_size=None, cp_split_sizes=None, slice_point=sp,
+                                     denoising_range_num=dn, range_num=sp + dn, extract_prefix_video_feature=False,
+                                     fwd_extra_1st_chunk=bool(extra), distill_nearly_clean_chunk=bool(ncc),
+                                     clip_token_nums=clip, enable_cuda_graph=False, core_attn_params=core,
+                                     cross_attn_params=cross)
+                inf.update_kv_cache = bool(upd)
+                hs = g.torch(f"{s}.hidden_states", "cuda")
+                for m in layers:
+                    c, x = m(hs, g.torch(f"{s}.key_value_states", "cuda"), inf, g.torch(f"{s}.rope", "cuda"), meta)
+                    outs.append((c.clone(), x.clone()))
+                    hs = (hs.float() + 0.1 * c.float().mean(-1, keepdim=True)).to(torch.bfloat16)   # layer 2 sees other data
+        torch.cuda.synchronize()
+        if offload:
+            KVOffload.of(inf, torch.device("cuda", 0)).synchronize()
+        return outs, inf
+
+    ref_outs, ref_inf = run(False)
+    off_outs, off_inf = run(True)
+    for (c0, x0), (c1, x1) in zip(ref_outs, off_outs):
+        assert torch.equal(c0, c1) and torch.equal(x0, x1)
+    st = off_inf.kv_offload_state
+    assert st.prefetch_hits > 0 and st.d2h_bytes > 0 and st.h2d_bytes > 0
+    for ln_ in (1, 2):
+        host = off_inf.key_value_memory_dict[ln_]
+        assert not host.is_cuda and host.is_pinned()
+        dev_cache = ref_inf.key_value_memory_dict[ln_]
+        rows = 3 * clip          # rows written by the sequence (the rest of torch.empty storage is undefined)
+        assert torch.equal(host[:rows].cuda(), dev_cache[:rows])
+
+
 def test_reference_named_pieces_match_golden():
     """get_q / get_kv / get_qkv / get_xqkv / adjust_key_and_value_for_inference / full_attention keep the reference's
     names and argument meaning (dit_module.py:933-1096); their outputs are compared with what the reference's own
