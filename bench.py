@@ -35,6 +35,10 @@ WORKLOADS = {
     "cfg2-cache": dict(desc="cfg2, window advanced: 3 chunks in flight reading cached chunk 0, k=[(0,2),(0,3),(0,4)]",
                        Hq=24, Hkv=8, layers=34, clip=9360, k_chunks=[(0, 2), (0, 3), (0, 4)], text=[512, 512, 512],
                        slice_point=1),
+    "cfg3": dict(desc="MAGI-1 4.5B-distill 34L, 480x832, pipelined denoising: 3 chunks in flight behind one cached chunk "
+                      "with the noise2clean windows + the distill nearly-clean extra self-only range, "
+                      "k=[(0,2),(0,3),(1,4),(4,5)] (mixed varlen ranges)", Hq=24, Hkv=8, layers=34, clip=9360,
+                 k_chunks=[(0, 2), (0, 3), (1, 4), (4, 5)], text=[512, 512, 512, 512], slice_point=1),
     "cfg1": dict(desc="MAGI-1 4.5B cut to 2 blocks, 256x256 (1536 tok), 1 chunk", Hq=24, Hkv=8, layers=2, clip=1536,
                  k_chunks=[(0, 1)], text=[512], slice_point=0),
     "cfg4": dict(desc="MAGI-1 24B 48L 48q/8kv x128, 720x1280 (21600 tok/chunk), peak state 5 ranges "
