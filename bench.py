@@ -306,6 +306,99 @@ class HotPath:
             fn(l, timed_events)
 
 
+# ----------------------------------------------------------------------------------------------- whole DiT blocks
+def dit_step_leg(w, dev, world, rank, steps, max_over_ranks, barrier):
+    """BASELINE.json's second metric, "DiT denoise-step latency": one forward of ALL transformer blocks of the named
+    model on the same state - the attention hot path (this repository's kernels) plus everything around it in the
+    block (hidden LayerNorms, q/qx/k/v, text-kv, out-projection and MLP GEMMs through cuBLAS, the fused adaLN gating
+    chains) via the drop-in TransformerLayer (magi-1_b200/transformer_layer.py); random-init weights of the real
+    architecture, synthetic latents / captions / timestep embeddings. N > 1: sequence-sharded blocks, Ulysses
+    attention with the all-to-alls fused into the kernels."""
+    import numpy as np
+    import torch
+    from magi_b200 import context_parallel as cpm
+    from magi_b200.common import (EngineConfig, InferenceParams, ModelConfig, ModelMetaArgs, PackedCoreAttnParams,
+                                  PackedCrossAttnParams)
+    from magi_b200.transformer_layer import TransformerLayer, high_precision_promote
+    big = w["Hq"] == 48
+    mc = (ModelConfig.magi_24b if big else ModelConfig.magi_4p5b)(num_layers=w["layers"])
+    ec = EngineConfig(cp_size=world, cp_strategy="none" if world == 1 else "cp_ulysses")
+    clip, n, sp = w["clip"], len(w["k_chunks"]), w["slice_point"]
+    S = clip * n
+    torch.manual_seed(1234)
+    layers = []
+    for l in range(w["layers"]):
+        with torch.device(dev):
+            layer = high_precision_promote(TransformerLayer(mc, ec, layer_number=l))
+        for name, p_ in layer.named_parameters():
+            if "layernorm" in name or "post_norm" in name or name.endswith("bias"):
+                p_.data.normal_(0.0, 0.02)
+            elif name.endswith("layer_norm.weight"):
+                p_.data.fill_(1.0)
+            else:
+                p_.data.normal_(0.0, 1.0 / math.sqrt(p_.shape[-1]))
+        layers.append(layer.eval())
+    g = torch.Generator(device=dev).manual_seed(99)
+    hs = torch.randn(S, 1, mc.hidden_size, device=dev, generator=g).to(torch.bfloat16)
+    cond = torch.randn(1, n, int(mc.hidden_size * mc.cond_hidden_ratio), device=dev, generator=g).to(torch.bfloat16)
+    cmap = torch.arange(n, device=dev).repeat_interleave(clip).reshape(1, -1).transpose(0, 1).contiguous()
+    y = torch.randn(sum(w["text"]), mc.hidden_size, device=dev, generator=g).to(torch.bfloat16)
+    ang = torch.rand(S, 48, device=dev, generator=g) * 6.2831853
+    rope = torch.cat([torch.sin(ang), torch.cos(ang)], -1)
+    i32 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.int32), device=dev)
+    q_range = np.array([[i * clip, (i + 1) * clip] for i in range(n)], dtype=np.int32)
+    k_range = np.array([[s_ * clip, e_ * clip] for s_, e_ in w["k_chunks"]], dtype=np.int32)
+    cu_q = np.arange(n + 1, dtype=np.int32) * clip
+    cu_k = np.concatenate([[0], np.cumsum(w["text"])]).astype(np.int32)
+    core = PackedCoreAttnParams(i32(q_range), i32(k_range), q_range, k_range, clip, int(k_range.max() - k_range.min()))
+    cross = PackedCrossAttnParams(i32(np.stack([cu_q[:-1], cu_q[1:]], 1)), i32(np.stack([cu_k[:-1], cu_k[1:]], 1)),
+                                  i32(cu_q), i32(cu_k), clip, 800)
+    split = None
+    if world > 1:
+        ardf = dict(denoising_range_num=n, q_range=core.q_range, k_range=core.k_range, max_seqlen_q=clip,
+                    max_seqlen_k=core.max_seqlen_k)
+        hs, cmap, rope, _, split, core, cross = cpm.cp_pre_process(world, ec.cp_strategy, hs, cmap, rope, None, ardf,
+                                                                   core, cross)
+    meta = ModelMetaArgs(H=1, W=1, cp_pad_size=0, cp_split_sizes=split, slice_point=sp, denoising_range_num=n,
+                         range_num=sp + n, extract_prefix_video_feature=False, fwd_extra_1st_chunk=True,
+                         distill_nearly_clean_chunk=False, clip_token_nums=clip, enable_cuda_graph=False,
+                         core_attn_params=core, cross_attn_params=cross)
+    inf = InferenceParams(max_batch_size=1, max_sequence_length=(sp + n) * clip)
+    inf.update_kv_cache = True
+
+    def step():
+        x = hs
+        for layer in layers:
+            x = layer(x, cond, cmap, y, rope, inf, meta)
+        return x
+
+    for _ in range(2):
+        out = step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = step()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    h, f = mc.hidden_size, mc.ffn_hidden_size
+    per_tok = 2 * h * (2 * w["Hq"] * 128 + 2 * w["Hkv"] * 128) + 2 * (2 * w["Hq"] * 128) * h \
+        + 2 * h * f * (3 if mc.gated_linear_unit else 2)
+    gemm = (per_tok * S + 2 * sum(w["text"]) * h * 2 * w["Hkv"] * 128) * w["layers"]
+    self_f, cross_f = attn_flops(w)
+    total = gemm + (self_f + cross_f) * w["layers"]
+    assert bool(torch.isfinite(out.float()).all())
+    del layers
+    torch.cuda.empty_cache()
+    return {"ms_per_step": round(ms, 2), "layers": w["layers"], "model": "MAGI-1 24B" if big else "MAGI-1 4.5B",
+            "tflops_total": round(total / (ms * 1e-3) / 1e12, 1), "gemm_tflop_per_step": round(gemm / 1e12, 1),
+            "attn_tflop_per_step": round((self_f + cross_f) * w["layers"] / 1e12, 1),
+            "what": "all transformer blocks of one denoise forward: attention hot path (own kernels) + cuBLAS GEMMs + "
+                    "fused adaLN gating chains, random-init weights, " + ("single GPU" if world == 1 else
+                                                                         f"cp_ulysses{world} fused all-to-alls")}
+
+
 # ----------------------------------------------------------------------------------------------- CPU baseline
 def cpu_baseline_sample(w, budget_s=20.0):
     """The reference's math (oracle port, numpy fp32, all host threads) on a bounded sample of the SAME workload:
@@ -374,12 +467,13 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-dit-step", action="store_true", help="skip the whole-DiT-block step latency leg")
     ap.add_argument("--profile", action="store_true",
                     help="short run for ncu: no e2e / CPU legs, warm-up exactly as given (numbers are not bench values)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.profile:
-        args.no_e2e = args.no_cpu_baseline = True
+        args.no_e2e = args.no_cpu_baseline = args.no_dit_step = True
     if args.impl == "reference":
         return run_reference(args, w)
 
@@ -512,6 +606,10 @@ def main():
                "api": "magi_b200.functional (ctypes -> libmagi_attn.so C-ABI), pinned host buffers"
                       + (", copies double-buffered on a copy stream" if world == 1 else "")}
 
+    dit = None
+    if not args.no_dit_step:
+        dit = dit_step_leg(w, dev, world, rank, min(args.steps, 3), max_over_ranks, barrier)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         _, cpu = cpu_baseline_sample(w, budget_s=args.ref_budget)
@@ -548,6 +646,8 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if dit is not None:
+            line["dit_denoise_step"] = dit
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

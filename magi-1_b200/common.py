@@ -79,6 +79,8 @@ class ModelConfig:
     xattn_cond_hidden_ratio: float = 1.0
     caption_max_length: int = 800
     gated_linear_unit: bool = False
+    cond_hidden_ratio: float = 0.25
+    cond_gating_ratio: float = 1.0
 
     @classmethod
     def magi_4p5b(cls, **kw):

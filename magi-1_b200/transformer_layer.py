@@ -1,0 +1,130 @@
+"""Drop-in `TransformerLayer` for the reference's DiT block (inference/model/dit/dit_module.py:1252-1367), the caller
+on either side of the attention hot path: same constructor
+`(model_config, engine_config, layer_number)`, same sub-module / parameter names (reference state_dicts load:
+`ada_modulate_layer.proj.0`, `self_attention.*`, `self_attn_post_norm`, `mlp.{layer_norm,linear_fc1,linear_fc2}`,
+`mlp_post_norm`), same `forward(hidden_states, condition, condition_map, y_xattn_flat, rotary_pos_emb,
+inference_params, meta_args)`.
+
+What runs where
+  * the attention hot path: hand-written CUDA (attention.py / functional.py);
+  * both gating chains (`bias_modulate_add`, dit_module.py:292-307): one fused kernel launch each;
+  * the out-projection input "sq b (hn n hd)": written in place by the two attention kernels (no cat / rearrange);
+  * the dense GEMMs (q/qx/k/v, kv_xattn, linear_proj, MLP fc1/fc2), the hidden-size LayerNorms in front of them, GELU /
+    SwiGLU and the tiny adaLN projection stay plain torch / cuBLAS library calls: they are not on the path this
+    repository rebuilds.
+"""
+import torch
+import torch.nn as nn
+
+from . import functional as F
+from .attention import FullyParallelAttention, HeadLayerNorm
+from .common import EngineConfig, InferenceParams, ModelConfig, ModelMetaArgs
+
+
+class AdaModulateLayer(nn.Module):
+    """dit_module.py:177-195: SiLU -> Linear(hidden * cond_hidden_ratio -> hidden * cond_gating_ratio * 2)."""
+
+    def __init__(self, model_config: ModelConfig):
+        super().__init__()
+        self.model_config = model_config
+        self.gate_num_chunks = 2
+        self.act = nn.SiLU()
+        self.proj = nn.Sequential(nn.Linear(int(model_config.hidden_size * model_config.cond_hidden_ratio),
+                                            int(model_config.hidden_size * model_config.cond_gating_ratio
+                                                * self.gate_num_chunks),
+                                            bias=True, dtype=model_config.params_dtype))
+
+    def forward(self, c):
+        return self.proj(self.act(c))
+
+
+def softcap(x: torch.Tensor, cap: float):
+    """dit_module.py:360-361."""
+    return (cap * torch.tanh(x.float() / cap)).to(x.dtype)
+
+
+class CustomMLP(nn.Module):
+    """dit_module.py:493-551 (bf16 linears; the fp8 variants are outside this build): LayerNorm -> fc1 -> GELU, or
+    SwiGLU (`flashinfer.activation.silu_and_mul`: silu(x[..., :d]) * x[..., d:]) when gated_linear_unit -> fc2."""
+
+    def __init__(self, model_config: ModelConfig, engine_config: EngineConfig, layer_number: int):
+        super().__init__()
+        if engine_config.fp8_quant:
+            raise NotImplementedError("fp8_quant linears are outside the hot path of this build")
+        self.model_config = model_config
+        dt, h, f = model_config.params_dtype, model_config.hidden_size, model_config.ffn_hidden_size
+        self.layer_norm = nn.LayerNorm(h, eps=model_config.layernorm_epsilon, dtype=dt)
+        self.linear_fc1 = nn.Linear(h, 2 * f if model_config.gated_linear_unit else f, bias=False, dtype=dt)
+        self.linear_fc2 = nn.Linear(f, h, bias=False, dtype=dt)
+
+    def forward(self, hidden_states):
+        x = self.linear_fc1(self.layer_norm(hidden_states))
+        if self.model_config.gated_linear_unit:
+            a, b = x.chunk(2, dim=-1)
+            x = torch.nn.functional.silu(a) * b
+        else:
+            x = torch.nn.functional.gelu(x)
+        return self.linear_fc2(x)
+
+
+class TransformerLayer(nn.Module):
+    def __init__(self, model_config: ModelConfig, engine_config: EngineConfig, layer_number: int = 1):
+        super().__init__()
+        self.model_config = model_config
+        self.engine_config = engine_config
+        self.layer_number = layer_number          # pp_size == 1 on this path: no layer offset (dit_module.py:1284-1295)
+        self.ada_modulate_layer = AdaModulateLayer(model_config)
+        self.self_attention = FullyParallelAttention(model_config, engine_config, self.layer_number)
+        self.self_attn_post_norm = HeadLayerNorm(model_config, model_config.hidden_size)
+        self.mlp = CustomMLP(model_config, engine_config, self.layer_number)
+        self.mlp_post_norm = HeadLayerNorm(model_config, model_config.hidden_size)
+
+    @torch.no_grad()
+    def forward(self, hidden_states: torch.Tensor, condition: torch.Tensor, condition_map: torch.Tensor,
+                y_xattn_flat: torch.Tensor, rotary_pos_emb: torch.Tensor, inference_params: InferenceParams,
+                meta_args: ModelMetaArgs):
+        residual = hidden_states
+        attn = self.self_attention
+        if (self.engine_config.cp_strategy == "none"
+                and self.model_config.num_attention_heads % FullyParallelAttention.PROJ_GROUPS == 0):
+            # both attention kernels write straight into the out-projection input (dit_module.py:1332-1338); the
+            # "(n hn hd) -> (hn n hd)" groups are whole heads when Hq is a multiple of hn = 8 (24 and 48 are)
+            proj_in = attn(hidden_states, y_xattn_flat, inference_params, rotary_pos_emb, meta_args,
+                           fused_proj_input=True)
+        else:
+            core_attn_out, cross_attn_out = attn(hidden_states, y_xattn_flat, inference_params, rotary_pos_emb,
+                                                 meta_args)
+            proj_in = FullyParallelAttention.attn_linear_proj_input(core_attn_out, cross_attn_out)
+        return self.attn_post_process_from_proj_input(proj_in, residual, condition, condition_map)
+
+    def attn_post_process(self, core_attn_out, cross_attn_out, residual, condition, condition_map):
+        """dit_module.py:1320-1330, for callers that hold the two attention outputs."""
+        proj_in = FullyParallelAttention.attn_linear_proj_input(core_attn_out, cross_attn_out)
+        return self.attn_post_process_from_proj_input(proj_in, residual, condition, condition_map)
+
+    def attn_post_process_from_proj_input(self, proj_in, residual, condition, condition_map):
+        # attn_linear_proj, dit_module.py:1332-1346. The reference wraps the projection in
+        # torch.autocast("cuda", dtype=torch.float32), which CUDA autocast does not support (it warns and disables
+        # itself), so the projection runs in the parameters' dtype, as here.
+        attn_out = self.self_attention.linear_proj(proj_in)
+        return self.gating_and_mlp(attn_out, residual, condition, condition_map)
+
+    def gating_and_mlp(self, hidden_states, residual, condition, condition_map):
+        """dit_module.py:1348-1367 with both bias_modulate_add chains fused."""
+        gate_output = softcap(self.ada_modulate_layer(condition), 1.0)
+        gate_msa, gate_mlp = gate_output.chunk(2, dim=-1)
+        hidden_states = F.bias_modulate_add(hidden_states, residual, condition_map, gate_msa, self.self_attn_post_norm)
+        residual = hidden_states
+        hidden_states = self.mlp(hidden_states)
+        return F.bias_modulate_add(hidden_states, residual, condition_map, gate_mlp, self.mlp_post_norm)
+
+
+def high_precision_promote(module: nn.Module) -> nn.Module:
+    """The part of `_high_precision_promoter` (dit_model.py:621-638) that concerns a transformer layer: the
+    self-attention q / k LayerNorms (not the `_xattn` ones) and both post-norms hold fp32 parameters."""
+    for name, sub in module.named_modules():
+        if "_xattn" in name:
+            continue
+        if any(k in name for k in ("q_layernorm", "k_layernorm", "self_attn_post_norm", "mlp_post_norm")):
+            sub.float()
+    return module

@@ -13,7 +13,8 @@ without a GPU:
   * flash_attn_func / flash_attn_varlen_func (CUDA)     -> fp32 softmax(QK^T/sqrt(d))V with GQA, output cast to bf16
   * torch.cuda.current_device / Tensor.cuda / get_device_capability -> CPU stand-ins
   * range_mod_kernel_fwd (the reference's own Triton kernel, dit_module.py:201-241) -> the same row-gather multiply
-    in torch; its host wrapper range_mod_triton and bias_modulate_add run unmodified
+    in torch; its host wrapper range_mod_triton and bias_modulate_add run unmodified (in the whole-layer scenario the
+    wrapper's `assert x.is_cuda` forces restating the wrapper too: range_mod_cpu)
 """
 import math
 import os
@@ -430,6 +431,72 @@ def gen_gating():
     print("gating fixture written")
 
 
+# ------------------------------------------------------------------ scenario 6: a whole TransformerLayer
+def range_mod_cpu(x, c_mapping, gatings):
+    """range_mod_triton (dit_module.py:244-289) with its Triton program (:201-241) restated: the host wrapper's
+    transposes / flattens kept, the per-row program replaced by the gather-multiply it performs."""
+    s, b, h = x.shape
+    x2 = x.transpose(0, 1).flatten(0, 1)
+    cm = c_mapping.transpose(0, 1).flatten(0, 1)
+    y = x2 * gatings.flatten(0, 1)[cm.long()]
+    return y.reshape(b, s, h).transpose(0, 1)
+
+
+def gen_layer():
+    dm = install_patches()
+    dm.range_mod_triton = range_mod_cpu
+    init_dist(0, 1, 29581)
+    from inference.common import InferenceParams
+    mc, ec = make_configs(hidden=256, hq=4, hkv=2)
+    torch.manual_seed(4321)
+    layer = dm.TransformerLayer(mc, ec, layer_number=0)
+    g = torch.Generator().manual_seed(4321)
+    with torch.no_grad():
+        for name, p_ in layer.named_parameters():
+            if "layernorm" in name or "post_norm" in name:
+                p_.copy_((torch.randn(p_.shape, generator=g) * 0.2).to(p_.dtype))
+            elif name.endswith("layer_norm.weight"):
+                p_.copy_((1.0 + torch.randn(p_.shape, generator=g) * 0.02).to(p_.dtype))
+            elif name.endswith("bias"):
+                p_.copy_((torch.randn(p_.shape, generator=g) * 0.02).to(p_.dtype))
+            else:
+                p_.copy_((torch.randn(p_.shape, generator=g) * (1.0 / math.sqrt(p_.shape[-1]))).to(p_.dtype))
+    for name, sub in layer.named_modules():       # dit_model.py:621-638
+        if "_xattn" in name:
+            continue
+        if any(k in name for k in ("q_layernorm", "k_layernorm", "self_attn_post_norm", "mlp_post_norm")):
+            sub.float()
+    layer.eval()
+    H = W = 4
+    frames = 3
+    clip = frames * H * W
+    hidden = mc.hidden_size
+    fx = {"w." + k_: pk(v_) for k_, v_ in layer.state_dict().items()}
+    fx["clip"] = np.array(clip)
+    fx["heads"] = np.array([4, 2])
+    inf = InferenceParams(max_batch_size=1, max_sequence_length=4 * clip)
+    inf.key_value_memory_dict[0] = torch.zeros(4 * clip, 2, 256, dtype=torch.bfloat16)
+    for tag, sp, dn, k_chunks, y_index, update in (("A", 0, 2, [(0, 1), (0, 2)], [50, 41], True),
+                                                   ("B", 1, 2, [(0, 2), (1, 3)], [33, 90], True)):
+        S = dn * clip
+        hs = torch.randn(S, 1, hidden, generator=g).to(torch.bfloat16)
+        kvs = torch.randn(int(sum(y_index)), hidden, generator=g).to(torch.bfloat16)
+        cond = torch.randn(1, dn, int(hidden * mc.cond_hidden_ratio), generator=g).to(torch.bfloat16)
+        cmap = torch.arange(dn).repeat_interleave(clip).reshape(1, -1).transpose(0, 1).contiguous()
+        rope = rope_for(dm, (sp + dn) * frames, H, W, dn * frames)
+        m = meta(dm, clip, sp, dn, 1, [[s * clip, e * clip] for s, e in k_chunks], y_index)
+        inf.update_kv_cache = update
+        with torch.no_grad():
+            out = layer(hs, cond, cmap, kvs, rope, inf, m)
+        fx.update({f"{tag}.hidden_states": pk(hs), f"{tag}.key_value_states": pk(kvs), f"{tag}.condition": pk(cond),
+                   f"{tag}.condition_map": cmap.numpy(), f"{tag}.rope": pk(rope),
+                   f"{tag}.k_range": np.array([[s * clip, e * clip] for s, e in k_chunks], dtype=np.int32),
+                   f"{tag}.y_index": np.array(y_index), f"{tag}.meta": np.array([sp, dn, int(update)]),
+                   f"{tag}.out": pk(out)})
+    np.savez_compressed(os.path.join(OUT, "transformer_layer.npz"), **fx)
+    print("transformer layer fixture written")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -441,6 +508,8 @@ if __name__ == "__main__":
         gen_cp(4, 29561, 8, 2, "cp4")   # cp > Hkv: exercises KV-head replication (context_parallel.py:393-394)
     if which in ("all", "cso"):
         gen_cso(2, 29571)
+    if which in ("all", "layer"):
+        gen_layer()
     if which in ("gating",):      # run on its own: it monkey-patches Tensor.is_cuda while it runs
         gen_gating()
     if which in ("all", "single"):

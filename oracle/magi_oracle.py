@@ -458,6 +458,80 @@ def bias_modulate_add(x: np.ndarray, residual: np.ndarray, condition_map: np.nda
     return bf16_round(y + residual.astype(F32))
 
 
+# ----------------------------------------------------------------------------------------------- whole block
+def linear_bf16(x: np.ndarray, w: np.ndarray, b: Optional[np.ndarray] = None) -> np.ndarray:
+    """nn.Linear on bf16 tensors: fp32 accumulate, one rounding of the result to bf16."""
+    y = x.astype(F32) @ w.astype(F32).T
+    if b is not None:
+        y = y + b.astype(F32)
+    return bf16_round(y)
+
+
+def gelu(x: np.ndarray) -> np.ndarray:
+    """torch.nn.functional.gelu (erf form) on a bf16 tensor: fp32 math, bf16 result."""
+    from scipy.special import erf
+    x = x.astype(F32)
+    return bf16_round(F32(0.5) * x * (F32(1.0) + erf(x / np.sqrt(F32(2.0))).astype(F32)))
+
+
+def fully_parallel_attention(w, hs, kvs, rope, cache, has_inf, slice_point, dn, clip, np_q_range, np_k_range, y_index,
+                             update_kv_cache, fwd_extra_1st_chunk=False, distill_nearly_clean_chunk=False, pre=""):
+    """FullyParallelAttention.forward with cp_strategy "none", dit_module.py:1138-1174, composed from the pieces above.
+    w: name -> array of the module's state_dict (prefix `pre`); hs (sq, b, hidden), kvs (ytot, hidden) bf16 values.
+    Returns (core_attn_out, xattn_out), each (sq, b, Hq * 128)."""
+    g = lambda n: w[pre + n]
+    sq, b, _ = hs.shape
+    Hq = g("linear_qkv.q.weight").shape[0] // 128
+    Hkv = g("linear_qkv.k.weight").shape[0] // 128
+    mixed = bf16_round(layer_norm(hs, g("linear_qkv.layer_norm.weight"), g("linear_qkv.layer_norm.bias"), 1e-6,
+                                  zero_centered_gamma=False))
+    lin = {n: linear_bf16(mixed, g(f"linear_qkv.{n}.weight")) for n in ("q", "qx", "k", "v")}
+    sin, cos = rope[:, :48], rope[:, 48:]
+    q = get_q_or_k(lin["q"], Hq, g("q_layernorm.weight"), g("q_layernorm.bias"), sin, cos)
+    kv = get_kv(lin["k"], lin["v"], Hkv, g("k_layernorm.weight"), g("k_layernorm.bias"), sin, cos)
+    key, value = adjust_key_and_value_for_inference(kv, cache, has_inf, slice_point, clip, 1, update_kv_cache, False,
+                                                    fwd_extra_1st_chunk, distill_nearly_clean_chunk)
+    core = core_attention(q, key, value, b, np_q_range, np_k_range, dn).reshape(sq, b, Hq * 128)
+    # get_xqkv + cross_attention, dit_module.py:1005-1021, 1098-1136
+    xq = np.transpose(lin["qx"].reshape(sq, b, Hq, 128), (1, 0, 2, 3)).reshape(b * sq, Hq, 128)
+    xq = xattn_layer_norm(xq, g("q_layernorm_xattn.weight"), g("q_layernorm_xattn.bias"))
+    kvx = linear_bf16(kvs, g("linear_kv_xattn.weight")).reshape(kvs.shape[0], Hkv, 256)
+    xk = xattn_layer_norm(kvx[..., :128], g("k_layernorm_xattn.weight"), g("k_layernorm_xattn.bias"))
+    p = cross_attn_params(clip, dn, b, y_index)
+    xo = attn_varlen(xq, xk, kvx[..., 128:], p["cu_seqlens_q"], p["cu_seqlens_kv"])
+    xo = np.transpose(xo.reshape(b, sq, Hq * 128), (1, 0, 2))
+    return core, xo
+
+
+def transformer_layer(w, hs, condition, condition_map, kvs, rope, cache, has_inf, slice_point, dn, clip, np_q_range,
+                      np_k_range, y_index, update_kv_cache, gated_linear_unit=False):
+    """TransformerLayer.forward, dit_module.py:1297-1367: attention -> "sq b (n hn hd) -> sq b (hn n hd)" (n = 2,
+    hn = 8) -> linear_proj (the float32 autocast of :1343 is not supported by CUDA autocast and disables itself, so
+    the projection runs in bf16) -> softcap(adaLN gates) -> bias_modulate_add -> MLP -> bias_modulate_add."""
+    core, xo = fully_parallel_attention(w, hs, kvs, rope, cache, has_inf, slice_point, dn, clip, np_q_range, np_k_range,
+                                        y_index, update_kv_cache, pre="self_attention.")
+    sq, b, width = core.shape
+    x = np.stack([core, xo], axis=2).reshape(sq, b, 2, 8, width // 8)
+    x = np.transpose(x, (0, 1, 3, 2, 4)).reshape(sq, b, 2 * width)
+    attn_out = linear_bf16(x, w["self_attention.linear_proj.weight"])
+    c = condition.astype(F32)
+    silu = bf16_round(c / (F32(1.0) + np.exp(-c)))
+    gate = softcap(linear_bf16(silu, w["ada_modulate_layer.proj.0.weight"], w["ada_modulate_layer.proj.0.bias"]), 1.0)
+    h = hs.shape[-1]
+    gate_msa, gate_mlp = gate[..., :h], gate[..., h:]
+    x1 = bias_modulate_add(attn_out, hs, condition_map, gate_msa, w["self_attn_post_norm.weight"],
+                           w["self_attn_post_norm.bias"])
+    m = bf16_round(layer_norm(x1, w["mlp.layer_norm.weight"], w["mlp.layer_norm.bias"], 1e-6, zero_centered_gamma=False))
+    m = linear_bf16(m, w["mlp.linear_fc1.weight"])
+    if gated_linear_unit:
+        a, bb = m[..., :m.shape[-1] // 2], m[..., m.shape[-1] // 2:]
+        m = bf16_round(bf16_round(a / (F32(1.0) + np.exp(-a))) * bb)
+    else:
+        m = gelu(m)
+    m = linear_bf16(m, w["mlp.linear_fc2.weight"])
+    return bias_modulate_add(m, x1, condition_map, gate_mlp, w["mlp_post_norm.weight"], w["mlp_post_norm.bias"])
+
+
 # ----------------------------------------------------------------------------------------------- RoPE table
 def rope_table(T_total: int, H: int, W: int, bands: Optional[np.ndarray] = None, keep_last_T: Optional[int] = None):
     """LearnableRotaryEmbeddingCat.get_embed as used at dit_model.py:163-166 (in_pixels=False, dim=128):

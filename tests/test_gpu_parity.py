@@ -456,6 +456,51 @@ def test_full_attention_block_matches_reference_golden():
             assert x_out[:clip].abs().sum() == 0   # zero caption tokens -> zeros (dit_module.py:1124 semantics)
 
 
+def test_transformer_layer_matches_reference_golden():
+    """The drop-in TransformerLayer (attention hot path + fused gating chains + torch GEMMs) against the reference's own
+    TransformerLayer.forward (tests/golden/transformer_layer.npz): reference state_dict loads by name, two forwards
+    (no cache, then one cached chunk). Tolerance: SURVEY.md section 8(c) per-step latent criterion, rel-L2 <= 2e-2
+    (cuBLAS vs ATen-CPU bf16 GEMMs)."""
+    from magi_b200.common import (EngineConfig, InferenceParams, ModelConfig, ModelMetaArgs, PackedCoreAttnParams,
+                                  PackedCrossAttnParams)
+    from magi_b200.transformer_layer import TransformerLayer, high_precision_promote
+    g = Golden("transformer_layer.npz")
+    hidden = g.raw("w.self_attention.linear_qkv.layer_norm.weight").shape[0]
+    Hq, Hkv = [int(x) for x in g["heads"]]
+    mc = ModelConfig(num_layers=4, hidden_size=hidden, ffn_hidden_size=4 * hidden, num_attention_heads=Hq,
+                     num_query_groups=Hkv)
+    layer = high_precision_promote(TransformerLayer(mc, EngineConfig(), layer_number=0))
+    sd = {k[2:]: g.torch(k) for k in g.files if k.startswith("w.")}
+    layer.load_state_dict(sd, strict=True)
+    layer = layer.cuda().eval()
+    assert layer.self_attn_post_norm.weight.dtype == torch.float32
+    clip = int(g["clip"])
+    inf = InferenceParams(max_batch_size=1, max_sequence_length=4 * clip)
+    # as in the fixture: step A (slice_point 0, no extra chunk) does not touch the cache, step B reads chunk 0 of it
+    inf.key_value_memory_dict[0] = torch.zeros(4 * clip, Hkv, 256, dtype=torch.bfloat16, device="cuda")
+    for tag in ("A", "B"):
+        sp, dn, upd = [int(x) for x in g[f"{tag}.meta"]]
+        q_range, k_range = O.core_q_ranges(clip, dn, 1), g.raw(f"{tag}.k_range")
+        p = O.cross_attn_params(clip, dn, 1, g[f"{tag}.y_index"])
+        core = PackedCoreAttnParams(q_range=i32(q_range), k_range=i32(k_range), np_q_range=q_range, np_k_range=k_range,
+                                    max_seqlen_q=clip, max_seqlen_k=O.max_seqlen_k(k_range))
+        cross = PackedCrossAttnParams(q_ranges=i32(p["q_ranges"]), kv_ranges=i32(p["kv_ranges"]),
+                                      cu_seqlens_q=i32(p["cu_seqlens_q"]), cu_seqlens_kv=i32(p["cu_seqlens_kv"]),
+                                      max_seqlen_q=clip, max_seqlen_kv=800)
+        meta = ModelMetaArgs(H=4, W=4, cp_pad_size=None, cp_split_sizes=None, slice_point=sp, denoising_range_num=dn,
+                             range_num=sp + dn, extract_prefix_video_feature=False, fwd_extra_1st_chunk=False,
+                             distill_nearly_clean_chunk=False, clip_token_nums=clip, enable_cuda_graph=False,
+                             core_attn_params=core, cross_attn_params=cross)
+        inf.update_kv_cache = bool(upd)
+        out = layer(g.torch(f"{tag}.hidden_states", "cuda"), g.torch(f"{tag}.condition", "cuda"),
+                    g.torch(f"{tag}.condition_map", "cuda"), g.torch(f"{tag}.key_value_states", "cuda"),
+                    g.torch(f"{tag}.rope", "cuda"), inf, meta)
+        ref = g[f"{tag}.out"]
+        got = out.float().cpu().numpy()
+        rel = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+        assert got.shape == ref.shape and rel < 2e-2, (tag, rel)
+
+
 def test_kv_offload_matches_resident_cache():
     """kv_offload (dit_module.py:803-811, 914-929): caches in pinned host memory, prefix staged to the device (the next
     layer's prefix prefetched on a copy stream), new rows written back asynchronously. Two layers replay the golden
