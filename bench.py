@@ -56,10 +56,10 @@ def attn_flops(w):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE self-attention launch of the named workload, from the committed
-# `ncu --set full` capture (profiles/r01_ncu_final_raw.csv: 623.07 MB read + 199.84 MB written). The algorithmic
+# `ncu --set full` capture (profiles/r01_ncu_final2_raw.csv: 623.43 MB read + 200.83 MB written). The algorithmic
 # minimum (q + out + packed kv once) is 230 + 230 + 153 = 613 MB: K/V re-reads by the 3 query heads of a GQA group and by
 # the 37 query tiles of a chunk are served by L2.
-NCU_TRAFFIC_BYTES = {"cfg2": 822909440}
+NCU_TRAFFIC_BYTES = {"cfg2": 824263168}
 
 
 def load_peaks():
