@@ -122,15 +122,21 @@ class HotPath:
     """Synthetic inputs of one denoise forward's attention hot path, resident in HBM, and the per-layer launch
     sequence through the public API (magi_b200.functional -> C-ABI)."""
 
-    def __init__(self, w, device, cp=1, rank=0, seed=1234, fused=True):
+    def __init__(self, w, device, cp=1, rank=0, seed=1234, fused=True, ring=False):
         import torch
         import magi_b200.functional as F
         self.torch, self.F, self.w, self.cp, self.rank, self.dev = torch, F, w, cp, rank, device
-        self.fused = fused and cp > 1
+        self.ring = ring and cp > 1
+        self.fused = fused and cp > 1 and not self.ring
         Hq, Hkv, clip = w["Hq"], w["Hkv"], w["clip"]
         self.S = clip * len(w["k_chunks"])
         from magi_b200 import context_parallel as cpm
-        if cp > 1:
+        n_chunks = len(w["k_chunks"])
+        if self.ring:
+            # cp_ring_kv: every chunk striped across the ranks (context_parallel.ring_split_sizes)
+            self.ring_sizes = cpm.ring_split_sizes(clip, cp)
+            self.split = [n_chunks * s_ for s_ in self.ring_sizes]
+        elif cp > 1:
             self.split = cpm.ulysses_split_sizes(self.S, cp)
         else:
             self.split = [self.S]
@@ -161,12 +167,15 @@ class HotPath:
         xq_r, xk_r = [], []
         for i in range(n):
             a, b = max(i * clip, off), min((i + 1) * clip, off + self.S_loc)
+            if self.ring:                         # local rows are (chunk, stripe row)
+                nr = self.ring_sizes[rank]
+                a, b = off + i * nr, off + (i + 1) * nr
             if a < b:
                 xq_r.append([a - off, b - off])
                 xk_r.append([cu_k[i], cu_k[i + 1]])
         self.x_q_ranges, self.x_k_ranges = i32(xq_r), i32(xk_r)
         # per-layer KV cache in post-all-to-all layout (dit_module.py:794-819)
-        self.hkv_loc = max(1, Hkv // cp)
+        self.hkv_loc = Hkv if self.ring else max(1, Hkv // cp)   # ring-KV keeps all heads (and a replicated cache)
         self.hq_loc = Hq // cp
         self.cache_rows = (sp + n) * clip
         self.start = sp * clip
@@ -298,10 +307,42 @@ class HotPath:
         ws.barrier()
         self.core_out = ws.out[:self.S_loc]
 
+    # -- one layer, ring-KV (FullyParallelAttention._forward_ring): every rank keeps its query shard with all heads, the
+    #    packed K/V blocks of the new tokens travel round the ring (NCCL send/recv over NVLink, next block in flight
+    #    while the current one is attended), partial results merged by log-sum-exp; the cache is replicated
+    def layer_cp_ring(self, l, timed_events=False):
+        from magi_b200 import context_parallel as cpm
+        F, w, inp, torch = self.F, self.w, self.inputs, self.torch
+        cache = self.caches[l]
+        q, kv_local = F.qk_norm_rope(inp["xq"], inp["xk"], inp["xv"], w["Hq"], w["Hkv"], self.ln["q"], self.ln["k"],
+                                     inp["sin"], inp["cos"])
+        dev = self.dev
+
+        def attn(q_, blk, cache_prefix, qr, kr):
+            t = lambda a: torch.as_tensor(a, dtype=torch.int32).to(dev, non_blocking=True)
+            kc = vc = None
+            if cache_prefix is not None:
+                kc, vc = cache_prefix[..., :128], cache_prefix[..., 128:]
+            if timed_events:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            r = F.attn_ranges(q_, blk[..., :128], blk[..., 128:], t(qr), t(kr), k_cache=kc, v_cache=vc, zero_fill=True)
+            if timed_events:
+                e1.record()
+                self.attn_events.append((e0, e1))
+            return r
+
+        n = len(w["k_chunks"])
+        out, _ = cpm.RingKVScheduler.run(q, kv_local, cache, w["k_chunks"], w["slice_point"], w["clip"], n,
+                                         self.ring_sizes, n, attn, F.lse_merge)
+        self.core_out = out
+        self.cross(inp)
+
     ulysses_overlap_degree = 1
 
     def step(self, timed_events=False):
-        fn = (self.layer_cp_fused if self.fused else self.layer_cp) if self.cp > 1 else self.layer
+        fn = (self.layer_cp_ring if self.ring else self.layer_cp_fused if self.fused else self.layer_cp) \
+            if self.cp > 1 else self.layer
         for l in range(self.w["layers"]):
             fn(l, timed_events)
 
@@ -462,8 +503,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--overlap-degree", type=int, default=1)
-    ap.add_argument("--cp-mode", default="fused", choices=["fused", "nccl"],
-                    help="N > 1: all-to-alls fused into the kernels' stores over NVLink peer memory, or NCCL calls")
+    ap.add_argument("--cp-mode", default="fused", choices=["fused", "nccl", "ring"],
+                    help="N > 1: Ulysses with the all-to-alls fused into the kernels' stores over NVLink peer memory, "
+                         "Ulysses with NCCL all_to_all_single, or the ring-KV exchange (sequence sharded)")
     ap.add_argument("--ref-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -493,7 +535,7 @@ def main():
         mpu.initialize_model_parallel(cp_size=world)
     from magi_b200 import _lib
 
-    hp = HotPath(w, dev, cp=world, rank=rank, fused=args.cp_mode == "fused")
+    hp = HotPath(w, dev, cp=world, rank=rank, fused=args.cp_mode == "fused", ring=args.cp_mode == "ring")
     hp.ulysses_overlap_degree = args.overlap_degree
     self_f, cross_f = attn_flops(w)
     step_flops = (self_f + cross_f) * w["layers"]
@@ -607,7 +649,7 @@ def main():
                       + (", copies double-buffered on a copy stream" if world == 1 else "")}
 
     dit = None
-    if not args.no_dit_step:
+    if not args.no_dit_step and args.cp_mode != "ring":
         dit = dit_step_leg(w, dev, world, rank, min(args.steps, 3), max_over_ranks, barrier)
 
     cpu = None
@@ -622,8 +664,9 @@ def main():
             "config": {"workload": w["desc"], "name": args.workload,
                        "parallelism": "none" if world == 1 else (
                            f"cp_ulysses{world}, all-to-alls fused into the kernels' stores (NVLink peer memory), 2 barriers "
-                           f"per layer" if hp.fused else f"cp_ulysses{world}, NCCL all_to_all_single "
-                           f"(overlap_degree {args.overlap_degree})"),
+                           f"per layer" if hp.fused else f"cp_ring_kv{world}, K/V blocks round the ring by NCCL send/recv, "
+                           f"log-sum-exp merge, replicated cache" if hp.ring else
+                           f"cp_ulysses{world}, NCCL all_to_all_single (overlap_degree {args.overlap_degree})"),
                        "step": "attention hot path of one denoise forward over all layers: fused LN+RoPE prologue with "
                                "KV-cache append, range-masked self-attention, text cross-attention",
                        "tokens_q": hp.S, "layers": w["layers"],

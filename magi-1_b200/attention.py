@@ -685,8 +685,12 @@ class FullyParallelAttention(nn.Module):
             return F.attn_ranges(q, blk[..., :F.HEAD_DIM], blk[..., F.HEAD_DIM:], t(qr), t(kr), k_cache=kc, v_cache=vc,
                                  zero_fill=True)
 
-        out, _ = cpm.RingKVScheduler.run(query, kv_local, cache, p.np_q_range, p.np_k_range, start, app,
-                                         meta_args.cp_split_sizes, attn, F.lse_merge, F.kv_cache_append)
+        clip = meta_args.clip_token_nums
+        dn = len(p.np_k_range)
+        chunk_ranges = [(int(a) // clip, int(e) // clip) for a, e in p.np_k_range]
+        sizes = [s // dn for s in meta_args.cp_split_sizes]
+        out, _ = cpm.RingKVScheduler.run(query, kv_local, cache, chunk_ranges, start // clip, clip, dn, sizes,
+                                         app // clip, attn, F.lse_merge)
         core_attn_out = out.view(sq, 1, Hq * F.HEAD_DIM)
         xattn_out = self.cross_attention(mixed_qqkv, key_value_states, meta_args.cross_attn_params)
         return core_attn_out, xattn_out

@@ -202,10 +202,14 @@ def cp_pre_process(cp_size: int, cp_strategy: str, x: torch.Tensor, condition_ma
                    xattn_mask_for_cuda_graph, ardf_meta: dict, core_attn_params: PackedCoreAttnParams,
                    cross_attn_params: PackedCrossAttnParams):
     """context_parallel.py:308-361. Returns (x, condition_map, rope, cp_pad_size, cp_split_sizes, core_attn_params,
-    cross_attn_params). `cp_ring_kv` (new) shards the sequence exactly like `cp_ulysses`."""
+    cross_attn_params). `cp_ring_kv` (new) stripes every chunk across the ranks (`cp_ring_kv_process`)."""
     if cp_size == 1:
         return x, condition_map, rope, None, None, core_attn_params, cross_attn_params
-    if cp_strategy in ("cp_ulysses", "cp_ring_kv"):
+    if cp_strategy == "cp_ring_kv":
+        x, condition_map, rope, cp_split_sizes, cross_attn_params = cp_ring_kv_process(
+            cp_size, x, condition_map, rope, ardf_meta, cross_attn_params)
+        return x, condition_map, rope, 0, cp_split_sizes, core_attn_params, cross_attn_params
+    if cp_strategy == "cp_ulysses":
         x, condition_map, rope, cp_split_sizes, cross_attn_params = cp_ulysses_process(
             cp_size, x, condition_map, rope, xattn_mask_for_cuda_graph, cross_attn_params)
         return x, condition_map, rope, 0, cp_split_sizes, core_attn_params, cross_attn_params
@@ -222,7 +226,9 @@ def cp_post_process(cp_size: int, cp_strategy: str, x: torch.Tensor, meta_args: 
     if cp_strategy == "cp_shuffle_overlap":
         return gather_from_context_parallel_region(x, meta_args.cp_split_sizes, meta_args.denoising_range_num,
                                                    meta_args.cp_pad_size)
-    if cp_strategy in ("cp_ulysses", "cp_ring_kv"):
+    if cp_strategy == "cp_ring_kv":
+        return gather_ring_kv(x, meta_args.cp_split_sizes, meta_args.denoising_range_num)
+    if cp_strategy == "cp_ulysses":
         return gather_from_context_parallel_region(x, meta_args.cp_split_sizes)
     raise ValueError(f"Invalid CP strategy: {cp_strategy}, expected cp_ulysses, cp_shuffle_overlap or cp_ring_kv")
 
@@ -497,93 +503,131 @@ class CSOHelper:
 #####################################################
 # Ring-KV exchange (new capability)
 #####################################################
-def ring_step_ranges(np_q_range: np.ndarray, np_k_range: np.ndarray, seq_start: int, q_off: int, q_len: int,
-                     blk_off: int, blk_len: int, with_cache: bool):
-    """Host-side interval arithmetic for one ring step.
+def ring_split_sizes(clip: int, cp_size: int) -> List[int]:
+    """Rows of EVERY chunk a rank holds under cp_ring_kv: clip // cp (+1 on the first clip % cp ranks). Striping
+    every chunk across the ranks (instead of cutting the flattened sequence into cp contiguous pieces) gives every
+    rank the same share of every (q-range x k-range) rectangle: under the chunk-causal mask a contiguous split leaves
+    the rank holding the last chunk with several times the work of the one holding the first (measured on 8 x B200,
+    24B / 720p state: 4724 vs 8870 TFLOP/s for Ulysses; profiles/README.md)."""
+    return ulysses_split_sizes(clip, cp_size)
 
-    Global coordinates: new-token row g of this forward has key coordinate seq_start + g (dit_module.py:914-931);
-    this rank owns query rows [q_off, q_off + q_len) of the new tokens; the visiting K/V block holds new-token rows
-    [blk_off, blk_off + blk_len). Returns (q_ranges, k_ranges) for the attention call of this step, q rows local to
-    the rank's shard, k rows in the coordinate system concat(cache[0:seq_start] if with_cache else [], block).
-    Rectangles with an empty intersection are dropped (their rows keep out = 0, lse = -inf for the merge)."""
+
+def cp_ring_kv_process(cp_size: int, x: torch.Tensor, condition_map: torch.Tensor, rope: torch.Tensor, ardf_meta: dict,
+                       cross_attn_params: PackedCrossAttnParams):
+    """Pre-processing of cp_ring_kv: per-chunk striped scatter (no padding: uneven slices), cross-attention ranges of
+    the local slices. Local row order is (chunk, slice row). Returns (x, condition_map, rope, cp_split_sizes,
+    cross_attn_params) with cp_split_sizes[r] = dn * (slice rows of rank r), what the exit all-gather needs."""
+    seq_len, N, _ = x.shape
+    assert N == 1, "cp_ring_kv supports batch size 1"
+    dn = ardf_meta["denoising_range_num"]
+    clip = divide(seq_len, dn)
+    sizes = ring_split_sizes(clip, cp_size)
+    rank = mpu.get_cp_rank()
+    lo, n = sum(sizes[:rank]), sizes[rank]
+
+    def stripe(t):
+        return t.unflatten(0, (dn, clip))[:, lo:lo + n].flatten(0, 1).contiguous()
+
+    x, condition_map, rope = stripe(x), stripe(condition_map), stripe(rope)
+    # every local chunk slice is one query segment against that chunk's caption (dit_model.py:215-259)
+    kv = cross_attn_params.kv_ranges
+    cu_k = cross_attn_params.cu_seqlens_kv
+    q_ranges = torch.arange(dn + 1, dtype=torch.int32, device=kv.device) * n
+    cross = PackedCrossAttnParams(q_ranges=torch.stack([q_ranges[:-1], q_ranges[1:]], 1), kv_ranges=kv,
+                                  cu_seqlens_q=q_ranges, cu_seqlens_kv=cu_k, max_seqlen_q=n,
+                                  max_seqlen_kv=cross_attn_params.max_seqlen_kv)
+    return x, condition_map, rope, [dn * s_ for s_ in sizes], cross
+
+
+def gather_ring_kv(input_: torch.Tensor, cp_split_sizes: List[int], dn: int) -> torch.Tensor:
+    """Exit all-gather of cp_ring_kv: stripes padded to the widest one (equal-sized messages),
+    then "(cp dn n_r) -> dn (cp n_r)" with the padding dropped."""
+    world = mpu.get_cp_world_size()
+    if world == 1:
+        return input_
+    sizes = [divide(s_, dn) for s_ in cp_split_sizes]
+    n_max = max(sizes)
+    tail = tuple(input_.shape[1:])
+    mine = input_.unflatten(0, (dn, input_.shape[0] // dn))
+    if mine.shape[1] < n_max:
+        mine = torch.nn.functional.pad(mine, [0, 0] * len(tail) + [0, n_max - mine.shape[1]])
+    output = torch.empty((world, dn, n_max) + tail, dtype=input_.dtype, device=input_.device)
+    dist.all_gather(list(output.unbind(0)), mine.contiguous(), group=mpu.get_cp_group())
+    return torch.cat([output[r, :, :sizes[r]] for r in range(world)], dim=1).flatten(0, 1)
+
+
+def ring_step_ranges(chunk_ranges: Sequence[Tuple[int, int]], slice_point: int, clip: int, n_q: int, n_blk: int,
+                     with_cache: bool):
+    """Host-side interval arithmetic for one ring step under the striped sharding.
+
+    chunk_ranges[i] = (s_i, e_i): query chunk i attends absolute chunks [s_i, e_i) (dit_module.py:914-931 coordinates
+    divided by clip); chunks below slice_point live in the (replicated) KV cache, the in-flight chunk j is absolute
+    chunk slice_point + j. This rank's queries of chunk i are local rows [i * n_q, (i + 1) * n_q); the visiting block
+    holds, for every in-flight chunk j, rows [j * n_blk, (j + 1) * n_blk) - chunk order, so the in-flight part of a
+    range is ONE contiguous interval of the block. Returns (q_ranges, k_ranges) with k rows in the coordinates of
+    concat(cache[: slice_point * clip] if with_cache else [], block). The cached part of a range is attended exactly
+    once, in the step that has with_cache (it is contiguous with the block part, which then starts at block row 0).
+    Rectangles with an empty key interval are dropped (their rows keep out = 0, lse = -inf for the merge)."""
     qs, ks = [], []
-    base = seq_start if with_cache else 0
-    for (q0, q1), (k0, k1) in zip(np.asarray(np_q_range).reshape(-1, 2), np.asarray(np_k_range).reshape(-1, 2)):
-        a, b = max(int(q0), q_off), min(int(q1), q_off + q_len)
-        if a >= b:
+    base = slice_point * clip if with_cache else 0
+    for i, (s_i, e_i) in enumerate(chunk_ranges):
+        b0, b1 = max(s_i, slice_point) - slice_point, max(e_i, slice_point) - slice_point   # in-flight chunks
+        k0, k1 = base + b0 * n_blk, base + b1 * n_blk
+        if with_cache and s_i < slice_point:
+            k0 = s_i * clip
+            if e_i <= slice_point:
+                k1 = e_i * clip
+        if k0 >= k1 or n_q == 0:
             continue
-        nb0 = max(int(k0), seq_start + blk_off)
-        nb1 = min(int(k1), seq_start + blk_off + blk_len)
-        lo = hi = None
-        if nb0 < nb1:   # part of the range inside the visiting block
-            lo, hi = base + nb0 - (seq_start + blk_off), base + nb1 - (seq_start + blk_off)
-        if with_cache and int(k0) < seq_start:   # part of the range inside the cache prefix
-            c0, c1 = int(k0), min(int(k1), seq_start)
-            if lo is None:
-                lo, hi = c0, c1
-            else:
-                # contiguous by construction: a range that reaches the cache and this block covers [seq_start,
-                # seq_start + blk_off) entirely, which is only non-empty for blocks other than the first
-                assert c1 == seq_start and nb0 == seq_start + blk_off
-                if blk_off != 0:
-                    raise AssertionError("cache part must be folded into the step whose block starts at row 0 "
-                                         "or handled as a separate rectangle")
-                lo = c0
-        if lo is None:
-            continue
-        qs.append([a - q_off, b - q_off])
-        ks.append([lo, hi])
+        qs.append([i * n_q, (i + 1) * n_q])
+        ks.append([k0, k1])
     return (np.asarray(qs, dtype=np.int32).reshape(-1, 2), np.asarray(ks, dtype=np.int32).reshape(-1, 2))
 
 
 class RingKVScheduler:
-    """Sequence-sharded attention: every rank keeps its contiguous query shard with ALL heads; the packed K/V blocks
+    """Sequence-sharded attention: every rank keeps a stripe of every query chunk with ALL heads; the packed K/V blocks
     of the new tokens travel around the ring (cp - 1 point-to-point steps, next transfer in flight while the current
     block is attended), partial results are merged with their log-sum-exp. The KV cache of clean chunks is kept
-    replicated (full heads, full sequence) on every rank: each visiting block is appended as it passes, which at
-    24B / 720p / 8 chunks is 34 GB of the 180 GB per GPU and means cached chunks are never re-communicated.
-    Oracle: the single-GPU result; the reference has no ring attention."""
+    replicated (full heads, full sequence, chunk-major) on every rank: each visiting block is scattered into it as it
+    passes, which at 24B / 720p / 8 chunks is 34 GB of the 180 GB per GPU and means cached chunks are never
+    re-communicated. Oracle: the single-GPU result; the reference has no ring attention."""
 
     @staticmethod
-    def run(query: torch.Tensor, kv_local: torch.Tensor, cache: Optional[torch.Tensor], np_q_range: np.ndarray,
-            np_k_range: np.ndarray, seq_start: int, cache_rows_limit: int, cp_split_sizes: Sequence[int],
-            attn_func: Callable, merge_func: Callable, append_func: Optional[Callable]):
-        """query (S_loc, Hq, 128); kv_local packed (S_loc, Hkv, 256); cache packed (max_seq, Hkv, 256) or None.
-        attn_func(q, kv_block, cache_prefix_or_None, q_ranges, k_ranges) -> (out, lse) with uncovered rows 0 / -inf;
-        merge_func(out_a, lse_a, out_b, lse_b) merges in place into a; append_func(cache, block, row_offset, rows).
-        cache_rows_limit: number of leading new-token rows that go to the cache (0 = no update)."""
-        cp = mpu.get_cp_world_size()
-        rank = mpu.get_cp_rank()
-        group = mpu.get_cp_group()
-        offs = np.concatenate([[0], np.cumsum(np.asarray(cp_split_sizes, dtype=np.int64))]).astype(np.int64)
-        q_off, q_len = int(offs[rank]), int(cp_split_sizes[rank])
-        max_len = int(max(cp_split_sizes))
+    def run(query: torch.Tensor, kv_local: torch.Tensor, cache: Optional[torch.Tensor],
+            chunk_ranges: Sequence[Tuple[int, int]], slice_point: int, clip: int, dn: int, sizes: Sequence[int],
+            cache_chunks: int, attn_func: Callable, merge_func: Callable):
+        """query (dn * n_me, Hq, 128); kv_local packed (dn * n_me, Hkv, 256); cache packed (max_seq, Hkv, 256) or None.
+        sizes[r]: rows of every chunk on rank r. cache_chunks: leading in-flight chunks that go to the cache (0 = no
+        update). attn_func(q, kv_block, cache_prefix_or_None, q_ranges, k_ranges) -> (out, lse) with uncovered rows
+        0 / -inf; merge_func(out_a, lse_a, out_b, lse_b) merges in place into a."""
+        cp, rank, group = mpu.get_cp_world_size(), mpu.get_cp_rank(), mpu.get_cp_group()
+        offs = np.concatenate([[0], np.cumsum(np.asarray(sizes, dtype=np.int64))]).astype(np.int64)
+        n_me, n_max = int(sizes[rank]), int(max(sizes))
         nxt, prv = mpu.cp_global_rank((rank + 1) % cp), mpu.cp_global_rank((rank - 1) % cp)
-        bufs = [torch.empty((max_len,) + tuple(kv_local.shape[1:]), dtype=kv_local.dtype, device=kv_local.device)
+        tail = tuple(kv_local.shape[1:])
+        bufs = [torch.empty((dn * n_max,) + tail, dtype=kv_local.dtype, device=kv_local.device)
                 for _ in range(2)] if cp > 1 else []
         cur = kv_local
         out = lse = None
+        seq_start = slice_point * clip
         for step in range(cp):
             src = (rank - step) % cp
-            blk_off, blk_len = int(offs[src]), int(cp_split_sizes[src])
+            n_blk = int(sizes[src])
             reqs = None
             if step + 1 < cp:
-                # forward the block we hold to the next rank while we attend to it
-                send = cur if cur.shape[0] == max_len else torch.nn.functional.pad(
-                    cur, [0, 0] * (cur.dim() - 1) + [0, max_len - cur.shape[0]])
+                # forward the block we hold to the next rank while we attend to it (fixed-size messages)
+                send = cur if cur.shape[0] == dn * n_max else torch.nn.functional.pad(
+                    cur[:dn * n_blk], [0, 0] * (cur.dim() - 1) + [0, dn * n_max - dn * n_blk])
                 ops = [dist.P2POp(dist.isend, send.contiguous(), nxt, group=group),
                        dist.P2POp(dist.irecv, bufs[step % 2], prv, group=group)]
                 reqs = dist.batch_isend_irecv(ops)
-            blk = cur[:blk_len]
-            if cache is not None and append_func is not None and cache_rows_limit > blk_off:
-                append_func(cache, blk, seq_start + blk_off, min(blk_len, cache_rows_limit - blk_off))
-            # the cache prefix joins the step whose block starts at new-token row 0 (contiguous coordinates)
-            with_cache = cache is not None and seq_start > 0 and blk_off == 0
-            qr, kr = ring_step_ranges(np_q_range, np_k_range, seq_start, q_off, q_len, blk_off, blk_len, with_cache)
-            if cache is not None and seq_start > 0 and blk_off != 0:
-                # ranges that reach into the cache but whose new-token part does not touch this block are covered
-                # in the blk_off == 0 step; nothing to do here
-                pass
+            blk = cur[:dn * n_blk]
+            if cache is not None and cache_chunks > 0 and n_blk > 0:
+                # replicated cache, chunk-major: chunk j of the block goes to rows [(sp + j) * clip + offs[src], + n_blk)
+                dst = cache[seq_start:seq_start + cache_chunks * clip].unflatten(0, (cache_chunks, clip))
+                dst[:, int(offs[src]):int(offs[src]) + n_blk].copy_(blk.unflatten(0, (dn, n_blk))[:cache_chunks])
+            with_cache = cache is not None and seq_start > 0 and step == 0
+            qr, kr = ring_step_ranges(chunk_ranges, slice_point, clip, n_me, n_blk, with_cache)
             if qr.shape[0] > 0:
                 o, l = attn_func(query, blk, cache[:seq_start] if with_cache else None, qr, kr)
                 if out is None:

@@ -232,11 +232,13 @@ def _ring_worker(rank, world, port, errq):
         cached = bfr(rng.standard_normal((seq_start, Hkv, 256)))
         q_range = O.core_q_ranges(clip, dn, 1)
         k_range = np.array([[0, 2 * clip], [clip, 3 * clip], [0, 4 * clip]], dtype=np.int32)   # window + full ranges
-        split = cpm.ulysses_split_sizes(S, world)
-        off = sum(split[:rank])
+        sizes = cpm.ring_split_sizes(clip, world)  # rows of EVERY chunk on each rank (striped sharding)
+        lo, n = sum(sizes[:rank]), sizes[rank]
+        stripe = lambda a: a.reshape((dn, clip) + a.shape[1:])[:, lo:lo + n].reshape((dn * n,) + a.shape[1:])
         cache = torch.zeros(5 * clip, Hkv, 256, dtype=torch.bfloat16)
         cache[:seq_start] = n2t(cached)
-        limit = S - clip                           # distill_nearly_clean_chunk: last chunk is not cached
+        cache_chunks = dn - 1                      # distill_nearly_clean_chunk: last chunk is not cached
+        limit = cache_chunks * clip
 
         def attn(q, blk, cache_prefix, qr, kr):
             kvc = t2n(blk) if cache_prefix is None else np.concatenate([t2n(cache_prefix), t2n(blk)], axis=0)
@@ -248,22 +250,24 @@ def _ring_worker(rank, world, port, errq):
             oa.copy_(n2t(o))
             la.copy_(torch.from_numpy(l))
 
-        def append(c, blk, row, rows):
-            c[row:row + rows] = blk[:rows]
-
-        out, lse = cpm.RingKVScheduler.run(n2t(q_full[off:off + split[rank]]), n2t(kv_full[off:off + split[rank]]),
-                                           cache, q_range, k_range, seq_start, limit, split, attn, merge, append)
+        chunk_ranges = [(int(a) // clip, int(b) // clip) for a, b in k_range]
+        out, lse = cpm.RingKVScheduler.run(n2t(stripe(q_full)), n2t(stripe(kv_full)), cache, chunk_ranges, sp, clip, dn,
+                                           sizes, cache_chunks, attn, merge)
         full_kv = np.concatenate([cached, kv_full], axis=0)
         ref, ref_lse = O.attn_ranges(q_full, full_kv[..., :128], full_kv[..., 128:], q_range, k_range,
                                      round_output=False)
-        err = np.abs(t2n(out) - ref[off:off + split[rank]]).max()
+        err = np.abs(t2n(out) - stripe(ref)).max()
         assert err < 2.5e-2, err                   # one extra bf16 rounding per merge step
-        assert np.abs(lse.numpy() - ref_lse[off:off + split[rank]]).max() < 1e-3
+        assert np.abs(lse.numpy() - stripe(ref_lse)).max() < 1e-3
         # replicated cache: every rank ends with the same rows as the single-rank cache update (dit_module.py:918-929)
         exp = torch.zeros_like(cache)
         exp[:seq_start] = n2t(cached)
         exp[seq_start:seq_start + limit] = n2t(kv_full[:limit])
         assert torch.equal(cache, exp)
+        # exit gather puts the stripes back in (chunk, row) order
+        mine = torch.from_numpy(stripe(np.arange(S, dtype=np.float32)[:, None].repeat(3, 1)))
+        back = cpm.gather_ring_kv(mine, [dn * s_ for s_ in sizes], dn)
+        assert torch.equal(back[:, 0], torch.arange(S, dtype=torch.float32))
         dist.barrier()
     except Exception:
         errq.put(f"rank {rank}:\n{traceback.format_exc()}")
@@ -326,31 +330,34 @@ def test_head_groups_are_contiguous_and_cover():
 
 
 def test_ring_step_ranges_partition_every_rectangle():
-    """Over all ring steps of all ranks, the emitted (q, k) rectangles tile exactly the original rectangles."""
-    from magi_b200.context_parallel import ring_step_ranges, ulysses_split_sizes
+    """Over all ring steps of all ranks, the emitted (q, k) rectangles tile exactly the original rectangles
+    (striped sharding: rank r holds rows [offs[r], offs[r+1]) of EVERY chunk)."""
+    from magi_b200.context_parallel import ring_step_ranges, ring_split_sizes
     clip, dn, sp = 50, 3, 2
     seq_start = sp * clip
-    q_range = np.array([[i * clip, (i + 1) * clip] for i in range(dn)])
-    k_range = np.array([[0, 3 * clip], [clip, 4 * clip], [3 * clip, 5 * clip]])
-    for cp in (2, 3, 4):
-        split = ulysses_split_sizes(dn * clip, cp)
-        offs = np.concatenate([[0], np.cumsum(split)])
+    chunk_ranges = [(0, 3), (1, 4), (3, 5)]
+    for cp in (2, 3, 4, 7):
+        sizes = ring_split_sizes(clip, cp)
+        offs = np.concatenate([[0], np.cumsum(sizes)])
         cover = np.zeros((dn * clip, 5 * clip), dtype=np.int32)
         for r in range(cp):
             for step in range(cp):
                 src = (r - step) % cp
-                with_cache = offs[src] == 0
-                qr, kr = ring_step_ranges(q_range, k_range, seq_start, int(offs[r]), split[r], int(offs[src]),
-                                          split[src], with_cache)
+                with_cache = step == 0
+                n_q, n_blk = sizes[r], sizes[src]
+                qr, kr = ring_step_ranges(chunk_ranges, sp, clip, n_q, n_blk, with_cache)
                 base = seq_start if with_cache else 0
                 for (a, b), (c, d) in zip(qr, kr):
+                    assert a % n_q == 0 and b - a == n_q
+                    rows = (a // n_q) * clip + offs[r] + np.arange(n_q)
                     for kk in range(c, d):
                         if with_cache and kk < seq_start:
                             col = kk
                         else:
-                            col = seq_start + offs[src] + (kk - base)
-                        cover[offs[r] + a:offs[r] + b, col] += 1
+                            j, t = divmod(kk - base, n_blk)
+                            col = seq_start + j * clip + offs[src] + t
+                        cover[rows, col] += 1
         exp = np.zeros_like(cover)
-        for (a, b), (c, d) in zip(q_range, k_range):
-            exp[a:b, c:d] = 1
+        for i, (s_i, e_i) in enumerate(chunk_ranges):
+            exp[i * clip:(i + 1) * clip, s_i * clip:e_i * clip] = 1
         assert np.array_equal(cover, exp), cp
