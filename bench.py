@@ -122,11 +122,13 @@ class HotPath:
     """Synthetic inputs of one denoise forward's attention hot path, resident in HBM, and the per-layer launch
     sequence through the public API (magi_b200.functional -> C-ABI)."""
 
-    def __init__(self, w, device, cp=1, rank=0, seed=1234, fused=True, ring=False):
+    def __init__(self, w, device, cp=1, rank=0, seed=1234, fused=True, ring=False, ring_fused=True):
         import torch
         import magi_b200.functional as F
         self.torch, self.F, self.w, self.cp, self.rank, self.dev = torch, F, w, cp, rank, device
         self.ring = ring and cp > 1
+        self.ring_fused = self.ring and ring_fused
+        self.ring_multicast = False
         self.fused = fused and cp > 1 and not self.ring
         Hq, Hkv, clip = w["Hq"], w["Hkv"], w["clip"]
         self.S = clip * len(w["k_chunks"])
@@ -179,15 +181,23 @@ class HotPath:
         self.hq_loc = Hq // cp
         self.cache_rows = (sp + n) * clip
         self.start = sp * clip
-        if self.fused:
-            # fused all-to-alls: caches and receive buffers live in symmetric (NVLink peer-mapped) memory
+        if self.fused or self.ring_fused:
+            # fused all-to-alls / all-gather: caches and receive buffers live in symmetric (NVLink peer-mapped) memory
             import torch.distributed._symmetric_memory as symm
             from magi_b200 import parallel_state as mpu
-            self.caches, self.cache_ptrs = [], []
+            self.caches, self.cache_ptrs, self.cache_mc = [], [], []
             for _ in range(w["layers"]):
                 c = symm.empty((self.cache_rows, self.hkv_loc, 256), dtype=torch.bfloat16, device=device)
-                self.cache_ptrs.append([int(p_) for p_ in symm.rendezvous(c, mpu.get_cp_group().group_name).buffer_ptrs])
+                h_ = symm.rendezvous(c, mpu.get_cp_group().group_name)
+                self.cache_ptrs.append([int(p_) for p_ in h_.buffer_ptrs])
+                self.cache_mc.append(int(getattr(h_, "multicast_ptr", 0) or 0))
                 self.caches.append(c)
+        if self.ring_fused:
+            self.ring_ws = cpm.RingGatherWorkspace.get(mpu.get_cp_group(), self.S, Hkv, device)
+            self.ring_multicast = cpm.ring_multicast_enabled() and all(self.cache_mc)
+            e = torch.arange(n + 1, dtype=torch.int32) * self.ring_sizes[rank]
+            self.stripe_q_ranges = torch.stack([e[:-1], e[1:]], 1).contiguous().to(device)
+        elif self.fused:
             self.ws = cpm.UlyssesPeerWorkspace.get(mpu.get_cp_group(), self.S, max(self.split), self.hq_loc,
                                                    self.hkv_loc, Hq, device)
             self.row_off, self.bounds, self.head_off = cpm.fused_ulysses_plan(self.split, rank, Hq, cp)
@@ -338,10 +348,37 @@ class HotPath:
         self.core_out = out
         self.cross(inp)
 
+    # -- one layer, ring-KV with the exchange fused into the prologue (FullyParallelAttention._forward_ring_fused): the
+    #    K/V stores of the prologue ARE the all-gather (NVLink peer stores or one NVSwitch multicast store per row),
+    #    straight into every rank's replicated cache slot; one device barrier; one attention launch per rank
+    def layer_cp_ring_fused(self, l, timed_events=False):
+        F, w, inp, torch = self.F, self.w, self.inputs, self.torch
+        cache = self.caches[l]
+        slot = self.start * w["Hkv"] * 256 * 2
+        targets = [self.cache_mc[l] + slot] if self.ring_multicast else [p_ + slot for p_ in self.cache_ptrs[l]]
+        q, _ = F.qk_norm_rope(inp["xq"], inp["xk"], inp["xv"], w["Hq"], w["Hkv"], self.ln["q"], self.ln["k"],
+                              inp["sin"], inp["cos"], gather_kv_out=targets,
+                              gather_geometry=(self.ring_sizes[self.rank], w["clip"], sum(self.ring_sizes[:self.rank])))
+        x_prepared = self.cross_prepare(inp)
+        self.ring_ws.barrier()
+        kv = cache[self.start:self.start + self.S]
+        kc = vc = None
+        if self.start > 0:
+            kc, vc = cache[:self.start, :, :128], cache[:self.start, :, 128:]
+        if timed_events:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        F.attn_ranges(q, kv[..., :128], kv[..., 128:], self.stripe_q_ranges, self.k_ranges, k_cache=kc, v_cache=vc,
+                      out=self.core_out, return_lse=False)
+        if timed_events:
+            e1.record()
+            self.attn_events.append((e0, e1))
+        self.cross_attend(x_prepared)
+
     ulysses_overlap_degree = 1
 
     def step(self, timed_events=False):
-        fn = (self.layer_cp_ring if self.ring else self.layer_cp_fused if self.fused else self.layer_cp) \
+        fn = (self.layer_cp_ring_fused if self.ring_fused else self.layer_cp_ring if self.ring else self.layer_cp_fused if self.fused else self.layer_cp) \
             if self.cp > 1 else self.layer
         for l in range(self.w["layers"]):
             fn(l, timed_events)
@@ -503,9 +540,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--overlap-degree", type=int, default=1)
-    ap.add_argument("--cp-mode", default="fused", choices=["fused", "nccl", "ring"],
+    ap.add_argument("--cp-mode", default="fused", choices=["fused", "nccl", "ring", "ring-nccl"],
                     help="N > 1: Ulysses with the all-to-alls fused into the kernels' stores over NVLink peer memory, "
-                         "Ulysses with NCCL all_to_all_single, or the ring-KV exchange (sequence sharded)")
+                         "Ulysses with NCCL all_to_all_single, sequence-sharded ring-KV with the K/V all-gather fused "
+                         "into the prologue's stores, or the NCCL send/recv ring")
     ap.add_argument("--ref-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -535,7 +573,8 @@ def main():
         mpu.initialize_model_parallel(cp_size=world)
     from magi_b200 import _lib
 
-    hp = HotPath(w, dev, cp=world, rank=rank, fused=args.cp_mode == "fused", ring=args.cp_mode == "ring")
+    hp = HotPath(w, dev, cp=world, rank=rank, fused=args.cp_mode == "fused", ring=args.cp_mode.startswith("ring"),
+                 ring_fused=args.cp_mode == "ring")
     hp.ulysses_overlap_degree = args.overlap_degree
     self_f, cross_f = attn_flops(w)
     step_flops = (self_f + cross_f) * w["layers"]
@@ -649,7 +688,7 @@ def main():
                       + (", copies double-buffered on a copy stream" if world == 1 else "")}
 
     dit = None
-    if not args.no_dit_step and args.cp_mode != "ring":
+    if not args.no_dit_step and not args.cp_mode.startswith("ring"):
         dit = dit_step_leg(w, dev, world, rank, min(args.steps, 3), max_over_ranks, barrier)
 
     cpu = None
@@ -664,7 +703,11 @@ def main():
             "config": {"workload": w["desc"], "name": args.workload,
                        "parallelism": "none" if world == 1 else (
                            f"cp_ulysses{world}, all-to-alls fused into the kernels' stores (NVLink peer memory), 2 barriers "
-                           f"per layer" if hp.fused else f"cp_ring_kv{world}, K/V blocks round the ring by NCCL send/recv, "
+                           f"per layer" if hp.fused else
+                           f"cp_ring_kv{world} (every chunk striped across the ranks), K/V all-gather fused into the "
+                           f"prologue's stores ({'NVSwitch multicast' if hp.ring_multicast else 'NVLink peer stores'}) "
+                           f"into the replicated cache slot, 1 barrier per layer" if hp.ring_fused else
+                           f"cp_ring_kv{world}, K/V blocks round the ring by NCCL send/recv, "
                            f"log-sum-exp merge, replicated cache" if hp.ring else
                            f"cp_ulysses{world}, NCCL all_to_all_single (overlap_degree {args.overlap_degree})"),
                        "step": "attention hot path of one denoise forward over all layers: fused LN+RoPE prologue with "

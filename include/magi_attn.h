@@ -162,6 +162,18 @@ typedef struct magi_prologue_args {
   void* peer_q_out[MAGI_MAX_PEERS];
   void* peer_kv_out[MAGI_MAX_PEERS];
   int64_t peer_row_offset;
+  /* Fused K/V all-gather for the sequence-sharded strategy cp_ring_kv (gather_peers > 0; head_perm_cp <= 1, no cache,
+   * num_peers == 0): q goes to q_out as usual; every K/V row r of this rank's stripe is stored into ALL
+   * gather_peers ranks' gathered in-flight K/V buffers (this rank's own included), packed (rows, Hkv, 256) with the
+   * kv_out strides, at row
+   *   (r / gather_rows_per_chunk) * gather_chunk_stride + gather_row_offset + (r % gather_rows_per_chunk)
+   * i.e. chunk-major: local rows are (chunk, stripe row), gather_chunk_stride = tokens per chunk, gather_row_offset =
+   * first row of this rank's stripe inside a chunk. The stores are the transfer (NVLink peer memory); kv_out is
+   * unused (may be NULL). Replaces the cp - 1 ring steps of K/V blocks (new capability: the reference has no
+   * sequence-sharded attention). The caller owns the cross-GPU synchronisation. */
+  int32_t gather_peers; /* 0 = off */
+  void* gather_kv_out[MAGI_MAX_PEERS];
+  int64_t gather_rows_per_chunk, gather_chunk_stride, gather_row_offset;
 } magi_prologue_args;
 
 MAGI_API int magi_qk_norm_rope_fwd(const magi_prologue_args* args, void* stream);

@@ -112,6 +112,11 @@ class MagiPrologueArgs(C.Structure):
         ("peer_q_out", C.c_void_p * MAX_PEERS),
         ("peer_kv_out", C.c_void_p * MAX_PEERS),
         ("peer_row_offset", C.c_int64),
+        ("gather_peers", C.c_int32),
+        ("gather_kv_out", C.c_void_p * MAX_PEERS),
+        ("gather_rows_per_chunk", C.c_int64),
+        ("gather_chunk_stride", C.c_int64),
+        ("gather_row_offset", C.c_int64),
     ]
 
 

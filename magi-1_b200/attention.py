@@ -191,13 +191,15 @@ class FullyParallelAttention(nn.Module):
         if self.engine_config.kv_offload:
             # dit_module.py:803-811: the cache lives in pinned host memory; see KVOffload for how it is staged
             return torch.empty(shape, dtype=dtype, device="cpu", pin_memory=True)
-        if self._fused_ulysses(batch_size, device):
-            # fused Ulysses: the cache lives in symmetric (NVLink peer-mapped) memory so that the other ranks'
-            # prologue kernels store their K/V rows straight into the cache slot. Collective: every rank of the
-            # group allocates its layer cache in the same forward.
+        if self._fused_ulysses(batch_size, device) or self._fused_ring(batch_size, device):
+            # fused Ulysses / fused ring-KV: the cache lives in symmetric (NVLink peer-mapped) memory so that the other
+            # ranks' prologue kernels store their K/V rows straight into the cache slot. Collective: every rank of
+            # the group allocates its layer cache in the same forward.
             import torch.distributed._symmetric_memory as symm
             cache = symm.empty(shape, dtype=dtype, device=device)
-            self._cache_peer_ptrs = [int(p_) for p_ in symm.rendezvous(cache, mpu.get_cp_group().group_name).buffer_ptrs]
+            handle = symm.rendezvous(cache, mpu.get_cp_group().group_name)
+            self._cache_peer_ptrs = [int(p_) for p_ in handle.buffer_ptrs]
+            self._cache_mc_ptr = int(getattr(handle, "multicast_ptr", 0) or 0)
             self._cache_peer_of = cache.data_ptr()
             return cache
         return torch.empty(shape, dtype=dtype, device=device)
@@ -206,6 +208,11 @@ class FullyParallelAttention(nn.Module):
         return (self.engine_config.cp_strategy == "cp_ulysses" and batch_size == 1 and not self.engine_config.kv_offload
                 and getattr(self.engine_config, "cp_fused_all_to_all", False)
                 and cpm.UlyssesPeerWorkspace.available(mpu.get_cp_group(), device))
+
+    def _fused_ring(self, batch_size, device) -> bool:
+        return (self.engine_config.cp_strategy == "cp_ring_kv" and batch_size == 1 and not self.engine_config.kv_offload
+                and getattr(self.engine_config, "cp_fused_all_to_all", False)
+                and cpm.RingGatherWorkspace.available(mpu.get_cp_group(), device))
 
     def _cache(self, inference_params: InferenceParams, dtype, device):
         d = inference_params.key_value_memory_dict
@@ -474,7 +481,8 @@ class FullyParallelAttention(nn.Module):
             fwd = self._forward_ulysses_fused if self._fused_ulysses(batch_size, dev) else self._forward_ulysses
             core_attn_out, xattn_out = fwd(mixed_qqkv, key_value_states, inference_params, sin_emb, cos_emb, meta_args)
         elif strategy == "cp_ring_kv":
-            core_attn_out, xattn_out = self._forward_ring(mixed_qqkv, key_value_states, inference_params, sin_emb,
+            fwd = self._forward_ring_fused if self._fused_ring(batch_size, dev) else self._forward_ring
+            core_attn_out, xattn_out = fwd(mixed_qqkv, key_value_states, inference_params, sin_emb,
                                                           cos_emb, meta_args)
         elif strategy == "cp_shuffle_overlap":
             core_attn_out, xattn_out = self._forward_cso(mixed_qqkv, key_value_states, inference_params, sin_emb,
@@ -661,6 +669,66 @@ class FullyParallelAttention(nn.Module):
         return result.view(sq, b, Hq * F.HEAD_DIM), xattn_out
 
     # ------------------------------------------------------------------ ring-KV (new)
+    _stripe_ranges = {}
+
+    def _forward_ring_fused(self, mixed_qqkv, key_value_states, inference_params, sin_emb, cos_emb, meta_args):
+        """cp_ring_kv without NCCL on the data path and without ring steps: the prologue kernel stores this rank's
+        stripe of every in-flight chunk's [K|V] into EVERY rank's gathered buffer (NVLink peer stores, or one store
+        to the NVSwitch multicast mapping), chunk-major - straight into the replicated KV-cache slot when every row of
+        the forward is cached. One device-side barrier, then ONE attention launch of the local query stripe against
+        cache ++ gathered K/V with the unmodified k ranges: the same per-row key order as the single-GPU forward,
+        hence the same values, and no log-sum-exp merges (`_forward_ring` is the NCCL send/recv ring it replaces)."""
+        sq, b, _ = mixed_qqkv.shape
+        assert b == 1
+        group, rank = mpu.get_cp_group(), mpu.get_cp_rank()
+        Hq, Hkv = self.model_config.num_attention_heads, self.model_config.num_query_groups
+        eps, z = self.model_config.layernorm_epsilon, self.model_config.apply_layernorm_1p
+        dev, dt = mixed_qqkv.device, mixed_qqkv.dtype
+        p = meta_args.core_attn_params
+        clip, dn = meta_args.clip_token_nums, len(p.np_k_range)
+        sizes = [s // dn for s in meta_args.cp_split_sizes]
+        n_me, off_me = sizes[rank], sum(sizes[:rank])
+        total_rows = dn * clip
+        cache, start, app = self._cache_plan(inference_params, meta_args, total_rows, dt, dev)
+        ws = cpm.RingGatherWorkspace.get(group, total_rows, Hkv, dev)
+        buf, ptrs, mc = ws.next()
+        direct = (cache is not None and app == total_rows
+                  and getattr(self, "_cache_peer_of", None) == cache.data_ptr())
+        if direct:
+            slot = start * Hkv * 2 * F.HEAD_DIM * 2
+            ptrs = [p_ + slot for p_ in self._cache_peer_ptrs]
+            mc = self._cache_mc_ptr + slot if self._cache_mc_ptr else 0
+        targets = [mc] if (mc and cpm.ring_multicast_enabled()) else ptrs
+        query = None
+        if sq > 0:
+            xq, xk, xv = self._project(mixed_qqkv)
+            query, _ = F.qk_norm_rope(xq, xk, xv, Hq, Hkv, self._ln(self.q_layernorm), self._ln(self.k_layernorm),
+                                      sin_emb, cos_emb, batch=1, eps=eps, zero_centered_gamma=z,
+                                      gather_kv_out=targets, gather_geometry=(n_me, clip, off_me))
+        x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states)
+        ws.barrier()                                              # every rank's K/V stripes have landed everywhere
+        kv = cache[start:start + total_rows] if direct else buf[:total_rows]
+        if cache is not None and app > 0 and not direct:
+            F.kv_cache_append(cache, kv, start, app)
+        kc = vc = None
+        if cache is not None and start > 0:
+            kc, vc = cache[:start, :, :F.HEAD_DIM], cache[:start, :, F.HEAD_DIM:]
+        out = torch.empty((sq, Hq, F.HEAD_DIM), dtype=dt, device=dev)
+        if sq > 0:
+            key = (dn, n_me, str(dev))
+            q_range = self._stripe_ranges.get(key)
+            if q_range is None:    # local rows are (chunk, stripe row): chunk i = rows [i * n_me, (i + 1) * n_me)
+                e = torch.arange(dn + 1, dtype=torch.int32) * n_me
+                q_range = self._stripe_ranges[key] = torch.stack([e[:-1], e[1:]], 1).contiguous().to(dev)
+            F.attn_ranges(query, kv[..., :F.HEAD_DIM], kv[..., F.HEAD_DIM:], q_range, p.k_range, k_cache=kc, v_cache=vc,
+                          out=out, return_lse=False)
+        xattn_out = self.cross_attention_attend(x_prepared, (sq, b), meta_args.cross_attn_params)
+        if direct and self.model_config.num_layers < 2:
+            # the peers' next forward writes this layer's cache slot again: with a single layer there is no other
+            # layer's barrier between this attention and that prologue
+            ws.barrier()
+        return out.view(sq, 1, Hq * F.HEAD_DIM), xattn_out
+
     def _forward_ring(self, mixed_qqkv, key_value_states, inference_params, sin_emb, cos_emb, meta_args):
         sq, b, _ = mixed_qqkv.shape
         if b != 1:

@@ -556,6 +556,59 @@ def gather_ring_kv(input_: torch.Tensor, cp_split_sizes: List[int], dn: int) -> 
     return torch.cat([output[r, :, :sizes[r]] for r in range(world)], dim=1).flatten(0, 1)
 
 
+class RingGatherWorkspace:
+    """In-flight K/V buffers of the fused cp_ring_kv path, in symmetric memory (same virtual layout on every rank,
+    peer-mapped over NVLink, plus an NVSwitch multicast mapping when the fabric offers one):
+
+        kv[2]  (max in-flight rows, Hkv, 256)   every rank's prologue kernel stores its stripe of every chunk into
+                                                EVERY rank's buffer, chunk-major (= the single-GPU row order)
+
+    The cp - 1 ring steps of K/V blocks, their attention launches and log-sum-exp merges collapse into: one prologue
+    launch whose K/V stores are the all-gather, ONE device-side barrier, one attention launch per rank over its query
+    stripe. Two buffers used alternately make one barrier per layer enough: a rank that writes buffer b for call n has
+    passed the barrier of call n - 1, which every rank enters only after its attention of call n - 2 (the previous
+    reader of b) in stream order."""
+
+    _instances = {}
+
+    def __init__(self, group, rows: int, heads_kv: int, device):
+        import torch.distributed._symmetric_memory as symm
+        self.group, self.rows, self.calls = group, rows, 0
+        self.kv, self.handles, self.ptrs, self.mc_ptrs = [], [], [], []
+        for _ in range(2):
+            t = symm.empty((rows, heads_kv, 256), dtype=torch.bfloat16, device=device)
+            h = symm.rendezvous(t, group.group_name)
+            self.kv.append(t)
+            self.handles.append(h)
+            self.ptrs.append([int(p) for p in h.buffer_ptrs])
+            self.mc_ptrs.append(int(getattr(h, "multicast_ptr", 0) or 0))
+
+    def next(self):
+        """(buffer, peer pointers, multicast pointer or 0) for this call; every rank makes the same sequence of calls."""
+        b = self.calls % 2
+        self.calls += 1
+        return self.kv[b], self.ptrs[b], self.mc_ptrs[b]
+
+    def barrier(self) -> None:
+        self.handles[0].barrier(channel=0)
+
+    @classmethod
+    def get(cls, group, rows, heads_kv, device):
+        key = (id(group), heads_kv, str(device))
+        ws = cls._instances.get(key)
+        if ws is None or ws.rows < rows:   # collective: every rank reaches this with the same key at the same forward
+            ws = cls._instances[key] = cls(group, rows, heads_kv, device)
+        return ws
+
+    available = staticmethod(UlyssesPeerWorkspace.available)
+
+
+def ring_multicast_enabled() -> bool:
+    """MAGI_RING_MULTICAST=0 keeps the per-peer stores even when the fabric offers an NVSwitch multicast mapping."""
+    import os
+    return os.environ.get("MAGI_RING_MULTICAST", "1") != "0"
+
+
 def ring_step_ranges(chunk_ranges: Sequence[Tuple[int, int]], slice_point: int, clip: int, n_q: int, n_blk: int,
                      with_cache: bool):
     """Host-side interval arithmetic for one ring step under the striped sharding.

@@ -225,8 +225,8 @@ int magi_qk_norm_rope_fwd(const magi_prologue_args* a, void* stream_) {
   MAGI_CHECK(a->xq_head_stride % 8 == 0 && a->xk_head_stride % 8 == 0 && a->xv_head_stride % 8 == 0 &&
                  a->xq_head_stride >= 0 && a->xk_head_stride >= 0 && a->xv_head_stride >= 0,
              "input head strides must be non-negative multiples of 8 elements");
-  if (a->x_k) MAGI_CHECK((a->kv_out || a->num_peers > 0) && a->ln_k_w && a->ln_k_b, "k path needs kv_out, ln_k_w, ln_k_b");
-  if (a->x_v) MAGI_CHECK(a->kv_out || a->num_peers > 0, "v path needs kv_out");
+  if (a->x_k) MAGI_CHECK((a->kv_out || a->num_peers > 0 || a->gather_peers > 0) && a->ln_k_w && a->ln_k_b, "k path needs kv_out, ln_k_w, ln_k_b");
+  if (a->x_v) MAGI_CHECK(a->kv_out || a->num_peers > 0 || a->gather_peers > 0, "v path needs kv_out");
   if (a->x_k || a->x_v)
     MAGI_CHECK(a->num_heads_kv > 0 && a->xk_row_stride % 8 == 0 && a->xv_row_stride % 8 == 0 &&
                    a->kv_out_token_stride % 8 == 0 && a->kv_out_head_stride % 8 == 0,
@@ -283,6 +283,26 @@ int magi_qk_norm_rope_fwd(const magi_prologue_args* a, void* stream_) {
     }
     p.use_peers = 1;
     p.peer_row_offset = a->peer_row_offset;
+  }
+  p.gather_peers = 0;
+  p.gather_rows_per_chunk = 1; p.gather_chunk_stride = 0; p.gather_row_offset = 0;
+  if (a->gather_peers > 0) {
+    MAGI_CHECK(a->gather_peers <= MAGI_MAX_PEERS, "gather_peers must be at most %d", MAGI_MAX_PEERS);
+    MAGI_CHECK(cp == 1 && a->num_peers == 0 && a->cache == nullptr,
+               "the K/V all-gather is not available together with head_perm_cp, num_peers or the cache append");
+    MAGI_CHECK(a->gather_rows_per_chunk > 0 && a->rows % a->gather_rows_per_chunk == 0 && a->gather_row_offset >= 0 &&
+                   a->gather_row_offset + a->gather_rows_per_chunk <= a->gather_chunk_stride,
+               "bad gather geometry: rows must be whole stripes and a stripe must fit inside a chunk");
+    if (a->x_k || a->x_v)
+      for (int i = 0; i < a->gather_peers; ++i) {
+        MAGI_CHECK(a->gather_kv_out[i] && (reinterpret_cast<uintptr_t>(a->gather_kv_out[i]) & 15) == 0,
+                   "bad gather_kv_out[%d]", i);
+        p.peer_kv[i] = a->gather_kv_out[i];
+      }
+    p.gather_peers = a->gather_peers;
+    p.gather_rows_per_chunk = a->gather_rows_per_chunk;
+    p.gather_chunk_stride = a->gather_chunk_stride;
+    p.gather_row_offset = a->gather_row_offset;
   }
 
   int64_t units = 0;

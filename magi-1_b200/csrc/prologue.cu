@@ -137,7 +137,9 @@ struct RingSuper {
   int cnt;         // valid units (1..kRingGroup)
 };
 
-template <bool kLnBf16, bool kPerm>
+// kMode 0: q / packed kv (+ KV-cache append) in place; 1: Ulysses send layout or peer receive buffers (head_perm_cp);
+// 2: q in place, every K/V row stored into ALL ranks' gathered in-flight K/V buffers (fused all-gather, cp_ring_kv)
+template <bool kLnBf16, int kMode>
 __global__ void __launch_bounds__(kRingThreads, MAGI_PRO_RING_BLOCKS) prologue_ring_kernel(const PrologueParams p) {
   extern __shared__ __align__(128) uint8_t ring_smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(ring_smem);
@@ -276,7 +278,13 @@ __global__ void __launch_bounds__(kRingThreads, MAGI_PRO_RING_BLOCKS) prologue_r
       const int64_t out_tstride = type == 0 ? p.q_out_token_stride : p.kv_out_token_stride;
       const int64_t out_hstride = type == 0 ? p.q_out_head_stride : p.kv_out_head_stride;
       __nv_bfloat16* cache_row = nullptr;
-      if constexpr (!kPerm) {
+      int64_t grow = 0;                          // kMode 2: row of this unit in the gathered (chunk-major) buffers
+      if constexpr (kMode == 2) {
+        const uint32_t rpc = static_cast<uint32_t>(p.gather_rows_per_chunk);
+        const uint32_t chunk = r / rpc;
+        grow = static_cast<int64_t>(chunk) * p.gather_chunk_stride + p.gather_row_offset + (r - chunk * rpc);
+      }
+      if constexpr (kMode == 0) {
         if (type != 0 && p.cache != nullptr && static_cast<int64_t>(r) < p.cache_rows)
           cache_row = reinterpret_cast<__nv_bfloat16*>(p.cache) + (p.cache_row_offset + r) * p.cache_token_stride +
                       (type == 2 ? 128 : 0);
@@ -341,9 +349,18 @@ __global__ void __launch_bounds__(kRingThreads, MAGI_PRO_RING_BLOCKS) prologue_r
           *reinterpret_cast<uint4*>(dst + e0) = pa;
           *reinterpret_cast<uint4*>(dst + e1) = pb;
         };
-        if constexpr (!kPerm) {
+        if constexpr (kMode == 0) {
           store(out_base + r * out_tstride + h * out_hstride);
           if (cache_row != nullptr) store(cache_row + h * p.cache_head_stride);
+        } else if constexpr (kMode == 2) {
+          if (type == 0) {
+            store(out_base + r * out_tstride + h * out_hstride);
+          } else {
+            // fused K/V all-gather: the same 16-byte stores, once per rank of the group (own buffer included), over
+            // NVLink peer memory; row = (chunk, this rank's stripe offset + row in stripe)
+            const int64_t off = grow * out_tstride + h * out_hstride + (type == 2 ? 128 : 0);
+            for (int c = 0; c < p.gather_peers; ++c) store(reinterpret_cast<__nv_bfloat16*>(p.peer_kv[c]) + off);
+          }
         } else {
           // all-to-all SEND layout "(cp seq) hn hd" in one local buffer, or - fused all-to-all - straight into the
           // receive buffer of the rank that owns the head slice, at this rank's row offset (NVLink peer stores)
@@ -481,11 +498,11 @@ int prologue_units(const PrologueParams& p, int64_t* units) {
   *units = p.rows * ((p.x_q ? upr_q : 0) + (p.x_k ? upr_kv : 0) + (p.x_v ? upr_kv : 0));
   return MAGI_PRO_RING_BLOCKS;
 }
-template <bool kLnBf16, bool kPerm>
+template <bool kLnBf16, int kMode>
 static cudaError_t prologue_launch_t(const PrologueParams& p, int64_t units, int sms, cudaStream_t stream) {
   static bool attr_set = false;   // per template instance; idempotent
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(prologue_ring_kernel<kLnBf16, kPerm>,
+    cudaError_t e = cudaFuncSetAttribute(prologue_ring_kernel<kLnBf16, kMode>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kRingSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -495,17 +512,20 @@ static cudaError_t prologue_launch_t(const PrologueParams& p, int64_t units, int
   const int64_t need = (units / kRingGroup + kRingConsumerGroups) / kRingConsumerGroups;
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
-  prologue_ring_kernel<kLnBf16, kPerm><<<static_cast<int>(blocks), kRingThreads, kRingSmemBytes, stream>>>(p);
+  prologue_ring_kernel<kLnBf16, kMode><<<static_cast<int>(blocks), kRingThreads, kRingSmemBytes, stream>>>(p);
   return cudaGetLastError();
 }
 cudaError_t prologue_launch(const PrologueParams& p, bool ln_bf16, int sms, cudaStream_t stream) {
   int64_t units = 0;
   prologue_units(p, &units);
-  const bool perm = p.head_perm_cp > 1;
-  if (ln_bf16) return perm ? prologue_launch_t<true, true>(p, units, sms, stream)
-                           : prologue_launch_t<true, false>(p, units, sms, stream);
-  return perm ? prologue_launch_t<false, true>(p, units, sms, stream)
-              : prologue_launch_t<false, false>(p, units, sms, stream);
+  const int mode = p.gather_peers > 0 ? 2 : (p.head_perm_cp > 1 ? 1 : 0);
+  if (ln_bf16)
+    return mode == 2 ? prologue_launch_t<true, 2>(p, units, sms, stream)
+                     : mode == 1 ? prologue_launch_t<true, 1>(p, units, sms, stream)
+                                 : prologue_launch_t<true, 0>(p, units, sms, stream);
+  return mode == 2 ? prologue_launch_t<false, 2>(p, units, sms, stream)
+                   : mode == 1 ? prologue_launch_t<false, 1>(p, units, sms, stream)
+                               : prologue_launch_t<false, 0>(p, units, sms, stream);
 }
 cudaError_t kv_append_launch(void* cache, int64_t cache_stride, const void* kv, int64_t kv_stride, int64_t row_offset,
                              int64_t rows, int row_vecs, int grid, cudaStream_t stream) {

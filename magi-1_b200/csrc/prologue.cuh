@@ -24,6 +24,9 @@ struct PrologueParams {
   int use_peers;
   void* peer_q[8]; void* peer_kv[8];
   int64_t peer_row_offset;
+  // fused K/V all-gather (cp_ring_kv): peer_kv[0 .. gather_peers) are the ranks' gathered in-flight K/V buffers
+  int gather_peers;
+  int64_t gather_rows_per_chunk, gather_chunk_stride, gather_row_offset;
 };
 
 // number of work units of a launch (-> *units) and the resident 256-thread CTAs per SM the kernel is built for

@@ -294,6 +294,8 @@ def qk_norm_rope(
     peer_kv_out: Optional[Sequence[int]] = None,
     peer_row_offset: int = 0,
     peer_heads: Optional[Tuple[int, int]] = None,
+    gather_kv_out: Optional[Sequence[int]] = None,
+    gather_geometry: Optional[Tuple[int, int, int]] = None,
 ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """Fused per-head LayerNorm(w+1, b) -> NeoX RoPE on 96 of 128 dims -> bf16, writing q in attention layout and
     [K|V] packed (rows, Hkv, 256), optionally also appending to the KV cache (dit_module.py:953-996, 918-929).
@@ -306,6 +308,10 @@ def qk_norm_rope(
     With peer_q_out / peer_kv_out (head_perm_cp device pointers each) the all-to-all itself is fused: head slice c is
     stored straight into rank c's receive buffer ((all rows, peer_heads[0], 128) resp. (all rows, peer_heads[1], 256))
     at row peer_row_offset + r over NVLink peer memory (include/magi_attn.h); nothing is returned for that tensor.
+    With gather_kv_out (device pointers of every rank's gathered in-flight K/V buffer, (chunks * chunk_stride, Hkv, 256)
+    packed, this rank's own included - or ONE NVSwitch multicast pointer) and gather_geometry = (rows_per_chunk,
+    chunk_stride, row_offset) the K/V all-gather of cp_ring_kv is fused: local row (chunk j, stripe row t) is stored at
+    row j * chunk_stride + row_offset + t of every buffer; q is written locally as usual, no kv tensor is returned.
     """
     ref = next(t for t in (x_q, x_k, x_v) if t is not None)
     dev = ref.device
@@ -349,9 +355,19 @@ def qk_norm_rope(
         if (x_q is not None and (peer_q_out is None or len(peer_q_out) != cp)) or (
                 (x_k is not None or x_v is not None) and (peer_kv_out is None or len(peer_kv_out) != cp)):
             raise ValueError("peer pointer lists must have head_perm_cp entries")
+    gather = gather_kv_out is not None
+    if gather:
+        if use_peers or cp > 1 or (cache is not None and cache_rows > 0) or gather_geometry is None:
+            raise ValueError("gather_kv_out needs gather_geometry and excludes head_perm_cp, peer routing and the cache "
+                             "append")
+        if not 1 <= len(gather_kv_out) <= _lib.MAX_PEERS:
+            raise ValueError(f"gather_kv_out must hold 1..{_lib.MAX_PEERS} pointers")
+        rpc, cstride, roff = gather_geometry
+        if rpc <= 0 or rows % rpc != 0 or roff < 0 or roff + rpc > cstride:
+            raise ValueError("bad gather_geometry: rows must be whole stripes and a stripe must fit inside a chunk")
     if x_q is not None and q_out is None and not use_peers:
         q_out = torch.empty((rows * cp, num_heads_q // cp, HEAD_DIM), dtype=torch.bfloat16, device=dev)
-    if (x_k is not None or x_v is not None) and kv_out is None and not use_peers:
+    if (x_k is not None or x_v is not None) and kv_out is None and not use_peers and not gather:
         hn_kv = max(1, num_heads_kv // cp) if cp > 1 else num_heads_kv
         kv_out = torch.empty((rows * cp, hn_kv, 2 * HEAD_DIM), dtype=torch.bfloat16, device=dev)
 
@@ -393,6 +409,12 @@ def qk_norm_rope(
         for i in range(cp):
             a.peer_q_out[i] = peer_q_out[i] if peer_q_out is not None else None
             a.peer_kv_out[i] = peer_kv_out[i] if peer_kv_out is not None else None
+    if gather:
+        a.gather_peers = len(gather_kv_out)
+        a.gather_rows_per_chunk, a.gather_chunk_stride, a.gather_row_offset = gather_geometry
+        a.kv_out_token_stride, a.kv_out_head_stride = num_heads_kv * 2 * HEAD_DIM, 2 * HEAD_DIM
+        for i, ptr in enumerate(gather_kv_out):
+            a.gather_kv_out[i] = ptr
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().magi_qk_norm_rope_fwd(C.byref(a), _stream()), "magi_qk_norm_rope_fwd")
     return q_out, kv_out

@@ -51,6 +51,8 @@ def test_struct_layout_matches_header():
       printf("%zu %zu %zu %zu %zu %zu %zu\n", offsetof(magi_attn_args, peer_out), offsetof(magi_attn_args, peer_row_bounds),
              offsetof(magi_prologue_args, peer_kv_out), offsetof(magi_prologue_args, peer_row_offset),
              sizeof(MagiGatingArgs), offsetof(MagiGatingArgs, ln_w), offsetof(MagiGatingArgs, hidden));
+      printf("%zu %zu %zu\n", offsetof(magi_prologue_args, gather_peers), offsetof(magi_prologue_args, gather_kv_out),
+             offsetof(magi_prologue_args, gather_row_offset));
       return 0;
     }'''
     import tempfile
@@ -59,8 +61,9 @@ def test_struct_layout_matches_header():
         open(c, "w").write(src)
         exe = os.path.join(d, "t")
         subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
-        a, b, c_ = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+        a, b, c_, d_ = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.strip().splitlines()
     A, P, G = _lib.MagiAttnArgs, _lib.MagiPrologueArgs, _lib.MagiGatingArgs
+    assert [int(x) for x in d_.split()] == [P.gather_peers.offset, P.gather_kv_out.offset, P.gather_row_offset.offset]
     assert [int(x) for x in c_.split()] == [A.peer_out.offset, A.peer_row_bounds.offset, P.peer_kv_out.offset,
                                             P.peer_row_offset.offset, C.sizeof(G), G.ln_w.offset, G.hidden.offset]
     assert [int(x) for x in a.split()] == [C.sizeof(_lib.MagiView), C.sizeof(A), A.out.offset, A.n_ranges.offset,

@@ -340,6 +340,55 @@ def test_fused_all_to_all_routing_on_virtual_ranks(F, cp, Hq, Hkv):
     assert torch.equal(torch.cat(out_recv, 0), out_full)
 
 
+@pytest.mark.parametrize("cp,clip", [(2, 150), (3, 100), (8, 333)])
+def test_fused_kv_gather_on_virtual_ranks(F, cp, clip):
+    """cp_ring_kv with the K/V all-gather fused into the prologue's stores, exercised on ONE device: every "rank" owns
+    a stripe of every chunk and a gathered K/V buffer whose address the kernels get as a peer pointer. After all
+    ranks' prologues every buffer must hold exactly the single-rank packed K/V (chunk-major), rows outside the stripes
+    untouched; the attention of every rank's query stripe against it, with the unmodified k ranges, must be
+    bit-identical to the single-rank rows (same kernel, same per-row key order)."""
+    from magi_b200.context_parallel import ring_split_sizes
+    dn, Hq, Hkv, sp = 3, 6, 2, 1
+    S = clip * dn
+    sizes = ring_split_sizes(clip, cp)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    xq, xk, xv = bf(rnd((S, Hq * 128), 1)), bf(rnd((S, Hkv * 128), 2)), bf(rnd((S, Hkv * 128), 3))
+    cache = bf(rnd((sp * clip, Hkv, 256), 4))
+    ln = [torch.from_numpy(rnd((128,), 10 + i, 0.2)).cuda() for i in range(4)]
+    ang = torch.from_numpy(rnd((S, 48), 20, 3.0))
+    sin, cos = torch.sin(ang).cuda(), torch.cos(ang).cuda()
+    q_ranges = i32([[i * clip, (i + 1) * clip] for i in range(dn)])
+    k_ranges = i32([[0, 2 * clip], [clip, 3 * clip], [0, 4 * clip]])       # absolute rows: cache prefix ++ in-flight
+    q_full, kv_full = F.qk_norm_rope(xq, xk, xv, Hq, Hkv, (ln[0], ln[1]), (ln[2], ln[3]), sin, cos)
+    out_full, _ = F.attn_ranges(q_full, kv_full[..., :128], kv_full[..., 128:], q_ranges, k_ranges,
+                                k_cache=cache[..., :128], v_cache=cache[..., 128:])
+    pad = 5                                                                   # guard rows around every buffer
+    bufs = [torch.full((S + 2 * pad, Hkv, 256), 7.0, dtype=torch.bfloat16, device="cuda") for _ in range(cp)]
+    stripe = lambda t, r: t.unflatten(0, (dn, clip))[:, int(offs[r]):int(offs[r + 1])].flatten(0, 1).contiguous()
+    qs = []
+    for me in range(cp):
+        q_me, kv_me = F.qk_norm_rope(stripe(xq, me), stripe(xk, me), stripe(xv, me), Hq, Hkv, (ln[0], ln[1]),
+                                     (ln[2], ln[3]), stripe(sin, me), stripe(cos, me),
+                                     gather_kv_out=[b[pad:].data_ptr() for b in bufs],
+                                     gather_geometry=(sizes[me], clip, int(offs[me])))
+        assert kv_me is None
+        qs.append(q_me)
+    for b in bufs:
+        assert torch.equal(b[pad:pad + S], kv_full)
+        assert bool((b[:pad] == 7.0).all()) and bool((b[pad + S:] == 7.0).all())
+    for me in range(cp):
+        n = sizes[me]
+        qr = i32([[i * n, (i + 1) * n] for i in range(dn)])
+        kv = bufs[me][pad:pad + S]
+        o, _ = F.attn_ranges(qs[me], kv[..., :128], kv[..., 128:], qr, k_ranges, k_cache=cache[..., :128],
+                             v_cache=cache[..., 128:])
+        assert torch.equal(o, stripe(out_full, me))
+    with pytest.raises(ValueError):
+        F.qk_norm_rope(stripe(xq, 0), stripe(xk, 0), stripe(xv, 0), Hq, Hkv, (ln[0], ln[1]), (ln[2], ln[3]),
+                       stripe(sin, 0), stripe(cos, 0), gather_kv_out=[bufs[0].data_ptr()],
+                       gather_geometry=(sizes[0], sizes[0] - 1, 0))          # a stripe larger than a chunk
+
+
 def test_cso_unshuffle_and_full_attention(F):
     """CSO pieces with the real kernels: the receive-side gather "(cp dn spb) -> dn (cp spb)"[:, :clip]
     (dit_module.py:1215-1224) is bit exact and can land in the KV-cache slot; full_attention on the padded query

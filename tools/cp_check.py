@@ -5,8 +5,9 @@
 Every rank builds the same FullyParallelAttention weights and the same full-sequence inputs, runs the cp_ulysses, cp_shuffle_overlap and
 cp_ring_kv forwards on its shard through a KV-cache sequence (cache fill, window advance, update on/off, distill extra
 range), all-gathers the outputs and compares them with the single-GPU (cp_strategy="none") forward computed locally
-(oracle O3 of SURVEY.md section 8c). Ulysses and cp_shuffle_overlap must be bit-identical (same kernels, same per-head inputs); ring-KV is
-bounded by one bf16 rounding per merge step."""
+(oracle O3 of SURVEY.md section 8c). Ulysses, cp_shuffle_overlap and the fused-gather cp_ring_kv must be bit-identical (same
+kernels, same per-row inputs and key order); the NCCL ring is bounded by one bf16 rounding per merge step.
+MAGI_RING_MULTICAST=0 keeps the fused gather on per-peer stores when an NVSwitch multicast mapping exists."""
 import os
 import sys
 
@@ -80,7 +81,9 @@ def main():
         kv_loc = max(1, Hkv // world)
         second = kv_loc if kv_loc > 1 else 3      # whole kv heads per group, or 3 q-head groups in the MQA case
         # cp_ulysses: all-to-alls fused into the kernels (NVLink peer stores), then the NCCL path at two overlap degrees
-        for overlap, fused in (((1, True), (1, False), (second, False)) if strategy == "cp_ulysses" else ((1, False),)):
+        # cp_ring_kv: K/V all-gather fused into the prologue's stores (one attention launch), then the NCCL ring
+        for overlap, fused in (((1, True), (1, False), (second, False)) if strategy == "cp_ulysses" else
+                               ((1, True), (1, False)) if strategy == "cp_ring_kv" else ((1, False),)):
             ref_m, cp_m = build("none", 1), build(strategy, world)
             inf_ref = InferenceParams(1, 5 * clip)
             inf_cp = InferenceParams(1, 5 * clip)
@@ -116,11 +119,15 @@ def main():
     if rank == 0:
         ok = True
         for k, w in results.items():
-            bound = 2.5e-2 if k.startswith("cp_ring_kv") else 0.0
+            bound = 2.5e-2 if k.startswith("cp_ring_kv/nccl") else 0.0   # the fused gather keeps every row's key order
             good = w["core"] <= bound and w["xattn"] == 0.0
             ok &= good
             print(f"[cp_check N={world}] {k}: core max_abs {w['core']:.3e} (bound {bound}) xattn max_abs "
                   f"{w['xattn']:.3e} -> {'OK' if good else 'FAIL'}", flush=True)
+        mcast = [any(w_.mc_ptrs) for w_ in cpm.RingGatherWorkspace._instances.values()]
+        print(f"[cp_check N={world}] fused gather stores: "
+              f"{'NVSwitch multicast' if (mcast and all(mcast) and cpm.ring_multicast_enabled()) else 'per-peer NVLink stores'}"
+              f" (multicast mapping available: {bool(mcast and all(mcast))})", flush=True)
         print("CP_CHECK", "PASS" if ok else "FAIL", flush=True)
     dist.destroy_process_group()
 
