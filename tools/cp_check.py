@@ -77,7 +77,9 @@ def main():
         (1, 3, [(0, 2), (1, 3), (3, 4)], [33, 90, 33], True, False, True),
     ]
     results = {}
-    for strategy in ("cp_ulysses", "cp_shuffle_overlap", "cp_ring_kv"):
+    # CP_CHECK_STRATEGIES=cp_ring_kv,... restricts the run (the 8-GPU box time is charged 8x)
+    chosen = os.environ.get("CP_CHECK_STRATEGIES", "cp_ulysses,cp_shuffle_overlap,cp_ring_kv").split(",")
+    for strategy in [s_ for s_ in ("cp_ulysses", "cp_shuffle_overlap", "cp_ring_kv") if s_ in chosen]:
         kv_loc = max(1, Hkv // world)
         second = kv_loc if kv_loc > 1 else 3      # whole kv heads per group, or 3 q-head groups in the MQA case
         # cp_ulysses: all-to-alls fused into the kernels (NVLink peer stores), then the NCCL path at two overlap degrees
