@@ -732,7 +732,11 @@ class FullyParallelAttention(nn.Module):
     def _forward_ring(self, mixed_qqkv, key_value_states, inference_params, sin_emb, cos_emb, meta_args):
         sq, b, _ = mixed_qqkv.shape
         if b != 1:
-            raise NotImplementedError("cp_ring_kv supports batch size 1 (the 3-CFG uncond pass uses cp_ulysses)")
+            # the batched uncond pass of the 3-CFG models (dit_model.py:413-494): one range shared by all batch rows, no
+            # KV cache; its shards are the contiguous Ulysses shards (cp_ring_kv_process), so it runs as cp_ulysses
+            if self._uses_cache(inference_params, meta_args) or meta_args.denoising_range_num != 1:
+                raise NotImplementedError("cp_ring_kv with batch size > 1 supports the cache-less uncond pass only")
+            return self._forward_ulysses(mixed_qqkv, key_value_states, inference_params, sin_emb, cos_emb, meta_args)
         if self.engine_config.kv_offload:
             raise NotImplementedError("kv_offload is available with cp_strategy 'none' and 'cp_ulysses'")
         Hq, Hkv = self.model_config.num_attention_heads, self.model_config.num_query_groups

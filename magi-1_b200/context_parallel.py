@@ -518,8 +518,13 @@ def cp_ring_kv_process(cp_size: int, x: torch.Tensor, condition_map: torch.Tenso
     the local slices. Local row order is (chunk, slice row). Returns (x, condition_map, rope, cp_split_sizes,
     cross_attn_params) with cp_split_sizes[r] = dn * (slice rows of rank r), what the exit all-gather needs."""
     seq_len, N, _ = x.shape
-    assert N == 1, "cp_ring_kv supports batch size 1"
     dn = ardf_meta["denoising_range_num"]
+    if N > 1:
+        # the batched uncond pass (dit_model.py:413-494: chunks moved to the batch dim, one range, no KV cache): with
+        # one chunk per batch row the stripes ARE the contiguous Ulysses shards, and the attention block runs it as
+        # cp_ulysses (each row attends only itself, nothing to gather across chunks)
+        assert dn == 1, "cp_ring_kv with batch size > 1 needs denoising_range_num == 1 (dit_module.py:1048)"
+        return cp_ulysses_process(cp_size, x, condition_map, rope, None, cross_attn_params)
     clip = divide(seq_len, dn)
     sizes = ring_split_sizes(clip, cp_size)
     rank = mpu.get_cp_rank()

@@ -115,6 +115,40 @@ def main():
                 xo = cpm.cp_post_process(world, strategy, xo.contiguous(), m_cp)
                 worst["core"] = max(worst["core"], (core.float() - ref_core.float()).abs().max().item())
                 worst["xattn"] = max(worst["xattn"], (xo.float() - ref_x.float()).abs().max().item())
+            if strategy != "cp_shuffle_overlap":
+                # batched uncond pass of the 3-CFG models (dit_model.py:413-494): chunks on the batch dim, one range
+                # per batch row, no KV cache (runs on the NCCL Ulysses path under both strategies)
+                bs = 3
+                hs = torch.randn(clip, bs, hidden, generator=g).to(torch.bfloat16).to(dev)
+                yi = [50, 0, 77]
+                kvs = torch.randn(sum(yi), hidden, generator=g).to(torch.bfloat16).to(dev)
+                ang = torch.rand(clip, 48, generator=g) * 6.28
+                rope = torch.cat([torch.sin(ang), torch.cos(ang)], -1).to(dev)
+                edges = np.arange(bs + 1, dtype=np.int32) * clip
+                rng_ = np.stack([edges[:-1], edges[1:]], 1)
+                cu_k = np.concatenate([[0], np.cumsum(yi)]).astype(np.int32)
+                core_u = PackedCoreAttnParams(i32(rng_), i32(rng_), rng_, rng_, clip, bs * clip)
+                cross_u = PackedCrossAttnParams(i32(rng_), i32(np.stack([cu_k[:-1], cu_k[1:]], 1)), i32(edges), i32(cu_k),
+                                                clip, 800)
+
+                def meta_u(split, cross):
+                    return ModelMetaArgs(H=1, W=1, cp_pad_size=0, cp_split_sizes=split, slice_point=0,
+                                         denoising_range_num=1, range_num=1, extract_prefix_video_feature=False,
+                                         fwd_extra_1st_chunk=False, distill_nearly_clean_chunk=False,
+                                         clip_token_nums=clip, enable_cuda_graph=False, core_attn_params=core_u,
+                                         cross_attn_params=cross)
+
+                ref_core, ref_x = ref_m(hs, kvs, None, rope, meta_u(None, cross_u))
+                ardf = dict(denoising_range_num=1, q_range=core_u.q_range, k_range=core_u.k_range, max_seqlen_q=clip,
+                            max_seqlen_k=bs * clip)
+                x, _, rope_l, pad, split, _, cross_l = cpm.cp_pre_process(
+                    world, strategy, hs, torch.zeros(clip, bs, device=dev), rope, None, ardf, core_u, cross_u)
+                m_cp = meta_u(split, cross_l)
+                core, xo = cp_m(x, kvs, None, rope_l, m_cp)
+                core = cpm.cp_post_process(world, strategy, core.contiguous(), m_cp)
+                xo = cpm.cp_post_process(world, strategy, xo.contiguous(), m_cp)
+                worst["core"] = max(worst["core"], (core.float() - ref_core.float()).abs().max().item())
+                worst["xattn"] = max(worst["xattn"], (xo.float() - ref_x.float()).abs().max().item())
             results[f"{strategy}/{'fused-p2p' if fused else 'nccl'}/overlap{overlap}"] = worst
     torch.cuda.synchronize()
     dist.barrier()
