@@ -14,7 +14,7 @@ layer. N > 1 runs the SAME workload context-parallel (Ulysses head all-to-all ov
 
     python bench.py                                  # N=1, prints one JSON line
     torchrun --nproc-per-node N bench.py --gpus N    # context parallel
-    python bench.py --impl reference                 # the reference's CPU math (oracle port) on the host cores
+    python bench.py --impl reference                 # the reference's CPU torch path (oracle port) on the host cores
 """
 import argparse
 import json
@@ -479,33 +479,28 @@ def dit_step_leg(w, dev, world, rank, steps, max_over_ranks, barrier):
 
 # ----------------------------------------------------------------------------------------------- CPU baseline
 def cpu_baseline_sample(w, budget_s=20.0):
-    """The reference's math (oracle port, numpy fp32, all host threads) on a bounded sample of the SAME workload:
-    range 0 of layer 0 (clip q x clip k) for as many q heads as fit the time budget. Returns (tflops, dict)."""
+    """The reference's CPU torch path on a bounded sample of the SAME workload: the self-attention of layer 0 of the
+    workload state through oracle/torch_cpu_path.py (the reference's fallback loop of flash_attn_func calls,
+    dit_module.py:1046-1065, restated with torch fp32 scaled_dot_product_attention on all host threads - flash-attn
+    itself is CUDA-only), ranges taken in order until the time budget is spent. Returns (tflops, dict)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import numpy as np
-    import magi_oracle as O
-    clip, Hq, Hkv = w["clip"], w["Hq"], w["Hkv"]
-    g = Hq // Hkv
-    rng = np.random.default_rng(1234)
-    kv = rng.standard_normal((clip, 1, 256), dtype=np.float32)
-    t_total, heads_done = 0.0, 0
-    flops_per_group = 4 * 128 * g * clip * clip
-    while t_total < budget_s and heads_done < Hq:
-        q = rng.standard_normal((clip, g, 128), dtype=np.float32)
-        t0 = time.perf_counter()
-        O.attn_ranges(q, kv[..., :128], kv[..., 128:], [[0, clip]], [[0, clip]], round_output=True)
-        t_total += time.perf_counter() - t0
-        heads_done += g
-    tf = flops_per_group * (heads_done // g) / t_total / 1e12
+    import torch
+    import torch_cpu_path as T
     cores = os.cpu_count() or 1
-    return tf, {"value": round(tf, 4), "unit": "TFLOP/s", "cores": cores, "kind": "port",
-                "sample": f"layer 0, range 0 ({clip} q x {clip} k), {heads_done} of {Hq} q heads, numpy fp32 oracle, "
-                          f"{t_total:.1f} s"}
+    torch.set_num_threads(cores)
+    flops, secs, done, threads = T.timed_self_attention_sample(w["clip"], w["Hq"], w["Hkv"], w["k_chunks"], budget_s)
+    tf = flops / secs / 1e12
+    ks = ",".join(f"({s},{e})" for s, e in w["k_chunks"][:done])
+    return tf, {"value": round(tf, 4), "unit": "TFLOP/s", "cores": threads, "kind": "port",
+                "sample": f"self-attention of layer 0, ranges 0..{done - 1} of {len(w['k_chunks'])} (k chunks {ks}; "
+                          f"{w['clip']} q rows each, all {w['Hq']} q heads): {flops / 1e12:.2f} TFLOP in {secs:.1f} s, "
+                          f"torch fp32 CPU port of the reference's flash_attn_func loop (oracle/torch_cpu_path.py)"}
 
 
 def run_reference(args, w):
-    """--impl reference: the reference's CPU implementation of the path (the oracle port: the reference is Python whose
-    CUDA-only third-party kernels cannot run on a CPU) on the host cores, same metric/config."""
+    """--impl reference: the reference's CPU implementation of the path on the host cores, same metric/config: the
+    torch fp32 port of its attention fallback loop (oracle/torch_cpu_path.py; the reference is Python whose CUDA-only
+    third-party kernels cannot run on a CPU). Each step times a bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return

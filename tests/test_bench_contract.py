@@ -1,4 +1,4 @@
-"""bench.py contract checks that run without a GPU: the reference arm (the oracle port timed on the host cores) prints
+"""bench.py contract checks that run without a GPU: the reference arm (the torch fp32 CPU port of the reference's attention loop, timed on the host cores) prints
 exactly one JSON line with the keys the driver reads, and the FLOP accounting follows SURVEY.md section 8(d)."""
 import json
 import os

@@ -116,6 +116,36 @@ def test_cross_attention_matches_reference(g, s):
         assert np.all(g["B.xattn_out"][:clip] == 0) and np.all(out[:clip] == 0)
 
 
+def test_torch_cpu_path_matches_reference_golden(g):
+    """oracle/torch_cpu_path.py (the torch fp32 CPU form of the reference's attention calls that bench.py times as
+    `cpu_baseline` / `--impl reference`) against the reference's own core_attn_out / xattn_out and the numpy oracle."""
+    import torch
+    import torch_cpu_path as T
+    clip = int(g["clip"])
+    cache = np.zeros((4 * clip, 2, 256), dtype=np.float32)
+    for s in ["A", "B", "C", "D"]:
+        m = _meta(g, s)
+        key, value = O.adjust_key_and_value_for_inference(
+            g[f"{s}.kv"], cache, m["has_inf"], m["slice_point"], clip, 1, m["update"], False, m["fwd_extra"],
+            m["distill_ncc"])
+        out = T.core_attention(torch.from_numpy(g[f"{s}.q"]), torch.from_numpy(np.ascontiguousarray(key)),
+                               torch.from_numpy(np.ascontiguousarray(value)), g[f"{s}.q_range"], g[f"{s}.k_range"],
+                               m["dn"]).numpy()
+        ref = g[f"{s}.core_attn_out"].reshape(out.shape)
+        ok, err, nbad = close_bf16(O.bf16_round(out), ref, ulps=2.0, atol=2e-3)
+        assert ok, f"step {s}: core_attn_out max err {err}, {nbad} bad"
+        mine, _ = O.attn_ranges(g[f"{s}.q"], key, value, g[f"{s}.q_range"][:m["dn"]], g[f"{s}.k_range"][:m["dn"]],
+                                round_output=False)
+        assert float(np.abs(mine - out).max()) <= 2e-5, "torch CPU path and numpy oracle disagree in fp32"
+        # cross-attention incl. the zero-length caption segment of step B
+        p = O.cross_attn_params(clip, m["dn"], m["bs"], g[f"{s}.y_index"])
+        x = T.cross_attention(torch.from_numpy(g[f"{s}.xq"]), torch.from_numpy(g[f"{s}.xk"]),
+                              torch.from_numpy(g[f"{s}.xv"]), p["cu_seqlens_q"], p["cu_seqlens_kv"]).numpy()
+        ok, err, nbad = close_bf16(O.bf16_round(x.reshape(x.shape[0], -1)), g[f"{s}.xattn_out"][:, 0], ulps=2.0,
+                                   atol=2e-3)
+        assert ok, f"step {s}: xattn_out max err {err}, {nbad} bad"
+
+
 def test_rope_table_matches_reference_builder(g):
     """The reference's build_rotary_pos_embed (dit_module.py:599-717) with the dit_model.py:163-166 recipe."""
     for s, (T_total, keep) in {"A": (6, 6), "C": (9, 6), "D": (12, 9)}.items():
