@@ -273,6 +273,33 @@ def all_to_all_output_split(tensor: torch.Tensor, cp_split_sizes: List[int]):
     return out, handle
 
 
+def fused_qkv_communication(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cp_split_sizes: List[int],
+                            relayout: Optional[Callable] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """context_parallel.py:426-449: ONE all-to-all for q, k and v (fewer host operations when the sequence is very
+    short). q (seq, cp*hn_q, hd), k / v (seq, Hkv, hd) -> (sum(sizes), hn_q, hd), (sum(sizes), hn_kv, hd) x 2, where
+    k and v come back as views of one packed (sum(sizes), hn_kv, 2*hd) = [K | V] buffer - the KV-cache / kernel
+    layout, so the reference's `torch.cat([k, v], -1)` behind it (context_parallel.py:546) is free.
+    `relayout(tensor, cp, kv_repeat)` produces the "(cp seq) hn hd" send layout (incl. KV-head replication)."""
+    cp = mpu.get_cp_world_size()
+    if cp == 1:
+        return q, k, v
+    assert cp_split_sizes is not None
+    k_head = k.shape[1]
+    rep = cp // k_head if (cp % k_head == 0 and cp != k_head) else 1
+    qs, ks, vs = relayout(q, cp, 1), relayout(k, cp, rep), relayout(v, cp, rep)
+    hq, hk, hd = qs.shape[1], ks.shape[1], qs.shape[2]
+    # wire format per row: [q heads | (K | V) per kv head], one contiguous message per destination rank
+    send = torch.empty((qs.shape[0], (hq + 2 * hk) * hd), device=q.device, dtype=q.dtype)
+    send[:, :hq * hd].view(-1, hq, hd).copy_(qs)
+    packed = send[:, hq * hd:].view(-1, hk, 2 * hd)
+    packed[..., :hd].copy_(ks)
+    packed[..., hd:].copy_(vs)
+    recv = torch.empty((sum(cp_split_sizes), send.shape[1]), device=q.device, dtype=q.dtype)
+    dist.all_to_all_single(recv, send, output_split_sizes=list(cp_split_sizes), group=mpu.get_cp_group())
+    kv = recv[:, hq * hd:].view(-1, hk, 2 * hd)
+    return recv[:, :hq * hd].view(-1, hq, hd), kv[..., :hd], kv[..., hd:]
+
+
 def head_groups(q_heads: int, kv_heads: int, overlap_degree: int) -> List[Tuple[int, int, int, int]]:
     """Split the local heads into `overlap_degree` CONTIGUOUS groups (q_lo, q_hi, kv_lo, kv_hi) for the
     attention / all-to-all pipeline of context_parallel.py:565-589. overlap_degree == -1 selects q_heads // kv_heads.
@@ -318,6 +345,49 @@ class UlyssesScheduler:
         handle_q.wait()
         return UlyssesScheduler.get_attn_and_xattn_base(query, key, value, core_attn_func, cross_attn_func,
                                                         overlap_degree, batch_size, cp_size, cp_split_sizes,
+                                                        relayout_out=relayout_out)
+
+    @staticmethod
+    def get_attn_and_xattn_with_comm_overlap(get_q_func: Callable, get_k_func: Callable, get_v_func: Callable,
+                                             kv_cache_func: Callable, core_attn_func: Callable,
+                                             cross_attn_func: Callable, overlap_degree: int, batch_size: int,
+                                             cp_size: int, cp_split_sizes: List[int] = None, *,
+                                             relayout_in: Callable = None, relayout_out: Callable = None):
+        """context_parallel.py:457-501: v, k and q each start their own all-to-all as soon as they are computed
+        (v_comm under k_compute, k_comm under q_compute, q_comm under the cache update). kv_cache_func receives the
+        packed [K | V] tensor like in the reference (`torch.concat([key, value], -1)`, :493)."""
+        value = get_v_func()
+        value, handle_v = all_to_all_input_split(value, cp_split_sizes, relayout_in)
+        key = get_k_func()
+        key, handle_k = all_to_all_input_split(key, cp_split_sizes, relayout_in)
+        query = get_q_func()
+        query, handle_q = all_to_all_input_split(query, cp_split_sizes, relayout_in)
+        handle_v.wait()
+        handle_k.wait()
+        key, value = kv_cache_func(torch.cat([key, value], dim=-1))
+        handle_q.wait()
+        return UlyssesScheduler.get_attn_and_xattn_base(query, key, value, core_attn_func, cross_attn_func,
+                                                        overlap_degree, batch_size, cp_size, cp_split_sizes,
+                                                        relayout_out=relayout_out)
+
+    @staticmethod
+    def get_attn_and_xattn_with_fused_qkv_comm(get_qkv_func: Callable, kv_cache_func: Callable,
+                                               core_attn_func: Callable, cross_attn_func: Callable,
+                                               overlap_degree: int, batch_size: int, cp_size: int,
+                                               cp_split_sizes: List[int] = None, *, relayout_in: Callable = None,
+                                               relayout_out: Callable = None):
+        """context_parallel.py:529-548: q, k and v travel in ONE all-to-all (the reference takes this branch for
+        CUDA-graph runs with <= 3 denoising ranges, dit_module.py:1182-1193). get_qkv_func() -> (q, k, v)."""
+        q, k, v = get_qkv_func()
+        q, k, v = fused_qkv_communication(q, k, v, cp_split_sizes, relayout_in)
+        if k.shape[-1] == v.shape[-1] and k.data_ptr() + k.shape[-1] * k.element_size() == v.data_ptr() \
+                and k.stride() == v.stride():
+            kv = k.as_strided((k.shape[0], k.shape[1], 2 * k.shape[2]), k.stride(), k.storage_offset())  # already packed
+        else:
+            kv = torch.cat([k, v], dim=-1)
+        k, v = kv_cache_func(kv)
+        return UlyssesScheduler.get_attn_and_xattn_base(q, k, v, core_attn_func, cross_attn_func, overlap_degree,
+                                                        batch_size, cp_size, cp_split_sizes,
                                                         relayout_out=relayout_out)
 
     @staticmethod

@@ -119,6 +119,22 @@ def _ulysses_worker(rank, world, port, tag, overlap, errq):
         rel = np.linalg.norm(t2n(core_out) - ref) / np.linalg.norm(ref)
         # numpy vs ATen GEMMs feed the two sides: bf16 attention tolerance
         assert err < 6e-2 and rel < 1.5e-2, (err, rel)
+        # (3b) the other two scheduler entry points of the reference (context_parallel.py:457-501, 529-548: per-tensor
+        # all-to-alls, and q/k/v in ONE all-to-all) deliver exactly the same tensors to the same compute
+        kv_cache = lambda t: (t[..., :128], t[..., 128:])
+        out_b, _ = cpm.UlyssesScheduler.get_attn_and_xattn_with_comm_overlap(
+            lambda: q, lambda: kv[..., :128], lambda: kv[..., 128:], kv_cache, core, lambda: "xattn", overlap, 1,
+            world, split, relayout_in=relayout_in, relayout_out=relayout_out)
+        assert torch.equal(out_b, core_out)
+        out_c, _ = cpm.UlyssesScheduler.get_attn_and_xattn_with_fused_qkv_comm(
+            lambda: (q, kv[..., :128], kv[..., 128:]), kv_cache, core, lambda: "xattn", overlap, 1, world, split,
+            relayout_in=relayout_in, relayout_out=relayout_out)
+        assert torch.equal(out_c, core_out)
+        hd = min(probe.shape[-1], kvprobe.shape[-1] // 2)
+        fq, fk, fv = cpm.fused_qkv_communication(probe[..., :hd], kvprobe[..., :hd], kvprobe[..., hd:2 * hd], split,
+                                                 relayout_in)
+        assert torch.equal(fq, a_in[..., :hd]) and torch.equal(fk, kv_in[..., :hd])
+        assert torch.equal(fv, kv_in[..., hd:2 * hd])
         # (4) post-process gather == reference's
         gathered = cpm.cp_post_process(world, "cp_ulysses", gr.torch("core_attn_out").float(),
                                        type("M", (), {"cp_split_sizes": split})())
