@@ -497,6 +497,77 @@ def gen_layer():
     print("transformer layer fixture written")
 
 
+def gen_two_blocks():
+    """BASELINE.json configs[0] in miniature: the DiT cut to 2 blocks. Two reference TransformerLayers (layer numbers
+    0 and 1, own weights, own KV caches) chained through a three-forward KV-cache sequence; the fixture holds the
+    hidden state after both blocks (what the final norm + projection turn into the step's denoised latent)."""
+    dm = install_patches()
+    dm.range_mod_triton = range_mod_cpu
+    init_dist(0, 1, 29591)
+    from inference.common import InferenceParams
+    mc, ec = make_configs(hidden=256, hq=4, hkv=2)
+    layers = []
+    for ln_ in (0, 1):
+        torch.manual_seed(777 + ln_)
+        layer = dm.TransformerLayer(mc, ec, layer_number=ln_)
+        g = torch.Generator().manual_seed(777 + ln_)
+        with torch.no_grad():
+            for name, p_ in layer.named_parameters():
+                if "layernorm" in name or "post_norm" in name:
+                    p_.copy_((torch.randn(p_.shape, generator=g) * 0.2).to(p_.dtype))
+                elif name.endswith("layer_norm.weight"):
+                    p_.copy_((1.0 + torch.randn(p_.shape, generator=g) * 0.02).to(p_.dtype))
+                elif name.endswith("bias"):
+                    p_.copy_((torch.randn(p_.shape, generator=g) * 0.02).to(p_.dtype))
+                else:
+                    p_.copy_((torch.randn(p_.shape, generator=g) * (1.0 / math.sqrt(p_.shape[-1]))).to(p_.dtype))
+        for name, sub in layer.named_modules():       # dit_model.py:621-638
+            if "_xattn" in name:
+                continue
+            if any(k in name for k in ("q_layernorm", "k_layernorm", "self_attn_post_norm", "mlp_post_norm")):
+                sub.float()
+        layers.append(layer.eval())
+    H = W = 4
+    frames = 3
+    clip = frames * H * W
+    hidden = mc.hidden_size
+    fx = {}
+    for ln_, layer in enumerate(layers):
+        fx.update({f"w{ln_}." + k_: pk(v_) for k_, v_ in layer.state_dict().items()})
+    fx["clip"] = np.array(clip)
+    fx["heads"] = np.array([4, 2])
+    inf = InferenceParams(max_batch_size=1, max_sequence_length=4 * clip)
+    g = torch.Generator().manual_seed(778899)
+    # A: first stage step with the extra clean-chunk forward (writes chunks 0, 1 of both caches);
+    # B: window advanced, two chunks in flight behind cached chunk 0 (reads what A wrote, overwrites slots 1, 2);
+    # C: same state, update_kv_cache False (3-CFG first pass): reads chunk 0, leaves the caches alone
+    for tag, sp, dn, k_chunks, y_index, update, extra in (
+            ("A", 0, 2, [(0, 1), (0, 2)], [50, 41], True, True),
+            ("B", 1, 2, [(0, 2), (0, 3)], [33, 90], True, False),
+            ("C", 1, 2, [(0, 2), (1, 3)], [0, 64], False, False)):
+        S = dn * clip
+        hs = torch.randn(S, 1, hidden, generator=g).to(torch.bfloat16)
+        kvs = torch.randn(int(sum(y_index)), hidden, generator=g).to(torch.bfloat16)
+        cond = torch.randn(1, dn, int(hidden * mc.cond_hidden_ratio), generator=g).to(torch.bfloat16)
+        cmap = torch.arange(dn).repeat_interleave(clip).reshape(1, -1).transpose(0, 1).contiguous()
+        rope = rope_for(dm, (sp + dn) * frames, H, W, dn * frames)
+        m = meta(dm, clip, sp, dn, 1, [[s_ * clip, e_ * clip] for s_, e_ in k_chunks], y_index, fwd_extra=extra)
+        inf.update_kv_cache = update
+        x = hs
+        with torch.no_grad():
+            for layer in layers:
+                x = layer(x, cond, cmap, kvs, rope, inf, m)
+        fx.update({f"{tag}.hidden_states": pk(hs), f"{tag}.key_value_states": pk(kvs), f"{tag}.condition": pk(cond),
+                   f"{tag}.condition_map": cmap.numpy(), f"{tag}.rope": pk(rope),
+                   f"{tag}.k_range": np.array([[s_ * clip, e_ * clip] for s_, e_ in k_chunks], dtype=np.int32),
+                   f"{tag}.y_index": np.array(y_index), f"{tag}.meta": np.array([sp, dn, int(update), int(extra)]),
+                   f"{tag}.out": pk(x)})
+    for ln_ in (0, 1):
+        fx[f"cache{ln_}"] = pk(inf.key_value_memory_dict[ln_][:3 * clip])   # rows beyond are torch.empty garbage
+    np.savez_compressed(os.path.join(OUT, "dit_two_blocks.npz"), **fx)
+    print("two-block fixture written")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -510,6 +581,8 @@ if __name__ == "__main__":
         gen_cso(2, 29571)
     if which in ("all", "layer"):
         gen_layer()
+    if which in ("two_blocks",):  # run on its own (a process group per scenario)
+        gen_two_blocks()
     if which in ("gating",):      # run on its own: it monkey-patches Tensor.is_cuda while it runs
         gen_gating()
     if which in ("all", "single"):

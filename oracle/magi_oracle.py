@@ -504,12 +504,13 @@ def fully_parallel_attention(w, hs, kvs, rope, cache, has_inf, slice_point, dn, 
 
 
 def transformer_layer(w, hs, condition, condition_map, kvs, rope, cache, has_inf, slice_point, dn, clip, np_q_range,
-                      np_k_range, y_index, update_kv_cache, gated_linear_unit=False):
+                      np_k_range, y_index, update_kv_cache, gated_linear_unit=False, fwd_extra_1st_chunk=False):
     """TransformerLayer.forward, dit_module.py:1297-1367: attention -> "sq b (n hn hd) -> sq b (hn n hd)" (n = 2,
     hn = 8) -> linear_proj (the float32 autocast of :1343 is not supported by CUDA autocast and disables itself, so
     the projection runs in bf16) -> softcap(adaLN gates) -> bias_modulate_add -> MLP -> bias_modulate_add."""
     core, xo = fully_parallel_attention(w, hs, kvs, rope, cache, has_inf, slice_point, dn, clip, np_q_range, np_k_range,
-                                        y_index, update_kv_cache, pre="self_attention.")
+                                        y_index, update_kv_cache, fwd_extra_1st_chunk=fwd_extra_1st_chunk,
+                                        pre="self_attention.")
     sq, b, width = core.shape
     x = np.stack([core, xo], axis=2).reshape(sq, b, 2, 8, width // 8)
     x = np.transpose(x, (0, 1, 3, 2, 4)).reshape(sq, b, 2 * width)

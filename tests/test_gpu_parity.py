@@ -812,3 +812,54 @@ def test_fullsize_matches_flash_attn_library(F):
     err = (out.float() - ref.float()).abs().max().item()
     rel = ((out.float() - ref.float()).norm() / ref.float().norm()).item()
     assert err <= ATTN_MAX_ABS and rel <= ATTN_REL_L2, (err, rel)
+
+
+def test_two_block_dit_matches_reference_golden():
+    """BASELINE.json configs[0] in miniature (the DiT cut to 2 blocks): two drop-in TransformerLayers, loaded from the
+    reference's state_dicts, chained through the three-forward KV-cache sequence of tests/golden/dit_two_blocks.npz
+    (extra clean-chunk forward filling both caches; window advanced, reading them; update_kv_cache False with an empty
+    caption segment) against the reference's own two TransformerLayers run on CPU. Tolerance: the per-step latent
+    criterion of SURVEY.md section 8(c), rel-L2 <= 2e-2, on the hidden state after both blocks and on the contents of
+    both KV caches at the end (the CPU oracle's composition sits at 4.3e-3 on the same fixture)."""
+    from magi_b200.common import (EngineConfig, InferenceParams, ModelConfig, ModelMetaArgs, PackedCoreAttnParams,
+                                  PackedCrossAttnParams)
+    from magi_b200.transformer_layer import TransformerLayer, high_precision_promote
+    g = Golden("dit_two_blocks.npz")
+    hidden = g.raw("w0.self_attention.linear_qkv.layer_norm.weight").shape[0]
+    Hq, Hkv = [int(x) for x in g["heads"]]
+    mc = ModelConfig(num_layers=2, hidden_size=hidden, ffn_hidden_size=4 * hidden, num_attention_heads=Hq,
+                     num_query_groups=Hkv)
+    layers = []
+    for l in (0, 1):
+        layer = high_precision_promote(TransformerLayer(mc, EngineConfig(), layer_number=l))
+        layer.load_state_dict({k[3:]: g.torch(k) for k in g.files if k.startswith(f"w{l}.")}, strict=True)
+        layers.append(layer.cuda().eval())
+    clip = int(g["clip"])
+    inf = InferenceParams(max_batch_size=1, max_sequence_length=4 * clip)   # both layer caches are allocated lazily
+    for tag in ("A", "B", "C"):
+        sp, dn, upd, extra = [int(x) for x in g[f"{tag}.meta"]]
+        q_range, k_range = O.core_q_ranges(clip, dn, 1), g.raw(f"{tag}.k_range")
+        p = O.cross_attn_params(clip, dn, 1, g[f"{tag}.y_index"])
+        core = PackedCoreAttnParams(q_range=i32(q_range), k_range=i32(k_range), np_q_range=q_range, np_k_range=k_range,
+                                    max_seqlen_q=clip, max_seqlen_k=O.max_seqlen_k(k_range))
+        cross = PackedCrossAttnParams(q_ranges=i32(p["q_ranges"]), kv_ranges=i32(p["kv_ranges"]),
+                                      cu_seqlens_q=i32(p["cu_seqlens_q"]), cu_seqlens_kv=i32(p["cu_seqlens_kv"]),
+                                      max_seqlen_q=clip, max_seqlen_kv=800)
+        meta = ModelMetaArgs(H=4, W=4, cp_pad_size=None, cp_split_sizes=None, slice_point=sp, denoising_range_num=dn,
+                             range_num=sp + dn, extract_prefix_video_feature=False, fwd_extra_1st_chunk=bool(extra),
+                             distill_nearly_clean_chunk=False, clip_token_nums=clip, enable_cuda_graph=False,
+                             core_attn_params=core, cross_attn_params=cross)
+        inf.update_kv_cache = bool(upd)
+        x = g.torch(f"{tag}.hidden_states", "cuda")
+        for layer in layers:
+            x = layer(x, g.torch(f"{tag}.condition", "cuda"), g.torch(f"{tag}.condition_map", "cuda"),
+                      g.torch(f"{tag}.key_value_states", "cuda"), g.torch(f"{tag}.rope", "cuda"), inf, meta)
+        ref = g[f"{tag}.out"]
+        got = x.float().cpu().numpy()
+        rel = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+        assert got.shape == ref.shape and rel < 2e-2, (tag, rel)
+    for l in (0, 1):
+        ref = g[f"cache{l}"]
+        got = inf.key_value_memory_dict[l][:3 * clip].float().cpu().numpy()
+        rel = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+        assert rel < 2e-2, (l, rel)
