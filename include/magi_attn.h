@@ -243,6 +243,32 @@ typedef struct MagiGatingArgs {
 } MagiGatingArgs;
 MAGI_API int magi_bias_modulate_add(const MagiGatingArgs* args, void* stream);
 
+/*
+ * Stand-alone non-interleaved (NeoX) rotary embedding, out of place (or in place: out == x with equal strides):
+ *   out[..., :r/2] = x1 cos - x2 sin,  out[..., r/2:r] = x1 sin + x2 cos,  out[..., r:] = x[..., r:]
+ * with x1 = x[..., :r/2], x2 = x[..., r/2:r], computed in fp32, one rounding to the storage type.
+ * Replaces flash_apply_rotary_emb(q, cos_emb, sin_emb) = flash_attn.layers.rotary.apply_rotary_emb (Triton),
+ * dit_module.py:961, 978, for callers that keep the reference's unfused get_q / get_k; the fused prologue
+ * (magi_qk_norm_rope_fwd) does not need it.
+ * x / out: (batch, seqlen, heads, head_dim), fp32 (dtype 0; what the reference passes: the transposed view of the fp32
+ * LayerNorm output) or bf16 (dtype 1), explicit batch / sequence / head strides in elements, innermost dim contiguous.
+ * cos / sin: (seqlen, rotary_dim / 2) fp32 contiguous; row s is applied to every batch row and head.
+ * rotary_dim <= head_dim; rotary_dim / 2 and head_dim - rotary_dim multiples of 4; strides multiples of 4 (fp32) or
+ * 8 (bf16) elements; all pointers 16-byte aligned.
+ */
+typedef struct magi_rotary_args {
+  const void* x;
+  void* out;
+  int32_t dtype; /* 0 = fp32, 1 = bf16 (x and out) */
+  int64_t batch, seqlen;
+  int32_t heads, head_dim, rotary_dim;
+  int64_t x_batch_stride, x_seq_stride, x_head_stride;
+  int64_t out_batch_stride, out_seq_stride, out_head_stride;
+  const float* cos;
+  const float* sin;
+} magi_rotary_args;
+MAGI_API int magi_apply_rotary_emb(const magi_rotary_args* args, void* stream);
+
 /* Diagnostics */
 MAGI_API const char* magi_last_error(void);
 MAGI_API const char* magi_build_info(void);

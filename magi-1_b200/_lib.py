@@ -22,6 +22,7 @@ EXPORTS = (
     "magi_ulysses_relayout",
     "magi_cso_unshuffle",
     "magi_bias_modulate_add",
+    "magi_apply_rotary_emb",
     "magi_last_error",
     "magi_build_info",
     "magi_launch_count",
@@ -133,6 +134,17 @@ class MagiGatingArgs(C.Structure):
     ]
 
 
+class MagiRotaryArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("out", C.c_void_p), ("dtype", C.c_int32),
+        ("batch", C.c_int64), ("seqlen", C.c_int64),
+        ("heads", C.c_int32), ("head_dim", C.c_int32), ("rotary_dim", C.c_int32),
+        ("x_batch_stride", C.c_int64), ("x_seq_stride", C.c_int64), ("x_head_stride", C.c_int64),
+        ("out_batch_stride", C.c_int64), ("out_seq_stride", C.c_int64), ("out_head_stride", C.c_int64),
+        ("cos", C.c_void_p), ("sin", C.c_void_p),
+    ]
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile libmagi_attn.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
     if force:
@@ -179,6 +191,8 @@ def lib() -> C.CDLL:
                                      C.c_int64, C.c_int64, C.c_void_p]
     L.magi_bias_modulate_add.restype = C.c_int
     L.magi_bias_modulate_add.argtypes = [C.POINTER(MagiGatingArgs), C.c_void_p]
+    L.magi_apply_rotary_emb.restype = C.c_int
+    L.magi_apply_rotary_emb.argtypes = [C.POINTER(MagiRotaryArgs), C.c_void_p]
     L.magi_last_error.restype = C.c_char_p
     L.magi_build_info.restype = C.c_char_p
     L.magi_launch_count.restype = C.c_uint64

@@ -10,6 +10,7 @@
 #include "attn_fwd.cuh"
 #include "prologue.cuh"
 #include "gating.cuh"
+#include "rope.cuh"
 
 namespace {
 
@@ -34,6 +35,9 @@ int fail(const char* fmt, ...) {
     cudaError_t e__ = (expr);                                                                \
     if (e__ != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(e__));    \
   } while (0)
+
+#define MAGI_STR_(x) #x
+#define MAGI_STR(x) MAGI_STR_(x)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -108,7 +112,7 @@ const char* magi_last_error(void) { return g_err; }
 const char* magi_build_info(void) {
   return "magi_attn sm_100a tcgen05/TMEM/TMA; built " __DATE__ " " __TIME__
 #ifdef __CUDACC_VER_MAJOR__
-         "; nvcc "
+         "; nvcc " MAGI_STR(__CUDACC_VER_MAJOR__) "." MAGI_STR(__CUDACC_VER_MINOR__) "." MAGI_STR(__CUDACC_VER_BUILD__)
 #endif
          ;
 }
@@ -424,6 +428,38 @@ int magi_bias_modulate_add(const MagiGatingArgs* a, void* stream_) {
   int sms = 0;
   if (int rc = device_sm_count(&sms)) return rc;
   MAGI_CUDA(magi::gating_launch(p, a->x_dtype == 1, a->gate_dtype == 1, sms, stream));
+  g_launches++;
+  return 0;
+}
+
+int magi_apply_rotary_emb(const magi_rotary_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MAGI_CHECK(a != nullptr, "NULL args");
+  MAGI_CHECK(a->dtype == 0 || a->dtype == 1, "dtype must be 0 (fp32) or 1 (bf16)");
+  MAGI_CHECK(a->batch >= 0 && a->seqlen >= 0 && a->heads > 0 && a->head_dim > 0, "bad shape");
+  MAGI_CHECK(a->rotary_dim >= 0 && a->rotary_dim <= a->head_dim, "rotary_dim must be <= head_dim");
+  MAGI_CHECK(a->rotary_dim % 8 == 0 && (a->head_dim - a->rotary_dim) % 4 == 0,
+             "rotary_dim / 2 and head_dim - rotary_dim must be multiples of 4");
+  if (a->batch == 0 || a->seqlen == 0) return 0;
+  MAGI_CHECK(a->x && a->out && (a->rotary_dim == 0 || (a->cos && a->sin)), "NULL pointer");
+  const int64_t al = a->dtype == 1 ? 8 : 4;   // elements per 16 bytes
+  MAGI_CHECK(a->x_batch_stride % al == 0 && a->x_seq_stride % al == 0 && a->x_head_stride % al == 0 &&
+                 a->out_batch_stride % al == 0 && a->out_seq_stride % al == 0 && a->out_head_stride % al == 0,
+             "strides must be multiples of 16 bytes");
+  MAGI_CHECK(a->x_head_stride >= a->head_dim && a->out_head_stride >= a->head_dim, "head stride < head_dim");
+  MAGI_CHECK(((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->out) |
+               reinterpret_cast<uintptr_t>(a->cos) | reinterpret_cast<uintptr_t>(a->sin)) & 15) == 0,
+             "pointers must be 16-byte aligned");
+  magi::RotaryParams p;
+  p.x = a->x; p.out = a->out; p.batch = a->batch; p.seqlen = a->seqlen;
+  p.heads = a->heads; p.head_dim = a->head_dim; p.rotary_dim = a->rotary_dim;
+  p.x_bs = a->x_batch_stride; p.x_ss = a->x_seq_stride; p.x_hs = a->x_head_stride;
+  p.o_bs = a->out_batch_stride; p.o_ss = a->out_seq_stride; p.o_hs = a->out_head_stride;
+  p.cos = a->cos; p.sin = a->sin;
+  const int64_t items = a->rotary_dim / 8 + (a->head_dim - a->rotary_dim) / 4;
+  int grid = 1;
+  if (int rc = grid_for(a->batch * a->seqlen * a->heads * items, 256, &grid)) return rc;
+  MAGI_CUDA(magi::rotary_launch(p, a->dtype == 1, grid, stream));
   g_launches++;
   return 0;
 }

@@ -10,6 +10,8 @@ inference/model/dit/dit_module.py, backed by libmagi_attn.so (hand-written sm_10
     qk_norm_rope            get_q / get_k / get_v / get_kv / get_xqkv fused      (dit_module.py:953-1021)
     kv_cache_append, lse_merge, ulysses_relayout, cso_unshuffle : helpers around the context-parallel exchange
     bias_modulate_add       <- bias_modulate_add / range_mod_triton / post_norm    (dit_module.py:201-307)
+    apply_rotary_emb        <- flash_attn.layers.rotary.apply_rotary_emb (`flash_apply_rotary_emb`, dit_module.py:961,
+                            978), for callers that keep the unfused get_q / get_k; qk_norm_rope fuses it away
 
 No CPU fallback: every function requires CUDA tensors and the built extension.
 """
@@ -20,7 +22,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import MagiAttnArgs, MagiGatingArgs, MagiPrologueArgs, MagiView
+from ._lib import MagiAttnArgs, MagiGatingArgs, MagiPrologueArgs, MagiRotaryArgs, MagiView
 
 HEAD_DIM = 128
 
@@ -557,4 +559,42 @@ def bias_modulate_add(x: torch.Tensor, residual: torch.Tensor, condition_map: to
     a.rows, a.hidden = x2.shape[0], h
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().magi_bias_modulate_add(C.byref(a), _stream()), "magi_bias_modulate_add")
+    return out
+
+
+def apply_rotary_emb(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, interleaved: bool = False,
+                     inplace: bool = False) -> torch.Tensor:
+    """Same call as `flash_attn.layers.rotary.apply_rotary_emb(x, cos, sin)` as the reference uses it
+    (`flash_apply_rotary_emb(q, cos_emb, sin_emb)`, dit_module.py:961, 978): x (batch, seqlen, heads, head_dim) fp32 or
+    bf16 - any batch / sequence / head strides, so the reference's transposed (b, sq, hn, hd) view needs no copy -
+    cos / sin (seqlen, rotary_dim / 2); non-interleaved (NeoX) rotation of the first rotary_dim dims in fp32, the rest
+    copied; returns a new tensor in x's dtype (or x itself with inplace=True)."""
+    if interleaved:
+        raise NotImplementedError("the reference only uses the non-interleaved (NeoX) form")
+    if not x.is_cuda:
+        raise ValueError("x must be a CUDA tensor (this package has no CPU path)")
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError(f"x must be fp32 or bf16, got {x.dtype}")
+    if x.dim() != 4:
+        raise ValueError(f"x must have shape (batch, seqlen, heads, head_dim), got {tuple(x.shape)}")
+    b, s, h, d = x.shape
+    if cos.shape != sin.shape or cos.dim() != 2 or cos.shape[0] < s:
+        raise ValueError("cos / sin must both be (seqlen, rotary_dim / 2)")
+    ro = 2 * cos.shape[1]
+    if ro > d:
+        raise ValueError("rotary_dim must be <= head_dim")     # flash-attn asserts the same
+    if x.numel() > 0 and x.stride(-1) != 1:
+        x = x.contiguous()
+        inplace = False
+    cos = cos.to(device=x.device, dtype=torch.float32).contiguous()
+    sin = sin.to(device=x.device, dtype=torch.float32).contiguous()
+    out = x if inplace else torch.empty((b, s, h, d), dtype=x.dtype, device=x.device)
+    a = MagiRotaryArgs()
+    a.x, a.out, a.dtype = x.data_ptr(), out.data_ptr(), 1 if x.dtype == torch.bfloat16 else 0
+    a.batch, a.seqlen, a.heads, a.head_dim, a.rotary_dim = b, s, h, d, ro
+    a.x_batch_stride, a.x_seq_stride, a.x_head_stride = x.stride(0), x.stride(1), x.stride(2)
+    a.out_batch_stride, a.out_seq_stride, a.out_head_stride = out.stride(0), out.stride(1), out.stride(2)
+    a.cos, a.sin = cos.data_ptr(), sin.data_ptr()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().magi_apply_rotary_emb(C.byref(a), _stream()), "magi_apply_rotary_emb")
     return out

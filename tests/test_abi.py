@@ -53,6 +53,9 @@ def test_struct_layout_matches_header():
              sizeof(MagiGatingArgs), offsetof(MagiGatingArgs, ln_w), offsetof(MagiGatingArgs, hidden));
       printf("%zu %zu %zu\n", offsetof(magi_prologue_args, gather_peers), offsetof(magi_prologue_args, gather_kv_out),
              offsetof(magi_prologue_args, gather_row_offset));
+      printf("%zu %zu %zu %zu %zu\n", sizeof(magi_rotary_args), offsetof(magi_rotary_args, batch),
+             offsetof(magi_rotary_args, heads), offsetof(magi_rotary_args, x_batch_stride),
+             offsetof(magi_rotary_args, cos));
       return 0;
     }'''
     import tempfile
@@ -61,8 +64,11 @@ def test_struct_layout_matches_header():
         open(c, "w").write(src)
         exe = os.path.join(d, "t")
         subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
-        a, b, c_, d_ = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.strip().splitlines()
-    A, P, G = _lib.MagiAttnArgs, _lib.MagiPrologueArgs, _lib.MagiGatingArgs
+        a, b, c_, d_, e_ = subprocess.run([exe], capture_output=True, text=True,
+                                          check=True).stdout.strip().splitlines()
+    A, P, G, R = _lib.MagiAttnArgs, _lib.MagiPrologueArgs, _lib.MagiGatingArgs, _lib.MagiRotaryArgs
+    assert [int(x) for x in e_.split()] == [C.sizeof(R), R.batch.offset, R.heads.offset, R.x_batch_stride.offset,
+                                            R.cos.offset]
     assert [int(x) for x in d_.split()] == [P.gather_peers.offset, P.gather_kv_out.offset, P.gather_row_offset.offset]
     assert [int(x) for x in c_.split()] == [A.peer_out.offset, A.peer_row_bounds.offset, P.peer_kv_out.offset,
                                             P.peer_row_offset.offset, C.sizeof(G), G.ln_w.offset, G.hidden.offset]
@@ -93,6 +99,14 @@ def test_argument_errors_are_reported_not_crashed():
     assert b"no input tensor" in L.magi_last_error()
     assert L.magi_kv_cache_append(None, 256, None, 256, 0, 4, 12, None) != 0
     assert L.magi_ulysses_relayout(None, None, 4, 3, 128, 2, 1, 0, 0, 0, None) != 0   # 3 heads not divisible by cp=2
+    r = _lib.MagiRotaryArgs()
+    r.dtype, r.batch, r.seqlen, r.heads, r.head_dim, r.rotary_dim = 0, 1, 4, 2, 128, 100
+    assert L.magi_apply_rotary_emb(C.byref(r), None) != 0
+    assert b"multiples of 4" in L.magi_last_error()
+    r.rotary_dim = 160
+    assert L.magi_apply_rotary_emb(C.byref(r), None) != 0 and b"<= head_dim" in L.magi_last_error()
+    r.rotary_dim = 96
+    assert L.magi_apply_rotary_emb(C.byref(r), None) != 0 and b"NULL pointer" in L.magi_last_error()
     assert L.magi_attn_workspace_bytes(5) >= 4 * (4 + 6 + 20)
     assert b"sm_100a" in L.magi_build_info()
 
@@ -108,6 +122,8 @@ def test_python_shim_refuses_cpu_tensors():
     with pytest.raises(ValueError, match="CUDA"):
         F.qk_norm_rope(torch.zeros(4, 256, dtype=torch.bfloat16), None, None, 2, 2,
                        (torch.zeros(128), torch.zeros(128)), None, None, None)
+    with pytest.raises(ValueError, match="CUDA"):
+        F.apply_rotary_emb(torch.zeros(1, 4, 2, 128), torch.zeros(4, 48), torch.zeros(4, 48))
 
 
 def test_product_does_not_import_oracle():

@@ -863,3 +863,36 @@ def test_two_block_dit_matches_reference_golden():
         got = inf.key_value_memory_dict[l][:3 * clip].float().cpu().numpy()
         rel = np.linalg.norm(got - ref) / np.linalg.norm(ref)
         assert rel < 2e-2, (l, rel)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_apply_rotary_emb_dropin(F, dtype):
+    """`flash_apply_rotary_emb(q, cos_emb, sin_emb)` (dit_module.py:961, 978) as a stand-alone call, on the layout the
+    reference passes: the (b, sq, hn, hd) TRANSPOSED view of the (sq, b, hn, hd) LayerNorm output, fp32; also bf16,
+    in place, and a rotary_dim == head_dim table. Oracle: apply_rotary_neox (flash-attn's apply_rotary_emb_torch).
+    fp32: the two sides may contract the multiply-adds differently -> 4 fp32 ulp at |x| <= 8; bf16: one rounding."""
+    sq, b, hn, hd = 37, 2, 3, 128
+    x_sb = torch.from_numpy(rnd((sq, b, hn, hd), 5)).to("cuda").to(dtype)
+    sin, cos = O.rope_table(3, 4, 4)                                     # (48 rows, 48) each
+    sin, cos = sin[:sq], cos[:sq]
+    x = x_sb.transpose(0, 1)                                             # (b, sq, hn, hd), non-contiguous
+    out = F.apply_rotary_emb(x, torch.from_numpy(cos).cuda(), torch.from_numpy(sin).cuda())
+    ref = O.apply_rotary_neox(x.float().cpu().numpy(), cos, sin)
+    assert out.shape == x.shape and out.dtype == dtype
+    if dtype == torch.float32:
+        np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=0, atol=4e-6)
+    else:
+        assert torch.equal(out.cpu(), torch.from_numpy(ref).to(torch.bfloat16)) or \
+            np.abs(out.float().cpu().numpy() - ref).max() <= 2.0 ** -7 * 8
+    assert torch.equal(out[..., 96:], x[..., 96:])                       # dims past rotary_dim pass through
+    # in place on a contiguous tensor == out of place
+    y = x.contiguous()
+    r = F.apply_rotary_emb(y, torch.from_numpy(cos).cuda(), torch.from_numpy(sin).cuda(), inplace=True)
+    assert r.data_ptr() == y.data_ptr() and torch.equal(y, out)
+    # full-width rotation (rotary_dim == head_dim)
+    g = np.random.default_rng(3)
+    ang = g.uniform(0, 6.28, (sq, 64)).astype(np.float32)
+    out2 = F.apply_rotary_emb(x, torch.from_numpy(np.cos(ang)).cuda(), torch.from_numpy(np.sin(ang)).cuda())
+    ref2 = O.apply_rotary_neox(x.float().cpu().numpy(), np.cos(ang), np.sin(ang))
+    tol = 4e-6 if dtype == torch.float32 else 2.0 ** -7 * 8
+    assert np.abs(out2.float().cpu().numpy() - ref2).max() <= tol
