@@ -477,6 +477,54 @@ def dit_step_leg(w, dev, world, rank, steps, max_over_ranks, barrier):
                                                                          f"cp_ulysses{world} fused all-to-alls")}
 
 
+# ----------------------------------------------------------------------------------------------- GPU reference leg
+def gpu_reference_leg(w, dev, iters=3):
+    """B-REF-GPU ("the number to beat"): what the unmodified reference executes on this box for
+    the self-attention of one layer - its fallback branch, a Python loop of flash_attn_func over the denoising ranges
+    on `.contiguous()` K / V slices (dit_module.py:1025-1029, 1046-1065), with the flash-attn wheel of this image
+    (library code, used here ONLY as the measured baseline; nothing in the product imports it). MagiAttention, the
+    reference's preferred kernel, is not installable here. Same q / k / v shapes as the timed
+    workload, CUDA events, L2 not flushed between iterations (q + K/V + out of one layer are several times the 126 MB L2)."""
+    import torch
+    try:
+        from flash_attn import flash_attn_func
+    except Exception as e:  # pragma: no cover
+        return {"unavailable": f"flash_attn import failed: {e}"[:200]}
+    clip, Hq, Hkv = w["clip"], w["Hq"], w["Hkv"]
+    n = len(w["k_chunks"])
+    k_hi = max(e for _, e in w["k_chunks"])
+    g = torch.Generator(device=dev).manual_seed(4242)
+    q = torch.randn(1, n * clip, Hq, 128, device=dev, generator=g).to(torch.bfloat16)
+    kv = torch.randn(1, k_hi * clip, Hkv, 256, device=dev, generator=g).to(torch.bfloat16)
+
+    def layer():
+        # the reference materialises contiguous key / value from the packed tensor on every forward (dit_module.py:945-946)
+        k, v = kv[..., :128].contiguous(), kv[..., 128:].contiguous()
+        outs = []
+        for i, (s_, e_) in enumerate(w["k_chunks"]):
+            outs.append(flash_attn_func(q[:, i * clip:(i + 1) * clip], k[:, s_ * clip:e_ * clip],
+                                        v[:, s_ * clip:e_ * clip]))
+        return torch.cat(outs, dim=1)
+
+    try:
+        layer()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            layer()
+        e1.record()
+        torch.cuda.synchronize()
+    except Exception as e:  # pragma: no cover - e.g. a wheel without sm_100 kernels
+        return {"unavailable": f"flash_attn_func failed: {e}"[:200]}
+    ms = e0.elapsed_time(e1) / iters
+    self_f, _ = attn_flops(w)
+    import flash_attn
+    return {"kind": f"flash-attn {flash_attn.__version__} wheel, the reference's fallback loop of flash_attn_func over "
+                    f"{n} ranges (dit_module.py:1046-1065) incl. its K/V .contiguous() copies",
+            "self_attn_ms_per_layer": round(ms, 3), "tflops": round(self_f / (ms * 1e-3) / 1e12, 1), "iters": iters}
+
+
 # ----------------------------------------------------------------------------------------------- CPU baseline
 def cpu_baseline_sample(w, budget_s=20.0):
     """The reference's CPU torch path on a bounded sample of the SAME workload: the self-attention of layer 0 of the
@@ -543,12 +591,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-dit-step", action="store_true", help="skip the whole-DiT-block step latency leg")
+    ap.add_argument("--no-gpu-reference", action="store_true",
+                    help="skip the flash-attn (reference fallback) self-attention leg on the GPU")
     ap.add_argument("--profile", action="store_true",
                     help="short run for ncu: no e2e / CPU legs, warm-up exactly as given (numbers are not bench values)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.profile:
-        args.no_e2e = args.no_cpu_baseline = args.no_dit_step = True
+        args.no_e2e = args.no_cpu_baseline = args.no_dit_step = args.no_gpu_reference = True
     if args.impl == "reference":
         return run_reference(args, w)
 
@@ -686,6 +736,11 @@ def main():
     if not args.no_dit_step and not args.cp_mode.startswith("ring"):
         dit = dit_step_leg(w, dev, world, rank, min(args.steps, 3), max_over_ranks, barrier)
 
+    gpu_ref = None
+    if world == 1 and not args.no_gpu_reference:
+        # last GPU leg on purpose: it runs third-party library kernels, nothing measured above can be affected by it
+        gpu_ref = gpu_reference_leg(w, dev)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         _, cpu = cpu_baseline_sample(w, budget_s=args.ref_budget)
@@ -729,6 +784,8 @@ def main():
             line["cpu_baseline"] = cpu
         if dit is not None:
             line["dit_denoise_step"] = dit
+        if gpu_ref is not None:
+            line["gpu_reference"] = gpu_ref
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
