@@ -482,8 +482,7 @@ class FullyParallelAttention(nn.Module):
             core_attn_out, xattn_out = fwd(mixed_qqkv, key_value_states, inference_params, sin_emb, cos_emb, meta_args)
         elif strategy == "cp_ring_kv":
             fwd = self._forward_ring_fused if self._fused_ring(batch_size, dev) else self._forward_ring
-            core_attn_out, xattn_out = fwd(mixed_qqkv, key_value_states, inference_params, sin_emb,
-                                                          cos_emb, meta_args)
+            core_attn_out, xattn_out = fwd(mixed_qqkv, key_value_states, inference_params, sin_emb, cos_emb, meta_args)
         elif strategy == "cp_shuffle_overlap":
             core_attn_out, xattn_out = self._forward_cso(mixed_qqkv, key_value_states, inference_params, sin_emb,
                                                          cos_emb, meta_args)

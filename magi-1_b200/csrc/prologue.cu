@@ -8,8 +8,8 @@
 //   KV-cache slice-assign                   dit_module.py:918-929
 //   all_to_all_input_split's re-layout      inference/infra/parallelism/context_parallel.py:393-396
 //
-// HBM-bound: every element is read once (2 B) and written once (2 B); one half-warp owns one (row, head) vector of
-// 128 bf16 as 16 x 16-byte lanes, so every global access is a full 256-byte coalesced segment.
+// HBM-bound: every element is read once (2 B) and written once (2 B); in the prologue 8 lanes own one (row, head)
+// vector of 128 bf16 (two 16-byte pieces per lane), the helper kernels move 16 bytes per thread.
 #include "common.cuh"
 #include "prologue.cuh"
 
