@@ -27,7 +27,11 @@ def val(t):
 
 def main(n_cases):
     dm = G.install_patches()
-    G.init_dist(0, 1, 29621)
+    import socket
+    with socket.socket() as s_:           # a free rendezvous port for the single-rank gloo group the reference needs
+        s_.bind(("127.0.0.1", 0))
+        port = s_.getsockname()[1]
+    G.init_dist(0, 1, port)
     from inference.common import InferenceParams
     rng = np.random.default_rng(2024)
     worst = dict(core_rel=0.0, xattn_rel=0.0, cache_rel=0.0)

@@ -293,6 +293,12 @@ def _ring_worker(rank, world, port, errq):
 
 
 def _spawn(fn, world, args):
+    # the rendezvous port in `args[0]` is only a label: a free port is picked at run time so that a busy or lingering
+    # socket from another process / an earlier run cannot fail the test
+    import socket
+    with socket.socket() as s_:
+        s_.bind(("127.0.0.1", 0))
+        args = (s_.getsockname()[1],) + tuple(args[1:])
     ctx = mp.get_context("spawn")
     errq = ctx.Queue()
     procs = [ctx.Process(target=fn, args=(r, world) + args + (errq,)) for r in range(world)]
