@@ -15,6 +15,7 @@ timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest_gpu.log 2>&
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $out/${tag}_smoke.log
 timeout 900 python bench.py > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err; echo "bench rc=$?"; cut -c1-400 $out/${tag}_bench_n1.json
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_bench_reference.json 2>&1; echo "reference arm rc=$?"
+timeout 300 python tools/graph_step.py --workload cfg1 > $out/${tag}_graph_step_cfg1.json 2>&1; echo "graph step rc=$?"; tail -1 $out/${tag}_graph_step_cfg1.json
 # launch list of one profiled step (cold-cache, serialised: shares, not absolutes)
 P="python bench.py --profile --steps 1 --warmup 1"
 timeout 600 $P > $out/${tag}_profile_plain.log 2>&1 &&
