@@ -612,8 +612,6 @@ class FullyParallelAttention(nn.Module):
         chunk i-1."""
         sq, b, _ = mixed_qqkv.shape
         assert b == 1                                       # dit_module.py:1070
-        if self.engine_config.kv_offload:
-            raise NotImplementedError("kv_offload is available with cp_strategy 'none' and 'cp_ulysses'")
         cp, dn = self.engine_config.cp_size, meta_args.denoising_range_num
         Hq, Hkv = self.model_config.num_attention_heads, self.model_config.num_query_groups
         eps, z = self.model_config.layernorm_epsilon, self.model_config.apply_layernorm_1p
@@ -646,15 +644,19 @@ class FullyParallelAttention(nn.Module):
         handle_kv.wait()
         total_rows = dn * clip
         cache, start, app = self._cache_plan(inference_params, meta_args, total_rows, dt, dev)
-        if cache is not None and app == total_rows:        # un-shuffle straight into the cache slot
+        offload = cache is not None and not cache.is_cuda  # kv_offload: pinned-host cache staged through KVOffload
+        if cache is not None and app == total_rows and not offload:   # un-shuffle straight into the cache slot
             kv_new = F.cso_unshuffle(kv_recv, cp, dn, clip, out=cache[start:start + total_rows])
         else:
             kv_new = F.cso_unshuffle(kv_recv, cp, dn, clip)
-            if cache is not None and app > 0:
+            if offload:
+                KVOffload.of(inference_params, dev).store(self.layer_number, cache, kv_new, start, app)
+            elif cache is not None and app > 0:
                 F.kv_cache_append(cache, kv_new, start, app)
         kc = vc = None
         if cache is not None and start > 0:
-            kc, vc = cache[:start, :, :F.HEAD_DIM], cache[:start, :, F.HEAD_DIM:]
+            kc, vc = (self._offload_views(inference_params, cache, start) if offload else
+                      (cache[:start, :, :F.HEAD_DIM], cache[:start, :, F.HEAD_DIM:]))
 
         handle_q.wait()
         outs, handle_attn = helper.overlap(partial(self.full_attention, b, meta_args, k_cache=kc, v_cache=vc), query,
@@ -737,7 +739,8 @@ class FullyParallelAttention(nn.Module):
                 raise NotImplementedError("cp_ring_kv with batch size > 1 supports the cache-less uncond pass only")
             return self._forward_ulysses(mixed_qqkv, key_value_states, inference_params, sin_emb, cos_emb, meta_args)
         if self.engine_config.kv_offload:
-            raise NotImplementedError("kv_offload is available with cp_strategy 'none' and 'cp_ulysses'")
+            raise NotImplementedError("kv_offload is available with cp_strategy 'none', 'cp_ulysses' and "
+                                      "'cp_shuffle_overlap'")
         Hq, Hkv = self.model_config.num_attention_heads, self.model_config.num_query_groups
         eps, z = self.model_config.layernorm_epsilon, self.model_config.apply_layernorm_1p
         dev, dt = mixed_qqkv.device, mixed_qqkv.dtype

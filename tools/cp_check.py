@@ -35,10 +35,10 @@ def main():
     Hq, Hkv, hidden, clip = 24, 8, 512, 1111       # 1111: shards and tiles are ragged everywhere
     mc = ModelConfig(num_layers=4, hidden_size=hidden, num_attention_heads=Hq, num_query_groups=Hkv)
 
-    def build(strategy, cp):
+    def build(strategy, cp, offload=False):
         torch.manual_seed(1234)
         m = FullyParallelAttention(mc, EngineConfig(cp_size=cp, cp_strategy=strategy, ulysses_overlap_degree=overlap,
-                                                    cp_fused_all_to_all=fused), layer_number=1)
+                                                    cp_fused_all_to_all=fused, kv_offload=offload), layer_number=1)
         g = torch.Generator().manual_seed(99)
         with torch.no_grad():
             for n, p in m.named_parameters():
@@ -84,9 +84,15 @@ def main():
         second = kv_loc if kv_loc > 1 else 3      # whole kv heads per group, or 3 q-head groups in the MQA case
         # cp_ulysses: all-to-alls fused into the kernels (NVLink peer stores), then the NCCL path at two overlap degrees
         # cp_ring_kv: K/V all-gather fused into the prologue's stores (one attention launch), then the NCCL ring
-        for overlap, fused in (((1, True), (1, False), (second, False)) if strategy == "cp_ulysses" else
-                               ((1, True), (1, False)) if strategy == "cp_ring_kv" else ((1, False),)):
-            ref_m, cp_m = build("none", 1), build(strategy, world)
+        # CP_CHECK_KV_OFFLOAD=1 adds, for the two reference strategies, the NCCL path with the KV caches in pinned host
+        # memory (kv_offload, dit_module.py:803-811) against the resident single-GPU forward
+        off_variants = ((1, False, True),) if (os.environ.get("CP_CHECK_KV_OFFLOAD") == "1"
+                                               and strategy != "cp_ring_kv") else ()
+        for overlap, fused, offload in ((((1, True, False), (1, False, False), (second, False, False))
+                                         if strategy == "cp_ulysses" else
+                                         ((1, True, False), (1, False, False)) if strategy == "cp_ring_kv" else
+                                         ((1, False, False),)) + off_variants):
+            ref_m, cp_m = build("none", 1), build(strategy, world, offload)
             inf_ref = InferenceParams(1, 5 * clip)
             inf_cp = InferenceParams(1, 5 * clip)
             worst = {"core": 0.0, "xattn": 0.0}
@@ -149,7 +155,7 @@ def main():
                 xo = cpm.cp_post_process(world, strategy, xo.contiguous(), m_cp)
                 worst["core"] = max(worst["core"], (core.float() - ref_core.float()).abs().max().item())
                 worst["xattn"] = max(worst["xattn"], (xo.float() - ref_x.float()).abs().max().item())
-            results[f"{strategy}/{'fused-p2p' if fused else 'nccl'}/overlap{overlap}"] = worst
+            results[f"{strategy}/{'fused-p2p' if fused else 'nccl'}/overlap{overlap}{'/kv_offload' if offload else ''}"] = worst
     torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:
