@@ -896,3 +896,33 @@ def test_apply_rotary_emb_dropin(F, dtype):
     ref2 = O.apply_rotary_neox(x.float().cpu().numpy(), np.cos(ang), np.sin(ang))
     tol = 4e-6 if dtype == torch.float32 else 2.0 ** -7 * 8
     assert np.abs(out2.float().cpu().numpy() - ref2).max() <= tol
+
+
+def test_maxsize_24b_720p_sampled_rows_vs_oracle(F):
+    """The largest single-GPU state of BASELINE.json (configs[3]'s per-GPU problem before sharding: 24B heads 48 / 8,
+    720x1280 -> 21 600 tokens per chunk, 5 ranges in flight = 108 000 query rows, keys up to 3 chunks, noise2clean
+    windows that start mid-sequence) in ONE launch; the fp32 oracle is evaluated on sampled (row, head) pairs - first,
+    last and a random row of every range, first / last / random head - where it costs a 64 800 x 128 product each.
+    Same tolerances as everywhere: out max_abs <= 2e-2, lse <= 1e-3. Also: the launch is deterministic."""
+    clip, Hq, Hkv = 21600, 48, 8
+    k_chunks = [(0, 1), (0, 2), (0, 3), (1, 4), (3, 5)]
+    g = torch.Generator(device="cuda").manual_seed(11)
+    q = torch.randn(5 * clip, Hq, 128, device="cuda", dtype=torch.bfloat16, generator=g)
+    kv = torch.randn(5 * clip, Hkv, 256, device="cuda", dtype=torch.bfloat16, generator=g)
+    qr = i32([[i * clip, (i + 1) * clip] for i in range(5)])
+    kr = i32([[s * clip, e * clip] for s, e in k_chunks])
+    out, lse = F.attn_ranges(q, kv[..., :128], kv[..., 128:], qr, kr)
+    out2, lse2 = F.attn_ranges(q, kv[..., :128], kv[..., 128:], qr, kr)
+    assert torch.equal(out, out2) and torch.equal(lse, lse2)
+    rng = np.random.default_rng(5)
+    worst_o = worst_l = 0.0
+    for i, (s, e) in enumerate(k_chunks):
+        for row in (i * clip, i * clip + int(rng.integers(1, clip - 1)), (i + 1) * clip - 1):
+            for h in (0, int(rng.integers(1, Hq - 1)), Hq - 1):
+                hk = h // (Hq // Hkv)
+                keys = kv[s * clip:e * clip, hk].float().cpu().numpy()
+                ref_o, ref_l = O.attn_ranges(q[row:row + 1, h:h + 1].float().cpu().numpy(), keys[:, None, :128],
+                                             keys[:, None, 128:], [[0, 1]], [[0, keys.shape[0]]], round_output=False)
+                worst_o = max(worst_o, float(np.abs(out[row, h].float().cpu().numpy() - ref_o[0, 0]).max()))
+                worst_l = max(worst_l, abs(float(lse[row, h]) - float(ref_l[0, 0])))
+    assert worst_o <= ATTN_MAX_ABS and worst_l <= 1e-3, (worst_o, worst_l)
