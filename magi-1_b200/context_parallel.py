@@ -236,6 +236,19 @@ def cp_post_process(cp_size: int, cp_strategy: str, x: torch.Tensor, meta_args: 
 #####################################################
 # Ulysses all-to-all
 #####################################################
+def _kernel_relayout_in(tensor: torch.Tensor, cp: int, rep: int) -> torch.Tensor:
+    """Default send-side re-layout when the caller injects none: the CUDA kernel behind magi_ulysses_relayout (mode 0).
+    Imported lazily - the CPU (gloo) tests inject torch doubles and never load the library."""
+    from . import functional as F
+    return F.ulysses_relayout(tensor.contiguous(), cp, 0, kv_repeat=rep)
+
+
+def _kernel_relayout_out(recv: torch.Tensor, cp: int, result: torch.Tensor, q_head: int, lo: int) -> None:
+    """Default receive-side re-layout (mode 1), writing heads [lo, lo + hn) of every cp block of `result` in place."""
+    from . import functional as F
+    F.ulysses_relayout(recv, cp, 1, out=result, dst_heads_total=q_head, dst_head_offset=lo)
+
+
 def all_to_all_input_split(tensor: torch.Tensor, cp_split_sizes: List[int], relayout: Optional[Callable] = None,
                            send_layout: bool = False, out: Optional[torch.Tensor] = None):
     """context_parallel.py:381-401: scatter heads / gather sequence. tensor (seq, cp*hn, hd) -> (sum(sizes), hn, hd).
@@ -249,7 +262,7 @@ def all_to_all_input_split(tensor: torch.Tensor, cp_split_sizes: List[int], rela
     if not send_layout:
         _, hn, _ = tensor.shape
         rep = cp // hn if (cp % hn == 0 and cp != hn) else 1
-        tensor = relayout(tensor, cp, rep)
+        tensor = (relayout or _kernel_relayout_in)(tensor, cp, rep)
     assert tensor.is_contiguous()
     if out is None:
         out = torch.empty([sum(cp_split_sizes), *tensor.shape[1:]], device=tensor.device, dtype=tensor.dtype)
@@ -286,6 +299,7 @@ def fused_qkv_communication(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, c
     assert cp_split_sizes is not None
     k_head = k.shape[1]
     rep = cp // k_head if (cp % k_head == 0 and cp != k_head) else 1
+    relayout = relayout or _kernel_relayout_in
     qs, ks, vs = relayout(q, cp, 1), relayout(k, cp, rep), relayout(v, cp, rep)
     hq, hk, hd = qs.shape[1], ks.shape[1], qs.shape[2]
     # wire format per row: [q heads | (K | V) per kv head], one contiguous message per destination rank
@@ -398,6 +412,7 @@ class UlyssesScheduler:
         cross-attention (local tokens, all heads, no communication) overlaps the last one."""
         q_seq, q_head, q_hidden = query.shape
         kv_head = key.shape[1]
+        relayout_out = relayout_out or _kernel_relayout_out
         groups = head_groups(q_head, kv_head, overlap_degree)
         local = cp_split_sizes[mpu.get_cp_rank()] if cp_split_sizes is not None else q_seq
         result = torch.empty((local, cp_size * q_head, q_hidden), dtype=query.dtype, device=query.device)
