@@ -240,6 +240,10 @@ class FullyParallelAttention(nn.Module):
             assert start + rows <= cache.size(0)   # dit_module.py:927
         return cache, start, rows
 
+    def _offloaded(self, cache) -> bool:
+        """kv_offload (dit_module.py:803-811): this layer's cache lives in pinned host memory."""
+        return cache is not None and self.engine_config.kv_offload and not cache.is_cuda
+
     def _offload_views(self, inference_params, cache, start):
         """kv_offload: device views (k, v) of the cache prefix cache[:start], staged through KVOffload."""
         off = KVOffload.of(inference_params, torch.device("cuda", torch.cuda.current_device()))
@@ -316,7 +320,7 @@ class FullyParallelAttention(nn.Module):
             return key_and_value[..., :F.HEAD_DIM], key_and_value[..., F.HEAD_DIM:]
         cache, start, app = self._cache_plan(inference_params, meta_args, key_and_value.shape[0], key_and_value.dtype,
                                              key_and_value.device)
-        if cache is not None and not cache.is_cuda:      # kv_offload
+        if self._offloaded(cache):
             off = KVOffload.of(inference_params, key_and_value.device)
             pre = off.prefix(self.layer_number, cache, start,
                              inference_params.key_value_memory_dict.get(self.layer_number + 1)) if start > 0 else None
@@ -453,7 +457,7 @@ class FullyParallelAttention(nn.Module):
             assert self.engine_config.cp_size == 1
             xq, xk, xv = self._project(mixed_qqkv)
             cache, start, app = self._cache_plan(inference_params, meta_args, rows, dt, dev)
-            offload = cache is not None and not cache.is_cuda
+            offload = self._offloaded(cache)
             query, kv_new = F.qk_norm_rope(xq, xk, xv, Hq, Hkv, self._ln(self.q_layernorm), self._ln(self.k_layernorm),
                                            sin_emb, cos_emb, batch=batch_size, eps=eps, zero_centered_gamma=z,
                                            cache=cache if app > 0 and not offload else None, cache_row_offset=start,
@@ -503,7 +507,7 @@ class FullyParallelAttention(nn.Module):
         x2d = mixed_qqkv.reshape(rows, -1)
         cache, start, app = self._cache_plan(inference_params, meta_args, total_rows, dt, dev)
         hkv_loc = self.num_query_groups_per_partition
-        offload = cache is not None and not cache.is_cuda
+        offload = self._offloaded(cache)
         # the KV all-to-all lands straight in the cache slot when every received row is to be cached
         direct = cache is not None and app == total_rows and not offload
         kv_recv = cache[start:start + total_rows] if direct else None
@@ -644,7 +648,7 @@ class FullyParallelAttention(nn.Module):
         handle_kv.wait()
         total_rows = dn * clip
         cache, start, app = self._cache_plan(inference_params, meta_args, total_rows, dt, dev)
-        offload = cache is not None and not cache.is_cuda  # kv_offload: pinned-host cache staged through KVOffload
+        offload = self._offloaded(cache)                   # pinned-host cache staged through KVOffload
         if cache is not None and app == total_rows and not offload:   # un-shuffle straight into the cache slot
             kv_new = F.cso_unshuffle(kv_recv, cp, dn, clip, out=cache[start:start + total_rows])
         else:

@@ -1,0 +1,149 @@
+"""TEST DOUBLE of magi_b200.functional on the CPU, built on the oracle. It exists so that the HOST LOGIC of the drop-in
+module under context parallelism (FullyParallelAttention._forward_ulysses / _forward_cso / _forward_ring: cache plans,
+send layouts, all-to-all plumbing, head groups, range handling) can run in the CPU suite on gloo, world size > 1,
+against the reference's per-rank golden outputs. It mirrors the argument meaning of the real functions; the kernels'
+own numerics are what tests/test_gpu_parity.py checks on the B200. Never imported by the product.
+
+Only what the non-fused paths call is implemented (no NVLink peer / multicast routing: gloo has no symmetric memory,
+and the module falls back to its NCCL-style paths by itself)."""
+import numpy as np
+import torch
+
+import magi_oracle as O
+
+HEAD_DIM = 128
+
+
+def _np(t):
+    return t.detach().float().numpy()
+
+
+def _bf(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(torch.bfloat16)
+
+
+def _norm_rope(x, heads, ln, sin, cos, batch, eps, zcg):
+    rows = x.shape[0]
+    v = _np(x).reshape(rows, heads, HEAD_DIM)
+    if ln is not None:
+        w, b = ln
+        if w.dtype == torch.bfloat16:
+            v = O.xattn_layer_norm(v, _np(w), _np(b), eps, zcg)
+        else:
+            v = O.layer_norm(v, _np(w), _np(b), eps, zcg)
+    if sin is not None:
+        s, c = np.repeat(_np(sin), batch, axis=0), np.repeat(_np(cos), batch, axis=0)   # row r -> table row r // batch
+        v = O.apply_rotary_neox(v, c, s)
+    return O.bf16_round(v)
+
+
+def _send_layout(v, cp, rep=1):
+    """"seq (cp hn) hd -> (cp seq) hn hd" with KV-head replication (context_parallel.py:393-396)."""
+    if rep > 1:
+        v = np.repeat(v, rep, axis=1)
+    rows, heads, d = v.shape
+    return v.reshape(rows, cp, heads // cp, d).transpose(1, 0, 2, 3).reshape(cp * rows, heads // cp, d)
+
+
+def qk_norm_rope(x_q, x_k, x_v, num_heads_q, num_heads_kv, ln_q, ln_k, sin, cos, batch=1, eps=1e-6,
+                 zero_centered_gamma=True, q_out=None, kv_out=None, cache=None, cache_row_offset=0, cache_rows=0,
+                 head_perm_cp=1, **unsupported):
+    assert not {k for k, v in unsupported.items() if v is not None and v != 0}, "peer / gather routing has no CPU double"
+    cp = max(1, head_perm_cp)
+    q_res = kv_res = None
+    if x_q is not None:
+        q = _norm_rope(x_q, num_heads_q, ln_q, sin, cos, batch, eps, zero_centered_gamma)
+        if cp > 1:
+            q = _send_layout(q, cp)
+        q_res = _bf(q)
+        if q_out is not None:
+            q_out.copy_(q_res)
+            q_res = q_out
+    if x_k is not None or x_v is not None:
+        rows = (x_k if x_k is not None else x_v).shape[0]
+        k = _norm_rope(x_k, num_heads_kv, ln_k, sin, cos, batch, eps, zero_centered_gamma)
+        v = _np(x_v).reshape(rows, num_heads_kv, HEAD_DIM)
+        kv = np.concatenate([k, v], axis=-1)
+        if cp > 1:
+            kv = _send_layout(kv, cp, cp // num_heads_kv if cp > num_heads_kv else 1)
+        kv_res = _bf(kv)
+        if kv_out is not None:
+            kv_out.copy_(kv_res)
+            kv_res = kv_out
+        if cache is not None and cache_rows > 0:
+            assert cp == 1
+            cache[cache_row_offset:cache_row_offset + cache_rows] = kv_res[:cache_rows]
+    return q_res, kv_res
+
+
+def attn_ranges(q, k_new, v_new, q_ranges=None, k_ranges=None, k_cache=None, v_cache=None, cu_seqlens_q=None,
+                cu_seqlens_k=None, softmax_scale=None, out=None, return_lse=True, zero_fill=False, num_sms=0,
+                proj_input=None, peer_out=None):
+    assert peer_out is None, "peer routing has no CPU double"
+    ks = [t for t in (k_cache, k_new) if t is not None and t.shape[0] > 0]
+    vs = [t for t in (v_cache, v_new) if t is not None and t.shape[0] > 0]
+    if q_ranges is None:
+        cq, ck = cu_seqlens_q.numpy().astype(np.int64), cu_seqlens_k.numpy().astype(np.int64)
+        qr, kr = np.stack([cq[:-1], cq[1:]], 1), np.stack([ck[:-1], ck[1:]], 1)
+    else:
+        qr, kr = q_ranges.numpy().astype(np.int64).reshape(-1, 2), k_ranges.numpy().astype(np.int64).reshape(-1, 2)
+    hkv = (k_new if k_new is not None else k_cache).shape[1]
+    k = np.concatenate([_np(t) for t in ks], 0) if ks else np.zeros((0, hkv, HEAD_DIM), np.float32)
+    v = np.concatenate([_np(t) for t in vs], 0) if vs else np.zeros((0, hkv, HEAD_DIM), np.float32)
+    kr = np.clip(kr, 0, k.shape[0])
+    o, lse = O.attn_ranges(_np(q), k, v, qr, kr, softmax_scale)
+    covered = np.zeros(q.shape[0], dtype=bool)
+    for a, b in qr:
+        covered[a:b] = True
+    rows = torch.from_numpy(np.nonzero(covered)[0])
+    res = _bf(o)
+    if proj_input is not None:
+        buf, n_src, hn = proj_input
+        tq, hq = q.shape[0], q.shape[1]
+        view = buf.view(tq, hn, 2, hq // hn, HEAD_DIM)
+        view[rows, :, n_src] = res.view(tq, hn, hq // hn, HEAD_DIM)[rows]
+        out = buf
+    elif out is None:
+        out = res if zero_fill else res            # uncovered rows of a fresh tensor are unspecified: zeros here
+    else:
+        out[rows] = res[rows]                      # rows covered by no range are left untouched
+    return out, (torch.from_numpy(lse) if return_lse else None)
+
+
+def kv_cache_append(cache, kv, row_offset, rows=None):
+    rows = kv.shape[0] if rows is None else rows
+    cache[row_offset:row_offset + rows] = kv[:rows]
+
+
+def cso_unshuffle(recv, cp, dn, clip, out=None):
+    """dst[d * clip + t] = src[((t // spb) * dn + d) * spb + t % spb] (dit_module.py:1215-1224)."""
+    spb = recv.shape[0] // (cp * dn)
+    t = np.arange(clip)
+    idx = np.concatenate([((t // spb) * dn + d) * spb + t % spb for d in range(dn)])
+    res = recv[torch.from_numpy(idx)]
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res.contiguous()
+
+
+def ulysses_relayout(src, cp, mode, kv_repeat=1, out=None, dst_heads_total=0, dst_head_offset=0):
+    t_, h_, e_ = src.shape
+    if mode == 0:
+        res = _bf(_send_layout(_np(src), cp, kv_repeat))
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+    seq = t_ // cp
+    total = dst_heads_total if dst_heads_total > 0 else h_
+    if out is None:
+        out = torch.zeros((seq, cp * total, e_), dtype=src.dtype)
+    out.view(seq, cp, total, e_)[:, :, dst_head_offset:dst_head_offset + h_] = src.view(cp, seq, h_, e_).permute(1, 0, 2, 3)
+    return out
+
+
+def lse_merge(out_a, lse_a, out_b, lse_b):
+    m, l = O.lse_merge(_np(out_a), lse_a.numpy(), _np(out_b), lse_b.numpy())
+    out_a.copy_(_bf(m))
+    lse_a.copy_(torch.from_numpy(l))
