@@ -104,7 +104,7 @@ def attn_ranges(q, k_new, v_new, q_ranges=None, k_ranges=None, k_cache=None, v_c
         view[rows, :, n_src] = res.view(tq, hn, hq // hn, HEAD_DIM)[rows]
         out = buf
     elif out is None:
-        out = res if zero_fill else res            # uncovered rows of a fresh tensor are unspecified: zeros here
+        out = res                                  # uncovered rows of a fresh tensor are unspecified: zeros here
     else:
         out[rows] = res[rows]                      # rows covered by no range are left untouched
     return out, (torch.from_numpy(lse) if return_lse else None)
@@ -147,3 +147,15 @@ def lse_merge(out_a, lse_a, out_b, lse_b):
     m, l = O.lse_merge(_np(out_a), lse_a.numpy(), _np(out_b), lse_b.numpy())
     out_a.copy_(_bf(m))
     lse_a.copy_(torch.from_numpy(l))
+
+
+def bias_modulate_add(x, residual, condition_map, gate, post_norm, out=None):
+    if isinstance(post_norm, (tuple, list)):
+        w, b, eps, zcg = post_norm
+    else:
+        w, b, eps, zcg = post_norm.weight, post_norm.bias, post_norm.eps, post_norm.zero_centered_gamma
+    res = _bf(O.bias_modulate_add(_np(x), _np(residual), condition_map.numpy(), _np(gate), _np(w), _np(b), eps, zcg))
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res

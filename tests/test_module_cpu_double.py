@@ -1,0 +1,150 @@
+"""The drop-in modules' HOST logic on one CPU rank, kernels replaced by the oracle-backed doubles of
+tests/cpu_functional_double.py: FullyParallelAttention (cp_strategy "none": cache plans, two-segment key handling,
+batched uncond pass, the fused out-projection input layout) replaying the reference's golden forward sequence, and the
+two-block TransformerLayer stack. The same scenarios run with the real kernels in tests/test_gpu_parity.py; here they
+guard the Python around the kernels in the CPU suite."""
+import numpy as np
+import pytest
+import torch
+
+import cpu_functional_double as D
+import magi_oracle as O
+from golden_io import Golden
+
+
+@pytest.fixture()
+def doubles(monkeypatch):
+    import magi_b200  # noqa: F401
+    import magi_b200.attention as A
+    import magi_b200.transformer_layer as T
+    monkeypatch.setattr(A, "F", D)
+    monkeypatch.setattr(T, "F", D)
+    return A, T
+
+
+def i32(a):
+    return torch.as_tensor(np.asarray(a, dtype=np.int32))
+
+
+def _meta(clip, sp, dn, bs, q_range, k_range, y_index, extra=False, ncc=False):
+    from magi_b200.common import ModelMetaArgs, PackedCoreAttnParams, PackedCrossAttnParams
+    p = O.cross_attn_params(clip, dn, bs, y_index)
+    core = PackedCoreAttnParams(q_range=i32(q_range), k_range=i32(k_range), np_q_range=q_range, np_k_range=k_range,
+                                max_seqlen_q=clip, max_seqlen_k=O.max_seqlen_k(k_range))
+    cross = PackedCrossAttnParams(q_ranges=i32(p["q_ranges"]), kv_ranges=i32(p["kv_ranges"]),
+                                  cu_seqlens_q=i32(p["cu_seqlens_q"]), cu_seqlens_kv=i32(p["cu_seqlens_kv"]),
+                                  max_seqlen_q=clip, max_seqlen_kv=800)
+    return ModelMetaArgs(H=4, W=4, cp_pad_size=None, cp_split_sizes=None, slice_point=sp, denoising_range_num=dn,
+                         range_num=sp + dn, extract_prefix_video_feature=False, fwd_extra_1st_chunk=bool(extra),
+                         distill_nearly_clean_chunk=bool(ncc), clip_token_nums=clip, enable_cuda_graph=False,
+                         core_attn_params=core, cross_attn_params=cross)
+
+
+def _rel(got, ref):
+    got, ref = got.float().numpy(), np.asarray(ref, np.float32).reshape(tuple(got.shape))
+    return float(np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-9)), float(np.abs(got - ref).max())
+
+
+def test_attention_module_replays_the_reference_sequence(doubles):
+    """Steps A-E of tests/golden/attention_single_rank.npz (cache fill, fwd_extra_1st_chunk, update_kv_cache off / on,
+    distill extra range, batched uncond pass without inference params)."""
+    A, _ = doubles
+    from magi_b200.common import EngineConfig, InferenceParams, ModelConfig
+    g = Golden("attention_single_rank.npz")
+    Hq, Hkv = g["A.q"].shape[1], g["A.kv"].shape[1]
+    hidden = g.raw("w.linear_qkv.layer_norm.weight").shape[0]
+    attn = A.FullyParallelAttention(ModelConfig(num_layers=4, hidden_size=hidden, num_attention_heads=Hq,
+                                                num_query_groups=Hkv), EngineConfig(), layer_number=1)
+    for n_ in ("q_layernorm", "k_layernorm"):
+        getattr(attn, n_).float()
+    attn.load_state_dict({name: g.torch(key) for name, key in g.weights().items()}, strict=True)
+    attn.eval()
+    clip = int(g["clip"])
+    inf = InferenceParams(max_batch_size=1, max_sequence_length=4 * clip)
+    inf.key_value_memory_dict[1] = torch.zeros(4 * clip, Hkv, 256, dtype=torch.bfloat16)
+    for s in ["A", "B", "C", "D", "E"]:
+        sp, dn, bs, upd, extra, ncc, has_inf = [int(x) for x in g[f"{s}.meta"]]
+        meta = _meta(clip, sp, dn, bs, g.raw(f"{s}.q_range"), g.raw(f"{s}.k_range"), g[f"{s}.y_index"], extra, ncc)
+        params = inf if has_inf else None
+        if params is not None:
+            params.update_kv_cache = bool(upd)
+        core, xo = attn(g.torch(f"{s}.hidden_states"), g.torch(f"{s}.key_value_states"), params, g.torch(f"{s}.rope"),
+                        meta)
+        for name, got, ref in (("core_attn_out", core, g[f"{s}.core_attn_out"]), ("xattn_out", xo, g[f"{s}.xattn_out"])):
+            rel, err = _rel(got, ref)
+            assert rel <= 5e-3 and err <= 3e-2, (s, name, rel, err)
+        if f"{s}.cache_after" in g:
+            ref_cache = g[f"{s}.cache_after"]
+            cache = inf.key_value_memory_dict[1].float().numpy()
+            assert np.array_equal(np.abs(cache).sum(axis=(1, 2)) > 0, np.abs(ref_cache).sum(axis=(1, 2)) > 0), s
+            assert np.abs(cache - ref_cache).max() <= 4e-2, s
+        if s == "B":
+            assert float(xo[:clip].abs().sum()) == 0.0      # a chunk without caption tokens -> zeros
+
+
+def test_fused_out_projection_input_equals_cat_and_rearrange(doubles):
+    """forward(..., fused_proj_input=True) writes "sq b (hn n hd)" in place; it must equal the reference's
+    torch.cat + rearrange of the two outputs (attn_linear_proj, dit_module.py:1332-1338) - incl. a cached prefix."""
+    A, _ = doubles
+    from magi_b200.common import EngineConfig, InferenceParams, ModelConfig
+    torch.manual_seed(0)
+    Hq, Hkv, hidden, clip = 8, 2, 128, 24
+    attn = A.FullyParallelAttention(ModelConfig(num_layers=2, hidden_size=hidden, num_attention_heads=Hq,
+                                                num_query_groups=Hkv), EngineConfig(), layer_number=0)
+    for n_ in ("q_layernorm", "k_layernorm"):
+        getattr(attn, n_).float()
+    with torch.no_grad():
+        for n, p in attn.named_parameters():
+            p.copy_((torch.randn(p.shape) * (0.2 if "layernorm" in n or "layer_norm" in n else p.shape[-1] ** -0.5)
+                     + (1.0 if n.endswith("layer_norm.weight") else 0.0)).to(p.dtype))
+    attn.eval()
+    outs = []
+    for fused in (False, True):
+        inf = InferenceParams(1, 4 * clip)
+        g = torch.Generator().manual_seed(3)
+        res = []
+        for sp, dn, kc, yi, extra in ((0, 2, [(0, 1), (0, 2)], [9, 0], True), (1, 2, [(0, 2), (1, 3)], [5, 11], False)):
+            hs = torch.randn(dn * clip, 1, hidden, generator=g).to(torch.bfloat16)
+            kvs = torch.randn(sum(yi), hidden, generator=g).to(torch.bfloat16)
+            ang = torch.rand(dn * clip, 48, generator=g) * 6.28
+            rope = torch.cat([torch.sin(ang), torch.cos(ang)], -1)
+            meta = _meta(clip, sp, dn, 1, O.core_q_ranges(clip, dn, 1),
+                         np.array([[a * clip, b * clip] for a, b in kc], np.int32), yi, extra)
+            inf.update_kv_cache = True
+            r = attn(hs, kvs, inf, rope, meta, fused_proj_input=fused)
+            res.append(r if fused else A.FullyParallelAttention.attn_linear_proj_input(*r))
+        outs.append(res)
+    for a, b in zip(*outs):
+        assert a.shape == b.shape and torch.equal(a, b)
+
+
+def test_two_block_stack_matches_reference(doubles):
+    """tests/golden/dit_two_blocks.npz through the product's TransformerLayer modules (kernel doubles): hidden state
+    after both blocks within the per-step latent criterion (asserted at 8e-3), caches as the reference left them."""
+    _, T = doubles
+    from magi_b200.common import EngineConfig, InferenceParams, ModelConfig
+    g = Golden("dit_two_blocks.npz")
+    hidden = g.raw("w0.self_attention.linear_qkv.layer_norm.weight").shape[0]
+    Hq, Hkv = [int(x) for x in g["heads"]]
+    mc = ModelConfig(num_layers=2, hidden_size=hidden, ffn_hidden_size=4 * hidden, num_attention_heads=Hq,
+                     num_query_groups=Hkv)
+    layers = []
+    for l in (0, 1):
+        layer = T.high_precision_promote(T.TransformerLayer(mc, EngineConfig(), layer_number=l))
+        layer.load_state_dict({k[3:]: g.torch(k) for k in g.files if k.startswith(f"w{l}.")}, strict=True)
+        layers.append(layer.eval())
+    clip = int(g["clip"])
+    inf = InferenceParams(max_batch_size=1, max_sequence_length=4 * clip)
+    for tag in ("A", "B", "C"):
+        sp, dn, upd, extra = [int(x) for x in g[f"{tag}.meta"]]
+        meta = _meta(clip, sp, dn, 1, O.core_q_ranges(clip, dn, 1), g.raw(f"{tag}.k_range"), g[f"{tag}.y_index"], extra)
+        inf.update_kv_cache = bool(upd)
+        x = g.torch(f"{tag}.hidden_states")
+        for layer in layers:
+            x = layer(x, g.torch(f"{tag}.condition"), g.torch(f"{tag}.condition_map"),
+                      g.torch(f"{tag}.key_value_states"), g.torch(f"{tag}.rope"), inf, meta)
+        rel, _ = _rel(x, g[f"{tag}.out"])
+        assert rel < 8e-3, (tag, rel)
+    for l in (0, 1):
+        rel, _ = _rel(inf.key_value_memory_dict[l][:3 * clip], g[f"cache{l}"])
+        assert rel < 8e-3, (l, rel)
