@@ -159,3 +159,73 @@ def bias_modulate_add(x, residual, condition_map, gate, post_norm, out=None):
         out.copy_(res)
         return out
     return res
+
+
+# ----------------------------------------------------------------------------------------------- peer-memory emulation
+# The fused context-parallel paths hand the kernels raw device addresses of OTHER ranks' buffers (NVLink peer memory).
+# For the CPU emulation (tests/test_cp_fused_emulated.py: virtual ranks = threads of one process) a "pointer" is
+# (registry id << 40) + byte offset, so the byte arithmetic the module performs on such pointers keeps working.
+_PEER_TENSORS = []
+
+
+def fake_ptr(t: torch.Tensor) -> int:
+    assert t.is_contiguous() and t.dtype == torch.bfloat16
+    _PEER_TENSORS.append(t.view(-1))
+    return len(_PEER_TENSORS) << 40
+
+
+def _peer(ptr: int, shape):
+    """View of the registered buffer behind `ptr` from its byte offset on, shaped (-1, *shape[1:])."""
+    flat = _PEER_TENSORS[(ptr >> 40) - 1]
+    off = (ptr & ((1 << 40) - 1)) // 2
+    row = int(np.prod(shape[1:]))
+    n = (flat.numel() - off) // row
+    return flat[off:off + n * row].view((n,) + tuple(shape[1:]))
+
+
+_plain_qk_norm_rope, _plain_attn_ranges = qk_norm_rope, attn_ranges
+
+
+def qk_norm_rope(x_q, x_k, x_v, num_heads_q, num_heads_kv, ln_q, ln_k, sin, cos, *, peer_q_out=None, peer_kv_out=None,
+                 peer_row_offset=0, peer_heads=None, gather_kv_out=None, gather_geometry=None, **kw):  # noqa: F811
+    """Adds the routing of include/magi_attn.h's peer_* / gather_* fields on top of the plain double."""
+    if peer_q_out is None and peer_kv_out is None and gather_kv_out is None:
+        return _plain_qk_norm_rope(x_q, x_k, x_v, num_heads_q, num_heads_kv, ln_q, ln_k, sin, cos, **kw)
+    if gather_kv_out is not None:
+        # cp_ring_kv: q stays local; K/V row (chunk j, stripe row t) -> row j * chunk_stride + row_offset + t everywhere
+        q, kv = _plain_qk_norm_rope(x_q, x_k, x_v, num_heads_q, num_heads_kv, ln_q, ln_k, sin, cos, **kw)
+        rpc, cstride, roff = gather_geometry
+        r = torch.arange(kv.shape[0])
+        dst = (r // rpc) * cstride + roff + r % rpc
+        for ptr in gather_kv_out:
+            _peer(ptr, (0, num_heads_kv, 2 * HEAD_DIM))[dst] = kv
+        return q, None
+    cp = kw["head_perm_cp"]
+    q, kv = _plain_qk_norm_rope(x_q, x_k, x_v, num_heads_q, num_heads_kv, ln_q, ln_k, sin, cos, **kw)  # send layout
+    rows = (x_q if x_q is not None else x_k).shape[0]
+    for c in range(cp):     # head slice c -> rank c's receive buffer, at this rank's row offset
+        if q is not None:
+            _peer(peer_q_out[c], (0, peer_heads[0], HEAD_DIM))[peer_row_offset:peer_row_offset + rows] = \
+                q[c * rows:(c + 1) * rows]
+        if kv is not None:
+            _peer(peer_kv_out[c], (0, peer_heads[1], 2 * HEAD_DIM))[peer_row_offset:peer_row_offset + rows] = \
+                kv[c * rows:(c + 1) * rows]
+    return None, None
+
+
+def attn_ranges(q, k_new, v_new, q_ranges=None, k_ranges=None, *, peer_out=None, **kw):  # noqa: F811
+    if peer_out is None:
+        return _plain_attn_ranges(q, k_new, v_new, q_ranges, k_ranges, **kw)
+    ptrs, bounds, head_off, heads_total = peer_out
+    kw.pop("out", None)
+    res, _ = _plain_attn_ranges(q, k_new, v_new, q_ranges, k_ranges, **dict(kw, return_lse=False))
+    covered = np.zeros(q.shape[0], dtype=bool)
+    for a, b in q_ranges.numpy().reshape(-1, 2):
+        covered[a:b] = True
+    hq = q.shape[1]
+    for rho, ptr in enumerate(ptrs):    # row g of local head h -> rank rho's output, row g - bounds[rho], head slot
+        lo, hi = int(bounds[rho]), int(bounds[rho + 1])
+        rows = torch.from_numpy(np.nonzero(covered[lo:hi])[0])
+        if len(rows):
+            _peer(ptr, (0, heads_total, HEAD_DIM))[rows, head_off:head_off + hq] = res[lo:hi][rows]
+    return None, None
