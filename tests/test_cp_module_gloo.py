@@ -94,7 +94,31 @@ def test_module_matches_reference_per_rank_outputs(strategy, port):
     _spawn(_golden_worker, 2, (port, strategy))
 
 
-def _sequence_worker(rank, world, port, strategy, errq):
+class _HostOffload:
+    """CPU stand-in for attention.KVOffload (which stages through CUDA streams): same interface, synchronous copies.
+    Lets the module's kv_offload branches (pinned-host cache, staged prefix, write-back) run in the CPU suite."""
+
+    def __init__(self, device):
+        self.stores = self.prefixes = 0
+
+    @classmethod
+    def of(cls, inference_params, device):
+        st = getattr(inference_params, "kv_offload_state", None)
+        if st is None:
+            st = inference_params.kv_offload_state = cls(device)
+        return st
+
+    def prefix(self, layer, cache, rows, next_layer_cache):
+        self.prefixes += 1
+        return cache[:rows].clone()
+
+    def store(self, layer, cache, kv_new, row_offset, rows):
+        if rows > 0:
+            cache[row_offset:row_offset + rows] = kv_new[:rows]
+            self.stores += 1
+
+
+def _sequence_worker(rank, world, port, strategy, errq, offload=False):
     try:
         _setup(rank, world, port)
         from magi_b200 import context_parallel as cpm
@@ -116,6 +140,15 @@ def _sequence_worker(rank, world, port, strategy, errq):
         cp_m = _module(None, strategy, world, Hq, Hkv, hidden)
         cp_m.load_state_dict(ref_m.state_dict())
         inf_ref, inf_cp = InferenceParams(1, 5 * clip), InferenceParams(1, 5 * clip)
+        if offload:
+            # kv_offload (dit_module.py:803-811): the rank's cache lives in host memory and is staged through the
+            # offload manager; the resident single-rank forward stays the checker
+            import magi_b200.attention as A
+            A.KVOffload = _HostOffload
+            torch.cuda.current_device = lambda: 0
+            cp_m.engine_config.kv_offload = True
+            inf_cp.key_value_memory_dict[1] = torch.zeros(5 * clip, cp_m.num_query_groups_per_partition, 256,
+                                                          dtype=torch.bfloat16)
         steps = [  # slice_point, dn, k ranges in chunks, caption tokens, update, fwd_extra, distill_ncc
             (0, 2, [(0, 1), (0, 2)], [20, 31], True, False, False),
             (0, 3, [(0, 1), (0, 2), (1, 3)], [0, 17, 40], True, True, False),
@@ -164,6 +197,9 @@ def _sequence_worker(rank, world, port, strategy, errq):
             e_core = float((core - ref_core.float()).abs().max())
             e_x = float((xo - ref_x.float()).abs().max())
             assert e_core <= bound and e_x <= 1e-2, (strategy, (sp, dn, kc), e_core, e_x)
+        if offload:
+            st = inf_cp.kv_offload_state
+            assert st.stores >= 2 and st.prefixes >= 2, (st.stores, st.prefixes)
         dist.barrier()
     except Exception:
         errq.put(f"rank {rank}:\n{traceback.format_exc()}")
@@ -177,3 +213,13 @@ def _sequence_worker(rank, world, port, strategy, errq):
                                                  ("cp_ulysses", 4, 29655)])   # cp 4 > 2 kv heads: KV-head replication
 def test_module_kv_cache_sequence_matches_single_rank(strategy, world, port):
     _spawn(_sequence_worker, world, (port, strategy))
+
+
+@pytest.mark.parametrize("strategy,port", [("cp_ulysses", 29661), ("cp_shuffle_overlap", 29662)])
+def test_module_kv_offload_branches_match_single_rank(strategy, port):
+    """The same sequence with engine_config.kv_offload: host-resident caches staged through the offload manager."""
+    _spawn(_sequence_worker_offload, 2, (port, strategy))
+
+
+def _sequence_worker_offload(rank, world, port, strategy, errq):
+    _sequence_worker(rank, world, port, strategy, errq, offload=True)
