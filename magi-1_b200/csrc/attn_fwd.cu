@@ -66,6 +66,27 @@ static_assert(kSplit != 1 || 256 * MAGI_SOFTMAX_REGS + 128 * MAGI_AUX_REGS <= 38
               "register pool of the CTA exceeded");
 static_assert(MAGI_SOFTMAX_REGS % 8 == 0 && MAGI_AUX_REGS % 8 == 0, "setmaxnreg takes multiples of 8");
 constexpr int kEmuMod = MAGI_EMU_MOD;
+// Round-2 candidate found by reading the SASS with the single-warp issue model, OFF by default
+// until measured on a B200:
+//   MAGI_STATIC_BARRIERS=1  the mbarriers live in static shared memory, so their addresses are link-time constants. With
+//                           the struct behind the hand-aligned dynamic base, ptxas re-derives that base (S2R
+//                           SR_CgaCtaId / SR_SWINHI, LEA, LOP3, ~15 instructions with long stalls) inside the divergent
+//                           region of EVERY lane-0 mbarrier.arrive of the softmax warps instead of keeping it in a register.
+// Also seen there: ptxas sinks the arrive that publishes the FIRST half of P below 100-200 instructions of the second
+// half's arithmetic (nothing depends on it), so both halves become visible to the MMA issuer 90 instructions apart
+// and P*V starts later than the source suggests. An empty `asm volatile` with "+r" operands on the second half's
+// scores does not move it (it vanishes in PTX; the sinking is ptxas's): that needs a real dependency and a B200 to
+// measure it.
+#ifndef MAGI_STATIC_BARRIERS
+#define MAGI_STATIC_BARRIERS 0
+#endif
+//   MAGI_EARLY_PUBLISH=1    that real dependency: the first publish's mbarrier.arrive returns its state token, and the
+//                           second half's `-m * scale` operand is OR-ed with (token & 0) where the 0 is opaque to the
+//                           compiler (Hq >> 30), one LOP3 per tile. Every FFMA2 of the second half then depends on the
+//                           arrive, so ptxas has to issue it first.
+#ifndef MAGI_EARLY_PUBLISH
+#define MAGI_EARLY_PUBLISH 0
+#endif
 
 #ifdef MAGI_TRACE
 // Debug build only: clock64 stamps of CTA 0 (warp 0 of each softmax warpgroup, and the MMA issuer), first 512 tiles.
@@ -228,7 +249,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;                               // kQStages x 2 tiles
   uint8_t* smem_kv = smem + 2 * kQStages * kTileBytes;  // kStages tiles
+#if MAGI_STATIC_BARRIERS
+  __shared__ Barriers bar_storage;
+  Barriers* bar = &bar_storage;
+#else
   Barriers* bar = reinterpret_cast<Barriers*>(smem + (2 * kQStages + kStages) * kTileBytes);
+#endif
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -286,6 +312,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int pair_bar = 1 + t * 4 + quarter;  // named barrier shared by the two warps that split a row (kSplit == 2)
     uint32_t s_phase = 0, o_phase = 0;
     const float scale_log2 = p.scale_log2;
+#if MAGI_EARLY_PUBLISH
+    const uint32_t opaque_zero = static_cast<uint32_t>(p.Hq) >> 30;   // 0 at run time, unknown at compile time
+#endif
     __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(p.out);
     auto pair_max = [&](float v, int par) -> float {   // max over the two threads that share this row
       if constexpr (kSplit == 1) return v;
@@ -372,12 +401,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         };
         auto local_max = [&]() { return fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd)); };
         // publish the P half whose keys are [64 hg, 64 hg + 64) from local registers sr[64 hl ..]
+#if MAGI_EARLY_PUBLISH
+        uint32_t publish_token = 0;
+#endif
         auto publish = [&](int hl, int hg) {
           MAGI_TMEM_ST32(tS + 64 * hg, sr, 64 * hl);
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
+#if MAGI_EARLY_PUBLISH
+          if (lane == 0) publish_token = static_cast<uint32_t>(mbar_arrive_token(&bar->p_half[t][hg]));
+#else
           if (lane == 0) mbar_arrive(&bar->p_half[t][hg]);
+#endif
         };
 
         float alpha = 1.f;
@@ -425,7 +461,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         publish(0, kSplit == 1 ? 0 : ch);
         if (tr) TRACE(t, j, 4);
         if constexpr (kSplit == 1) {
+#if MAGI_EARLY_PUBLISH
+          const float neg_m = __uint_as_float(__float_as_uint(-m * scale_log2) | (publish_token & opaque_zero));
+#else
           const float neg_m = -m * scale_log2;
+#endif
           half(1, scale2, pack_f2(neg_m, neg_m), false);
           if (tr) TRACE(t, j, 5);
           publish(1, 1);

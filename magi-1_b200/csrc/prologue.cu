@@ -41,13 +41,6 @@ __device__ __forceinline__ uint4 ld_stream(const void* p) {
                : "l"(p));
   return r;
 }
-__device__ __forceinline__ float half_warp_sum(float x) {
-  x += __shfl_xor_sync(0xffffffffu, x, 8);
-  x += __shfl_xor_sync(0xffffffffu, x, 4);
-  x += __shfl_xor_sync(0xffffffffu, x, 2);
-  x += __shfl_xor_sync(0xffffffffu, x, 1);
-  return x;
-}
 
 }  // namespace
 
