@@ -6,6 +6,7 @@ itself", which is what bounds the softmax -> P*V -> next-S chain of attn_fwd_ker
     cuobjdump -sass -fun <mangled kernel> magi-1_b200/csrc/build/attn_fwd.o > /tmp/attn.sass
     python tools/sass_issue_model.py /tmp/attn.sass 0x75b0 0x88c0            # cycles, instruction mix, event times
     python tools/sass_issue_model.py /tmp/attn.sass 0x75b0 0x88c0 --dump     # the listing with its control fields
+    python tools/sass_issue_model.py /tmp/attn.sass --attn-chain             # the softmax chain, located automatically
 
 Model: T advances by each instruction's stall count, waits for the scoreboard slots in its wait mask, and for its pipe
 (fma and alu: one warp instruction per 2 cycles; MUFU: one per 8; per SMSP). Variable-latency results (MUFU, LDTM, ...)
@@ -84,14 +85,43 @@ def simulate(ins, lo, hi, lat_mufu=22, lat_ldtm=30, lat_other=20, events=("SYNCS
     return t, n, mix, waits, marks
 
 
+def attn_chain(path):
+    """Locates the steady-state softmax path of attn_fwd_kernel in a listing (first half with the running-max update,
+    the vote that guards the rare rescale, the publish / second half / publish stretch up to the loop's back edge) and
+    returns the modelled single-warp cycles of each stretch."""
+    ins = parse(path)
+    texts = [t for _, t, _ in ins]
+    addr = [a for a, _, _ in ins]
+    v = next(i for i, t in enumerate(texts) if t.startswith("VOTE.ANY P6"))
+    b0 = max(i for i in range(v) if "BRA" in texts[i] and "BRA.DIV" not in texts[i]) + 1
+    g = next(i for i in range(v, len(texts)) if texts[i].startswith("@!P6 BRA"))
+    z = int(texts[g].split()[-1], 16)
+    arrives = [i for i, t in enumerate(texts) if "SYNCS.ARRIVE.TRANS64.A1T0" in t and addr[i] > z]
+    back = next(i for i in range(arrives[1], len(texts)) if texts[i].startswith("@P0 BRA"))
+    out = {}
+    for name, lo, hi in (("first half + max", addr[b0], addr[v]), ("vote + moves", addr[v], addr[g] + 16),
+                         ("publish, second half, publish", z, addr[back] + 16)):
+        t, n, _, _, marks = simulate(ins, lo, hi)
+        out[name] = (t, n, [m for m in marks if "ARRIVE" in m[1]])
+    return out
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("sass")
-    ap.add_argument("lo", type=lambda x: int(x, 16))
-    ap.add_argument("hi", type=lambda x: int(x, 16))
+    ap.add_argument("lo", type=lambda x: int(x, 16), nargs="?")
+    ap.add_argument("hi", type=lambda x: int(x, 16), nargs="?")
+    ap.add_argument("--attn-chain", action="store_true",
+                    help="locate and model the steady-state softmax chain of attn_fwd_kernel (no address range needed)")
     ap.add_argument("--dump", action="store_true")
     ap.add_argument("--lat-mufu", type=int, default=22)
     a = ap.parse_args()
+    if a.attn_chain:
+        parts = attn_chain(a.sass)
+        print(f"{a.sass}: single-warp cycles per 128-key tile = {sum(v[0] for v in parts.values())}")
+        for name, (t, n, marks) in parts.items():
+            print(f"  {name:32s} {t:5d} cycles, {n:4d} instructions" + "".join(f"; arrive at {m[0]}" for m in marks))
+        raise SystemExit(0)
     ins = parse(a.sass)
     if a.dump:
         for addr, text, word in ins:
@@ -109,3 +139,4 @@ if __name__ == "__main__":
     print("exposed waits:", dict(waits.most_common(6)))
     for when, what in marks:
         print(f"  t={when:5d}  {what}")
+
