@@ -57,6 +57,10 @@ typedef struct magi_view {
  * new tokens of this forward; either may be empty (tokens == 0). Query ranges must be disjoint (the reference passes
  * disable_fwd_atomic_reduction=True, dit_module.py:1042). Rows covered by no range are left untouched.
  * A range with an empty key interval yields out = 0, lse = -inf.
+ * K/V are read in tiles of 128 rows: a tile may extend past the end of a key range (those scores are masked) and past
+ * the end of a VIEW (rows beyond `tokens` are zero-filled by the TMA unit, never read). Rows that lie inside a view
+ * but outside every key range must therefore hold finite values - a masked probability of exactly 0 times a NaN / Inf
+ * in V would still poison the accumulator (pass `cache[:prefix_rows]`, not the whole torch.empty allocation).
  *
  * Exactly one of {q_ranges,k_ranges} / {cu_seqlens_q,cu_seqlens_k} must be non-NULL; all are int32 DEVICE pointers
  * ((n,2) row-major, resp. n+1 entries). lse is (total_q, Hq) fp32 natural-log, may be NULL.
