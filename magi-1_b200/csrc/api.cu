@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -36,6 +37,10 @@ int fail(const char* fmt, ...) {
     if (e__ != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(e__));    \
   } while (0)
 
+#ifndef MAGI_DEFAULT_PAIR
+#define MAGI_DEFAULT_PAIR 0   // which attention kernel runs when MAGI_ATTN_KERNEL is unset
+#endif
+
 #define MAGI_STR_(x) #x
 #define MAGI_STR(x) MAGI_STR_(x)
 
@@ -60,7 +65,7 @@ EncodeTiledFn get_encode_fn() {
 
 // (tokens, heads, 128) bf16 view -> 3-D tensor map {128, heads, tokens}, box {64, 1, 128}, 128B swizzle.
 // Rows past `tokens` are zero-filled by the TMA unit, which is what makes ragged range edges safe.
-int make_view_map(CUtensorMap* m, const magi_view& v, int heads, const char* what) {
+int make_view_map(CUtensorMap* m, const magi_view& v, int heads, const char* what, int box_rows = 128) {
   EncodeTiledFn enc = get_encode_fn();
   MAGI_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
   const bool empty = v.tokens <= 0 || v.ptr == nullptr;
@@ -71,7 +76,7 @@ int make_view_map(CUtensorMap* m, const magi_view& v, int heads, const char* wha
   MAGI_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "%s: pointer must be 16-byte aligned", what);
   MAGI_CHECK(v.head_stride % 8 == 0 && v.token_stride % 8 == 0, "%s: strides must be multiples of 8 elements", what);
   MAGI_CHECK(v.head_stride >= 128, "%s: head stride < 128", what);
-  cuuint32_t box[3] = {64, 1, 128};
+  cuuint32_t box[3] = {64, 1, (cuuint32_t)box_rows};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -148,14 +153,25 @@ int magi_attn_fwd(const magi_attn_args* a, void* stream_) {
              "workspace too small: need %zu bytes", magi_attn_workspace_bytes(a->n_ranges));
   MAGI_CHECK((reinterpret_cast<uintptr_t>(a->workspace) & 15) == 0, "workspace must be 16-byte aligned");
 
+  // kernel choice: the CTA-pair kernel (attn_pair.cu) unless MAGI_ATTN_KERNEL=single (attn_fwd.cu) is set or fewer
+  // than two SMs are asked for
+  static const int kernel_env = [] {
+    const char* e = getenv("MAGI_ATTN_KERNEL");
+    return (e != nullptr && strcmp(e, "single") == 0) ? 1 : (e != nullptr && strcmp(e, "pair") == 0) ? 2 : 0;
+  }();
+  int sms = a->num_sms;
+  if (sms <= 0) { if (int r2 = device_sm_count(&sms)) return r2; }
+  const bool use_pair = (kernel_env == 2 || (kernel_env == 0 && MAGI_DEFAULT_PAIR)) && sms >= 2;
+  const int k_box = use_pair ? 64 : 128;   // a CTA of a pair stages its 64 keys of every K tile
+
   CUtensorMap tm_q, tm_ka, tm_va, tm_kb, tm_vb;
   int rc = make_view_map(&tm_q, a->q, a->num_heads_q, "q");
   if (rc) return rc == 2 ? fail("q is empty") : rc;
-  int rka = make_view_map(&tm_ka, a->k_a, a->num_heads_kv, "k_a");
+  int rka = make_view_map(&tm_ka, a->k_a, a->num_heads_kv, "k_a", k_box);
   if (rka == 1) return 1;
   int rva = make_view_map(&tm_va, a->v_a, a->num_heads_kv, "v_a");
   if (rva == 1) return 1;
-  int rkb = make_view_map(&tm_kb, a->k_b, a->num_heads_kv, "k_b");
+  int rkb = make_view_map(&tm_kb, a->k_b, a->num_heads_kv, "k_b", k_box);
   if (rkb == 1) return 1;
   int rvb = make_view_map(&tm_vb, a->v_b, a->num_heads_kv, "v_b");
   if (rvb == 1) return 1;
@@ -205,10 +221,9 @@ int magi_attn_fwd(const magi_attn_args* a, void* stream_) {
     p.peer_bounds[a->num_peers] = a->peer_row_bounds[a->num_peers];
   }
 
-  int sms = a->num_sms;
-  if (sms <= 0) { if (int r2 = device_sm_count(&sms)) return r2; }
   const CUtensorMap maps[5] = {tm_q, tm_ka, tm_va, tm_kb, tm_vb};
-  MAGI_CUDA(magi::attn_fwd_launch(maps, p, sms, stream));
+  if (use_pair) MAGI_CUDA(magi::attn_pair_launch(maps, p, sms, stream));
+  else MAGI_CUDA(magi::attn_fwd_launch(maps, p, sms, stream));
   g_launches++;
   return 0;
 }

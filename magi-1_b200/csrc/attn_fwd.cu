@@ -66,8 +66,7 @@ static_assert(kSplit != 1 || 256 * MAGI_SOFTMAX_REGS + 128 * MAGI_AUX_REGS <= 38
               "register pool of the CTA exceeded");
 static_assert(MAGI_SOFTMAX_REGS % 8 == 0 && MAGI_AUX_REGS % 8 == 0, "setmaxnreg takes multiples of 8");
 constexpr int kEmuMod = MAGI_EMU_MOD;
-// Round-2 candidate found by reading the SASS with the single-warp issue model, OFF by default
-// until measured on a B200:
+// Found by reading the SASS with the single-warp issue model, measured in round 2:
 //   MAGI_STATIC_BARRIERS=1  the mbarriers live in static shared memory, so their addresses are link-time constants. With
 //                           the struct behind the hand-aligned dynamic base, ptxas re-derives that base (S2R
 //                           SR_CgaCtaId / SR_SWINHI, LEA, LOP3, ~15 instructions with long stalls) inside the divergent
@@ -78,7 +77,7 @@ constexpr int kEmuMod = MAGI_EMU_MOD;
 // scores does not move it (it vanishes in PTX; the sinking is ptxas's): that needs a real dependency and a B200 to
 // measure it.
 #ifndef MAGI_STATIC_BARRIERS
-#define MAGI_STATIC_BARRIERS 0
+#define MAGI_STATIC_BARRIERS 1   // measured (profiles/r02_variants.log): 1180 vs 1135 TFLOP/s sustained, 1373 vs 1312 burst
 #endif
 //   MAGI_EARLY_PUBLISH=1    that real dependency: the first publish's mbarrier.arrive returns its state token, and the
 //                           second half's `-m * scale` operand is OR-ed with (token & 0) where the 0 is opaque to the
@@ -87,6 +86,17 @@ constexpr int kEmuMod = MAGI_EMU_MOD;
 #ifndef MAGI_EARLY_PUBLISH
 #define MAGI_EARLY_PUBLISH 0
 #endif
+//   MAGI_GUARD_BY_SUM=1     steady-state tiles (j > 0) no longer track the row max over all 128 columns. The running max
+//                           m is only a REFERENCE POINT for the exponentials (softmax is shift-invariant and fp32 / bf16
+//                           share an 8-bit exponent), so all that has to be guaranteed before a half of P is published
+//                           is that no 2^x overflowed: for the first half that is read off its row sum (already
+//                           computed: sum >= max, and an inf / NaN fails the comparison too), for the second half off
+//                           a max over ITS 64 columns only (32 FMNMX3 instead of 108 FMNMX3 / FMNMX per tile). Either
+//                           guard failing takes the same exact path as before (reload S, true tile max, rescale O).
+#ifndef MAGI_GUARD_BY_SUM
+#define MAGI_GUARD_BY_SUM 0
+#endif
+constexpr float kSumGuard = 32768.f;      // 2^15: a 64-column half of P summing to more than this re-references the row
 
 #ifdef MAGI_TRACE
 // Debug build only: clock64 stamps of CTA 0 (warp 0 of each softmax warpgroup, and the MMA issuer), first 512 tiles.
@@ -367,23 +377,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         // computed optimistically against the running max m while the chains run on the ALU pipe next to it; only
         // if some row's max grew by more than 2^8 (rare) is the tile redone with the new max.
         float mxa, mxb, mxc, mxd;
-        auto max_step = [&](int k) {   // k = 0 .. kCols/4 - 1: consumes columns 4k .. 4k+3
+        auto max_step = [&](int k, bool first = false) {   // k = 0 .. kCols/4 - 1: consumes columns 4k .. 4k+3
           const float a0 = __uint_as_float(sr[4 * k]), a1 = __uint_as_float(sr[4 * k + 1]);
           const float a2 = __uint_as_float(sr[4 * k + 2]), a3 = __uint_as_float(sr[4 * k + 3]);
-          if (k == 0) { mxa = fmaxf(a0, a1); mxb = fmaxf(a2, a3); mxc = mxa; mxd = mxb; }
+          if (k == 0 || first) { mxa = fmaxf(a0, a1); mxb = fmaxf(a2, a3); mxc = mxa; mxd = mxb; }
           else if (k & 1) { mxc = fmax3(mxc, a0, a1); mxd = fmax3(mxd, a2, a3); }
           else { mxa = fmax3(mxa, a0, a1); mxb = fmax3(mxb, a2, a3); }
         };
         uint64_t sum_a, sum_b;
         // local columns [64 hl, 64 hl + 64) -> packed bf16 P in sr[64 hl .. 64 hl + 32) (in place), row sums accumulated
-        auto half = [&](const int hl, const uint64_t scale2, const uint64_t negm2, const bool with_max) {
+        // with_max: 0 = no max chains, 1 = all kCols columns are covered by max steps during the first local half,
+        //           2 = only the columns of the SECOND half are (MAGI_GUARD_BY_SUM)
+        auto half = [&](const int hl, const uint64_t scale2, const uint64_t negm2, const int with_max) {
 #pragma unroll
           for (int c = 64 * hl; c < 64 * hl + 64; c += 2) {
             const int pair = c >> 1;
-            // all kCols columns are covered by max steps during the first local half
-            if (with_max) {
+            if (with_max == 1) {
               if constexpr (kSplit == 1) max_step(pair);
               else if ((pair & 1) == 0) max_step(pair >> 1);
+            } else if (with_max == 2) {
+              if ((pair & 1) == 0) max_step(16 + (pair >> 1), pair == 0);
             }
             const uint64_t x2 = ffma2(pack_f2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), scale2, negm2);
             float x0, x1, p0, p1;
@@ -427,25 +440,44 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           m = pair_max(local_max(), j & 1);
           if (tr) TRACE(t, j, 3);
           const float neg_m = -m * scale_log2;
-          half(0, scale2, pack_f2(neg_m, neg_m), false);
+          half(0, scale2, pack_f2(neg_m, neg_m), 0);
         } else {
           if (tr) TRACE(t, j, 3);
           const float neg_m = -m * scale_log2;
-          half(0, scale2, pack_f2(neg_m, neg_m), true);
+#if MAGI_GUARD_BY_SUM
+          static_assert(kSplit == 1, "MAGI_GUARD_BY_SUM is written for one thread per row");
+          half(0, scale2, pack_f2(neg_m, neg_m), 2);
+          float mx = local_max();                    // max over the SECOND half's columns only
+          {
+            float g0, g1;
+            unpack_f2(fadd2(sum_a, sum_b), g0, g1);
+            // first half: guarded by its row sum (negated comparison: inf / NaN take the exact path too)
+            need = !(g0 + g1 <= kSumGuard) || (mx - m) * scale_log2 > kRescaleThreshold;
+          }
+#else
+          half(0, scale2, pack_f2(neg_m, neg_m), 1);
           const float mx = pair_max(local_max(), j & 1);
           need = (mx - m) * scale_log2 > kRescaleThreshold;
+#endif
           if (__any_sync(0xffffffffu, need)) {
             // rare: redo the first half against the new max and bring O back into range before P*V accumulates.
             // Both threads of a row see the same mx, hence take the same decision.
+            load_s();
+#if MAGI_GUARD_BY_SUM
+            // exact tile max from the reloaded scores (the first half of sr was overwritten by P)
+#pragma unroll
+            for (int k = 0; k < kCols / 4; ++k) max_step(k);
+            mx = local_max();
+            need = mx > m;
+#endif
             if (need) {
               alpha = ex2_approx((m - mx) * scale_log2);
               m = mx;
             }
-            load_s();
             sum_a = pack_f2(0.f, 0.f);
             sum_b = sum_a;
             const float neg_m2 = -m * scale_log2;
-            half(0, scale2, pack_f2(neg_m2, neg_m2), false);
+            half(0, scale2, pack_f2(neg_m2, neg_m2), 0);
 #pragma unroll 1
             for (int c = 0; c < kCols; c += 32) {
               uint32_t orr[32];
@@ -466,7 +498,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #else
           const float neg_m = -m * scale_log2;
 #endif
-          half(1, scale2, pack_f2(neg_m, neg_m), false);
+          half(1, scale2, pack_f2(neg_m, neg_m), 0);
           if (tr) TRACE(t, j, 5);
           publish(1, 1);
         }
@@ -715,8 +747,15 @@ cudaError_t attn_setup_launch(const int* q_ranges, const int* k_ranges, const in
 }
 
 cudaError_t attn_fwd_launch(const CUtensorMap* maps, const AttnKernelParams& p, int num_ctas, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  static bool attr_set[64] = {false};   // per device; the attribute is sticky, so set it once instead of per call
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
+  if (dev >= 64 || !attr_set[dev]) {
+    e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    if (dev < 64) attr_set[dev] = true;
+  }
   attn_fwd_kernel<<<num_ctas, kThreads, kSmemBytes, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
   return cudaGetLastError();
 }

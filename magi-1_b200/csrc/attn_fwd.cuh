@@ -32,4 +32,8 @@ cudaError_t attn_setup_launch(const int* q_ranges, const int* k_ranges, const in
 // maps: {q, k_a, v_a, k_b, v_b}
 cudaError_t attn_fwd_launch(const CUtensorMap* maps, const AttnKernelParams& p, int num_ctas, cudaStream_t stream);
 
+// CTA-pair kernel (attn_pair.cu): maps {q (128-row box), k_a (64-row box), v_a (128), k_b (64), v_b (128)}; num_ctas is
+// rounded down to an even number (one cluster of two CTAs per pair of SMs). Same params, work list and results.
+cudaError_t attn_pair_launch(const CUtensorMap* maps, const AttnKernelParams& p, int num_ctas, cudaStream_t stream);
+
 }  // namespace magi

@@ -6,7 +6,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CASES = ["g_ragged_ranges", "h_two_segments", "j_many_items", "p_bench_cfg2", "q_bench_single", "s_bench_cross"]
+CASES = ["g_ragged_ranges", "h_two_segments", "j_many_items", "p_bench_cfg2", "p2_bench_cfg2_sustained", "s_bench_cross"]
 
 if __name__ == "__main__":
     libs = sorted(glob.glob(os.path.join(ROOT, "magi-1_b200", "variants", "lib_*.so")))

@@ -178,6 +178,34 @@ def p_bench_cfg2():
 
 
 @case
+def p2_bench_cfg2_sustained():
+    """the cfg2 launch back to back for ~2.5 s: the power-capped (in-step) regime instead of burst clocks."""
+    import torch
+    import magi_b200.functional as F
+    dev = "cuda"
+    clip, Hq, Hkv = 9360, 24, 8
+    q = torch.randn(4 * clip, Hq, 128, device=dev, dtype=torch.bfloat16)
+    kv = torch.randn(4 * clip, Hkv, 256, device=dev, dtype=torch.bfloat16)
+    qr = torch.tensor([[i * clip, (i + 1) * clip] for i in range(4)], dtype=torch.int32, device=dev)
+    kr = torch.tensor([[0, (i + 1) * clip] for i in range(4)], dtype=torch.int32, device=dev)
+    out = torch.empty_like(q)
+    flops = 4 * 128 * Hq * clip * clip * 10
+    fn = lambda: F.attn_ranges(q, kv[..., :128], kv[..., 128:], qr, kr, out=out, return_lse=False)
+    for _ in range(120):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n = 160
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    print(f"[cfg2 sustained x{n}] {ms:.3f} ms/launch -> {flops/ms/1e9:.1f} TFLOP/s", flush=True)
+    return True
+
+
+@case
 def q_bench_single():
     bench_attn("1 range 9360x37440, 24/8 heads", 9360, 1, [(0, 4)], 24, 8)
     return True
@@ -323,7 +351,11 @@ def main():
     names = sys.argv[1:] or sorted(CASES)
     if len(names) == 1 and names[0].startswith("--run="):
         n = names[0][6:]
-        ok = CASES[n]()
+        try:
+            ok = CASES[n]()
+        except Exception as e:  # a trap / launch failure: one line, not a traceback
+            print(f"[{n}] FAIL: {type(e).__name__}: {str(e).splitlines()[0][:200]}", flush=True)
+            ok = False
         sys.exit(0 if ok else 1)
     results = {}
     for n in names:
