@@ -55,11 +55,12 @@ def attn_flops(w):
     return self_f, cross_f
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE self-attention launch of the named workload, from the committed
-# `ncu --set full` capture (profiles/r01_ncu_final2_raw.csv: 623.43 MB read + 200.83 MB written). The algorithmic
-# minimum (q + out + packed kv once) is 230 + 230 + 153 = 613 MB: K/V re-reads by the 3 query heads of a GQA group and by
-# the 37 query tiles of a chunk are served by L2.
-NCU_TRAFFIC_BYTES = {"cfg2": 824263168}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE self-attention launch of the named workload: NOT measured by the
+# run that prints it (a number taken under a profiler is never a bench value) but read off the committed `ncu --set
+# full` capture named next to it. The algorithmic minimum (q + out + packed kv once) is 230 + 230 + 153 = 613 MB: K/V
+# re-reads by the 3 query heads of a GQA group and by the 37 query tiles of a chunk are served by L2.
+NCU_TRAFFIC = {"cfg2": (824263168, "ncu capture profiles/r01_ncu_final2_raw.csv (attn_fwd_kernel: 623.43 MB read + "
+                                   "200.83 MB written per launch), not re-measured by this run")}
 
 
 def load_peaks():
@@ -122,9 +123,11 @@ class HotPath:
     """Synthetic inputs of one denoise forward's attention hot path, resident in HBM, and the per-layer launch
     sequence through the public API (magi_b200.functional -> C-ABI)."""
 
-    def __init__(self, w, device, cp=1, rank=0, seed=1234, fused=True, ring=False, ring_fused=True):
+    def __init__(self, w, device, cp=1, rank=0, seed=1234, fused=True, ring=False, ring_fused=True, layers=None):
         import torch
         import magi_b200.functional as F
+        if layers is not None:
+            w = dict(w, layers=layers)
         self.torch, self.F, self.w, self.cp, self.rank, self.dev = torch, F, w, cp, rank, device
         self.ring = ring and cp > 1
         self.ring_fused = self.ring and ring_fused
@@ -144,19 +147,27 @@ class HotPath:
             self.split = [self.S]
         self.S_loc = self.split[rank]
         off = sum(self.split[:rank])
-        g = torch.Generator(device=device).manual_seed(seed + rank)
+        g = torch.Generator(device=device).manual_seed(seed + rank)     # this rank's token shard
+        gw = torch.Generator(device=device).manual_seed(seed + 7919)    # replicated tensors: same on every rank
 
-        def rnd(*shape, scale=1.0, dtype=torch.bfloat16):
-            return (torch.randn(*shape, device=device, generator=g) * scale).to(dtype)
+        def rnd(*shape, scale=1.0, dtype=torch.bfloat16, gen=None):
+            return (torch.randn(*shape, device=device, generator=gen or g) * scale).to(dtype)
 
         # projection outputs of the LOCAL token shard (all heads) - the inputs of the hot path
         self.inputs = dict(xq=rnd(self.S_loc, Hq * 128), qx=rnd(self.S_loc, Hq * 128), xk=rnd(self.S_loc, Hkv * 128),
-                           xv=rnd(self.S_loc, Hkv * 128), text_kv=rnd(sum(w["text"]), Hkv, 256))
+                           xv=rnd(self.S_loc, Hkv * 128), text_kv=rnd(sum(w["text"]), Hkv, 256, gen=gw))
         ang = torch.rand(self.S_loc, 48, device=device, generator=g) * 6.2831853
         self.inputs["sin"], self.inputs["cos"] = torch.sin(ang), torch.cos(ang)
-        self.ln = {k: (rnd(128, scale=0.02, dtype=torch.float32), rnd(128, scale=0.02, dtype=torch.float32))
+        self.ln = {k: (rnd(128, scale=0.02, dtype=torch.float32, gen=gw), rnd(128, scale=0.02, dtype=torch.float32, gen=gw))
                    for k in ("q", "k")}
-        self.lnx = {k: (rnd(128, scale=0.02), rnd(128, scale=0.02)) for k in ("q", "k")}
+        self.lnx = {k: (rnd(128, scale=0.02, gen=gw), rnd(128, scale=0.02, gen=gw)) for k in ("q", "k")}
+        # global (single-GPU order) row index of every local row: contiguous shard, or (chunk, stripe row) for ring-KV
+        if self.ring:
+            nr, so = self.ring_sizes[rank], sum(self.ring_sizes[:rank])
+            self.global_rows = torch.cat([torch.arange(i * clip + so, i * clip + so + nr, device=device)
+                                          for i in range(n_chunks)])
+        else:
+            self.global_rows = torch.arange(off, off + self.S_loc, device=device)
         i32 = lambda a: torch.tensor(a, dtype=torch.int32, device=device)
         sp = w["slice_point"]
         n = len(w["k_chunks"])
@@ -377,11 +388,18 @@ class HotPath:
 
     ulysses_overlap_degree = 1
 
+    def layer_fn(self):
+        return (self.layer_cp_ring_fused if self.ring_fused else self.layer_cp_ring if self.ring else
+                self.layer_cp_fused if self.fused else self.layer_cp) if self.cp > 1 else self.layer
+
     def step(self, timed_events=False):
-        fn = (self.layer_cp_ring_fused if self.ring_fused else self.layer_cp_ring if self.ring else self.layer_cp_fused if self.fused else self.layer_cp) \
-            if self.cp > 1 else self.layer
+        fn = self.layer_fn()
         for l in range(self.w["layers"]):
             fn(l, timed_events)
+
+    def mode(self):
+        return "none" if self.cp == 1 else ("ring-fused" if self.ring_fused else "ring-nccl" if self.ring else
+                                            "ulysses-fused" if self.fused else "ulysses-nccl")
 
 
 # ----------------------------------------------------------------------------------------------- whole DiT blocks
@@ -545,6 +563,35 @@ def cpu_baseline_sample(w, budget_s=20.0):
                           f"torch fp32 CPU port of the reference's flash_attn_func loop (oracle/torch_cpu_path.py)"}
 
 
+def parallelism_desc(world, mode, overlap=1, multicast=False):
+    if world == 1:
+        return "none"
+    return {
+        "ulysses-fused": f"cp_ulysses{world}, all-to-alls fused into the kernels' stores (NVLink peer memory via symmetric "
+                         f"memory, no NCCL on the data path), 2 device barriers per layer",
+        "ulysses-nccl": f"cp_ulysses{world}, NCCL all_to_all_single (overlap_degree {overlap})",
+        "ring-fused": f"cp_ring_kv{world} (every chunk striped across the ranks), K/V all-gather fused into the prologue's "
+                      f"stores ({'NVSwitch multicast (multimem.st)' if multicast else 'NVLink peer stores'}) into the "
+                      f"replicated cache slot, 1 device barrier per layer",
+        "ring-nccl": f"cp_ring_kv{world}, K/V blocks round the ring by NCCL send/recv, log-sum-exp merge, replicated cache",
+    }[mode]
+
+
+def static_config(args, w, world):
+    """The `config` object: names the workload. Identical in both arms (ours / --impl reference); everything measured
+    lives in `roofline`, `e2e`, `clocks`, `cpu_baseline`."""
+    self_f, cross_f = attn_flops(w)
+    mode = "none" if world == 1 else {"fused": "ulysses-fused", "nccl": "ulysses-nccl", "ring": "ring-fused",
+                                      "ring-nccl": "ring-nccl"}[args.cp_mode]
+    return {"workload": w["desc"], "name": args.workload,
+            "parallelism": parallelism_desc(world, mode, args.overlap_degree, True),
+            "step": "attention hot path of one denoise forward over all layers: fused LN+RoPE prologue with KV-cache "
+                    "append, range-masked self-attention, text cross-attention",
+            "tokens_q": w["clip"] * len(w["k_chunks"]), "layers": w["layers"],
+            "flops_per_step": (self_f + cross_f) * w["layers"], "self_attn_flops_per_layer": self_f,
+            "l2": "inputs larger than L2 (>= 600 MB of projection outputs re-read per layer)"}
+
+
 def run_reference(args, w):
     """--impl reference: the reference's CPU implementation of the path on the host cores, same metric/config: the
     torch fp32 port of its attention fallback loop (oracle/torch_cpu_path.py; the reference is Python whose CUDA-only
@@ -563,15 +610,176 @@ def run_reference(args, w):
     tf = sum(tfs) / len(tfs)
     step_flops = (self_f + cross_f) * w["layers"]
     info["value"] = round(tf, 4)
+    info["sample"] += "; ms_per_step is extrapolated from the timed sample to the whole step"
     line = {"impl": "reference", "metric": "chunk_causal_attn_tflops", "value": round(tf, 4), "unit": "TFLOP/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(step_flops / (tf * 1e12) * 1e3, 1), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["desc"], "note": "ms_per_step extrapolated from the timed sample: "
-                       "each step times a bounded sample of the workload (see cpu_baseline.sample)"},
+            "config": static_config(args, w, args.gpus),
             "cpu_baseline": info, "e2e": {"value": round(tf, 4), "unit": "TFLOP/s", "h2d_bytes_per_step": 0,
                                           "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- measurement legs
+class Ctx:
+    """Rank / device plumbing shared by the legs."""
+
+    def __init__(self, torch, dist, dev, world, rank, local):
+        self.torch, self.dist, self.dev, self.world, self.rank, self.local = torch, dist, dev, world, rank, local
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([v], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def timed_leg(cx, hp, steps, warm, sample_clocks=True):
+    """W warm-up steps, then exactly `steps` steps between barrier + synchronize, CUDA events, max over ranks."""
+    from magi_b200 import _lib
+    torch = cx.torch
+    for _ in range(warm):
+        hp.step()
+    cx.barrier()
+    hp.attn_events = []
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(cx.local) as clk:
+        e0.record()
+        for _ in range(steps):
+            hp.step(timed_events=True)
+        e1.record()
+        cx.barrier()
+    launches = _lib.launch_count() - l0
+    ms_total = cx.max_over_ranks(e0.elapsed_time(e1))
+    attn_ms = [a.elapsed_time(b) for a, b in hp.attn_events]
+    return dict(ms_step=ms_total / steps, ms_total=ms_total, attn_ms=attn_ms, launches=int(launches),
+                clocks=clk.summary())
+
+
+def e2e_leg(cx, hp, steps):
+    """End to end through the public API with HOST buffers: every step copies all of its inputs in from pinned host
+    memory and all of its results out, inside the timed region. Inputs and outputs are double-buffered on one copy
+    stream at every N: the H2D copy of step t + 1 and the D2H read of step t run under the kernels of the
+    neighbouring step. Under context parallelism the attention output lives in the (single) symmetric-memory
+    receive buffer, so it is first copied to the step's private output set on the compute stream."""
+    torch = cx.torch
+    host_in = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in hp.inputs.items()}
+    host_out = [torch.empty(hp.core_out.numel(), dtype=torch.bfloat16, pin_memory=True),
+                torch.empty(hp.x_out.numel(), dtype=torch.bfloat16, pin_memory=True)]
+    copy = torch.cuda.Stream()
+    in_sets = [hp.inputs, {k: torch.empty_like(v) for k, v in hp.inputs.items()}]
+    out_sets = [(torch.empty_like(hp.core_out), torch.empty_like(hp.x_out)) for _ in range(2)]
+    if cx.world == 1:
+        out_sets[0] = (hp.core_out, hp.x_out)
+    h2d_done, compute_done, d2h_done = [None, None], [None, None], [None, None]
+
+    def issue_h2d(i):
+        with torch.cuda.stream(copy):
+            if compute_done[i] is not None:
+                copy.wait_event(compute_done[i])      # set i was last read by the step before last
+            for k, v in host_in.items():
+                in_sets[i][k].copy_(v, non_blocking=True)
+            h2d_done[i] = torch.cuda.Event()
+            h2d_done[i].record(copy)
+
+    def e2e_step(t):
+        i = t & 1
+        cur = torch.cuda.current_stream()
+        cur.wait_event(h2d_done[i])
+        if d2h_done[i] is not None:
+            cur.wait_event(d2h_done[i])               # output set i has been read back
+        hp.inputs = in_sets[i]
+        if cx.world == 1:
+            hp.core_out, hp.x_out = out_sets[i]       # the kernels write the step's output set directly
+            hp.step()
+        else:
+            hp.x_out = out_sets[i][1]
+            hp.step()
+            out_sets[i][0].copy_(hp.core_out)         # out of the shared receive buffer (device copy, compute stream)
+        compute_done[i] = torch.cuda.Event()
+        compute_done[i].record(cur)
+        issue_h2d(i ^ 1)
+        with torch.cuda.stream(copy):
+            copy.wait_event(compute_done[i])
+            host_out[0].copy_(out_sets[i][0].reshape(-1), non_blocking=True)
+            host_out[1].copy_(out_sets[i][1].reshape(-1), non_blocking=True)
+            d2h_done[i] = torch.cuda.Event()
+            d2h_done[i].record(copy)
+
+    def e2e_run(n):
+        copy.wait_stream(torch.cuda.current_stream())   # the first H2D starts inside the timed region
+        issue_h2d(0)
+        for t in range(n):
+            e2e_step(t)
+        torch.cuda.current_stream().wait_stream(copy)   # ... and the last D2H ends inside it
+
+    e2e_run(2)
+    cx.barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    e2e_run(steps)
+    s1.record()
+    cx.barrier()
+    hp.inputs = in_sets[0]
+    return cx.max_over_ranks(s0.elapsed_time(s1)) / steps
+
+
+def cp_parity_leg(cx, hp, args_w):
+    """Multi-GPU correctness under the driver's eyes: ONE layer of the context-parallel path that was just timed vs
+    the same layer through the single-GPU path (cp = 1, same kernels) on the all-gathered inputs, every rank checking
+    its own rows of the self- and cross-attention outputs; max |diff| over all ranks. The fused paths and NCCL
+    Ulysses keep every row's key order, so the bound is 0.0 (bit-identical); the NCCL ring re-associates the softmax
+    over key blocks (one extra bf16 rounding per log-sum-exp merge): bound 2.5e-2."""
+    torch, dist, w = cx.torch, cx.dist, hp.w
+    mode = hp.mode()
+    if w["slice_point"] != 0:
+        return {"mode": mode, "skipped": "state with a cache prefix: the synthetic prefix differs per rank"}
+    S = hp.S
+    rows = hp.global_rows
+    counts = torch.tensor([rows.numel()], device=cx.dev)
+    all_counts = [torch.zeros_like(counts) for _ in range(cx.world)]
+    dist.all_gather(all_counts, counts)
+    nmax = max(int(c.item()) for c in all_counts)
+    pad_rows = torch.full((nmax,), -1, device=cx.dev, dtype=rows.dtype)
+    pad_rows[:rows.numel()] = rows
+    all_rows = [torch.empty_like(pad_rows) for _ in range(cx.world)]
+    dist.all_gather(all_rows, pad_rows)
+    ref = HotPath(dict(w), cx.dev, cp=1, rank=0, layers=1)
+    ref.ln, ref.lnx = hp.ln, hp.lnx
+    for k, v in hp.inputs.items():
+        if k == "text_kv":
+            ref.inputs[k] = v
+            continue
+        buf = torch.zeros((nmax,) + tuple(v.shape[1:]), dtype=v.dtype, device=cx.dev)
+        buf[:v.shape[0]] = v
+        parts = [torch.empty_like(buf) for _ in range(cx.world)]
+        dist.all_gather(parts, buf)
+        full = torch.empty((S,) + tuple(v.shape[1:]), dtype=v.dtype, device=cx.dev)
+        for r_, part in zip(all_rows, parts):
+            keep = r_ >= 0
+            full[r_[keep]] = part[keep]
+        ref.inputs[k] = full
+    ref.layer(0)
+    hp.layer_fn()(0)
+    cx.torch.cuda.synchronize()
+    d_self = (hp.core_out.float() - ref.core_out[rows].float()).abs().max().item()
+    d_cross = (hp.x_out.float() - ref.x_out[rows].float()).abs().max().item()
+    finite = bool(torch.isfinite(hp.core_out.float()).all()) and bool(torch.isfinite(hp.x_out.float()).all())
+    max_abs = cx.max_over_ranks(max(d_self, d_cross) if finite else float("inf"))
+    bound = 2.5e-2 if mode == "ring-nccl" else 0.0
+    del ref
+    torch.cuda.empty_cache()
+    return {"mode": mode, "max_abs": max_abs, "bound": bound, "ok": bool(max_abs <= bound), "rows": S,
+            "what": "one layer (self- and cross-attention outputs) of the timed context-parallel path vs the "
+                    "single-GPU path on the gathered inputs, max |diff| over all rows of all ranks"}
 
 
 # ----------------------------------------------------------------------------------------------- main
@@ -593,12 +801,15 @@ def main():
     ap.add_argument("--no-dit-step", action="store_true", help="skip the whole-DiT-block step latency leg")
     ap.add_argument("--no-gpu-reference", action="store_true",
                     help="skip the flash-attn (reference fallback) self-attention leg on the GPU")
+    ap.add_argument("--no-extra-legs", action="store_true",
+                    help="N > 1: skip the extra (not-the-value) legs: ring-KV on the same workload, and configs[3] "
+                         "(24B / 720p) under Ulysses and ring-KV")
     ap.add_argument("--profile", action="store_true",
                     help="short run for ncu: no e2e / CPU legs, warm-up exactly as given (numbers are not bench values)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.profile:
-        args.no_e2e = args.no_cpu_baseline = args.no_dit_step = args.no_gpu_reference = True
+        args.no_e2e = args.no_cpu_baseline = args.no_dit_step = args.no_gpu_reference = args.no_extra_legs = True
     if args.impl == "reference":
         return run_reference(args, w)
 
@@ -612,11 +823,13 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: stdout carries exactly one JSON line
+        # NCCL_DEBUG is left as the caller set it. NCCL carries only plumbing here (barriers, the max-over-ranks
+        # all-reduce, rendezvous of the symmetric-memory buffers); the default data plane is the kernels' own NVLink
+        # peer stores, so NCCL's channel log says nothing about the bytes that matter.
         dist.init_process_group("nccl", device_id=dev)
         from magi_b200 import parallel_state as mpu
         mpu.initialize_model_parallel(cp_size=world)
-    from magi_b200 import _lib
+    cx = Ctx(torch, dist, dev, world, rank, local)
 
     hp = HotPath(w, dev, cp=world, rank=rank, fused=args.cp_mode == "fused", ring=args.cp_mode.startswith("ring"),
                  ring_fused=args.cp_mode == "ring")
@@ -624,37 +837,11 @@ def main():
     self_f, cross_f = attn_flops(w)
     step_flops = (self_f + cross_f) * w["layers"]
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     # ---- device-resident timing (value)
     n_warm = args.warmup if args.profile else max(args.warmup, 3)
-    for _ in range(n_warm):
-        hp.step()
-    barrier()
-    hp.attn_events = []
-    l0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        e0.record()
-        for _ in range(args.steps):
-            hp.step(timed_events=True)
-        e1.record()
-        barrier()
-    launches = _lib.launch_count() - l0
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    ms_step = ms_total / args.steps
+    t = timed_leg(cx, hp, args.steps, n_warm)
+    ms_step, ms_total, attn_ms = t["ms_step"], t["ms_total"], t["attn_ms"]
     value = step_flops / (ms_step * 1e-3) / 1e12
-    attn_ms = [a.elapsed_time(b) for a, b in hp.attn_events]
     attn_avg_ms = sum(attn_ms) / len(attn_ms)
     launch_flops = self_f / world / (len(attn_ms) / (args.steps * w["layers"]))   # per self-attention launch
     achieved = launch_flops / (attn_avg_ms * 1e-3) / 1e12
@@ -663,78 +850,43 @@ def main():
     # ---- end to end: host buffers in, host buffers out, copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        host_in = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in hp.inputs.items()}
-        host_out = [torch.empty(hp.core_out.numel(), dtype=torch.bfloat16, pin_memory=True),
-                    torch.empty(hp.x_out.numel(), dtype=torch.bfloat16, pin_memory=True)]
-
-        if world == 1:
-            # double-buffered inputs and outputs, one copy stream: the H2D copy of step t + 1 and the D2H read of
-            # step t run under the kernels of the neighbouring step; every step still copies all of its inputs in
-            # and all of its results out inside the timed region
-            copy = torch.cuda.Stream()
-            in_sets = [hp.inputs, {k: torch.empty_like(v) for k, v in hp.inputs.items()}]
-            out_sets = [(hp.core_out, hp.x_out), (torch.empty_like(hp.core_out), torch.empty_like(hp.x_out))]
-            h2d_done, compute_done, d2h_done = [None, None], [None, None], [None, None]
-
-            def issue_h2d(i):
-                with torch.cuda.stream(copy):
-                    if compute_done[i] is not None:
-                        copy.wait_event(compute_done[i])      # set i was last read by the step before last
-                    for k, v in host_in.items():
-                        in_sets[i][k].copy_(v, non_blocking=True)
-                    h2d_done[i] = torch.cuda.Event()
-                    h2d_done[i].record(copy)
-
-            def e2e_step(t):
-                i = t & 1
-                cur = torch.cuda.current_stream()
-                cur.wait_event(h2d_done[i])
-                if d2h_done[i] is not None:
-                    cur.wait_event(d2h_done[i])               # output set i has been read back
-                hp.inputs = in_sets[i]
-                hp.core_out, hp.x_out = out_sets[i]
-                hp.step()
-                compute_done[i] = torch.cuda.Event()
-                compute_done[i].record(cur)
-                issue_h2d(i ^ 1)
-                with torch.cuda.stream(copy):
-                    copy.wait_event(compute_done[i])
-                    host_out[0].copy_(out_sets[i][0].reshape(-1), non_blocking=True)
-                    host_out[1].copy_(out_sets[i][1].reshape(-1), non_blocking=True)
-                    d2h_done[i] = torch.cuda.Event()
-                    d2h_done[i].record(copy)
-
-            def e2e_run(n):
-                copy.wait_stream(torch.cuda.current_stream())   # the first H2D starts inside the timed region
-                issue_h2d(0)
-                for t in range(n):
-                    e2e_step(t)
-                torch.cuda.current_stream().wait_stream(copy)   # ... and the last D2H ends inside it
-        else:
-            def e2e_run(n):
-                for _ in range(n):
-                    for k, v in host_in.items():
-                        hp.inputs[k].copy_(v, non_blocking=True)
-                    hp.step()
-                    host_out[0].copy_(hp.core_out.reshape(-1), non_blocking=True)
-                    host_out[1].copy_(hp.x_out.reshape(-1), non_blocking=True)
-
-        e2e_run(2)
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        e2e_run(args.steps)
-        s1.record()
-        barrier()
-        e2e_ms = max_over_ranks(s0.elapsed_time(s1)) / args.steps
+        e2e_ms = e2e_leg(cx, hp, args.steps)
         e2e = {"value": round(step_flops / (e2e_ms * 1e-3) / 1e12, 2), "unit": "TFLOP/s",
                "ms_per_step": round(e2e_ms, 3), "h2d_bytes_per_step": hp.h2d_bytes, "d2h_bytes_per_step": hp.d2h_bytes,
-               "api": "magi_b200.functional (ctypes -> libmagi_attn.so C-ABI), pinned host buffers"
-                      + (", copies double-buffered on a copy stream" if world == 1 else "")}
+               "api": "magi_b200.functional (ctypes -> libmagi_attn.so C-ABI), pinned host buffers, copies "
+                      "double-buffered on a copy stream" + (" (per rank: its token shard in, its rows out)"
+                                                            if world > 1 else "")}
+
+    # ---- multi-GPU parity of the path that was just timed
+    cp_parity = cp_parity_leg(cx, hp, w) if world > 1 and not args.profile else None
 
     dit = None
     if not args.no_dit_step and not args.cp_mode.startswith("ring"):
-        dit = dit_step_leg(w, dev, world, rank, min(args.steps, 3), max_over_ranks, barrier)
+        dit = dit_step_leg(w, dev, world, rank, min(args.steps, 3), cx.max_over_ranks, cx.barrier)
+
+    # ---- extra legs at N > 1 (never the value): ring-KV on the same workload, configs[3] under both strategies
+    extra = None
+    if world > 1 and not args.no_extra_legs and args.cp_mode == "fused" and args.workload == "cfg2":
+        extra = {}
+        del hp
+        torch.cuda.empty_cache()
+        for name, wl, ring in (("cfg2_ring_kv", "cfg2", True), ("cfg4_ulysses", "cfg4", False), ("cfg4_ring_kv", "cfg4", True)):
+            w2 = WORKLOADS[wl]
+            try:
+                hp2 = HotPath(w2, dev, cp=world, rank=rank, fused=not ring, ring=ring, ring_fused=ring)
+                steps2 = max(2, min(args.steps, 3 if wl == "cfg4" else 5))
+                t2 = timed_leg(cx, hp2, steps2, 3 if wl == "cfg2" else 1)
+                f2 = sum(attn_flops(w2)) * w2["layers"]
+                par = cp_parity_leg(cx, hp2, w2)
+                extra[name] = {"workload": w2["desc"][:60], "parallelism": hp2.mode(),
+                               "value": round(f2 / (t2["ms_step"] * 1e-3) / 1e12, 1), "unit": "TFLOP/s",
+                               "ms_per_step": round(t2["ms_step"], 2), "steps": steps2,
+                               "cp_parity_max_abs": par.get("max_abs"), "cp_parity_ok": par.get("ok")}
+                del hp2
+            except Exception as e:  # an extra leg must never cost the headline line
+                extra[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
+            torch.cuda.empty_cache()
+        hp = None
 
     gpu_ref = None
     if world == 1 and not args.no_gpu_reference:
@@ -746,44 +898,43 @@ def main():
         _, cpu = cpu_baseline_sample(w, budget_s=args.ref_budget)
 
     if rank == 0:
+        from magi_b200 import _lib
+        traffic = NCU_TRAFFIC.get(args.workload) if world == 1 else None
         line = {
             "metric": "chunk_causal_attn_tflops", "value": round(value, 2), "unit": "TFLOP/s", "n_gpus": world,
             "steps": args.steps, "warmup": n_warm, "ms_per_step": round(ms_step, 3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": w["desc"], "name": args.workload,
-                       "parallelism": "none" if world == 1 else (
-                           f"cp_ulysses{world}, all-to-alls fused into the kernels' stores (NVLink peer memory), 2 barriers "
-                           f"per layer" if hp.fused else
-                           f"cp_ring_kv{world} (every chunk striped across the ranks), K/V all-gather fused into the "
-                           f"prologue's stores ({'NVSwitch multicast' if hp.ring_multicast else 'NVLink peer stores'}) "
-                           f"into the replicated cache slot, 1 barrier per layer" if hp.ring_fused else
-                           f"cp_ring_kv{world}, K/V blocks round the ring by NCCL send/recv, "
-                           f"log-sum-exp merge, replicated cache" if hp.ring else
-                           f"cp_ulysses{world}, NCCL all_to_all_single (overlap_degree {args.overlap_degree})"),
-                       "step": "attention hot path of one denoise forward over all layers: fused LN+RoPE prologue with "
-                               "KV-cache append, range-masked self-attention, text cross-attention",
-                       "tokens_q": hp.S, "layers": w["layers"],
-                       "flops_per_step": step_flops, "self_attn_flops_per_layer": self_f,
-                       "l2": "inputs larger than L2 (>= 600 MB of projection outputs re-read per layer)",
-                       "pct_of_bf16_peak_burst": round(100 * value / world / peaks["burst"], 1),
-                       "pct_of_bf16_peak_sustained": round(100 * value / world / peaks["sustained"], 1),
-                       "pct_of_bf16_datasheet_2250": round(100 * value / world / 2250.0, 1)},
-            "clocks": clk.summary(),
+            "config": static_config(args, w, world),
+            "clocks": t["clocks"],
             "e2e": e2e,
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "magi::attn_fwd_kernel (self-attention launch)",
+            "gpu_launches": t["launches"],
+            "roofline": {"bound": "tensor", "kernel": f"magi::{_lib.attn_kernel_name()} (self-attention launch)",
                          "achieved": round(achieved, 1), "peak": peaks["sustained"], "unit": "TFLOP/s",
                          "frac": round(achieved / peaks["sustained"], 3),
-                         "traffic": NCU_TRAFFIC_BYTES.get(args.workload) if world == 1 else None,
+                         "traffic": traffic[0] if traffic else None,
+                         "traffic_source": traffic[1] if traffic else "not captured at N > 1 (ncu is single-GPU only)",
                          "peak_source": peaks["source"] + ", sustained (kernel timed inside a long step); burst "
                                         f"{peaks['burst']} -> frac {achieved / peaks['burst']:.3f}",
                          "flops_per_launch": launch_flops, "avg_launch_ms": round(attn_avg_ms, 4),
-                         "share_of_step": round(sum(attn_ms) / ms_total, 3)},
+                         "share_of_step": round(sum(attn_ms) / ms_total, 3),
+                         "pct_of_bf16_peak_burst": round(100 * value / world / peaks["burst"], 1),
+                         "pct_of_bf16_peak_sustained": round(100 * value / world / peaks["sustained"], 1),
+                         "pct_of_bf16_datasheet_2250": round(100 * value / world / 2250.0, 1)},
         }
+        # measured companions ride inside `roofline` too: the driver's record keeps that object whole
+        if cp_parity is not None:
+            line["cp_parity"] = cp_parity
+            line["roofline"]["cp_parity"] = {k: cp_parity.get(k) for k in ("mode", "max_abs", "bound", "ok", "skipped")
+                                             if k in cp_parity}
+        if extra is not None:
+            line["extra_legs"] = extra
+            line["roofline"]["extra_legs"] = extra
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if dit is not None:
             line["dit_denoise_step"] = dit
+            line["roofline"]["dit_denoise_step_ms"] = dit["ms_per_step"]
+            line["roofline"]["dit_denoise_step_tflops"] = dit["tflops_total"]
         if gpu_ref is not None:
             line["gpu_reference"] = gpu_ref
         print(json.dumps(line), flush=True)

@@ -208,3 +208,15 @@ def check(rc: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(lib().magi_launch_count())
+
+
+def attn_kernel_name() -> str:
+    """Which attention kernel magi_attn_fwd launches in this process (MAGI_ATTN_KERNEL=single|pair overrides the
+    library's built-in default, reported by magi_build_info)."""
+    e = os.environ.get("MAGI_ATTN_KERNEL", "")
+    if e == "single":
+        return "attn_fwd_kernel"
+    if e == "pair":
+        return "attn_pair_kernel"
+    info = lib().magi_build_info().decode("utf-8", "replace")
+    return "attn_pair_kernel" if "default attention kernel: pair" in info else "attn_fwd_kernel"

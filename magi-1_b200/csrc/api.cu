@@ -41,6 +41,12 @@ int fail(const char* fmt, ...) {
 #define MAGI_DEFAULT_PAIR 0   // which attention kernel runs when MAGI_ATTN_KERNEL is unset
 #endif
 
+#if MAGI_DEFAULT_PAIR
+#define MAGI_DEFAULT_KERNEL_NAME "pair"
+#else
+#define MAGI_DEFAULT_KERNEL_NAME "single"
+#endif
+
 #define MAGI_STR_(x) #x
 #define MAGI_STR(x) MAGI_STR_(x)
 
@@ -115,7 +121,8 @@ extern "C" {
 const char* magi_last_error(void) { return g_err; }
 
 const char* magi_build_info(void) {
-  return "magi_attn sm_100a tcgen05/TMEM/TMA; built " __DATE__ " " __TIME__
+  return "magi_attn sm_100a tcgen05/TMEM/TMA; default attention kernel: " MAGI_DEFAULT_KERNEL_NAME
+         "; built " __DATE__ " " __TIME__
 #ifdef __CUDACC_VER_MAJOR__
          "; nvcc " MAGI_STR(__CUDACC_VER_MAJOR__) "." MAGI_STR(__CUDACC_VER_MINOR__) "." MAGI_STR(__CUDACC_VER_BUILD__)
 #endif

@@ -56,10 +56,33 @@ constexpr uint32_t kIdescQK = make_idesc_bf16(256, 128, 0, 0);
 constexpr uint32_t kIdescPV = make_idesc_bf16(256, 128, 0, 1);
 constexpr float kRescaleThreshold = 8.0f;  // log2 units: lazily rescale O only when the row max grew by > 2^8
 #ifndef MAGI_PAIR_EMU_MOD
-#define MAGI_PAIR_EMU_MOD 3                // every n-th column pair takes the polynomial exp2 (0 = never)
+#define MAGI_PAIR_EMU_MOD 4                // every n-th column pair takes the polynomial exp2 (0 = never); 4 measured best
 #endif
 constexpr int kEmuMod = MAGI_PAIR_EMU_MOD;
-constexpr uint32_t kColS = 0, kColO = 256, kColP = 384;
+// MAGI_PAIR_LSUM=1: the softmax row sums come off the TENSOR pipe instead of 64 FADD2 per thread and tile: one more
+// (tiny) MMA per tile, L[256 x 16] += P[256 x 128 keys] * ones[128 keys x 16], accumulates sum_j P_ij (of the bf16 P
+// the P V product uses, so numerator and denominator see the same rounding) into 16 TMEM columns; the epilogue reads
+// its row's sum from there. Its columns come from single-buffering P (P V of tile g has always drained long before the
+// softmax of tile g + 1 stores: checked with one mbarrier test per tile).
+// Measured (profiles/r02_pair_variants2.log): correct, not faster (1136 vs 1141 TFLOP/s) - the exponentials of the two
+// warps that share an SM sub-partition are MUFU-bound and run in lockstep - so it is OFF by default.
+#ifndef MAGI_PAIR_LSUM
+#define MAGI_PAIR_LSUM 0
+#endif
+constexpr bool kLsum = MAGI_PAIR_LSUM != 0;
+constexpr uint32_t kColS = 0, kColO = 256, kColP = 384, kColL = 448;
+constexpr uint32_t kIdescL = make_idesc_bf16(256, 16, 0, 0);
+constexpr int kOnesBytes = 1024;
+
+#ifdef MAGI_TRACE
+// Debug build only: clock64 stamps of the leader CTA of pair 0 (softmax warps 0 and 4, which share SM sub-partition
+// 0, and the MMA issuer), first 512 tiles. who: 0 = warp 0, 1 = warp 4, 2 = issuer (S side), 3 = issuer (P V side).
+__device__ long long g_ptrace[4][512][8];
+#define PTRACE(who, idx, slot) \
+  do { if ((idx) < 512u) g_ptrace[who][idx][slot] = clock64(); } while (0)
+#else
+#define PTRACE(who, idx, slot) do {} while (0)
+#endif
 
 struct PairBarriers {
   // arrived on in BOTH CTAs by the leader's multicast tcgen05.commit
@@ -72,13 +95,13 @@ struct PairBarriers {
   uint64_t kv_full[kStages];   // 1 arrival (leader's expect_tx) + the bytes of both CTAs' halves
   uint64_t q_full[kQStages];
   uint64_t s_free[2];          // 16 arrivals: every softmax warp of the pair has S[b] in registers
-  uint64_t p_full[2];          // 16 arrivals: P[b] stored
+  uint64_t p_full[2];          // 16 arrivals: P[b] stored (one buffer, hence one barrier, with MAGI_PAIR_LSUM)
   uint64_t o_free;             // 16 arrivals: O read by the epilogue
   uint32_t tmem_base;
   float xl[kTileM], xm[kTileM];  // row sum / row max handed from the fragment layout to the row-per-thread epilogue
 };
 
-constexpr int kSmemBytes = kQStages * kQBytes + kStages * kHalfBytes + 1024 /*align slack*/;
+constexpr int kSmemBytes = kQStages * kQBytes + kStages * kHalfBytes + kOnesBytes + 1024 /*align slack*/;
 static_assert(kSmemBytes + sizeof(PairBarriers) <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 
 struct Item {
@@ -175,6 +198,14 @@ __device__ __forceinline__ void issue_pv(uint32_t d_tmem, uint32_t p_tmem, uint6
                 (accumulate | (ks > 0)) ? 1u : 0u);
 }
 
+// L[256 x 16] (+)= P[256 x 128(keys)] * ones[128(keys) x 16]: every column of L is the row sum of P. B is a block of
+// bf16 ones (any in-range placement reads ones, so one descriptor serves all eight k-steps).
+__device__ __forceinline__ void issue_l(uint32_t d_tmem, uint32_t p_tmem, uint64_t ones_desc, uint32_t accumulate) {
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks)
+    mma_ts_pair(d_tmem, p_tmem + ks * 8, ones_desc, kIdescL, (accumulate | (ks > 0)) ? 1u : 0u);
+}
+
 }  // namespace
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -185,6 +216,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;                         // kQStages Q tiles
   uint8_t* smem_kv = smem + kQStages * kQBytes;   // kStages half tiles
+  uint8_t* smem_ones = smem_kv + kStages * kHalfBytes;
   __shared__ PairBarriers bar;
 
   const int warp = threadIdx.x >> 5;
@@ -217,6 +249,10 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (warp == kMmaWarp) {
     tmem_alloc_pair(&bar.tmem_base, 512);
     tmem_relinquish_pair();
+  }
+  if (kLsum && threadIdx.x < kOnesBytes / 4) {
+    reinterpret_cast<uint32_t*>(smem_ones)[threadIdx.x] = 0x3f803f80u;   // bf16 1.0 x 2
+    fence_proxy_async_smem();   // generic-proxy writes, read by the tensor core (async proxy)
   }
   if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -293,8 +329,18 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         int seg, krow0, nvalid;
         tile_info(it, j, seg, krow0, nvalid);
         const uint32_t b = g & 1, ph = (g >> 1) & 1;
+        const uint32_t pb = kLsum ? 0u : b;   // P buffer
+#ifdef MAGI_TRACE
+        const bool tr = blockIdx.x == 0 && quarter == 0 && lane == 0;
+#endif
+#ifdef MAGI_TRACE
+        if (tr) PTRACE(hh, g, 0);
+#endif
         mbar_wait(&bar.s_full[b], ph);
         tc_fence_after();
+#ifdef MAGI_TRACE
+        if (tr) PTRACE(hh, g, 1);
+#endif
         uint32_t s[64];   // s[4n + 2h + e] = S[row rl0 + 8h][column 8n + 2 qd + e]
         MAGI_TMEM_LD_16x256b_X16(tmem_base + frag_lane + kColS + b * 128, s, 0);
         tmem_wait_ld();
@@ -302,6 +348,9 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(s_free_remote + 8 * b);
+#ifdef MAGI_TRACE
+        if (tr) PTRACE(hh, g, 2);
+#endif
         if (nvalid < kTileN) {
           // only the last key tile of a segment is partial (the empty asm keeps this out of the common path)
           asm volatile("" ::: "memory");
@@ -349,8 +398,10 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 p0 = ex2_approx(x0);
                 p1 = ex2_approx(x1);
               }
-              const uint64_t p2 = pack_f2(p0, p1);
-              if (n & 1) sum_b = fadd2(sum_b, p2); else sum_a = fadd2(sum_a, p2);
+              if constexpr (!kLsum) {
+                const uint64_t p2 = pack_f2(p0, p1);
+                if (n & 1) sum_b = fadd2(sum_b, p2); else sum_a = fadd2(sum_a, p2);
+              }
               pk[2 * n + h] = pack_bf16x2(p0, p1);
             }
             float s0, s1;
@@ -367,6 +418,9 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           // optimistic: P against the reference max m while the max chains run beside it on the ALU pipe; only when
           // some row's max grew by more than 2^8 (rare) is O brought back into range and the tile redone.
           exps();
+#ifdef MAGI_TRACE
+          if (tr) PTRACE(hh, g, 3);
+#endif
           float mx[2];
           tile_max(mx);
           const bool need0 = (mx[0] - m[0]) * scale_log2 > kRescaleThreshold;
@@ -386,15 +440,40 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
               for (int k = 0; k < 16; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha[(k >> 1) & 1]);
               MAGI_TMEM_ST_16x256b_X4(tmem_base + frag_lane + kColO + c, o, 0);
             }
+            if constexpr (kLsum) {
+              uint32_t o[8];   // the 16 row-sum columns
+              MAGI_TMEM_LD_16x256b_X2(tmem_base + frag_lane + kColL, o, 0);
+              tmem_wait_ld();
+#pragma unroll
+              for (int k = 0; k < 8; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha[(k >> 1) & 1]);
+              MAGI_TMEM_ST_16x256b_X2(tmem_base + frag_lane + kColL, o, 0);
+            }
             tmem_wait_st();
             exps();
           }
         }
-        MAGI_TMEM_ST_16x128b_X16(tmem_base + frag_lane + kColP + b * 64, pk, 0);
+        if constexpr (kLsum) {
+          // single P buffer: P V (and the row-sum MMA) of the previous tile must have drained. It has, long ago, in
+          // any steady state; the test is one try_wait.
+          if (g > 0) {
+            mbar_wait(&bar.pv_done, (g - 1) & 1);
+            tc_fence_after();
+          }
+        }
+#ifdef MAGI_TRACE
+        if (tr) PTRACE(hh, g, 4);
+#endif
+        MAGI_TMEM_ST_16x128b_X16(tmem_base + frag_lane + kColP + pb * 64, pk, 0);
         tmem_wait_st();
+#ifdef MAGI_TRACE
+        if (tr) PTRACE(hh, g, 5);
+#endif
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(p_full_remote + 8 * b);
+        if (lane == 0) mbar_arrive_cluster(p_full_remote + 8 * pb);
+#ifdef MAGI_TRACE
+        if (tr) PTRACE(hh, g, 6);
+#endif
         l[0] = l[0] * alpha[0] + ts[0];
         l[1] = l[1] * alpha[1] + ts[1];
       }
@@ -410,10 +489,15 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         bar.xm[rl0] = m[0]; bar.xm[rl0 + 8] = m[1];
       }
       asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");   // warps w and w + 4 share a lane quarter
-      const float row_l = bar.xl[erow_l], row_m = bar.xm[erow_l];
+      float row_l = bar.xl[erow_l];
+      const float row_m = bar.xm[erow_l];
       mbar_wait(&bar.o_full, items & 1);
       ++items;
       tc_fence_after();
+      if constexpr (kLsum) {
+        row_l = __uint_as_float(tmem_ld_32x32b_x1(tmem_base + quart_lane + kColL));
+        tmem_wait_ld();
+      }
       const float inv_l = 1.f / row_l;
 #pragma unroll 1
       for (int c = 0; c < 64; c += 32) {
@@ -458,11 +542,21 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       auto issue_s = [&]() {
         const int nt = uniform(cs.it.nt);
         const uint32_t qs = items_s % kQStages;
+#ifdef MAGI_TRACE
+        const bool tr = blockIdx.x == 0 && lane == 0;
+        if (tr) PTRACE(2, gs, 0);
+#endif
         if (js == 0) mbar_wait_cluster(&bar.q_full[qs], (items_s / kQStages) & 1);
         mbar_wait_cluster(&bar.kv_full[stage], phase);
+#ifdef MAGI_TRACE
+        if (tr) PTRACE(2, gs, 1);
+#endif
         const uint32_t b = gs & 1;
         mbar_wait_cluster(&bar.s_free[b], ((gs >> 1) & 1) ^ 1);
         tc_fence_after();
+#ifdef MAGI_TRACE
+        if (tr) PTRACE(2, gs, 2);
+#endif
         if (elect_one()) {
           issue_qk(tb + kColS + b * 128, desc_kmajor(q_addr + qs * kQBytes), desc_kmajor(kv_addr + stage * kHalfBytes));
           tc_commit_pair(&bar.s_full[b]);
@@ -470,6 +564,9 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           if (js == nt - 1) tc_commit_pair(&bar.q_empty[qs]);
         }
         __syncwarp();
+#ifdef MAGI_TRACE
+        if (tr) PTRACE(2, gs, 3);
+#endif
         advance();
         ++gs;
         if (++js == nt) {
@@ -480,18 +577,34 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       };
       auto issue_p = [&]() {
         const int nt = uniform(cp.it.nt);
+#ifdef MAGI_TRACE
+        const bool tr = blockIdx.x == 0 && lane == 0;
+        if (tr) PTRACE(3, gp, 0);
+#endif
         mbar_wait_cluster(&bar.kv_full[stage], phase);
         if (jp == 0) mbar_wait_cluster(&bar.o_free, (items_p & 1) ^ 1);
-        const uint32_t b = gp & 1;
-        mbar_wait_cluster(&bar.p_full[b], (gp >> 1) & 1);
+#ifdef MAGI_TRACE
+        if (tr) PTRACE(3, gp, 1);
+#endif
+        const uint32_t b = kLsum ? 0u : (gp & 1);
+        mbar_wait_cluster(&bar.p_full[b], kLsum ? (gp & 1) : ((gp >> 1) & 1));
         tc_fence_after();
+#ifdef MAGI_TRACE
+        if (tr) PTRACE(3, gp, 2);
+#endif
         if (elect_one()) {
           issue_pv(tb + kColO, tb + kColP + b * 64, desc_v(kv_addr + stage * kHalfBytes), jp > 0 ? 1u : 0u);
+          if constexpr (kLsum)
+            issue_l(tb + kColL, tb + kColP + b * 64, make_smem_desc_noswizzle(smem_u32(smem_ones), 128, 256),
+                    jp > 0 ? 1u : 0u);
           tc_commit_pair(&bar.kv_empty[stage]);
           tc_commit_pair(&bar.pv_done);
           if (jp == nt - 1) tc_commit_pair(&bar.o_full);
         }
         __syncwarp();
+#ifdef MAGI_TRACE
+        if (tr) PTRACE(3, gp, 3);
+#endif
         advance();
         ++gp;
         if (++jp == nt) {
@@ -586,6 +699,12 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   cluster_sync_all();   // neither CTA may exit (or free TMEM) while the other can still signal it
   if (warp == kMmaWarp) tmem_dealloc_pair(tmem_base, 512);
 }
+
+#ifdef MAGI_TRACE
+extern "C" __attribute__((visibility("default"))) int magi_debug_read_trace_pair(long long* host, size_t bytes) {
+  return (int)cudaMemcpyFromSymbol(host, g_ptrace, bytes < sizeof(g_ptrace) ? bytes : sizeof(g_ptrace));
+}
+#endif
 
 cudaError_t attn_pair_launch(const CUtensorMap* maps, const AttnKernelParams& p, int num_ctas, cudaStream_t stream) {
   static bool attr_set[64] = {false};   // per device; the attribute is sticky, so set it once instead of per call

@@ -296,6 +296,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t addr, uint32_t
   return d;
 }
 
+// Same, no swizzle (canonical 8-row x 16-byte core matrices; lbo / sbo = byte strides between core matrices along
+// K / along M-N). Used for the all-ones operand of the row-sum MMA, where the exact element placement is irrelevant.
+__device__ __forceinline__ uint64_t make_smem_desc_noswizzle(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3ffffu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;  // descriptor version (Blackwell)
+  return d;
+}
+
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
 //   b_mn_major = 1 when B is stored N-contiguous (used for P*V with V kept [key][head_dim]).
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
@@ -328,6 +339,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
         "=r"(r[o + 30]), "=r"(r[o + 31])                                                                      \
       : "r"(taddr)                                                                                            \
       : "memory")
+
+// one column: thread i receives column c of TMEM lane (base_lane + i)
+__device__ __forceinline__ uint32_t tmem_ld_32x32b_x1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
+}
 
 #define MAGI_TMEM_ST32(taddr, r, o)                                                                           \
   asm volatile(                                                                                               \
