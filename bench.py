@@ -369,7 +369,8 @@ class HotPath:
         targets = [self.cache_mc[l] + slot] if self.ring_multicast else [p_ + slot for p_ in self.cache_ptrs[l]]
         q, _ = F.qk_norm_rope(inp["xq"], inp["xk"], inp["xv"], w["Hq"], w["Hkv"], self.ln["q"], self.ln["k"],
                               inp["sin"], inp["cos"], gather_kv_out=targets,
-                              gather_geometry=(self.ring_sizes[self.rank], w["clip"], sum(self.ring_sizes[:self.rank])))
+                              gather_geometry=(self.ring_sizes[self.rank], w["clip"], sum(self.ring_sizes[:self.rank])),
+                              gather_multicast=self.ring_multicast)
         x_prepared = self.cross_prepare(inp)
         self.ring_ws.barrier()
         kv = cache[self.start:self.start + self.S]

@@ -100,6 +100,10 @@ typedef struct magi_attn_args {
   int32_t peer_head_offset;
   void* peer_out[MAGI_MAX_PEERS];
   int64_t peer_row_bounds[MAGI_MAX_PEERS + 1];
+  /* Which kernel runs: 0 = the library default (the environment variable MAGI_ATTN_KERNEL=single|pair overrides it),
+   * 1 = attn_fwd_kernel (one CTA per SM, two query tiles per CTA), 2 = attn_pair_kernel (CTA pairs, cta_group::2;
+   * experimental: correct, measured slower - DESIGN.md section 4.1). Same results within the documented tolerance. */
+  int32_t kernel;
 } magi_attn_args;
 
 MAGI_API size_t magi_attn_workspace_bytes(int32_t n_ranges);
@@ -178,6 +182,10 @@ typedef struct magi_prologue_args {
   int32_t gather_peers; /* 0 = off */
   void* gather_kv_out[MAGI_MAX_PEERS];
   int64_t gather_rows_per_chunk, gather_chunk_stride, gather_row_offset;
+  /* gather_multicast != 0: gather_peers == 1 and gather_kv_out[0] is the NVSwitch MULTICAST mapping of the symmetric
+   * buffer (one store, replicated to every rank by the switch). The kernel then stores with multimem.st - the PTX ISA
+   * leaves ordinary ld/st to a multimem address undefined. */
+  int32_t gather_multicast;
 } magi_prologue_args;
 
 MAGI_API int magi_qk_norm_rope_fwd(const magi_prologue_args* args, void* stream);
@@ -272,6 +280,18 @@ typedef struct magi_rotary_args {
   const float* sin;
 } magi_rotary_args;
 MAGI_API int magi_apply_rotary_emb(const magi_rotary_args* args, void* stream);
+
+/*
+ * MLP activation between fc1 and fc2 (CustomMLP.forward, dit_module.py:541-549), one memory-bound launch:
+ *   gated != 0 (24B, gated_linear_unit): out[r, c] = bf16(silu(float(x[r, c])) * float(x[r, f + c])), x = (rows, 2 f)
+ *                 = flashinfer.activation.silu_and_mul (dit_module.py:546)
+ *   gated == 0 (4.5B): out[r, c] = bf16(gelu(float(x[r, c]))) with the erf form of torch.nn.functional.gelu
+ *                 (dit_module.py:548), x = (rows, f)
+ * x / out bf16, f a multiple of 8, row strides in elements (multiples of 8), pointers 16-byte aligned; out may not
+ * alias x when gated.
+ */
+MAGI_API int magi_mlp_activation(const void* x, int64_t x_row_stride, void* out, int64_t out_row_stride, int64_t rows,
+                                 int32_t f, int32_t gated, void* stream);
 
 /* Diagnostics */
 MAGI_API const char* magi_last_error(void);

@@ -23,6 +23,7 @@ EXPORTS = (
     "magi_cso_unshuffle",
     "magi_bias_modulate_add",
     "magi_apply_rotary_emb",
+    "magi_mlp_activation",
     "magi_last_error",
     "magi_build_info",
     "magi_launch_count",
@@ -70,6 +71,7 @@ class MagiAttnArgs(C.Structure):
         ("peer_head_offset", C.c_int32),
         ("peer_out", C.c_void_p * MAX_PEERS),
         ("peer_row_bounds", C.c_int64 * (MAX_PEERS + 1)),
+        ("kernel", C.c_int32),
     ]
 
 
@@ -118,6 +120,7 @@ class MagiPrologueArgs(C.Structure):
         ("gather_rows_per_chunk", C.c_int64),
         ("gather_chunk_stride", C.c_int64),
         ("gather_row_offset", C.c_int64),
+        ("gather_multicast", C.c_int32),
     ]
 
 
@@ -193,6 +196,9 @@ def lib() -> C.CDLL:
     L.magi_bias_modulate_add.argtypes = [C.POINTER(MagiGatingArgs), C.c_void_p]
     L.magi_apply_rotary_emb.restype = C.c_int
     L.magi_apply_rotary_emb.argtypes = [C.POINTER(MagiRotaryArgs), C.c_void_p]
+    L.magi_mlp_activation.restype = C.c_int
+    L.magi_mlp_activation.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                                      C.c_void_p]
     L.magi_last_error.restype = C.c_char_p
     L.magi_build_info.restype = C.c_char_p
     L.magi_launch_count.restype = C.c_uint64

@@ -118,6 +118,13 @@ class KVOffload:
             self.prefetch_hits += 1
         else:
             idx = layer & 1
+            # any copy-stream transfer still in flight into a staging buffer (an orphaned prefetch: its row count no
+            # longer matches, or it belongs to another layer after an aborted forward) must land before the compute
+            # stream writes the same buffer
+            if hit is not None:
+                cur.wait_event(hit[2])
+            for stale in [l for l, e in self.prefetched.items() if e[0] == idx]:
+                cur.wait_event(self.prefetched.pop(stale)[2])
             buf = self._h2d(layer, cache, rows, idx, cur)
         if next_layer_cache is not None and rows > 0:
             # the other staging buffer was last read by the previous layer's attention, which the compute stream has
@@ -703,13 +710,15 @@ class FullyParallelAttention(nn.Module):
             slot = start * Hkv * 2 * F.HEAD_DIM * 2
             ptrs = [p_ + slot for p_ in self._cache_peer_ptrs]
             mc = self._cache_mc_ptr + slot if self._cache_mc_ptr else 0
-        targets = [mc] if (mc and cpm.ring_multicast_enabled()) else ptrs
+        use_mc = bool(mc and cpm.ring_multicast_enabled())
+        targets = [mc] if use_mc else ptrs
         query = None
         if sq > 0:
             xq, xk, xv = self._project(mixed_qqkv)
             query, _ = F.qk_norm_rope(xq, xk, xv, Hq, Hkv, self._ln(self.q_layernorm), self._ln(self.k_layernorm),
                                       sin_emb, cos_emb, batch=1, eps=eps, zero_centered_gamma=z,
-                                      gather_kv_out=targets, gather_geometry=(n_me, clip, off_me))
+                                      gather_kv_out=targets, gather_geometry=(n_me, clip, off_me),
+                                      gather_multicast=use_mc)
         x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states)
         ws.barrier()                                              # every rank's K/V stripes have landed everywhere
         kv = cache[start:start + total_rows] if direct else buf[:total_rows]

@@ -481,15 +481,39 @@ class UlyssesPeerWorkspace:
             ws = cls._instances[key] = cls(group, total_rows, max_local_rows, hq_loc, hkv_loc, heads_q, device)
         return ws
 
+    _probe = {}   # id(group) -> bool: result of the one-time symmetric-memory probe
+
     @staticmethod
     def available(group, device) -> bool:
+        """True when the fused (peer-store) paths can run on this group: NCCL backend, at most MAGI_MAX_PEERS ranks
+        (the C-ABI's peer tables), and a symmetric-memory rendezvous that actually succeeds - probed ONCE per group
+        with a tiny buffer and agreed on by all ranks (a group without P2P / NVLink access, e.g. spanning nodes, fails
+        the rendezvous: the callers then fall back to the NCCL paths instead of crashing). Collective on first use."""
         if group is None or not dist.is_initialized() or torch.device(device).type != "cuda":
             return False
+        key = id(group)
+        ok = UlyssesPeerWorkspace._probe.get(key)
+        if ok is not None:
+            return ok
+        ok = False
         try:
-            import torch.distributed._symmetric_memory as _symm  # noqa: F401
-            return dist.get_backend(group) == "nccl"
+            from ._lib import MAX_PEERS
+            if dist.get_backend(group) == "nccl" and dist.get_world_size(group) <= MAX_PEERS:
+                import torch.distributed._symmetric_memory as symm
+                mine = 1
+                try:
+                    t = symm.empty((256,), dtype=torch.bfloat16, device=device)
+                    h = symm.rendezvous(t, group.group_name)
+                    mine = 1 if len(h.buffer_ptrs) == dist.get_world_size(group) else 0
+                except Exception:
+                    mine = 0
+                flag = torch.tensor([mine], device=device, dtype=torch.int32)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)   # every rank takes the same path
+                ok = bool(flag.item())
         except Exception:
-            return False
+            ok = False
+        UlyssesPeerWorkspace._probe[key] = ok
+        return ok
 
 
 def fused_ulysses_plan(cp_split_sizes: Sequence[int], rank: int, heads_q: int, cp: int):

@@ -12,6 +12,7 @@
 #include "prologue.cuh"
 #include "gating.cuh"
 #include "rope.cuh"
+#include "activation.cuh"
 
 namespace {
 
@@ -168,7 +169,9 @@ int magi_attn_fwd(const magi_attn_args* a, void* stream_) {
   }();
   int sms = a->num_sms;
   if (sms <= 0) { if (int r2 = device_sm_count(&sms)) return r2; }
-  const bool use_pair = (kernel_env == 2 || (kernel_env == 0 && MAGI_DEFAULT_PAIR)) && sms >= 2;
+  MAGI_CHECK(a->kernel >= 0 && a->kernel <= 2, "kernel must be 0 (default), 1 (single) or 2 (pair)");
+  const int kernel_sel = a->kernel != 0 ? a->kernel : kernel_env;
+  const bool use_pair = (kernel_sel == 2 || (kernel_sel == 0 && MAGI_DEFAULT_PAIR)) && sms >= 2;
   const int k_box = use_pair ? 64 : 128;   // a CTA of a pair stages its 64 keys of every K tile
 
   CUtensorMap tm_q, tm_ka, tm_va, tm_kb, tm_vb;
@@ -311,6 +314,7 @@ int magi_qk_norm_rope_fwd(const magi_prologue_args* a, void* stream_) {
     p.peer_row_offset = a->peer_row_offset;
   }
   p.gather_peers = 0;
+  p.gather_multicast = 0;
   p.gather_rows_per_chunk = 1; p.gather_chunk_stride = 0; p.gather_row_offset = 0;
   if (a->gather_peers > 0) {
     MAGI_CHECK(a->gather_peers <= MAGI_MAX_PEERS, "gather_peers must be at most %d", MAGI_MAX_PEERS);
@@ -325,7 +329,9 @@ int magi_qk_norm_rope_fwd(const magi_prologue_args* a, void* stream_) {
                    "bad gather_kv_out[%d]", i);
         p.peer_kv[i] = a->gather_kv_out[i];
       }
+    MAGI_CHECK(a->gather_multicast == 0 || a->gather_peers == 1, "gather_multicast takes exactly one (multicast) pointer");
     p.gather_peers = a->gather_peers;
+    p.gather_multicast = a->gather_multicast != 0;
     p.gather_rows_per_chunk = a->gather_rows_per_chunk;
     p.gather_chunk_stride = a->gather_chunk_stride;
     p.gather_row_offset = a->gather_row_offset;
@@ -450,6 +456,25 @@ int magi_bias_modulate_add(const MagiGatingArgs* a, void* stream_) {
   int sms = 0;
   if (int rc = device_sm_count(&sms)) return rc;
   MAGI_CUDA(magi::gating_launch(p, a->x_dtype == 1, a->gate_dtype == 1, sms, stream));
+  g_launches++;
+  return 0;
+}
+
+int magi_mlp_activation(const void* x, int64_t x_row_stride, void* out, int64_t out_row_stride, int64_t rows, int32_t f,
+                        int32_t gated, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MAGI_CHECK(rows >= 0 && f > 0 && f % 8 == 0, "rows must be >= 0 and f a positive multiple of 8");
+  if (rows == 0) return 0;
+  MAGI_CHECK(x && out, "NULL pointer");
+  MAGI_CHECK(x_row_stride % 8 == 0 && out_row_stride % 8 == 0 && out_row_stride >= f &&
+                 x_row_stride >= (gated ? 2 : 1) * (int64_t)f,
+             "row strides must be multiples of 8 elements and cover a row");
+  MAGI_CHECK(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+             "pointers must be 16-byte aligned");
+  MAGI_CHECK(!(gated && x == out), "out may not alias x when gated");
+  int sms = 0;
+  if (int rc = device_sm_count(&sms)) return rc;
+  MAGI_CUDA(magi::mlp_act_launch(x, x_row_stride, out, out_row_stride, rows, f, gated != 0, sms, stream));
   g_launches++;
   return 0;
 }

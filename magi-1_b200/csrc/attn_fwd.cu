@@ -194,13 +194,17 @@ __device__ __forceinline__ void issue_qk(uint32_t d_tmem, uint64_t q_desc, uint6
 // O[128 x 128(hd)] (+)= P[128 x 128(keys)] * V[128(keys) x 128(hd)] ; P from TMEM (bf16, 2 per column),
 // V is MN-major (head_dim contiguous): 8-key groups 1024 B apart (SBO), 64-wide hd blocks kBlkBytes apart (LBO).
 // `half` selects keys [64 half, 64 half + 64) of the tile (k-steps 4 half .. 4 half + 3).
+// `nks` = 16-key groups of the tile that hold at least one key of the range (8 for a full tile): the groups past the
+// end of a partial last tile are not issued at all - their P is exactly 0, and skipping them keeps V rows that lie
+// inside the tensor view but past the key range (possibly NaN / Inf padding) out of the accumulator.
 __device__ __forceinline__ void issue_pv(uint32_t d_tmem, uint32_t p_tmem, uint64_t v_desc, uint32_t accumulate,
-                                         int half) {
+                                         int half, int nks) {
 #pragma unroll
   for (int ks = 4 * half; ks < 4 * half + 4; ++ks) {
     // P half h (keys [64h, 64h+64), bf16) sits in columns [64h, 64h+32) of S_t: over the S columns its writer read
-    mma_ts(d_tmem, p_tmem + 64 * half + (ks - 4 * half) * 8, v_desc + static_cast<uint64_t>((ks * 2048) >> 4), kIdescPV,
-           (accumulate | (ks > 0)) ? 1u : 0u);   // only k-step 0 of a fresh accumulator overwrites
+    if (ks < nks)
+      mma_ts(d_tmem, p_tmem + 64 * half + (ks - 4 * half) * 8, v_desc + static_cast<uint64_t>((ks * 2048) >> 4),
+             kIdescPV, (accumulate | (ks > 0)) ? 1u : 0u);   // only k-step 0 of a fresh accumulator overwrites
   }
 }
 
@@ -582,17 +586,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (++stage == kStages) { stage = 0; phase ^= 1; }
     };
     // O_t (+)= P_t V in two 64-key halves, each issued as soon as the softmax warpgroup has published that half of P
-    auto pv = [&](uint32_t tO, uint32_t tS, int t, uint32_t& ph, uint32_t vst_, uint32_t acc) {
+    auto pv = [&](uint32_t tO, uint32_t tS, int t, uint32_t& ph, uint32_t vst_, uint32_t acc, int nks) {
       const uint64_t vd = desc_v(kv_addr + vst_ * kTileBytes);
       mbar_wait_warp(&bar->p_half[t][0], ph);
       tc_fence_after();
-      if (elect_one()) issue_pv(tO, tS, vd, acc, 0);
+      if (elect_one()) issue_pv(tO, tS, vd, acc, 0, nks);
       __syncwarp();
       mbar_wait_warp(&bar->p_half[t][1], ph);
       tc_fence_after();
-      if (elect_one()) issue_pv(tO, tS, vd, acc, 1);
+      if (elect_one()) issue_pv(tO, tS, vd, acc, 1, nks);
       __syncwarp();
       ph ^= 1;
+    };
+    // A partial last tile of a segment (nvalid < 128): the 16-key group that straddles the end of the range still
+    // enters P V, so its rows past the range are zeroed in shared memory once the tile has landed (at most 15 rows x
+    // 256 B, this warp's 32 lanes); the groups after it are skipped by `nks`. Returns nks.
+    auto v_tail = [&](const Item& it_, int j_, uint32_t vst_) -> int {
+      int seg, krow0, nvalid;
+      tile_info(it_, j_, seg, krow0, nvalid);
+      nvalid = uniform(nvalid);
+      if (nvalid >= kTileN) return 8;
+      const int r1 = (nvalid + 15) & ~15;
+      for (int idx = lane; idx < (r1 - nvalid) * 16; idx += 32) {
+        const int row = nvalid + (idx >> 4), c = idx & 15;   // 16-byte pieces: 0-7 in hd block 0, 8-15 in block 1
+        *reinterpret_cast<uint4*>(smem_kv + vst_ * kTileBytes + (c >> 3) * kBlkBytes + row * 128 + (c & 7) * 16) =
+            make_uint4(0, 0, 0, 0);
+      }
+      fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's (async proxy) operand reads
+      __syncwarp();
+      return r1 >> 4;
     };
     for (int round = 0; round * static_cast<int>(gridDim.x) < total_items; ++round) {
       const int item = round * static_cast<int>(gridDim.x) +
@@ -627,8 +649,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_wait_warp(&bar->kv_full[stage], phase);
       uint32_t vst = stage;
       advance();
+      int nks = v_tail(it, 0, vst);   // k-step count of the V tile in `vst`
       mbar_wait_warp(&bar->o_free[0], o_free_parity);
-      pv(tO0, tS0, 0, p_phase0, vst, 0);
+      pv(tO0, tS0, 0, p_phase0, vst, 0, nks);
       for (int i = 1; i < nt; ++i) {
         // K_i -> S0(i)   (P0(i-1) already consumed by the in-order PV0(i-1))
         mbar_wait_warp(&bar->kv_full[stage], phase);
@@ -646,7 +669,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         // O1 (+)= P1(i-1) V_{i-1} ; S1(i)
         if (i == 1) mbar_wait_warp(&bar->o_free[1], o_free_parity);
         if (tr && lane == 0) TRACE(2, i, 2);
-        pv(tO1, tS1, 1, p_phase1, vst, i > 1 ? 1u : 0u);
+        pv(tO1, tS1, 1, p_phase1, vst, i > 1 ? 1u : 0u, nks);
         if (elect_one()) {
           tc_commit(&bar->kv_empty[vst]);
           issue_qk(tS1, q1_desc, desc_kmajor(kv_addr + kst * kTileBytes));
@@ -660,15 +683,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_wait_warp(&bar->kv_full[stage], phase);
         vst = stage;
         advance();
+        nks = v_tail(it, i, vst);
         if (tr && lane == 0) TRACE(2, i, 4);
-        pv(tO0, tS0, 0, p_phase0, vst, 1);
+        pv(tO0, tS0, 0, p_phase0, vst, 1, nks);
         if (tr && lane == 0) { TRACE(2, i, 5); TRACE(2, i, 6); }
       }
       // O1 (+)= P1(nt-1) V_{nt-1}
       if (nt == 1) mbar_wait_warp(&bar->o_free[1], o_free_parity);
       if (elect_one()) tc_commit(&bar->o_full[0]);   // everything up to PV0(nt-1)
       __syncwarp();
-      pv(tO1, tS1, 1, p_phase1, vst, nt > 1 ? 1u : 0u);
+      pv(tO1, tS1, 1, p_phase1, vst, nt > 1 ? 1u : 0u, nks);
       if (elect_one()) {
         tc_commit(&bar->kv_empty[vst]);
         tc_commit(&bar->o_full[1]);

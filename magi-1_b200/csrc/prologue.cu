@@ -15,6 +15,13 @@
 
 namespace magi {
 
+// 16-byte store to an NVSwitch multicast (multimem) address: the switch replicates it to every GPU of the group.
+__device__ __forceinline__ void multimem_st_v4(void* mc_ptr, const uint4& v) {
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_ptr), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+               : "memory");
+}
+
 namespace {
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* v) {
@@ -352,7 +359,14 @@ __global__ void __launch_bounds__(kRingThreads, MAGI_PRO_RING_BLOCKS) prologue_r
             // fused K/V all-gather: the same 16-byte stores, once per rank of the group (own buffer included), over
             // NVLink peer memory; row = (chunk, this rank's stripe offset + row in stripe)
             const int64_t off = grow * out_tstride + h * out_hstride + (type == 2 ? 128 : 0);
-            for (int c = 0; c < p.gather_peers; ++c) store(reinterpret_cast<__nv_bfloat16*>(p.peer_kv[c]) + off);
+            if (p.gather_multicast) {
+              // NVSwitch multicast mapping: multimem.st (an ordinary st to a multimem address is undefined in the PTX ISA)
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.peer_kv[0]) + off;
+              multimem_st_v4(dst + e0, pa);
+              multimem_st_v4(dst + e1, pb);
+            } else {
+              for (int c = 0; c < p.gather_peers; ++c) store(reinterpret_cast<__nv_bfloat16*>(p.peer_kv[c]) + off);
+            }
           }
         } else {
           // all-to-all SEND layout "(cp seq) hn hd" in one local buffer, or - fused all-to-all - straight into the

@@ -26,6 +26,7 @@ struct PrologueParams {
   int64_t peer_row_offset;
   // fused K/V all-gather (cp_ring_kv): peer_kv[0 .. gather_peers) are the ranks' gathered in-flight K/V buffers
   int gather_peers;
+  int gather_multicast;   // peer_kv[0] is a multimem (NVSwitch multicast) address: store with multimem.st
   int64_t gather_rows_per_chunk, gather_chunk_stride, gather_row_offset;
 };
 

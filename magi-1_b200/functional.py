@@ -73,8 +73,11 @@ def attn_ranges(
     num_sms: int = 0,
     proj_input: Optional[Tuple[torch.Tensor, int, int]] = None,
     peer_out: Optional[Tuple[Sequence[int], Sequence[int], int, int]] = None,
+    kernel: int = 0,
 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Range-masked attention over keys = concat(k_cache, k_new) without materialising the concatenation.
+
+    kernel: 0 = library default, 1 = attn_fwd_kernel, 2 = attn_pair_kernel (experimental CTA-pair kernel).
 
     peer_out = (pointers, row_bounds, head_offset, heads_total): fused Ulysses output all-to-all. Query row g of
     local head h is stored into the (rows_rho, heads_total, 128) bf16 buffer at pointers[rho] of the rank rho with
@@ -185,6 +188,7 @@ def attn_ranges(
     a.softmax_scale = float(softmax_scale) if softmax_scale is not None else -1.0
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 4
     a.num_sms = num_sms
+    a.kernel = kernel
     if peer_out is not None:
         a.num_peers, a.peer_head_offset = len(ptrs), head_off
         for i, ptr in enumerate(ptrs):
@@ -298,6 +302,7 @@ def qk_norm_rope(
     peer_heads: Optional[Tuple[int, int]] = None,
     gather_kv_out: Optional[Sequence[int]] = None,
     gather_geometry: Optional[Tuple[int, int, int]] = None,
+    gather_multicast: bool = False,
 ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """Fused per-head LayerNorm(w+1, b) -> NeoX RoPE on 96 of 128 dims -> bf16, writing q in attention layout and
     [K|V] packed (rows, Hkv, 256), optionally also appending to the KV cache (dit_module.py:953-996, 918-929).
@@ -413,6 +418,9 @@ def qk_norm_rope(
             a.peer_kv_out[i] = peer_kv_out[i] if peer_kv_out is not None else None
     if gather:
         a.gather_peers = len(gather_kv_out)
+        if gather_multicast and len(gather_kv_out) != 1:
+            raise ValueError("gather_multicast takes exactly one pointer: the multicast mapping of the buffer")
+        a.gather_multicast = 1 if gather_multicast else 0
         a.gather_rows_per_chunk, a.gather_chunk_stride, a.gather_row_offset = gather_geometry
         a.kv_out_token_stride, a.kv_out_head_stride = num_heads_kv * 2 * HEAD_DIM, 2 * HEAD_DIM
         for i, ptr in enumerate(gather_kv_out):
@@ -597,4 +605,31 @@ def apply_rotary_emb(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, inte
     a.cos, a.sin = cos.data_ptr(), sin.data_ptr()
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().magi_apply_rotary_emb(C.byref(a), _stream()), "magi_apply_rotary_emb")
+    return out
+
+
+def mlp_activation(x: torch.Tensor, gated: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The activation between fc1 and fc2 of CustomMLP (dit_module.py:541-549) as ONE memory-bound launch:
+    gated -> `flashinfer.activation.silu_and_mul(x)` = silu(x[..., :f]) * x[..., f:] with a single rounding to bf16
+    (the 24B model's SwiGLU); otherwise `torch.nn.functional.gelu(x)` (erf form, the 4.5B model).
+    x: (..., 2 f) or (..., f) bf16 CUDA tensor, contiguous in the last dimension; returns (..., f) bf16."""
+    if not x.is_cuda or x.dtype != torch.bfloat16:
+        raise ValueError("x must be a bfloat16 CUDA tensor (this package has no CPU path)")
+    width = x.shape[-1]
+    f = width // 2 if gated else width
+    if (gated and width % 2) or f % 8:
+        raise ValueError("the activation width must be a multiple of 8")
+    x2 = x.reshape(-1, width)
+    if x2.numel() > 0 and x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    rows = x2.shape[0]
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (f,), dtype=torch.bfloat16, device=x.device)
+    o2 = out.view(-1, f)
+    if o2.shape[0] != rows or o2.stride(1) != 1:
+        raise ValueError("out must be a (..., f) bf16 tensor contiguous in the last dimension")
+    if rows > 0:
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().magi_mlp_activation(x2.data_ptr(), x2.stride(0), o2.data_ptr(), o2.stride(0), rows, f,
+                                                      1 if gated else 0, _stream()), "magi_mlp_activation")
     return out

@@ -59,12 +59,9 @@ class CustomMLP(nn.Module):
 
     def forward(self, hidden_states):
         x = self.linear_fc1(self.layer_norm(hidden_states))
-        if self.model_config.gated_linear_unit:
-            a, b = x.chunk(2, dim=-1)
-            x = torch.nn.functional.silu(a) * b
-        else:
-            x = torch.nn.functional.gelu(x)
-        return self.linear_fc2(x)
+        # one launch of magi_mlp_activation: silu_and_mul (single rounding, like the flashinfer kernel the reference
+        # calls) or erf-GELU
+        return self.linear_fc2(F.mlp_activation(x, self.model_config.gated_linear_unit))
 
 
 class TransformerLayer(nn.Module):

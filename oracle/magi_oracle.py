@@ -474,6 +474,21 @@ def gelu(x: np.ndarray) -> np.ndarray:
     return bf16_round(F32(0.5) * x * (F32(1.0) + erf(x / np.sqrt(F32(2.0))).astype(F32)))
 
 
+def silu_and_mul(x: np.ndarray) -> np.ndarray:
+    """flashinfer.activation.silu_and_mul (dit_module.py:546; third-party CUDA kernel absent from /root/reference,
+    flashinfer pinned nowhere in requirements.txt - published definition): the last dimension holds [a | b];
+    out = silu(a) * b in fp32, ONE rounding to the storage type."""
+    x = x.astype(F32)
+    f = x.shape[-1] // 2
+    a, b = x[..., :f], x[..., f:]
+    return bf16_round(a / (F32(1.0) + np.exp(-a)) * b)
+
+
+def mlp_activation(x: np.ndarray, gated: bool) -> np.ndarray:
+    """CustomMLP.forward between fc1 and fc2, dit_module.py:545-548."""
+    return silu_and_mul(x) if gated else gelu(x)
+
+
 def fully_parallel_attention(w, hs, kvs, rope, cache, has_inf, slice_point, dn, clip, np_q_range, np_k_range, y_index,
                              update_kv_cache, fwd_extra_1st_chunk=False, distill_nearly_clean_chunk=False, pre=""):
     """FullyParallelAttention.forward with cp_strategy "none", dit_module.py:1138-1174, composed from the pieces above.
@@ -524,11 +539,7 @@ def transformer_layer(w, hs, condition, condition_map, kvs, rope, cache, has_inf
                            w["self_attn_post_norm.bias"])
     m = bf16_round(layer_norm(x1, w["mlp.layer_norm.weight"], w["mlp.layer_norm.bias"], 1e-6, zero_centered_gamma=False))
     m = linear_bf16(m, w["mlp.linear_fc1.weight"])
-    if gated_linear_unit:
-        a, bb = m[..., :m.shape[-1] // 2], m[..., m.shape[-1] // 2:]
-        m = bf16_round(bf16_round(a / (F32(1.0) + np.exp(-a))) * bb)
-    else:
-        m = gelu(m)
+    m = mlp_activation(m, gated_linear_unit)
     m = linear_bf16(m, w["mlp.linear_fc2.weight"])
     return bias_modulate_add(m, x1, condition_map, gate_mlp, w["mlp_post_norm.weight"], w["mlp_post_norm.bias"])
 

@@ -168,6 +168,14 @@ def bias_modulate_add(x, residual, condition_map, gate, post_norm, out=None):
 _PEER_TENSORS = []
 
 
+def mlp_activation(x, gated, out=None):
+    r = _bf(O.mlp_activation(_np(x), gated))
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r
+
+
 def fake_ptr(t: torch.Tensor) -> int:
     assert t.is_contiguous() and t.dtype == torch.bfloat16
     _PEER_TENSORS.append(t.view(-1))

@@ -34,3 +34,18 @@ def test_flop_accounting_matches_survey():
     assert cross_f == 4 * 128 * 24 * 9360 * (50 + 512 + 512 + 512)
     w4 = bench.WORKLOADS["cfg4"]
     assert abs(bench.attn_flops(w4)[0] / 1e12 - 172.0) < 0.1
+
+
+def test_both_arms_name_the_same_config():
+    """`config` names the workload and is identical in both arms (ours / --impl reference), so the driver's
+    same_config check can hold; everything measured lives elsewhere in the line."""
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    a = argparse.Namespace(cp_mode="fused", overlap_degree=1, workload="cfg2", gpus=1)
+    c1 = bench.static_config(a, bench.WORKLOADS["cfg2"], 1)
+    assert c1 == bench.static_config(a, bench.WORKLOADS["cfg2"], 1)
+    assert {"workload", "name", "parallelism", "step", "flops_per_step"} <= set(c1) and "model" not in c1
+    assert "ulysses" in bench.static_config(a, bench.WORKLOADS["cfg2"], 8)["parallelism"]
+    a.cp_mode = "ring"
+    assert "multimem" in bench.static_config(a, bench.WORKLOADS["cfg2"], 2)["parallelism"]

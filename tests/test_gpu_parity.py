@@ -94,6 +94,79 @@ def test_attn_ranges_vs_oracle(F, case):
     assert np.abs(lse[fin] - ref_lse[fin]).max() < 1e-3
 
 
+@pytest.mark.parametrize("case", RANGE_CASES, ids=[c[0] for c in RANGE_CASES])
+def test_pair_kernel_vs_oracle_and_single_kernel(F, case):
+    """The CTA-pair kernel (attn_pair.cu: cta_group::2 MMAs, double-buffered S, quad-fragment softmax; `kernel=2`) on
+    the same range layouts: against the fp32 oracle with the same tolerance, and against the default kernel (same
+    math in a different association order: a few bf16 ulps)."""
+    name, Tq, Tk, Hq, Hkv, qr, kr, cache_len = case
+    q, kv = rnd((Tq, Hq, 128), 1), rnd((Tk, Hkv, 256), 2)
+    ref, ref_lse = O.attn_ranges(q, kv[..., :128], kv[..., 128:], qr, kr, round_output=False)
+    tq, tkv = bf(q), bf(kv)
+    kc = vc = None
+    if cache_len:
+        kc, vc = tkv[:cache_len, :, :128], tkv[:cache_len, :, 128:]
+    kn, vn = tkv[cache_len:, :, :128], tkv[cache_len:, :, 128:]
+    outs = {}
+    for kern in (1, 2):
+        out, lse = F.attn_ranges(tq, kn, vn, i32(qr), i32(kr), k_cache=kc, v_cache=vc, zero_fill=True, kernel=kern)
+        check_attn(out, ref, f"{name} kernel {kern}")
+        fin = np.isfinite(ref_lse)
+        assert np.abs(lse.cpu().numpy()[fin] - ref_lse[fin]).max() < 1e-3
+        outs[kern] = out.float()
+    assert (outs[1] - outs[2]).abs().max().item() <= 1.6e-2
+
+
+def test_pair_kernel_rescale_path_and_many_items(F):
+    """Pair kernel: rows whose running max jumps by far more than 2^8 (O rescaled in TMEM through the 16x256b fragment
+    shape, behind the P V completion barrier) and a launch with several items per CTA pair and both K/V segments."""
+    Tq, Tk, Hq, Hkv = 300, 1100, 4, 2
+    q, k, v = rnd((Tq, Hq, 128), 1), rnd((Tk, Hkv, 128), 2), rnd((Tk, Hkv, 128), 3)
+    ramp = np.ones(Tk, dtype=np.float32)
+    ramp[256:384] = 6.0
+    ramp[640:700] = 14.0
+    ramp[1000:] = 0.25
+    k = O.bf16_round(k * ramp[:, None, None])
+    q[::7] = 0.0
+    ref, ref_lse = O.attn_ranges(q, k, v, [[0, 300]], [[0, 1100]], round_output=False)
+    out, lse = F.attn_ranges(bf(q), bf(k), bf(v), i32([[0, 300]]), i32([[0, 1100]]), kernel=2)
+    check_attn(out, ref, "pair kernel, growing max")
+    assert np.abs(lse.cpu().numpy() - ref_lse).max() < 2e-3
+    qr = [[i * 520, (i + 1) * 520] for i in range(6)]
+    kr = [[0, (i + 1) * 520] for i in range(6)]
+    q, kv = rnd((3120, 24, 128), 5), rnd((3120, 8, 256), 6)
+    ref, _ = O.attn_ranges(q, kv[..., :128], kv[..., 128:], qr, kr, round_output=False)
+    tkv = bf(kv)
+    out, _ = F.attn_ranges(bf(q), tkv[1000:, :, :128], tkv[1000:, :, 128:], i32(qr), i32(kr), k_cache=tkv[:1000, :, :128],
+                           v_cache=tkv[:1000, :, 128:], kernel=2, num_sms=8)
+    check_attn(out, ref, "pair kernel, 888 items on 4 pairs")
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_padding_rows_inside_the_view_may_be_nan(F, kernel):
+    """K / V rows that lie inside the tensor views but outside every key range (torch.empty padding: here NaN) must
+    not reach the output: masked scores are forced to -inf whatever K holds, the 16-key groups of a partial last tile
+    past the range are never multiplied, and the rows of the straddling group are zeroed in shared memory
+    (flash-attn's predicated loads never read such rows). kernel 2 (experimental pair kernel) keeps
+    the documented precondition instead: finite padding."""
+    Tq, Tk, Hq, Hkv = 400, 1000, 4, 2
+    qr, kr = [[0, 130], [130, 400]], [[7, 300], [450, 777]]
+    q, kv = rnd((Tq, Hq, 128), 31), rnd((Tk, Hkv, 256), 32)
+    ref, _ = O.attn_ranges(q, kv[..., :128], kv[..., 128:], qr, kr, round_output=False)
+    bad = kv.copy()
+    fill = np.nan if kernel == 1 else 1e4
+    for a, b in ((0, 7), (300, 450), (777, 1000)):
+        bad[a:b] = fill
+    tkv = bf(bad)
+    out, _ = F.attn_ranges(bf(q), tkv[..., :128], tkv[..., 128:], i32(qr), i32(kr), kernel=kernel)
+    assert bool(torch.isfinite(out.float()).all())
+    check_attn(out, ref, "NaN padding" if kernel == 1 else "finite padding")
+    # the same through the cache / new-token seam with the seam inside the padding
+    out2, _ = F.attn_ranges(bf(q), tkv[400:, :, :128], tkv[400:, :, 128:], i32(qr), i32(kr), k_cache=tkv[:400, :, :128],
+                            v_cache=tkv[:400, :, 128:], kernel=kernel)
+    check_attn(out2, ref, "padding across the seam")
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_attn_random_range_sets_vs_oracle(F, seed):
     """Randomised disjoint q ranges with arbitrary (overlapping, ragged) k ranges."""
@@ -455,6 +528,40 @@ def test_bias_modulate_add_sizes_vs_oracle(F, hidden, rows, xdt):
     got = out.float().cpu().numpy()
     tol = np.maximum(np.abs(ref), np.abs(got)) * 2.0 ** -7 + 1e-6
     assert (np.abs(got - ref) <= tol).all(), float(np.abs(got - ref).max())
+
+
+@pytest.mark.parametrize("gated,rows,f", [(True, 1000, 16384), (False, 777, 12288), (True, 3, 8), (False, 1, 4096)])
+def test_mlp_activation_vs_oracle_and_libraries(F, gated, rows, f):
+    """magi_mlp_activation (fused SwiGLU / GELU between fc1 and fc2, dit_module.py:545-548) vs the oracle (<= 1 bf16
+    ulp: fast-exp vs exp), and against what the reference itself calls: flashinfer.activation.silu_and_mul (when the
+    wheel imports) and torch.nn.functional.gelu."""
+    x = rnd((rows, (2 if gated else 1) * f), 77, scale=2.5)
+    ref = O.mlp_activation(x, gated)
+    tx = bf(x)
+    out = F.mlp_activation(tx, gated)
+    assert out.shape == (rows, f) and out.dtype == torch.bfloat16
+    got = out.float().cpu().numpy()
+    # <= 1 bf16 ulp; 1 + erf(x / sqrt 2) cancels for x << 0, where implementations differ in the last bit more often
+    assert np.all(np.abs(got - ref) <= np.abs(ref) * 2.0 ** -6 + 1e-5)
+    assert (got != ref).mean() < (0.01 if gated else 0.05)
+    if gated:
+        try:
+            import flashinfer
+            lib = flashinfer.activation.silu_and_mul(tx)
+        except Exception:
+            lib = None
+    else:
+        lib = torch.nn.functional.gelu(tx)
+    if lib is not None:
+        d = (out.float() - lib.float()).abs()
+        assert bool((d <= lib.float().abs() * 2.0 ** -6 + 1e-5).all())
+        assert float((d > 0).float().mean()) < (0.01 if gated else 0.05)
+    # strided input rows (a view into a wider buffer) and a caller-provided output
+    wide = torch.zeros(rows, tx.shape[1] + 64, dtype=torch.bfloat16, device="cuda")
+    wide[:, :tx.shape[1]] = tx
+    out2 = torch.empty(rows, f, dtype=torch.bfloat16, device="cuda")
+    F.mlp_activation(wide[:, :tx.shape[1]], gated, out=out2)
+    assert torch.equal(out2, out)
 
 
 def test_full_attention_block_matches_reference_golden():

@@ -82,3 +82,20 @@ def test_constant_v_gives_constant_rows_and_gqa_maps_by_group(case):
         if b > a and d > c:
             for h in range(hq):          # softmax weights sum to 1: every covered row equals its kv head's constant
                 np.testing.assert_allclose(out[a:b, h], h // g + 1.0, rtol=0, atol=2e-5)
+
+
+def test_mlp_activation_follows_the_published_definitions():
+    """silu_and_mul (flashinfer, dit_module.py:546): act(float(a)) * float(b), one rounding; gelu: torch's erf form on
+    a bf16 tensor. Checked against torch on the CPU (the same formulas through another implementation)."""
+    import torch
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(37, 2 * 96, generator=g) * 3).to(torch.bfloat16)
+    a, b = x[:, :96].float(), x[:, 96:].float()
+    want = (torch.nn.functional.silu(a) * b).to(torch.bfloat16).float().numpy()
+    got = O.mlp_activation(x.float().numpy(), True)
+    assert np.abs(got - want).max() <= np.abs(want).max() * 2.0 ** -7   # <= 1 bf16 ulp (exp implementations differ)
+    assert (got != want).mean() < 0.01
+    want = torch.nn.functional.gelu(x).float().numpy()
+    got = O.mlp_activation(x.float().numpy(), False)
+    # 1 + erf(x / sqrt 2) cancels for x << 0: implementations differ in the last bf16 bit on a few per cent of elements
+    assert (got != want).mean() < 0.05 and np.all(np.abs(got - want) <= np.abs(want) * 2.0 ** -6 + 1e-5)
