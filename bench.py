@@ -221,6 +221,7 @@ class HotPath:
         self.core_out = torch.empty(self.S_loc, Hq, 128, dtype=torch.bfloat16, device=device)
         self.x_out = torch.empty(self.S_loc, Hq, 128, dtype=torch.bfloat16, device=device)
         self.attn_events = []
+        self._plans = {}
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.inputs.values())
         self.d2h_bytes = 2 * self.core_out.numel() * 2
 
@@ -237,7 +238,8 @@ class HotPath:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         F.attn_ranges(q, kv[..., :128], kv[..., 128:], self.q_ranges, self.k_ranges, k_cache=kc, v_cache=vc,
-                      out=self.core_out, return_lse=False)
+                      out=self.core_out, return_lse=False,
+                      plan=self.plan("self", q, self.start + kv.shape[0], self.q_ranges, self.k_ranges))
         if timed_events:
             e1.record()
             self.attn_events.append((e0, e1))
@@ -254,7 +256,8 @@ class HotPath:
     def cross_attend(self, prepared):
         xq, xkv = prepared
         self.F.attn_ranges(xq, xkv[..., :128], xkv[..., 128:], self.x_q_ranges, self.x_k_ranges, out=self.x_out,
-                           return_lse=False)
+                           return_lse=False,
+                           plan=self.plan("cross", xq, xkv.shape[0], self.x_q_ranges, self.x_k_ranges))
 
     def cross(self, inp):
         self.cross_attend(self.cross_prepare(inp))
@@ -285,7 +288,8 @@ class HotPath:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
             F.attn_ranges(qg, kg, vg, self.q_ranges, self.k_ranges, k_cache=None if kc is None else kc[:, a:b],
-                          v_cache=None if vc is None else vc[:, a:b], out=out, return_lse=False)
+                          v_cache=None if vc is None else vc[:, a:b], out=out, return_lse=False,
+                          plan=self.plan("self", qg, self.start + kg.shape[0], self.q_ranges, self.k_ranges))
             if timed_events:
                 e1.record()
                 self.attn_events.append((e0, e1))
@@ -320,7 +324,8 @@ class HotPath:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         F.attn_ranges(ws.q, kv[..., :128], kv[..., 128:], self.q_ranges, self.k_ranges, k_cache=kc, v_cache=vc,
-                      return_lse=False, peer_out=(ws.out_ptrs, self.bounds, self.head_off, w["Hq"]))
+                      return_lse=False, peer_out=(ws.out_ptrs, self.bounds, self.head_off, w["Hq"]),
+                      plan=self.plan("self", ws.q, self.start + kv.shape[0], self.q_ranges, self.k_ranges))
         if timed_events:
             e1.record()
             self.attn_events.append((e0, e1))
@@ -381,7 +386,8 @@ class HotPath:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         F.attn_ranges(q, kv[..., :128], kv[..., 128:], self.stripe_q_ranges, self.k_ranges, k_cache=kc, v_cache=vc,
-                      out=self.core_out, return_lse=False)
+                      out=self.core_out, return_lse=False,
+                      plan=self.plan("self", q, self.start + kv.shape[0], self.stripe_q_ranges, self.k_ranges))
         if timed_events:
             e1.record()
             self.attn_events.append((e0, e1))
@@ -389,12 +395,22 @@ class HotPath:
 
     ulysses_overlap_degree = 1
 
+    def plan(self, kind, q, total_k, qr, kr):
+        """The work list of a range table is built ONCE per step (= per denoise forward, all layers share the ranges:
+        magi_attn_plan) and reused by every layer's launch."""
+        key = (kind, q.shape[1], q.shape[0], total_k)
+        pl = self._plans.get(key)
+        if pl is None:
+            pl = self._plans[key] = self.F.attn_plan(qr, kr, num_heads_q=q.shape[1], total_q=q.shape[0], total_k=total_k)
+        return pl
+
     def layer_fn(self):
         return (self.layer_cp_ring_fused if self.ring_fused else self.layer_cp_ring if self.ring else
                 self.layer_cp_fused if self.fused else self.layer_cp) if self.cp > 1 else self.layer
 
     def step(self, timed_events=False):
         fn = self.layer_fn()
+        self._plans = {}
         for l in range(self.w["layers"]):
             fn(l, timed_events)
 
@@ -479,6 +495,27 @@ def dit_step_leg(w, dev, world, rank, steps, max_over_ranks, barrier):
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    # the same stack as ONE CUDA graph per forward signature (EngineConfig.enable_cuda_graph, cuda_graph.py)
+    graph_ms = graph_note = None
+    if world == 1:
+        from magi_b200.cuda_graph import GraphedLayerStack
+        ec.enable_cuda_graph = True
+        stack = GraphedLayerStack(layers, ec)
+        for _ in range(2):
+            out_g = stack(hs, cond, cmap, y, rope, inf, meta)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(steps):
+            out_g = stack(hs, cond, cmap, y, rope, inf, meta)
+        g1.record()
+        barrier()
+        if stack.disabled_reason is None:
+            graph_ms = max_over_ranks(g0.elapsed_time(g1)) / steps
+            graph_note = "bit-identical to eager" if torch.equal(out_g, out) else "DIFFERS from eager"
+        else:
+            graph_note = "capture failed, ran eagerly: " + stack.disabled_reason
+        del stack
     h, f = mc.hidden_size, mc.ffn_hidden_size
     per_tok = 2 * h * (2 * w["Hq"] * 128 + 2 * w["Hkv"] * 128) + 2 * (2 * w["Hq"] * 128) * h \
         + 2 * h * f * (3 if mc.gated_linear_unit else 2)
@@ -488,7 +525,8 @@ def dit_step_leg(w, dev, world, rank, steps, max_over_ranks, barrier):
     assert bool(torch.isfinite(out.float()).all())
     del layers
     torch.cuda.empty_cache()
-    return {"ms_per_step": round(ms, 2), "layers": w["layers"], "model": "MAGI-1 24B" if big else "MAGI-1 4.5B",
+    return {"ms_per_step": round(ms, 2), "graph_ms_per_step": None if graph_ms is None else round(graph_ms, 2),
+            "graph_note": graph_note, "layers": w["layers"], "model": "MAGI-1 24B" if big else "MAGI-1 4.5B",
             "tflops_total": round(total / (ms * 1e-3) / 1e12, 1), "gemm_tflop_per_step": round(gemm / 1e12, 1),
             "attn_tflop_per_step": round((self_f + cross_f) * w["layers"] / 1e12, 1),
             "what": "all transformer blocks of one denoise forward: attention hot path (own kernels) + cuBLAS GEMMs + "
@@ -642,27 +680,52 @@ class Ctx:
         return float(t.item())
 
 
-def timed_leg(cx, hp, steps, warm, sample_clocks=True):
-    """W warm-up steps, then exactly `steps` steps between barrier + synchronize, CUDA events, max over ranks."""
+def timed_leg(cx, hp, steps, warm, graph=False):
+    """W warm-up steps, then exactly `steps` steps between barrier + synchronize, CUDA events, max over ranks.
+    graph=True: the step is captured ONCE into a CUDA graph after the warm-up (every launch of the hot path is
+    capturable: no host reads, no syncs) and the timed region replays it `steps` times; the per-launch times of the
+    self-attention kernel (roofline) then come from two eager steps with events right after the timed region."""
     from magi_b200 import _lib
     torch = cx.torch
     for _ in range(warm):
         hp.step()
     cx.barrier()
+    replay = None
+    if graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            hp.step()
+        torch.cuda.current_stream().wait_stream(side)
+        replay = g.replay
+        replay()
+        cx.barrier()
     hp.attn_events = []
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(cx.local) as clk:
         e0.record()
         for _ in range(steps):
-            hp.step(timed_events=True)
+            if replay is not None:
+                replay()
+            else:
+                hp.step(timed_events=True)
         e1.record()
         cx.barrier()
     launches = _lib.launch_count() - l0
     ms_total = cx.max_over_ranks(e0.elapsed_time(e1))
+    events_steps = steps
+    if replay is not None:
+        l1 = _lib.launch_count()
+        events_steps = 2
+        for _ in range(events_steps):
+            hp.step(timed_events=True)
+        cx.barrier()
+        launches = (_lib.launch_count() - l1) // events_steps * steps   # what one replayed step launches, x steps
     attn_ms = [a.elapsed_time(b) for a, b in hp.attn_events]
     return dict(ms_step=ms_total / steps, ms_total=ms_total, attn_ms=attn_ms, launches=int(launches),
-                clocks=clk.summary())
+                clocks=clk.summary(), events_steps=events_steps, graph=replay is not None)
 
 
 def e2e_leg(cx, hp, steps):
@@ -805,6 +868,8 @@ def main():
     ap.add_argument("--no-extra-legs", action="store_true",
                     help="N > 1: skip the extra (not-the-value) legs: ring-KV on the same workload, and configs[3] "
                          "(24B / 720p) under Ulysses and ring-KV")
+    ap.add_argument("--graph", default="off", choices=["on", "off"],
+                    help="replay the hot-path step from one CUDA graph in the timed region (launch-bound workloads)")
     ap.add_argument("--profile", action="store_true",
                     help="short run for ncu: no e2e / CPU legs, warm-up exactly as given (numbers are not bench values)")
     args = ap.parse_args()
@@ -840,11 +905,11 @@ def main():
 
     # ---- device-resident timing (value)
     n_warm = args.warmup if args.profile else max(args.warmup, 3)
-    t = timed_leg(cx, hp, args.steps, n_warm)
+    t = timed_leg(cx, hp, args.steps, n_warm, graph=args.graph == "on")
     ms_step, ms_total, attn_ms = t["ms_step"], t["ms_total"], t["attn_ms"]
     value = step_flops / (ms_step * 1e-3) / 1e12
     attn_avg_ms = sum(attn_ms) / len(attn_ms)
-    launch_flops = self_f / world / (len(attn_ms) / (args.steps * w["layers"]))   # per self-attention launch
+    launch_flops = self_f / world / (len(attn_ms) / (t["events_steps"] * w["layers"]))   # per self-attention launch
     achieved = launch_flops / (attn_avg_ms * 1e-3) / 1e12
     peaks = load_peaks()
 
@@ -917,7 +982,10 @@ def main():
                          "peak_source": peaks["source"] + ", sustained (kernel timed inside a long step); burst "
                                         f"{peaks['burst']} -> frac {achieved / peaks['burst']:.3f}",
                          "flops_per_launch": launch_flops, "avg_launch_ms": round(attn_avg_ms, 4),
-                         "share_of_step": round(sum(attn_ms) / ms_total, 3),
+                         "share_of_step": round(sum(attn_ms) / t["events_steps"] / ms_step, 3),
+                         "step_launch_mode": "one CUDA graph replay per step; kernel times from 2 eager steps after "
+                                             "the timed region" if t["graph"] else "eager launches, events in the "
+                                             "timed region",
                          "pct_of_bf16_peak_burst": round(100 * value / world / peaks["burst"], 1),
                          "pct_of_bf16_peak_sustained": round(100 * value / world / peaks["sustained"], 1),
                          "pct_of_bf16_datasheet_2250": round(100 * value / world / 2250.0, 1)},

@@ -104,10 +104,18 @@ typedef struct magi_attn_args {
    * 1 = attn_fwd_kernel (one CTA per SM, two query tiles per CTA), 2 = attn_pair_kernel (CTA pairs, cta_group::2;
    * experimental: correct, measured slower - DESIGN.md section 4.1). Same results within the documented tolerance. */
   int32_t kernel;
+  /* plan_ready != 0: `workspace` already holds the work list magi_attn_plan built for exactly these ranges,
+   * num_heads_q and token counts; magi_attn_fwd then launches the attention kernel only (one launch instead of two).
+   * The ranges of a denoise forward are the same for every layer (dit_model.py:215-259): plan once, reuse 34 / 48 times. */
+  int32_t plan_ready;
 } magi_attn_args;
 
 MAGI_API size_t magi_attn_workspace_bytes(int32_t n_ranges);
 MAGI_API int magi_attn_fwd(const magi_attn_args* args, void* stream);
+/* Builds the work list of magi_attn_fwd (ranges clamped to the token counts, sorted longest-key-range first, prefix sums
+ * of the 256-row work items) into args->workspace, on `stream`, without host reads. Uses only the range pointers,
+ * n_ranges, num_heads_q, q.tokens, k_a.tokens + k_b.tokens and workspace / workspace_bytes of `args`. */
+MAGI_API int magi_attn_plan(const magi_attn_args* args, void* stream);
 
 /*
  * Fused QK-LayerNorm(+1p) + RoPE-96 + layout prologue.

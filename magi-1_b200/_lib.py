@@ -16,6 +16,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 EXPORTS = (
     "magi_attn_workspace_bytes",
     "magi_attn_fwd",
+    "magi_attn_plan",
     "magi_qk_norm_rope_fwd",
     "magi_kv_cache_append",
     "magi_lse_merge",
@@ -72,6 +73,7 @@ class MagiAttnArgs(C.Structure):
         ("peer_out", C.c_void_p * MAX_PEERS),
         ("peer_row_bounds", C.c_int64 * (MAX_PEERS + 1)),
         ("kernel", C.c_int32),
+        ("plan_ready", C.c_int32),
     ]
 
 
@@ -178,6 +180,8 @@ def lib() -> C.CDLL:
     L.magi_attn_workspace_bytes.argtypes = [C.c_int32]
     L.magi_attn_fwd.restype = C.c_int
     L.magi_attn_fwd.argtypes = [C.POINTER(MagiAttnArgs), C.c_void_p]
+    L.magi_attn_plan.restype = C.c_int
+    L.magi_attn_plan.argtypes = [C.POINTER(MagiAttnArgs), C.c_void_p]
     L.magi_qk_norm_rope_fwd.restype = C.c_int
     L.magi_qk_norm_rope_fwd.argtypes = [C.POINTER(MagiPrologueArgs), C.c_void_p]
     L.magi_kv_cache_append.restype = C.c_int
@@ -210,6 +214,29 @@ def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = lib().magi_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"{what}: {msg}")
+
+
+def source_hash() -> str:
+    """sha256 (first 16 hex digits) over the library's sources, computed the way csrc/Makefile stamps it into
+    magi_build_info(): sorted *.cu and *.cuh of csrc/, then include/magi_attn.h."""
+    import glob
+    import hashlib
+    files = sorted(glob.glob(os.path.join(CSRC_DIR, "*.cu")) + glob.glob(os.path.join(CSRC_DIR, "*.cuh")),
+                   key=os.path.basename)
+    files.append(os.path.join(os.path.dirname(_HERE), "include", "magi_attn.h"))
+    h = hashlib.sha256()
+    for f in files:
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def binary_is_current() -> bool:
+    """True when the loaded library was built from the sources in the tree (variant builds selected through
+    MAGI_ATTN_LIB are exempt: they are built with other flags on purpose)."""
+    if os.environ.get("MAGI_ATTN_LIB"):
+        return True
+    return ("source " + source_hash()) in lib().magi_build_info().decode("utf-8", "replace")
 
 
 def launch_count() -> int:

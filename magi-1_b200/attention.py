@@ -155,6 +155,21 @@ class KVOffload:
         self.copy_stream.synchronize()
 
 
+def _shared_plan(holder, tag: str, heads_q: int, total_q: int, total_k: int, q_ranges, k_ranges):
+    """The attention work list (F.attn_plan) of one range table, built once per forward: `holder` is the per-forward
+    parameter object (PackedCoreAttnParams / PackedCrossAttnParams, the same instance for every layer of a denoise
+    forward, dit_model.py:301-337), on which the plans are kept. Layers 1.. reuse what layer 0 built."""
+    plans = holder.__dict__.get("_magi_plans")
+    if plans is None:
+        plans = {}
+        object.__setattr__(holder, "_magi_plans", plans)   # frozen dataclass: plain attribute, not a field
+    key = (tag, heads_q, total_q, total_k, q_ranges.data_ptr(), k_ranges.data_ptr())
+    plan = plans.get(key)
+    if plan is None:
+        plan = plans[key] = F.attn_plan(q_ranges, k_ranges, num_heads_q=heads_q, total_q=total_q, total_k=total_k)
+    return plan
+
+
 class FullyParallelAttention(nn.Module):
     def __init__(self, model_config: ModelConfig, engine_config: EngineConfig, layer_number: int):
         super().__init__()
@@ -372,8 +387,10 @@ class FullyParallelAttention(nn.Module):
             return dict(out=out if i is None else row(out, i))
 
         if bs == 1:
+            total_k = k_new.shape[0] + (0 if k_cache is None else k_cache.shape[0])
+            plan = _shared_plan(p, "core", query.shape[1], query.shape[0], total_k, p.q_range, p.k_range)
             F.attn_ranges(query, k_new, v_new, p.q_range, p.k_range, k_cache=k_cache, v_cache=v_cache,
-                          return_lse=False, **dest())
+                          return_lse=False, plan=plan, **dest())
             return out
         assert not (bs > 1 and meta_args.denoising_range_num > 1)
         assert k_cache is None
@@ -424,7 +441,12 @@ class FullyParallelAttention(nn.Module):
                 dst = dict(proj_input=(proj_buf.view(sq, b, -1)[:, i], 1, self.PROJ_GROUPS))
             else:
                 dst = dict(out=out[:, i])
-            F.attn_ranges(q_rows[i], kv_x[..., :F.HEAD_DIM], kv_x[..., F.HEAD_DIM:], qr, kr, return_lse=False, **dst)
+            plan = None
+            if b == 1 and qr.dtype == torch.int32 and qr.is_contiguous() and kr.is_contiguous():
+                plan = _shared_plan(cross_attn_params, "cross", q_rows[i].shape[1], q_rows[i].shape[0], kv_x.shape[0],
+                                    qr, kr)
+            F.attn_ranges(q_rows[i], kv_x[..., :F.HEAD_DIM], kv_x[..., F.HEAD_DIM:], qr, kr, return_lse=False,
+                          plan=plan, **dst)
         return None if proj_buf is not None else out.view(sq, b, Hq * F.HEAD_DIM)
 
     def cross_attention(self, mixed_qqkv, key_value_states, cross_attn_params: PackedCrossAttnParams, proj_buf=None):

@@ -48,6 +48,10 @@ int fail(const char* fmt, ...) {
 #define MAGI_DEFAULT_KERNEL_NAME "single"
 #endif
 
+#ifndef MAGI_SOURCE_HASH
+#define MAGI_SOURCE_HASH "unstamped"
+#endif
+
 #define MAGI_STR_(x) #x
 #define MAGI_STR(x) MAGI_STR_(x)
 
@@ -123,7 +127,7 @@ const char* magi_last_error(void) { return g_err; }
 
 const char* magi_build_info(void) {
   return "magi_attn sm_100a tcgen05/TMEM/TMA; default attention kernel: " MAGI_DEFAULT_KERNEL_NAME
-         "; built " __DATE__ " " __TIME__
+         "; source " MAGI_SOURCE_HASH "; built " __DATE__ " " __TIME__
 #ifdef __CUDACC_VER_MAJOR__
          "; nvcc " MAGI_STR(__CUDACC_VER_MAJOR__) "." MAGI_STR(__CUDACC_VER_MINOR__) "." MAGI_STR(__CUDACC_VER_BUILD__)
 #endif
@@ -194,9 +198,11 @@ int magi_attn_fwd(const magi_attn_args* a, void* stream_) {
   const int len_b = rkb == 2 ? 0 : (int)a->k_b.tokens;
   int* ws = reinterpret_cast<int*>(a->workspace);
 
-  MAGI_CUDA(magi::attn_setup_launch(a->q_ranges, a->k_ranges, a->cu_seqlens_q, a->cu_seqlens_k, a->n_ranges,
-                                    a->num_heads_q, (int)a->q.tokens, len_a + len_b, ws, stream));
-  g_launches++;
+  if (!a->plan_ready) {
+    MAGI_CUDA(magi::attn_setup_launch(a->q_ranges, a->k_ranges, a->cu_seqlens_q, a->cu_seqlens_k, a->n_ranges,
+                                      a->num_heads_q, (int)a->q.tokens, len_a + len_b, ws, stream));
+    g_launches++;
+  }
 
   magi::AttnKernelParams p;
   p.out = a->out;
@@ -234,6 +240,27 @@ int magi_attn_fwd(const magi_attn_args* a, void* stream_) {
   const CUtensorMap maps[5] = {tm_q, tm_ka, tm_va, tm_kb, tm_vb};
   if (use_pair) MAGI_CUDA(magi::attn_pair_launch(maps, p, sms, stream));
   else MAGI_CUDA(magi::attn_fwd_launch(maps, p, sms, stream));
+  g_launches++;
+  return 0;
+}
+
+int magi_attn_plan(const magi_attn_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MAGI_CHECK(a != nullptr, "args is NULL");
+  MAGI_CHECK(a->num_heads_q > 0 && a->n_ranges >= 0, "num_heads_q must be positive and n_ranges non-negative");
+  const bool by_ranges = a->q_ranges != nullptr && a->k_ranges != nullptr;
+  const bool by_cu = a->cu_seqlens_q != nullptr && a->cu_seqlens_k != nullptr;
+  MAGI_CHECK(by_ranges != by_cu, "give exactly one of (q_ranges,k_ranges) or (cu_seqlens_q,cu_seqlens_k)");
+  MAGI_CHECK(a->q.tokens >= 0 && a->k_a.tokens >= 0 && a->k_b.tokens >= 0 && a->q.tokens < (1ll << 31) &&
+                 a->k_a.tokens + a->k_b.tokens < (1ll << 31),
+             "token counts must be non-negative and fit int32");
+  if (a->n_ranges == 0) return 0;
+  MAGI_CHECK(a->workspace != nullptr && a->workspace_bytes >= magi_attn_workspace_bytes(a->n_ranges),
+             "workspace too small: need %zu bytes", magi_attn_workspace_bytes(a->n_ranges));
+  MAGI_CHECK((reinterpret_cast<uintptr_t>(a->workspace) & 15) == 0, "workspace must be 16-byte aligned");
+  MAGI_CUDA(magi::attn_setup_launch(a->q_ranges, a->k_ranges, a->cu_seqlens_q, a->cu_seqlens_k, a->n_ranges,
+                                    a->num_heads_q, (int)a->q.tokens, (int)(a->k_a.tokens + a->k_b.tokens),
+                                    reinterpret_cast<int*>(a->workspace), stream));
   g_launches++;
   return 0;
 }

@@ -56,6 +56,52 @@ def _ranges_arg(r: torch.Tensor, name: str) -> torch.Tensor:
     return r.contiguous()
 
 
+class AttnPlan:
+    """The device-side work list of one (ranges, num_heads_q, token counts) combination, built by `attn_plan` and
+    reusable by every `attn_ranges` call with the same combination - all layers of a denoise forward share their
+    ranges (dit_model.py:215-259), so the list is built once per forward instead of once per layer."""
+    __slots__ = ("ws", "n", "heads_q", "total_q", "total_k", "by_ranges", "_keep")
+
+    def matches(self, n, heads_q, total_q, total_k, by_ranges) -> bool:
+        return (self.n, self.heads_q, self.total_q, self.total_k, self.by_ranges) == (n, heads_q, total_q, total_k,
+                                                                                      by_ranges)
+
+
+def attn_plan(q_ranges: Optional[torch.Tensor] = None, k_ranges: Optional[torch.Tensor] = None, *,
+              cu_seqlens_q: Optional[torch.Tensor] = None, cu_seqlens_k: Optional[torch.Tensor] = None,
+              num_heads_q: int, total_q: int, total_k: int) -> AttnPlan:
+    """magi_attn_plan: sort / clamp the ranges and write the work list on the device (no host reads). total_q = rows
+    of q, total_k = rows of the key sequence (cache prefix + new tokens)."""
+    by_ranges = q_ranges is not None and k_ranges is not None
+    by_cu = cu_seqlens_q is not None and cu_seqlens_k is not None
+    if by_ranges == by_cu:
+        raise ValueError("give exactly one of (q_ranges, k_ranges) or (cu_seqlens_q, cu_seqlens_k)")
+    if by_ranges:
+        q_ranges, k_ranges = _ranges_arg(q_ranges, "q_ranges"), _ranges_arg(k_ranges, "k_ranges")
+        n, dev, keep = q_ranges.shape[0], q_ranges.device, (q_ranges, k_ranges)
+    else:
+        cu_seqlens_q, cu_seqlens_k = _ranges_arg(cu_seqlens_q, "cu_seqlens_q"), _ranges_arg(cu_seqlens_k, "cu_seqlens_k")
+        n, dev, keep = cu_seqlens_q.shape[0] - 1, cu_seqlens_q.device, (cu_seqlens_q, cu_seqlens_k)
+    L = _lib.lib()
+    plan = AttnPlan()
+    plan.ws = torch.empty((L.magi_attn_workspace_bytes(max(n, 0)) + 3) // 4, dtype=torch.int32, device=dev)
+    plan.n, plan.heads_q, plan.total_q, plan.total_k, plan.by_ranges = n, num_heads_q, total_q, total_k, by_ranges
+    plan._keep = keep
+    a = MagiAttnArgs()
+    a.q = MagiView(None, total_q, 0, 0)
+    a.k_a = MagiView(None, 0, 0, 0)
+    a.k_b = MagiView(None, total_k, 0, 0)
+    a.q_ranges = q_ranges.data_ptr() if by_ranges else None
+    a.k_ranges = k_ranges.data_ptr() if by_ranges else None
+    a.cu_seqlens_q = cu_seqlens_q.data_ptr() if by_cu else None
+    a.cu_seqlens_k = cu_seqlens_k.data_ptr() if by_cu else None
+    a.n_ranges, a.num_heads_q = n, num_heads_q
+    a.workspace, a.workspace_bytes = plan.ws.data_ptr(), plan.ws.numel() * 4
+    with torch.cuda.device(dev):
+        _lib.check(L.magi_attn_plan(C.byref(a), _stream()), "magi_attn_plan")
+    return plan
+
+
 def attn_ranges(
     q: torch.Tensor,
     k_new: Optional[torch.Tensor],
@@ -74,8 +120,12 @@ def attn_ranges(
     proj_input: Optional[Tuple[torch.Tensor, int, int]] = None,
     peer_out: Optional[Tuple[Sequence[int], Sequence[int], int, int]] = None,
     kernel: int = 0,
+    plan: Optional[AttnPlan] = None,
 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Range-masked attention over keys = concat(k_cache, k_new) without materialising the concatenation.
+
+    plan: an `attn_plan` result for the same ranges / head count / token counts (checked): skips the per-call work-list
+    kernel and workspace allocation.
 
     kernel: 0 = library default, 1 = attn_fwd_kernel, 2 = attn_pair_kernel (experimental CTA-pair kernel).
 
@@ -169,9 +219,18 @@ def attn_ranges(
         return out, lse
 
     L = _lib.lib()
-    ws_bytes = L.magi_attn_workspace_bytes(n)
-    ws = torch.empty((ws_bytes + 3) // 4, dtype=torch.int32, device=q.device)
+    if plan is not None:
+        total_k = sum(s_[0].shape[0] for s_ in segs if s_[0] is not None)
+        given = (q_ranges, k_ranges) if by_ranges else (cu_seqlens_q, cu_seqlens_k)
+        if not plan.matches(n, Hq, Tq, total_k, by_ranges) or any(
+                a_.data_ptr() != b_.data_ptr() for a_, b_ in zip(given, plan._keep)):
+            raise ValueError("plan was built for other range tensors / heads / token counts")
+        ws = plan.ws
+    else:
+        ws_bytes = L.magi_attn_workspace_bytes(n)
+        ws = torch.empty((ws_bytes + 3) // 4, dtype=torch.int32, device=q.device)
     a = MagiAttnArgs()
+    a.plan_ready = 1 if plan is not None else 0
     a.q = _view(q)
     a.k_a, a.v_a = _view(segs[0][0]), _view(segs[0][1])
     a.k_b, a.v_b = _view(segs[1][0]), _view(segs[1][1])

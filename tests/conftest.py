@@ -20,4 +20,10 @@ def _built_library():
     from magi_b200 import _lib
     if not os.path.exists(_lib.LIB_PATH):
         _lib.build()
+    elif not _lib.binary_is_current():
+        # a binary built from other sources than the tree's (source stamp in magi_build_info): rebuild before any test
+        # loads it; the loader caches the handle, so this must happen in a fresh process state
+        _lib._lib = None
+        _lib.build()
+        assert _lib.binary_is_current(), "libmagi_attn.so is stale and could not be rebuilt"
     return _lib.LIB_PATH

@@ -78,8 +78,11 @@ def qk_norm_rope(x_q, x_k, x_v, num_heads_q, num_heads_kv, ln_q, ln_k, sin, cos,
 
 def attn_ranges(q, k_new, v_new, q_ranges=None, k_ranges=None, k_cache=None, v_cache=None, cu_seqlens_q=None,
                 cu_seqlens_k=None, softmax_scale=None, out=None, return_lse=True, zero_fill=False, num_sms=0,
-                proj_input=None, peer_out=None):
+                proj_input=None, peer_out=None, kernel=0, plan=None):
     assert peer_out is None, "peer routing has no CPU double"
+    if plan is not None:   # the real function checks the plan against the call; so does the double
+        tk = sum(t.shape[0] for t in (k_cache, k_new) if t is not None)
+        assert plan == ("plan", q_ranges.data_ptr(), k_ranges.data_ptr(), q.shape[1], q.shape[0], tk), "stale plan"
     ks = [t for t in (k_cache, k_new) if t is not None and t.shape[0] > 0]
     vs = [t for t in (v_cache, v_new) if t is not None and t.shape[0] > 0]
     if q_ranges is None:
@@ -108,6 +111,10 @@ def attn_ranges(q, k_new, v_new, q_ranges=None, k_ranges=None, k_cache=None, v_c
     else:
         out[rows] = res[rows]                      # rows covered by no range are left untouched
     return out, (torch.from_numpy(lse) if return_lse else None)
+
+
+def attn_plan(q_ranges=None, k_ranges=None, *, cu_seqlens_q=None, cu_seqlens_k=None, num_heads_q, total_q, total_k):
+    return ("plan", q_ranges.data_ptr(), k_ranges.data_ptr(), num_heads_q, total_q, total_k)
 
 
 def kv_cache_append(cache, kv, row_offset, rows=None):

@@ -972,6 +972,69 @@ def test_two_block_dit_matches_reference_golden():
         assert rel < 2e-2, (l, rel)
 
 
+def test_graphed_layer_stack_replays_bit_identical_to_eager():
+    """EngineConfig.enable_cuda_graph (config.py:107) honoured by magi_b200.cuda_graph.GraphedLayerStack: the two-block
+    stack of the fixture above run through its three-forward KV-cache sequence TWICE - eagerly, and as one CUDA graph
+    per forward signature (the second pass replays every graph on other hidden states and changed range / caption
+    tensors) - must give bit-identical hidden states and KV-cache contents."""
+    from magi_b200.common import (EngineConfig, InferenceParams, ModelConfig, ModelMetaArgs, PackedCoreAttnParams,
+                                  PackedCrossAttnParams)
+    from magi_b200.cuda_graph import GraphedLayerStack
+    from magi_b200.transformer_layer import TransformerLayer, high_precision_promote
+    g = Golden("dit_two_blocks.npz")
+    hidden = g.raw("w0.self_attention.linear_qkv.layer_norm.weight").shape[0]
+    Hq, Hkv = [int(x) for x in g["heads"]]
+    mc = ModelConfig(num_layers=2, hidden_size=hidden, ffn_hidden_size=4 * hidden, num_attention_heads=Hq,
+                     num_query_groups=Hkv)
+    clip = int(g["clip"])
+
+    def run(graphed):
+        ec = EngineConfig(enable_cuda_graph=graphed)
+        layers = []
+        for l in (0, 1):
+            layer = high_precision_promote(TransformerLayer(mc, ec, layer_number=l))
+            layer.load_state_dict({k[3:]: g.torch(k) for k in g.files if k.startswith(f"w{l}.")}, strict=True)
+            layers.append(layer.cuda().eval())
+        stack = GraphedLayerStack(layers, ec)
+        inf = InferenceParams(max_batch_size=1, max_sequence_length=4 * clip)
+        outs = []
+        for rep in range(2):
+            for tag in ("A", "B", "C"):
+                sp, dn, upd, extra = [int(x) for x in g[f"{tag}.meta"]]
+                q_range, k_range = O.core_q_ranges(clip, dn, 1), g.raw(f"{tag}.k_range")
+                p = O.cross_attn_params(clip, dn, 1, g[f"{tag}.y_index"])
+                core = PackedCoreAttnParams(q_range=i32(q_range), k_range=i32(k_range), np_q_range=q_range,
+                                            np_k_range=k_range, max_seqlen_q=clip, max_seqlen_k=O.max_seqlen_k(k_range))
+                cross = PackedCrossAttnParams(q_ranges=i32(p["q_ranges"]), kv_ranges=i32(p["kv_ranges"]),
+                                              cu_seqlens_q=i32(p["cu_seqlens_q"]), cu_seqlens_kv=i32(p["cu_seqlens_kv"]),
+                                              max_seqlen_q=clip, max_seqlen_kv=800)
+                meta = ModelMetaArgs(H=4, W=4, cp_pad_size=None, cp_split_sizes=None, slice_point=sp,
+                                     denoising_range_num=dn, range_num=sp + dn, extract_prefix_video_feature=False,
+                                     fwd_extra_1st_chunk=bool(extra), distill_nearly_clean_chunk=False,
+                                     clip_token_nums=clip, enable_cuda_graph=graphed, core_attn_params=core,
+                                     cross_attn_params=cross)
+                inf.update_kv_cache = bool(upd)
+                x = g.torch(f"{tag}.hidden_states", "cuda")
+                y = g.torch(f"{tag}.key_value_states", "cuda")
+                if rep == 1:                      # same signature, other data
+                    x = (x.float() * 0.5 + 0.25).to(torch.bfloat16)
+                    y = (y.float() * -1.0).to(torch.bfloat16)
+                out = stack(x, g.torch(f"{tag}.condition", "cuda"), g.torch(f"{tag}.condition_map", "cuda"), y,
+                            g.torch(f"{tag}.rope", "cuda"), inf, meta)
+                outs.append(out.clone())
+        torch.cuda.synchronize()
+        return outs, [inf.key_value_memory_dict[l][:3 * clip].clone() for l in (0, 1)], stack
+
+    eager_outs, eager_caches, _ = run(False)
+    graph_outs, graph_caches, stack = run(True)
+    assert stack.disabled_reason is None, stack.disabled_reason
+    assert stack.captures == 3 and stack.replays == 6        # one graph per signature, replayed in both passes
+    for a, b in zip(eager_outs, graph_outs):
+        assert torch.equal(a, b)
+    for a, b in zip(eager_caches, graph_caches):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_apply_rotary_emb_dropin(F, dtype):
     """`flash_apply_rotary_emb(q, cos_emb, sin_emb)` (dit_module.py:961, 978) as a stand-alone call, on the layout the
