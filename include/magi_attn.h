@@ -290,6 +290,51 @@ typedef struct magi_rotary_args {
 MAGI_API int magi_apply_rotary_emb(const magi_rotary_args* args, void* stream);
 
 /*
+ * q / k / v (/ qx) projections fused with the QK-LayerNorm + RoPE prologue: ONE tensor-core GEMM whose epilogue is
+ * magi_qk_norm_rope_fwd.
+ * Replaces: CustomLayerNormLinear.forward_q / forward_qx / forward_k / forward_v   dit_module.py:405-425 (4 GEMMs)
+ *           + get_q / get_k / get_v / get_kv (:953-996) + the q half of get_xqkv (:1005-1009)
+ *
+ * x: (rows, hidden) bf16 = the LayerNorm'ed hidden states (forward_ln, dit_module.py:399-403), rows in "(sq b)" order.
+ * w: (heads_total * 128, hidden) bf16, the projection weights stacked in the order [Wq; Wk; Wv; Wqx]
+ *    (heads_total = Hq + 2 Hkv, + Hq when num_heads_qx == num_heads_q; must be even). nn.Linear layout: y = x w^T.
+ * Every 128-wide head of y is rounded to bf16 (the Linear's output dtype) and then treated exactly like the
+ * corresponding input of magi_qk_norm_rope_fwd: q and k heads LayerNorm (ln_dtype 0 = fp32 / 1 = bf16 parameters) +
+ * RoPE, v heads pass-through into the packed kv_out (and the KV-cache slot, rows [0, cache_rows)), qx heads LayerNorm
+ * with bf16 parameters and no RoPE into qx_out. hidden must be a multiple of 64; strides in elements (multiples of 8).
+ */
+typedef struct magi_qkv_proj_args {
+  const void* x;
+  int64_t rows, x_row_stride;
+  int32_t hidden;
+  const void* w;
+  int64_t w_row_stride;
+  int32_t num_heads_q, num_heads_kv, num_heads_qx; /* num_heads_qx: 0 or num_heads_q */
+  int32_t batch;
+  const void* ln_q_w;
+  const void* ln_q_b;
+  const void* ln_k_w;
+  const void* ln_k_b;
+  int32_t ln_dtype;
+  const void* ln_qx_w; /* bf16 */
+  const void* ln_qx_b;
+  float eps;
+  int32_t zero_centered_gamma;
+  const float* sin;
+  const float* cos;
+  void* q_out;
+  int64_t q_out_token_stride, q_out_head_stride;
+  void* kv_out;
+  int64_t kv_out_token_stride, kv_out_head_stride;
+  void* qx_out;
+  int64_t qx_out_token_stride, qx_out_head_stride;
+  void* cache;
+  int64_t cache_token_stride, cache_head_stride, cache_row_offset, cache_rows;
+  int32_t num_sms; /* 0 = all SMs of the current device */
+} magi_qkv_proj_args;
+MAGI_API int magi_qkv_proj_norm_rope_fwd(const magi_qkv_proj_args* args, void* stream);
+
+/*
  * MLP activation between fc1 and fc2 (CustomMLP.forward, dit_module.py:541-549), one memory-bound launch:
  *   gated != 0 (24B, gated_linear_unit): out[r, c] = bf16(silu(float(x[r, c])) * float(x[r, f + c])), x = (rows, 2 f)
  *                 = flashinfer.activation.silu_and_mul (dit_module.py:546)

@@ -25,6 +25,7 @@ EXPORTS = (
     "magi_bias_modulate_add",
     "magi_apply_rotary_emb",
     "magi_mlp_activation",
+    "magi_qkv_proj_norm_rope_fwd",
     "magi_last_error",
     "magi_build_info",
     "magi_launch_count",
@@ -126,6 +127,47 @@ class MagiPrologueArgs(C.Structure):
     ]
 
 
+class MagiQkvProjArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("rows", C.c_int64),
+        ("x_row_stride", C.c_int64),
+        ("hidden", C.c_int32),
+        ("w", C.c_void_p),
+        ("w_row_stride", C.c_int64),
+        ("num_heads_q", C.c_int32),
+        ("num_heads_kv", C.c_int32),
+        ("num_heads_qx", C.c_int32),
+        ("batch", C.c_int32),
+        ("ln_q_w", C.c_void_p),
+        ("ln_q_b", C.c_void_p),
+        ("ln_k_w", C.c_void_p),
+        ("ln_k_b", C.c_void_p),
+        ("ln_dtype", C.c_int32),
+        ("ln_qx_w", C.c_void_p),
+        ("ln_qx_b", C.c_void_p),
+        ("eps", C.c_float),
+        ("zero_centered_gamma", C.c_int32),
+        ("sin", C.c_void_p),
+        ("cos", C.c_void_p),
+        ("q_out", C.c_void_p),
+        ("q_out_token_stride", C.c_int64),
+        ("q_out_head_stride", C.c_int64),
+        ("kv_out", C.c_void_p),
+        ("kv_out_token_stride", C.c_int64),
+        ("kv_out_head_stride", C.c_int64),
+        ("qx_out", C.c_void_p),
+        ("qx_out_token_stride", C.c_int64),
+        ("qx_out_head_stride", C.c_int64),
+        ("cache", C.c_void_p),
+        ("cache_token_stride", C.c_int64),
+        ("cache_head_stride", C.c_int64),
+        ("cache_row_offset", C.c_int64),
+        ("cache_rows", C.c_int64),
+        ("num_sms", C.c_int32),
+    ]
+
+
 class MagiGatingArgs(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("x_dtype", C.c_int32), ("x_row_stride", C.c_int64),
@@ -200,6 +242,8 @@ def lib() -> C.CDLL:
     L.magi_bias_modulate_add.argtypes = [C.POINTER(MagiGatingArgs), C.c_void_p]
     L.magi_apply_rotary_emb.restype = C.c_int
     L.magi_apply_rotary_emb.argtypes = [C.POINTER(MagiRotaryArgs), C.c_void_p]
+    L.magi_qkv_proj_norm_rope_fwd.restype = C.c_int
+    L.magi_qkv_proj_norm_rope_fwd.argtypes = [C.POINTER(MagiQkvProjArgs), C.c_void_p]
     L.magi_mlp_activation.restype = C.c_int
     L.magi_mlp_activation.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                       C.c_void_p]

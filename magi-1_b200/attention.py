@@ -52,6 +52,15 @@ class CustomLayerNormLinear(nn.Module):
     def forward_ln(self, hidden_states):
         return self.layer_norm(hidden_states)
 
+    def stacked_weight(self, with_qx: bool) -> torch.Tensor:
+        """[Wq; Wk; Wv (; Wqx)] for the fused projection GEMM, built once and rebuilt only if a weight changes."""
+        ws = [self.q.weight, self.k.weight, self.v.weight] + ([self.qx.weight] if with_qx else [])
+        key = tuple((w.data_ptr(), w._version) for w in ws)
+        cached = getattr(self, "_stacked", None)
+        if cached is None or cached[0] != key:
+            cached = self._stacked = (key, F.stack_qkv_weights(*[w.detach() for w in ws]))
+        return cached[1]
+
     def forward_q(self, x):
         return self.q(x)
 
@@ -399,19 +408,21 @@ class FullyParallelAttention(nn.Module):
                           return_lse=False, **dest(i))
         return out
 
-    def cross_attention_prepare(self, mixed_qqkv, key_value_states):
+    def cross_attention_prepare(self, mixed_qqkv, key_value_states, q_rows=None):
         """get_xqkv, dit_module.py:1005-1021: qx / text-kv projections + the two bf16 LayerNorms (no RoPE). Split from
         the attention itself so that, under context parallelism, this half can overlap the input all-to-alls and the
         attention half the output all-to-all."""
         sq, b, _ = mixed_qqkv.shape
         Hq, Hkv = self.model_config.num_attention_heads, self.model_config.num_query_groups
         eps, z = self.model_config.layernorm_epsilon, self.model_config.apply_layernorm_1p
-        qx = self.linear_qkv.forward_qx(mixed_qqkv.reshape(sq * b, -1))                 # rows in (sq b) order
         kvx = torch.nn.functional.linear(key_value_states, self.linear_kv_xattn.weight)  # (ytot, Hkv*256)
         kvx = kvx.view(key_value_states.shape[0], Hkv, 2 * F.HEAD_DIM)
         # text K: LayerNorm (bf16 params, no RoPE); V: copy -> packed (ytot, Hkv, 256)
         _, kv_x = F.qk_norm_rope(None, kvx[..., :F.HEAD_DIM], kvx[..., F.HEAD_DIM:], Hq, Hkv, None,
                                  self._ln(self.k_layernorm_xattn), None, None, eps=eps, zero_centered_gamma=z)
+        if q_rows is not None:   # the normalised cross-attention query came out of the fused projection GEMM
+            return q_rows, kv_x
+        qx = self.linear_qkv.forward_qx(mixed_qqkv.reshape(sq * b, -1))                 # rows in (sq b) order
         q_rows = []
         for i in range(b):
             # "(sq b) -> (b sq)": batch row i is a strided view of the projection output
@@ -449,10 +460,11 @@ class FullyParallelAttention(nn.Module):
                           plan=plan, **dst)
         return None if proj_buf is not None else out.view(sq, b, Hq * F.HEAD_DIM)
 
-    def cross_attention(self, mixed_qqkv, key_value_states, cross_attn_params: PackedCrossAttnParams, proj_buf=None):
+    def cross_attention(self, mixed_qqkv, key_value_states, cross_attn_params: PackedCrossAttnParams, proj_buf=None,
+                        q_rows=None):
         """get_xqkv + cross_attention, dit_module.py:1005-1021, 1098-1136. Returns (sq, b, Hq*128), or writes slot
         n = 1 of the out-projection input `proj_buf` (sq*b, 2*Hq*128) and returns None."""
-        prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states)
+        prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states, q_rows)
         return self.cross_attention_attend(prepared, mixed_qqkv.shape[:2], cross_attn_params, proj_buf)
 
     @staticmethod
@@ -484,13 +496,33 @@ class FullyParallelAttention(nn.Module):
 
         if strategy == "none":
             assert self.engine_config.cp_size == 1
-            xq, xk, xv = self._project(mixed_qqkv)
             cache, start, app = self._cache_plan(inference_params, meta_args, rows, dt, dev)
             offload = self._offloaded(cache)
-            query, kv_new = F.qk_norm_rope(xq, xk, xv, Hq, Hkv, self._ln(self.q_layernorm), self._ln(self.k_layernorm),
-                                           sin_emb, cos_emb, batch=batch_size, eps=eps, zero_centered_gamma=z,
-                                           cache=cache if app > 0 and not offload else None, cache_row_offset=start,
-                                           cache_rows=app)
+            xq_rows = None
+            if (getattr(self.engine_config, "fused_qkv_proj", False) and mixed_qqkv.shape[-1] % 64 == 0
+                    and dt == torch.bfloat16):
+                # projections + prologue as one GEMM (its epilogue is the prologue); with batch 1 the cross-attention
+                # query rides along as a fourth group of heads
+                with_qx = batch_size == 1 and (2 * Hq + 2 * Hkv) % 2 == 0
+                if with_qx or (Hq + 2 * Hkv) % 2 == 0:
+                    query, kv_new, qx = F.qkv_proj_norm_rope(
+                        mixed_qqkv.reshape(rows, -1), self.linear_qkv.stacked_weight(with_qx), Hq, Hkv,
+                        self._ln(self.q_layernorm), self._ln(self.k_layernorm), sin_emb, cos_emb,
+                        ln_qx=self._ln(self.q_layernorm_xattn) if with_qx else None, batch=batch_size, eps=eps,
+                        zero_centered_gamma=z, cache=cache if app > 0 and not offload else None,
+                        cache_row_offset=start, cache_rows=app)
+                    xq_rows = [qx] if with_qx else None
+                else:
+                    query = None
+            else:
+                query = None
+            if query is None:
+                xq, xk, xv = self._project(mixed_qqkv)
+                query, kv_new = F.qk_norm_rope(xq, xk, xv, Hq, Hkv, self._ln(self.q_layernorm),
+                                               self._ln(self.k_layernorm), sin_emb, cos_emb, batch=batch_size, eps=eps,
+                                               zero_centered_gamma=z,
+                                               cache=cache if app > 0 and not offload else None,
+                                               cache_row_offset=start, cache_rows=app)
             kc = vc = None
             if cache is not None and start > 0:
                 kc, vc = (self._offload_views(inference_params, cache, start) if offload else
@@ -501,12 +533,14 @@ class FullyParallelAttention(nn.Module):
                 buf = torch.empty((rows, 2 * Hq * F.HEAD_DIM), dtype=dt, device=dev)
                 self.core_attention(query, kv_new[..., :F.HEAD_DIM], kv_new[..., F.HEAD_DIM:], batch_size, meta_args,
                                     kc, vc, proj_buf=buf)
-                self.cross_attention(mixed_qqkv, key_value_states, meta_args.cross_attn_params, proj_buf=buf)
+                self.cross_attention(mixed_qqkv, key_value_states, meta_args.cross_attn_params, proj_buf=buf,
+                                     q_rows=xq_rows)
                 return buf.view(sq, batch_size, 2 * Hq * F.HEAD_DIM)
             core = self.core_attention(query, kv_new[..., :F.HEAD_DIM], kv_new[..., F.HEAD_DIM:], batch_size,
                                        meta_args, kc, vc)
             core_attn_out = core.view(sq, batch_size, Hq * F.HEAD_DIM)
-            xattn_out = self.cross_attention(mixed_qqkv, key_value_states, meta_args.cross_attn_params)
+            xattn_out = self.cross_attention(mixed_qqkv, key_value_states, meta_args.cross_attn_params,
+                                             q_rows=xq_rows)
 
         elif fused_proj_input:
             raise NotImplementedError("fused_proj_input is available with cp_strategy 'none'")

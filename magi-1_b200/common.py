@@ -111,6 +111,12 @@ class EngineConfig:
     # new: under cp_ulysses, fuse both all-to-alls into the kernels' own stores over NVLink peer (symmetric) memory
     # instead of calling NCCL (falls back to NCCL when symmetric memory is unavailable, e.g. gloo / CPU tests)
     cp_fused_all_to_all: bool = True
+    # new: with cp_strategy "none", run the q / k / v / qx projections and the QK-LayerNorm + RoPE
+    # prologue as ONE tensor-core GEMM whose epilogue is the prologue (magi_qkv_proj_norm_rope_fwd) instead of four
+    # cuBLAS GEMMs + the prologue kernels. Measured on a B200 (profiles/r02b_gemm_bench.log): 1338 vs 1523 us per layer at
+    # cfg2 (4.5B, 37 440 rows), 3938 vs 4196 us at the 24B shapes; results equal to the unfused path up to single bf16
+    # ulps on 0.001 % of the elements.
+    fused_qkv_proj: bool = True
 
 
 def divide(numerator: int, denominator: int) -> int:

@@ -13,6 +13,7 @@
 #include "gating.cuh"
 #include "rope.cuh"
 #include "activation.cuh"
+#include "qkv_gemm.cuh"
 
 namespace {
 
@@ -483,6 +484,73 @@ int magi_bias_modulate_add(const MagiGatingArgs* a, void* stream_) {
   int sms = 0;
   if (int rc = device_sm_count(&sms)) return rc;
   MAGI_CUDA(magi::gating_launch(p, a->x_dtype == 1, a->gate_dtype == 1, sms, stream));
+  g_launches++;
+  return 0;
+}
+
+namespace {
+// (rows, cols) bf16 row-major matrix -> 2-D tensor map {cols, rows}, box {64, 128}, 128B swizzle (rows past the end are
+// zero-filled by the TMA unit)
+int make_matrix_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t row_stride, const char* what) {
+  EncodeTiledFn enc = get_encode_fn();
+  MAGI_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  MAGI_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && row_stride % 8 == 0 && row_stride >= cols,
+             "%s: pointer must be 16-byte aligned and the row stride a multiple of 8 elements", what);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)(row_stride * 2)};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MAGI_CHECK(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled failed (CUresult %d)", what, (int)r);
+  return 0;
+}
+}  // namespace
+
+int magi_qkv_proj_norm_rope_fwd(const magi_qkv_proj_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MAGI_CHECK(a != nullptr, "args is NULL");
+  MAGI_CHECK(a->rows >= 0 && a->rows < (1ll << 31), "rows out of range");
+  MAGI_CHECK(a->hidden > 0 && a->hidden % 64 == 0, "hidden must be a positive multiple of 64");
+  MAGI_CHECK(a->num_heads_q > 0 && a->num_heads_kv > 0, "num_heads_q / num_heads_kv must be positive");
+  MAGI_CHECK(a->num_heads_qx == 0 || a->num_heads_qx == a->num_heads_q, "num_heads_qx must be 0 or num_heads_q");
+  const int heads_total = a->num_heads_q + 2 * a->num_heads_kv + a->num_heads_qx;
+  MAGI_CHECK(heads_total % 2 == 0, "the stacked weight must hold an even number of heads (256-column tiles)");
+  MAGI_CHECK(a->ln_dtype == 0 || a->ln_dtype == 1, "ln_dtype must be 0 (fp32) or 1 (bf16)");
+  MAGI_CHECK(a->batch >= 1, "batch must be >= 1");
+  if (a->rows == 0) return 0;
+  MAGI_CHECK(a->x && a->w && a->q_out && a->kv_out && a->ln_q_w && a->ln_q_b && a->ln_k_w && a->ln_k_b, "NULL pointer");
+  MAGI_CHECK(a->num_heads_qx == 0 || (a->qx_out && a->ln_qx_w && a->ln_qx_b), "qx path needs qx_out, ln_qx_w, ln_qx_b");
+  MAGI_CHECK((a->sin == nullptr) == (a->cos == nullptr), "sin and cos must both be given or both be NULL");
+  MAGI_CHECK(a->q_out_token_stride % 8 == 0 && a->q_out_head_stride % 8 == 0 && a->kv_out_token_stride % 8 == 0 &&
+                 a->kv_out_head_stride % 8 == 0 && a->qx_out_token_stride % 8 == 0 && a->qx_out_head_stride % 8 == 0 &&
+                 a->cache_token_stride % 8 == 0 && a->cache_head_stride % 8 == 0,
+             "output strides must be multiples of 8 elements");
+  MAGI_CHECK(((reinterpret_cast<uintptr_t>(a->q_out) | reinterpret_cast<uintptr_t>(a->kv_out) |
+               reinterpret_cast<uintptr_t>(a->qx_out) | reinterpret_cast<uintptr_t>(a->cache) |
+               reinterpret_cast<uintptr_t>(a->sin) | reinterpret_cast<uintptr_t>(a->cos)) & 15) == 0,
+             "output / table pointers must be 16-byte aligned");
+  if (a->cache)
+    MAGI_CHECK(a->cache_rows >= 0 && a->cache_rows <= a->rows && a->cache_row_offset >= 0, "bad cache arguments");
+  CUtensorMap tm_x, tm_w;
+  if (int rc = make_matrix_map(&tm_x, a->x, a->rows, a->hidden, a->x_row_stride, "x")) return rc;
+  if (int rc = make_matrix_map(&tm_w, a->w, (int64_t)heads_total * 128, a->hidden, a->w_row_stride, "w")) return rc;
+  magi::QkvGemmParams p;
+  p.rows = a->rows; p.hidden = a->hidden; p.Hq = a->num_heads_q; p.Hkv = a->num_heads_kv; p.heads_total = heads_total;
+  p.batch = a->batch;
+  p.ln_q_w = a->ln_q_w; p.ln_q_b = a->ln_q_b; p.ln_k_w = a->ln_k_w; p.ln_k_b = a->ln_k_b;
+  p.ln_qx_w = a->num_heads_qx ? a->ln_qx_w : nullptr; p.ln_qx_b = a->num_heads_qx ? a->ln_qx_b : nullptr;
+  p.ln_bf16 = a->ln_dtype; p.eps = a->eps; p.zero_centered_gamma = a->zero_centered_gamma;
+  p.sin = a->sin; p.cos = a->cos;
+  p.q_out = a->q_out; p.q_out_token_stride = a->q_out_token_stride; p.q_out_head_stride = a->q_out_head_stride;
+  p.kv_out = a->kv_out; p.kv_out_token_stride = a->kv_out_token_stride; p.kv_out_head_stride = a->kv_out_head_stride;
+  p.qx_out = a->qx_out; p.qx_out_token_stride = a->qx_out_token_stride; p.qx_out_head_stride = a->qx_out_head_stride;
+  p.cache = a->cache; p.cache_token_stride = a->cache_token_stride; p.cache_head_stride = a->cache_head_stride;
+  p.cache_row_offset = a->cache_row_offset; p.cache_rows = a->cache ? a->cache_rows : 0;
+  int sms = a->num_sms;
+  if (sms <= 0) { if (int rc = device_sm_count(&sms)) return rc; }
+  MAGI_CUDA(magi::qkv_gemm_launch(tm_x, tm_w, p, sms, stream));
   g_launches++;
   return 0;
 }

@@ -22,7 +22,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import MagiAttnArgs, MagiGatingArgs, MagiPrologueArgs, MagiRotaryArgs, MagiView
+from ._lib import MagiAttnArgs, MagiGatingArgs, MagiPrologueArgs, MagiQkvProjArgs, MagiRotaryArgs, MagiView
 
 HEAD_DIM = 128
 
@@ -692,3 +692,82 @@ def mlp_activation(x: torch.Tensor, gated: bool, out: Optional[torch.Tensor] = N
             _lib.check(_lib.lib().magi_mlp_activation(x2.data_ptr(), x2.stride(0), o2.data_ptr(), o2.stride(0), rows, f,
                                                       1 if gated else 0, _stream()), "magi_mlp_activation")
     return out
+
+
+def qkv_proj_norm_rope(
+    x: torch.Tensor,
+    w: torch.Tensor,
+    num_heads_q: int,
+    num_heads_kv: int,
+    ln_q: Tuple[torch.Tensor, torch.Tensor],
+    ln_k: Tuple[torch.Tensor, torch.Tensor],
+    sin: Optional[torch.Tensor],
+    cos: Optional[torch.Tensor],
+    ln_qx: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+    batch: int = 1,
+    eps: float = 1e-6,
+    zero_centered_gamma: bool = True,
+    cache: Optional[torch.Tensor] = None,
+    cache_row_offset: int = 0,
+    cache_rows: int = 0,
+    num_sms: int = 0,
+):
+    """The q / k / v (and, with ln_qx, the cross-attention qx) projections of CustomLayerNormLinear
+    (dit_module.py:405-425) and the QK-LayerNorm + RoPE prologue (get_q / get_kv, :953-996; q half of get_xqkv,
+    :1005-1009) as ONE tensor-core GEMM whose epilogue is the prologue (magi_qkv_proj_norm_rope_fwd).
+
+    x: (rows, hidden) bf16, the LayerNorm'ed hidden states in "(sq b)" row order. w: the stacked weight
+    [Wq; Wk; Wv (; Wqx)] of shape ((Hq + 2 Hkv (+ Hq)) * 128, hidden), see `stack_qkv_weights`.
+    Returns (q (rows, Hq, 128), kv (rows, Hkv, 256) packed [K | V], qx (rows, Hq, 128) or None)."""
+    if not x.is_cuda or x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or x.dim() != 2 or w.dim() != 2:
+        raise ValueError("x and w must be 2-D bfloat16 CUDA tensors (this package has no CPU path)")
+    rows, hidden = x.shape
+    with_qx = ln_qx is not None
+    heads_total = num_heads_q + 2 * num_heads_kv + (num_heads_q if with_qx else 0)
+    if w.shape != (heads_total * HEAD_DIM, hidden) or x.stride(1) != 1 or w.stride(1) != 1:
+        raise ValueError(f"w must be ({heads_total * HEAD_DIM}, {hidden}) and both operands contiguous in the last dim")
+    if hidden % 64 or heads_total % 2:
+        raise ValueError("hidden must be a multiple of 64 and the stacked weight must hold an even number of heads")
+    ln_dtype = 1 if ln_q[0].dtype == torch.bfloat16 else 0
+    for t in (*ln_q, *ln_k):
+        if t.dtype != ln_q[0].dtype or t.numel() != HEAD_DIM or not t.is_cuda:
+            raise ValueError("q / k LayerNorm parameters must be 128-element CUDA tensors of one dtype")
+    dev = x.device
+    q = torch.empty((rows, num_heads_q, HEAD_DIM), dtype=torch.bfloat16, device=dev)
+    kv = torch.empty((rows, num_heads_kv, 2 * HEAD_DIM), dtype=torch.bfloat16, device=dev)
+    qx = torch.empty((rows, num_heads_q, HEAD_DIM), dtype=torch.bfloat16, device=dev) if with_qx else None
+    a = MagiQkvProjArgs()
+    a.x, a.rows, a.x_row_stride, a.hidden = x.data_ptr(), rows, x.stride(0), hidden
+    a.w, a.w_row_stride = w.data_ptr(), w.stride(0)
+    a.num_heads_q, a.num_heads_kv, a.num_heads_qx, a.batch = num_heads_q, num_heads_kv, num_heads_q if with_qx else 0, batch
+    keep = [t.contiguous() for t in (*ln_q, *ln_k)]
+    a.ln_q_w, a.ln_q_b, a.ln_k_w, a.ln_k_b = (t.data_ptr() for t in keep)
+    a.ln_dtype = ln_dtype
+    if with_qx:
+        kx = [t.to(torch.bfloat16).contiguous() for t in ln_qx]
+        keep += kx
+        a.ln_qx_w, a.ln_qx_b = kx[0].data_ptr(), kx[1].data_ptr()
+    a.eps, a.zero_centered_gamma = eps, 1 if zero_centered_gamma else 0
+    if sin is not None:
+        sin, cos = sin.contiguous().float(), cos.contiguous().float()
+        if sin.shape != (rows // batch, 48) or cos.shape != sin.shape:
+            raise ValueError("sin / cos must be (rows / batch, 48)")
+        a.sin, a.cos = sin.data_ptr(), cos.data_ptr()
+    a.q_out, a.q_out_token_stride, a.q_out_head_stride = q.data_ptr(), q.stride(0), q.stride(1)
+    a.kv_out, a.kv_out_token_stride, a.kv_out_head_stride = kv.data_ptr(), kv.stride(0), kv.stride(1)
+    if with_qx:
+        a.qx_out, a.qx_out_token_stride, a.qx_out_head_stride = qx.data_ptr(), qx.stride(0), qx.stride(1)
+    if cache is not None and cache_rows > 0:
+        if cache.dtype != torch.bfloat16 or cache.shape[1:] != (num_heads_kv, 2 * HEAD_DIM) or cache.stride(2) != 1:
+            raise ValueError("cache must be (rows, Hkv, 256) bf16")
+        a.cache, a.cache_token_stride, a.cache_head_stride = cache.data_ptr(), cache.stride(0), cache.stride(1)
+        a.cache_row_offset, a.cache_rows = cache_row_offset, cache_rows
+    a.num_sms = num_sms
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().magi_qkv_proj_norm_rope_fwd(C.byref(a), _stream()), "magi_qkv_proj_norm_rope_fwd")
+    return q, kv, qx
+
+
+def stack_qkv_weights(wq: torch.Tensor, wk: torch.Tensor, wv: torch.Tensor, wqx: Optional[torch.Tensor] = None):
+    """[Wq; Wk; Wv (; Wqx)]: the row order qkv_proj_norm_rope expects (nn.Linear weights, (out, in))."""
+    return torch.cat([t for t in (wq, wk, wv, wqx) if t is not None], dim=0).contiguous()

@@ -113,6 +113,25 @@ def attn_ranges(q, k_new, v_new, q_ranges=None, k_ranges=None, k_cache=None, v_c
     return out, (torch.from_numpy(lse) if return_lse else None)
 
 
+def stack_qkv_weights(wq, wk, wv, wqx=None):
+    return torch.cat([t for t in (wq, wk, wv, wqx) if t is not None], dim=0).contiguous()
+
+
+def qkv_proj_norm_rope(x, w, num_heads_q, num_heads_kv, ln_q, ln_k, sin, cos, ln_qx=None, batch=1, eps=1e-6,
+                       zero_centered_gamma=True, cache=None, cache_row_offset=0, cache_rows=0, num_sms=0):
+    """The fused projection GEMM as the composition it replaces: nn.Linear in bf16, then the prologue double."""
+    y = _bf(O.linear_bf16(_np(x), _np(w)))
+    nq, nk = num_heads_q * HEAD_DIM, num_heads_kv * HEAD_DIM
+    q, kv = qk_norm_rope(y[:, :nq], y[:, nq:nq + nk], y[:, nq + nk:nq + 2 * nk], num_heads_q, num_heads_kv, ln_q, ln_k,
+                         sin, cos, batch=batch, eps=eps, zero_centered_gamma=zero_centered_gamma, cache=cache,
+                         cache_row_offset=cache_row_offset, cache_rows=cache_rows)
+    qx = None
+    if ln_qx is not None:
+        qx, _ = qk_norm_rope(y[:, nq + 2 * nk:], None, None, num_heads_q, num_heads_kv, ln_qx, None, None, None,
+                             batch=batch, eps=eps, zero_centered_gamma=zero_centered_gamma)
+    return q, kv, qx
+
+
 def attn_plan(q_ranges=None, k_ranges=None, *, cu_seqlens_q=None, cu_seqlens_k=None, num_heads_q, total_q, total_k):
     return ("plan", q_ranges.data_ptr(), k_ranges.data_ptr(), num_heads_q, total_q, total_k)
 

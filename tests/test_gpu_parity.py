@@ -564,6 +564,59 @@ def test_mlp_activation_vs_oracle_and_libraries(F, gated, rows, f):
     assert torch.equal(out2, out)
 
 
+@pytest.mark.parametrize("rows,hidden,Hq,Hkv,with_qx,batch,fp32_ln", [
+    (300, 256, 4, 2, True, 1, True), (1000, 3072, 6, 2, False, 1, True), (514, 512, 2, 1, True, 2, False)])
+def test_fused_projection_gemm_vs_oracle(F, rows, hidden, Hq, Hkv, with_qx, batch, fp32_ln):
+    """magi_qkv_proj_norm_rope_fwd (the q / k / v / qx projections with the QK-LayerNorm + RoPE prologue as the GEMM
+    epilogue) against the oracle's composition of the reference steps: nn.Linear in bf16
+    (dit_module.py:405-425) -> get_q / get_kv (:953-996) / xattn q LayerNorm (:1008), and against this repository's
+    unfused path (cuBLAS GEMMs + magi_qk_norm_rope_fwd) on the same inputs. Tolerance: the prologue's 1 bf16 ulp plus
+    the ulp flips of the bf16-rounded GEMM output that different fp32 accumulation orders cause (a few 1e-2 after the
+    LayerNorm's 1 / sigma amplification on a handful of elements): max_abs 6e-2, rel-L2 6e-3."""
+    x = rnd((rows, hidden), 3, scale=1.0)
+    ws = [rnd((h * 128, hidden), 4 + i, scale=hidden ** -0.5) for i, h in enumerate((Hq, Hkv, Hkv, Hq))]
+    if not with_qx:
+        ws = ws[:3]
+    lnp = [rnd((128,), 20 + i, scale=0.2) for i in range(6)]
+    ang = np.random.default_rng(0).uniform(0, 6.28, size=(rows // batch, 48)).astype(np.float32)
+    sin, cos = np.sin(ang), np.cos(ang)
+    lin = [O.linear_bf16(x, w_) for w_ in ws]
+    sq = rows // batch
+    ref_q = O.get_q_or_k(lin[0].reshape(sq, batch, -1), Hq, lnp[0], lnp[1], sin, cos)
+    ref_kv = O.get_kv(lin[1].reshape(sq, batch, -1), lin[2].reshape(sq, batch, -1), Hkv, lnp[2], lnp[3], sin, cos)
+    dt = torch.float32 if fp32_ln else torch.bfloat16
+    t = lambda a, d=dt: torch.from_numpy(a).cuda().to(d)
+    w_cat = F.stack_qkv_weights(*[bf(w_) for w_ in ws])
+    cache = torch.zeros(rows + 50, Hkv, 256, dtype=torch.bfloat16, device="cuda")
+    q, kv, qx = F.qkv_proj_norm_rope(bf(x), w_cat, Hq, Hkv, (t(lnp[0]), t(lnp[1])), (t(lnp[2]), t(lnp[3])),
+                                     torch.from_numpy(sin).cuda(), torch.from_numpy(cos).cuda(),
+                                     ln_qx=(bf(lnp[4]), bf(lnp[5])) if with_qx else None, batch=batch,
+                                     cache=cache, cache_row_offset=50, cache_rows=rows - 7)
+
+    def close(a, ref, what):
+        a = a.float().cpu().numpy()
+        err = np.abs(a - ref).max()
+        rel = np.linalg.norm(a - ref) / np.linalg.norm(ref)
+        assert a.shape == ref.shape and err <= 6e-2 and rel <= 6e-3, f"{what}: max_abs {err:.3e} rel_l2 {rel:.3e}"
+
+    if fp32_ln:   # the oracle's get_q_or_k models fp32 LayerNorm parameters
+        close(q, ref_q, "q")
+        close(kv, ref_kv, "kv")
+    else:
+        close(kv[..., 128:], ref_kv[..., 128:], "v")
+    if with_qx:
+        ref_qx = O.xattn_layer_norm(lin[3].reshape(rows, Hq, 128), O.bf16_round(lnp[4]), O.bf16_round(lnp[5]))
+        close(qx, ref_qx, "qx")
+    assert torch.equal(cache[50:50 + rows - 7], kv[:rows - 7]) and float(cache[50 + rows - 7:].abs().sum()) == 0.0
+    # the unfused path of this repository on the same inputs
+    xt = bf(x)
+    y = [torch.nn.functional.linear(xt, bf(w_)) for w_ in ws]
+    q2, kv2 = F.qk_norm_rope(y[0], y[1], y[2], Hq, Hkv, (t(lnp[0]), t(lnp[1])), (t(lnp[2]), t(lnp[3])),
+                             torch.from_numpy(sin).cuda(), torch.from_numpy(cos).cuda(), batch=batch)
+    close(q, q2.float().cpu().numpy(), "q vs unfused")
+    close(kv, kv2.float().cpu().numpy(), "kv vs unfused")
+
+
 def test_full_attention_block_matches_reference_golden():
     """The drop-in FullyParallelAttention replays the reference's own forward sequence (steps A-E of
     oracle/gen_golden.py: KV-cache fill, fwd_extra_1st_chunk, update_kv_cache False/True, distill extra range,

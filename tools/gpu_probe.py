@@ -347,6 +347,63 @@ def t_bench_gating():
     return True
 
 
+@case
+def u_bench_qkv_gemm():
+    """cfg2 / 24B shapes: q / k / v / qx projections + prologue, fused GEMM vs cuBLAS GEMM(s) + prologue kernels."""
+    import torch
+    import magi_b200.functional as F
+    dev = "cuda"
+    for S, hidden, Hq, Hkv in ((37440, 3072, 24, 8), (27000, 6144, 48, 8)):
+        g = torch.Generator(device=dev).manual_seed(1)
+        x = torch.randn(S, hidden, device=dev, generator=g).to(torch.bfloat16)
+        ws = [(torch.randn(h * 128, hidden, device=dev, generator=g) * hidden ** -0.5).to(torch.bfloat16)
+              for h in (Hq, Hkv, Hkv, Hq)]
+        w_cat = F.stack_qkv_weights(*ws)
+        ln = [torch.randn(128, device=dev) * 0.1 for _ in range(4)]
+        lnx = [(torch.randn(128, device=dev) * 0.1).to(torch.bfloat16) for _ in range(2)]
+        ang = torch.rand(S, 48, device=dev) * 6.28
+        sin, cos = torch.sin(ang), torch.cos(ang)
+        cache = torch.empty(S, Hkv, 256, device=dev, dtype=torch.bfloat16)
+        flops = 2 * S * hidden * w_cat.shape[0]
+
+        def fused():
+            return F.qkv_proj_norm_rope(x, w_cat, Hq, Hkv, (ln[0], ln[1]), (ln[2], ln[3]), sin, cos,
+                                        ln_qx=(lnx[0], lnx[1]), cache=cache, cache_row_offset=0, cache_rows=S)
+
+        def unfused():
+            y = torch.nn.functional.linear(x, w_cat)
+            nq, nk = Hq * 128, Hkv * 128
+            q, kv = F.qk_norm_rope(y[:, :nq], y[:, nq:nq + nk], y[:, nq + nk:nq + 2 * nk], Hq, Hkv, (ln[0], ln[1]),
+                                   (ln[2], ln[3]), sin, cos, cache=cache, cache_row_offset=0, cache_rows=S)
+            qx, _ = F.qk_norm_rope(y[:, nq + 2 * nk:], None, None, Hq, Hkv, (lnx[0], lnx[1]), None, None, None)
+            return q, kv, qx
+
+        def gemm_only():
+            return torch.nn.functional.linear(x, w_cat)
+
+        res = {}
+        for nm, fn in (("fused GEMM+prologue", fused), ("cuBLAS GEMM + 2 prologue launches", unfused),
+                       ("cuBLAS GEMM alone", gemm_only)):
+            for _ in range(3):
+                out = fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(8):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); out = fn(); e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            res[nm] = out
+            print(f"[qkv {S}x{hidden}->{w_cat.shape[0]}: {nm}] best {min(ts)*1e3:.0f} us, median "
+                  f"{sorted(ts)[len(ts)//2]*1e3:.0f} us -> {flops/min(ts)/1e9:.0f} TFLOP/s (GEMM flops)", flush=True)
+        a, b_ = res["fused GEMM+prologue"], res["cuBLAS GEMM + 2 prologue launches"]
+        for nm, t0, t1 in zip(("q", "kv", "qx"), a, b_):
+            d = (t0.float() - t1.float()).abs()
+            print(f"    fused vs unfused {nm}: max_abs {d.max().item():.3e}, mismatching {100*(d>0).float().mean().item():.3f} %",
+                  flush=True)
+    return True
+
+
 def main():
     names = sys.argv[1:] or sorted(CASES)
     if len(names) == 1 and names[0].startswith("--run="):
