@@ -838,8 +838,9 @@ def cp_parity_leg(cx, hp, args_w):
     ref.layer(0)
     hp.layer_fn()(0)
     cx.torch.cuda.synchronize()
-    d_self = (hp.core_out.float() - ref.core_out[rows].float()).abs().max().item()
-    d_cross = (hp.x_out.float() - ref.x_out[rows].float()).abs().max().item()
+    flat = lambda t_: t_.reshape(rows.numel(), -1).float()   # (rows, Hq, 128) or the scheduler's (rows, 1, Hq * 128)
+    d_self = (flat(hp.core_out) - flat(ref.core_out[rows])).abs().max().item()
+    d_cross = (flat(hp.x_out) - flat(ref.x_out[rows])).abs().max().item()
     finite = bool(torch.isfinite(hp.core_out.float()).all()) and bool(torch.isfinite(hp.x_out.float()).all())
     max_abs = cx.max_over_ranks(max(d_self, d_cross) if finite else float("inf"))
     bound = 2.5e-2 if mode == "ring-nccl" else 0.0

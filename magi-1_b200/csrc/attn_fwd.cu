@@ -570,6 +570,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (ch == 0 && p.lse != nullptr) p.lse[static_cast<int64_t>(row) * p.Hq + it.h] = -INFINITY;
       }
     }
+    // fused output all-to-all: the rows stored into other GPUs' buffers must be visible system-wide before this kernel
+    // (and the device-side barrier that follows it in stream order) completes - see the note in prologue.cu
+    if (p.num_peers > 0) __threadfence_system();
   } else if (warp == kMmaWarp) {
     // ====================================================================== MMA issuer
     // The whole warp runs the loop (waits included) so that everything feeding the MMAs is warp-uniform; only the
@@ -605,6 +608,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       int seg, krow0, nvalid;
       tile_info(it_, j_, seg, krow0, nvalid);
       nvalid = uniform(nvalid);
+#ifdef MAGI_NO_VTAIL
+      return 8;   // debug variant: the round-1 behaviour (every k-step issued, nothing zeroed)
+#endif
       if (nvalid >= kTileN) return 8;
       const int r1 = (nvalid + 15) & ~15;
       for (int idx = lane; idx < (r1 - nvalid) * 16; idx += 32) {

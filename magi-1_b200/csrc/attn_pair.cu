@@ -523,6 +523,9 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         p.lse[static_cast<int64_t>(erow) * p.Hq + it.h] = (row_m * scale_log2 + log2f(row_l)) * 0.6931471805599453f;
       // xl / xm are rewritten only after the next item's tiles, which need both warps of the quarter (p_full)
     }
+    // fused output all-to-all: the rows stored into other GPUs' buffers must be visible system-wide before this kernel
+    // (and the device-side barrier that follows it in stream order) completes - see the note in prologue.cu
+    if (p.num_peers > 0) __threadfence_system();
   } else if (warp == kMmaWarp) {
     // ====================================================================== MMA issuer (leader CTA)
     // Flattened over this pair's tiles with the S cursor one tile ahead of the P V cursor:

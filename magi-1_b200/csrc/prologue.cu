@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(kRingThreads, MAGI_PRO_RING_BLOCKS) prologue_r
     const int e1 = s < 6 ? 48 + 8 * s : 96 + 8 * (s - 6);
     const bool rot = p.sin != nullptr && s < 6;
     const uint64_t one2 = pack_f2(1.f, 1.f);
+    const uint32_t opaque_zero = static_cast<uint32_t>(p.batch) >> 30;   // 0 at run time, unknown at compile time
     int cur_type = -1;
     uint64_t w2[8], b2[8];
 #pragma unroll
@@ -298,8 +299,15 @@ __global__ void __launch_bounds__(kRingThreads, MAGI_PRO_RING_BLOCKS) prologue_r
         ra[u] = lds128(sbase + u * 1024 + e0 * 2);
         rb[u] = lds128(sbase + u * 1024 + e1 * 2);
       }
+      // Hand the stage back to the producer - but only once the LDS above have RETURNED. mbarrier.arrive carries no
+      // register dependency on them and ptxas issued it right behind the loads (no scoreboard wait): with the
+      // load/store unit backed up by NVLink peer stores (fused all-to-all / all-gather modes) the producer's next bulk
+      // copy into this stage could land before the reads had happened, and a unit came out holding the data of the
+      // super-unit one ring later (round 2: 1-3 K/V rows of 37 440 per call on 2 x B200, found by bench.py's cp_parity
+      // leg). The arrive's address now depends on every loaded register through a zero the compiler cannot see.
+      const uint32_t landed = (ra[0].x ^ ra[0].w ^ ra[1].x ^ ra[1].w ^ rb[0].x ^ rb[0].w ^ rb[1].x ^ rb[1].w) & opaque_zero;
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[stage]);   // the unit is in registers: hand the stage back to the producer
+      if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(&empty[stage]) + landed));
 
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -394,6 +402,12 @@ __global__ void __launch_bounds__(kRingThreads, MAGI_PRO_RING_BLOCKS) prologue_r
         }
       }
     }
+    // Stores into OTHER GPUs' memory (fused all-to-all / all-gather over NVLink, unicast or NVSwitch multicast) are
+    // consumed by the peers after a device-side barrier that follows this kernel in stream order. The barrier's signal
+    // and these data stores may take different routes: make every store of this thread visible system-wide before the
+    // kernel (and hence the signal) can complete. Found in round 2: once the per-call work-list kernel no longer sat
+    // between the barrier and the attention launch, the peers occasionally read rows that had not landed yet.
+    if (kMode != 0 && (p.use_peers != 0 || p.gather_peers > 0)) __threadfence_system();
   }
 }
 

@@ -38,7 +38,11 @@ def main():
     def build(strategy, cp, offload=False):
         torch.manual_seed(1234)
         m = FullyParallelAttention(mc, EngineConfig(cp_size=cp, cp_strategy=strategy, ulysses_overlap_degree=overlap,
-                                                    cp_fused_all_to_all=fused, kv_offload=offload), layer_number=1)
+                                                    cp_fused_all_to_all=fused, kv_offload=offload,
+                                                    # like with like: the context-parallel paths project through
+                                                    # cuBLAS + the prologue kernel, so the single-GPU side does too
+                                                    # (the fused projection GEMM differs by single bf16 ulps)
+                                                    fused_qkv_proj=False), layer_number=1)
         g = torch.Generator().manual_seed(99)
         with torch.no_grad():
             for n, p in m.named_parameters():
