@@ -108,6 +108,15 @@ typedef struct magi_attn_args {
    * num_heads_q and token counts; magi_attn_fwd then launches the attention kernel only (one launch instead of two).
    * The ranges of a denoise forward are the same for every layer (dit_model.py:215-259): plan once, reuse 34 / 48 times. */
   int32_t plan_ready;
+  /* Launch ordering against the kernel BEFORE this one in the stream. The attention and prologue kernels are launched
+   * with programmatic stream serialization (their CTA set-up overlaps the tail of the earlier kernel; MAGI_PDL=0 in the
+   * environment restores plain launches). 0 = this launch may depend on that kernel: its memory accesses start once
+   * that kernel has completed. 1 = the caller asserts that NOTHING this launch reads or writes (q, k, v, out, lse,
+   * ranges, the plan in `workspace` - hence plan_ready must be set) is read or written by that kernel: the CTAs of
+   * this launch then run on the SMs the earlier kernel has already left, and the launch still COMPLETES in stream
+   * order (everything after it sees both finished). The text cross-attention after the self-attention of the same
+   * layer is such a launch (context_parallel.py:591: "no communication", no shared tensors). */
+  int32_t launch_dependency;
 } magi_attn_args;
 
 MAGI_API size_t magi_attn_workspace_bytes(int32_t n_ranges);

@@ -75,6 +75,7 @@ class MagiAttnArgs(C.Structure):
         ("peer_row_bounds", C.c_int64 * (MAX_PEERS + 1)),
         ("kernel", C.c_int32),
         ("plan_ready", C.c_int32),
+        ("launch_dependency", C.c_int32),
     ]
 
 

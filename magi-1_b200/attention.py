@@ -408,10 +408,28 @@ class FullyParallelAttention(nn.Module):
                           return_lse=False, **dest(i))
         return out
 
-    def cross_attention_prepare(self, mixed_qqkv, key_value_states, q_rows=None):
+    def cross_attention_prepare(self, mixed_qqkv, key_value_states, q_rows=None, cross_attn_params=None,
+                                proj_buf=None):
         """get_xqkv, dit_module.py:1005-1021: qx / text-kv projections + the two bf16 LayerNorms (no RoPE). Split from
         the attention itself so that, under context parallelism, this half can overlap the input all-to-alls and the
-        attention half the output all-to-all."""
+        attention half the output all-to-all.
+        With cross_attn_params (batch 1) the result also carries everything else the attention launch needs - its
+        destination and its work list - so that `cross_attention_attend(..., independent=True)` right after the
+        self-attention launch touches nothing that was allocated or written after that launch was issued."""
+        prepared = self._cross_attention_prepare(mixed_qqkv, key_value_states, q_rows)
+        sq, b, _ = mixed_qqkv.shape
+        if cross_attn_params is None or b != 1:
+            return prepared
+        q_rows_, kv_x = prepared
+        qr, kr = cross_attn_params.q_ranges, cross_attn_params.kv_ranges
+        if not (qr.dtype == torch.int32 and qr.is_contiguous() and kr.is_contiguous()):
+            return prepared
+        plan = _shared_plan(cross_attn_params, "cross", q_rows_[0].shape[1], q_rows_[0].shape[0], kv_x.shape[0], qr, kr)
+        out = None if proj_buf is not None else torch.empty(
+            (sq, b, self.model_config.num_attention_heads, F.HEAD_DIM), dtype=kv_x.dtype, device=kv_x.device)
+        return q_rows_, kv_x, out, plan
+
+    def _cross_attention_prepare(self, mixed_qqkv, key_value_states, q_rows=None):
         sq, b, _ = mixed_qqkv.shape
         Hq, Hkv = self.model_config.num_attention_heads, self.model_config.num_query_groups
         eps, z = self.model_config.layernorm_epsilon, self.model_config.apply_layernorm_1p
@@ -432,13 +450,19 @@ class FullyParallelAttention(nn.Module):
             q_rows.append(q_i)
         return q_rows, kv_x
 
-    def cross_attention_attend(self, prepared, shape, cross_attn_params: PackedCrossAttnParams, proj_buf=None):
-        """cross_attention, dit_module.py:1098-1136, on the tensors of cross_attention_prepare."""
-        q_rows, kv_x = prepared
+    def cross_attention_attend(self, prepared, shape, cross_attn_params: PackedCrossAttnParams, proj_buf=None,
+                               independent=False):
+        """cross_attention, dit_module.py:1098-1136, on the tensors of cross_attention_prepare.
+        independent: the launch directly follows the self-attention launch of the same layer; with a destination and
+        plan that `cross_attention_prepare` made before that launch it shares nothing with it and may overlap its
+        tail (functional.attn_ranges independent_of_prev)."""
+        q_rows, kv_x = prepared[:2]
+        pre_out, pre_plan = (prepared[2], prepared[3]) if len(prepared) == 4 else (None, None)
         sq, b = shape
         Hq = self.model_config.num_attention_heads
-        out = None if proj_buf is not None else torch.empty((sq, b, Hq, F.HEAD_DIM), dtype=kv_x.dtype,
-                                                            device=kv_x.device)
+        out = None if proj_buf is not None else pre_out if pre_out is not None else torch.empty(
+            (sq, b, Hq, F.HEAD_DIM), dtype=kv_x.dtype, device=kv_x.device)
+        independent = independent and pre_plan is not None and b == 1
         # q_ranges / kv_ranges (the flex_flash_attn_func arguments, dit_module.py:1111-1122) rather than cu_seqlens:
         # they stay valid when a caption segment is empty and after the per-rank rewrite under context parallelism
         n = cross_attn_params.q_ranges.shape[0]
@@ -452,12 +476,12 @@ class FullyParallelAttention(nn.Module):
                 dst = dict(proj_input=(proj_buf.view(sq, b, -1)[:, i], 1, self.PROJ_GROUPS))
             else:
                 dst = dict(out=out[:, i])
-            plan = None
-            if b == 1 and qr.dtype == torch.int32 and qr.is_contiguous() and kr.is_contiguous():
+            plan = pre_plan
+            if plan is None and b == 1 and qr.dtype == torch.int32 and qr.is_contiguous() and kr.is_contiguous():
                 plan = _shared_plan(cross_attn_params, "cross", q_rows[i].shape[1], q_rows[i].shape[0], kv_x.shape[0],
                                     qr, kr)
             F.attn_ranges(q_rows[i], kv_x[..., :F.HEAD_DIM], kv_x[..., F.HEAD_DIM:], qr, kr, return_lse=False,
-                          plan=plan, **dst)
+                          plan=plan, independent_of_prev=independent, **dst)
         return None if proj_buf is not None else out.view(sq, b, Hq * F.HEAD_DIM)
 
     def cross_attention(self, mixed_qqkv, key_value_states, cross_attn_params: PackedCrossAttnParams, proj_buf=None,
@@ -529,18 +553,24 @@ class FullyParallelAttention(nn.Module):
                           (cache[:start, :, :F.HEAD_DIM], cache[:start, :, F.HEAD_DIM:]))
             if offload:
                 KVOffload.of(inference_params, dev).store(self.layer_number, cache, kv_new, start, app)
+            # the cross-attention's own projections / norms, destination and plan come first: the launch of its
+            # attention then follows the self-attention launch with nothing shared between the two
+            xp = meta_args.cross_attn_params
+            # ... provided a self-attention kernel IS launched in between (batch 1: one launch over all ranges)
+            overlap = batch_size == 1 and rows > 0 and meta_args.core_attn_params.q_range.shape[0] > 0
             if fused_proj_input:
                 buf = torch.empty((rows, 2 * Hq * F.HEAD_DIM), dtype=dt, device=dev)
+                x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states, xq_rows, xp, proj_buf=buf)
                 self.core_attention(query, kv_new[..., :F.HEAD_DIM], kv_new[..., F.HEAD_DIM:], batch_size, meta_args,
                                     kc, vc, proj_buf=buf)
-                self.cross_attention(mixed_qqkv, key_value_states, meta_args.cross_attn_params, proj_buf=buf,
-                                     q_rows=xq_rows)
+                self.cross_attention_attend(x_prepared, (sq, batch_size), xp, proj_buf=buf, independent=overlap)
                 return buf.view(sq, batch_size, 2 * Hq * F.HEAD_DIM)
+            x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states, xq_rows, xp)
+            core_out = torch.empty_like(query)
             core = self.core_attention(query, kv_new[..., :F.HEAD_DIM], kv_new[..., F.HEAD_DIM:], batch_size,
-                                       meta_args, kc, vc)
+                                       meta_args, kc, vc, out=core_out)
             core_attn_out = core.view(sq, batch_size, Hq * F.HEAD_DIM)
-            xattn_out = self.cross_attention(mixed_qqkv, key_value_states, meta_args.cross_attn_params,
-                                             q_rows=xq_rows)
+            xattn_out = self.cross_attention_attend(x_prepared, (sq, batch_size), xp, independent=overlap)
 
         elif fused_proj_input:
             raise NotImplementedError("fused_proj_input is available with cp_strategy 'none'")
@@ -654,7 +684,7 @@ class FullyParallelAttention(nn.Module):
                        peer_kv_out=kv_ptrs, peer_row_offset=row_off, peer_heads=(hq_loc, hkv_loc))
         # no communication in the cross-attention (context_parallel.py:591): its projections + norms are issued
         # before the barrier, its attention before the second one
-        x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states)
+        x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states, None, meta_args.cross_attn_params)
         ws.barrier()                                                     # A: every rank's q / kv rows have landed
         kv = cache[start:start + total_rows] if direct else ws.kv
         if cache is not None and app > 0 and not direct:
@@ -665,7 +695,7 @@ class FullyParallelAttention(nn.Module):
         p = meta_args.core_attn_params
         F.attn_ranges(ws.q, kv[..., :F.HEAD_DIM], kv[..., F.HEAD_DIM:], p.q_range, p.k_range, k_cache=kc, v_cache=vc,
                       return_lse=False, peer_out=(ws.out_ptrs, bounds, head_off, Hq))
-        xattn_out = self.cross_attention_attend(x_prepared, (sq, b), meta_args.cross_attn_params)
+        xattn_out = self.cross_attention_attend(x_prepared, (sq, b), meta_args.cross_attn_params, independent=True)
         ws.barrier()                                                     # B: every rank's output rows have landed
         # the workspace is reused by the next layer: hand out a private copy of this rank's rows
         core_attn_out = ws.out[:split[rank]].reshape(sq, b, Hq * F.HEAD_DIM).clone()
@@ -775,7 +805,7 @@ class FullyParallelAttention(nn.Module):
                                       sin_emb, cos_emb, batch=1, eps=eps, zero_centered_gamma=z,
                                       gather_kv_out=targets, gather_geometry=(n_me, clip, off_me),
                                       gather_multicast=use_mc)
-        x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states)
+        x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states, None, meta_args.cross_attn_params)
         ws.barrier()                                              # every rank's K/V stripes have landed everywhere
         kv = cache[start:start + total_rows] if direct else buf[:total_rows]
         if cache is not None and app > 0 and not direct:
@@ -792,7 +822,8 @@ class FullyParallelAttention(nn.Module):
                 q_range = self._stripe_ranges[key] = torch.stack([e[:-1], e[1:]], 1).contiguous().to(dev)
             F.attn_ranges(query, kv[..., :F.HEAD_DIM], kv[..., F.HEAD_DIM:], q_range, p.k_range, k_cache=kc, v_cache=vc,
                           out=out, return_lse=False)
-        xattn_out = self.cross_attention_attend(x_prepared, (sq, b), meta_args.cross_attn_params)
+        xattn_out = self.cross_attention_attend(x_prepared, (sq, b), meta_args.cross_attn_params,
+                                                independent=sq > 0)
         if direct and self.model_config.num_layers < 2:
             # the peers' next forward writes this layer's cache slot again: with a single layer there is no other
             # layer's barrier between this attention and that prologue

@@ -238,6 +238,9 @@ int magi_attn_fwd(const magi_attn_args* a, void* stream_) {
     p.peer_bounds[a->num_peers] = a->peer_row_bounds[a->num_peers];
   }
 
+  MAGI_CHECK(a->launch_dependency == 0 || (a->launch_dependency == 1 && a->plan_ready),
+             "launch_dependency must be 0, or 1 together with plan_ready");
+  p.pdl_wait_at_end = a->launch_dependency == 1;
   const CUtensorMap maps[5] = {tm_q, tm_ka, tm_va, tm_kb, tm_vb};
   if (use_pair) MAGI_CUDA(magi::attn_pair_launch(maps, p, sms, stream));
   else MAGI_CUDA(magi::attn_fwd_launch(maps, p, sms, stream));

@@ -28,8 +28,12 @@ namespace {
 constexpr int kTileM = 128;               // query rows per softmax warpgroup
 constexpr int kPairM = 2 * kTileM;        // query rows per work item
 constexpr int kTileN = 128;               // keys per K/V tile
+// Measured interleaved in one process (tools/ab_variants.py, profiles/r02o_ab.log, cfg2 self-attention at the power
+// cap): Q single-buffered + 4 K/V stages 9.096 ms, + 5 stages 9.106, Q double-buffered + 3 stages 9.387 (9.185 with the
+// predicated P V issue path): the K/V ring depth is worth more than prefetching the next item's Q, also for the
+// 4-tile cross-attention items (364 vs 374 us).
 #ifndef MAGI_Q_STAGES
-#define MAGI_Q_STAGES 2     // the next item's Q tiles are prefetched while the current item runs (1 = single buffer, 4 KV stages)
+#define MAGI_Q_STAGES 1     // 2: the next item's Q tiles are prefetched while the current item runs (3 K/V stages)
 #endif
 #ifndef MAGI_KV_STAGES
 #define MAGI_KV_STAGES (MAGI_Q_STAGES == 1 ? 4 : 3)   // smem: (2 * Q stages + KV stages) * 32 KB <= 224 KB
@@ -208,6 +212,17 @@ __device__ __forceinline__ void issue_pv(uint32_t d_tmem, uint32_t p_tmem, uint6
   }
 }
 
+// The common case of issue_pv - a full tile (nks == 8) - without the per-k-step predicates: the issuer's instruction
+// count between "P half published" and the first UTCHMMA is on the critical path of every tile (the softmax
+// warpgroup's next S_t can only follow P_t V), and the predicated form costs ~50 instructions there against ~15.
+__device__ __forceinline__ void issue_pv_full(uint32_t d_tmem, uint32_t p_tmem, uint64_t v_desc, uint32_t accumulate,
+                                              int half) {
+#pragma unroll
+  for (int ks = 4 * half; ks < 4 * half + 4; ++ks)
+    mma_ts(d_tmem, p_tmem + 64 * half + (ks - 4 * half) * 8, v_desc + static_cast<uint64_t>((ks * 2048) >> 4), kIdescPV,
+           ks > 0 ? 1u : accumulate);
+}
+
 }  // namespace
 
 __global__ void attn_setup_kernel(const int* __restrict__ q_ranges, const int* __restrict__ k_ranges,
@@ -276,6 +291,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int* __restrict__ ws = p.work;
 
   if (threadIdx.x == 0) {
+    pdl_launch_dependents();   // the next launch in the stream may take the SMs this grid leaves (common.cuh)
     for (int s = 0; s < kQStages; ++s) {
       mbar_init(&bar->q_full[s], 1);
       mbar_init(&bar->q_empty[s], 1);
@@ -307,6 +323,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (!p.pdl_wait_at_end) pdl_wait();   // set-up above overlapped the tail of the kernel before; its results from here
   const uint32_t tmem_base = bar->tmem_base;
   const int total_items = ws[0];
 
@@ -591,13 +608,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // O_t (+)= P_t V in two 64-key halves, each issued as soon as the softmax warpgroup has published that half of P
     auto pv = [&](uint32_t tO, uint32_t tS, int t, uint32_t& ph, uint32_t vst_, uint32_t acc, int nks) {
       const uint64_t vd = desc_v(kv_addr + vst_ * kTileBytes);
+#ifdef MAGI_NO_PV_FAST
+      const bool full = false;
+#else
+      const bool full = nks == 8;   // warp-uniform
+#endif
       mbar_wait_warp(&bar->p_half[t][0], ph);
       tc_fence_after();
-      if (elect_one()) issue_pv(tO, tS, vd, acc, 0, nks);
+      if (full) { if (elect_one()) issue_pv_full(tO, tS, vd, acc, 0); }
+      else if (elect_one()) issue_pv(tO, tS, vd, acc, 0, nks);
       __syncwarp();
       mbar_wait_warp(&bar->p_half[t][1], ph);
       tc_fence_after();
-      if (elect_one()) issue_pv(tO, tS, vd, acc, 1, nks);
+      if (full) { if (elect_one()) issue_pv_full(tO, tS, vd, acc, 1); }
+      else if (elect_one()) issue_pv(tO, tS, vd, acc, 1, nks);
       __syncwarp();
       ph ^= 1;
     };
@@ -759,6 +783,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if constexpr (kSplit == 1) setmaxnreg_dec<MAGI_AUX_REGS>();   // idle warps (setmaxnreg is warpgroup-collective)
   }
 
+  if (p.pdl_wait_at_end) pdl_wait();    // complete in stream order even though nothing here depended on that kernel
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
@@ -786,8 +811,8 @@ cudaError_t attn_fwd_launch(const CUtensorMap* maps, const AttnKernelParams& p, 
     if (e != cudaSuccess) return e;
     if (dev < 64) attr_set[dev] = true;
   }
-  attn_fwd_kernel<<<num_ctas, kThreads, kSmemBytes, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
-  return cudaGetLastError();
+  return launch_kernel(attn_fwd_kernel, num_ctas, kThreads, kSmemBytes, stream, pdl_enabled(), maps[0], maps[1],
+                       maps[2], maps[3], maps[4], p);
 }
 
 }  // namespace magi

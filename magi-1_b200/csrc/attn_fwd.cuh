@@ -21,6 +21,11 @@ struct AttnKernelParams {
   int peer_head_offset;
   void* peer_out[8];
   int64_t peer_bounds[9];
+  // programmatic dependent launch: 0 = everything this launch touches may depend on the kernel before it in the stream
+  // (griddepcontrol.wait right after the CTA's set-up); 1 = the caller asserts that nothing this launch reads or writes
+  // is touched by that kernel (magi_attn_args.launch_dependency): the wait moves to the end of the kernel, so its CTAs
+  // do their work on the SMs the earlier kernel has already left, and the launch still completes in stream order
+  int pdl_wait_at_end;
 };
 
 // workspace ints: [total_items, n, 0, 0][prefix n+1][q0 n][q1 n][k0 n][k1 n]

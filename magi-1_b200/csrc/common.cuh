@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #ifndef MAGI_WATCHDOG_NS
 #define MAGI_WATCHDOG_NS 4000000000ull  // an mbarrier wait longer than 4 s traps instead of hanging the GPU
@@ -39,6 +40,39 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ int uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
 __device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
+// ---------------------------------------------------------------- programmatic dependent launch (griddepcontrol)
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become resident while the kernel
+// before it in the stream is still running: as soon as every CTA of that kernel has executed launch_dependents (or
+// exited). It must execute pdl_wait() before it touches anything the earlier kernel reads or writes; the wait returns
+// when the earlier grid has completed and its memory is visible. Both are no-ops in a plain launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Launch with (pdl = true) or without the programmatic-serialization attribute.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream,
+                                 bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(static_cast<unsigned>(block));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// MAGI_PDL=0 turns the attribute off everywhere (plain stream-ordered launches).
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MAGI_PDL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
 
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

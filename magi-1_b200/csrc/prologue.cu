@@ -149,10 +149,12 @@ __global__ void __launch_bounds__(kRingThreads, MAGI_PRO_RING_BLOCKS) prologue_r
   const int warp = uniform(static_cast<int>(threadIdx.x >> 5));
 
   if (threadIdx.x == 0) {
+    pdl_launch_dependents();
     for (int i = 0; i < kRingStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kRingGroup); }
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_wait();   // programmatic dependent launch (common.cuh): nothing before this line touches global memory
 
   const uint32_t rows = static_cast<uint32_t>(p.rows);
   const uint32_t upr_q = (p.Hq + kRingUnitHeads - 1) / kRingUnitHeads;
@@ -533,8 +535,8 @@ static cudaError_t prologue_launch_t(const PrologueParams& p, int64_t units, int
   const int64_t need = (units / kRingGroup + kRingConsumerGroups) / kRingConsumerGroups;
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
-  prologue_ring_kernel<kLnBf16, kMode><<<static_cast<int>(blocks), kRingThreads, kRingSmemBytes, stream>>>(p);
-  return cudaGetLastError();
+  return launch_kernel(prologue_ring_kernel<kLnBf16, kMode>, static_cast<int>(blocks), kRingThreads, kRingSmemBytes,
+                       stream, pdl_enabled(), p);
 }
 cudaError_t prologue_launch(const PrologueParams& p, bool ln_bf16, int sms, cudaStream_t stream) {
   int64_t units = 0;

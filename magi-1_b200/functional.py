@@ -121,8 +121,15 @@ def attn_ranges(
     peer_out: Optional[Tuple[Sequence[int], Sequence[int], int, int]] = None,
     kernel: int = 0,
     plan: Optional[AttnPlan] = None,
+    independent_of_prev: bool = False,
 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Range-masked attention over keys = concat(k_cache, k_new) without materialising the concatenation.
+
+    independent_of_prev: the caller asserts that no tensor of this call (inputs, `out`, the ranges, the plan) is read
+    or written by the kernel launched just before it on the stream (magi_attn_args.launch_dependency = 1): the launch
+    then overlaps that kernel's tail instead of waiting for it, and still completes in stream order. Needs a `plan`
+    and a caller-provided destination (`out` / `proj_input`) allocated BEFORE that earlier kernel was launched - a
+    tensor allocated in between may reuse memory the earlier kernel is still reading.
 
     plan: an `attn_plan` result for the same ranges / head count / token counts (checked): skips the per-call work-list
     kernel and workspace allocation.
@@ -248,6 +255,10 @@ def attn_ranges(
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 4
     a.num_sms = num_sms
     a.kernel = kernel
+    if independent_of_prev:
+        if plan is None or return_lse or peer_out is not None or (proj_input is None and zero_fill):
+            raise ValueError("independent_of_prev needs a plan and a destination allocated by the caller (no lse)")
+        a.launch_dependency = 1
     if peer_out is not None:
         a.num_peers, a.peer_head_offset = len(ptrs), head_off
         for i, ptr in enumerate(ptrs):

@@ -78,8 +78,10 @@ def qk_norm_rope(x_q, x_k, x_v, num_heads_q, num_heads_kv, ln_q, ln_k, sin, cos,
 
 def attn_ranges(q, k_new, v_new, q_ranges=None, k_ranges=None, k_cache=None, v_cache=None, cu_seqlens_q=None,
                 cu_seqlens_k=None, softmax_scale=None, out=None, return_lse=True, zero_fill=False, num_sms=0,
-                proj_input=None, peer_out=None, kernel=0, plan=None):
+                proj_input=None, peer_out=None, kernel=0, plan=None, independent_of_prev=False):
     assert peer_out is None, "peer routing has no CPU double"
+    if independent_of_prev:   # the real function's preconditions (functional.attn_ranges)
+        assert plan is not None and not return_lse and (out is not None or proj_input is not None)
     if plan is not None:   # the real function checks the plan against the call; so does the double
         tk = sum(t.shape[0] for t in (k_cache, k_new) if t is not None)
         assert plan == ("plan", q_ranges.data_ptr(), k_ranges.data_ptr(), q.shape[1], q.shape[0], tk), "stale plan"
