@@ -225,18 +225,29 @@ class HotPath:
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.inputs.values())
         self.d2h_bytes = 2 * self.core_out.numel() * 2
 
+    # phase marks (diagnostic steps only, phase_breakdown_leg): an event after every phase of a layer
+    marks = None
+
+    def mark(self, name):
+        if self.marks is not None:
+            e = self.torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.marks.append((name, e))
+
     # -- one layer, single GPU
     def layer(self, l, timed_events=False):
         F, w, inp, torch = self.F, self.w, self.inputs, self.torch
         cache = self.caches[l]
         q, kv = F.qk_norm_rope(inp["xq"], inp["xk"], inp["xv"], w["Hq"], w["Hkv"], self.ln["q"], self.ln["k"],
                                inp["sin"], inp["cos"], cache=cache, cache_row_offset=self.start, cache_rows=self.S)
+        self.mark("prologue_qkv")
         kc = vc = None
         if self.start > 0:
             kc, vc = cache[:self.start, :, :128], cache[:self.start, :, 128:]
         # the cross-attention's projections + norms (and both plans) are issued BEFORE the self-attention so that the
         # cross-attention launch that follows it depends on nothing the self-attention kernel touches
         x_prepared = self.cross_prepare(inp)
+        self.mark("prologue_cross")
         plan = self.plan("self", q, self.start + kv.shape[0], self.q_ranges, self.k_ranges)
         if timed_events:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -246,7 +257,9 @@ class HotPath:
         if timed_events:
             e1.record()
             self.attn_events.append((e0, e1))
-        self.cross_attend(x_prepared, independent=not timed_events)
+        self.mark("self_attention")
+        self.cross_attend(x_prepared, independent=not timed_events and self.marks is None)
+        self.mark("cross_attention")
 
     def cross_prepare(self, inp):
         F, w = self.F, self.w
@@ -321,8 +334,11 @@ class HotPath:
                        inp["cos"], head_perm_cp=cp, peer_q_out=ws.q_ptrs,
                        peer_kv_out=[p_ + self.start * row_bytes for p_ in self.cache_ptrs[l]],
                        peer_row_offset=self.row_off, peer_heads=(self.hq_loc, self.hkv_loc))
+        self.mark("prologue_qkv")
         x_prepared = self.cross_prepare(inp)
+        self.mark("prologue_cross")
         ws.barrier()
+        self.mark("barrier_a")
         kv = cache[self.start:self.start + self.S]
         kc = vc = None
         if self.start > 0:
@@ -336,8 +352,11 @@ class HotPath:
         if timed_events:
             e1.record()
             self.attn_events.append((e0, e1))
-        self.cross_attend(x_prepared, independent=not timed_events)
+        self.mark("self_attention")
+        self.cross_attend(x_prepared, independent=not timed_events and self.marks is None)
+        self.mark("cross_attention")
         ws.barrier()
+        self.mark("barrier_b")
         self.core_out = ws.out[:self.S_loc]
 
     # -- one layer, ring-KV (FullyParallelAttention._forward_ring): every rank keeps its query shard with all heads, the
@@ -747,6 +766,35 @@ def timed_leg(cx, hp, steps, warm, graph=False):
                 clocks=clk.summary(), events_steps=events_steps, graph=replay is not None)
 
 
+def phase_breakdown_leg(cx, hp, steps=2):
+    """Diagnostic, after the timed region: `steps` eager steps with an event after every phase of every layer; average
+    microseconds per layer and phase, max over ranks. The events serialise the launches (no overlap of the
+    cross-attention with the self-attention's tail), so the sum is an upper bound of the timed step's layer time."""
+    torch = cx.torch
+    if hp.layer_fn() not in (hp.layer, hp.layer_cp_fused):
+        return None
+    hp.marks = []
+    cx.barrier()
+    tot, cnt = {}, {}
+    for _ in range(steps):
+        hp.marks.append(("start", None))
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        hp.marks[-1] = ("start", e)
+        hp.step()
+    cx.barrier()
+    prev = None
+    for name, e in hp.marks:
+        if name != "start" and prev is not None:
+            tot[name] = tot.get(name, 0.0) + prev.elapsed_time(e) * 1e3
+            cnt[name] = cnt.get(name, 0) + 1
+        prev = e
+    hp.marks = None
+    out = {k: round(cx.max_over_ranks(tot[k] / cnt[k]), 1) for k in tot}
+    out["sum"] = round(sum(out.values()), 1)
+    return out
+
+
 def e2e_leg(cx, hp, steps):
     """End to end through the public API with HOST buffers: every step copies all of its inputs in from pinned host
     memory and all of its results out, inside the timed region. Inputs and outputs are double-buffered on one copy
@@ -944,6 +992,8 @@ def main():
                       "double-buffered on a copy stream" + (" (per rank: its token shard in, its rows out)"
                                                             if world > 1 else "")}
 
+    phases = phase_breakdown_leg(cx, hp) if not args.profile else None
+
     # ---- multi-GPU parity of the path that was just timed
     cp_parity = cp_parity_leg(cx, hp, w) if world > 1 and not args.profile else None
 
@@ -1013,6 +1063,8 @@ def main():
                          "pct_of_bf16_datasheet_2250": round(100 * value / world / 2250.0, 1)},
         }
         # measured companions ride inside `roofline` too: the driver's record keeps that object whole
+        if phases is not None:
+            line["roofline"]["phases_us_per_layer"] = phases
         if cp_parity is not None:
             line["cp_parity"] = cp_parity
             line["roofline"]["cp_parity"] = {k: cp_parity.get(k) for k in ("mode", "max_abs", "bound", "ok", "skipped")

@@ -241,6 +241,7 @@ int magi_attn_fwd(const magi_attn_args* a, void* stream_) {
   MAGI_CHECK(a->launch_dependency == 0 || (a->launch_dependency == 1 && a->plan_ready),
              "launch_dependency must be 0, or 1 together with plan_ready");
   p.pdl_wait_at_end = a->launch_dependency == 1;
+  p.counters = ws + magi::attn_workspace_ints(a->n_ranges) - 2;
   const CUtensorMap maps[5] = {tm_q, tm_ka, tm_va, tm_kb, tm_vb};
   if (use_pair) MAGI_CUDA(magi::attn_pair_launch(maps, p, sms, stream));
   else MAGI_CUDA(magi::attn_fwd_launch(maps, p, sms, stream));

@@ -38,6 +38,13 @@ constexpr int kTileN = 128;               // keys per K/V tile
 #ifndef MAGI_KV_STAGES
 #define MAGI_KV_STAGES (MAGI_Q_STAGES == 1 ? 4 : 3)   // smem: (2 * Q stages + KV stages) * 32 KB <= 224 KB
 #endif
+// MAGI_DYNAMIC_SCHED=1: work items are handed out by an atomic counter (the TMA warp fetches the CTA's next item and
+// publishes it to the other roles through a two-slot shared-memory mailbox) instead of the static boustrophedon walk.
+// Items are sorted longest-first, so this is LPT list scheduling; it is what lets a launch that overlaps the tail of
+// the kernel before it (launch_dependency = 1) do ALL of its work on the SMs that are already free.
+#ifndef MAGI_DYNAMIC_SCHED
+#define MAGI_DYNAMIC_SCHED 1
+#endif
 constexpr int kQStages = MAGI_Q_STAGES;
 constexpr int kStages = MAGI_KV_STAGES;   // K/V smem ring depth (tiles; K and V alternate)
 constexpr int kBlkBytes = 128 * 64 * 2;   // one 64-column (128 B wide) swizzle block of a 128-row tile
@@ -115,6 +122,8 @@ struct Barriers {
   uint64_t q_full[kQStages], q_empty[kQStages];
   uint64_t kv_full[kStages], kv_empty[kStages];
   uint64_t s_full[2], p_half[2][2], o_full[2], o_free[2];
+  uint64_t item_full[2], item_empty[2];   // MAGI_DYNAMIC_SCHED mailbox
+  int sched[2];
   uint32_t tmem_base;
   // exchange buffers of the two threads that share a row (only with MAGI_COL_SPLIT == 2)
   float xch[kSplit == 2 ? 2 : 1][2][2][kSplit == 2 ? 128 : 1];   // [parity][q tile][column half][row]: row max
@@ -267,6 +276,9 @@ __global__ void attn_setup_kernel(const int* __restrict__ q_ranges, const int* _
     prefix[n] = acc;
     ws[0] = acc;
     ws[1] = n;
+    int* counters = ws + attn_workspace_ints(n) - 2;   // {next item, CTAs finished}: MAGI_DYNAMIC_SCHED
+    counters[0] = 0;
+    counters[1] = 0;
   }
 }
 
@@ -306,6 +318,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_init(&bar->p_half[t][1], kTileM / 32);
       mbar_init(&bar->o_full[t], 1);
       mbar_init(&bar->o_free[t], kSplit * kTileM / 32);
+      mbar_init(&bar->item_full[t], 1);
+      mbar_init(&bar->item_empty[t], kSoftmaxWarps + 1);   // every softmax warp + the MMA issuer
     }
     fence_barrier_init();
   }
@@ -326,6 +340,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if (!p.pdl_wait_at_end) pdl_wait();   // set-up above overlapped the tail of the kernel before; its results from here
   const uint32_t tmem_base = bar->tmem_base;
   const int total_items = ws[0];
+#if MAGI_DYNAMIC_SCHED
+  // consumer side of the item mailbox (softmax warps, MMA issuer): -1 = no more work
+  uint32_t cslot = 0, cphase = 0;
+  auto next_item = [&]() -> int {
+    mbar_wait(&bar->item_full[cslot], cphase);
+    const int item = *reinterpret_cast<volatile int*>(&bar->sched[cslot]);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar->item_empty[cslot]);
+    if (++cslot == 2) { cslot = 0; cphase ^= 1; }
+    return item;
+  };
+#endif
 
   if (warp < kSoftmaxWarps) {
     // ====================================================================== softmax warpgroups
@@ -354,6 +380,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       return fmaxf(v, bar->xch[par][t][ch ^ 1][rowq]);
     };
 
+#if MAGI_DYNAMIC_SCHED
+    for (int item = next_item(); item >= 0; item = next_item()) {
+#else
     for (int round = 0; round * static_cast<int>(gridDim.x) < total_items; ++round) {
       // items are sorted longest-first; CTAs walk them boustrophedon (0..G-1, G-1..0, ...) so that the CTA that drew
       // the longest item of one round draws the shortest of the next: static LPT-like balance without atomics
@@ -361,6 +390,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                        ((round & 1) ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x)
                                     : static_cast<int>(blockIdx.x));
       if (item >= total_items) continue;
+#endif
       Item it;
       decode_item(ws, item, p.Hq, group, p.len_a, it);
       const int row = it.qrow0 + row_in_item;
@@ -646,11 +676,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       __syncwarp();
       return r1 >> 4;
     };
+#if MAGI_DYNAMIC_SCHED
+    for (int item = next_item(); item >= 0; item = next_item()) {
+#else
     for (int round = 0; round * static_cast<int>(gridDim.x) < total_items; ++round) {
       const int item = round * static_cast<int>(gridDim.x) +
                        ((round & 1) ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x)
                                     : static_cast<int>(blockIdx.x));
       if (item >= total_items) continue;
+#endif
       Item it;
       decode_item(ws, item, p.Hq, group, p.len_a, it);
       const int nt = uniform(it.nt);
@@ -735,11 +769,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if constexpr (kSplit == 1) setmaxnreg_dec<MAGI_AUX_REGS>();
     uint32_t stage = 0, phase = 0;  // kv ring (producer side)
     uint32_t item_cnt = 0;
+#if MAGI_DYNAMIC_SCHED
+    // scheduler: draws this CTA's next item from the global counter once all loads of the current one are issued
+    // (a few tiles before the other roles finish it) and posts it in the mailbox
+    uint32_t sslot = 0, sphase = 0;
+    auto draw = [&]() -> int {
+      mbar_wait_warp(&bar->item_empty[sslot], sphase ^ 1);
+      int item = 0;
+      if (lane == 0) item = atomicAdd(p.counters, 1);
+      item = uniform(item);
+      if (item >= total_items) item = -1;
+      if (lane == 0) {
+        *reinterpret_cast<volatile int*>(&bar->sched[sslot]) = item;
+        mbar_arrive(&bar->item_full[sslot]);
+      }
+      __syncwarp();
+      if (++sslot == 2) { sslot = 0; sphase ^= 1; }
+      return item;
+    };
+    for (int item = draw(); item >= 0; item = draw()) {
+#else
     for (int round = 0; round * static_cast<int>(gridDim.x) < total_items; ++round) {
       const int item = round * static_cast<int>(gridDim.x) +
                        ((round & 1) ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x)
                                     : static_cast<int>(blockIdx.x));
       if (item >= total_items) continue;
+#endif
       Item it;
       decode_item(ws, item, p.Hq, group, p.len_a, it);
       it.nt = uniform(it.nt); it.nt_a = uniform(it.nt_a);
@@ -787,6 +842,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+#if MAGI_DYNAMIC_SCHED
+  // the last CTA to leave rearms the counters: the plan is reused by the next layer's launch (stream-ordered after this)
+  if (threadIdx.x == 0 && atomicAdd(p.counters + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+    p.counters[0] = 0;
+    p.counters[1] = 0;
+    __threadfence();
+  }
+#endif
 }
 
 #ifdef MAGI_TRACE

@@ -26,10 +26,13 @@ struct AttnKernelParams {
   // is touched by that kernel (magi_attn_args.launch_dependency): the wait moves to the end of the kernel, so its CTAs
   // do their work on the SMs the earlier kernel has already left, and the launch still completes in stream order
   int pdl_wait_at_end;
+  int* counters;                              // {next item, CTAs finished}, the last two ints of the plan workspace
 };
 
-// workspace ints: [total_items, n, 0, 0][prefix n+1][q0 n][q1 n][k0 n][k1 n]
-inline size_t attn_workspace_ints(int n) { return 4 + (size_t)(n + 1) + 4 * (size_t)n; }
+// workspace ints: [total_items, n, 0, 0][prefix n+1][q0 n][q1 n][k0 n][k1 n][pad to 4][0, 0, next item, CTAs finished]
+__host__ __device__ inline size_t attn_workspace_ints(int n) {
+  return ((4 + (size_t)(n + 1) + 4 * (size_t)n + 3) & ~(size_t)3) + 4;
+}
 
 // Builds the LPT-ordered work list on the device from (q_ranges,k_ranges) or (cu_q,cu_k); no host sync.
 cudaError_t attn_setup_launch(const int* q_ranges, const int* k_ranges, const int* cu_q, const int* cu_k, int n,
