@@ -104,8 +104,11 @@ constexpr int kEmuMod = MAGI_EMU_MOD;
 //                           computed: sum >= max, and an inf / NaN fails the comparison too), for the second half off
 //                           a max over ITS 64 columns only (32 FMNMX3 instead of 108 FMNMX3 / FMNMX per tile). Either
 //                           guard failing takes the same exact path as before (reload S, true tile max, rescale O).
+//                           Measured interleaved (tools/ab_variants.py, profiles/r02r_ab.log, r02s_ab.log): 9.01-9.07 ms
+//                           against 9.30-9.31 for the full max tracking on the cfg2 self-attention launch at the power
+//                           cap (+3 %) once the K/V ring is 4 deep; neutral with the 3-deep ring of round 1.
 #ifndef MAGI_GUARD_BY_SUM
-#define MAGI_GUARD_BY_SUM 0
+#define MAGI_GUARD_BY_SUM 1
 #endif
 constexpr float kSumGuard = 32768.f;      // 2^15: a 64-column half of P summing to more than this re-references the row
 
