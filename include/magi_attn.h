@@ -95,7 +95,10 @@ typedef struct magi_attn_args {
    *   peer_out[rho] + (g - peer_row_bounds[rho]) * out_token_stride + (peer_head_offset + h) * out_head_stride
    * i.e. all_to_all_output_split followed by "(cp sq) hn hd -> sq (cp hn) hd" (context_parallel.py:404-423, 596)
    * performed by the epilogue's own stores over NVLink peer memory. `out` is then unused (may be NULL); rows outside
-   * every bound are dropped. The caller owns the cross-GPU synchronisation. */
+   * every bound are dropped. The caller owns the cross-GPU synchronisation.
+   * Together with out_group_heads > 0 the grouped addressing above applies to the destination head
+   * H = peer_head_offset + h: (H / out_group_heads) * out_group_stride + (H % out_group_heads) * out_head_stride, i.e.
+   * the rows land directly in the owner's out-projection input (single-CTA kernel only). */
   int32_t num_peers;
   int32_t peer_head_offset;
   void* peer_out[MAGI_MAX_PEERS];

@@ -91,6 +91,7 @@ class KVOffload:
         self.stage = [None, None]          # ping-pong device staging buffers (rows, Hkv, 256)
         self.prefetched = {}               # layer -> (buffer index, rows, event)
         self.written = {}                  # layer -> event of the last device -> host write-back
+        self.last_store = None             # event of the most recent write-back of any layer
         self.h2d_bytes = self.d2h_bytes = self.prefetch_hits = 0
 
     @classmethod
@@ -157,6 +158,7 @@ class KVOffload:
         ev = torch.cuda.Event()
         ev.record(self.copy_stream)
         self.written[layer] = ev
+        self.last_store = ev
         self.prefetched.pop(layer, None)   # a staged copy of this layer is stale now
         self.d2h_bytes += rows * cache[0].numel() * cache.element_size()
 
@@ -241,7 +243,7 @@ class FullyParallelAttention(nn.Module):
                 and cpm.UlyssesPeerWorkspace.available(mpu.get_cp_group(), device))
 
     def _fused_ring(self, batch_size, device) -> bool:
-        return (self.engine_config.cp_strategy == "cp_ring_kv" and batch_size == 1 and not self.engine_config.kv_offload
+        return (self.engine_config.cp_strategy == "cp_ring_kv" and batch_size == 1
                 and getattr(self.engine_config, "cp_fused_all_to_all", False)
                 and cpm.RingGatherWorkspace.available(mpu.get_cp_group(), device))
 
@@ -572,11 +574,19 @@ class FullyParallelAttention(nn.Module):
             core_attn_out = core.view(sq, batch_size, Hq * F.HEAD_DIM)
             xattn_out = self.cross_attention_attend(x_prepared, (sq, batch_size), xp, independent=overlap)
 
-        elif fused_proj_input:
-            raise NotImplementedError("fused_proj_input is available with cp_strategy 'none'")
+        elif fused_proj_input and not (strategy == "cp_ulysses" and self._fused_ulysses(batch_size, dev)):
+            raise NotImplementedError("fused_proj_input is available with cp_strategy 'none' and on the fused "
+                                      "cp_ulysses path (see supports_fused_proj_input)")
         elif strategy == "cp_ulysses":
-            fwd = self._forward_ulysses_fused if self._fused_ulysses(batch_size, dev) else self._forward_ulysses
-            core_attn_out, xattn_out = fwd(mixed_qqkv, key_value_states, inference_params, sin_emb, cos_emb, meta_args)
+            if self._fused_ulysses(batch_size, dev):
+                res = self._forward_ulysses_fused(mixed_qqkv, key_value_states, inference_params, sin_emb, cos_emb,
+                                                  meta_args, fused_proj_input=fused_proj_input)
+                if fused_proj_input:
+                    return res
+                core_attn_out, xattn_out = res
+            else:
+                core_attn_out, xattn_out = self._forward_ulysses(mixed_qqkv, key_value_states, inference_params,
+                                                                 sin_emb, cos_emb, meta_args)
         elif strategy == "cp_ring_kv":
             fwd = self._forward_ring_fused if self._fused_ring(batch_size, dev) else self._forward_ring
             core_attn_out, xattn_out = fwd(mixed_qqkv, key_value_states, inference_params, sin_emb, cos_emb, meta_args)
@@ -655,7 +665,15 @@ class FullyParallelAttention(nn.Module):
         return out
 
     # ------------------------------------------------------------------ Ulysses, all-to-alls fused into the kernels
-    def _forward_ulysses_fused(self, mixed_qqkv, key_value_states, inference_params, sin_emb, cos_emb, meta_args):
+    def supports_fused_proj_input(self, batch_size: int, device) -> bool:
+        """Can forward(..., fused_proj_input=True) run here: single GPU, or Ulysses with the fused all-to-alls."""
+        if self.model_config.num_attention_heads % self.PROJ_GROUPS != 0:
+            return False
+        s_ = self.engine_config.cp_strategy
+        return s_ == "none" or (s_ == "cp_ulysses" and self._fused_ulysses(batch_size, device))
+
+    def _forward_ulysses_fused(self, mixed_qqkv, key_value_states, inference_params, sin_emb, cos_emb, meta_args,
+                               fused_proj_input=False):
         """dit_module.py:1175-1205 without NCCL on the data path: ONE prologue launch stores every head slice of q and
         [K|V] straight into the owning rank's receive buffer, the attention epilogue stores every output row straight
         into the buffer of the rank that owns the row (NVLink peer memory; include/magi_attn.h "peer" fields). Two
@@ -684,7 +702,14 @@ class FullyParallelAttention(nn.Module):
                        peer_kv_out=kv_ptrs, peer_row_offset=row_off, peer_heads=(hq_loc, hkv_loc))
         # no communication in the cross-attention (context_parallel.py:591): its projections + norms are issued
         # before the barrier, its attention before the second one
-        x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states, None, meta_args.cross_attn_params)
+        proj = proj_ptrs = None
+        if fused_proj_input:
+            # the out-projection input of this rank's rows, in symmetric memory: slot 0 of "(hn n hd)" is filled by
+            # every rank's attention epilogue (its heads), slot 1 by the local cross-attention - no cat, no rearrange,
+            # no copy out of the receive buffer
+            proj, proj_ptrs = ws.next_proj()
+        x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states, None, meta_args.cross_attn_params,
+                                                  proj_buf=proj[:sq] if fused_proj_input else None)
         ws.barrier()                                                     # A: every rank's q / kv rows have landed
         kv = cache[start:start + total_rows] if direct else ws.kv
         if cache is not None and app > 0 and not direct:
@@ -693,8 +718,18 @@ class FullyParallelAttention(nn.Module):
         if cache is not None and start > 0:
             kc, vc = cache[:start, :, :F.HEAD_DIM], cache[:start, :, F.HEAD_DIM:]
         p = meta_args.core_attn_params
+        plan = _shared_plan(p, "core-ulysses", ws.q.shape[1], ws.q.shape[0],
+                            total_rows + (0 if kc is None else kc.shape[0]), p.q_range, p.k_range)
+        if fused_proj_input:
+            F.attn_ranges(ws.q, kv[..., :F.HEAD_DIM], kv[..., F.HEAD_DIM:], p.q_range, p.k_range, k_cache=kc,
+                          v_cache=vc, return_lse=False, peer_out=(proj_ptrs, bounds, head_off, Hq),
+                          peer_proj=(0, self.PROJ_GROUPS), plan=plan)
+            self.cross_attention_attend(x_prepared, (sq, b), meta_args.cross_attn_params, proj_buf=proj[:sq],
+                                        independent=True)
+            ws.barrier()                                                 # B: every rank's output rows have landed
+            return proj[:sq].view(sq, b, 2 * Hq * F.HEAD_DIM)
         F.attn_ranges(ws.q, kv[..., :F.HEAD_DIM], kv[..., F.HEAD_DIM:], p.q_range, p.k_range, k_cache=kc, v_cache=vc,
-                      return_lse=False, peer_out=(ws.out_ptrs, bounds, head_off, Hq))
+                      return_lse=False, peer_out=(ws.out_ptrs, bounds, head_off, Hq), plan=plan)
         xattn_out = self.cross_attention_attend(x_prepared, (sq, b), meta_args.cross_attn_params, independent=True)
         ws.barrier()                                                     # B: every rank's output rows have landed
         # the workspace is reused by the next layer: hand out a private copy of this rank's rows
@@ -788,9 +823,12 @@ class FullyParallelAttention(nn.Module):
         n_me, off_me = sizes[rank], sum(sizes[:rank])
         total_rows = dn * clip
         cache, start, app = self._cache_plan(inference_params, meta_args, total_rows, dt, dev)
+        # kv_offload: the (replicated) cache lives in pinned host memory; the gathered K/V land in the workspace, go
+        # back to the host on the copy stream and the cache prefix is staged through KVOffload like everywhere else
+        offload = self._offloaded(cache)
         ws = cpm.RingGatherWorkspace.get(group, total_rows, Hkv, dev)
         buf, ptrs, mc = ws.next()
-        direct = (cache is not None and app == total_rows
+        direct = (cache is not None and app == total_rows and not offload
                   and getattr(self, "_cache_peer_of", None) == cache.data_ptr())
         if direct:
             slot = start * Hkv * 2 * F.HEAD_DIM * 2
@@ -806,13 +844,22 @@ class FullyParallelAttention(nn.Module):
                                       gather_kv_out=targets, gather_geometry=(n_me, clip, off_me),
                                       gather_multicast=use_mc)
         x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states, None, meta_args.cross_attn_params)
+        if offload:
+            # the other workspace buffer is rewritten by the peers once they are past THIS barrier: the write-back that
+            # still reads it (issued by the previous layer on the copy stream) has to be done before we enter
+            off = KVOffload.of(inference_params, dev)
+            if off.last_store is not None:
+                torch.cuda.current_stream(dev).wait_event(off.last_store)
         ws.barrier()                                              # every rank's K/V stripes have landed everywhere
         kv = cache[start:start + total_rows] if direct else buf[:total_rows]
-        if cache is not None and app > 0 and not direct:
+        if offload:
+            off.store(self.layer_number, cache, kv, start, app)
+        elif cache is not None and app > 0 and not direct:
             F.kv_cache_append(cache, kv, start, app)
         kc = vc = None
         if cache is not None and start > 0:
-            kc, vc = cache[:start, :, :F.HEAD_DIM], cache[:start, :, F.HEAD_DIM:]
+            kc, vc = (self._offload_views(inference_params, cache, start) if offload else
+                      (cache[:start, :, :F.HEAD_DIM], cache[:start, :, F.HEAD_DIM:]))
         out = torch.empty((sq, Hq, F.HEAD_DIM), dtype=dt, device=dev)
         if sq > 0:
             key = (dn, n_me, str(dev))
@@ -839,8 +886,9 @@ class FullyParallelAttention(nn.Module):
                 raise NotImplementedError("cp_ring_kv with batch size > 1 supports the cache-less uncond pass only")
             return self._forward_ulysses(mixed_qqkv, key_value_states, inference_params, sin_emb, cos_emb, meta_args)
         if self.engine_config.kv_offload:
-            raise NotImplementedError("kv_offload is available with cp_strategy 'none', 'cp_ulysses' and "
-                                      "'cp_shuffle_overlap'")
+            raise NotImplementedError("cp_ring_kv with kv_offload runs on the fused gather path only "
+                                      "(cp_fused_all_to_all with NVLink peer access); the NCCL ring keeps the cache "
+                                      "resident")
         Hq, Hkv = self.model_config.num_attention_heads, self.model_config.num_query_groups
         eps, z = self.model_config.layernorm_epsilon, self.model_config.apply_layernorm_1p
         dev, dt = mixed_qqkv.device, mixed_qqkv.dtype

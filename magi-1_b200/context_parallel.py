@@ -468,6 +468,23 @@ class UlyssesPeerWorkspace:
         self.q_ptrs = [int(p) for p in self.h_q.buffer_ptrs]
         self.kv_ptrs = [int(p) for p in self.h_kv.buffer_ptrs]
         self.out_ptrs = [int(p) for p in self.h_out.buffer_ptrs]
+        self._alloc, self._proj_shape, self.proj, self.proj_ptrs, self.proj_calls = alloc, (max_local_rows, 2 * heads_q * 128), None, None, 0
+
+    def next_proj(self):
+        """(buffer, peer pointers) of this call's out-projection input "sq (hn n hd)" (fused_proj_input under the fused
+        Ulysses path): every rank's attention epilogue stores its heads' self-attention rows into slot n = 0 of the
+        OWNER's buffer, the local cross-attention fills slot n = 1. Two buffers used alternately, allocated on first
+        use (collective: every rank makes the same sequence of calls): the tensor handed to the caller stays valid
+        until the call after next - a peer writes buffer b again only after barrier A of that call, which this rank
+        enters after everything it issued in between - so no private copy is made."""
+        if self.proj is None:
+            pairs = [self._alloc(self._proj_shape) for _ in range(2)]
+            self.proj = [t for t, _ in pairs]
+            self._h_proj = [h for _, h in pairs]
+            self.proj_ptrs = [[int(p) for p in h.buffer_ptrs] for h in self._h_proj]
+        b = self.proj_calls % 2
+        self.proj_calls += 1
+        return self.proj[b], self.proj_ptrs[b]
 
     def barrier(self) -> None:
         """All ranks of the group, on the current stream, no host synchronisation."""

@@ -216,17 +216,20 @@ int magi_attn_fwd(const magi_attn_args* a, void* stream_) {
   p.len_a = len_a;
   const float scale = a->softmax_scale > 0.f ? a->softmax_scale : 0.08838834764831845f;  // 1/sqrt(128)
   p.scale_log2 = scale * 1.4426950408889634f;
-  MAGI_CHECK(a->out_group_heads >= 0 && (a->out_group_heads == 0 || (a->num_heads_q % a->out_group_heads == 0 &&
-                                                                    a->out_group_stride % 8 == 0)),
+  // with peers the groups are groups of the DESTINATION's heads (peer_head_offset + h), which this call cannot count
+  MAGI_CHECK(a->out_group_heads >= 0 &&
+                 (a->out_group_heads == 0 || ((a->num_peers > 0 || a->num_heads_q % a->out_group_heads == 0) &&
+                                              a->out_group_stride % 8 == 0)),
              "out_group_heads must divide num_heads_q and out_group_stride must be a multiple of 8 elements");
   p.out_group_heads = a->out_group_heads;
   p.out_group_stride = a->out_group_stride;
   p.num_peers = a->num_peers;
-  p.peer_head_offset = a->peer_head_offset;
+  p.peer_head_offset = a->num_peers > 0 ? a->peer_head_offset : 0;
   for (int i = 0; i < 8; ++i) { p.peer_out[i] = nullptr; p.peer_bounds[i] = 0; }
   p.peer_bounds[8] = 0;
   if (a->num_peers > 0) {
-    MAGI_CHECK(a->out_group_heads == 0 && a->lse == nullptr, "peer output routing excludes grouped output and lse");
+    MAGI_CHECK(a->lse == nullptr, "peer output routing excludes lse");
+    MAGI_CHECK(a->out_group_heads == 0 || !use_pair, "grouped peer output needs the single-CTA kernel");
     MAGI_CHECK(a->peer_head_offset >= 0, "negative peer_head_offset");
     for (int i = 0; i < a->num_peers; ++i) {
       MAGI_CHECK(a->peer_out[i] && (reinterpret_cast<uintptr_t>(a->peer_out[i]) & 15) == 0, "bad peer_out[%d]", i);

@@ -563,11 +563,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
 
       // ------------------------------------------------------------------ epilogue for this row
+      const int hd = p.peer_head_offset + it.h;   // head index in the destination (peer_head_offset = 0 without peers)
       const int64_t head_off =
           p.out_group_heads > 0
-              ? static_cast<int64_t>(it.h / p.out_group_heads) * p.out_group_stride +
-                    static_cast<int64_t>(it.h % p.out_group_heads) * p.out_head_stride
-              : static_cast<int64_t>(it.h) * p.out_head_stride;
+              ? static_cast<int64_t>(hd / p.out_group_heads) * p.out_group_stride +
+                    static_cast<int64_t>(hd % p.out_group_heads) * p.out_head_stride
+              : static_cast<int64_t>(hd) * p.out_head_stride;
       __nv_bfloat16* orow = out + static_cast<int64_t>(row) * p.out_token_stride + head_off + ch * kCols;
       bool store_ok = row_valid;
       if (p.num_peers > 0) {
@@ -579,7 +580,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         store_ok = row_valid && rho >= 0;
         if (store_ok)
           orow = reinterpret_cast<__nv_bfloat16*>(p.peer_out[rho]) + (row - p.peer_bounds[rho]) * p.out_token_stride +
-                 static_cast<int64_t>(p.peer_head_offset + it.h) * p.out_head_stride + ch * kCols;
+                 head_off + ch * kCols;
       }
       if (it.nt > 0) {
         if constexpr (kSplit == 2) {   // total row sum = sum of the two column halves

@@ -122,6 +122,7 @@ def attn_ranges(
     kernel: int = 0,
     plan: Optional[AttnPlan] = None,
     independent_of_prev: bool = False,
+    peer_proj: Optional[Tuple[int, int]] = None,
 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Range-masked attention over keys = concat(k_cache, k_new) without materialising the concatenation.
 
@@ -140,6 +141,9 @@ def attn_ranges(
     local head h is stored into the (rows_rho, heads_total, 128) bf16 buffer at pointers[rho] of the rank rho with
     row_bounds[rho] <= g < row_bounds[rho + 1], at row g - row_bounds[rho], head head_offset + h (NVLink peer
     memory; include/magi_attn.h). Returns (None, None); the caller synchronises the ranks.
+
+    peer_proj = (n, hn), with peer_out: the peers' buffers are out-projection inputs (rows_rho, 2 * heads_total * 128)
+    laid out "(hn n hd)" (see proj_input); the rows go straight into slot n of the owner's buffer.
 
     proj_input = (buffer, n, hn): instead of a (Tq, Hq, 128) tensor, write the result straight into the reference's
     out-projection input `buffer` (Tq, 2 * Hq * 128), laid out "(hn n hd)" with n = 0 for self-attention and n = 1
@@ -208,6 +212,14 @@ def attn_ranges(
         if len(ptrs) > _lib.MAX_PEERS or len(bounds) != len(ptrs) + 1:
             raise ValueError("peer_out needs at most 8 pointers and one more row bound than pointers")
         out_ptr, out_ts, out_hs = None, heads_total * HEAD_DIM, HEAD_DIM
+        if peer_proj is not None:
+            n_src, hn = peer_proj
+            if heads_total % hn != 0 or n_src not in (0, 1):
+                raise ValueError("peer_proj: hn must divide heads_total and n must be 0 or 1")
+            group_heads = heads_total // hn
+            group_stride = 2 * group_heads * HEAD_DIM
+            out_ts = 2 * heads_total * HEAD_DIM
+            ptrs = [int(p_) + n_src * group_heads * HEAD_DIM * 2 for p_ in ptrs]
     elif out is None:
         out = (torch.zeros if zero_fill else torch.empty)((Tq, Hq, HEAD_DIM), dtype=torch.bfloat16, device=q.device)
     else:

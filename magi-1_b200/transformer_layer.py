@@ -82,8 +82,7 @@ class TransformerLayer(nn.Module):
                 meta_args: ModelMetaArgs):
         residual = hidden_states
         attn = self.self_attention
-        if (self.engine_config.cp_strategy == "none"
-                and self.model_config.num_attention_heads % FullyParallelAttention.PROJ_GROUPS == 0):
+        if attn.supports_fused_proj_input(hidden_states.shape[1], hidden_states.device):
             # both attention kernels write straight into the out-projection input (dit_module.py:1332-1338); the
             # "(n hn hd) -> (hn n hd)" groups are whole heads when Hq is a multiple of hn = 8 (24 and 48 are)
             proj_in = attn(hidden_states, y_xattn_flat, inference_params, rotary_pos_emb, meta_args,

@@ -249,11 +249,12 @@ def qk_norm_rope(x_q, x_k, x_v, num_heads_q, num_heads_kv, ln_q, ln_k, sin, cos,
     return None, None
 
 
-def attn_ranges(q, k_new, v_new, q_ranges=None, k_ranges=None, *, peer_out=None, **kw):  # noqa: F811
+def attn_ranges(q, k_new, v_new, q_ranges=None, k_ranges=None, *, peer_out=None, peer_proj=None, **kw):  # noqa: F811
     if peer_out is None:
         return _plain_attn_ranges(q, k_new, v_new, q_ranges, k_ranges, **kw)
     ptrs, bounds, head_off, heads_total = peer_out
     kw.pop("out", None)
+    kw.pop("independent_of_prev", None)
     res, _ = _plain_attn_ranges(q, k_new, v_new, q_ranges, k_ranges, **dict(kw, return_lse=False))
     covered = np.zeros(q.shape[0], dtype=bool)
     for a, b in q_ranges.numpy().reshape(-1, 2):
@@ -262,6 +263,15 @@ def attn_ranges(q, k_new, v_new, q_ranges=None, k_ranges=None, *, peer_out=None,
     for rho, ptr in enumerate(ptrs):    # row g of local head h -> rank rho's output, row g - bounds[rho], head slot
         lo, hi = int(bounds[rho]), int(bounds[rho + 1])
         rows = torch.from_numpy(np.nonzero(covered[lo:hi])[0])
-        if len(rows):
+        if not len(rows):
+            continue
+        if peer_proj is None:
             _peer(ptr, (0, heads_total, HEAD_DIM))[rows, head_off:head_off + hq] = res[lo:hi][rows]
+        else:    # the owner's out-projection input "(hn n hd)": destination head H -> group H // gh, slot n, H % gh
+            n_src, hn = peer_proj
+            gh = heads_total // hn
+            dst = _peer(ptr, (0, hn, 2, gh, HEAD_DIM))
+            for h in range(hq):
+                H = head_off + h
+                dst[rows, H // gh, n_src, H % gh] = res[lo:hi][rows, h]
     return None, None

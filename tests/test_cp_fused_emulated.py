@@ -41,6 +41,12 @@ class _UlyssesWS:
         self.q, self.kv, self.out = bufs["q"][rank], bufs["kv"][rank], bufs["out"][rank]
         self.q_ptrs, self.kv_ptrs, self.out_ptrs = bufs["q_ptrs"], bufs["kv_ptrs"], bufs["out_ptrs"]
         self._b = shared.barrier
+        self._proj, self._proj_ptrs, self.proj_calls, self.rank = bufs["proj"], bufs["proj_ptrs"], 0, rank
+
+    def next_proj(self):
+        b = self.proj_calls % 2
+        self.proj_calls += 1
+        return self._proj[b][self.rank], self._proj_ptrs[b]
 
     def barrier(self):
         self._b.wait()
@@ -87,6 +93,8 @@ def emulation(monkeypatch):
                          out=[zeros(max_local_rows, heads_q, 128) for _ in range(w)])
                 for n in ("q", "kv", "out"):
                     b[n + "_ptrs"] = [D.fake_ptr(t) for t in b[n]]
+                b["proj"] = [[zeros(max_local_rows, 2 * heads_q * 128) for _ in range(w)] for _ in range(2)]
+                b["proj_ptrs"] = [[D.fake_ptr(t) for t in b["proj"][i]] for i in range(2)]
                 return b
             bufs = group.collective(("uly", total_rows, max_local_rows, hq_loc, hkv_loc, heads_q), make)
             key = ("uly_ws", TLS.rank, total_rows, max_local_rows)
@@ -135,9 +143,13 @@ def i32(a):
     return torch.as_tensor(np.asarray(a, dtype=np.int32))
 
 
-@pytest.mark.parametrize("strategy,world,Hq,Hkv", [("cp_ulysses", 2, 4, 2), ("cp_ulysses", 4, 4, 2),
-                                                   ("cp_ring_kv", 2, 4, 2), ("cp_ring_kv", 3, 6, 2)])
-def test_fused_paths_match_single_rank_through_a_cache_sequence(emulation, strategy, world, Hq, Hkv):
+@pytest.mark.parametrize("strategy,world,Hq,Hkv,fused_proj", [
+    ("cp_ulysses", 2, 4, 2, False), ("cp_ulysses", 4, 4, 2, False), ("cp_ring_kv", 2, 4, 2, False),
+    ("cp_ring_kv", 3, 6, 2, False),
+    # fused_proj_input under the fused Ulysses path: every rank's epilogue stores its heads into slot 0 of the OWNER's
+    # out-projection input "(hn n hd)" (hn = 8 groups), the local cross-attention fills slot 1; double-buffered
+    ("cp_ulysses", 2, 8, 2, True), ("cp_ulysses", 4, 16, 4, True)])
+def test_fused_paths_match_single_rank_through_a_cache_sequence(emulation, strategy, world, Hq, Hkv, fused_proj):
     A, cpm = emulation
     from magi_b200.common import (EngineConfig, InferenceParams, ModelConfig, ModelMetaArgs, PackedCoreAttnParams,
                                   PackedCrossAttnParams)
@@ -212,6 +224,11 @@ def test_fused_paths_match_single_rank_through_a_cache_sequence(emulation, strat
                     world, strategy, hs, torch.zeros(hs.shape[0], 1), rope, None, ardf, cpp, meta.cross_attn_params)
                 m_cp = dataclasses.replace(meta, cp_split_sizes=split, cross_attn_params=cross_l)
                 inf.update_kv_cache = upd
+                if fused_proj:
+                    assert m.supports_fused_proj_input(1, x.device)
+                    pin = m(x, kvs, inf, rope_l, m_cp, fused_proj_input=True)
+                    outs.append((pin.float().clone(), None, split))
+                    continue
                 core, xo = m(x, kvs, inf, rope_l, m_cp)
                 outs.append((core.float().clone(), xo.float().clone(), split))
             results[rank] = (outs, inf.key_value_memory_dict[1].float().clone())
@@ -232,6 +249,12 @@ def test_fused_paths_match_single_rank_through_a_cache_sequence(emulation, strat
         parts_c = [results[r][0][i][0] for r in range(world)]
         parts_x = [results[r][0][i][1] for r in range(world)]
         split = results[0][0][i][2]
+        if fused_proj:    # the reference's cat + rearrange (attn_linear_proj, dit_module.py:1332-1338) of the two outputs
+            want = A.FullyParallelAttention.attn_linear_proj_input(ref_core, ref_x).float()
+            got = torch.cat(parts_c, 0)
+            assert got.shape == want.shape
+            assert float((got - want).abs().max()) <= 1e-2, (strategy, world, i)
+            continue
         if strategy == "cp_ulysses":             # contiguous shards
             core, xo = torch.cat(parts_c, 0), torch.cat(parts_x, 0)
         else:                                    # every chunk striped across the ranks: local rows are (chunk, stripe)

@@ -90,8 +90,9 @@ def main():
         # cp_ring_kv: K/V all-gather fused into the prologue's stores (one attention launch), then the NCCL ring
         # CP_CHECK_KV_OFFLOAD=1 adds, for the two reference strategies, the NCCL path with the KV caches in pinned host
         # memory (kv_offload, dit_module.py:803-811) against the resident single-GPU forward
-        off_variants = ((1, False, True),) if (os.environ.get("CP_CHECK_KV_OFFLOAD") == "1"
-                                               and strategy != "cp_ring_kv") else ()
+        off_variants = ()
+        if os.environ.get("CP_CHECK_KV_OFFLOAD") == "1":   # cp_ring_kv: on the fused gather path (the NCCL ring has none)
+            off_variants = ((1, True, True),) if strategy == "cp_ring_kv" else ((1, False, True),)
         for overlap, fused, offload in ((((1, True, False), (1, False, False), (second, False, False))
                                          if strategy == "cp_ulysses" else
                                          ((1, True, False), (1, False, False)) if strategy == "cp_ring_kv" else
@@ -121,6 +122,14 @@ def main():
                     import dataclasses
                     m_cp = dataclasses.replace(m_cp, cp_pad_size=pad, core_attn_params=core_l)
                 core, xo = cp_m(x, kvs, inf_cp, rope_l, m_cp)
+                if strategy == "cp_ulysses" and fused and cp_m.supports_fused_proj_input(1, dev):
+                    # fused_proj_input under the fused path: the same forward again (cache untouched), both attention
+                    # kernels storing straight into the owner's out-projection input; must equal cat + rearrange
+                    inf_cp.update_kv_cache = False
+                    want = type(cp_m).attn_linear_proj_input(core, xo).clone()
+                    pin = cp_m(x, kvs, inf_cp, rope_l, m_cp, fused_proj_input=True)
+                    worst["proj"] = max(worst.get("proj", 0.0), (pin.float() - want.float()).abs().max().item())
+                    inf_cp.update_kv_cache = upd
                 core = cpm.cp_post_process(world, strategy, core.contiguous(), m_cp)
                 xo = cpm.cp_post_process(world, strategy, xo.contiguous(), m_cp)
                 worst["core"] = max(worst["core"], (core.float() - ref_core.float()).abs().max().item())
@@ -166,10 +175,11 @@ def main():
         ok = True
         for k, w in results.items():
             bound = 2.5e-2 if k.startswith("cp_ring_kv/nccl") else 0.0   # the fused gather keeps every row's key order
-            good = w["core"] <= bound and w["xattn"] == 0.0
+            good = w["core"] <= bound and w["xattn"] == 0.0 and w.get("proj", 0.0) == 0.0
             ok &= good
             print(f"[cp_check N={world}] {k}: core max_abs {w['core']:.3e} (bound {bound}) xattn max_abs "
-                  f"{w['xattn']:.3e} -> {'OK' if good else 'FAIL'}", flush=True)
+                  f"{w['xattn']:.3e}" + (f" fused_proj_input max_abs {w['proj']:.3e}" if "proj" in w else "")
+                  + f" -> {'OK' if good else 'FAIL'}", flush=True)
         mcast = [any(w_.mc_ptrs) for w_ in cpm.RingGatherWorkspace._instances.values()]
         print(f"[cp_check N={world}] fused gather stores: "
               f"{'NVSwitch multicast' if (mcast and all(mcast) and cpm.ring_multicast_enabled()) else 'per-peer NVLink stores'}"
