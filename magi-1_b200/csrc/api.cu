@@ -247,7 +247,7 @@ int magi_attn_fwd(const magi_attn_args* a, void* stream_) {
   p.counters = ws + magi::attn_workspace_ints(a->n_ranges) - 2;
   const CUtensorMap maps[5] = {tm_q, tm_ka, tm_va, tm_kb, tm_vb};
   if (use_pair) MAGI_CUDA(magi::attn_pair_launch(maps, p, sms, stream));
-  else MAGI_CUDA(magi::attn_fwd_launch(maps, p, sms, stream));
+  else MAGI_CUDA(magi::attn_fwd_launch(maps, p, sms, len_a + len_b, stream));
   g_launches++;
   return 0;
 }

@@ -38,7 +38,9 @@ __host__ __device__ inline size_t attn_workspace_ints(int n) {
 cudaError_t attn_setup_launch(const int* q_ranges, const int* k_ranges, const int* cu_q, const int* cu_k, int n,
                               int Hq, int total_q, int total_k, int* ws, cudaStream_t stream);
 // maps: {q, k_a, v_a, k_b, v_b}
-cudaError_t attn_fwd_launch(const CUtensorMap* maps, const AttnKernelParams& p, int num_ctas, cudaStream_t stream);
+// total_keys = rows of the whole key sequence (segments A + B): picks the scheduler mailbox flavour (attn_fwd.cu)
+cudaError_t attn_fwd_launch(const CUtensorMap* maps, const AttnKernelParams& p, int num_ctas, int total_keys,
+                            cudaStream_t stream);
 
 // CTA-pair kernel (attn_pair.cu): maps {q (128-row box), k_a (64-row box), v_a (128), k_b (64), v_b (128)}; num_ctas is
 // rounded down to an even number (one cluster of two CTAs per pair of SMs). Same params, work list and results.

@@ -411,6 +411,45 @@ def test_fused_all_to_all_routing_on_virtual_ranks(F, cp, Hq, Hkv):
                              return_lse=False, peer_out=([t.data_ptr() for t in out_recv], offs.tolist(), c * hn, Hq))
         assert o is None and l is None
     assert torch.equal(torch.cat(out_recv, 0), out_full)
+    if Hq % 8 == 0:
+        # fused_proj_input under the fused path (peer_proj): the same rows stored straight into slot n = 0 of every
+        # owner's out-projection input "sq (hn n hd)", hn = 8 (attn_linear_proj, dit_module.py:1332-1338)
+        proj = [torch.zeros(split[r], 2 * Hq * 128, dtype=torch.bfloat16, device="cuda") for r in range(cp)]
+        for c in range(cp):
+            F.attn_ranges(recv_q[c], recv_kv[c][..., :128], recv_kv[c][..., 128:], q_ranges, k_ranges,
+                          return_lse=False, peer_out=([t.data_ptr() for t in proj], offs.tolist(), c * hn, Hq),
+                          peer_proj=(0, 8))
+        got = torch.cat(proj, 0).view(S, 8, 2, Hq // 8, 128)
+        assert torch.equal(got[:, :, 0].reshape(S, Hq, 128), out_full)
+        assert not got[:, :, 1].any()          # slot n = 1 (the cross-attention's) is left alone
+
+
+def test_overlapped_launch_gives_the_same_bits(F):
+    """magi_attn_args.launch_dependency = 1: the cross-attention launch that may start under the tail of the
+    self-attention launch before it (programmatic dependent launch, wait moved to the end of the kernel) - same bits
+    as the serialised launch, for both launches, repeatedly, and the launch after the pair sees both finished."""
+    clip, Hq, Hkv = 1170, 3, 1                      # per-rank shapes of cp_ulysses with 8 ranks, scaled down
+    S = 4 * clip
+    q, kv = bf(rnd((S, Hq, 128), 1)), bf(rnd((S, Hkv, 256), 2))
+    qr = i32([[i * clip, (i + 1) * clip] for i in range(4)])
+    kr = i32([[0, (i + 1) * clip] for i in range(4)])
+    xq, xkv = bf(rnd((S // 8, 24, 128), 3)), bf(rnd((300, 8, 256), 4))
+    xqr, xkr = i32([[0, 200], [200, S // 8]]), i32([[0, 120], [120, 300]])
+    plan = F.attn_plan(qr, kr, num_heads_q=Hq, total_q=S, total_k=S)
+    xplan = F.attn_plan(xqr, xkr, num_heads_q=24, total_q=S // 8, total_k=300)
+    ref, _ = F.attn_ranges(q, kv[..., :128], kv[..., 128:], qr, kr, return_lse=False)
+    xref, _ = F.attn_ranges(xq, xkv[..., :128], xkv[..., 128:], xqr, xkr, return_lse=False)
+    torch.cuda.synchronize()
+    with pytest.raises(ValueError):                  # needs a plan and a caller-provided destination
+        F.attn_ranges(xq, xkv[..., :128], xkv[..., 128:], xqr, xkr, return_lse=False, independent_of_prev=True)
+    for _ in range(5):
+        out, xout = torch.full_like(ref, float("nan")), torch.full_like(xref, float("nan"))
+        F.attn_ranges(q, kv[..., :128], kv[..., 128:], qr, kr, out=out, return_lse=False, plan=plan)
+        F.attn_ranges(xq, xkv[..., :128], xkv[..., 128:], xqr, xkr, out=xout, return_lse=False, plan=xplan,
+                      independent_of_prev=True)
+        both = out.float().sum() + xout.float().sum()        # a plain launch after the pair: must see both complete
+        assert torch.equal(out, ref) and torch.equal(xout, xref)
+        assert torch.isfinite(both)
 
 
 @pytest.mark.parametrize("cp,clip", [(2, 150), (3, 100), (8, 333)])

@@ -17,6 +17,11 @@ from magi_b200 import _lib  # noqa: E402
 
 
 def use(path):
+    # lib_force0* / lib_force1*: copies of a build that are loaded with MAGI_SCHED_DECODED forced (read once per library)
+    name = os.path.basename(path)
+    os.environ.pop("MAGI_SCHED_DECODED", None)
+    if name.startswith("lib_force"):
+        os.environ["MAGI_SCHED_DECODED"] = name[9]
     _lib.LIB_PATH = path
     _lib._lib = None
     _lib.lib()
