@@ -120,6 +120,10 @@ typedef struct magi_attn_args {
    * order (everything after it sees both finished). The text cross-attention after the self-attention of the same
    * layer is such a launch (context_parallel.py:591: "no communication", no shared tensors). */
   int32_t launch_dependency;
+  /* != 0: query rows that no q range covers are written as zeros (lse = -inf) by the kernel itself - the behaviour
+   * flex_flash_attn_func / flash_attn_varlen_func callers rely on - instead of by a memset of the whole output before
+   * the launch. Plain output addressing only (no peers, no groups). */
+  int32_t fill_uncovered_rows;
 } magi_attn_args;
 
 MAGI_API size_t magi_attn_workspace_bytes(int32_t n_ranges);

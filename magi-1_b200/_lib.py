@@ -76,6 +76,7 @@ class MagiAttnArgs(C.Structure):
         ("kernel", C.c_int32),
         ("plan_ready", C.c_int32),
         ("launch_dependency", C.c_int32),
+        ("fill_uncovered_rows", C.c_int32),
     ]
 
 

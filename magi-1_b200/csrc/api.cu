@@ -176,7 +176,9 @@ int magi_attn_fwd(const magi_attn_args* a, void* stream_) {
   if (sms <= 0) { if (int r2 = device_sm_count(&sms)) return r2; }
   MAGI_CHECK(a->kernel >= 0 && a->kernel <= 2, "kernel must be 0 (default), 1 (single) or 2 (pair)");
   const int kernel_sel = a->kernel != 0 ? a->kernel : kernel_env;
-  const bool use_pair = (kernel_sel == 2 || (kernel_sel == 0 && MAGI_DEFAULT_PAIR)) && sms >= 2;
+  // an explicit kernel = 2 with fill_uncovered_rows is rejected below; a default / environment choice falls back
+  const bool use_pair = (kernel_sel == 2 || (kernel_sel == 0 && MAGI_DEFAULT_PAIR)) && sms >= 2 &&
+                        !(a->fill_uncovered_rows != 0 && a->kernel != 2);
   const int k_box = use_pair ? 64 : 128;   // a CTA of a pair stages its 64 keys of every K tile
 
   CUtensorMap tm_q, tm_ka, tm_va, tm_kb, tm_vb;
@@ -245,6 +247,10 @@ int magi_attn_fwd(const magi_attn_args* a, void* stream_) {
              "launch_dependency must be 0, or 1 together with plan_ready");
   p.pdl_wait_at_end = a->launch_dependency == 1;
   p.counters = ws + magi::attn_workspace_ints(a->n_ranges) - 2;
+  MAGI_CHECK(a->fill_uncovered_rows == 0 || (a->num_peers == 0 && a->out_group_heads == 0 && !use_pair),
+             "fill_uncovered_rows needs plain output addressing and the single-CTA kernel");
+  p.fill_uncovered = a->fill_uncovered_rows != 0;
+  p.total_q = (int)a->q.tokens;
   const CUtensorMap maps[5] = {tm_q, tm_ka, tm_va, tm_kb, tm_vb};
   if (use_pair) MAGI_CUDA(magi::attn_pair_launch(maps, p, sms, stream));
   else MAGI_CUDA(magi::attn_fwd_launch(maps, p, sms, len_a + len_b, stream));

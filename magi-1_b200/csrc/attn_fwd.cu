@@ -882,6 +882,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
   } else {
     if constexpr (kSplit == 1) setmaxnreg_dec<MAGI_AUX_REGS>();   // idle warps (setmaxnreg is warpgroup-collective)
+    // fill_uncovered: query rows that no range covers come back as zeros / lse = -inf (what the drop-in wrappers of
+    // flex_flash_attn_func / flash_attn_varlen_func promise) without a memset of the whole output before the launch:
+    // the first otherwise idle warp of every CTA tests its share of the rows against the plan's ranges
+#ifndef MAGI_NO_FILL   // (A/B builds only)
+    if (p.fill_uncovered && warp == kTmaWarp + 1) {
+      const int n = ws[1];
+      const int* rq0 = ws + 4 + (n + 1);
+      const int* rq1 = rq0 + n;
+      const int per_cta = (p.total_q + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+      const int r_end = min(p.total_q, (static_cast<int>(blockIdx.x) + 1) * per_cta);
+      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+      for (int r = static_cast<int>(blockIdx.x) * per_cta + lane; r < r_end; r += 32) {
+        bool covered = false;
+        for (int i = 0; i < n; ++i) covered |= (r >= rq0[i]) & (r < rq1[i]);
+        if (covered) continue;
+        for (int h = 0; h < p.Hq; ++h) {
+          __nv_bfloat16* orow = out + static_cast<int64_t>(r) * p.out_token_stride +
+                                static_cast<int64_t>(h) * p.out_head_stride;
+#pragma unroll
+          for (int c = 0; c < 128; c += 8) *reinterpret_cast<uint4*>(orow + c) = make_uint4(0, 0, 0, 0);
+          if (p.lse != nullptr) p.lse[static_cast<int64_t>(r) * p.Hq + h] = -INFINITY;
+        }
+      }
+    }
+#endif
   }
 
   if (p.pdl_wait_at_end) pdl_wait();    // complete in stream order even though nothing here depended on that kernel

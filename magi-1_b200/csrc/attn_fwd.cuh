@@ -27,6 +27,8 @@ struct AttnKernelParams {
   // do their work on the SMs the earlier kernel has already left, and the launch still completes in stream order
   int pdl_wait_at_end;
   int* counters;                              // {next item, CTAs finished}, the last two ints of the plan workspace
+  int fill_uncovered;                         // rows covered by no q range get out = 0, lse = -inf (single-CTA kernel)
+  int total_q;
 };
 
 // workspace ints: [total_items, n, 0, 0][prefix n+1][q0 n][q1 n][k0 n][k1 n][pad to 4][0, 0, next item, CTAs finished]

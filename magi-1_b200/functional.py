@@ -221,7 +221,10 @@ def attn_ranges(
             out_ts = 2 * heads_total * HEAD_DIM
             ptrs = [int(p_) + n_src * group_heads * HEAD_DIM * 2 for p_ in ptrs]
     elif out is None:
-        out = (torch.zeros if zero_fill else torch.empty)((Tq, Hq, HEAD_DIM), dtype=torch.bfloat16, device=q.device)
+        # zero_fill: the kernel writes the uncovered rows itself (fill_uncovered_rows); only a call that launches
+        # nothing (no ranges) needs the tensors cleared here
+        out = (torch.zeros if zero_fill and (n <= 0 or kernel == 2) else torch.empty)(
+            (Tq, Hq, HEAD_DIM), dtype=torch.bfloat16, device=q.device)
     else:
         _check_thd(out, "out")
         if out.shape != q.shape:
@@ -232,8 +235,8 @@ def attn_ranges(
         out_ptr, out_ts, out_hs = out.data_ptr(), out.stride(0), out.stride(1)
     lse = None
     if return_lse:
-        lse = torch.full((Tq, Hq), float("-inf"), dtype=torch.float32, device=q.device) if zero_fill else torch.empty(
-            (Tq, Hq), dtype=torch.float32, device=q.device)
+        lse = (torch.full((Tq, Hq), float("-inf"), dtype=torch.float32, device=q.device)
+               if zero_fill and (n <= 0 or kernel == 2) else torch.empty((Tq, Hq), dtype=torch.float32, device=q.device))
     if n <= 0 or Tq == 0:
         return out, lse
 
@@ -267,6 +270,8 @@ def attn_ranges(
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 4
     a.num_sms = num_sms
     a.kernel = kernel
+    if zero_fill and proj_input is None and peer_out is None and kernel != 2:   # (the pair kernel gets a pre-filled out)
+        a.fill_uncovered_rows = 1
     if independent_of_prev:
         if plan is None or return_lse or peer_out is not None or (proj_input is None and zero_fill):
             raise ValueError("independent_of_prev needs a plan and a destination allocated by the caller (no lse)")

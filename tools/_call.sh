@@ -1,3 +1,3 @@
-tag=r02zb; out=gpurun_out; mkdir -p $out
-for c in g_ragged_ranges h_two_segments j_many_items; do MAGI_ATTN_LIB=magi-1_b200/variants/lib_auto.so timeout 240 python tools/gpu_probe.py --run=$c 2>&1 | grep "^\[" | tail -1; done | tee $out/${tag}_probe.log
-timeout 600 python tools/ab_variants.py --rounds 5 --launches 30 2>&1 | tee $out/${tag}_ab.log
+tag=r02zd; out=gpurun_out; mkdir -p $out
+python -c "import __graft_entry__ as g; g.build()" > $out/${tag}_build.log 2>&1 || { echo "build failed"; exit 1; }
+timeout 900 python -m pytest tests -m gpu -q > $out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 $out/${tag}_pytest_gpu.log
