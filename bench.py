@@ -238,16 +238,18 @@ class HotPath:
     def layer(self, l, timed_events=False):
         F, w, inp, torch = self.F, self.w, self.inputs, self.torch
         cache = self.caches[l]
+        # ONE prologue launch per layer: q / k / v (+ KV-cache append) and the cross-attention's qx / text k / text v.
+        # Everything the cross-attention needs (and both plans) thereby exists BEFORE the self-attention launch, so the
+        # cross-attention launch that follows it depends on nothing the self-attention kernel touches
+        cross = self.cross_args(inp)
         q, kv = F.qk_norm_rope(inp["xq"], inp["xk"], inp["xv"], w["Hq"], w["Hkv"], self.ln["q"], self.ln["k"],
-                               inp["sin"], inp["cos"], cache=cache, cache_row_offset=self.start, cache_rows=self.S)
-        self.mark("prologue_qkv")
+                               inp["sin"], inp["cos"], cache=cache, cache_row_offset=self.start, cache_rows=self.S,
+                               cross=cross)
+        self.mark("prologue")
         kc = vc = None
         if self.start > 0:
             kc, vc = cache[:self.start, :, :128], cache[:self.start, :, 128:]
-        # the cross-attention's projections + norms (and both plans) are issued BEFORE the self-attention so that the
-        # cross-attention launch that follows it depends on nothing the self-attention kernel touches
-        x_prepared = self.cross_prepare(inp)
-        self.mark("prologue_cross")
+        x_prepared = self.cross_prepared(cross)
         plan = self.plan("self", q, self.start + kv.shape[0], self.q_ranges, self.k_ranges)
         if timed_events:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -261,7 +263,16 @@ class HotPath:
         self.cross_attend(x_prepared, independent=not timed_events and self.marks is None)
         self.mark("cross_attention")
 
+    def cross_args(self, inp):
+        """`cross=` of F.qk_norm_rope: the cross-attention's tensors ride in the layer's one prologue launch."""
+        return dict(x_qx=inp["qx"], ln_qx=self.lnx["q"], text_kv=inp["text_kv"], ln_tk=self.lnx["k"])
+
+    def cross_prepared(self, cross):
+        xq, xkv = cross["qx"], cross["tkv"]
+        return xq, xkv, self.plan("cross", xq, xkv.shape[0], self.x_q_ranges, self.x_k_ranges)
+
     def cross_prepare(self, inp):
+        """Two separate prologue launches (the NCCL paths, whose q and kv prologues are separate launches already)."""
         F, w = self.F, self.w
         xq, _ = F.qk_norm_rope(inp["qx"], None, None, w["Hq"], w["Hkv"], self.lnx["q"], None, None, None)
         tkv = inp["text_kv"]
@@ -330,13 +341,13 @@ class HotPath:
         F, w, inp, torch, cp = self.F, self.w, self.inputs, self.torch, self.cp
         cache, ws = self.caches[l], self.ws
         row_bytes = self.hkv_loc * 256 * 2
+        cross = self.cross_args(inp)
         F.qk_norm_rope(inp["xq"], inp["xk"], inp["xv"], w["Hq"], w["Hkv"], self.ln["q"], self.ln["k"], inp["sin"],
                        inp["cos"], head_perm_cp=cp, peer_q_out=ws.q_ptrs,
                        peer_kv_out=[p_ + self.start * row_bytes for p_ in self.cache_ptrs[l]],
-                       peer_row_offset=self.row_off, peer_heads=(self.hq_loc, self.hkv_loc))
-        self.mark("prologue_qkv")
-        x_prepared = self.cross_prepare(inp)
-        self.mark("prologue_cross")
+                       peer_row_offset=self.row_off, peer_heads=(self.hq_loc, self.hkv_loc), cross=cross)
+        self.mark("prologue")
+        x_prepared = self.cross_prepared(cross)
         ws.barrier()
         self.mark("barrier_a")
         kv = cache[self.start:self.start + self.S]
@@ -398,11 +409,12 @@ class HotPath:
         cache = self.caches[l]
         slot = self.start * w["Hkv"] * 256 * 2
         targets = [self.cache_mc[l] + slot] if self.ring_multicast else [p_ + slot for p_ in self.cache_ptrs[l]]
+        cross = self.cross_args(inp)
         q, _ = F.qk_norm_rope(inp["xq"], inp["xk"], inp["xv"], w["Hq"], w["Hkv"], self.ln["q"], self.ln["k"],
                               inp["sin"], inp["cos"], gather_kv_out=targets,
                               gather_geometry=(self.ring_sizes[self.rank], w["clip"], sum(self.ring_sizes[:self.rank])),
-                              gather_multicast=self.ring_multicast)
-        x_prepared = self.cross_prepare(inp)
+                              gather_multicast=self.ring_multicast, cross=cross)
+        x_prepared = self.cross_prepared(cross)
         self.ring_ws.barrier()
         kv = cache[self.start:self.start + self.S]
         kc = vc = None
@@ -662,8 +674,9 @@ def static_config(args, w, world):
                                       "ring-nccl": "ring-nccl"}[args.cp_mode]
     return {"workload": w["desc"], "name": args.workload,
             "parallelism": parallelism_desc(world, mode, args.overlap_degree, True),
-            "step": "attention hot path of one denoise forward over all layers: fused LN+RoPE prologue with KV-cache "
-                    "append, range-masked self-attention, text cross-attention",
+            "step": "attention hot path of one denoise forward over all layers, three launches per layer: fused LN+RoPE "
+                    "prologue (q / k / v with KV-cache append + the cross-attention's qx / text k / v), range-masked "
+                    "self-attention, text cross-attention",
             "tokens_q": w["clip"] * len(w["k_chunks"]), "layers": w["layers"],
             "flops_per_step": (self_f + cross_f) * w["layers"], "self_attn_flops_per_layer": self_f,
             "l2": "inputs larger than L2 (>= 600 MB of projection outputs re-read per layer)"}

@@ -210,6 +210,27 @@ typedef struct magi_prologue_args {
    * buffer (one store, replicated to every rank by the switch). The kernel then stores with multimem.st - the PTX ISA
    * leaves ordinary ld/st to a multimem address undefined. */
   int32_t gather_multicast;
+  /* Further tensors of the SAME launch - the cross-attention's half of a layer (get_xqkv, dit_module.py:1005-1021) - so
+   * that a layer's prologue is one launch instead of three. Always stored in place whatever the routing of q / k / v
+   * above; LayerNorm parameters bf16 (the `_xattn` norms are not promoted to fp32, dit_model.py:621-633), no RoPE.
+   *   x_qx  (rows, num_heads_q, 128) view       -> qx_out  (rows, num_heads_q, 128)
+   *   x_tk / x_tv (rows_t, num_heads_kv, 128) views (normally the two halves of the packed text projection,
+   *   head stride 256)                          -> tkv_out (rows_t, num_heads_kv, 256) packed [K | V]
+   * All NULL / 0 = off. */
+  const void* x_qx;
+  int64_t xqx_row_stride, xqx_head_stride; /* elements; head stride 0 selects 128 */
+  const void* ln_qx_w; /* bf16 */
+  const void* ln_qx_b;
+  void* qx_out;
+  int64_t qx_out_token_stride, qx_out_head_stride;
+  const void* x_tk;
+  const void* x_tv;
+  int64_t rows_t;
+  int64_t xt_row_stride, xt_head_stride;
+  const void* ln_tk_w; /* bf16 */
+  const void* ln_tk_b;
+  void* tkv_out;
+  int64_t tkv_out_token_stride, tkv_out_head_stride;
 } magi_prologue_args;
 
 MAGI_API int magi_qk_norm_rope_fwd(const magi_prologue_args* args, void* stream);

@@ -126,6 +126,24 @@ class MagiPrologueArgs(C.Structure):
         ("gather_chunk_stride", C.c_int64),
         ("gather_row_offset", C.c_int64),
         ("gather_multicast", C.c_int32),
+        ("x_qx", C.c_void_p),
+        ("xqx_row_stride", C.c_int64),
+        ("xqx_head_stride", C.c_int64),
+        ("ln_qx_w", C.c_void_p),
+        ("ln_qx_b", C.c_void_p),
+        ("qx_out", C.c_void_p),
+        ("qx_out_token_stride", C.c_int64),
+        ("qx_out_head_stride", C.c_int64),
+        ("x_tk", C.c_void_p),
+        ("x_tv", C.c_void_p),
+        ("rows_t", C.c_int64),
+        ("xt_row_stride", C.c_int64),
+        ("xt_head_stride", C.c_int64),
+        ("ln_tk_w", C.c_void_p),
+        ("ln_tk_b", C.c_void_p),
+        ("tkv_out", C.c_void_p),
+        ("tkv_out_token_stride", C.c_int64),
+        ("tkv_out_head_stride", C.c_int64),
     ]
 
 

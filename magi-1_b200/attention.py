@@ -410,15 +410,31 @@ class FullyParallelAttention(nn.Module):
                           return_lse=False, **dest(i))
         return out
 
+    def cross_prologue_inputs(self, mixed_qqkv, key_value_states, with_qx=True):
+        """The `cross=` argument of F.qk_norm_rope: the cross-attention's projections (qx, packed text [K|V]) and their
+        bf16 LayerNorm parameters, so that they ride in the SAME prologue launch as q / k / v (one prologue launch per
+        layer instead of three). None when that is not possible (batch > 1: the "(sq b) -> (b sq)" row order of the
+        query needs one strided view per batch row; `_xattn` norms promoted to fp32)."""
+        sq, b, _ = mixed_qqkv.shape
+        lq, lk = self._ln(self.q_layernorm_xattn), self._ln(self.k_layernorm_xattn)
+        if b != 1 or any(t.dtype != torch.bfloat16 for t in lq + lk) or mixed_qqkv.dtype != torch.bfloat16:
+            return None
+        Hkv = self.model_config.num_query_groups
+        kvx = torch.nn.functional.linear(key_value_states, self.linear_kv_xattn.weight)
+        d = dict(text_kv=kvx.view(key_value_states.shape[0], Hkv, 2 * F.HEAD_DIM), ln_tk=lk)
+        if with_qx:
+            d.update(x_qx=self.linear_qkv.forward_qx(mixed_qqkv.reshape(sq * b, -1)), ln_qx=lq)
+        return d
+
     def cross_attention_prepare(self, mixed_qqkv, key_value_states, q_rows=None, cross_attn_params=None,
-                                proj_buf=None):
+                                proj_buf=None, kv_x=None):
         """get_xqkv, dit_module.py:1005-1021: qx / text-kv projections + the two bf16 LayerNorms (no RoPE). Split from
         the attention itself so that, under context parallelism, this half can overlap the input all-to-alls and the
         attention half the output all-to-all.
         With cross_attn_params (batch 1) the result also carries everything else the attention launch needs - its
         destination and its work list - so that `cross_attention_attend(..., independent=True)` right after the
         self-attention launch touches nothing that was allocated or written after that launch was issued."""
-        prepared = self._cross_attention_prepare(mixed_qqkv, key_value_states, q_rows)
+        prepared = self._cross_attention_prepare(mixed_qqkv, key_value_states, q_rows, kv_x)
         sq, b, _ = mixed_qqkv.shape
         if cross_attn_params is None or b != 1:
             return prepared
@@ -431,10 +447,12 @@ class FullyParallelAttention(nn.Module):
             (sq, b, self.model_config.num_attention_heads, F.HEAD_DIM), dtype=kv_x.dtype, device=kv_x.device)
         return q_rows_, kv_x, out, plan
 
-    def _cross_attention_prepare(self, mixed_qqkv, key_value_states, q_rows=None):
+    def _cross_attention_prepare(self, mixed_qqkv, key_value_states, q_rows=None, kv_x=None):
         sq, b, _ = mixed_qqkv.shape
         Hq, Hkv = self.model_config.num_attention_heads, self.model_config.num_query_groups
         eps, z = self.model_config.layernorm_epsilon, self.model_config.apply_layernorm_1p
+        if kv_x is not None and q_rows is not None:   # both came out of the layer's one prologue launch
+            return q_rows, kv_x
         kvx = torch.nn.functional.linear(key_value_states, self.linear_kv_xattn.weight)  # (ytot, Hkv*256)
         kvx = kvx.view(key_value_states.shape[0], Hkv, 2 * F.HEAD_DIM)
         # text K: LayerNorm (bf16 params, no RoPE); V: copy -> packed (ytot, Hkv, 256)
@@ -542,13 +560,17 @@ class FullyParallelAttention(nn.Module):
                     query = None
             else:
                 query = None
+            x_kv = None
             if query is None:
                 xq, xk, xv = self._project(mixed_qqkv)
+                cross = self.cross_prologue_inputs(mixed_qqkv, key_value_states)
                 query, kv_new = F.qk_norm_rope(xq, xk, xv, Hq, Hkv, self._ln(self.q_layernorm),
                                                self._ln(self.k_layernorm), sin_emb, cos_emb, batch=batch_size, eps=eps,
                                                zero_centered_gamma=z,
                                                cache=cache if app > 0 and not offload else None,
-                                               cache_row_offset=start, cache_rows=app)
+                                               cache_row_offset=start, cache_rows=app, cross=cross)
+                if cross is not None:
+                    xq_rows, x_kv = [cross["qx"]], cross["tkv"]
             kc = vc = None
             if cache is not None and start > 0:
                 kc, vc = (self._offload_views(inference_params, cache, start) if offload else
@@ -562,12 +584,13 @@ class FullyParallelAttention(nn.Module):
             overlap = batch_size == 1 and rows > 0 and meta_args.core_attn_params.q_range.shape[0] > 0
             if fused_proj_input:
                 buf = torch.empty((rows, 2 * Hq * F.HEAD_DIM), dtype=dt, device=dev)
-                x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states, xq_rows, xp, proj_buf=buf)
+                x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states, xq_rows, xp, proj_buf=buf,
+                                                          kv_x=x_kv)
                 self.core_attention(query, kv_new[..., :F.HEAD_DIM], kv_new[..., F.HEAD_DIM:], batch_size, meta_args,
                                     kc, vc, proj_buf=buf)
                 self.cross_attention_attend(x_prepared, (sq, batch_size), xp, proj_buf=buf, independent=overlap)
                 return buf.view(sq, batch_size, 2 * Hq * F.HEAD_DIM)
-            x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states, xq_rows, xp)
+            x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states, xq_rows, xp, kv_x=x_kv)
             core_out = torch.empty_like(query)
             core = self.core_attention(query, kv_new[..., :F.HEAD_DIM], kv_new[..., F.HEAD_DIM:], batch_size,
                                        meta_args, kc, vc, out=core_out)
@@ -697,9 +720,12 @@ class FullyParallelAttention(nn.Module):
                   and getattr(self, "_cache_peer_of", None) == cache.data_ptr())
         row_bytes = hkv_loc * 2 * F.HEAD_DIM * 2
         kv_ptrs = [p_ + start * row_bytes for p_ in self._cache_peer_ptrs] if direct else ws.kv_ptrs
+        # the cross-attention's projections + norms ride in the same launch (they need no communication)
+        cross = self.cross_prologue_inputs(mixed_qqkv, key_value_states)
         F.qk_norm_rope(xq, xk, xv, Hq, Hkv, self._ln(self.q_layernorm), self._ln(self.k_layernorm), sin_emb, cos_emb,
                        batch=1, eps=eps, zero_centered_gamma=z, head_perm_cp=cp, peer_q_out=ws.q_ptrs,
-                       peer_kv_out=kv_ptrs, peer_row_offset=row_off, peer_heads=(hq_loc, hkv_loc))
+                       peer_kv_out=kv_ptrs, peer_row_offset=row_off, peer_heads=(hq_loc, hkv_loc), cross=cross)
+        xq_rows, x_kv = ([cross["qx"]], cross["tkv"]) if cross is not None else (None, None)
         # no communication in the cross-attention (context_parallel.py:591): its projections + norms are issued
         # before the barrier, its attention before the second one
         proj = proj_ptrs = None
@@ -708,8 +734,8 @@ class FullyParallelAttention(nn.Module):
             # every rank's attention epilogue (its heads), slot 1 by the local cross-attention - no cat, no rearrange,
             # no copy out of the receive buffer
             proj, proj_ptrs = ws.next_proj()
-        x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states, None, meta_args.cross_attn_params,
-                                                  proj_buf=proj[:sq] if fused_proj_input else None)
+        x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states, xq_rows, meta_args.cross_attn_params,
+                                                  proj_buf=proj[:sq] if fused_proj_input else None, kv_x=x_kv)
         ws.barrier()                                                     # A: every rank's q / kv rows have landed
         kv = cache[start:start + total_rows] if direct else ws.kv
         if cache is not None and app > 0 and not direct:
@@ -836,14 +862,18 @@ class FullyParallelAttention(nn.Module):
             mc = self._cache_mc_ptr + slot if self._cache_mc_ptr else 0
         use_mc = bool(mc and cpm.ring_multicast_enabled())
         targets = [mc] if use_mc else ptrs
-        query = None
+        query = xq_rows = x_kv = None
         if sq > 0:
             xq, xk, xv = self._project(mixed_qqkv)
+            cross = self.cross_prologue_inputs(mixed_qqkv, key_value_states)
             query, _ = F.qk_norm_rope(xq, xk, xv, Hq, Hkv, self._ln(self.q_layernorm), self._ln(self.k_layernorm),
                                       sin_emb, cos_emb, batch=1, eps=eps, zero_centered_gamma=z,
                                       gather_kv_out=targets, gather_geometry=(n_me, clip, off_me),
-                                      gather_multicast=use_mc)
-        x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states, None, meta_args.cross_attn_params)
+                                      gather_multicast=use_mc, cross=cross)
+            if cross is not None:
+                xq_rows, x_kv = [cross["qx"]], cross["tkv"]
+        x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states, xq_rows, meta_args.cross_attn_params,
+                                                  kv_x=x_kv)
         if offload:
             # the other workspace buffer is rewritten by the peers once they are past THIS barrier: the write-back that
             # still reads it (issued by the previous layer on the copy stream) has to be done before we enter

@@ -283,7 +283,9 @@ int magi_qk_norm_rope_fwd(const magi_prologue_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MAGI_CHECK(a != nullptr, "args is NULL");
   MAGI_CHECK(a->rows >= 0, "rows < 0");
-  MAGI_CHECK(a->x_q != nullptr || a->x_k != nullptr || a->x_v != nullptr, "no input tensor");
+  MAGI_CHECK(a->x_q != nullptr || a->x_k != nullptr || a->x_v != nullptr || a->x_qx != nullptr ||
+                 a->x_tk != nullptr || a->x_tv != nullptr,
+             "no input tensor");
   MAGI_CHECK(a->ln_dtype == 0 || a->ln_dtype == 1, "ln_dtype must be 0 (fp32) or 1 (bf16)");
   MAGI_CHECK(a->batch >= 1, "batch must be >= 1");
   if (a->x_q) {
@@ -320,11 +322,43 @@ int magi_qk_norm_rope_fwd(const magi_prologue_args* a, void* stream_) {
                reinterpret_cast<uintptr_t>(a->ln_q_w) | reinterpret_cast<uintptr_t>(a->ln_q_b) |
                reinterpret_cast<uintptr_t>(a->ln_k_w) | reinterpret_cast<uintptr_t>(a->ln_k_b)) & 15) == 0,
              "all pointers must be 16-byte aligned");
-  if (a->rows == 0) return 0;
+  if (a->x_qx) {
+    MAGI_CHECK(a->qx_out && a->ln_qx_w && a->ln_qx_b && a->num_heads_q > 0, "qx path needs qx_out, ln_qx_w, ln_qx_b");
+    MAGI_CHECK(a->xqx_row_stride % 8 == 0 && a->xqx_head_stride % 8 == 0 && a->xqx_head_stride >= 0 &&
+                   a->qx_out_token_stride % 8 == 0 && a->qx_out_head_stride % 8 == 0,
+               "qx strides must be multiples of 8 elements");
+  }
+  if (a->x_tk || a->x_tv) {
+    MAGI_CHECK(a->tkv_out && a->rows_t >= 0 && a->num_heads_kv > 0, "text k / v need tkv_out and rows_t >= 0");
+    if (a->x_tk) MAGI_CHECK(a->ln_tk_w && a->ln_tk_b, "text k needs ln_tk_w, ln_tk_b");
+    MAGI_CHECK(a->xt_row_stride % 8 == 0 && a->xt_head_stride % 8 == 0 && a->xt_head_stride >= 0 &&
+                   a->tkv_out_token_stride % 8 == 0 && a->tkv_out_head_stride % 8 == 0,
+               "text k / v strides must be multiples of 8 elements");
+  }
+  MAGI_CHECK(((reinterpret_cast<uintptr_t>(a->x_qx) | reinterpret_cast<uintptr_t>(a->x_tk) |
+               reinterpret_cast<uintptr_t>(a->x_tv) | reinterpret_cast<uintptr_t>(a->qx_out) |
+               reinterpret_cast<uintptr_t>(a->tkv_out) | reinterpret_cast<uintptr_t>(a->ln_qx_w) |
+               reinterpret_cast<uintptr_t>(a->ln_qx_b) | reinterpret_cast<uintptr_t>(a->ln_tk_w) |
+               reinterpret_cast<uintptr_t>(a->ln_tk_b)) & 15) == 0,
+             "all pointers must be 16-byte aligned");
+  const bool main_rows = a->x_q || a->x_k || a->x_v || a->x_qx;
+  const bool text_rows = (a->x_tk || a->x_tv) && a->rows_t > 0;
+  if ((!main_rows || a->rows == 0) && !text_rows) return 0;
 
   magi::PrologueParams p;
   p.x_q = a->x_q; p.x_k = a->x_k; p.x_v = a->x_v;
   p.rows = a->rows;
+  p.x_qx = a->x_qx; p.xqx_row_stride = a->xqx_row_stride;
+  p.xqx_head_stride = a->xqx_head_stride > 0 ? a->xqx_head_stride : 128;
+  p.ln_qx_w = a->ln_qx_w; p.ln_qx_b = a->ln_qx_b;
+  p.qx_out = a->qx_out; p.qx_out_token_stride = a->qx_out_token_stride; p.qx_out_head_stride = a->qx_out_head_stride;
+  p.x_tk = a->x_tk; p.x_tv = a->x_tv; p.rows_t = (a->x_tk || a->x_tv) ? a->rows_t : 0;
+  p.xt_row_stride = a->xt_row_stride; p.xt_head_stride = a->xt_head_stride > 0 ? a->xt_head_stride : 128;
+  p.ln_tk_w = a->ln_tk_w; p.ln_tk_b = a->ln_tk_b;
+  p.tkv_out = a->tkv_out; p.tkv_out_token_stride = a->tkv_out_token_stride;
+  p.tkv_out_head_stride = a->tkv_out_head_stride;
+  if (a->rows == 0) { p.x_q = p.x_k = p.x_v = p.x_qx = nullptr; }
+  if (p.rows_t == 0) { p.x_tk = p.x_tv = nullptr; }
   p.xq_row_stride = a->xq_row_stride; p.xk_row_stride = a->xk_row_stride; p.xv_row_stride = a->xv_row_stride;
   p.xq_head_stride = a->xq_head_stride > 0 ? a->xq_head_stride : 128;
   p.xk_head_stride = a->xk_head_stride > 0 ? a->xk_head_stride : 128;

@@ -132,7 +132,7 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 }
 
 struct RingSuper {
-  int type;        // 0 = q, 1 = k, 2 = v
+  int type;        // 0 = q, 1 = k, 2 = v, 3 = qx (cross-attention query), 4 = text k, 5 = text v
   uint32_t u0;     // first unit (index inside the tensor's unit list)
   int cnt;         // valid units (1..kRingGroup)
 };
@@ -157,20 +157,27 @@ __global__ void __launch_bounds__(kRingThreads, MAGI_PRO_RING_BLOCKS) prologue_r
   pdl_wait();   // programmatic dependent launch (common.cuh): nothing before this line touches global memory
 
   const uint32_t rows = static_cast<uint32_t>(p.rows);
+  const uint32_t rows_t = static_cast<uint32_t>(p.rows_t);
   const uint32_t upr_q = (p.Hq + kRingUnitHeads - 1) / kRingUnitHeads;
   const uint32_t upr_kv = (p.Hkv + kRingUnitHeads - 1) / kRingUnitHeads;
+  // units per tensor, tensor-major: q, k, v, then the cross-attention's qx, text k, text v
   const uint32_t n_q = p.x_q != nullptr ? rows * upr_q : 0u;
   const uint32_t n_k = p.x_k != nullptr ? rows * upr_kv : 0u;
   const uint32_t n_v = p.x_v != nullptr ? rows * upr_kv : 0u;
-  const uint32_t su_q = (n_q + kRingGroup - 1) / kRingGroup, su_k = (n_k + kRingGroup - 1) / kRingGroup;
-  const uint32_t su_v = (n_v + kRingGroup - 1) / kRingGroup;
-  const uint32_t total = su_q + su_k + su_v;
+  const uint32_t n_x = p.x_qx != nullptr ? rows * upr_q : 0u;
+  const uint32_t n_tk = p.x_tk != nullptr ? rows_t * upr_kv : 0u;
+  const uint32_t n_tv = p.x_tv != nullptr ? rows_t * upr_kv : 0u;
+  auto sus = [](uint32_t n) { return (n + kRingGroup - 1) / kRingGroup; };
+  const uint32_t e_q = sus(n_q), e_k = e_q + sus(n_k), e_v = e_k + sus(n_v), e_x = e_v + sus(n_x);
+  const uint32_t e_tk = e_x + sus(n_tk), total = e_tk + sus(n_tv);
   auto decode = [&](uint32_t su) {
     RingSuper d;
-    d.type = su < su_q ? 0 : (su < su_q + su_k ? 1 : 2);
-    const uint32_t local = su - (d.type == 0 ? 0u : d.type == 1 ? su_q : su_q + su_k);
-    const uint32_t n = d.type == 0 ? n_q : d.type == 1 ? n_k : n_v;
-    d.u0 = local * kRingGroup;
+    d.type = su < e_q ? 0 : su < e_k ? 1 : su < e_v ? 2 : su < e_x ? 3 : su < e_tk ? 4 : 5;
+    const uint32_t first = d.type == 0 ? 0u : d.type == 1 ? e_q : d.type == 2 ? e_k : d.type == 3 ? e_v
+                                                                              : d.type == 4 ? e_x : e_tk;
+    const uint32_t n = d.type == 0 ? n_q : d.type == 1 ? n_k : d.type == 2 ? n_v : d.type == 3 ? n_x
+                                                                          : d.type == 4 ? n_tk : n_tv;
+    d.u0 = (su - first) * kRingGroup;
     d.cnt = static_cast<int>(min(static_cast<uint32_t>(kRingGroup), n - d.u0));
     return d;
   };
@@ -184,11 +191,16 @@ __global__ void __launch_bounds__(kRingThreads, MAGI_PRO_RING_BLOCKS) prologue_r
       const uint32_t phase = (m / kRingStages) & 1u;
       if (m >= kRingStages) mbar_wait(&empty[stage], phase ^ 1u);
       const RingSuper d = decode(su);
-      const int H = d.type == 0 ? p.Hq : p.Hkv;
-      const uint32_t upr = d.type == 0 ? upr_q : upr_kv;
-      const int64_t rstride = d.type == 0 ? p.xq_row_stride : d.type == 1 ? p.xk_row_stride : p.xv_row_stride;
-      const int64_t hstride = d.type == 0 ? p.xq_head_stride : d.type == 1 ? p.xk_head_stride : p.xv_head_stride;
-      const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(d.type == 0 ? p.x_q : d.type == 1 ? p.x_k : p.x_v);
+      const bool qlike = d.type == 0 || d.type == 3;
+      const int H = qlike ? p.Hq : p.Hkv;
+      const uint32_t upr = qlike ? upr_q : upr_kv;
+      const int64_t rstride = d.type == 0 ? p.xq_row_stride : d.type == 1 ? p.xk_row_stride
+                              : d.type == 2 ? p.xv_row_stride : d.type == 3 ? p.xqx_row_stride : p.xt_row_stride;
+      const int64_t hstride = d.type == 0 ? p.xq_head_stride : d.type == 1 ? p.xk_head_stride
+                              : d.type == 2 ? p.xv_head_stride : d.type == 3 ? p.xqx_head_stride : p.xt_head_stride;
+      const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(
+          d.type == 0 ? p.x_q : d.type == 1 ? p.x_k : d.type == 2 ? p.x_v : d.type == 3 ? p.x_qx
+                                                                  : d.type == 4 ? p.x_tk : p.x_tv);
       const uint32_t dst = ring + stage * kRingStageBytes;
       if (hstride == 128 && rstride == static_cast<int64_t>(H) * 128 && (H % kRingUnitHeads) == 0) {
         // dense projection output: the units of a super-unit are consecutive 2 KB pieces of one array
@@ -241,25 +253,34 @@ __global__ void __launch_bounds__(kRingThreads, MAGI_PRO_RING_BLOCKS) prologue_r
         if (lane == 0) mbar_arrive(&empty[stage]);
         continue;
       }
-      const uint32_t upr = type == 0 ? upr_q : upr_kv;
+      const bool qlike = type == 0 || type == 3;
+      const bool is_v = type == 2 || type == 5;          // pass-through tensors
+      const bool extra = type >= 3;                      // the cross-attention's tensors: in place, bf16 LN, no RoPE
+      const uint32_t upr = qlike ? upr_q : upr_kv;
       const uint32_t unit = d.u0 + sub;
       const uint32_t r = upr == 1 ? unit : unit / upr;
       const int h0 = static_cast<int>(unit - r * upr) * kRingUnitHeads;
-      const int H = type == 0 ? p.Hq : p.Hkv;
+      const int H = qlike ? p.Hq : p.Hkv;
 
       if (type != cur_type) {
         cur_type = type;
-        if (type != 2) {
-          const void* w = type == 0 ? p.ln_q_w : p.ln_k_w;
-          const void* b = type == 0 ? p.ln_q_b : p.ln_k_b;
-          load_param8<kLnBf16>(w, e0, w2); load_param8<kLnBf16>(w, e1, w2 + 4);
-          load_param8<kLnBf16>(b, e0, b2); load_param8<kLnBf16>(b, e1, b2 + 4);
+        if (!is_v) {
+          const void* w = type == 0 ? p.ln_q_w : type == 1 ? p.ln_k_w : type == 3 ? p.ln_qx_w : p.ln_tk_w;
+          const void* b = type == 0 ? p.ln_q_b : type == 1 ? p.ln_k_b : type == 3 ? p.ln_qx_b : p.ln_tk_b;
+          const bool bf16_params = kLnBf16 || extra;
+          if (bf16_params) {
+            load_param8<true>(w, e0, w2); load_param8<true>(w, e1, w2 + 4);
+            load_param8<true>(b, e0, b2); load_param8<true>(b, e1, b2 + 4);
+          } else {
+            load_param8<false>(w, e0, w2); load_param8<false>(w, e1, w2 + 4);
+            load_param8<false>(b, e0, b2); load_param8<false>(b, e1, b2 + 4);
+          }
           if (p.zero_centered_gamma != 0) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               w2[i] = fadd2(w2[i], one2);
               // bf16 parameters: the reference computes `self.weight + 1` in bf16, i.e. rounds the sum
-              if constexpr (kLnBf16) w2[i] = bf2_to_f2(f2_to_bf2(w2[i]));
+              if (bf16_params) w2[i] = bf2_to_f2(f2_to_bf2(w2[i]));
             }
           }
         }
@@ -269,17 +290,22 @@ __global__ void __launch_bounds__(kRingThreads, MAGI_PRO_RING_BLOCKS) prologue_r
       // sits after the ring wait in program order, so the loads have the wait + LDS + LayerNorm time to land;
       // ncu showed the warp parked on these loads when they were unpacked right away)
       float4 c0 = make_float4(1.f, 1.f, 1.f, 1.f), c1 = c0, s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
-      if (type != 2 && rot) {
+      const bool rope = rot && type <= 1;
+      if (rope) {
         const uint32_t trow = p.batch == 1 ? r : r / static_cast<uint32_t>(p.batch);
         const float4* c = reinterpret_cast<const float4*>(p.cos + static_cast<int64_t>(trow) * 48 + 8 * s);
         const float4* sp = reinterpret_cast<const float4*>(p.sin + static_cast<int64_t>(trow) * 48 + 8 * s);
         c0 = __ldg(c); c1 = __ldg(c + 1); s0 = __ldg(sp); s1 = __ldg(sp + 1);
       }
 
-      __nv_bfloat16* out_base = type == 0 ? reinterpret_cast<__nv_bfloat16*>(p.q_out)
-                                          : reinterpret_cast<__nv_bfloat16*>(p.kv_out) + (type == 2 ? 128 : 0);
-      const int64_t out_tstride = type == 0 ? p.q_out_token_stride : p.kv_out_token_stride;
-      const int64_t out_hstride = type == 0 ? p.q_out_head_stride : p.kv_out_head_stride;
+      __nv_bfloat16* out_base =
+          type == 0 ? reinterpret_cast<__nv_bfloat16*>(p.q_out)
+          : type == 3 ? reinterpret_cast<__nv_bfloat16*>(p.qx_out)
+          : reinterpret_cast<__nv_bfloat16*>(extra ? p.tkv_out : p.kv_out) + (is_v ? 128 : 0);
+      const int64_t out_tstride = type == 0 ? p.q_out_token_stride : type == 3 ? p.qx_out_token_stride
+                                  : extra ? p.tkv_out_token_stride : p.kv_out_token_stride;
+      const int64_t out_hstride = type == 0 ? p.q_out_head_stride : type == 3 ? p.qx_out_head_stride
+                                  : extra ? p.tkv_out_head_stride : p.kv_out_head_stride;
       __nv_bfloat16* cache_row = nullptr;
       int64_t grow = 0;                          // kMode 2: row of this unit in the gathered (chunk-major) buffers
       if constexpr (kMode == 2) {
@@ -288,7 +314,7 @@ __global__ void __launch_bounds__(kRingThreads, MAGI_PRO_RING_BLOCKS) prologue_r
         grow = static_cast<int64_t>(chunk) * p.gather_chunk_stride + p.gather_row_offset + (r - chunk * rpc);
       }
       if constexpr (kMode == 0) {
-        if (type != 0 && p.cache != nullptr && static_cast<int64_t>(r) < p.cache_rows)
+        if ((type == 1 || type == 2) && p.cache != nullptr && static_cast<int64_t>(r) < p.cache_rows)
           cache_row = reinterpret_cast<__nv_bfloat16*>(p.cache) + (p.cache_row_offset + r) * p.cache_token_stride +
                       (type == 2 ? 128 : 0);
       }
@@ -316,7 +342,7 @@ __global__ void __launch_bounds__(kRingThreads, MAGI_PRO_RING_BLOCKS) prologue_r
         const int h = h0 + 4 * u + j;
         if (h0 + 4 * u >= H) break;                // warp-uniform: the whole step is past the last head
         uint4 pa = ra[u], pb = rb[u];
-        if (type != 2) {
+        if (!is_v) {
           uint64_t v[8];
           v[0] = bf2_to_f2(pa.x); v[1] = bf2_to_f2(pa.y); v[2] = bf2_to_f2(pa.z); v[3] = bf2_to_f2(pa.w);
           v[4] = bf2_to_f2(pb.x); v[5] = bf2_to_f2(pb.y); v[6] = bf2_to_f2(pb.z); v[7] = bf2_to_f2(pb.w);
@@ -338,7 +364,7 @@ __global__ void __launch_bounds__(kRingThreads, MAGI_PRO_RING_BLOCKS) prologue_r
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = ffma2(fmul2(v[i], rstd2), w2[i], b2[i]);
           // ---- NeoX RoPE: (x1, x2) -> (x1 cos - x2 sin, x2 cos + x1 sin); identity on lanes 6, 7 (cos 1, sin 0)
-          if (rot) {
+          if (rope) {
             const uint64_t cs2[4] = {pack_f2(c0.x, c0.y), pack_f2(c0.z, c0.w), pack_f2(c1.x, c1.y), pack_f2(c1.z, c1.w)};
             const uint64_t sn2[4] = {pack_f2(s0.x, s0.y), pack_f2(s0.z, s0.w), pack_f2(s1.x, s1.y), pack_f2(s1.z, s1.w)};
             const uint64_t nsn2[4] = {pack_f2(-s0.x, -s0.y), pack_f2(-s0.z, -s0.w), pack_f2(-s1.x, -s1.y),
@@ -359,7 +385,7 @@ __global__ void __launch_bounds__(kRingThreads, MAGI_PRO_RING_BLOCKS) prologue_r
           *reinterpret_cast<uint4*>(dst + e0) = pa;
           *reinterpret_cast<uint4*>(dst + e1) = pb;
         };
-        if constexpr (kMode == 0) {
+        if (kMode == 0 || extra) {
           store(out_base + r * out_tstride + h * out_hstride);
           if (cache_row != nullptr) store(cache_row + h * p.cache_head_stride);
         } else if constexpr (kMode == 2) {
@@ -518,7 +544,8 @@ cudaError_t cso_unshuffle_launch(void* dst, int64_t dst_stride, const void* src,
 
 int prologue_units(const PrologueParams& p, int64_t* units) {
   const int64_t upr_q = (p.Hq + kRingUnitHeads - 1) / kRingUnitHeads, upr_kv = (p.Hkv + kRingUnitHeads - 1) / kRingUnitHeads;
-  *units = p.rows * ((p.x_q ? upr_q : 0) + (p.x_k ? upr_kv : 0) + (p.x_v ? upr_kv : 0));
+  *units = p.rows * ((p.x_q ? upr_q : 0) + (p.x_k ? upr_kv : 0) + (p.x_v ? upr_kv : 0) + (p.x_qx ? upr_q : 0)) +
+           p.rows_t * ((p.x_tk ? upr_kv : 0) + (p.x_tv ? upr_kv : 0));
   return MAGI_PRO_RING_BLOCKS;
 }
 template <bool kLnBf16, int kMode>

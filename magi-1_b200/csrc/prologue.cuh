@@ -28,6 +28,17 @@ struct PrologueParams {
   int gather_peers;
   int gather_multicast;   // peer_kv[0] is a multimem (NVSwitch multicast) address: store with multimem.st
   int64_t gather_rows_per_chunk, gather_chunk_stride, gather_row_offset;
+  // Further tensors of the SAME launch (the cross-attention's half of a layer, get_xqkv dit_module.py:1005-1021): always
+  // stored in place, LayerNorm parameters in bf16, no RoPE, whatever the mode of q / k / v above.
+  //   qx: the cross-attention query, rows x Hq heads -> qx_out (rows, Hq, 128)
+  //   tk / tv: the text K / V (rows_t x Hkv heads, normally two column halves of the packed projection)
+  //            -> tkv_out (rows_t, Hkv, 256) packed [K | V]
+  const void* x_qx; int64_t xqx_row_stride, xqx_head_stride;
+  const void* ln_qx_w; const void* ln_qx_b;
+  void* qx_out; int64_t qx_out_token_stride, qx_out_head_stride;
+  const void* x_tk; const void* x_tv; int64_t rows_t, xt_row_stride, xt_head_stride;
+  const void* ln_tk_w; const void* ln_tk_b;
+  void* tkv_out; int64_t tkv_out_token_stride, tkv_out_head_stride;
 };
 
 // number of work units of a launch (-> *units) and the resident 256-thread CTAs per SM the kernel is built for

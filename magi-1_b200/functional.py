@@ -390,9 +390,16 @@ def qk_norm_rope(
     gather_kv_out: Optional[Sequence[int]] = None,
     gather_geometry: Optional[Tuple[int, int, int]] = None,
     gather_multicast: bool = False,
+    cross: Optional[dict] = None,
 ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """Fused per-head LayerNorm(w+1, b) -> NeoX RoPE on 96 of 128 dims -> bf16, writing q in attention layout and
     [K|V] packed (rows, Hkv, 256), optionally also appending to the KV cache (dit_module.py:953-996, 918-929).
+
+    cross = dict(x_qx=(rows, Hq*128) or (rows, Hq, 128) view, ln_qx=(w, b) bf16, text_kv=(rows_t, Hkv, 256) packed
+    text projection, ln_tk=(w, b) bf16[, qx_out=, tkv_out=]): the cross-attention's half of the layer (get_xqkv,
+    dit_module.py:1005-1021: two bf16-parameter LayerNorms, no RoPE) rides in the SAME launch - one prologue launch per
+    layer instead of three. The results are put back into the dict under "qx" (rows, Hq, 128) and "tkv"
+    (rows_t, Hkv, 256); they are always written in place, whatever the routing of q / k / v. Either half may be absent.
 
     x_* are the projection outputs, (rows, H*128) or strided (rows, H, 128) bf16 views (rows = "(sq b)" flattened;
     strides multiples of 8). ln_* = (weight, bias), both fp32 (self-attention, dit_model.py:621-633) or both bf16 (cross-attention).
@@ -407,9 +414,11 @@ def qk_norm_rope(
     chunk_stride, row_offset) the K/V all-gather of cp_ring_kv is fused: local row (chunk j, stripe row t) is stored at
     row j * chunk_stride + row_offset + t of every buffer; q is written locally as usual, no kv tensor is returned.
     """
-    ref = next(t for t in (x_q, x_k, x_v) if t is not None)
+    x_qx = cross.get("x_qx") if cross else None
+    text_kv = cross.get("text_kv") if cross else None
+    ref = next(t for t in (x_q, x_k, x_v, x_qx, text_kv) if t is not None)
     dev = ref.device
-    rows = ref.shape[0]
+    rows = next((t.shape[0] for t in (x_q, x_k, x_v, x_qx) if t is not None), 0)
     for t, nm, H in ((x_q, "x_q", num_heads_q), (x_k, "x_k", num_heads_kv), (x_v, "x_v", num_heads_kv)):
         if t is None:
             continue
@@ -466,6 +475,37 @@ def qk_norm_rope(
         kv_out = torch.empty((rows * cp, hn_kv, 2 * HEAD_DIM), dtype=torch.bfloat16, device=dev)
 
     a = MagiPrologueArgs()
+    if x_qx is not None:
+        if not x_qx.is_cuda or x_qx.dtype != torch.bfloat16 or not (
+                (x_qx.dim() == 2 and x_qx.shape == (rows, num_heads_q * HEAD_DIM) and x_qx.stride(1) == 1) or
+                (x_qx.dim() == 3 and x_qx.shape == (rows, num_heads_q, HEAD_DIM) and x_qx.stride(2) == 1)):
+            raise ValueError(f"cross['x_qx'] must be a CUDA bf16 (rows, {num_heads_q}*128) or (rows, {num_heads_q}, 128)")
+        w, b = cross["ln_qx"]
+        if w.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or w.numel() != HEAD_DIM or b.numel() != HEAD_DIM:
+            raise ValueError("cross['ln_qx'] must be bf16 with 128 elements")
+        qx_out = cross.get("qx_out")
+        if qx_out is None:
+            qx_out = torch.empty((rows, num_heads_q, HEAD_DIM), dtype=torch.bfloat16, device=dev)
+        a.x_qx, a.xqx_row_stride = x_qx.data_ptr(), x_qx.stride(0)
+        a.xqx_head_stride = x_qx.stride(1) if x_qx.dim() == 3 else HEAD_DIM
+        a.ln_qx_w, a.ln_qx_b = w.data_ptr(), b.data_ptr()
+        a.qx_out, a.qx_out_token_stride, a.qx_out_head_stride = qx_out.data_ptr(), qx_out.stride(0), qx_out.stride(1)
+        cross["qx"] = qx_out
+    if text_kv is not None:
+        if (not text_kv.is_cuda or text_kv.dtype != torch.bfloat16 or text_kv.dim() != 3 or
+                text_kv.shape[1:] != (num_heads_kv, 2 * HEAD_DIM) or text_kv.stride(2) != 1):
+            raise ValueError(f"cross['text_kv'] must be a CUDA bf16 (rows_t, {num_heads_kv}, 256) tensor")
+        w, b = cross["ln_tk"]
+        if w.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or w.numel() != HEAD_DIM or b.numel() != HEAD_DIM:
+            raise ValueError("cross['ln_tk'] must be bf16 with 128 elements")
+        tkv_out = cross.get("tkv_out")
+        if tkv_out is None:
+            tkv_out = torch.empty((text_kv.shape[0], num_heads_kv, 2 * HEAD_DIM), dtype=torch.bfloat16, device=dev)
+        a.x_tk, a.x_tv = text_kv.data_ptr(), text_kv.data_ptr() + HEAD_DIM * 2
+        a.rows_t, a.xt_row_stride, a.xt_head_stride = text_kv.shape[0], text_kv.stride(0), text_kv.stride(1)
+        a.ln_tk_w, a.ln_tk_b = w.data_ptr(), b.data_ptr()
+        a.tkv_out, a.tkv_out_token_stride, a.tkv_out_head_stride = tkv_out.data_ptr(), tkv_out.stride(0), tkv_out.stride(1)
+        cross["tkv"] = tkv_out
     a.x_q, a.x_k, a.x_v = _ptr(x_q), _ptr(x_k), _ptr(x_v)
     a.rows = rows
     a.xq_row_stride = x_q.stride(0) if x_q is not None else 0

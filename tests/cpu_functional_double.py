@@ -47,8 +47,20 @@ def _send_layout(v, cp, rep=1):
 
 def qk_norm_rope(x_q, x_k, x_v, num_heads_q, num_heads_kv, ln_q, ln_k, sin, cos, batch=1, eps=1e-6,
                  zero_centered_gamma=True, q_out=None, kv_out=None, cache=None, cache_row_offset=0, cache_rows=0,
-                 head_perm_cp=1, **unsupported):
+                 head_perm_cp=1, cross=None, **unsupported):
     assert not {k for k, v in unsupported.items() if v is not None and v != 0}, "peer / gather routing has no CPU double"
+    if cross:   # the cross-attention's tensors riding in the same launch: always plain layout, bf16 LN, no RoPE
+        if cross.get("x_qx") is not None:
+            cross["qx"], _ = qk_norm_rope(cross["x_qx"], None, None, num_heads_q, num_heads_kv, cross["ln_qx"], None,
+                                          None, None, eps=eps, zero_centered_gamma=zero_centered_gamma,
+                                          q_out=cross.get("qx_out"))
+        if cross.get("text_kv") is not None:
+            t = cross["text_kv"]
+            _, cross["tkv"] = qk_norm_rope(None, t[..., :HEAD_DIM], t[..., HEAD_DIM:], num_heads_q, num_heads_kv, None,
+                                           cross["ln_tk"], None, None, eps=eps,
+                                           zero_centered_gamma=zero_centered_gamma, kv_out=cross.get("tkv_out"))
+        if x_q is None and x_k is None and x_v is None:
+            return None, None
     cp = max(1, head_perm_cp)
     q_res = kv_res = None
     if x_q is not None:
@@ -223,10 +235,13 @@ _plain_qk_norm_rope, _plain_attn_ranges = qk_norm_rope, attn_ranges
 
 
 def qk_norm_rope(x_q, x_k, x_v, num_heads_q, num_heads_kv, ln_q, ln_k, sin, cos, *, peer_q_out=None, peer_kv_out=None,
-                 peer_row_offset=0, peer_heads=None, gather_kv_out=None, gather_geometry=None, **kw):  # noqa: F811
+                 peer_row_offset=0, peer_heads=None, gather_kv_out=None, gather_geometry=None, cross=None, **kw):  # noqa: F811
     """Adds the routing of include/magi_attn.h's peer_* / gather_* fields on top of the plain double."""
     if peer_q_out is None and peer_kv_out is None and gather_kv_out is None:
-        return _plain_qk_norm_rope(x_q, x_k, x_v, num_heads_q, num_heads_kv, ln_q, ln_k, sin, cos, **kw)
+        return _plain_qk_norm_rope(x_q, x_k, x_v, num_heads_q, num_heads_kv, ln_q, ln_k, sin, cos, cross=cross, **kw)
+    if cross:   # the cross-attention's tensors are local whatever the routing of q / k / v
+        _plain_qk_norm_rope(None, None, None, num_heads_q, num_heads_kv, None, None, None, None, cross=cross,
+                            eps=kw.get("eps", 1e-6), zero_centered_gamma=kw.get("zero_centered_gamma", True))
     if gather_kv_out is not None:
         # cp_ring_kv: q stays local; K/V row (chunk j, stripe row t) -> row j * chunk_stride + row_offset + t everywhere
         q, kv = _plain_qk_norm_rope(x_q, x_k, x_v, num_heads_q, num_heads_kv, ln_q, ln_k, sin, cos, **kw)

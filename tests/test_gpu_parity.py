@@ -304,6 +304,47 @@ def test_prologue_bf16_params_no_rope(F):
     assert torch.equal(kv[..., 128:], tkv[..., 128:])
 
 
+@pytest.mark.parametrize("mode", ["plain+cache", "send-layout", "gather", "cross-only", "ragged-heads"])
+def test_one_prologue_launch_per_layer_matches_three(F, mode):
+    """`cross=`: the cross-attention's qx / text k / text v in the SAME launch as q / k / v (fp32 LayerNorm + RoPE there,
+    bf16 LayerNorm and no RoPE here, a different row count for the text): every output bit-identical to the three
+    separate launches, whatever the routing of q / k / v (plain + KV-cache append, all-to-all send layout, fused
+    all-gather), with the self-attention tensors absent, and with head counts that are not multiples of 8."""
+    T, Tt = 333, 77
+    Hq, Hkv = (6, 3) if mode == "ragged-heads" else (8, 2)
+    xq, xk, xv = bf(rnd((T, Hq * 128), 1, 2.0)), bf(rnd((T, Hkv * 128), 2, 2.0)), bf(rnd((T, Hkv * 128), 3, 2.0))
+    qx, tkv = bf(rnd((T, Hq * 128), 4, 2.0)), bf(rnd((Tt, Hkv, 256), 5, 2.0))
+    ln = [torch.from_numpy(rnd((128,), 10 + i, 0.2)).cuda() for i in range(4)]
+    lnx = [bf(rnd((128,), 20 + i, 0.2)) for i in range(4)]
+    ang = torch.from_numpy(rnd((T, 48), 30, 3.0))
+    sin, cos = torch.sin(ang).cuda(), torch.cos(ang).cuda()
+    ref_qx, _ = F.qk_norm_rope(qx, None, None, Hq, Hkv, (lnx[0], lnx[1]), None, None, None)
+    _, ref_tkv = F.qk_norm_rope(None, tkv[..., :128], tkv[..., 128:], Hq, Hkv, None, (lnx[2], lnx[3]), None, None)
+    cross = dict(x_qx=qx, ln_qx=(lnx[0], lnx[1]), text_kv=tkv, ln_tk=(lnx[2], lnx[3]))
+    main = (xq, xk, xv, Hq, Hkv, (ln[0], ln[1]), (ln[2], ln[3]), sin, cos)
+    if mode == "cross-only":
+        q, kv = F.qk_norm_rope(None, None, None, Hq, Hkv, None, None, None, None, cross=cross)
+        assert q is None and kv is None
+    elif mode in ("plain+cache", "ragged-heads"):
+        c0 = torch.zeros(T + 50, Hkv, 256, dtype=torch.bfloat16, device="cuda")
+        c1 = torch.zeros_like(c0)
+        rq, rkv = F.qk_norm_rope(*main, cache=c0, cache_row_offset=50, cache_rows=T - 10)
+        q, kv = F.qk_norm_rope(*main, cache=c1, cache_row_offset=50, cache_rows=T - 10, cross=cross)
+        assert torch.equal(q, rq) and torch.equal(kv, rkv) and torch.equal(c0, c1)
+    elif mode == "send-layout":
+        rq, rkv = F.qk_norm_rope(*main, head_perm_cp=2)
+        q, kv = F.qk_norm_rope(*main, head_perm_cp=2, cross=cross)
+        assert torch.equal(q, rq) and torch.equal(kv, rkv)
+    else:   # fused K/V all-gather into two "ranks'" buffers, this rank's stripe = rows [111, 222) of every chunk of 333
+        g0 = [torch.zeros(3 * 333, Hkv, 256, dtype=torch.bfloat16, device="cuda") for _ in range(2)]
+        g1 = [torch.zeros_like(t) for t in g0]
+        rq, _ = F.qk_norm_rope(*main, gather_kv_out=[t.data_ptr() for t in g0], gather_geometry=(111, 333, 111))
+        q, _ = F.qk_norm_rope(*main, gather_kv_out=[t.data_ptr() for t in g1], gather_geometry=(111, 333, 111),
+                              cross=cross)
+        assert torch.equal(q, rq) and all(torch.equal(a, b) for a, b in zip(g0, g1))
+    assert torch.equal(cross["qx"], ref_qx) and torch.equal(cross["tkv"], ref_tkv)
+
+
 @pytest.mark.parametrize("cp,Hq,Hkv", [(2, 6, 2), (4, 8, 2), (8, 24, 8)])
 def test_prologue_writes_ulysses_send_layout(F, cp, Hq, Hkv):
     """head_perm_cp: outputs equal `repeat_interleave` + "seq (cp hn) hd -> (cp seq) hn hd" of the plain outputs
