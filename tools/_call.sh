@@ -1,12 +1,14 @@
-tag=r02ze; out=gpurun_out; mkdir -p $out
+tag=r02zf; n=2; out=gpurun_out; mkdir -p $out
 python -c "import __graft_entry__ as g; g.build()" > $out/${tag}_build.log 2>&1 || { echo "build failed"; exit 1; }
-timeout 900 python -m pytest tests -m gpu -q > $out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -8 $out/${tag}_pytest_gpu.log
-Q="--no-cpu-baseline --no-gpu-reference"
-timeout 600 python bench.py $Q > $out/${tag}_bench_a.json 2> $out/${tag}_bench_a.err; echo "bench rc=$?"; tail -3 $out/${tag}_bench_a.err
+run="python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1"
+CP_CHECK_KV_OFFLOAD=1 timeout 900 $run --master-port 29700 tools/cp_check.py > $out/${tag}_cp_check_n${n}.log 2>&1
+echo "cp_check rc=$?"; grep "cp_check\|CP_CHECK\|Error\|error" $out/${tag}_cp_check_n${n}.log | tail -16
+timeout 900 $run --master-port 29710 bench.py --gpus $n > $out/${tag}_bench_n${n}.json 2> $out/${tag}_bench_n${n}.err; echo "bench rc=$?"
 python - <<PY
 import json
-for l in open("$out/${tag}_bench_a.json"):
+for l in open("$out/${tag}_bench_n${n}.json"):
     if l.startswith("{"):
         d=json.loads(l); r=d["roofline"]
-        print(d["value"], d["ms_per_step"], "e2e", d["e2e"]["value"], "achieved", r["achieved"], r["avg_launch_ms"], "share", r["share_of_step"], d["clocks"]["sm_mhz"], "launches", d["gpu_launches"], r.get("phases_us_per_layer"), (d.get("dit_denoise_step") or {}).get("ms_per_step"))
+        print("n2", d["value"], d["ms_per_step"], "e2e", d["e2e"]["value"], "achieved", r["achieved"], "share", r["share_of_step"], "parity", d.get("cp_parity",{}).get("max_abs"), r.get("phases_us_per_layer"), (d.get("dit_denoise_step") or {}).get("ms_per_step"), {k:(v.get("value"),v.get("cp_parity_ok")) for k,v in (d.get("extra_legs") or {}).items()})
 PY
+tail -3 $out/${tag}_bench_n${n}.err
