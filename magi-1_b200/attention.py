@@ -242,6 +242,15 @@ class FullyParallelAttention(nn.Module):
                 and getattr(self.engine_config, "cp_fused_all_to_all", False)
                 and cpm.UlyssesPeerWorkspace.available(mpu.get_cp_group(), device))
 
+    def _fused_ulysses_forward(self, batch_size, device, inference_params, meta_args) -> bool:
+        """Does this forward take the fused all-to-all path: batch 1 always; batch > 1 when it is the cache-less pass
+        with one range shared by all batch rows (the uncond pass of the 3-CFG models, dit_model.py:413-494 - the only
+        batched form core_attention accepts, dit_module.py:1048)."""
+        if batch_size == 1:
+            return self._fused_ulysses(1, device)
+        return (self._fused_ulysses(1, device) and not self._uses_cache(inference_params, meta_args)
+                and meta_args.denoising_range_num == 1)
+
     def _fused_ring(self, batch_size, device) -> bool:
         return (self.engine_config.cp_strategy == "cp_ring_kv" and batch_size == 1
                 and getattr(self.engine_config, "cp_fused_all_to_all", False)
@@ -597,11 +606,12 @@ class FullyParallelAttention(nn.Module):
             core_attn_out = core.view(sq, batch_size, Hq * F.HEAD_DIM)
             xattn_out = self.cross_attention_attend(x_prepared, (sq, batch_size), xp, independent=overlap)
 
-        elif fused_proj_input and not (strategy == "cp_ulysses" and self._fused_ulysses(batch_size, dev)):
+        elif fused_proj_input and not (strategy == "cp_ulysses" and batch_size == 1
+                                       and self._fused_ulysses(batch_size, dev)):
             raise NotImplementedError("fused_proj_input is available with cp_strategy 'none' and on the fused "
                                       "cp_ulysses path (see supports_fused_proj_input)")
         elif strategy == "cp_ulysses":
-            if self._fused_ulysses(batch_size, dev):
+            if self._fused_ulysses_forward(batch_size, dev, inference_params, meta_args):
                 res = self._forward_ulysses_fused(mixed_qqkv, key_value_states, inference_params, sin_emb, cos_emb,
                                                   meta_args, fused_proj_input=fused_proj_input)
                 if fused_proj_input:
@@ -703,7 +713,9 @@ class FullyParallelAttention(nn.Module):
         device-side barriers per layer replace three all-to-all calls and the re-layout kernel, and the transfers
         overlap the kernels that issue them. Same values as _forward_ulysses (same kernels, same per-head inputs)."""
         sq, b, _ = mixed_qqkv.shape
-        assert b == 1
+        if b != 1:
+            assert not fused_proj_input
+            return self._forward_ulysses_fused_batched(mixed_qqkv, key_value_states, sin_emb, cos_emb, meta_args)
         cp, rank = self.engine_config.cp_size, mpu.get_cp_rank()
         Hq, Hkv = self.model_config.num_attention_heads, self.model_config.num_query_groups
         eps, z = self.model_config.layernorm_epsilon, self.model_config.apply_layernorm_1p
@@ -760,6 +772,41 @@ class FullyParallelAttention(nn.Module):
         ws.barrier()                                                     # B: every rank's output rows have landed
         # the workspace is reused by the next layer: hand out a private copy of this rank's rows
         core_attn_out = ws.out[:split[rank]].reshape(sq, b, Hq * F.HEAD_DIM).clone()
+        return core_attn_out, xattn_out
+
+    def _forward_ulysses_fused_batched(self, mixed_qqkv, key_value_states, sin_emb, cos_emb, meta_args):
+        """The fused path for batch > 1 without a KV cache (the uncond pass of the 3-CFG models): rows stay in the
+        reference's "(sq b)" order everywhere - the receive buffers hold "(S b)" rows (this rank's block starts at row
+        bounds[rank] * b), every batch row is a strided view of them (as in core_attention, dit_module.py:1048-1061), and
+        the epilogue of batch row i stores into the owners' "(sq b) (cp hn) hd" output at token stride b * Hq * 128."""
+        sq, b, _ = mixed_qqkv.shape
+        cp, rank = self.engine_config.cp_size, mpu.get_cp_rank()
+        Hq, Hkv = self.model_config.num_attention_heads, self.model_config.num_query_groups
+        eps, z = self.model_config.layernorm_epsilon, self.model_config.apply_layernorm_1p
+        dev = mixed_qqkv.device
+        split = list(meta_args.cp_split_sizes)           # sequence rows per rank (dit_module.py:1150 multiplies by b)
+        total = sum(split)
+        hq_loc, hkv_loc = divide(Hq, cp), (divide(Hkv, cp) if Hkv >= cp else 1)   # (also serves cp_ring_kv: no cache)
+        ws = cpm.UlyssesPeerWorkspace.get(mpu.get_cp_group(), total * b, max(split) * b, hq_loc, hkv_loc, Hq, dev)
+        _, bounds, head_off = cpm.fused_ulysses_plan(split, rank, Hq, cp)
+        xq, xk, xv = self._project(mixed_qqkv)
+        F.qk_norm_rope(xq, xk, xv, Hq, Hkv, self._ln(self.q_layernorm), self._ln(self.k_layernorm), sin_emb, cos_emb,
+                       batch=b, eps=eps, zero_centered_gamma=z, head_perm_cp=cp, peer_q_out=ws.q_ptrs,
+                       peer_kv_out=ws.kv_ptrs, peer_row_offset=bounds[rank] * b, peer_heads=(hq_loc, hkv_loc))
+        x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states)
+        ws.barrier()                                                     # A: every rank's q / kv rows have landed
+        p = meta_args.core_attn_params
+        assert meta_args.denoising_range_num == 1                        # dit_module.py:1048
+        q_all, kv_all = ws.q[:total * b].unflatten(0, (total, b)), ws.kv[:total * b].unflatten(0, (total, b))
+        tstride = b * Hq * F.HEAD_DIM
+        for i in range(b):
+            ptrs = [p_ + i * Hq * F.HEAD_DIM * 2 for p_ in ws.out_ptrs]
+            kv_i = kv_all[:, i]
+            F.attn_ranges(q_all[:, i], kv_i[..., :F.HEAD_DIM], kv_i[..., F.HEAD_DIM:], p.q_range[:1], p.k_range[:1],
+                          return_lse=False, peer_out=(ptrs, bounds, head_off, Hq, tstride))
+        xattn_out = self.cross_attention_attend(x_prepared, (sq, b), meta_args.cross_attn_params)
+        ws.barrier()                                                     # B: every rank's output rows have landed
+        core_attn_out = ws.out[:sq * b].reshape(sq, b, Hq * F.HEAD_DIM).clone()
         return core_attn_out, xattn_out
 
     # ------------------------------------------------------------------ CSO (dit_module.py:1207-1242)
@@ -914,6 +961,8 @@ class FullyParallelAttention(nn.Module):
             # KV cache; its shards are the contiguous Ulysses shards (cp_ring_kv_process), so it runs as cp_ulysses
             if self._uses_cache(inference_params, meta_args) or meta_args.denoising_range_num != 1:
                 raise NotImplementedError("cp_ring_kv with batch size > 1 supports the cache-less uncond pass only")
+            if self._fused_ring(1, mixed_qqkv.device):
+                return self._forward_ulysses_fused_batched(mixed_qqkv, key_value_states, sin_emb, cos_emb, meta_args)
             return self._forward_ulysses(mixed_qqkv, key_value_states, inference_params, sin_emb, cos_emb, meta_args)
         if self.engine_config.kv_offload:
             raise NotImplementedError("cp_ring_kv with kv_offload runs on the fused gather path only "

@@ -137,7 +137,7 @@ def attn_ranges(
 
     kernel: 0 = library default, 1 = attn_fwd_kernel, 2 = attn_pair_kernel (experimental CTA-pair kernel).
 
-    peer_out = (pointers, row_bounds, head_offset, heads_total): fused Ulysses output all-to-all. Query row g of
+    peer_out = (pointers, row_bounds, head_offset, heads_total[, token_stride]): fused Ulysses output all-to-all. Query row g of
     local head h is stored into the (rows_rho, heads_total, 128) bf16 buffer at pointers[rho] of the rank rho with
     row_bounds[rho] <= g < row_bounds[rho + 1], at row g - row_bounds[rho], head head_offset + h (NVLink peer
     memory; include/magi_attn.h). Returns (None, None); the caller synchronises the ranks.
@@ -208,10 +208,12 @@ def attn_ranges(
     elif peer_out is not None:
         if out is not None or return_lse:
             raise ValueError("peer_out excludes out and return_lse")
-        ptrs, bounds, head_off, heads_total = peer_out
+        ptrs, bounds, head_off, heads_total = peer_out[:4]
         if len(ptrs) > _lib.MAX_PEERS or len(bounds) != len(ptrs) + 1:
             raise ValueError("peer_out needs at most 8 pointers and one more row bound than pointers")
-        out_ptr, out_ts, out_hs = None, heads_total * HEAD_DIM, HEAD_DIM
+        # optional 5th entry: token stride of the peers' buffers in elements (batched rows "(sq b)": b * heads_total * 128,
+        # with the pointers already advanced to the batch row)
+        out_ptr, out_ts, out_hs = None, (peer_out[4] if len(peer_out) > 4 else heads_total * HEAD_DIM), HEAD_DIM
         if peer_proj is not None:
             n_src, hn = peer_proj
             if heads_total % hn != 0 or n_src not in (0, 1):

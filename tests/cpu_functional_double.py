@@ -267,7 +267,8 @@ def qk_norm_rope(x_q, x_k, x_v, num_heads_q, num_heads_kv, ln_q, ln_k, sin, cos,
 def attn_ranges(q, k_new, v_new, q_ranges=None, k_ranges=None, *, peer_out=None, peer_proj=None, **kw):  # noqa: F811
     if peer_out is None:
         return _plain_attn_ranges(q, k_new, v_new, q_ranges, k_ranges, **kw)
-    ptrs, bounds, head_off, heads_total = peer_out
+    ptrs, bounds, head_off, heads_total = peer_out[:4]
+    tstride = peer_out[4] if len(peer_out) > 4 else heads_total * HEAD_DIM      # batched rows: b * heads_total * 128
     kw.pop("out", None)
     kw.pop("independent_of_prev", None)
     res, _ = _plain_attn_ranges(q, k_new, v_new, q_ranges, k_ranges, **dict(kw, return_lse=False))
@@ -281,7 +282,12 @@ def attn_ranges(q, k_new, v_new, q_ranges=None, k_ranges=None, *, peer_out=None,
         if not len(rows):
             continue
         if peer_proj is None:
-            _peer(ptr, (0, heads_total, HEAD_DIM))[rows, head_off:head_off + hq] = res[lo:hi][rows]
+            # flat element indexing: with batched rows the pointer is advanced to the batch row, so the buffer does not
+            # hold a whole number of (tstride)-wide rows from there on
+            flat = _PEER_TENSORS[(ptr >> 40) - 1]
+            off = (ptr & ((1 << 40) - 1)) // 2
+            idx = off + rows[:, None] * tstride + head_off * HEAD_DIM + torch.arange(hq * HEAD_DIM)[None, :]
+            flat[idx] = res[lo:hi][rows].reshape(len(rows), hq * HEAD_DIM)
         else:    # the owner's out-projection input "(hn n hd)": destination head H -> group H // gh, slot n, H % gh
             n_src, hn = peer_proj
             gh = heads_total // hn

@@ -207,6 +207,30 @@ def test_fused_paths_match_single_rank_through_a_cache_sequence(emulation, strat
         refs.append(ref_m(hs, kvs, inf_ref, rope, meta))
         inputs.append((hs, kvs, rope, meta, upd, dn))
 
+    # the batched, cache-less uncond pass of the 3-CFG models (dit_model.py:413-494): chunks on the batch dim, one range
+    # shared by the batch rows - the fused path keeps the "(sq b)" row order through both all-to-alls
+    bs = 3
+    hs_u = torch.randn(clip, bs, hidden, generator=g).to(torch.bfloat16)
+    yi_u = [11, 0, 23]
+    kvs_u = torch.randn(sum(yi_u), hidden, generator=g).to(torch.bfloat16)
+    ang = torch.rand(clip, 48, generator=g) * 6.28
+    rope_u = torch.cat([torch.sin(ang), torch.cos(ang)], -1)
+    edges = np.arange(bs + 1, dtype=np.int32) * clip
+    rng_u = np.stack([edges[:-1], edges[1:]], 1)
+    cu_k = np.concatenate([[0], np.cumsum(yi_u)]).astype(np.int32)
+    core_u = PackedCoreAttnParams(i32(rng_u), i32(rng_u), rng_u, rng_u, clip, bs * clip)
+    cross_u = PackedCrossAttnParams(i32(rng_u), i32(np.stack([cu_k[:-1], cu_k[1:]], 1)), i32(edges), i32(cu_k), clip, 800)
+
+    def meta_u(split, cross):
+        return ModelMetaArgs(H=4, W=4, cp_pad_size=0, cp_split_sizes=split, slice_point=0, denoising_range_num=1,
+                             range_num=1, extract_prefix_video_feature=False, fwd_extra_1st_chunk=False,
+                             distill_nearly_clean_chunk=False, clip_token_nums=clip, enable_cuda_graph=False,
+                             core_attn_params=core_u, cross_attn_params=cross)
+
+    # (the uncond pass shards heads like Ulysses under both strategies: it needs Hkv | cp or cp | Hkv)
+    uncond = not fused_proj and (Hkv % world == 0 or world % Hkv == 0)
+    ref_u = ref_m(hs_u, kvs_u, None, rope_u, meta_u(None, cross_u)) if uncond else None
+
     results, errors = {}, []
 
     def rank_main(rank):
@@ -231,7 +255,15 @@ def test_fused_paths_match_single_rank_through_a_cache_sequence(emulation, strat
                     continue
                 core, xo = m(x, kvs, inf, rope_l, m_cp)
                 outs.append((core.float().clone(), xo.float().clone(), split))
-            results[rank] = (outs, inf.key_value_memory_dict[1].float().clone())
+            unc = None
+            if uncond:
+                ardf = dict(denoising_range_num=1, q_range=core_u.q_range, k_range=core_u.k_range, max_seqlen_q=clip,
+                            max_seqlen_k=bs * clip)
+                x, _, rope_l, pad, split, _, cross_l = cpm.cp_pre_process(
+                    world, strategy, hs_u, torch.zeros(clip, bs), rope_u, None, ardf, core_u, cross_u)
+                core, xo = m(x, kvs_u, None, rope_l, meta_u(split, cross_l))
+                unc = (core.float().clone(), xo.float().clone())
+            results[rank] = (outs, inf.key_value_memory_dict[1].float().clone(), unc)
         except Exception:                       # pragma: no cover - reported by the main thread
             import traceback
             errors.append(f"rank {rank}:\n{traceback.format_exc()}")
@@ -266,6 +298,11 @@ def test_fused_paths_match_single_rank_through_a_cache_sequence(emulation, strat
         e_core = float((core - ref_core.float()).abs().max())
         e_x = float((xo - ref_x.float()).abs().max())
         assert e_core <= 1e-2 and e_x <= 1e-2, (strategy, world, i, e_core, e_x)
+    if uncond:   # uncond pass: contiguous sequence shards under both strategies (cp_ring_kv_process)
+        core = torch.cat([results[r][2][0] for r in range(world)], 0)
+        xo = torch.cat([results[r][2][1] for r in range(world)], 0)
+        assert core.shape == ref_u[0].shape
+        assert float((core - ref_u[0].float()).abs().max()) <= 1e-2 and float((xo - ref_u[1].float()).abs().max()) <= 1e-2
     # KV caches: Ulysses keeps the rank's head slice, the ring strategy a full replica - all as the single rank left them
     ref_cache = inf_ref.key_value_memory_dict[1].float()
     for r in range(world):

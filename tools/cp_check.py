@@ -136,7 +136,7 @@ def main():
                 worst["xattn"] = max(worst["xattn"], (xo.float() - ref_x.float()).abs().max().item())
             if strategy != "cp_shuffle_overlap":
                 # batched uncond pass of the 3-CFG models (dit_model.py:413-494): chunks on the batch dim, one range
-                # per batch row, no KV cache (runs on the NCCL Ulysses path under both strategies)
+                # per batch row, no KV cache (fused variants: the batched fused path, rows stay "(sq b)"; else NCCL Ulysses)
                 bs = 3
                 hs = torch.randn(clip, bs, hidden, generator=g).to(torch.bfloat16).to(dev)
                 yi = [50, 0, 77]
