@@ -249,6 +249,15 @@ int magi_attn_fwd(const magi_attn_args* a, void* stream_) {
   p.counters = ws + magi::attn_workspace_ints(a->n_ranges) - 2;
   MAGI_CHECK(a->fill_uncovered_rows == 0 || (a->num_peers == 0 && a->out_group_heads == 0 && !use_pair),
              "fill_uncovered_rows needs plain output addressing and the single-CTA kernel");
+  {
+    uintptr_t bits = reinterpret_cast<uintptr_t>(a->out);
+    for (int i = 0; i < a->num_peers; ++i) bits |= reinterpret_cast<uintptr_t>(a->peer_out[i]);
+    p.out_align32 = (bits & 31) == 0 && a->out_token_stride % 16 == 0 && a->out_head_stride % 16 == 0 &&
+                    (a->out_group_heads == 0 || a->out_group_stride % 16 == 0);
+#ifdef MAGI_NO_STG256   // (A/B builds only)
+    p.out_align32 = 0;
+#endif
+  }
   p.fill_uncovered = a->fill_uncovered_rows != 0;
   p.total_q = (int)a->q.tokens;
   const CUtensorMap maps[5] = {tm_q, tm_ka, tm_va, tm_kb, tm_vb};

@@ -118,6 +118,10 @@ constexpr int kEmuMod = MAGI_EMU_MOD;
 #ifndef MAGI_GUARD_BY_SUM
 #define MAGI_GUARD_BY_SUM 1
 #endif
+#ifndef MAGI_EPI_UNROLL
+#define MAGI_EPI_UNROLL 2     // 32-column chunks of O per epilogue loop iteration (interleaved A/B r02zl_ab.log: 2 beats 1 and 4)
+#endif
+constexpr int kEpiUnroll = MAGI_EPI_UNROLL;
 constexpr float kSumGuard = 32768.f;      // 2^15: a 64-column half of P summing to more than this re-references the row
 
 #ifdef MAGI_TRACE
@@ -125,8 +129,13 @@ constexpr float kSumGuard = 32768.f;      // 2^15: a 64-column half of P summing
 __device__ long long g_trace[3][512][8];
 #define TRACE(who, idx, slot) \
   do { if (blockIdx.x == 0 && (idx) < 512) g_trace[who][idx][slot] = clock64(); } while (0)
+// per-ITEM stamps of CTA 0 (softmax warp 0, MMA issuer, TMA warp): where the time between two items goes
+__device__ long long g_itrace[3][128][8];
+#define ITRACE(who, idx, slot) \
+  do { if (blockIdx.x == 0 && (idx) < 128 && (threadIdx.x & 31) == 0) g_itrace[who][idx][slot] = clock64(); } while (0)
 #else
 #define TRACE(who, idx, slot) do {} while (0)
+#define ITRACE(who, idx, slot) do {} while (0)
 #endif
 
 struct alignas(16) Item {
@@ -246,6 +255,12 @@ __device__ __forceinline__ void issue_pv_full(uint32_t d_tmem, uint32_t p_tmem, 
   for (int ks = 4 * half; ks < 4 * half + 4; ++ks)
     mma_ts(d_tmem, p_tmem + 64 * half + (ks - 4 * half) * 8, v_desc + static_cast<uint64_t>((ks * 2048) >> 4), kIdescPV,
            ks > 0 ? 1u : accumulate);
+}
+
+__device__ __forceinline__ void stg256(void* ptr, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
 }
 
 }  // namespace
@@ -398,6 +413,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int row_in_item = t * kTileM + rowq;
     const int pair_bar = 1 + t * 4 + quarter;  // named barrier shared by the two warps that split a row (kSplit == 2)
     uint32_t s_phase = 0, o_phase = 0;
+#ifdef MAGI_TRACE
+    int s_items = 0;
+#endif
     const float scale_log2 = p.scale_log2;
 #if MAGI_EARLY_PUBLISH
     const uint32_t opaque_zero = static_cast<uint32_t>(p.Hq) >> 30;   // 0 at run time, unknown at compile time
@@ -428,6 +446,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const int row = it.qrow0 + row_in_item;
       const bool row_valid = row < it.q_end;
       float m = -INFINITY, l = 0.f;   // running max of the row (shared by its threads), this thread's partial row sum
+#ifdef MAGI_TRACE
+      if (warp == 0) ITRACE(0, s_items, 0);
+#endif
 
       for (int j = 0; j < it.nt; ++j) {
         int seg, krow0, nvalid;
@@ -438,6 +459,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         s_phase ^= 1;
         tc_fence_after();
         if (tr) TRACE(t, j, 1);
+#ifdef MAGI_TRACE
+        if (warp == 0 && j == 0) ITRACE(0, s_items, 1);
+#endif
 
         uint32_t sr[kCols];
         auto load_s = [&]() {
@@ -617,27 +641,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
           l += bar->xl[t][ch ^ 1][rowq];
         }
+#ifdef MAGI_TRACE
+        if (warp == 0) ITRACE(0, s_items, 2);
+#endif
         mbar_wait(&bar->o_full[t], o_phase);
         o_phase ^= 1;
         tc_fence_after();
+#ifdef MAGI_TRACE
+        if (warp == 0) ITRACE(0, s_items, 3);
+#endif
         const float inv_l = 1.f / l;
-#pragma unroll 1
+#pragma unroll kEpiUnroll
         for (int c = 0; c < kCols; c += 32) {
           uint32_t orr[32];
           MAGI_TMEM_LD32(tO + c, orr, 0);
           tmem_wait_ld();
           if (store_ok) {
+            // One thread owns one row, so the 32 lanes of a store instruction hit 32 different rows: with 16-byte
+            // stores every one of them is HALF a 32-byte sector, and the per-item trace (tools/trace_items.py) showed
+            // the epilogue at 5 700 cycles, 27 % of a 4-tile cross-attention item. 32-byte stores (STG.256) halve
+            // the instructions and write whole sectors; they need 32-byte aligned rows (checked on the host).
+            uint32_t w[16];
 #pragma unroll
-            for (int k = 0; k < 32; k += 8) {
-              uint4 v;
-              v.x = pack_bf16x2(__uint_as_float(orr[k + 0]) * inv_l, __uint_as_float(orr[k + 1]) * inv_l);
-              v.y = pack_bf16x2(__uint_as_float(orr[k + 2]) * inv_l, __uint_as_float(orr[k + 3]) * inv_l);
-              v.z = pack_bf16x2(__uint_as_float(orr[k + 4]) * inv_l, __uint_as_float(orr[k + 5]) * inv_l);
-              v.w = pack_bf16x2(__uint_as_float(orr[k + 6]) * inv_l, __uint_as_float(orr[k + 7]) * inv_l);
-              *reinterpret_cast<uint4*>(orow + c + k) = v;
+            for (int k = 0; k < 16; ++k)
+              w[k] = pack_bf16x2(__uint_as_float(orr[2 * k]) * inv_l, __uint_as_float(orr[2 * k + 1]) * inv_l);
+            if (p.out_align32) {
+              stg256(orow + c, w);
+              stg256(orow + c + 16, w + 8);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 16; k += 4)
+                *reinterpret_cast<uint4*>(orow + c + 2 * k) = make_uint4(w[k], w[k + 1], w[k + 2], w[k + 3]);
             }
           }
         }
+#ifdef MAGI_TRACE
+        if (warp == 0) { ITRACE(0, s_items, 4); ++s_items; }
+#endif
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar->o_free[t]);
@@ -724,14 +764,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #endif
       const int nt = uniform(it.nt);
       if (nt == 0) continue;
+      ITRACE(1, item_cnt, 0);
       const uint32_t o_free_parity = (item_cnt & 1) ^ 1;
       const uint32_t qs = item_cnt % kQStages;                       // Q stage of this item
       const uint64_t q0_desc = q_desc_base + static_cast<uint64_t>((qs * 2 * kTileBytes) >> 4);
       const uint64_t q1_desc = q0_desc + static_cast<uint64_t>(kTileBytes >> 4);
       mbar_wait_warp(&bar->q_full[qs], (item_cnt / kQStages) & 1);
+      ITRACE(1, item_cnt, 1);
       // K_0 -> S0(0), S1(0)
       mbar_wait_warp(&bar->kv_full[stage], phase);
       tc_fence_after();
+      ITRACE(1, item_cnt, 2);
       uint32_t kst = stage;
       advance();
       if (elect_one()) {
@@ -744,6 +787,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (nt == 1) tc_commit(&bar->q_empty[qs]);
       }
       __syncwarp();
+      ITRACE(1, item_cnt, 3);
       // V_0 -> O0 = P0(0) V_0
       mbar_wait_warp(&bar->kv_full[stage], phase);
       uint32_t vst = stage;
@@ -797,6 +841,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_commit(&bar->o_full[1]);
       }
       __syncwarp();
+      ITRACE(1, item_cnt, 4);
       ++item_cnt;
     }
   } else if (warp == kTmaWarp) {
@@ -847,8 +892,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       it.h = uniform(it.h); it.hkv = uniform(it.hkv); it.qrow0 = uniform(it.qrow0);
       it.ka0 = uniform(it.ka0); it.ka1 = uniform(it.ka1); it.kb0 = uniform(it.kb0); it.kb1 = uniform(it.kb1);
       if (it.nt == 0) continue;
+      ITRACE(2, item_cnt, 0);
       const uint32_t qs = item_cnt % kQStages;
       mbar_wait_warp(&bar->q_empty[qs], ((item_cnt / kQStages) & 1) ^ 1);
+      ITRACE(2, item_cnt, 1);
       if (elect_one()) {
         uint8_t* qdst = smem_q + qs * 2 * kTileBytes;
         mbar_expect_tx(&bar->q_full[qs], 2 * kTileBytes);
@@ -859,6 +906,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
       __syncwarp();
+      ITRACE(2, item_cnt, 2);
       for (int j = 0; j < it.nt; ++j) {
         int seg, krow0, nvalid;
         tile_info(it, j, seg, krow0, nvalid);
@@ -878,6 +926,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
+      ITRACE(2, item_cnt, 3);
       ++item_cnt;
     }
   } else {
@@ -926,6 +975,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #ifdef MAGI_TRACE
 extern "C" __attribute__((visibility("default"))) int magi_debug_read_trace(long long* host, size_t bytes) {
   return (int)cudaMemcpyFromSymbol(host, g_trace, bytes < sizeof(g_trace) ? bytes : sizeof(g_trace));
+}
+extern "C" __attribute__((visibility("default"))) int magi_debug_read_itrace(long long* host, size_t bytes) {
+  return (int)cudaMemcpyFromSymbol(host, g_itrace, bytes < sizeof(g_itrace) ? bytes : sizeof(g_itrace));
 }
 #endif
 

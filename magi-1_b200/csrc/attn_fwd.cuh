@@ -27,6 +27,7 @@ struct AttnKernelParams {
   // do their work on the SMs the earlier kernel has already left, and the launch still completes in stream order
   int pdl_wait_at_end;
   int* counters;                              // {next item, CTAs finished}, the last two ints of the plan workspace
+  int out_align32;                            // every output row is 32-byte aligned: the epilogue may use STG.256
   int fill_uncovered;                         // rows covered by no q range get out = 0, lse = -inf (single-CTA kernel)
   int total_q;
 };

@@ -465,6 +465,24 @@ def test_fused_all_to_all_routing_on_virtual_ranks(F, cp, Hq, Hkv):
         assert not got[:, :, 1].any()          # slot n = 1 (the cross-attention's) is left alone
 
 
+def test_output_rows_that_are_only_16_byte_aligned(F):
+    """The epilogue writes 32-byte vectors when every output row is 32-byte aligned (the normal case) and falls back to
+    16-byte stores otherwise: a destination whose token stride is a multiple of 8 but not of 16 elements, and one whose
+    base is offset by 16 bytes, must give the same bits as the aligned destination."""
+    Tq, Hq, Hkv = 300, 4, 2
+    q, kv = bf(rnd((Tq, Hq, 128), 1)), bf(rnd((500, Hkv, 256), 2))
+    qr, kr = i32([[0, 130], [130, 300]]), i32([[0, 200], [100, 500]])
+    ref, _ = F.attn_ranges(q, kv[..., :128], kv[..., 128:], qr, kr, return_lse=False)
+    wide = torch.zeros(Tq, Hq * 128 + 8, dtype=torch.bfloat16, device="cuda")           # token stride 520: 16-byte rows
+    out = wide[:, :Hq * 128].unflatten(1, (Hq, 128))
+    F.attn_ranges(q, kv[..., :128], kv[..., 128:], qr, kr, out=out, return_lse=False)
+    assert torch.equal(out, ref) and not wide[:, Hq * 128:].any()
+    flat = torch.zeros(Tq * Hq * 128 + 8, dtype=torch.bfloat16, device="cuda")           # base offset by 16 bytes
+    out2 = flat[8:].view(Tq, Hq, 128)
+    F.attn_ranges(q, kv[..., :128], kv[..., 128:], qr, kr, out=out2, return_lse=False)
+    assert torch.equal(out2, ref) and not flat[:8].any()
+
+
 def test_overlapped_launch_gives_the_same_bits(F):
     """magi_attn_args.launch_dependency = 1: the cross-attention launch that may start under the tail of the
     self-attention launch before it (programmatic dependent launch, wait moved to the end of the kernel) - same bits
