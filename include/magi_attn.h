@@ -368,6 +368,15 @@ typedef struct magi_qkv_proj_args {
   void* cache;
   int64_t cache_token_stride, cache_head_stride, cache_row_offset, cache_rows;
   int32_t num_sms; /* 0 = all SMs of the current device */
+  /* Fused Ulysses input all-to-all (num_peers = cp > 1), the routing of magi_prologue_args.peer_*: head slice c of q and
+   * of the packed [K|V] is stored straight into rank c's receive buffer - (all rows, num_heads_q / cp, 128) and
+   * (all rows, max(1, num_heads_kv / cp), 256) - at row peer_row_offset + r, with KV-head replication when
+   * cp > num_heads_kv (NVLink peer memory; the caller owns the cross-GPU barrier). q_out / kv_out / cache are then
+   * unused (may be NULL); qx_out stays local. */
+  int32_t num_peers;
+  void* peer_q_out[MAGI_MAX_PEERS];
+  void* peer_kv_out[MAGI_MAX_PEERS];
+  int64_t peer_row_offset;
 } magi_qkv_proj_args;
 MAGI_API int magi_qkv_proj_norm_rope_fwd(const magi_qkv_proj_args* args, void* stream);
 

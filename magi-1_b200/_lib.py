@@ -185,6 +185,10 @@ class MagiQkvProjArgs(C.Structure):
         ("cache_row_offset", C.c_int64),
         ("cache_rows", C.c_int64),
         ("num_sms", C.c_int32),
+        ("num_peers", C.c_int32),
+        ("peer_q_out", C.c_void_p * MAX_PEERS),
+        ("peer_kv_out", C.c_void_p * MAX_PEERS),
+        ("peer_row_offset", C.c_int64),
     ]
 
 

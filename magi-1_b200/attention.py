@@ -725,19 +725,34 @@ class FullyParallelAttention(nn.Module):
         hq_loc, hkv_loc = divide(Hq, cp), self.num_query_groups_per_partition
         ws = cpm.UlyssesPeerWorkspace.get(mpu.get_cp_group(), total_rows, max(split), hq_loc, hkv_loc, Hq, dev)
         row_off, bounds, head_off = cpm.fused_ulysses_plan(split, rank, Hq, cp)
-        xq, xk, xv = self._project(mixed_qqkv)
         cache, start, app = self._cache_plan(inference_params, meta_args, total_rows, dt, dev)
         # when every row of this forward is cached, the peers store K/V straight into the cache slot
         direct = (cache is not None and app == total_rows
                   and getattr(self, "_cache_peer_of", None) == cache.data_ptr())
         row_bytes = hkv_loc * 2 * F.HEAD_DIM * 2
         kv_ptrs = [p_ + start * row_bytes for p_ in self._cache_peer_ptrs] if direct else ws.kv_ptrs
-        # the cross-attention's projections + norms ride in the same launch (they need no communication)
-        cross = self.cross_prologue_inputs(mixed_qqkv, key_value_states)
-        F.qk_norm_rope(xq, xk, xv, Hq, Hkv, self._ln(self.q_layernorm), self._ln(self.k_layernorm), sin_emb, cos_emb,
-                       batch=1, eps=eps, zero_centered_gamma=z, head_perm_cp=cp, peer_q_out=ws.q_ptrs,
-                       peer_kv_out=kv_ptrs, peer_row_offset=row_off, peer_heads=(hq_loc, hkv_loc), cross=cross)
-        xq_rows, x_kv = ([cross["qx"]], cross["tkv"]) if cross is not None else (None, None)
+        lnx = self._ln(self.q_layernorm_xattn) + self._ln(self.k_layernorm_xattn)
+        if (getattr(self.engine_config, "fused_qkv_proj", False) and dt == torch.bfloat16
+                and mixed_qqkv.shape[-1] % 64 == 0 and all(t.dtype == torch.bfloat16 for t in lnx)):
+            # projections + prologue + input all-to-all as ONE launch: the GEMM's epilogue normalises / rotates every
+            # head and stores it into the owning rank's receive buffer while the main loop computes the next tile
+            _, _, qx = F.qkv_proj_norm_rope(
+                mixed_qqkv.reshape(sq, -1), self.linear_qkv.stacked_weight(True), Hq, Hkv, self._ln(self.q_layernorm),
+                self._ln(self.k_layernorm), sin_emb, cos_emb, ln_qx=self._ln(self.q_layernorm_xattn), batch=1, eps=eps,
+                zero_centered_gamma=z, peer_q_out=ws.q_ptrs, peer_kv_out=kv_ptrs, peer_row_offset=row_off)
+            kvx = torch.nn.functional.linear(key_value_states, self.linear_kv_xattn.weight)
+            cross = dict(text_kv=kvx.view(key_value_states.shape[0], Hkv, 2 * F.HEAD_DIM),
+                         ln_tk=self._ln(self.k_layernorm_xattn))
+            F.qk_norm_rope(None, None, None, Hq, Hkv, None, None, None, None, eps=eps, zero_centered_gamma=z, cross=cross)
+            xq_rows, x_kv = [qx], cross["tkv"]
+        else:
+            xq, xk, xv = self._project(mixed_qqkv)
+            # the cross-attention's projections + norms ride in the same launch (they need no communication)
+            cross = self.cross_prologue_inputs(mixed_qqkv, key_value_states)
+            F.qk_norm_rope(xq, xk, xv, Hq, Hkv, self._ln(self.q_layernorm), self._ln(self.k_layernorm), sin_emb,
+                           cos_emb, batch=1, eps=eps, zero_centered_gamma=z, head_perm_cp=cp, peer_q_out=ws.q_ptrs,
+                           peer_kv_out=kv_ptrs, peer_row_offset=row_off, peer_heads=(hq_loc, hkv_loc), cross=cross)
+            xq_rows, x_kv = ([cross["qx"]], cross["tkv"]) if cross is not None else (None, None)
         # no communication in the cross-attention (context_parallel.py:591): its projections + norms are issued
         # before the barrier, its attention before the second one
         proj = proj_ptrs = None

@@ -576,7 +576,20 @@ int magi_qkv_proj_norm_rope_fwd(const magi_qkv_proj_args* a, void* stream_) {
   MAGI_CHECK(a->ln_dtype == 0 || a->ln_dtype == 1, "ln_dtype must be 0 (fp32) or 1 (bf16)");
   MAGI_CHECK(a->batch >= 1, "batch must be >= 1");
   if (a->rows == 0) return 0;
-  MAGI_CHECK(a->x && a->w && a->q_out && a->kv_out && a->ln_q_w && a->ln_q_b && a->ln_k_w && a->ln_k_b, "NULL pointer");
+  const int cp = a->num_peers > 1 ? a->num_peers : 0;
+  MAGI_CHECK(a->num_peers >= 0 && a->num_peers <= MAGI_MAX_PEERS && a->num_peers != 1, "num_peers must be 0 or 2..8");
+  MAGI_CHECK(a->x && a->w && a->ln_q_w && a->ln_q_b && a->ln_k_w && a->ln_k_b, "NULL pointer");
+  MAGI_CHECK(cp > 0 || (a->q_out && a->kv_out), "q_out / kv_out are NULL");
+  if (cp > 0) {
+    MAGI_CHECK(a->cache == nullptr, "the cache append is not available together with peer routing");
+    MAGI_CHECK(a->num_heads_q % cp == 0 && (a->num_heads_kv % cp == 0 || cp % a->num_heads_kv == 0),
+               "head counts and num_peers are not compatible");
+    MAGI_CHECK(a->peer_row_offset >= 0, "negative peer_row_offset");
+    for (int i = 0; i < cp; ++i)
+      MAGI_CHECK(a->peer_q_out[i] && a->peer_kv_out[i] &&
+                     ((reinterpret_cast<uintptr_t>(a->peer_q_out[i]) | reinterpret_cast<uintptr_t>(a->peer_kv_out[i])) & 15) == 0,
+                 "bad peer_q_out / peer_kv_out[%d]", i);
+  }
   MAGI_CHECK(a->num_heads_qx == 0 || (a->qx_out && a->ln_qx_w && a->ln_qx_b), "qx path needs qx_out, ln_qx_w, ln_qx_b");
   MAGI_CHECK((a->sin == nullptr) == (a->cos == nullptr), "sin and cos must both be given or both be NULL");
   MAGI_CHECK(a->q_out_token_stride % 8 == 0 && a->q_out_head_stride % 8 == 0 && a->kv_out_token_stride % 8 == 0 &&
@@ -604,6 +617,21 @@ int magi_qkv_proj_norm_rope_fwd(const magi_qkv_proj_args* a, void* stream_) {
   p.qx_out = a->qx_out; p.qx_out_token_stride = a->qx_out_token_stride; p.qx_out_head_stride = a->qx_out_head_stride;
   p.cache = a->cache; p.cache_token_stride = a->cache_token_stride; p.cache_head_stride = a->cache_head_stride;
   p.cache_row_offset = a->cache_row_offset; p.cache_rows = a->cache ? a->cache_rows : 0;
+  p.cp = cp;
+  p.hq_loc = cp > 0 ? a->num_heads_q / cp : a->num_heads_q;
+  p.hkv_loc = cp > 0 ? (a->num_heads_kv >= cp ? a->num_heads_kv / cp : 1) : a->num_heads_kv;
+  p.peer_row_offset = a->peer_row_offset;
+  uintptr_t bits = reinterpret_cast<uintptr_t>(a->qx_out) | reinterpret_cast<uintptr_t>(a->cache);
+  for (int i = 0; i < 8; ++i) {
+    p.peer_q[i] = i < cp ? a->peer_q_out[i] : nullptr;
+    p.peer_kv[i] = i < cp ? a->peer_kv_out[i] : nullptr;
+    bits |= reinterpret_cast<uintptr_t>(p.peer_q[i]) | reinterpret_cast<uintptr_t>(p.peer_kv[i]);
+  }
+  if (cp == 0) bits |= reinterpret_cast<uintptr_t>(a->q_out) | reinterpret_cast<uintptr_t>(a->kv_out);
+  p.align32 = (bits & 31) == 0 && a->qx_out_token_stride % 16 == 0 && a->qx_out_head_stride % 16 == 0 &&
+              a->cache_token_stride % 16 == 0 && a->cache_head_stride % 16 == 0 &&
+              (cp > 0 || (a->q_out_token_stride % 16 == 0 && a->q_out_head_stride % 16 == 0 &&
+                          a->kv_out_token_stride % 16 == 0 && a->kv_out_head_stride % 16 == 0));
   int sms = a->num_sms;
   if (sms <= 0) { if (int rc = device_sm_count(&sms)) return rc; }
   MAGI_CUDA(magi::qkv_gemm_launch(tm_x, tm_w, p, sms, stream));

@@ -59,6 +59,20 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       : "memory");
 }
 
+// Tile order: bands of kBandM row-tiles, inside a band column-tile major, row-tile minor - so that the tiles the CTA
+// pairs work on at the same time (consecutive indices) share a few row-tiles of X and a few column-tiles of W that fit
+// L2 together. Row-major order made every wave of pairs stream the WHOLE weight: at 24B shapes (W = 176 MB > L2) that
+// was m_tiles x |W| = 18.7 GB of HBM reads per launch, more than the GEMM's own time.
+constexpr int kBandM = 8;
+__device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int& mt, int& nt) {
+  const int band = tile / (kBandM * n_tiles);
+  const int m0 = band * kBandM;
+  const int bh = min(kBandM, m_tiles - m0);          // height of this (possibly last, shorter) band
+  const int local = tile - band * kBandM * n_tiles;
+  nt = local / bh;
+  mt = m0 + (local - nt * bh);
+}
+
 __device__ __forceinline__ float bf16_round_f(float x) {
   return __uint_as_float(static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(x))) << 16);
 }
@@ -133,7 +147,8 @@ qkv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     // ====================================================================== TMA producer (both CTAs)
     uint32_t stage = 0, phase = 0;
     for (int tile = pair; tile < total_tiles; tile += pairs) {
-      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+      int mt, nt;
+      tile_coords(tile, m_tiles, n_tiles, mt, nt);
       const int row0 = mt * 2 * kBM + rank * kBM;          // this CTA's 128 rows of X
       const int wrow0 = nt * kBN + rank * 128;             // this CTA's 128 rows of W (its half of the tile's N)
       for (int kb = 0; kb < k_blocks; ++kb) {
@@ -184,7 +199,8 @@ qkv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     const int Hq = p.Hq, Hkv = p.Hkv;
     uint32_t t = 0;
     for (int tile = pair; tile < total_tiles; tile += pairs, ++t) {
-      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+      int mt, nt;
+      tile_coords(tile, m_tiles, n_tiles, mt, nt);
       const uint32_t b = t & 1;
       const int64_t row = static_cast<int64_t>(mt) * 2 * kBM + rank * kBM + quarter * 32 + lane;
       const bool row_ok = row < p.rows;
@@ -248,31 +264,65 @@ qkv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           }
         }
         if (!row_ok) continue;
-        __nv_bfloat16* dst;
-        __nv_bfloat16* cache_dst = nullptr;
-        if (type == 0) {
-          dst = reinterpret_cast<__nv_bfloat16*>(p.q_out) + row * p.q_out_token_stride + h * p.q_out_head_stride;
+        // destinations of this head vector: one, plus the KV-cache slot, or - context parallel with fewer kv heads than
+        // ranks - the receive buffers of every rank that holds a replica of the head
+        __nv_bfloat16* dst[9];
+        int nd = 1;
+        const bool peers = p.cp > 1 && type != 3;
+        if (peers) {
+          const int64_t prow = p.peer_row_offset + row;
+          if (type == 0) {
+            dst[0] = reinterpret_cast<__nv_bfloat16*>(p.peer_q[h / p.hq_loc]) + prow * (p.hq_loc * 128) +
+                     (h % p.hq_loc) * 128;
+          } else {
+            const int off = type == 2 ? 128 : 0;
+            if (p.cp > Hkv) {       // repeat_interleave (context_parallel.py:393-394): rank c holds kv head c / rep
+              const int rep = p.cp / Hkv;
+              nd = rep;
+              for (int c = 0; c < rep; ++c)
+                dst[c] = reinterpret_cast<__nv_bfloat16*>(p.peer_kv[h * rep + c]) + prow * 256 + off;
+            } else {
+              dst[0] = reinterpret_cast<__nv_bfloat16*>(p.peer_kv[h / p.hkv_loc]) + prow * (p.hkv_loc * 256) +
+                       (h % p.hkv_loc) * 256 + off;
+            }
+          }
+        } else if (type == 0) {
+          dst[0] = reinterpret_cast<__nv_bfloat16*>(p.q_out) + row * p.q_out_token_stride + h * p.q_out_head_stride;
         } else if (type == 3) {
-          dst = reinterpret_cast<__nv_bfloat16*>(p.qx_out) + row * p.qx_out_token_stride + h * p.qx_out_head_stride;
+          dst[0] = reinterpret_cast<__nv_bfloat16*>(p.qx_out) + row * p.qx_out_token_stride + h * p.qx_out_head_stride;
         } else {
           const int off = type == 2 ? 128 : 0;
-          dst = reinterpret_cast<__nv_bfloat16*>(p.kv_out) + row * p.kv_out_token_stride + h * p.kv_out_head_stride + off;
+          dst[0] = reinterpret_cast<__nv_bfloat16*>(p.kv_out) + row * p.kv_out_token_stride + h * p.kv_out_head_stride +
+                   off;
           if (p.cache != nullptr && row < p.cache_rows)
-            cache_dst = reinterpret_cast<__nv_bfloat16*>(p.cache) + (p.cache_row_offset + row) * p.cache_token_stride +
+            dst[nd++] = reinterpret_cast<__nv_bfloat16*>(p.cache) + (p.cache_row_offset + row) * p.cache_token_stride +
                         h * p.cache_head_stride + off;
         }
+        // one thread owns one row: 32-byte stores write whole sectors (16-byte ones half a sector each, see the
+        // attention epilogue); they need 32-byte aligned destination rows (checked on the host)
 #pragma unroll
-        for (int i = 0; i < 128; i += 8) {
-          uint4 o;
-          o.x = pack_bf16x2(v[i], v[i + 1]); o.y = pack_bf16x2(v[i + 2], v[i + 3]);
-          o.z = pack_bf16x2(v[i + 4], v[i + 5]); o.w = pack_bf16x2(v[i + 6], v[i + 7]);
-          *reinterpret_cast<uint4*>(dst + i) = o;
-          if (cache_dst != nullptr) *reinterpret_cast<uint4*>(cache_dst + i) = o;
+        for (int i = 0; i < 128; i += 16) {
+          uint32_t o[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = pack_bf16x2(v[i + 2 * k], v[i + 2 * k + 1]);
+          for (int d = 0; d < nd; ++d) {
+            if (p.align32) {
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst[d] + i), "r"(o[0]),
+                           "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
+                           : "memory");
+            } else {
+              *reinterpret_cast<uint4*>(dst[d] + i) = make_uint4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<uint4*>(dst[d] + i + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+          }
         }
       }
     }
   }
 
+  // stores into other GPUs' memory must be visible system-wide before the kernel (and the device barrier that follows
+  // it in stream order) completes - see the note at the end of the prologue kernel
+  if (p.cp > 1 && warp >= 2) __threadfence_system();
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();

@@ -21,6 +21,14 @@ struct QkvGemmParams {
   void* kv_out; int64_t kv_out_token_stride, kv_out_head_stride;
   void* qx_out; int64_t qx_out_token_stride, qx_out_head_stride;
   void* cache; int64_t cache_token_stride, cache_head_stride, cache_row_offset, cache_rows;
+  // fused Ulysses input all-to-all (context parallel): head slice c of q / [K|V] goes straight into rank c's receive
+  // buffer ((all rows, hq_loc, 128) / (all rows, hkv_loc, 256)) at row peer_row_offset + r - the same routing as the
+  // prologue kernel's peer mode (magi_prologue_args.peer_*), with KV-head replication when cp > Hkv. qx stays local.
+  int cp;                        // 0 / 1 = off
+  int hq_loc, hkv_loc;
+  void* peer_q[8]; void* peer_kv[8];
+  int64_t peer_row_offset;
+  int align32;                   // every destination row is 32-byte aligned: 32-byte stores
 };
 
 cudaError_t qkv_gemm_launch(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const QkvGemmParams& p, int num_ctas,

@@ -781,6 +781,9 @@ def qkv_proj_norm_rope(
     cache_row_offset: int = 0,
     cache_rows: int = 0,
     num_sms: int = 0,
+    peer_q_out: Optional[Sequence[int]] = None,
+    peer_kv_out: Optional[Sequence[int]] = None,
+    peer_row_offset: int = 0,
 ):
     """The q / k / v (and, with ln_qx, the cross-attention qx) projections of CustomLayerNormLinear
     (dit_module.py:405-425) and the QK-LayerNorm + RoPE prologue (get_q / get_kv, :953-996; q half of get_xqkv,
@@ -788,7 +791,11 @@ def qkv_proj_norm_rope(
 
     x: (rows, hidden) bf16, the LayerNorm'ed hidden states in "(sq b)" row order. w: the stacked weight
     [Wq; Wk; Wv (; Wqx)] of shape ((Hq + 2 Hkv (+ Hq)) * 128, hidden), see `stack_qkv_weights`.
-    Returns (q (rows, Hq, 128), kv (rows, Hkv, 256) packed [K | V], qx (rows, Hq, 128) or None)."""
+    Returns (q (rows, Hq, 128), kv (rows, Hkv, 256) packed [K | V], qx (rows, Hq, 128) or None).
+
+    peer_q_out / peer_kv_out (cp device pointers each) + peer_row_offset: the Ulysses input all-to-all fused into the
+    GEMM's epilogue, with the routing of `qk_norm_rope`'s peer arguments (head slice c -> rank c's receive buffer, at
+    row peer_row_offset + r, KV-head replication when cp > Hkv); returns (None, None, qx)."""
     if not x.is_cuda or x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or x.dim() != 2 or w.dim() != 2:
         raise ValueError("x and w must be 2-D bfloat16 CUDA tensors (this package has no CPU path)")
     rows, hidden = x.shape
@@ -803,8 +810,12 @@ def qkv_proj_norm_rope(
         if t.dtype != ln_q[0].dtype or t.numel() != HEAD_DIM or not t.is_cuda:
             raise ValueError("q / k LayerNorm parameters must be 128-element CUDA tensors of one dtype")
     dev = x.device
-    q = torch.empty((rows, num_heads_q, HEAD_DIM), dtype=torch.bfloat16, device=dev)
-    kv = torch.empty((rows, num_heads_kv, 2 * HEAD_DIM), dtype=torch.bfloat16, device=dev)
+    peers = peer_q_out is not None
+    if peers and (peer_kv_out is None or len(peer_q_out) != len(peer_kv_out) or not 2 <= len(peer_q_out) <= _lib.MAX_PEERS
+                  or (cache is not None and cache_rows > 0)):
+        raise ValueError("peer routing needs 2..8 pointers for q and for kv and excludes the cache append")
+    q = None if peers else torch.empty((rows, num_heads_q, HEAD_DIM), dtype=torch.bfloat16, device=dev)
+    kv = None if peers else torch.empty((rows, num_heads_kv, 2 * HEAD_DIM), dtype=torch.bfloat16, device=dev)
     qx = torch.empty((rows, num_heads_q, HEAD_DIM), dtype=torch.bfloat16, device=dev) if with_qx else None
     a = MagiQkvProjArgs()
     a.x, a.rows, a.x_row_stride, a.hidden = x.data_ptr(), rows, x.stride(0), hidden
@@ -823,8 +834,13 @@ def qkv_proj_norm_rope(
         if sin.shape != (rows // batch, 48) or cos.shape != sin.shape:
             raise ValueError("sin / cos must be (rows / batch, 48)")
         a.sin, a.cos = sin.data_ptr(), cos.data_ptr()
-    a.q_out, a.q_out_token_stride, a.q_out_head_stride = q.data_ptr(), q.stride(0), q.stride(1)
-    a.kv_out, a.kv_out_token_stride, a.kv_out_head_stride = kv.data_ptr(), kv.stride(0), kv.stride(1)
+    if peers:
+        a.num_peers, a.peer_row_offset = len(peer_q_out), peer_row_offset
+        for i, (pq, pk) in enumerate(zip(peer_q_out, peer_kv_out)):
+            a.peer_q_out[i], a.peer_kv_out[i] = pq, pk
+    else:
+        a.q_out, a.q_out_token_stride, a.q_out_head_stride = q.data_ptr(), q.stride(0), q.stride(1)
+        a.kv_out, a.kv_out_token_stride, a.kv_out_head_stride = kv.data_ptr(), kv.stride(0), kv.stride(1)
     if with_qx:
         a.qx_out, a.qx_out_token_stride, a.qx_out_head_stride = qx.data_ptr(), qx.stride(0), qx.stride(1)
     if cache is not None and cache_rows > 0:

@@ -132,13 +132,22 @@ def stack_qkv_weights(wq, wk, wv, wqx=None):
 
 
 def qkv_proj_norm_rope(x, w, num_heads_q, num_heads_kv, ln_q, ln_k, sin, cos, ln_qx=None, batch=1, eps=1e-6,
-                       zero_centered_gamma=True, cache=None, cache_row_offset=0, cache_rows=0, num_sms=0):
+                       zero_centered_gamma=True, cache=None, cache_row_offset=0, cache_rows=0, num_sms=0,
+                       peer_q_out=None, peer_kv_out=None, peer_row_offset=0):
     """The fused projection GEMM as the composition it replaces: nn.Linear in bf16, then the prologue double."""
     y = _bf(O.linear_bf16(_np(x), _np(w)))
     nq, nk = num_heads_q * HEAD_DIM, num_heads_kv * HEAD_DIM
-    q, kv = qk_norm_rope(y[:, :nq], y[:, nq:nq + nk], y[:, nq + nk:nq + 2 * nk], num_heads_q, num_heads_kv, ln_q, ln_k,
-                         sin, cos, batch=batch, eps=eps, zero_centered_gamma=zero_centered_gamma, cache=cache,
-                         cache_row_offset=cache_row_offset, cache_rows=cache_rows)
+    if peer_q_out is not None:    # the Ulysses input all-to-all fused into the epilogue: the prologue double's routing
+        cp = len(peer_q_out)
+        hkv_loc = num_heads_kv // cp if num_heads_kv >= cp else 1
+        q, kv = qk_norm_rope(y[:, :nq], y[:, nq:nq + nk], y[:, nq + nk:nq + 2 * nk], num_heads_q, num_heads_kv, ln_q,
+                             ln_k, sin, cos, batch=batch, eps=eps, zero_centered_gamma=zero_centered_gamma,
+                             head_perm_cp=cp, peer_q_out=peer_q_out, peer_kv_out=peer_kv_out,
+                             peer_row_offset=peer_row_offset, peer_heads=(num_heads_q // cp, hkv_loc))
+    else:
+        q, kv = qk_norm_rope(y[:, :nq], y[:, nq:nq + nk], y[:, nq + nk:nq + 2 * nk], num_heads_q, num_heads_kv, ln_q,
+                             ln_k, sin, cos, batch=batch, eps=eps, zero_centered_gamma=zero_centered_gamma, cache=cache,
+                             cache_row_offset=cache_row_offset, cache_rows=cache_rows)
     qx = None
     if ln_qx is not None:
         qx, _ = qk_norm_rope(y[:, nq + 2 * nk:], None, None, num_heads_q, num_heads_kv, ln_qx, None, None, None,

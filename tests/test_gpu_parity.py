@@ -662,6 +662,38 @@ def test_mlp_activation_vs_oracle_and_libraries(F, gated, rows, f):
     assert torch.equal(out2, out)
 
 
+@pytest.mark.parametrize("cp,Hq,Hkv", [(2, 4, 2), (4, 8, 2), (8, 8, 1)])
+def test_fused_projection_gemm_peer_routing_on_virtual_ranks(F, cp, Hq, Hkv):
+    """The Ulysses input all-to-all fused into the projection GEMM's epilogue (magi_qkv_proj_args.peer_*), on ONE device:
+    every "rank" projects its own rows and stores each head slice into the owning rank's receive buffer. What arrives
+    must be, bit for bit, the head slices of the single-rank fused GEMM over all rows (incl. KV-head replication when
+    cp > Hkv); the cross-attention query stays local."""
+    S, hidden = 700, 256
+    split = [S // cp + (1 if i < S % cp else 0) for i in range(cp)]
+    offs = np.concatenate([[0], np.cumsum(split)]).astype(np.int64)
+    x = bf(rnd((S, hidden), 1))
+    w = F.stack_qkv_weights(*[bf(rnd((h * 128, hidden), 2 + i, hidden ** -0.5)) for i, h in enumerate((Hq, Hkv, Hkv, Hq))])
+    ln = [torch.from_numpy(rnd((128,), 10 + i, 0.2)).cuda() for i in range(4)]
+    lnx = (bf(rnd((128,), 20, 0.2)), bf(rnd((128,), 21, 0.2)))
+    ang = torch.from_numpy(rnd((S, 48), 30, 3.0))
+    sin, cos = torch.sin(ang).cuda(), torch.cos(ang).cuda()
+    q_full, kv_full, qx_full = F.qkv_proj_norm_rope(x, w, Hq, Hkv, (ln[0], ln[1]), (ln[2], ln[3]), sin, cos, ln_qx=lnx)
+    hn, hkv_loc = Hq // cp, max(1, Hkv // cp)
+    recv_q = [torch.zeros(S, hn, 128, dtype=torch.bfloat16, device="cuda") for _ in range(cp)]
+    recv_kv = [torch.zeros(S, hkv_loc, 256, dtype=torch.bfloat16, device="cuda") for _ in range(cp)]
+    for me in range(cp):
+        sl = slice(int(offs[me]), int(offs[me + 1]))
+        q, kv, qx = F.qkv_proj_norm_rope(x[sl], w, Hq, Hkv, (ln[0], ln[1]), (ln[2], ln[3]), sin[sl], cos[sl], ln_qx=lnx,
+                                         peer_q_out=[t.data_ptr() for t in recv_q],
+                                         peer_kv_out=[t.data_ptr() for t in recv_kv], peer_row_offset=int(offs[me]))
+        assert q is None and kv is None and torch.equal(qx, qx_full[sl])
+    rep = cp // Hkv if cp > Hkv else 1
+    for c in range(cp):
+        assert torch.equal(recv_q[c], q_full[:, c * hn:(c + 1) * hn])
+        k_lo = c // rep if cp > Hkv else c * hkv_loc
+        assert torch.equal(recv_kv[c], kv_full[:, k_lo:k_lo + hkv_loc])
+
+
 @pytest.mark.parametrize("rows,hidden,Hq,Hkv,with_qx,batch,fp32_ln", [
     (300, 256, 4, 2, True, 1, True), (1000, 3072, 6, 2, False, 1, True), (514, 512, 2, 1, True, 2, False)])
 def test_fused_projection_gemm_vs_oracle(F, rows, hidden, Hq, Hkv, with_qx, batch, fp32_ln):

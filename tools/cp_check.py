@@ -31,6 +31,7 @@ def main():
     from magi_b200.common import (EngineConfig, InferenceParams, ModelConfig, ModelMetaArgs, PackedCoreAttnParams,
                                   PackedCrossAttnParams)
     mpu.initialize_model_parallel(cp_size=world)
+    GEMM = os.environ.get("CP_CHECK_FUSED_GEMM") == "1"
 
     Hq, Hkv, hidden, clip = 24, 8, 512, 1111       # 1111: shards and tiles are ragged everywhere
     mc = ModelConfig(num_layers=4, hidden_size=hidden, num_attention_heads=Hq, num_query_groups=Hkv)
@@ -42,7 +43,10 @@ def main():
                                                     # like with like: the context-parallel paths project through
                                                     # cuBLAS + the prologue kernel, so the single-GPU side does too
                                                     # (the fused projection GEMM differs by single bf16 ulps)
-                                                    fused_qkv_proj=False), layer_number=1)
+                                                    # CP_CHECK_FUSED_GEMM=1: the fused projection GEMM on both
+                                                    # sides instead (under fused Ulysses its epilogue IS the input
+                                                    # all-to-all) - only that variant is run then
+                                                    fused_qkv_proj=GEMM), layer_number=1)
         g = torch.Generator().manual_seed(99)
         with torch.no_grad():
             for n, p in m.named_parameters():
@@ -83,6 +87,8 @@ def main():
     results = {}
     # CP_CHECK_STRATEGIES=cp_ring_kv,... restricts the run (the 8-GPU box time is charged 8x)
     chosen = os.environ.get("CP_CHECK_STRATEGIES", "cp_ulysses,cp_shuffle_overlap,cp_ring_kv").split(",")
+    if GEMM:
+        chosen = ["cp_ulysses"]
     for strategy in [s_ for s_ in ("cp_ulysses", "cp_shuffle_overlap", "cp_ring_kv") if s_ in chosen]:
         kv_loc = max(1, Hkv // world)
         second = kv_loc if kv_loc > 1 else 3      # whole kv heads per group, or 3 q-head groups in the MQA case
@@ -97,6 +103,8 @@ def main():
                                          if strategy == "cp_ulysses" else
                                          ((1, True, False), (1, False, False)) if strategy == "cp_ring_kv" else
                                          ((1, False, False),)) + off_variants):
+            if GEMM and not fused:
+                continue
             ref_m, cp_m = build("none", 1), build(strategy, world, offload)
             inf_ref = InferenceParams(1, 5 * clip)
             inf_cp = InferenceParams(1, 5 * clip)
@@ -168,7 +176,8 @@ def main():
                 xo = cpm.cp_post_process(world, strategy, xo.contiguous(), m_cp)
                 worst["core"] = max(worst["core"], (core.float() - ref_core.float()).abs().max().item())
                 worst["xattn"] = max(worst["xattn"], (xo.float() - ref_x.float()).abs().max().item())
-            results[f"{strategy}/{'fused-p2p' if fused else 'nccl'}/overlap{overlap}{'/kv_offload' if offload else ''}"] = worst
+            results[f"{strategy}/{'fused-p2p' if fused else 'nccl'}/overlap{overlap}{'/kv_offload' if offload else ''}"
+                    f"{'/fused-gemm' if GEMM else ''}"] = worst
     torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:
