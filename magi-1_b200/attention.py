@@ -804,10 +804,19 @@ class FullyParallelAttention(nn.Module):
         hq_loc, hkv_loc = divide(Hq, cp), (divide(Hkv, cp) if Hkv >= cp else 1)   # (also serves cp_ring_kv: no cache)
         ws = cpm.UlyssesPeerWorkspace.get(mpu.get_cp_group(), total * b, max(split) * b, hq_loc, hkv_loc, Hq, dev)
         _, bounds, head_off = cpm.fused_ulysses_plan(split, rank, Hq, cp)
-        xq, xk, xv = self._project(mixed_qqkv)
-        F.qk_norm_rope(xq, xk, xv, Hq, Hkv, self._ln(self.q_layernorm), self._ln(self.k_layernorm), sin_emb, cos_emb,
-                       batch=b, eps=eps, zero_centered_gamma=z, head_perm_cp=cp, peer_q_out=ws.q_ptrs,
-                       peer_kv_out=ws.kv_ptrs, peer_row_offset=bounds[rank] * b, peer_heads=(hq_loc, hkv_loc))
+        if (getattr(self.engine_config, "fused_qkv_proj", False) and mixed_qqkv.dtype == torch.bfloat16
+                and mixed_qqkv.shape[-1] % 64 == 0 and (Hq + 2 * Hkv) % 2 == 0):
+            # same choice as the single-GPU forward makes for batch > 1: q / k / v through the fused projection GEMM (no
+            # qx: its "(sq b) -> (b sq)" row order needs one strided view per batch row), here with peer routing
+            F.qkv_proj_norm_rope(mixed_qqkv.reshape(sq * b, -1), self.linear_qkv.stacked_weight(False), Hq, Hkv,
+                                 self._ln(self.q_layernorm), self._ln(self.k_layernorm), sin_emb, cos_emb, batch=b,
+                                 eps=eps, zero_centered_gamma=z, peer_q_out=ws.q_ptrs, peer_kv_out=ws.kv_ptrs,
+                                 peer_row_offset=bounds[rank] * b)
+        else:
+            xq, xk, xv = self._project(mixed_qqkv)
+            F.qk_norm_rope(xq, xk, xv, Hq, Hkv, self._ln(self.q_layernorm), self._ln(self.k_layernorm), sin_emb,
+                           cos_emb, batch=b, eps=eps, zero_centered_gamma=z, head_perm_cp=cp, peer_q_out=ws.q_ptrs,
+                           peer_kv_out=ws.kv_ptrs, peer_row_offset=bounds[rank] * b, peer_heads=(hq_loc, hkv_loc))
         x_prepared = self.cross_attention_prepare(mixed_qqkv, key_value_states)
         ws.barrier()                                                     # A: every rank's q / kv rows have landed
         p = meta_args.core_attn_params
