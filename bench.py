@@ -59,8 +59,8 @@ def attn_flops(w):
 # run that prints it (a number taken under a profiler is never a bench value) but read off the committed `ncu --set
 # full` capture named next to it. The algorithmic minimum (q + out + packed kv once) is 230 + 230 + 153 = 613 MB: K/V
 # re-reads by the 3 query heads of a GQA group and by the 37 query tiles of a chunk are served by L2.
-NCU_TRAFFIC = {"cfg2": (819149824, "ncu capture profiles/r02y_ncu_raw.csv (attn_fwd_kernel: 620.24 MB read + "
-                                   "198.91 MB written per launch), not re-measured by this run")}
+NCU_TRAFFIC = {"cfg2": (824810240, "ncu capture profiles/r02zz_ncu_raw.csv (attn_fwd_kernel: 622.31 MB read + "
+                                   "202.50 MB written per launch), not re-measured by this run")}
 
 
 def load_peaks():
