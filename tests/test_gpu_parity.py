@@ -465,6 +465,62 @@ def test_fused_all_to_all_routing_on_virtual_ranks(F, cp, Hq, Hkv):
         assert not got[:, :, 1].any()          # slot n = 1 (the cross-attention's) is left alone
 
 
+@pytest.mark.parametrize("grouped", [False, True])
+def test_kernel_writes_only_the_rows_its_ranges_cover(F, grouped):
+    """Write canaries (the pool has no compute-sanitizer): the destination is pre-filled with a sentinel and sits
+    between guard rows; ragged ranges that end inside a 128-row tile, start off a tile boundary and leave gaps must
+    change exactly the rows they cover - with the 32-byte epilogue stores, in the plain layout and in the grouped
+    out-projection-input layout (where the other half of every group belongs to the cross-attention)."""
+    Tq, Hq, Hkv = 1000, 8, 2
+    q, kv = bf(rnd((Tq, Hq, 128), 1)), bf(rnd((700, Hkv, 256), 2))
+    qr_l, kr_l = [[3, 130], [131, 389], [600, 857]], [[0, 200], [100, 700], [5, 133]]
+    qr, kr = i32(qr_l), i32(kr_l)
+    ref, _ = F.attn_ranges(q, kv[..., :128], kv[..., 128:], qr, kr, return_lse=False, zero_fill=True)
+    covered = torch.zeros(Tq, dtype=torch.bool, device="cuda")
+    for a, b in qr_l:
+        covered[a:b] = True
+    sent = 7.0
+    if not grouped:
+        big = torch.full((Tq + 64, Hq, 128), sent, dtype=torch.bfloat16, device="cuda")
+        out = big[32:32 + Tq]
+        F.attn_ranges(q, kv[..., :128], kv[..., 128:], qr, kr, out=out, return_lse=False)
+        assert torch.equal(out[covered], ref[covered])
+        assert bool((out[~covered] == sent).all()) and bool((big[:32] == sent).all()) and bool((big[32 + Tq:] == sent).all())
+    else:
+        big = torch.full((Tq + 64, 2 * Hq * 128), sent, dtype=torch.bfloat16, device="cuda")
+        buf = big[32:32 + Tq]
+        F.attn_ranges(q, kv[..., :128], kv[..., 128:], qr, kr, return_lse=False, proj_input=(buf, 0, 8))
+        v = buf.view(Tq, 8, 2, Hq // 8, 128)
+        assert torch.equal(v[:, :, 0].reshape(Tq, Hq, 128)[covered], ref[covered])
+        assert bool((v[:, :, 0][~covered] == sent).all()) and bool((v[:, :, 1] == sent).all())
+        assert bool((big[:32] == sent).all()) and bool((big[32 + Tq:] == sent).all())
+
+
+def test_dynamic_scheduler_is_grid_independent_and_rearms_its_counters(F):
+    """The atomic work counter lives in the plan workspace and the last CTA of a launch re-arms it: the same plan used
+    by many launches in a row, with grids of 1, 3 and all SMs (one CTA walking every item through the two-slot mailbox;
+    more CTAs than items at the other end), and both mailbox flavours (index / decoded item, chosen by the key count),
+    must give the same bits every time."""
+    Hq, Hkv = 6, 2
+    rng = np.random.default_rng(5)
+    for total_k in (900, 9000):                  # <= 8192 keys: decoded mailbox; above: index mailbox
+        Tq = 2100
+        q, kv = bf(rnd((Tq, Hq, 128), 1)), bf(rnd((total_k, Hkv, 256), 2))
+        cuts = np.sort(rng.choice(np.arange(1, Tq), size=11, replace=False))
+        edges = np.concatenate([[0], cuts, [Tq]])
+        qr_l = [[int(a), int(b)] for a, b in zip(edges[:-1], edges[1:])]
+        kr_l = []
+        for _ in qr_l:
+            a = int(rng.integers(0, total_k - 1))
+            kr_l.append([a, int(rng.integers(a + 1, total_k + 1))])
+        qr, kr = i32(qr_l), i32(kr_l)
+        plan = F.attn_plan(qr, kr, num_heads_q=Hq, total_q=Tq, total_k=total_k)
+        ref, ref_lse = F.attn_ranges(q, kv[..., :128], kv[..., 128:], qr, kr)       # per-call work list, full grid
+        for sms in (1, 3, 0, 3, 1, 0, 0):
+            out, lse = F.attn_ranges(q, kv[..., :128], kv[..., 128:], qr, kr, plan=plan, num_sms=sms)
+            assert torch.equal(out, ref) and torch.equal(lse, ref_lse), (total_k, sms)
+
+
 def test_output_rows_that_are_only_16_byte_aligned(F):
     """The epilogue writes 32-byte vectors when every output row is 32-byte aligned (the normal case) and falls back to
     16-byte stores otherwise: a destination whose token stride is a multiple of 8 but not of 16 elements, and one whose

@@ -1,6 +1,3 @@
-tag=r02zq; n=2; out=gpurun_out; mkdir -p $out
-run="python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1"
-CP_CHECK_FUSED_GEMM=1 timeout 600 $run --master-port 29700 tools/cp_check.py > $out/${tag}_cp_check_gemm_n${n}.log 2>&1
-echo "cp_check (fused gemm) rc=$?"; grep "cp_check\|CP_CHECK\|Error\|error" $out/${tag}_cp_check_gemm_n${n}.log | tail -6
-timeout 600 $run --master-port 29701 tools/cp_check.py > $out/${tag}_cp_check_n${n}.log 2>&1
-echo "cp_check rc=$?"; grep "CP_CHECK\|FAIL" $out/${tag}_cp_check_n${n}.log | tail -4
+tag=r02zs; out=gpurun_out; mkdir -p $out
+python -c "import __graft_entry__ as g; g.build()" > $out/${tag}_build.log 2>&1 || { echo "build failed"; exit 1; }
+timeout 600 python -m pytest tests -m gpu -q -k "canar or only_the_rows or scheduler or aligned or overlapped or one_prologue" > $out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -12 $out/${tag}_pytest_gpu.log

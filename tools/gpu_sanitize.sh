@@ -3,6 +3,8 @@
 # that has just exited 0 without it): the smoke pass - prologue with cache append, range-masked attention over
 # cache ++ new tokens, varlen cross-attention with an empty segment - under memcheck (default), racecheck, initcheck or
 # synccheck. Run it in a call of its own, never together with ncu.
+# NOTE (round 2): this pool refuses compute-sanitizer ("closed on this pool: runs under it have left GPUs needing a
+# reset"); the write-canary / NaN-padding / bit-identity tests of tests/test_gpu_parity.py stand in for it.
 #
 #   gpurun --timeout 900 -- 'bash tools/gpu_sanitize.sh memcheck r02a'
 tool="${1:-memcheck}"; tag="${2:-rXX}"
