@@ -377,8 +377,29 @@ typedef struct magi_qkv_proj_args {
   void* peer_q_out[MAGI_MAX_PEERS];
   void* peer_kv_out[MAGI_MAX_PEERS];
   int64_t peer_row_offset;
+  /* fp8_quant (PerTensorQuantizedFp8Linear, dit_module.py:431-457: the q / qx / k / v projections of every layer but
+   * the first and the last when engine_config.fp8_quant, e.g. example/4.5B/4.5B_distill_quant_config.json): fp8 != 0
+   * means x and w hold float8_e4m3fn bytes - x as written by magi_fp8_quantize, w the stacked fp8 weights - strides
+   * are in bytes = elements, hidden and both row strides must be multiples of 128 / 16, and every 128-wide head of
+   * the fp32 accumulator is multiplied by out_scale[t] before the bf16 rounding, t = 0 q, 1 k, 2 v, 3 qx:
+   * out_scale (DEVICE pointer to 4 floats) holds input_scale[0] * weight_scale[0] of each projection, the two scalars
+   * bmm_fp8 hands to cuBLASLt (:450-457). The four projections must share one quantised x (equal input_scale). */
+  int32_t fp8;
+  const float* out_scale;
 } magi_qkv_proj_args;
 MAGI_API int magi_qkv_proj_norm_rope_fwd(const magi_qkv_proj_args* args, void* stream);
+
+/*
+ * Activation quantiser in front of the fp8 linears: `div_clamp_to` (dit_module.py:364-384), one memory-bound launch.
+ *   out[r, c] = float8_e4m3fn( bfloat16( clamp( float(x[r, c]) / scale[scale_len == 1 ? 0 : c], -448, 448 ) ) )
+ * with IEEE division and both roundings to nearest even, i.e. byte-identical to the reference's eager chain.
+ * x (rows, cols) bf16, out (rows, cols) bytes, scale fp32 on the device with scale_len == 1 (scalar) or == cols
+ * (per input channel: PerTensorQuantizedFp8Linear.input_scale is a vector of in_features, :443;
+ * PerChannelQuantizedFp8Linear.smooth_scale is (1, in_features), :474). cols a multiple of 16, row strides in
+ * elements (x: multiple of 8, out: multiple of 16), x / out / a per-channel scale 16-byte aligned.
+ */
+MAGI_API int magi_fp8_quantize(const void* x, int64_t x_row_stride, const float* scale, int32_t scale_len, void* out,
+                               int64_t out_row_stride, int64_t rows, int32_t cols, void* stream);
 
 /*
  * MLP activation between fc1 and fc2 (CustomMLP.forward, dit_module.py:541-549), one memory-bound launch:

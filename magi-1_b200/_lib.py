@@ -24,6 +24,7 @@ EXPORTS = (
     "magi_cso_unshuffle",
     "magi_bias_modulate_add",
     "magi_apply_rotary_emb",
+    "magi_fp8_quantize",
     "magi_mlp_activation",
     "magi_qkv_proj_norm_rope_fwd",
     "magi_last_error",
@@ -189,6 +190,8 @@ class MagiQkvProjArgs(C.Structure):
         ("peer_q_out", C.c_void_p * MAX_PEERS),
         ("peer_kv_out", C.c_void_p * MAX_PEERS),
         ("peer_row_offset", C.c_int64),
+        ("fp8", C.c_int32),
+        ("out_scale", C.c_void_p),
     ]
 
 
@@ -268,6 +271,9 @@ def lib() -> C.CDLL:
     L.magi_apply_rotary_emb.argtypes = [C.POINTER(MagiRotaryArgs), C.c_void_p]
     L.magi_qkv_proj_norm_rope_fwd.restype = C.c_int
     L.magi_qkv_proj_norm_rope_fwd.argtypes = [C.POINTER(MagiQkvProjArgs), C.c_void_p]
+    L.magi_fp8_quantize.restype = C.c_int
+    L.magi_fp8_quantize.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
+                                    C.c_int32, C.c_void_p]
     L.magi_mlp_activation.restype = C.c_int
     L.magi_mlp_activation.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                       C.c_void_p]

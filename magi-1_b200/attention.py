@@ -23,6 +23,7 @@ from . import context_parallel as cpm
 from . import functional as F
 from . import parallel_state as mpu
 from .common import EngineConfig, InferenceParams, ModelConfig, ModelMetaArgs, PackedCrossAttnParams, divide
+from .fp8_linear import PerChannelQuantizedFp8Linear, PerTensorQuantizedFp8Linear, uses_fp8
 
 
 class HeadLayerNorm(nn.Module):
@@ -38,28 +39,65 @@ class HeadLayerNorm(nn.Module):
 
 
 class CustomLayerNormLinear(nn.Module):
-    """dit_module.py:390-425 (bf16 linears; the fp8 variants are outside the hot path)."""
+    """dit_module.py:390-425: LayerNorm(hidden) and the q / qx / k / v linears - bf16 `nn.Linear`, or
+    `PerTensorQuantizedFp8Linear` on the layers `fp8_quant` covers (:407-410)."""
 
     def __init__(self, input_size, output_size_q, output_size_kv, layer_number, model_config, engine_config):
         super().__init__()
-        if engine_config.fp8_quant:
-            raise NotImplementedError("fp8_quant projections are outside the hot path of this build")
         self.layer_norm = nn.LayerNorm(input_size, eps=model_config.layernorm_epsilon, dtype=model_config.params_dtype)
         self.layer_number = layer_number
+        self.is_fp8 = uses_fp8(engine_config, model_config, layer_number)
         for name, size in {"q": output_size_q, "qx": output_size_q, "k": output_size_kv, "v": output_size_kv}.items():
-            setattr(self, name, nn.Linear(input_size, size, bias=False, dtype=model_config.params_dtype))
+            if self.is_fp8:
+                setattr(self, name, PerTensorQuantizedFp8Linear(input_size, size))
+            else:
+                setattr(self, name, nn.Linear(input_size, size, bias=False, dtype=model_config.params_dtype))
 
     def forward_ln(self, hidden_states):
         return self.layer_norm(hidden_states)
 
+    def _versions(self, names):
+        ps = [p for n in names for p in getattr(self, n).parameters()]
+        return tuple((p.data_ptr(), p._version) for p in ps)
+
     def stacked_weight(self, with_qx: bool) -> torch.Tensor:
         """[Wq; Wk; Wv (; Wqx)] for the fused projection GEMM, built once and rebuilt only if a weight changes."""
-        ws = [self.q.weight, self.k.weight, self.v.weight] + ([self.qx.weight] if with_qx else [])
-        key = tuple((w.data_ptr(), w._version) for w in ws)
+        names = ["q", "k", "v"] + (["qx"] if with_qx else [])
+        key = self._versions(names)
         cached = getattr(self, "_stacked", None)
         if cached is None or cached[0] != key:
-            cached = self._stacked = (key, F.stack_qkv_weights(*[w.detach() for w in ws]))
+            ws = [getattr(self, n).weight.detach() for n in names]
+            if self.is_fp8:
+                ws = [w[0] for w in ws]                       # (1, out, in) float8_e4m3fn, dit_module.py:441
+            cached = self._stacked = (key, F.stack_qkv_weights(*ws))
         return cached[1]
+
+    def fp8_fusable(self) -> bool:
+        """The fused fp8 GEMM quantises x ONCE, so the four linears must divide by the same `input_scale` vector -
+        which they do when calibrated on their common input, the LayerNorm output. Checked once per set of weights
+        (one host sync); otherwise every linear quantises its own copy and runs as a library GEMM."""
+        key = self._versions(["q", "k", "v", "qx"])
+        cached = getattr(self, "_fusable", None)
+        if cached is None or cached[0] != key:
+            ref = self.q.input_scale
+            same = all(torch.equal(getattr(self, n).input_scale, ref) for n in ("k", "v", "qx"))
+            scale = torch.stack([(getattr(self, n).input_scale[0] * getattr(self, n).weight_scale[0]).detach()
+                                 for n in ("q", "k", "v", "qx")]).float().contiguous()
+            cached = self._fusable = (key, bool(same), scale)
+        return cached[1]
+
+    def fused_operands(self, x2d: torch.Tensor, with_qx: bool):
+        """(x, stacked w, out_scale) for `F.qkv_proj_norm_rope`, or None when this layer cannot use the fused GEMM.
+        bf16 layers: x itself and the stacked bf16 weights. fp8 layers (PerTensorQuantizedFp8Linear.forward,
+        dit_module.py:446-457): x quantised once by `div_clamp_to`, the stacked e4m3 weights, and per projection the
+        product of the two scalars `bmm_fp8` applies."""
+        if x2d.dtype != torch.bfloat16:
+            return None
+        if not self.is_fp8:
+            return (x2d, self.stacked_weight(with_qx), None) if x2d.shape[-1] % 64 == 0 else None
+        if x2d.shape[-1] % 128 != 0 or not self.fp8_fusable():
+            return None
+        return self.q.quantize_input(x2d), self.stacked_weight(with_qx), self._fusable[2]
 
     def forward_q(self, x):
         return self.q(x)
@@ -210,8 +248,11 @@ class FullyParallelAttention(nn.Module):
                                                 self.kv_projection_size, layer_number, model_config, engine_config)
         self.linear_kv_xattn = nn.Linear(int(model_config.hidden_size * model_config.xattn_cond_hidden_ratio),
                                          2 * self.kv_projection_size, dtype=model_config.params_dtype, bias=False)
-        self.linear_proj = nn.Linear(2 * self.query_projection_size, model_config.hidden_size,
-                                     dtype=model_config.params_dtype, bias=False)
+        # dit_module.py:873-880: the out-projection is a PerChannelQuantizedFp8Linear on the layers fp8_quant covers
+        self.adapt_linear_quant = uses_fp8(engine_config, model_config, layer_number)
+        proj_cls = PerChannelQuantizedFp8Linear if self.adapt_linear_quant else nn.Linear
+        self.linear_proj = proj_cls(2 * self.query_projection_size, model_config.hidden_size,
+                                    dtype=model_config.params_dtype, bias=False)
         self.q_layernorm = HeadLayerNorm(model_config, hd)
         self.q_layernorm_xattn = HeadLayerNorm(model_config, hd)
         self.k_layernorm = HeadLayerNorm(model_config, hd)
@@ -552,23 +593,21 @@ class FullyParallelAttention(nn.Module):
             cache, start, app = self._cache_plan(inference_params, meta_args, rows, dt, dev)
             offload = self._offloaded(cache)
             xq_rows = None
-            if (getattr(self.engine_config, "fused_qkv_proj", False) and mixed_qqkv.shape[-1] % 64 == 0
-                    and dt == torch.bfloat16):
+            query = None
+            if getattr(self.engine_config, "fused_qkv_proj", False):
                 # projections + prologue as one GEMM (its epilogue is the prologue); with batch 1 the cross-attention
                 # query rides along as a fourth group of heads
                 with_qx = batch_size == 1 and (2 * Hq + 2 * Hkv) % 2 == 0
-                if with_qx or (Hq + 2 * Hkv) % 2 == 0:
+                ops = (self.linear_qkv.fused_operands(mixed_qqkv.reshape(rows, -1), with_qx)
+                       if with_qx or (Hq + 2 * Hkv) % 2 == 0 else None)
+                if ops is not None:
                     query, kv_new, qx = F.qkv_proj_norm_rope(
-                        mixed_qqkv.reshape(rows, -1), self.linear_qkv.stacked_weight(with_qx), Hq, Hkv,
+                        ops[0], ops[1], Hq, Hkv,
                         self._ln(self.q_layernorm), self._ln(self.k_layernorm), sin_emb, cos_emb,
                         ln_qx=self._ln(self.q_layernorm_xattn) if with_qx else None, batch=batch_size, eps=eps,
                         zero_centered_gamma=z, cache=cache if app > 0 and not offload else None,
-                        cache_row_offset=start, cache_rows=app)
+                        cache_row_offset=start, cache_rows=app, out_scale=ops[2])
                     xq_rows = [qx] if with_qx else None
-                else:
-                    query = None
-            else:
-                query = None
             x_kv = None
             if query is None:
                 xq, xk, xv = self._project(mixed_qqkv)
@@ -732,14 +771,17 @@ class FullyParallelAttention(nn.Module):
         row_bytes = hkv_loc * 2 * F.HEAD_DIM * 2
         kv_ptrs = [p_ + start * row_bytes for p_ in self._cache_peer_ptrs] if direct else ws.kv_ptrs
         lnx = self._ln(self.q_layernorm_xattn) + self._ln(self.k_layernorm_xattn)
-        if (getattr(self.engine_config, "fused_qkv_proj", False) and dt == torch.bfloat16
-                and mixed_qqkv.shape[-1] % 64 == 0 and all(t.dtype == torch.bfloat16 for t in lnx)):
+        ops = (self.linear_qkv.fused_operands(mixed_qqkv.reshape(sq, -1), True)
+               if getattr(self.engine_config, "fused_qkv_proj", False)
+               and all(t.dtype == torch.bfloat16 for t in lnx) else None)
+        if ops is not None:
             # projections + prologue + input all-to-all as ONE launch: the GEMM's epilogue normalises / rotates every
             # head and stores it into the owning rank's receive buffer while the main loop computes the next tile
             _, _, qx = F.qkv_proj_norm_rope(
-                mixed_qqkv.reshape(sq, -1), self.linear_qkv.stacked_weight(True), Hq, Hkv, self._ln(self.q_layernorm),
+                ops[0], ops[1], Hq, Hkv, self._ln(self.q_layernorm),
                 self._ln(self.k_layernorm), sin_emb, cos_emb, ln_qx=self._ln(self.q_layernorm_xattn), batch=1, eps=eps,
-                zero_centered_gamma=z, peer_q_out=ws.q_ptrs, peer_kv_out=kv_ptrs, peer_row_offset=row_off)
+                zero_centered_gamma=z, peer_q_out=ws.q_ptrs, peer_kv_out=kv_ptrs, peer_row_offset=row_off,
+                out_scale=ops[2])
             kvx = torch.nn.functional.linear(key_value_states, self.linear_kv_xattn.weight)
             cross = dict(text_kv=kvx.view(key_value_states.shape[0], Hkv, 2 * F.HEAD_DIM),
                          ln_tk=self._ln(self.k_layernorm_xattn))
@@ -804,14 +846,15 @@ class FullyParallelAttention(nn.Module):
         hq_loc, hkv_loc = divide(Hq, cp), (divide(Hkv, cp) if Hkv >= cp else 1)   # (also serves cp_ring_kv: no cache)
         ws = cpm.UlyssesPeerWorkspace.get(mpu.get_cp_group(), total * b, max(split) * b, hq_loc, hkv_loc, Hq, dev)
         _, bounds, head_off = cpm.fused_ulysses_plan(split, rank, Hq, cp)
-        if (getattr(self.engine_config, "fused_qkv_proj", False) and mixed_qqkv.dtype == torch.bfloat16
-                and mixed_qqkv.shape[-1] % 64 == 0 and (Hq + 2 * Hkv) % 2 == 0):
+        ops = (self.linear_qkv.fused_operands(mixed_qqkv.reshape(sq * b, -1), False)
+               if getattr(self.engine_config, "fused_qkv_proj", False) and (Hq + 2 * Hkv) % 2 == 0 else None)
+        if ops is not None:
             # same choice as the single-GPU forward makes for batch > 1: q / k / v through the fused projection GEMM (no
             # qx: its "(sq b) -> (b sq)" row order needs one strided view per batch row), here with peer routing
-            F.qkv_proj_norm_rope(mixed_qqkv.reshape(sq * b, -1), self.linear_qkv.stacked_weight(False), Hq, Hkv,
+            F.qkv_proj_norm_rope(ops[0], ops[1], Hq, Hkv,
                                  self._ln(self.q_layernorm), self._ln(self.k_layernorm), sin_emb, cos_emb, batch=b,
                                  eps=eps, zero_centered_gamma=z, peer_q_out=ws.q_ptrs, peer_kv_out=ws.kv_ptrs,
-                                 peer_row_offset=bounds[rank] * b)
+                                 peer_row_offset=bounds[rank] * b, out_scale=ops[2])
         else:
             xq, xk, xv = self._project(mixed_qqkv)
             F.qk_norm_rope(xq, xk, xv, Hq, Hkv, self._ln(self.q_layernorm), self._ln(self.k_layernorm), sin_emb,

@@ -14,6 +14,7 @@
 #include "rope.cuh"
 #include "activation.cuh"
 #include "qkv_gemm.cuh"
+#include "fp8_quant.cuh"
 
 namespace {
 
@@ -547,16 +548,20 @@ int magi_bias_modulate_add(const MagiGatingArgs* a, void* stream_) {
 namespace {
 // (rows, cols) bf16 row-major matrix -> 2-D tensor map {cols, rows}, box {64, 128}, 128B swizzle (rows past the end are
 // zero-filled by the TMA unit)
-int make_matrix_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t row_stride, const char* what) {
+// 2-D map of a row-major GEMM operand, box = 128 rows x one 128-byte swizzle row (64 bf16 or 128 e4m3 bytes)
+int make_matrix_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t row_stride, const char* what,
+                    bool fp8 = false) {
   EncodeTiledFn enc = get_encode_fn();
   MAGI_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
-  MAGI_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && row_stride % 8 == 0 && row_stride >= cols,
-             "%s: pointer must be 16-byte aligned and the row stride a multiple of 8 elements", what);
+  const int esize = fp8 ? 1 : 2;
+  MAGI_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (row_stride * esize) % 16 == 0 && row_stride >= cols,
+             "%s: pointer must be 16-byte aligned and the row stride a multiple of 16 bytes", what);
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)(row_stride * 2)};
-  cuuint32_t box[2] = {64, 128};
+  cuuint64_t strides[1] = {(cuuint64_t)(row_stride * esize)};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esize), 128};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(m, fp8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MAGI_CHECK(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled failed (CUresult %d)", what, (int)r);
@@ -568,7 +573,11 @@ int magi_qkv_proj_norm_rope_fwd(const magi_qkv_proj_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MAGI_CHECK(a != nullptr, "args is NULL");
   MAGI_CHECK(a->rows >= 0 && a->rows < (1ll << 31), "rows out of range");
-  MAGI_CHECK(a->hidden > 0 && a->hidden % 64 == 0, "hidden must be a positive multiple of 64");
+  const bool fp8 = a->fp8 != 0;
+  MAGI_CHECK(a->hidden > 0 && a->hidden % (fp8 ? 128 : 64) == 0,
+             "hidden must be a positive multiple of 64 (bf16) / 128 (fp8)");
+  MAGI_CHECK(!fp8 || (a->out_scale != nullptr && (reinterpret_cast<uintptr_t>(a->out_scale) & 3) == 0),
+             "fp8 needs out_scale (device pointer to 4 floats)");
   MAGI_CHECK(a->num_heads_q > 0 && a->num_heads_kv > 0, "num_heads_q / num_heads_kv must be positive");
   MAGI_CHECK(a->num_heads_qx == 0 || a->num_heads_qx == a->num_heads_q, "num_heads_qx must be 0 or num_heads_q");
   const int heads_total = a->num_heads_q + 2 * a->num_heads_kv + a->num_heads_qx;
@@ -603,8 +612,8 @@ int magi_qkv_proj_norm_rope_fwd(const magi_qkv_proj_args* a, void* stream_) {
   if (a->cache)
     MAGI_CHECK(a->cache_rows >= 0 && a->cache_rows <= a->rows && a->cache_row_offset >= 0, "bad cache arguments");
   CUtensorMap tm_x, tm_w;
-  if (int rc = make_matrix_map(&tm_x, a->x, a->rows, a->hidden, a->x_row_stride, "x")) return rc;
-  if (int rc = make_matrix_map(&tm_w, a->w, (int64_t)heads_total * 128, a->hidden, a->w_row_stride, "w")) return rc;
+  if (int rc = make_matrix_map(&tm_x, a->x, a->rows, a->hidden, a->x_row_stride, "x", fp8)) return rc;
+  if (int rc = make_matrix_map(&tm_w, a->w, (int64_t)heads_total * 128, a->hidden, a->w_row_stride, "w", fp8)) return rc;
   magi::QkvGemmParams p;
   p.rows = a->rows; p.hidden = a->hidden; p.Hq = a->num_heads_q; p.Hkv = a->num_heads_kv; p.heads_total = heads_total;
   p.batch = a->batch;
@@ -621,6 +630,8 @@ int magi_qkv_proj_norm_rope_fwd(const magi_qkv_proj_args* a, void* stream_) {
   p.hq_loc = cp > 0 ? a->num_heads_q / cp : a->num_heads_q;
   p.hkv_loc = cp > 0 ? (a->num_heads_kv >= cp ? a->num_heads_kv / cp : 1) : a->num_heads_kv;
   p.peer_row_offset = a->peer_row_offset;
+  p.fp8 = fp8 ? 1 : 0;
+  p.out_scale = fp8 ? a->out_scale : nullptr;
   uintptr_t bits = reinterpret_cast<uintptr_t>(a->qx_out) | reinterpret_cast<uintptr_t>(a->cache);
   for (int i = 0; i < 8; ++i) {
     p.peer_q[i] = i < cp ? a->peer_q_out[i] : nullptr;
@@ -635,6 +646,25 @@ int magi_qkv_proj_norm_rope_fwd(const magi_qkv_proj_args* a, void* stream_) {
   int sms = a->num_sms;
   if (sms <= 0) { if (int rc = device_sm_count(&sms)) return rc; }
   MAGI_CUDA(magi::qkv_gemm_launch(tm_x, tm_w, p, sms, stream));
+  g_launches++;
+  return 0;
+}
+
+int magi_fp8_quantize(const void* x, int64_t x_row_stride, const float* scale, int32_t scale_len, void* out,
+                      int64_t out_row_stride, int64_t rows, int32_t cols, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MAGI_CHECK(rows >= 0 && cols > 0 && cols % 16 == 0, "rows must be >= 0 and cols a positive multiple of 16");
+  MAGI_CHECK(scale_len == 1 || scale_len == cols, "scale_len must be 1 or cols");
+  if (rows == 0) return 0;
+  MAGI_CHECK(x && out && scale, "NULL pointer");
+  MAGI_CHECK(x_row_stride % 8 == 0 && out_row_stride % 16 == 0 && x_row_stride >= cols && out_row_stride >= cols,
+             "row strides must cover a row and keep 16-byte alignment (x: multiple of 8, out: multiple of 16)");
+  MAGI_CHECK(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(scale) & (scale_len == 1 ? 3 : 15)) == 0,
+             "x / out (and a per-channel scale) must be 16-byte aligned");
+  int sms = 0;
+  if (int rc = device_sm_count(&sms)) return rc;
+  MAGI_CUDA(magi::fp8_quant_launch(x, x_row_stride, scale, scale_len, out, out_row_stride, rows, cols, sms, stream));
   g_launches++;
   return 0;
 }

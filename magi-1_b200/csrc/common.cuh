@@ -305,6 +305,18 @@ __device__ __forceinline__ void mma_ss_pair(uint32_t d_tmem, uint64_t a_desc, ui
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same with 8-bit floating point operands (formats in the instruction descriptor), K = 32 per instruction
+__device__ __forceinline__ void mma_ss_pair_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // D[tmem] (+)= A[tmem, each CTA its own 128 rows] * B[smem, N/2 columns per CTA]
 __device__ __forceinline__ void mma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -349,6 +361,14 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
          | (1u << 10)                   // B format: BF16
          | (uint32_t(a_mn_major) << 15) // A major
          | (uint32_t(b_mn_major) << 16) // B major
+         | (uint32_t(N >> 3) << 17)     // N / 8
+         | (uint32_t(M >> 4) << 24);    // M / 16
+}
+
+// Instruction descriptor for kind::f8f6f4, e4m3 x e4m3 -> fp32, both operands K-major (format code 0 = E4M3 in bits
+// [7, 10) and [10, 13); K = 32 per instruction).
+__host__ __device__ constexpr uint32_t make_idesc_e4m3(int M, int N) {
+  return (1u << 4)                      // D format: F32
          | (uint32_t(N >> 3) << 17)     // N / 8
          | (uint32_t(M >> 4) << 24);    // M / 16
 }

@@ -17,6 +17,13 @@
 //   warp 0      TMA producer (both CTAs)
 //   warp 1      MMA issuer (leader CTA) + TMEM allocator (both)
 //   warps 2-5   epilogue: TMEM lane quarter = warp % 4, one thread per row, two heads per tile
+//
+// fp8_quant (PerTensorQuantizedFp8Linear, dit_module.py:431-457, the q / qx / k / v of every layer but the first and
+// the last in the *_distill_quant configs): the same kernel instantiated with kFp8 = true. X and W are e4m3 bytes, a k
+// block is 128 elements (still one 128-byte swizzle row, so staging, descriptors and the pipeline are unchanged), the
+// instruction is tcgen05.mma.kind::f8f6f4 (K = 32 per instruction, twice the bf16 rate), and the epilogue multiplies
+// the fp32 accumulator by input_scale * weight_scale of the head's projection (what bmm_fp8 / cuBLASLt does with its
+// A / B scale pointers) before the bf16 rounding.
 #include <math.h>
 #include <stdio.h>
 
@@ -29,9 +36,9 @@ namespace {
 
 constexpr int kBM = 128;                 // rows of X per CTA (256 per pair)
 constexpr int kBN = 256;                 // columns of Y per tile = 2 heads; each CTA stages 128 rows of W
-constexpr int kBK = 64;                  // k block: 64 bf16 = one 128-byte swizzle row
-constexpr int kABytes = kBM * kBK * 2;   // 16 KB
-constexpr int kBBytes = 128 * kBK * 2;   // 16 KB
+constexpr int kBKBytes = 128;            // k block: one 128-byte swizzle row = 64 bf16 or 128 e4m3
+constexpr int kABytes = kBM * kBKBytes;  // 16 KB
+constexpr int kBBytes = 128 * kBKBytes;  // 16 KB
 constexpr int kStageBytes = kABytes + kBBytes;
 #ifndef MAGI_GEMM_STAGES
 #define MAGI_GEMM_STAGES 6
@@ -39,7 +46,8 @@ constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kStages = MAGI_GEMM_STAGES;
 constexpr int kThreads = 192;
 constexpr int kEpiWarps = 4;
-constexpr uint32_t kIdesc = make_idesc_bf16(256, 256, 0, 0);
+constexpr uint32_t kIdescBf16 = make_idesc_bf16(256, 256, 0, 0);
+constexpr uint32_t kIdescE4m3 = make_idesc_e4m3(256, 256);
 constexpr int kSmemBytes = kStages * kStageBytes + 1024;
 
 struct GemmBarriers {
@@ -79,6 +87,7 @@ __device__ __forceinline__ float bf16_round_f(float x) {
 
 }  // namespace
 
+template <bool kFp8>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 qkv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                 const QkvGemmParams p) {
@@ -94,6 +103,7 @@ qkv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   const int n_tiles = p.heads_total / 2;                           // tiles along N (2 heads each)
   const int m_tiles = static_cast<int>((p.rows + 2 * kBM - 1) / (2 * kBM));
   const int total_tiles = m_tiles * n_tiles;
+  constexpr int kBK = kFp8 ? kBKBytes : kBKBytes / 2;             // elements per k block
   const int k_blocks = p.hidden / kBK;
 
   if (threadIdx.x == 0) {
@@ -179,10 +189,16 @@ qkv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           if (elect_one()) {
             const uint64_t ad = make_smem_desc_sw128(base + stage * kStageBytes, 16, 1024);
             const uint64_t bd = make_smem_desc_sw128(base + stage * kStageBytes + kABytes, 16, 1024);
+            // four instructions per k block, each 32 bytes of K further into the swizzle row (K = 16 bf16 / 32 e4m3)
 #pragma unroll
-            for (int ks = 0; ks < kBK / 16; ++ks)
-              mma_ss_pair(tb + b * 256, ad + static_cast<uint64_t>(ks * 2), bd + static_cast<uint64_t>(ks * 2), kIdesc,
-                          (kb > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < kBKBytes / 32; ++ks) {
+              if constexpr (kFp8)
+                mma_ss_pair_f8(tb + b * 256, ad + static_cast<uint64_t>(ks * 2), bd + static_cast<uint64_t>(ks * 2),
+                               kIdescE4m3, (kb > 0 || ks > 0) ? 1u : 0u);
+              else
+                mma_ss_pair(tb + b * 256, ad + static_cast<uint64_t>(ks * 2), bd + static_cast<uint64_t>(ks * 2),
+                            kIdescBf16, (kb > 0 || ks > 0) ? 1u : 0u);
+            }
             tc_commit_pair(&bar.empty[stage]);
             if (kb == k_blocks - 1) tc_commit_pair(&bar.acc_full[b]);
           }
@@ -226,8 +242,14 @@ qkv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         else if (head < Hq + 2 * Hkv) { type = 2; h = head - Hq - Hkv; }
         else { type = 3; h = head - Hq - 2 * Hkv; }
         float v[128];
+        if constexpr (kFp8) {
+          const float sc = __ldg(p.out_scale + type);   // input_scale * weight_scale of this head's projection
 #pragma unroll
-        for (int i = 0; i < 128; ++i) v[i] = bf16_round_f(__uint_as_float(u[i]));   // the Linear's bf16 output
+          for (int i = 0; i < 128; ++i) v[i] = bf16_round_f(__uint_as_float(u[i]) * sc);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 128; ++i) v[i] = bf16_round_f(__uint_as_float(u[i]));   // the Linear's bf16 output
+        }
         if (type != 2) {
           const int set = type == 3 ? 2 : type;
           // fp32 LayerNorm over the head (two-pass, biased variance)
@@ -336,13 +358,18 @@ cudaError_t qkv_gemm_launch(const CUtensorMap& tm_x, const CUtensorMap& tm_w, co
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev >= 64 || !attr_set[dev]) {
-    e = cudaFuncSetAttribute(qkv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    e = cudaFuncSetAttribute(qkv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(qkv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
     if (dev < 64) attr_set[dev] = true;
   }
   num_ctas &= ~1;
   if (num_ctas < 2) num_ctas = 2;
-  qkv_gemm_kernel<<<num_ctas, kThreads, kSmemBytes, stream>>>(tm_x, tm_w, p);
+  if (p.fp8)
+    qkv_gemm_kernel<true><<<num_ctas, kThreads, kSmemBytes, stream>>>(tm_x, tm_w, p);
+  else
+    qkv_gemm_kernel<false><<<num_ctas, kThreads, kSmemBytes, stream>>>(tm_x, tm_w, p);
   return cudaGetLastError();
 }
 

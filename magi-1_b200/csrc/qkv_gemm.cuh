@@ -29,6 +29,10 @@ struct QkvGemmParams {
   void* peer_q[8]; void* peer_kv[8];
   int64_t peer_row_offset;
   int align32;                   // every destination row is 32-byte aligned: 32-byte stores
+  // fp8_quant: X and W hold e4m3 bytes, hidden is a multiple of 128, and out_scale (device, 4 floats: q, k, v, qx)
+  // holds input_scale * weight_scale of each projection
+  int fp8;
+  const float* out_scale;
 };
 
 cudaError_t qkv_gemm_launch(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const QkvGemmParams& p, int num_ctas,

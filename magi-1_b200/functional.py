@@ -784,6 +784,7 @@ def qkv_proj_norm_rope(
     peer_q_out: Optional[Sequence[int]] = None,
     peer_kv_out: Optional[Sequence[int]] = None,
     peer_row_offset: int = 0,
+    out_scale: Optional[torch.Tensor] = None,
 ):
     """The q / k / v (and, with ln_qx, the cross-attention qx) projections of CustomLayerNormLinear
     (dit_module.py:405-425) and the QK-LayerNorm + RoPE prologue (get_q / get_kv, :953-996; q half of get_xqkv,
@@ -795,16 +796,27 @@ def qkv_proj_norm_rope(
 
     peer_q_out / peer_kv_out (cp device pointers each) + peer_row_offset: the Ulysses input all-to-all fused into the
     GEMM's epilogue, with the routing of `qk_norm_rope`'s peer arguments (head slice c -> rank c's receive buffer, at
-    row peer_row_offset + r, KV-head replication when cp > Hkv); returns (None, None, qx)."""
-    if not x.is_cuda or x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or x.dim() != 2 or w.dim() != 2:
-        raise ValueError("x and w must be 2-D bfloat16 CUDA tensors (this package has no CPU path)")
+    row peer_row_offset + r, KV-head replication when cp > Hkv); returns (None, None, qx).
+
+    out_scale (4 fp32 on the device: input_scale * weight_scale of q, k, v, qx) selects the fp8 instantiation
+    (PerTensorQuantizedFp8Linear, dit_module.py:431-457): x is then the e4m3 output of `fp8_quantize` and w the stacked
+    e4m3 weights (dtype float8_e4m3fn or uint8), hidden a multiple of 128."""
+    fp8 = out_scale is not None
+    ok_dt = (torch.float8_e4m3fn, torch.uint8) if fp8 else (torch.bfloat16,)
+    if not x.is_cuda or x.dtype not in ok_dt or w.dtype not in ok_dt or x.dim() != 2 or w.dim() != 2:
+        raise ValueError("x and w must be 2-D bfloat16 (or, with out_scale, float8_e4m3fn) CUDA tensors "
+                         "(this package has no CPU path)")
+    if fp8 and (out_scale.dtype != torch.float32 or out_scale.numel() != 4 or not out_scale.is_cuda
+                or not out_scale.is_contiguous()):
+        raise ValueError("out_scale must be 4 contiguous fp32 values on the device")
     rows, hidden = x.shape
     with_qx = ln_qx is not None
     heads_total = num_heads_q + 2 * num_heads_kv + (num_heads_q if with_qx else 0)
     if w.shape != (heads_total * HEAD_DIM, hidden) or x.stride(1) != 1 or w.stride(1) != 1:
         raise ValueError(f"w must be ({heads_total * HEAD_DIM}, {hidden}) and both operands contiguous in the last dim")
-    if hidden % 64 or heads_total % 2:
-        raise ValueError("hidden must be a multiple of 64 and the stacked weight must hold an even number of heads")
+    if hidden % (128 if fp8 else 64) or heads_total % 2:
+        raise ValueError("hidden must be a multiple of 64 (fp8: 128) and the stacked weight must hold an even number "
+                         "of heads")
     ln_dtype = 1 if ln_q[0].dtype == torch.bfloat16 else 0
     for t in (*ln_q, *ln_k):
         if t.dtype != ln_q[0].dtype or t.numel() != HEAD_DIM or not t.is_cuda:
@@ -849,11 +861,59 @@ def qkv_proj_norm_rope(
         a.cache, a.cache_token_stride, a.cache_head_stride = cache.data_ptr(), cache.stride(0), cache.stride(1)
         a.cache_row_offset, a.cache_rows = cache_row_offset, cache_rows
     a.num_sms = num_sms
+    if fp8:
+        a.fp8, a.out_scale = 1, out_scale.data_ptr()
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().magi_qkv_proj_norm_rope_fwd(C.byref(a), _stream()), "magi_qkv_proj_norm_rope_fwd")
     return q, kv, qx
 
 
 def stack_qkv_weights(wq: torch.Tensor, wk: torch.Tensor, wv: torch.Tensor, wqx: Optional[torch.Tensor] = None):
-    """[Wq; Wk; Wv (; Wqx)]: the row order qkv_proj_norm_rope expects (nn.Linear weights, (out, in))."""
-    return torch.cat([t for t in (wq, wk, wv, wqx) if t is not None], dim=0).contiguous()
+    """[Wq; Wk; Wv (; Wqx)]: the row order qkv_proj_norm_rope expects (nn.Linear weights, (out, in)). float8 weights
+    are stacked as bytes."""
+    ws = [t for t in (wq, wk, wv, wqx) if t is not None]
+    if ws[0].dtype == torch.float8_e4m3fn:
+        ws = [t.view(torch.uint8) for t in ws]
+    return torch.cat(ws, dim=0).contiguous()
+
+
+FP8_MAX = 448.0   # torch.finfo(torch.float8_e4m3fn).max
+
+
+def fp8_quantize(x: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    """`div_clamp_to` (dit_module.py:364-384) as one launch of magi_fp8_quantize:
+    float8_e4m3fn(bfloat16(clamp(x.float() / scale.float(), -448, 448))), same shape as x. `scale` holds one value
+    or one per element of the last dimension (PerTensorQuantizedFp8Linear.input_scale: (in_features,),
+    PerChannelQuantizedFp8Linear.smooth_scale: (1, in_features)). Byte-identical to the reference's eager chain."""
+    if not x.is_cuda or x.dtype != torch.bfloat16:
+        raise ValueError("x must be a bfloat16 CUDA tensor (this package has no CPU path)")
+    cols = x.shape[-1]
+    if scale.numel() not in (1, cols) or cols % 16:
+        raise ValueError("scale must hold 1 or x.shape[-1] values and x.shape[-1] must be a multiple of 16")
+    x2 = x.reshape(-1, cols)
+    if x2.stride(1) != 1 or x2.stride(0) % 8:
+        x2 = x2.contiguous()
+    sc = scale.detach().reshape(-1)
+    if sc.dtype != torch.float32 or not sc.is_contiguous() or sc.device != x.device:
+        sc = sc.to(device=x.device, dtype=torch.float32).contiguous()
+    out = torch.empty(x.shape, dtype=torch.float8_e4m3fn, device=x.device)
+    rows = x2.shape[0]
+    if rows > 0:
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().magi_fp8_quantize(x2.data_ptr(), x2.stride(0), sc.data_ptr(), sc.numel(),
+                                                    out.data_ptr(), cols, rows, cols, _stream()), "magi_fp8_quantize")
+    return out
+
+
+def fp8_scaled_linear(xq: torch.Tensor, weight: torch.Tensor, input_scale: torch.Tensor, weight_scale: torch.Tensor,
+                      out_dtype=torch.bfloat16) -> torch.Tensor:
+    """The GEMM of the reference's fp8 linears: `flashinfer.bmm_fp8(xq (1, m, k), weight.transpose(-2, -1), input_scale,
+    weight_scale, dtype)` (dit_module.py:450-457, 482-488) = the cuBLASLt fp8 matmul with per-tensor A / B scale
+    pointers, out = dtype((xq @ weight^T) * input_scale[0] * weight_scale[0]). A library GEMM in the reference and a
+    library GEMM here (torch._scaled_mm -> the same cuBLASLt entry); cuBLASLt reads ONE float behind each scale
+    pointer, which is why a vector input_scale contributes its first element.
+    xq (..., k) float8_e4m3fn, weight (n, k) float8_e4m3fn."""
+    k = xq.shape[-1]
+    y = torch._scaled_mm(xq.reshape(-1, k), weight.t(), scale_a=input_scale.detach().reshape(-1)[0],
+                         scale_b=weight_scale.detach().reshape(-1)[0], out_dtype=out_dtype)
+    return y.view(*xq.shape[:-1], weight.shape[0])

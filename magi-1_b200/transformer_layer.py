@@ -19,6 +19,7 @@ import torch.nn as nn
 from . import functional as F
 from .attention import FullyParallelAttention, HeadLayerNorm
 from .common import EngineConfig, InferenceParams, ModelConfig, ModelMetaArgs
+from .fp8_linear import PerChannelQuantizedFp8Linear, PerTensorQuantizedFp8Linear, uses_fp8
 
 
 class AdaModulateLayer(nn.Module):
@@ -44,18 +45,20 @@ def softcap(x: torch.Tensor, cap: float):
 
 
 class CustomMLP(nn.Module):
-    """dit_module.py:493-551 (bf16 linears; the fp8 variants are outside this build): LayerNorm -> fc1 -> GELU, or
-    SwiGLU (`flashinfer.activation.silu_and_mul`: silu(x[..., :d]) * x[..., d:]) when gated_linear_unit -> fc2."""
+    """dit_module.py:493-551: LayerNorm -> fc1 -> GELU, or SwiGLU (`flashinfer.activation.silu_and_mul`:
+    silu(x[..., :d]) * x[..., d:]) when gated_linear_unit -> fc2. On the layers `fp8_quant` covers fc1 is a
+    PerTensorQuantizedFp8Linear and fc2 a PerChannelQuantizedFp8Linear (:520-540)."""
 
     def __init__(self, model_config: ModelConfig, engine_config: EngineConfig, layer_number: int):
         super().__init__()
-        if engine_config.fp8_quant:
-            raise NotImplementedError("fp8_quant linears are outside the hot path of this build")
         self.model_config = model_config
         dt, h, f = model_config.params_dtype, model_config.hidden_size, model_config.ffn_hidden_size
         self.layer_norm = nn.LayerNorm(h, eps=model_config.layernorm_epsilon, dtype=dt)
-        self.linear_fc1 = nn.Linear(h, 2 * f if model_config.gated_linear_unit else f, bias=False, dtype=dt)
-        self.linear_fc2 = nn.Linear(f, h, bias=False, dtype=dt)
+        fp8 = uses_fp8(engine_config, model_config, layer_number)
+        fc1_cls = PerTensorQuantizedFp8Linear if fp8 else nn.Linear
+        fc2_cls = PerChannelQuantizedFp8Linear if fp8 else nn.Linear
+        self.linear_fc1 = fc1_cls(h, 2 * f if model_config.gated_linear_unit else f, bias=False, dtype=dt)
+        self.linear_fc2 = fc2_cls(f, h, bias=False, dtype=dt)
 
     def forward(self, hidden_states):
         x = self.linear_fc1(self.layer_norm(hidden_states))
@@ -99,9 +102,10 @@ class TransformerLayer(nn.Module):
         return self.attn_post_process_from_proj_input(proj_in, residual, condition, condition_map)
 
     def attn_post_process_from_proj_input(self, proj_in, residual, condition, condition_map):
-        # attn_linear_proj, dit_module.py:1332-1346. The reference wraps the projection in
+        # attn_linear_proj, dit_module.py:1332-1346. The reference wraps the bf16 projection in
         # torch.autocast("cuda", dtype=torch.float32), which CUDA autocast does not support (it warns and disables
-        # itself), so the projection runs in the parameters' dtype, as here.
+        # itself), so the projection runs in the parameters' dtype, as here; the fp8 out-projection
+        # (adapt_linear_quant, :1339-1340) is called as it is.
         attn_out = self.self_attention.linear_proj(proj_in)
         return self.gating_and_mlp(attn_out, residual, condition, condition_map)
 

@@ -12,6 +12,8 @@ without a GPU:
   * flash_attn.layers.rotary.apply_rotary_emb (Triton)  -> flash-attn's own `apply_rotary_emb_torch`
   * flash_attn_func / flash_attn_varlen_func (CUDA)     -> fp32 softmax(QK^T/sqrt(d))V with GQA, output cast to bf16
   * torch.cuda.current_device / Tensor.cuda / get_device_capability -> CPU stand-ins
+  * flashinfer.gemm.bmm_fp8 (cuBLASLt fp8 matmul, fp8_quant mode only) -> (A.float() @ B.float()) * (a_scale[0] *
+    b_scale[0]) cast to the output dtype: fp32 accumulation, ONE float read behind each scale pointer
   * range_mod_kernel_fwd (the reference's own Triton kernel, dit_module.py:201-241) -> the same row-gather multiply
     in torch; its host wrapper range_mod_triton and bias_modulate_add run unmodified (in the whole-layer scenario the
     wrapper's `assert x.is_cuda` forces restating the wrapper too: range_mod_cpu)
@@ -568,6 +570,126 @@ def gen_two_blocks():
     print("two-block fixture written")
 
 
+# ------------------------------------------------------------------ scenario: fp8_quant linears
+def bmm_fp8_cpu(A, B, A_scale, B_scale, dtype, out=None, backend="cublas"):
+    """flashinfer.gemm.bmm_fp8 -> cuBLASLt: D = dtype((A @ B) * a_scale * b_scale), per-tensor scalars."""
+    acc = torch.matmul(A.float(), B.float())
+    return (acc * (A_scale.flatten()[0].float() * B_scale.flatten()[0].float())).to(dtype)
+
+
+def init_fp8_linear(lin, g, input_amax=4.0, vector_jitter=0.0):
+    """Fill a reference fp8 linear the way a calibrated checkpoint would: e4m3 weights with a per-tensor weight_scale,
+    input_scale = amax / 448 (a vector of equal values for the per-tensor class, dit_module.py:443), smooth_scale
+    around 1. vector_jitter > 0 makes the per-channel divisors differ (they are divisors in div_clamp_to, :447)."""
+    out_f, in_f = lin.weight.shape[1:]
+    w = torch.randn(out_f, in_f, generator=g) / math.sqrt(in_f)
+    ws = w.abs().max() / 448.0
+    with torch.no_grad():
+        lin.weight.copy_((w / ws).to(torch.float8_e4m3fn)[None])
+        lin.weight_scale.fill_(float(ws))
+        base = input_amax / 448.0
+        if hasattr(lin, "smooth_scale"):
+            lin.smooth_scale.copy_(1.0 + 0.25 * torch.rand(1, in_f, generator=g))
+            lin.input_scale.fill_(base)
+        else:
+            lin.input_scale.copy_(base * (1.0 + vector_jitter * torch.rand(in_f, generator=g)))
+
+
+def gen_fp8():
+    dm = install_patches()
+    dm.bmm_fp8 = bmm_fp8_cpu
+    dm.range_mod_triton = range_mod_cpu
+    init_dist(0, 1, 29591)
+    from inference.common import InferenceParams
+    from inference.common.config import EngineConfig
+    g = torch.Generator().manual_seed(2024)
+    fx = {}
+    # (1) div_clamp_to on its own: per-channel and scalar divisors, values beyond the clamp, zeros, subnormal results
+    x = (torch.randn(96, 256, generator=g) * 3.0)
+    x[0, :8] = torch.tensor([0.0, -0.0, 1e-4, -1e-4, 500.0, -500.0, 3.9, 448.0])
+    x = x.to(torch.bfloat16)
+    sv = (4.0 / 448.0) * (1.0 + torch.rand(256, generator=g))
+    ss = torch.tensor([0.011])
+    fx.update({"dct.x": pk(x), "dct.scale_vec": sv.numpy(), "dct.scale_scalar": ss.numpy(),
+               "dct.out_vec": dm.div_clamp_to(x, sv).view(torch.uint8).numpy(),
+               "dct.out_scalar": dm.div_clamp_to(x, ss).view(torch.uint8).numpy()})
+    # (2) the two linear classes on their own (per-tensor one with unequal per-channel divisors)
+    pt = dm.PerTensorQuantizedFp8Linear(256, 384)
+    pc = dm.PerChannelQuantizedFp8Linear(256, 128)
+    init_fp8_linear(pt, g, vector_jitter=0.5)
+    init_fp8_linear(pc, g)
+    xin = torch.randn(40, 2, 256, generator=g).to(torch.bfloat16)
+    with torch.no_grad():
+        fx.update({"lin.x": pk(xin), "lin.pt.out": pk(pt(xin)), "lin.pc.out": pk(pc(xin))})
+    for n_, m_ in (("pt", pt), ("pc", pc)):
+        for k_, v_ in m_.state_dict().items():
+            fx[f"lin.{n_}.{k_}"] = v_.view(torch.uint8).numpy() if v_.dtype == torch.float8_e4m3fn else pk(v_)
+    # (3) a whole fp8 TransformerLayer (layer 1 of 4: every linear the mode covers is fp8, dit_module.py:407, 522, 535,
+    # 875) through a two-step KV-cache sequence; `shared` = q / k / v / qx calibrated on their common input (equal
+    # input_scale vectors), `split` = unequal ones
+    mc, _ = make_configs(hidden=256, hq=4, hkv=2)
+    ec = EngineConfig(cp_size=1, cp_strategy="none", ulysses_overlap_degree=1, fp8_quant=True)
+    H = W = 4
+    frames = 3
+    clip = frames * H * W
+    hidden = mc.hidden_size
+    for variant in ("shared", "split"):
+        torch.manual_seed(99)
+        layer = dm.TransformerLayer(mc, ec, layer_number=1)
+        with torch.no_grad():
+            for name, p_ in layer.named_parameters():
+                if p_.dtype == torch.float8_e4m3fn or name.endswith("_scale"):
+                    continue
+                if "layernorm" in name or "post_norm" in name:
+                    p_.copy_((torch.randn(p_.shape, generator=g) * 0.2).to(p_.dtype))
+                elif name.endswith("layer_norm.weight"):
+                    p_.copy_((1.0 + torch.randn(p_.shape, generator=g) * 0.02).to(p_.dtype))
+                elif name.endswith("bias"):
+                    p_.copy_((torch.randn(p_.shape, generator=g) * 0.02).to(p_.dtype))
+                else:
+                    p_.copy_((torch.randn(p_.shape, generator=g) * (1.0 / math.sqrt(p_.shape[-1]))).to(p_.dtype))
+        for name, sub in layer.named_modules():
+            if isinstance(sub, (dm.PerTensorQuantizedFp8Linear, dm.PerChannelQuantizedFp8Linear)):
+                amax = {"shared": 4.0, "split": 4.0 + 0.5 * len(name)}[variant] if "linear_qkv" in name else 6.0
+                init_fp8_linear(sub, g, input_amax=amax)
+        for name, sub in layer.named_modules():       # dit_model.py:621-638
+            if "_xattn" in name:
+                continue
+            if any(k in name for k in ("q_layernorm", "k_layernorm", "self_attn_post_norm", "mlp_post_norm")):
+                sub.float()
+        layer.eval()
+        pre = variant + "."
+        for k_, v_ in layer.state_dict().items():
+            fx[pre + "w." + k_] = v_.view(torch.uint8).numpy() if v_.dtype == torch.float8_e4m3fn else pk(v_)
+        inf = InferenceParams(max_batch_size=1, max_sequence_length=4 * clip)
+        inf.key_value_memory_dict[1] = torch.zeros(4 * clip, 2, 256, dtype=torch.bfloat16)
+        for tag, sp, dn, k_chunks, y_index, update in (("A", 0, 2, [(0, 1), (0, 2)], [50, 41], True),
+                                                       ("B", 1, 2, [(0, 2), (1, 3)], [33, 90], True)):
+            S = dn * clip
+            hs = torch.randn(S, 1, hidden, generator=g).to(torch.bfloat16)
+            kvs = torch.randn(int(sum(y_index)), hidden, generator=g).to(torch.bfloat16)
+            cond = torch.randn(1, dn, int(hidden * mc.cond_hidden_ratio), generator=g).to(torch.bfloat16)
+            cmap = torch.arange(dn).repeat_interleave(clip).reshape(1, -1).transpose(0, 1).contiguous()
+            rope = rope_for(dm, (sp + dn) * frames, H, W, dn * frames)
+            m = meta(dm, clip, sp, dn, 1, [[s_ * clip, e_ * clip] for s_, e_ in k_chunks], y_index)
+            inf.update_kv_cache = update
+            with torch.no_grad():
+                core, xattn = layer.self_attention(hs, kvs, inf, rope, m)
+                # the attention call above already appended this step's K/V: the layer call repeats the same write
+                out = layer(hs, cond, cmap, kvs, rope, inf, m)
+            t = pre + tag
+            fx.update({f"{t}.hidden_states": pk(hs), f"{t}.key_value_states": pk(kvs), f"{t}.condition": pk(cond),
+                       f"{t}.condition_map": cmap.numpy(), f"{t}.rope": pk(rope),
+                       f"{t}.k_range": np.array([[s_ * clip, e_ * clip] for s_, e_ in k_chunks], dtype=np.int32),
+                       f"{t}.y_index": np.array(y_index), f"{t}.meta": np.array([sp, dn, int(update)]),
+                       f"{t}.core": pk(core), f"{t}.xattn": pk(xattn), f"{t}.out": pk(out)})
+        fx[pre + "cache"] = pk(inf.key_value_memory_dict[1][:3 * clip])
+    fx["clip"] = np.array(clip)
+    fx["heads"] = np.array([4, 2])
+    np.savez_compressed(os.path.join(OUT, "fp8_quant.npz"), **fx)
+    print("fp8 fixture written")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -583,6 +705,8 @@ if __name__ == "__main__":
         gen_layer()
     if which in ("two_blocks",):  # run on its own (a process group per scenario)
         gen_two_blocks()
+    if which in ("fp8",):         # run on its own (a process group per scenario)
+        gen_fp8()
     if which in ("gating",):      # run on its own: it monkey-patches Tensor.is_cuda while it runs
         gen_gating()
     if which in ("all", "single"):

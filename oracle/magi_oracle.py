@@ -467,6 +467,78 @@ def linear_bf16(x: np.ndarray, w: np.ndarray, b: Optional[np.ndarray] = None) ->
     return bf16_round(y)
 
 
+# ----------------------------------------------------------------------------------------------- fp8 linears
+E4M3_MAX = F32(448.0)   # torch.finfo(torch.float8_e4m3fn).max
+
+
+def e4m3_round(x: np.ndarray) -> np.ndarray:
+    """Round fp32 values with |x| <= 448 to the nearest float8_e4m3fn value (ties to even), returned as fp32: 3
+    mantissa bits, exponent bias 7, smallest normal 2^-6, subnormal quantum 2^-9 (what `.to(torch.float8_e4m3fn)`
+    does for in-range values)."""
+    x = np.asarray(x, dtype=np.float64)
+    a = np.abs(x)
+    e = np.floor(np.log2(np.where(a > 0, a, 1.0)))
+    q = np.exp2(np.maximum(e, -6.0) - 3.0)           # spacing of representable values around x
+    return (np.rint(x / q) * q).astype(F32)          # np.rint rounds half to even
+
+
+def e4m3_encode(x: np.ndarray) -> np.ndarray:
+    """The byte pattern (sign | 4-bit exponent | 3-bit mantissa) of values that are exactly representable."""
+    x = np.asarray(x, dtype=np.float64)
+    a = np.abs(x)
+    e = np.maximum(np.floor(np.log2(np.where(a > 0, a, 1.0))), -6.0)
+    normal = a >= 2.0 ** -6
+    mant = np.where(normal, np.rint((a / np.exp2(e) - 1.0) * 8.0), np.rint(a * 512.0)).astype(np.int64)
+    expo = np.where(normal, e.astype(np.int64) + 7, 0)
+    sign = np.signbit(x).astype(np.int64) << 7
+    return (sign | (expo << 3) | mant).astype(np.uint8)
+
+
+def e4m3_decode(b: np.ndarray) -> np.ndarray:
+    b = np.asarray(b, dtype=np.uint8).astype(np.int64)
+    expo, mant = (b >> 3) & 15, b & 7
+    v = np.where(expo > 0, (1.0 + mant / 8.0) * np.exp2(expo - 7.0), mant / 8.0 * 2.0 ** -6)
+    v = np.where((b & 0x7F) == 0x7F, np.nan, v)
+    return np.where(b & 0x80, -v, v).astype(F32)
+
+
+def div_clamp_to(x: np.ndarray, scale: np.ndarray) -> np.ndarray:
+    """div_clamp_to, dit_module.py:364-384: clamp(x.float() / scale.float(), -448, 448).bfloat16().to(float8_e4m3fn);
+    `scale` broadcasts against the last dimension. Returns the fp8 VALUES as fp32 (e4m3_encode gives the bytes). The
+    256 MB partitioning of :370-380 only bounds the memory peak."""
+    r = (np.asarray(x, dtype=F32) / np.asarray(scale, dtype=F32).reshape(-1)).astype(F32)
+    r = np.clip(r, -E4M3_MAX, E4M3_MAX)
+    return e4m3_round(bf16_round(r))
+
+
+def linear_fp8(x: np.ndarray, weight_bytes: np.ndarray, quant_scale: np.ndarray, input_scale: np.ndarray,
+               weight_scale: np.ndarray) -> np.ndarray:
+    """PerTensorQuantizedFp8Linear.forward (dit_module.py:446-457; quant_scale = input_scale, a vector of in_features)
+    and PerChannelQuantizedFp8Linear.forward (:478-488; quant_scale = smooth_scale (1, in_features), input_scale a
+    scalar): div_clamp_to, then `flashinfer.bmm_fp8(xq, weight^T, input_scale, weight_scale, bf16)`. bmm_fp8 is a
+    third-party CUDA kernel absent from /root/reference (flashinfer==0.2.0.post2, requirements.txt:21); its published
+    definition is the cuBLASLt fp8 matmul with per-tensor scale pointers: out = bf16((A @ B) * a_scale * b_scale) with
+    fp32 accumulation, cuBLASLt reading ONE float behind each pointer (the first element of a vector input_scale).
+    weight_bytes: (1, out, in) or (out, in) uint8 e4m3 patterns."""
+    xq = div_clamp_to(x, quant_scale)
+    wq = e4m3_decode(np.asarray(weight_bytes).reshape(-1, x.shape[-1]))
+    acc = xq.astype(F32) @ wq.T
+    s = F32(np.asarray(input_scale, dtype=F32).reshape(-1)[0]) * F32(np.asarray(weight_scale, dtype=F32).reshape(-1)[0])
+    return bf16_round(acc * s)
+
+
+def linear_named(w, name: str, x: np.ndarray) -> np.ndarray:
+    """The linear `name` of a state_dict, by the class its parameters reveal (dit_module.py:405-410, 520-540, 873-880):
+    smooth_scale -> PerChannelQuantizedFp8Linear, input_scale -> PerTensorQuantizedFp8Linear, else nn.Linear."""
+    if name + ".smooth_scale" in w:
+        return linear_fp8(x, w[name + ".weight"], w[name + ".smooth_scale"], w[name + ".input_scale"],
+                          w[name + ".weight_scale"])
+    if name + ".input_scale" in w:
+        return linear_fp8(x, w[name + ".weight"], w[name + ".input_scale"], w[name + ".input_scale"],
+                          w[name + ".weight_scale"])
+    return linear_bf16(x, w[name + ".weight"])
+
+
 def gelu(x: np.ndarray) -> np.ndarray:
     """torch.nn.functional.gelu (erf form) on a bf16 tensor: fp32 math, bf16 result."""
     from scipy.special import erf
@@ -496,11 +568,11 @@ def fully_parallel_attention(w, hs, kvs, rope, cache, has_inf, slice_point, dn, 
     Returns (core_attn_out, xattn_out), each (sq, b, Hq * 128)."""
     g = lambda n: w[pre + n]
     sq, b, _ = hs.shape
-    Hq = g("linear_qkv.q.weight").shape[0] // 128
-    Hkv = g("linear_qkv.k.weight").shape[0] // 128
+    Hq = g("linear_qkv.q.weight").shape[-2] // 128      # (out, in), or (1, out, in) for the fp8 linears
+    Hkv = g("linear_qkv.k.weight").shape[-2] // 128
     mixed = bf16_round(layer_norm(hs, g("linear_qkv.layer_norm.weight"), g("linear_qkv.layer_norm.bias"), 1e-6,
                                   zero_centered_gamma=False))
-    lin = {n: linear_bf16(mixed, g(f"linear_qkv.{n}.weight")) for n in ("q", "qx", "k", "v")}
+    lin = {n: linear_named(w, pre + f"linear_qkv.{n}", mixed) for n in ("q", "qx", "k", "v")}
     sin, cos = rope[:, :48], rope[:, 48:]
     q = get_q_or_k(lin["q"], Hq, g("q_layernorm.weight"), g("q_layernorm.bias"), sin, cos)
     kv = get_kv(lin["k"], lin["v"], Hkv, g("k_layernorm.weight"), g("k_layernorm.bias"), sin, cos)
@@ -529,7 +601,7 @@ def transformer_layer(w, hs, condition, condition_map, kvs, rope, cache, has_inf
     sq, b, width = core.shape
     x = np.stack([core, xo], axis=2).reshape(sq, b, 2, 8, width // 8)
     x = np.transpose(x, (0, 1, 3, 2, 4)).reshape(sq, b, 2 * width)
-    attn_out = linear_bf16(x, w["self_attention.linear_proj.weight"])
+    attn_out = linear_named(w, "self_attention.linear_proj", x)
     c = condition.astype(F32)
     silu = bf16_round(c / (F32(1.0) + np.exp(-c)))
     gate = softcap(linear_bf16(silu, w["ada_modulate_layer.proj.0.weight"], w["ada_modulate_layer.proj.0.bias"]), 1.0)
@@ -538,9 +610,9 @@ def transformer_layer(w, hs, condition, condition_map, kvs, rope, cache, has_inf
     x1 = bias_modulate_add(attn_out, hs, condition_map, gate_msa, w["self_attn_post_norm.weight"],
                            w["self_attn_post_norm.bias"])
     m = bf16_round(layer_norm(x1, w["mlp.layer_norm.weight"], w["mlp.layer_norm.bias"], 1e-6, zero_centered_gamma=False))
-    m = linear_bf16(m, w["mlp.linear_fc1.weight"])
+    m = linear_named(w, "mlp.linear_fc1", m)
     m = mlp_activation(m, gated_linear_unit)
-    m = linear_bf16(m, w["mlp.linear_fc2.weight"])
+    m = linear_named(w, "mlp.linear_fc2", m)
     return bias_modulate_add(m, x1, condition_map, gate_mlp, w["mlp_post_norm.weight"], w["mlp_post_norm.bias"])
 
 

@@ -128,15 +128,39 @@ def attn_ranges(q, k_new, v_new, q_ranges=None, k_ranges=None, k_cache=None, v_c
 
 
 def stack_qkv_weights(wq, wk, wv, wqx=None):
-    return torch.cat([t for t in (wq, wk, wv, wqx) if t is not None], dim=0).contiguous()
+    ws = [t for t in (wq, wk, wv, wqx) if t is not None]
+    if ws[0].dtype == torch.float8_e4m3fn:
+        ws = [t.view(torch.uint8) for t in ws]
+    return torch.cat(ws, dim=0).contiguous()
+
+
+def fp8_quantize(x, scale):
+    """div_clamp_to through the oracle, as a float8_e4m3fn tensor."""
+    b = O.e4m3_encode(O.div_clamp_to(_np(x), _np(scale)))
+    return torch.from_numpy(np.ascontiguousarray(b)).view(torch.float8_e4m3fn).reshape(x.shape)
+
+
+def fp8_scaled_linear(xq, weight, input_scale, weight_scale, out_dtype=torch.bfloat16):
+    """bmm_fp8's published math on the already quantised input (see magi_oracle.linear_fp8)."""
+    acc = O.e4m3_decode(xq.view(torch.uint8).numpy()).reshape(-1, xq.shape[-1]) @ \
+        O.e4m3_decode(weight.view(torch.uint8).numpy()).T
+    s = np.float32(_np(input_scale).reshape(-1)[0]) * np.float32(_np(weight_scale).reshape(-1)[0])
+    return _bf(O.bf16_round(acc * s)).to(out_dtype).view(*xq.shape[:-1], weight.shape[0])
 
 
 def qkv_proj_norm_rope(x, w, num_heads_q, num_heads_kv, ln_q, ln_k, sin, cos, ln_qx=None, batch=1, eps=1e-6,
                        zero_centered_gamma=True, cache=None, cache_row_offset=0, cache_rows=0, num_sms=0,
-                       peer_q_out=None, peer_kv_out=None, peer_row_offset=0):
-    """The fused projection GEMM as the composition it replaces: nn.Linear in bf16, then the prologue double."""
-    y = _bf(O.linear_bf16(_np(x), _np(w)))
+                       peer_q_out=None, peer_kv_out=None, peer_row_offset=0, out_scale=None):
+    """The fused projection GEMM as the composition it replaces: nn.Linear in bf16 (or, with out_scale, the fp8 GEMM
+    scaled per projection), then the prologue double."""
     nq, nk = num_heads_q * HEAD_DIM, num_heads_kv * HEAD_DIM
+    if out_scale is not None:
+        assert x.dtype in (torch.float8_e4m3fn, torch.uint8) and w.dtype in (torch.float8_e4m3fn, torch.uint8)
+        acc = O.e4m3_decode(x.view(torch.uint8).numpy()) @ O.e4m3_decode(w.view(torch.uint8).numpy()).T
+        col_scale = np.repeat(_np(out_scale), [nq, nk, nk, nq])[:acc.shape[1]]
+        y = _bf(O.bf16_round(acc * col_scale))
+    else:
+        y = _bf(O.linear_bf16(_np(x), _np(w)))
     if peer_q_out is not None:    # the Ulysses input all-to-all fused into the epilogue: the prologue double's routing
         cp = len(peer_q_out)
         hkv_loc = num_heads_kv // cp if num_heads_kv >= cp else 1

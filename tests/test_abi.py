@@ -56,6 +56,9 @@ def test_struct_layout_matches_header():
       printf("%zu %zu %zu %zu %zu\n", sizeof(magi_rotary_args), offsetof(magi_rotary_args, batch),
              offsetof(magi_rotary_args, heads), offsetof(magi_rotary_args, x_batch_stride),
              offsetof(magi_rotary_args, cos));
+      printf("%zu %zu %zu %zu %zu %zu\n", sizeof(magi_qkv_proj_args), offsetof(magi_qkv_proj_args, w),
+             offsetof(magi_qkv_proj_args, num_sms), offsetof(magi_qkv_proj_args, peer_row_offset),
+             offsetof(magi_qkv_proj_args, fp8), offsetof(magi_qkv_proj_args, out_scale));
       return 0;
     }'''
     import tempfile
@@ -64,8 +67,11 @@ def test_struct_layout_matches_header():
         open(c, "w").write(src)
         exe = os.path.join(d, "t")
         subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
-        a, b, c_, d_, e_ = subprocess.run([exe], capture_output=True, text=True,
-                                          check=True).stdout.strip().splitlines()
+        a, b, c_, d_, e_, f_ = subprocess.run([exe], capture_output=True, text=True,
+                                              check=True).stdout.strip().splitlines()
+    Q = _lib.MagiQkvProjArgs
+    assert [int(x) for x in f_.split()] == [C.sizeof(Q), Q.w.offset, Q.num_sms.offset, Q.peer_row_offset.offset,
+                                            Q.fp8.offset, Q.out_scale.offset]
     A, P, G, R = _lib.MagiAttnArgs, _lib.MagiPrologueArgs, _lib.MagiGatingArgs, _lib.MagiRotaryArgs
     assert [int(x) for x in e_.split()] == [C.sizeof(R), R.batch.offset, R.heads.offset, R.x_batch_stride.offset,
                                             R.cos.offset]
@@ -107,6 +113,15 @@ def test_argument_errors_are_reported_not_crashed():
     assert L.magi_apply_rotary_emb(C.byref(r), None) != 0 and b"<= head_dim" in L.magi_last_error()
     r.rotary_dim = 96
     assert L.magi_apply_rotary_emb(C.byref(r), None) != 0 and b"NULL pointer" in L.magi_last_error()
+    assert L.magi_fp8_quantize(None, 64, None, 1, None, 64, 4, 60, None) != 0 and b"multiple of 16" in L.magi_last_error()
+    assert L.magi_fp8_quantize(None, 64, None, 7, None, 64, 4, 64, None) != 0 and b"scale_len" in L.magi_last_error()
+    assert L.magi_fp8_quantize(None, 64, None, 1, None, 64, 4, 64, None) != 0 and b"NULL" in L.magi_last_error()
+    assert L.magi_fp8_quantize(None, 64, None, 1, None, 64, 0, 64, None) == 0          # nothing to do
+    qp = _lib.MagiQkvProjArgs()
+    qp.rows, qp.hidden, qp.num_heads_q, qp.num_heads_kv, qp.batch, qp.fp8 = 4, 192, 2, 2, 1, 1
+    assert L.magi_qkv_proj_norm_rope_fwd(C.byref(qp), None) != 0 and b"128 (fp8)" in L.magi_last_error()
+    qp.hidden = 256
+    assert L.magi_qkv_proj_norm_rope_fwd(C.byref(qp), None) != 0 and b"out_scale" in L.magi_last_error()
     assert L.magi_attn_workspace_bytes(5) >= 4 * (4 + 6 + 20)
     assert b"sm_100a" in L.magi_build_info()
 

@@ -17,8 +17,10 @@ def doubles(monkeypatch):
     import magi_b200  # noqa: F401
     import magi_b200.attention as A
     import magi_b200.transformer_layer as T
+    import magi_b200.fp8_linear as L
     monkeypatch.setattr(A, "F", D)
     monkeypatch.setattr(T, "F", D)
+    monkeypatch.setattr(L, "F", D)
     return A, T
 
 
@@ -148,3 +150,67 @@ def test_two_block_stack_matches_reference(doubles):
     for l in (0, 1):
         rel, _ = _rel(inf.key_value_memory_dict[l][:3 * clip], g[f"cache{l}"])
         assert rel < 8e-3, (l, rel)
+
+
+@pytest.mark.parametrize("variant,fused", [("shared", True), ("shared", False), ("split", True)])
+def test_fp8_quant_layer_replays_the_reference(doubles, variant, fused):
+    """engine_config.fp8_quant (example/*/..._distill_quant_config.json): layer 1 of 4 holds fp8 q / qx / k / v, fc1
+    (per-tensor), fc2 and the out-projection (per-channel) - dit_module.py:407, 522, 535, 875 - while layers 0 and 3
+    stay bf16. The reference's calibrated-checkpoint layout loads with strict=True, and two forwards through the KV cache
+    match the reference's own fp8 TransformerLayer. `shared` (equal input scales) takes the fused GEMM path unless
+    fused_qkv_proj is off; `split` (unequal ones) must fall back to one quantisation per linear by itself."""
+    A, T = doubles
+    from magi_b200.common import EngineConfig, InferenceParams, ModelConfig
+    from magi_b200.fp8_linear import PerChannelQuantizedFp8Linear, PerTensorQuantizedFp8Linear
+    g = Golden("fp8_quant.npz")
+    pre = variant + "."
+    Hq, Hkv = [int(x) for x in g["heads"]]
+    hidden = g.raw(pre + "w.self_attention.linear_qkv.layer_norm.weight").shape[0]
+    mc = ModelConfig(num_layers=4, hidden_size=hidden, ffn_hidden_size=4 * hidden, num_attention_heads=Hq,
+                     num_query_groups=Hkv)
+    ec = EngineConfig(fp8_quant=True, fused_qkv_proj=fused)
+    for ln_ in (0, 3):      # first and last layer keep bf16 linears
+        assert isinstance(T.TransformerLayer(mc, ec, layer_number=ln_).mlp.linear_fc1, torch.nn.Linear)
+    layer = T.TransformerLayer(mc, ec, layer_number=1)
+    assert isinstance(layer.self_attention.linear_qkv.q, PerTensorQuantizedFp8Linear)
+    assert isinstance(layer.self_attention.linear_proj, PerChannelQuantizedFp8Linear)
+    assert isinstance(layer.mlp.linear_fc1, PerTensorQuantizedFp8Linear)
+    assert isinstance(layer.mlp.linear_fc2, PerChannelQuantizedFp8Linear)
+    assert isinstance(layer.self_attention.linear_kv_xattn, torch.nn.Linear)
+    T.high_precision_promote(layer)
+    sd = {}
+    for name, key in g.weights(pre + "w.").items():
+        a = g.raw(key)
+        sd[name] = (torch.from_numpy(a.copy()).view(torch.float8_e4m3fn) if a.dtype == np.uint8 else g.torch(key))
+    layer.load_state_dict(sd, strict=True)
+    layer.eval()
+    calls = {"fused_fp8": 0}
+    real = D.qkv_proj_norm_rope
+
+    def counting(*a, **k):
+        calls["fused_fp8"] += k.get("out_scale") is not None
+        return real(*a, **k)
+    D_q = D.qkv_proj_norm_rope
+    D.qkv_proj_norm_rope = counting
+    try:
+        clip = int(g["clip"])
+        inf = InferenceParams(max_batch_size=1, max_sequence_length=4 * clip)
+        inf.key_value_memory_dict[1] = torch.zeros(4 * clip, Hkv, 256, dtype=torch.bfloat16)
+        for tag in ("A", "B"):
+            t = pre + tag
+            sp, dn, upd = [int(x) for x in g[f"{t}.meta"]]
+            meta = _meta(clip, sp, dn, 1, O.core_q_ranges(clip, dn, 1), g.raw(f"{t}.k_range"), g[f"{t}.y_index"])
+            inf.update_kv_cache = bool(upd)
+            core, xo = layer.self_attention(g.torch(f"{t}.hidden_states"), g.torch(f"{t}.key_value_states"), inf,
+                                            g.torch(f"{t}.rope"), meta)
+            out = layer(g.torch(f"{t}.hidden_states"), g.torch(f"{t}.condition"), g.torch(f"{t}.condition_map"),
+                        g.torch(f"{t}.key_value_states"), g.torch(f"{t}.rope"), inf, meta)
+            for name, got, ref in (("core", core, g[f"{t}.core"]), ("xattn", xo, g[f"{t}.xattn"]),
+                                   ("out", out, g[f"{t}.out"])):
+                rel, err = _rel(got, ref)
+                assert rel <= 5e-3, (variant, tag, name, rel, err)
+        cache = inf.key_value_memory_dict[1].float().numpy()[:3 * clip]
+        assert np.abs(cache - g[pre + "cache"]).max() <= 4e-2
+    finally:
+        D.qkv_proj_norm_rope = D_q
+    assert (calls["fused_fp8"] > 0) == (variant == "shared" and fused)

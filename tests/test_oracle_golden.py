@@ -364,3 +364,77 @@ def test_lse_merge_is_softmax_over_union():
     e, le = O.attn_ranges(q, k, v, [[0, 40]], [[5, 5]], round_output=False)
     m2, lm2 = O.lse_merge(a, la, e, le)
     np.testing.assert_allclose(lm2, la, atol=0)
+
+
+# ----------------------------------------------------------------------------------------------- fp8_quant linears
+def test_e4m3_helpers_match_torch():
+    """The oracle's hand-written float8_e4m3fn rounding / encoding against torch's own conversion: all 256 byte
+    patterns, and rounding (ties to even, subnormals) of bf16 values across the clamped range."""
+    import torch
+    b = np.arange(256, dtype=np.uint8)
+    t = torch.from_numpy(b).view(torch.float8_e4m3fn).float().numpy()
+    d = O.e4m3_decode(b)
+    fin = ~np.isnan(t)
+    assert np.array_equal(np.isnan(t), np.isnan(d)) and np.array_equal(t[fin], d[fin])
+    assert np.array_equal(O.e4m3_encode(t[fin]), b[fin])
+    gen = torch.Generator().manual_seed(5)
+    x = torch.cat([(torch.randn(50000, generator=gen) * 100).clamp(-448, 448), torch.randn(50000, generator=gen) * 0.01,
+                   torch.tensor([0.0, -0.0, 448.0, -448.0, 2.0 ** -10, 3 * 2.0 ** -10, 0.06640625])]).bfloat16()
+    ref = x.to(torch.float8_e4m3fn)
+    mine = O.e4m3_round(x.float().numpy())
+    assert np.array_equal(ref.float().numpy(), mine)
+    assert np.array_equal(ref.view(torch.uint8).numpy(), O.e4m3_encode(mine))
+
+
+def test_div_clamp_to_bytes_match_reference():
+    """div_clamp_to (dit_module.py:364-384) executed by the reference vs the oracle: byte-exact, per-channel and
+    scalar divisors, including values beyond the clamp, signed zeros and subnormal results."""
+    g = Golden("fp8_quant.npz")
+    x = g["dct.x"]
+    for kind in ("vec", "scalar"):
+        got = O.e4m3_encode(O.div_clamp_to(x, g.raw(f"dct.scale_{kind}")))
+        assert np.array_equal(got, g.raw(f"dct.out_{kind}")), kind
+
+
+@pytest.mark.parametrize("cls", ["pt", "pc"])
+def test_fp8_linear_classes_match_reference(cls):
+    """PerTensorQuantizedFp8Linear / PerChannelQuantizedFp8Linear (dit_module.py:431-488) executed by the reference
+    (bmm_fp8 replaced by its published math) vs the oracle: the fp8 products are exact in fp32, so only the fp32
+    summation order differs (numpy vs ATen GEMM) - at most one bf16 ulp on a handful of outputs."""
+    g = Golden("fp8_quant.npz")
+    w = {k[len(f"lin.{cls}."):]: g.raw(k) if g.raw(k).dtype == np.uint8 else g[k]
+         for k in g.files if k.startswith(f"lin.{cls}.") and not k.endswith(".out")}
+    quant = w["smooth_scale"] if cls == "pc" else w["input_scale"]
+    out = O.linear_fp8(g["lin.x"], w["weight"], quant, w["input_scale"], w["weight_scale"])
+    ref = g[f"lin.{cls}.out"]
+    assert out.shape == ref.shape
+    diff = np.abs(out - ref)
+    assert (diff <= np.abs(ref) * 2.0 ** -7 + 1e-30).all()          # never more than one bf16 ulp
+    assert (diff > 0).mean() < 1e-2
+
+
+@pytest.mark.parametrize("variant", ["shared", "split"])
+def test_fp8_transformer_layer_matches_reference(variant):
+    """A whole fp8_quant DiT block (layer 1 of 4: q / qx / k / v, out-projection, fc1, fc2 all fp8) through the oracle
+    against the reference's own TransformerLayer run on CPU, two forwards through the KV cache; `split` gives the four
+    qkv linears unequal input scales. Same criterion as the bf16 block (rel-L2 <= 2e-2); the
+    attention outputs and the cache are checked too."""
+    g = Golden("fp8_quant.npz")
+    pre = variant + "."
+    w = {k[len(pre) + 2:]: (g.raw(k) if g.raw(k).dtype == np.uint8 else g[k])
+         for k in g.files if k.startswith(pre + "w.")}
+    clip = int(g["clip"])
+    cache = np.zeros((4 * clip, 2, 256), dtype=np.float32)
+    for tag in ("A", "B"):
+        t = pre + tag
+        sp, dn, upd = [int(x) for x in g[f"{t}.meta"]]
+        args = (g[f"{t}.key_value_states"], g[f"{t}.rope"], cache, True, sp, dn, clip, O.core_q_ranges(clip, dn, 1),
+                g.raw(f"{t}.k_range"), g[f"{t}.y_index"], bool(upd))
+        out = O.transformer_layer(w, g[f"{t}.hidden_states"], g[f"{t}.condition"], g.raw(f"{t}.condition_map"), *args)
+        core, xo = O.fully_parallel_attention(w, g[f"{t}.hidden_states"], *args, pre="self_attention.")
+        for name, got, ref in (("out", out, g[f"{t}.out"]), ("core", core, g[f"{t}.core"]),
+                               ("xattn", xo, g[f"{t}.xattn"])):
+            rel = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+            assert got.shape == ref.shape and rel < 5e-3, (variant, tag, name, rel)
+    ref_cache = g[pre + "cache"]
+    assert np.abs(cache[:3 * clip] - ref_cache).max() <= 1.6e-2

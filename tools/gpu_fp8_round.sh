@@ -1,0 +1,15 @@
+#!/bin/bash
+# ONE short gpurun call for the fp8_quant mode: the fp8 GPU tests (one pytest process per group, so a trap in the GEMM
+# does not take the quantiser's results down) and the fp8 bench probe.
+#   gpurun --timeout 420 -- 'bash tools/gpu_fp8_round.sh r02fp8a'
+tag="${1:-rXX}"
+out=gpurun_out
+mkdir -p $out
+cd "$(dirname "$0")/.."
+python -c "import __graft_entry__ as g; g.build()" > $out/${tag}_build.log 2>&1 || { echo "build failed"; tail -20 $out/${tag}_build.log; exit 1; }
+for grp in quantize projection_gemm linear_classes transformer_layer; do
+  timeout 150 python -m pytest tests/test_fp8_gpu.py -q -k $grp > $out/${tag}_pytest_$grp.log 2>&1
+  echo "pytest $grp rc=$?"; tail -4 $out/${tag}_pytest_$grp.log | cut -c1-300
+done
+timeout 200 python tools/gpu_probe.py v_bench_fp8_qkv > $out/${tag}_fp8_bench.log 2>&1; echo "bench rc=$?"
+cut -c1-220 $out/${tag}_fp8_bench.log | tail -24

@@ -404,6 +404,82 @@ def u_bench_qkv_gemm():
     return True
 
 
+@case
+def v_bench_fp8_qkv():
+    """fp8_quant at cfg2 / 24B shapes: the quantiser alone (GB/s over 3 bytes per element), quantiser + fused fp8 GEMM
+    (tcgen05 kind::f8f6f4, prologue epilogue) against the library path the reference takes (eager div_clamp_to chain +
+    cuBLASLt fp8 matmul per projection) + this repository's prologue kernels, and against the bf16 fused GEMM."""
+    import torch
+    import magi_b200.functional as F
+    dev = "cuda"
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for S, hidden, Hq, Hkv in ((37440, 3072, 24, 8), (27000, 6144, 48, 8)):
+        g = torch.Generator(device=dev).manual_seed(1)
+        x = torch.randn(S, hidden, device=dev, generator=g).to(torch.bfloat16)
+        heads = (Hq, Hkv, Hkv, Hq)
+        wb = [(torch.randn(h * 128, hidden, device=dev, generator=g) * hidden ** -0.5) for h in heads]
+        wsc = [w.abs().max() / 448.0 for w in wb]
+        w8 = [(w / s).to(torch.float8_e4m3fn) for w, s in zip(wb, wsc)]
+        w_cat8 = F.stack_qkv_weights(*w8)
+        w_cat16 = F.stack_qkv_weights(*[w.to(torch.bfloat16) for w in wb])
+        in_scale = torch.full((hidden,), 4.0 / 448.0, device=dev)
+        out_scale = torch.stack([in_scale[0] * s for s in wsc]).float().contiguous()
+        ln = [torch.randn(128, device=dev) * 0.1 for _ in range(4)]
+        lnx = [(torch.randn(128, device=dev) * 0.1).to(torch.bfloat16) for _ in range(2)]
+        ang = torch.rand(S, 48, device=dev) * 6.28
+        sin, cos = torch.sin(ang), torch.cos(ang)
+        flops = 2 * S * hidden * w_cat8.shape[0]
+
+        def quant():
+            return F.fp8_quantize(x, in_scale)
+
+        def eager_quant():   # the literal lines of div_clamp_to (one part: S * hidden * 4 B > 256 MB would split in two)
+            return torch.clamp(x.float() / in_scale.float(), -448.0, 448.0).bfloat16().to(torch.float8_e4m3fn)
+
+        def fused8():
+            return F.qkv_proj_norm_rope(quant(), w_cat8, Hq, Hkv, (ln[0], ln[1]), (ln[2], ln[3]), sin, cos,
+                                        ln_qx=(lnx[0], lnx[1]), out_scale=out_scale)
+
+        def fused16():
+            return F.qkv_proj_norm_rope(x, w_cat16, Hq, Hkv, (ln[0], ln[1]), (ln[2], ln[3]), sin, cos,
+                                        ln_qx=(lnx[0], lnx[1]))
+
+        def library8():
+            y = [F.fp8_scaled_linear(eager_quant(), w_, in_scale, s.reshape(1)) for w_, s in zip(w8, wsc)]
+            q, kv = F.qk_norm_rope(y[0], y[1], y[2], Hq, Hkv, (ln[0], ln[1]), (ln[2], ln[3]), sin, cos)
+            qx, _ = F.qk_norm_rope(y[3], None, None, Hq, Hkv, (lnx[0], lnx[1]), None, None, None)
+            return q, kv, qx
+
+        res = {}
+        for nm, fn in (("quantiser alone", quant), ("eager div_clamp_to chain", eager_quant),
+                       ("quantiser + fused fp8 GEMM+prologue", fused8), ("bf16 fused GEMM+prologue", fused16),
+                       ("reference-style: 4 x (eager quant + cuBLASLt fp8) + prologue launches", library8)):
+            for _ in range(2):
+                out = fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(6):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); out = fn(); e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            res[nm] = out
+            extra = (f"{3 * S * hidden / min(ts) / 1e6:.0f} GB/s (3 B per element)" if "quant" in nm and "GEMM" not in nm
+                     and "cuBLAS" not in nm else f"{flops / min(ts) / 1e9:.0f} TFLOP/s (GEMM flops)")
+            print(f"[fp8 {S}x{hidden}->{w_cat8.shape[0]}: {nm}] best {min(ts)*1e3:.0f} us, median "
+                  f"{sorted(ts)[len(ts)//2]*1e3:.0f} us -> {extra}", flush=True)
+        same = torch.equal(res["quantiser alone"].view(torch.uint8), res["eager div_clamp_to chain"].view(torch.uint8))
+        print(f"    quantiser bytes identical to the eager chain: {same}", flush=True)
+        a = res["quantiser + fused fp8 GEMM+prologue"]
+        b_ = res["reference-style: 4 x (eager quant + cuBLASLt fp8) + prologue launches"]
+        for nm, t0, t1 in zip(("q", "kv", "qx"), a, b_):
+            d = (t0.float() - t1.float()).abs()
+            print(f"    fused fp8 vs library fp8 {nm}: max_abs {d.max().item():.3e}, mismatching "
+                  f"{100*(d>0).float().mean().item():.3f} %", flush=True)
+    return True
+
+
 def main():
     names = sys.argv[1:] or sorted(CASES)
     if len(names) == 1 and names[0].startswith("--run="):
