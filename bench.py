@@ -466,13 +466,16 @@ class HotPath:
 
 
 # ----------------------------------------------------------------------------------------------- whole DiT blocks
-def dit_step_leg(w, dev, world, rank, steps, max_over_ranks, barrier):
+def dit_step_leg(w, dev, world, rank, steps, max_over_ranks, barrier, fp8=False):
     """BASELINE.json's second metric, "DiT denoise-step latency": one forward of ALL transformer blocks of the named
     model on the same state - the attention hot path (this repository's kernels) plus everything around it in the
     block (hidden LayerNorms, q/qx/k/v, text-kv, out-projection and MLP GEMMs through cuBLAS, the fused adaLN gating
     chains) via the drop-in TransformerLayer (magi-1_b200/transformer_layer.py); random-init weights of the real
     architecture, synthetic latents / captions / timestep embeddings. N > 1: sequence-sharded blocks, Ulysses
-    attention with the all-to-alls fused into the kernels."""
+    attention with the all-to-alls fused into the kernels.
+    fp8=True: engine_config.fp8_quant (the *_distill_quant configs): every layer but the first and the last holds fp8
+    q / qx / k / v (fused tcgen05 kind::f8f6f4 GEMM with the prologue as its epilogue), out-projection, fc1 and fc2
+    (activation quantiser kernel + cuBLASLt fp8 matmul, the library GEMM the reference calls through bmm_fp8)."""
     import numpy as np
     import torch
     from magi_b200 import context_parallel as cpm
@@ -481,7 +484,7 @@ def dit_step_leg(w, dev, world, rank, steps, max_over_ranks, barrier):
     from magi_b200.transformer_layer import TransformerLayer, high_precision_promote
     big = w["Hq"] == 48
     mc = (ModelConfig.magi_24b if big else ModelConfig.magi_4p5b)(num_layers=w["layers"])
-    ec = EngineConfig(cp_size=world, cp_strategy="none" if world == 1 else "cp_ulysses")
+    ec = EngineConfig(cp_size=world, cp_strategy="none" if world == 1 else "cp_ulysses", fp8_quant=fp8)
     clip, n, sp = w["clip"], len(w["k_chunks"]), w["slice_point"]
     S = clip * n
     torch.manual_seed(1234)
@@ -490,7 +493,15 @@ def dit_step_leg(w, dev, world, rank, steps, max_over_ranks, barrier):
         with torch.device(dev):
             layer = high_precision_promote(TransformerLayer(mc, ec, layer_number=l))
         for name, p_ in layer.named_parameters():
-            if "layernorm" in name or "post_norm" in name or name.endswith("bias"):
+            if p_.dtype == torch.float8_e4m3fn:      # a calibrated-checkpoint-like fp8 linear: |w| <= 448 * weight_scale
+                p_.data.copy_((torch.randn(p_.shape, device=dev) * 100.0).clamp_(-448.0, 448.0).to(p_.dtype))
+            elif name.endswith("weight_scale"):
+                p_.data.fill_(0.01 / math.sqrt(dict(layer.named_parameters())[name[:-6]].shape[-1]))
+            elif name.endswith("input_scale"):
+                p_.data.fill_(6.0 / 448.0)
+            elif name.endswith("smooth_scale"):
+                p_.data.fill_(1.0)
+            elif "layernorm" in name or "post_norm" in name or name.endswith("bias"):
                 p_.data.normal_(0.0, 0.02)
             elif name.endswith("layer_norm.weight"):
                 p_.data.fill_(1.0)
@@ -581,7 +592,8 @@ def dit_step_leg(w, dev, world, rank, steps, max_over_ranks, barrier):
             "attn_tflop_per_step": round((self_f + cross_f) * w["layers"] / 1e12, 1),
             "what": "all transformer blocks of one denoise forward: attention hot path (own kernels) + cuBLAS GEMMs + "
                     "fused adaLN gating chains, random-init weights, " + ("single GPU" if world == 1 else
-                                                                         f"cp_ulysses{world} fused all-to-alls")}
+                                                                         f"cp_ulysses{world} fused all-to-alls")
+                    + (", fp8_quant: fp8 linears in every layer but the first and the last" if fp8 else "")}
 
 
 # ----------------------------------------------------------------------------------------------- GPU reference leg
@@ -944,6 +956,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-dit-step", action="store_true", help="skip the whole-DiT-block step latency leg")
+    ap.add_argument("--no-fp8-dit-step", action="store_true",
+                    help="N = 1: skip the fp8_quant variant of the DiT step leg (the *_distill_quant configs)")
     ap.add_argument("--no-gpu-reference", action="store_true",
                     help="skip the flash-attn (reference fallback) self-attention leg on the GPU")
     ap.add_argument("--no-extra-legs", action="store_true",
@@ -1013,6 +1027,12 @@ def main():
     dit = None
     if not args.no_dit_step and not args.cp_mode.startswith("ring"):
         dit = dit_step_leg(w, dev, world, rank, min(args.steps, 3), cx.max_over_ranks, cx.barrier)
+        if world == 1 and not args.no_fp8_dit_step:
+            try:
+                dit["fp8_quant"] = dit_step_leg(w, dev, world, rank, min(args.steps, 3), cx.max_over_ranks, cx.barrier,
+                                                fp8=True)
+            except Exception as e:  # an extra leg must never cost the headline line
+                dit["fp8_quant"] = {"error": f"{type(e).__name__}: {e}"[:200]}
 
     # ---- extra legs at N > 1 (never the value): ring-KV on the same workload, configs[3] under both strategies
     extra = None
@@ -1091,6 +1111,8 @@ def main():
             line["dit_denoise_step"] = dit
             line["roofline"]["dit_denoise_step_ms"] = dit["ms_per_step"]
             line["roofline"]["dit_denoise_step_tflops"] = dit["tflops_total"]
+            if "ms_per_step" in dit.get("fp8_quant", {}):
+                line["roofline"]["dit_denoise_step_fp8_quant_ms"] = dit["fp8_quant"]["ms_per_step"]
         if gpu_ref is not None:
             line["gpu_reference"] = gpu_ref
         print(json.dumps(line), flush=True)

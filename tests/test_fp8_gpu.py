@@ -71,6 +71,33 @@ def test_fp8_quantize_vs_oracle_and_eager(F, rows, cols, vector):
                                                                   out.view(torch.uint8))
 
 
+def test_fp8_quantize_exhaustive_over_bf16_inputs(F):
+    """Every bf16 bit pattern (NaNs aside) against 64 divisors - random ones, 'nice' ones whose quotients sit exactly on
+    bf16 rounding ties (0.1, 3, powers of two), and ones whose reciprocal is subnormal or infinite - byte exact against
+    the reference's eager chain on the same GPU. This is the test of the kernel's shortcut (x * (1 / s), with the exact
+    division only near rounding boundaries, csrc/fp8_quant.cu)."""
+    bits = torch.arange(65536, dtype=torch.int32, device="cuda").to(torch.int16)
+    x = bits.view(torch.bfloat16).view(-1, 1).expand(-1, 64).contiguous()
+    rng = np.random.default_rng(7)
+    sc = np.concatenate([rng.uniform(0.004, 0.02, 40), rng.uniform(0.5, 2.0, 8),
+                         [1.0, 0.0078125, 3.0, 0.1, 7.0, 448.0, 0.3, 0.75, 1e-30, 1e30, 1e-42, 1e38, 3e38, 2.0 ** -126,
+                          2.0 ** 126, 6.0]]).astype(np.float32)
+    assert sc.size == 64
+    st = torch.from_numpy(sc).cuda()
+    out = F.fp8_quantize(x, st).view(torch.uint8)
+    eager = torch.clamp(x.float() / st.float(), -448.0, 448.0).bfloat16().to(torch.float8_e4m3fn).view(torch.uint8)
+    ok = ~torch.isnan(x.float())
+    assert torch.equal(out[ok], eager[ok])
+    assert np.array_equal(out[ok].cpu().numpy(),
+                          O.e4m3_encode(O.div_clamp_to(x.float().cpu().numpy(), sc))[ok.cpu().numpy()])
+    # scalar divisor: the same inputs against each of a few divisors
+    for s1 in (0.0123, 0.1, 1e-42):
+        s1t = torch.tensor([s1], dtype=torch.float32, device="cuda")
+        o1 = F.fp8_quantize(x[:, :16].contiguous(), s1t).view(torch.uint8)
+        e1 = torch.clamp(x[:, :16].float() / s1t, -448.0, 448.0).bfloat16().to(torch.float8_e4m3fn).view(torch.uint8)
+        assert torch.equal(o1[ok[:, :16]], e1[ok[:, :16]]), s1
+
+
 def _fp8_weights(shape, seed):
     w = rnd(shape, seed, scale=shape[1] ** -0.5)
     ws = np.float32(np.abs(w).max() / 448.0)
@@ -126,7 +153,7 @@ def test_fp8_projection_gemm_vs_oracle(F, rows, hidden, Hq, Hkv, with_qx, batch)
                              batch=batch)
     close(q, q2.float().cpu().numpy(), "q vs cuBLASLt path")
     close(kv, kv2.float().cpu().numpy(), "kv vs cuBLASLt path")
-    close(y[0].float().cpu().numpy(), lin[0], "cuBLASLt fp8 linear vs oracle")
+    close(y[0], lin[0], "cuBLASLt fp8 linear vs oracle")
 
 
 @pytest.mark.parametrize("cls", ["pt", "pc"])

@@ -7,9 +7,22 @@ out=gpurun_out
 mkdir -p $out
 cd "$(dirname "$0")/.."
 python -c "import __graft_entry__ as g; g.build()" > $out/${tag}_build.log 2>&1 || { echo "build failed"; tail -20 $out/${tag}_build.log; exit 1; }
-for grp in quantize projection_gemm linear_classes transformer_layer; do
+for grp in quantize projection_gemm linear_classes transformer_layer; do  # "quantize" also selects the exhaustive test
   timeout 150 python -m pytest tests/test_fp8_gpu.py -q -k $grp > $out/${tag}_pytest_$grp.log 2>&1
   echo "pytest $grp rc=$?"; tail -4 $out/${tag}_pytest_$grp.log | cut -c1-300
 done
-timeout 200 python tools/gpu_probe.py v_bench_fp8_qkv > $out/${tag}_fp8_bench.log 2>&1; echo "bench rc=$?"
+timeout 200 python tools/gpu_probe.py --run=v_bench_fp8_qkv > $out/${tag}_fp8_bench.log 2>&1; echo "bench rc=$?"
 cut -c1-220 $out/${tag}_fp8_bench.log | tail -24
+# the DiT step with and without fp8_quant (short: the hot-path legs are not what this call is about)
+timeout 400 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-gpu-reference --no-e2e \
+    > $out/${tag}_bench_short.json 2> $out/${tag}_bench_short.err; echo "bench.py rc=$?"
+python - <<PY
+import json
+try:
+    d = json.loads(open("$out/${tag}_bench_short.json").read().strip().splitlines()[-1])
+    print("value", d["value"], "dit", {k: v for k, v in d["dit_denoise_step"].items() if k != "what" and k != "fp8_quant"})
+    print("dit fp8", {k: v for k, v in d["dit_denoise_step"].get("fp8_quant", {}).items() if k != "what"})
+except Exception as e:
+    print("no bench line:", e)
+PY
+tail -3 $out/${tag}_bench_short.err | cut -c1-300
