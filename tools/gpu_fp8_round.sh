@@ -13,6 +13,12 @@ for grp in quantize projection_gemm linear_classes transformer_layer; do  # "qua
 done
 timeout 200 python tools/gpu_probe.py --run=v_bench_fp8_qkv > $out/${tag}_fp8_bench.log 2>&1; echo "bench rc=$?"
 cut -c1-220 $out/${tag}_fp8_bench.log | tail -24
+# one full ncu capture of the quantiser and of the fp8 GEMM at cfg2 shapes (the 9th / 10th matching launch of the probe:
+# the first "quantiser + fused fp8 GEMM" call), after the probe itself has exited 0 without ncu
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'fp8_quant_kernel|qkv_gemm_kernel' -s 8 -c 2 \
+    -o $out/${tag}_fp8prof python tools/gpu_probe.py --run=v_bench_fp8_qkv > $out/${tag}_ncu_fp8.log 2>&1; echo "ncu rc=$?"
+[ -f $out/${tag}_fp8prof.ncu-rep ] && ncu -i $out/${tag}_fp8prof.ncu-rep --page raw --csv > $out/${tag}_ncu_fp8_raw.csv 2>/dev/null
+[ "$2" = "short" ] && exit 0
 # the DiT step with and without fp8_quant (short: the hot-path legs are not what this call is about)
 timeout 400 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-gpu-reference --no-e2e \
     > $out/${tag}_bench_short.json 2> $out/${tag}_bench_short.err; echo "bench.py rc=$?"
