@@ -7,12 +7,15 @@ out=gpurun_out
 mkdir -p $out
 cd "$(dirname "$0")/.."
 python -c "import __graft_entry__ as g; g.build()" > $out/${tag}_build.log 2>&1 || { echo "build failed"; tail -20 $out/${tag}_build.log; exit 1; }
-for grp in quantize projection_gemm linear_classes transformer_layer; do  # "quantize" also selects the exhaustive test
+groups="quantize projection_gemm linear_classes transformer_layer"
+[ "$2" = "quant" ] && groups="quantize"
+for grp in $groups; do  # "quantize" also selects the exhaustive test
   timeout 150 python -m pytest tests/test_fp8_gpu.py -q -k $grp > $out/${tag}_pytest_$grp.log 2>&1
   echo "pytest $grp rc=$?"; tail -4 $out/${tag}_pytest_$grp.log | cut -c1-300
 done
 timeout 200 python tools/gpu_probe.py --run=v_bench_fp8_qkv > $out/${tag}_fp8_bench.log 2>&1; echo "bench rc=$?"
 cut -c1-220 $out/${tag}_fp8_bench.log | tail -24
+[ "$2" = "quant" ] && exit 0
 # one full ncu capture of the quantiser and of the fp8 GEMM at cfg2 shapes (the 9th / 10th matching launch of the probe:
 # the first "quantiser + fused fp8 GEMM" call), after the probe itself has exited 0 without ncu
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:'fp8_quant_kernel|qkv_gemm_kernel' -s 8 -c 2 \
