@@ -5,8 +5,9 @@ state_dicts load: `linear_qkv.{layer_norm,q,qx,k,v}`, `linear_kv_xattn`, `linear
 inference_params, rotary_pos_emb, meta_args) -> (core_attn_out, xattn_out)`.
 
 What runs where
-  * LayerNorm(hidden) and the q/qx/k/v, kv_xattn projections are plain torch/cuBLAS GEMMs (outside the hot path,
-    SURVEY.md section 2.3 K11).
+  * LayerNorm(hidden) and the kv_xattn / out projections are plain torch / cuBLAS library calls; the q / qx / k / v
+    projections run as ONE hand-written tcgen05 GEMM whose epilogue is the prologue (EngineConfig.fused_qkv_proj;
+    bf16, or e4m3 under fp8_quant behind the hand-written activation quantiser), with cuBLAS as the opt-out.
   * everything between the projections and the two attention outputs is hand-written CUDA behind the C-ABI:
     fused per-head LayerNorm(+1p) + RoPE + packing + KV-cache append (one kernel instead of ~15 eager ones),
     range-masked tcgen05 attention reading the KV cache in place (no torch.cat / chunk().contiguous()),

@@ -9,9 +9,10 @@ What runs where
   * the attention hot path: hand-written CUDA (attention.py / functional.py);
   * both gating chains (`bias_modulate_add`, dit_module.py:292-307): one fused kernel launch each;
   * the out-projection input "sq b (hn n hd)": written in place by the two attention kernels (no cat / rearrange);
-  * the dense GEMMs (q/qx/k/v, kv_xattn, linear_proj, MLP fc1/fc2), the hidden-size LayerNorms in front of them, GELU /
-    SwiGLU and the tiny adaLN projection stay plain torch / cuBLAS library calls: they are not on the path this
-    repository rebuilds.
+  * q / qx / k / v: one fused tcgen05 GEMM inside the attention module (attention.py); GELU / SwiGLU: one launch of
+    magi_mlp_activation; under fp8_quant the activation quantiser in front of every fp8 linear: magi_fp8_quantize;
+  * the other dense GEMMs (kv_xattn, linear_proj, MLP fc1 / fc2; cuBLASLt fp8 under fp8_quant, as in the reference), the
+    hidden-size LayerNorms in front of them and the tiny adaLN projection stay plain torch / cuBLAS library calls.
 """
 import torch
 import torch.nn as nn

@@ -485,7 +485,7 @@ def e4m3_round(x: np.ndarray) -> np.ndarray:
 def e4m3_encode(x: np.ndarray) -> np.ndarray:
     """The byte pattern (sign | 4-bit exponent | 3-bit mantissa) of values that are exactly representable."""
     x = np.asarray(x, dtype=np.float64)
-    a = np.abs(x)
+    a = np.where(np.isfinite(x), np.abs(x), 0.0)      # NaN / infinity have no meaningful pattern here: encoded as 0
     e = np.maximum(np.floor(np.log2(np.where(a > 0, a, 1.0))), -6.0)
     normal = a >= 2.0 ** -6
     mant = np.where(normal, np.rint((a / np.exp2(e) - 1.0) * 8.0), np.rint(a * 512.0)).astype(np.int64)

@@ -718,22 +718,32 @@ def test_mlp_activation_vs_oracle_and_libraries(F, gated, rows, f):
     assert torch.equal(out2, out)
 
 
-@pytest.mark.parametrize("cp,Hq,Hkv", [(2, 4, 2), (4, 8, 2), (8, 8, 1)])
-def test_fused_projection_gemm_peer_routing_on_virtual_ranks(F, cp, Hq, Hkv):
+@pytest.mark.parametrize("cp,Hq,Hkv,fp8", [(2, 4, 2, False), (4, 8, 2, False), (8, 8, 1, False), (2, 4, 2, True),
+                                            (8, 8, 1, True)])
+def test_fused_projection_gemm_peer_routing_on_virtual_ranks(F, cp, Hq, Hkv, fp8):
     """The Ulysses input all-to-all fused into the projection GEMM's epilogue (magi_qkv_proj_args.peer_*), on ONE device:
     every "rank" projects its own rows and stores each head slice into the owning rank's receive buffer. What arrives
     must be, bit for bit, the head slices of the single-rank fused GEMM over all rows (incl. KV-head replication when
-    cp > Hkv); the cross-attention query stays local."""
+    cp > Hkv); the cross-attention query stays local. fp8: the same through the fp8_quant instantiation (e4m3 operands,
+    per-projection output scale)."""
     S, hidden = 700, 256
     split = [S // cp + (1 if i < S % cp else 0) for i in range(cp)]
     offs = np.concatenate([[0], np.cumsum(split)]).astype(np.int64)
     x = bf(rnd((S, hidden), 1))
-    w = F.stack_qkv_weights(*[bf(rnd((h * 128, hidden), 2 + i, hidden ** -0.5)) for i, h in enumerate((Hq, Hkv, Hkv, Hq))])
+    ws = [bf(rnd((h * 128, hidden), 2 + i, hidden ** -0.5)) for i, h in enumerate((Hq, Hkv, Hkv, Hq))]
+    kw = {}
+    if fp8:
+        x = F.fp8_quantize(x, torch.full((hidden,), 4.0 / 448.0, device="cuda"))
+        ws = [(w_.float() * 4000.0).clamp(-448.0, 448.0).to(torch.float8_e4m3fn) for w_ in ws]
+        kw = dict(out_scale=torch.tensor([2.1e-6, 2.3e-6, 2.2e-6, 2.4e-6], device="cuda"))
+    w = F.stack_qkv_weights(*ws)
     ln = [torch.from_numpy(rnd((128,), 10 + i, 0.2)).cuda() for i in range(4)]
     lnx = (bf(rnd((128,), 20, 0.2)), bf(rnd((128,), 21, 0.2)))
     ang = torch.from_numpy(rnd((S, 48), 30, 3.0))
     sin, cos = torch.sin(ang).cuda(), torch.cos(ang).cuda()
-    q_full, kv_full, qx_full = F.qkv_proj_norm_rope(x, w, Hq, Hkv, (ln[0], ln[1]), (ln[2], ln[3]), sin, cos, ln_qx=lnx)
+    q_full, kv_full, qx_full = F.qkv_proj_norm_rope(x, w, Hq, Hkv, (ln[0], ln[1]), (ln[2], ln[3]), sin, cos, ln_qx=lnx,
+                                                    **kw)
+    assert float(q_full.float().abs().mean()) > 0.1 and float(kv_full[..., 128:].float().abs().mean()) > 0.01
     hn, hkv_loc = Hq // cp, max(1, Hkv // cp)
     recv_q = [torch.zeros(S, hn, 128, dtype=torch.bfloat16, device="cuda") for _ in range(cp)]
     recv_kv = [torch.zeros(S, hkv_loc, 256, dtype=torch.bfloat16, device="cuda") for _ in range(cp)]
@@ -741,7 +751,8 @@ def test_fused_projection_gemm_peer_routing_on_virtual_ranks(F, cp, Hq, Hkv):
         sl = slice(int(offs[me]), int(offs[me + 1]))
         q, kv, qx = F.qkv_proj_norm_rope(x[sl], w, Hq, Hkv, (ln[0], ln[1]), (ln[2], ln[3]), sin[sl], cos[sl], ln_qx=lnx,
                                          peer_q_out=[t.data_ptr() for t in recv_q],
-                                         peer_kv_out=[t.data_ptr() for t in recv_kv], peer_row_offset=int(offs[me]))
+                                         peer_kv_out=[t.data_ptr() for t in recv_kv], peer_row_offset=int(offs[me]),
+                                         **kw)
         assert q is None and kv is None and torch.equal(qx, qx_full[sl])
     rep = cp // Hkv if cp > Hkv else 1
     for c in range(cp):
