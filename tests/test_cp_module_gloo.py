@@ -20,14 +20,16 @@ import torch.distributed as dist
 from test_cp_gloo import _setup, _spawn
 
 
-def _module(g, strategy, world, Hq, Hkv, hidden):
+def _module(g, strategy, world, Hq, Hkv, hidden, fp8=False):
     import cpu_functional_double as D
     import magi_b200.attention as A
+    import magi_b200.fp8_linear as L8
     from magi_b200.common import EngineConfig, ModelConfig
     A.F = D                                     # the module's kernels -> CPU doubles
+    L8.F = D
     mc = ModelConfig(num_layers=4, hidden_size=hidden, num_attention_heads=Hq, num_query_groups=Hkv)
-    m = A.FullyParallelAttention(mc, EngineConfig(cp_size=world if strategy != "none" else 1, cp_strategy=strategy),
-                                 layer_number=1)
+    m = A.FullyParallelAttention(mc, EngineConfig(cp_size=world if strategy != "none" else 1, cp_strategy=strategy,
+                                                  fp8_quant=fp8), layer_number=1)
     for n_ in ("q_layernorm", "k_layernorm"):   # dit_model.py:621-633
         getattr(m, n_).float()
     if g is not None:
@@ -118,18 +120,26 @@ class _HostOffload:
             self.stores += 1
 
 
-def _sequence_worker(rank, world, port, strategy, errq, offload=False):
+def _sequence_worker(rank, world, port, strategy, errq, offload=False, fp8=False):
     try:
         _setup(rank, world, port)
         from magi_b200 import context_parallel as cpm
         from magi_b200.common import InferenceParams, PackedCrossAttnParams
         Hq, Hkv, hidden, clip = 4, 2, 128, 37          # 37: shards and chunk stripes are ragged
         torch.manual_seed(4)
-        ref_m = _module(None, "none", 1, Hq, Hkv, hidden)
+        ref_m = _module(None, "none", 1, Hq, Hkv, hidden, fp8=fp8)
         g = torch.Generator().manual_seed(99)
         with torch.no_grad():
             for n, p in ref_m.named_parameters():
-                if "layernorm" in n:
+                if p.dtype == torch.float8_e4m3fn:       # fp8_quant: weights in e4m3 units of weight_scale
+                    p.copy_((torch.randn(p.shape, generator=g) * 120.0).clamp_(-448, 448).to(p.dtype))
+                elif n.endswith("weight_scale"):
+                    p.fill_(1.0 / (120.0 * hidden ** 0.5))
+                elif n.endswith("input_scale"):
+                    p.fill_(5.0 / 448.0)
+                elif n.endswith("smooth_scale"):
+                    p.copy_(1.0 + 0.2 * torch.rand(p.shape, generator=g))
+                elif "layernorm" in n:
                     p.copy_((torch.randn(p.shape, generator=g) * 0.2).to(p.dtype))
                 elif n.endswith("layer_norm.weight"):
                     p.fill_(1.0)
@@ -137,7 +147,7 @@ def _sequence_worker(rank, world, port, strategy, errq, offload=False):
                     p.zero_()
                 else:
                     p.copy_((torch.randn(p.shape, generator=g) / p.shape[-1] ** 0.5).to(p.dtype))
-        cp_m = _module(None, strategy, world, Hq, Hkv, hidden)
+        cp_m = _module(None, strategy, world, Hq, Hkv, hidden, fp8=fp8)
         cp_m.load_state_dict(ref_m.state_dict())
         inf_ref, inf_cp = InferenceParams(1, 5 * clip), InferenceParams(1, 5 * clip)
         if offload:
@@ -223,3 +233,15 @@ def test_module_kv_offload_branches_match_single_rank(strategy, port):
 
 def _sequence_worker_offload(rank, world, port, strategy, errq):
     _sequence_worker(rank, world, port, strategy, errq, offload=True)
+
+
+@pytest.mark.parametrize("strategy,port", [("cp_ulysses", 29671), ("cp_ring_kv", 29672)])
+def test_module_fp8_quant_sequence_matches_single_rank(strategy, port):
+    """The same sequence with engine_config.fp8_quant (fp8 q / qx / k / v linears, dit_module.py:405-410): the
+    single-rank forward takes the fused fp8 projection GEMM, the context-parallel paths over gloo project through the
+    fp8 linear modules one by one - same quantised activations, same results."""
+    _spawn(_sequence_worker_fp8, 2, (port, strategy))
+
+
+def _sequence_worker_fp8(rank, world, port, strategy, errq):
+    _sequence_worker(rank, world, port, strategy, errq, fp8=True)
