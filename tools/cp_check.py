@@ -31,7 +31,8 @@ def main():
     from magi_b200.common import (EngineConfig, InferenceParams, ModelConfig, ModelMetaArgs, PackedCoreAttnParams,
                                   PackedCrossAttnParams)
     mpu.initialize_model_parallel(cp_size=world)
-    GEMM = os.environ.get("CP_CHECK_FUSED_GEMM") == "1"
+    FP8 = os.environ.get("CP_CHECK_FP8") == "1"      # engine_config.fp8_quant: fp8 q / qx / k / v (fused e4m3 GEMM)
+    GEMM = os.environ.get("CP_CHECK_FUSED_GEMM") == "1" or FP8
 
     Hq, Hkv, hidden, clip = 24, 8, 512, 1111       # 1111: shards and tiles are ragged everywhere
     mc = ModelConfig(num_layers=4, hidden_size=hidden, num_attention_heads=Hq, num_query_groups=Hkv)
@@ -46,11 +47,19 @@ def main():
                                                     # CP_CHECK_FUSED_GEMM=1: the fused projection GEMM on both
                                                     # sides instead (under fused Ulysses its epilogue IS the input
                                                     # all-to-all) - only that variant is run then
-                                                    fused_qkv_proj=GEMM), layer_number=1)
+                                                    fused_qkv_proj=GEMM, fp8_quant=FP8), layer_number=1)
         g = torch.Generator().manual_seed(99)
         with torch.no_grad():
             for n, p in m.named_parameters():
-                if "layernorm" in n:
+                if p.dtype == torch.float8_e4m3fn:
+                    p.copy_((torch.randn(p.shape, generator=g) * 120.0).clamp_(-448, 448).to(p.dtype))
+                elif n.endswith("weight_scale"):
+                    p.fill_(1.0 / (120.0 * hidden ** 0.5))
+                elif n.endswith("input_scale"):
+                    p.fill_(5.0 / 448.0)
+                elif n.endswith("smooth_scale"):
+                    p.fill_(1.0)
+                elif "layernorm" in n:
                     p.copy_((torch.randn(p.shape, generator=g) * 0.2).to(p.dtype))
                 elif n.endswith("layer_norm.weight"):
                     p.fill_(1.0)
@@ -177,7 +186,7 @@ def main():
                 worst["core"] = max(worst["core"], (core.float() - ref_core.float()).abs().max().item())
                 worst["xattn"] = max(worst["xattn"], (xo.float() - ref_x.float()).abs().max().item())
             results[f"{strategy}/{'fused-p2p' if fused else 'nccl'}/overlap{overlap}{'/kv_offload' if offload else ''}"
-                    f"{'/fused-gemm' if GEMM else ''}"] = worst
+                    f"{'/fused-gemm' if GEMM else ''}{'/fp8_quant' if FP8 else ''}"] = worst
     torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:
