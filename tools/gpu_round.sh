@@ -34,4 +34,10 @@ timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'at
     -s 6 -c 5 -o $out/${tag}_prof $P > $out/${tag}_ncu_full.log 2>&1
 echo "full capture rc=$?"
 [ -f $out/${tag}_prof.ncu-rep ] && ncu -i $out/${tag}_prof.ncu-rep --page raw --csv > $out/${tag}_ncu_raw.csv 2>/dev/null
+# fp8_quant mode: bench probe (plain, then one full capture of the quantiser and the fp8 GEMM at cfg2 shapes)
+timeout 200 python tools/gpu_probe.py --run=v_bench_fp8_qkv > $out/${tag}_fp8_bench.log 2>&1 &&
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'fp8_quant_kernel|qkv_gemm_kernel' -s 8 -c 2 \
+    -o $out/${tag}_fp8prof python tools/gpu_probe.py --run=v_bench_fp8_qkv > $out/${tag}_ncu_fp8.log 2>&1
+echo "fp8 probe + capture rc=$?"; grep "quantiser alone\|fused fp8" $out/${tag}_fp8_bench.log | cut -c1-160
+[ -f $out/${tag}_fp8prof.ncu-rep ] && ncu -i $out/${tag}_fp8prof.ncu-rep --page raw --csv > $out/${tag}_ncu_fp8_raw.csv 2>/dev/null
 ls -la $out | tail -20
