@@ -102,7 +102,7 @@ class EngineConfig:
     pp_size: int = 1
     cp_size: int = 1
     cp_strategy: str = "none"  # "none" | "cp_ulysses" | "cp_shuffle_overlap" | "cp_ring_kv" (new)
-    ulysses_overlap_degree: int = 1
+    ulysses_overlap_degree: int = 1  # head groups of the NCCL Ulysses path; the fused path overlaps by itself and ignores it
     fp8_quant: bool = False
     distill_nearly_clean_chunk_threshold: float = 0.3
     distill: bool = False
