@@ -72,6 +72,17 @@ def load_peaks():
     return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def prologue_bytes(w):
+    """Algorithmic bytes of the single-GPU layer's ONE prologue launch (SURVEY.md section 8(d) extended by what rides in
+    the launch): projection outputs in (q, k, v, qx, text [K|V]) + the sin / cos rows, and out: q, packed [K|V], its
+    KV-cache copy, the cross-attention query and the normalised text [K|V]."""
+    S, T = w["clip"] * len(w["k_chunks"]), sum(w["text"])
+    hq, hkv = w["Hq"] * 128 * 2, w["Hkv"] * 128 * 2          # bytes of one row of q / of k (or v)
+    read = S * (2 * hq + 2 * hkv + 96 * 4) + T * 2 * hkv
+    write = S * (2 * hq + 2 * hkv + 2 * hkv) + T * 2 * hkv
+    return read + write
+
+
 # ----------------------------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
     """Samples SM clock and throttle reasons of this rank's GPU during the timed region (NVML)."""
@@ -1098,6 +1109,16 @@ def main():
         # measured companions ride inside `roofline` too: the driver's record keeps that object whole
         if phases is not None:
             line["roofline"]["phases_us_per_layer"] = phases
+            if world == 1 and phases.get("prologue"):
+                # the path's memory-bound kernel against the measured HBM copy peak. The phase time is an event-to-event
+                # interval of the diagnostic steps (launch gap included), i.e. an upper bound of the kernel's duration
+                pb = prologue_bytes(w)
+                gbs = pb / (phases["prologue"] * 1e-6) / 1e9
+                line["roofline"]["prologue_hbm"] = {
+                    "bound": "hbm", "kernel": "magi::prologue_ring_kernel (one launch per layer: q / k / v + cache "
+                                              "append + cross-attention qx / text kv)",
+                    "algorithmic_bytes": pb, "us": phases["prologue"], "achieved": round(gbs, 1), "peak": peaks["hbm"],
+                    "unit": "GB/s", "frac": round(gbs / peaks["hbm"], 3)}
         if cp_parity is not None:
             line["cp_parity"] = cp_parity
             line["roofline"]["cp_parity"] = {k: cp_parity.get(k) for k in ("mode", "max_abs", "bound", "ok", "skipped")
