@@ -120,12 +120,74 @@ class TransformerLayer(nn.Module):
         return F.bias_modulate_add(hidden_states, residual, condition_map, gate_mlp, self.mlp_post_norm)
 
 
+class FusedLayerNorm(HeadLayerNorm):
+    """dit_module.py:323-357 as a callable module (the block's final norm): LayerNorm with `weight + 1` when
+    apply_layernorm_1p. The per-head and post-attention / post-MLP instances of the reference class are parameter
+    holders here (HeadLayerNorm) because their arithmetic lives inside the fused kernels."""
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        weight = self.weight + 1 if self.zero_centered_gamma else self.weight
+        return torch.nn.functional.layer_norm(input, tuple(self.weight.shape), weight, self.bias, self.eps)
+
+
+class TransformerBlock(nn.Module):
+    """Drop-in for the reference's `TransformerBlock` (dit_module.py:1373-1441), the caller of the layers: same
+    constructor `(model_config, engine_config, pre_process, post_process)`, same sub-module names (`layers.<i>.*`,
+    `final_layernorm`), same `set_input_tensor` / `forward`. pp_size == 1 on this path, so the block holds all
+    `num_layers` layers (`:1390`) and layer numbers carry no offset. With `engine_config.enable_cuda_graph` the layer
+    stack runs as one CUDA graph per forward signature (cuda_graph.GraphedLayerStack); the final fp32 LayerNorm
+    (`:1438-1439`) stays outside the graph, so the returned tensor is the caller's own."""
+
+    def __init__(self, model_config: ModelConfig, engine_config: EngineConfig, pre_process: bool = True,
+                 post_process: bool = True):
+        super().__init__()
+        self.model_config = model_config
+        self.engine_config = engine_config
+        self.pre_process = pre_process
+        self.post_process = post_process
+        self.input_tensor = None          # required for pipeline parallel schedules (dit_module.py:1387-1388)
+        if engine_config.pp_size != 1:
+            raise NotImplementedError("pipeline parallelism is outside this build (pp_size must be 1)")
+        self.layers = nn.ModuleList([TransformerLayer(model_config, engine_config, layer_number=i)
+                                     for i in range(model_config.num_layers)])
+        if self.post_process:
+            self.final_layernorm = FusedLayerNorm(model_config, model_config.hidden_size)
+        self._graphed = None
+
+    def set_input_tensor(self, input_tensor: torch.Tensor):
+        """dit_module.py:1403-1411."""
+        self.input_tensor = input_tensor
+
+    @torch.no_grad()
+    def forward(self, hidden_states: torch.Tensor, condition: torch.Tensor, condition_map: torch.Tensor,
+                y_xattn_flat: torch.Tensor, rotary_pos_emb: torch.Tensor, inference_params: InferenceParams,
+                meta_args: ModelMetaArgs) -> torch.Tensor:
+        if not self.pre_process:
+            assert self.input_tensor is not None, "please call set_input_tensor for pp"
+            hidden_states = self.input_tensor
+        if self.engine_config.enable_cuda_graph and hidden_states.is_cuda:
+            if self._graphed is None:
+                from .cuda_graph import GraphedLayerStack
+                self._graphed = GraphedLayerStack(list(self.layers), self.engine_config)
+            hidden_states = self._graphed(hidden_states, condition, condition_map, y_xattn_flat, rotary_pos_emb,
+                                          inference_params, meta_args)
+        else:
+            for layer in self.layers:
+                hidden_states = layer(hidden_states, condition, condition_map, y_xattn_flat, rotary_pos_emb,
+                                      inference_params, meta_args)
+        if self.post_process:
+            hidden_states = self.final_layernorm(hidden_states.float())
+        return hidden_states
+
+
 def high_precision_promote(module: nn.Module) -> nn.Module:
-    """The part of `_high_precision_promoter` (dit_model.py:621-638) that concerns a transformer layer: the
-    self-attention q / k LayerNorms (not the `_xattn` ones) and both post-norms hold fp32 parameters."""
+    """The part of `_high_precision_promoter` (dit_model.py:621-638) that concerns the transformer block: the
+    self-attention q / k LayerNorms (not the `_xattn` ones), both post-norms and the block's final norm hold fp32
+    parameters."""
     for name, sub in module.named_modules():
         if "_xattn" in name:
             continue
-        if any(k in name for k in ("q_layernorm", "k_layernorm", "self_attn_post_norm", "mlp_post_norm")):
+        if any(k in name for k in ("q_layernorm", "k_layernorm", "self_attn_post_norm", "mlp_post_norm",
+                                   "final_layernorm")):
             sub.float()
     return module

@@ -690,6 +690,86 @@ def gen_fp8():
     print("fp8 fixture written")
 
 
+# ------------------------------------------------------------------ scenario: the block stack (TransformerBlock)
+def gen_block():
+    """The caller of the layers: the reference's own TransformerBlock (dit_module.py:1373-1441) with three layers and
+    fp8_quant on - layers 0 and 2 keep bf16 linears, layer 1 holds the fp8 ones (:407, 522, 535, 875) - and the final
+    fp32 LayerNorm, through a two-forward KV-cache sequence."""
+    dm = install_patches()
+    dm.bmm_fp8 = bmm_fp8_cpu
+    dm.range_mod_triton = range_mod_cpu
+    init_dist(0, 1, 29593)
+    from inference.common import InferenceParams
+    from inference.common.config import EngineConfig, ModelConfig
+    mc = ModelConfig(model_name="videodit_ardf", num_layers=3, hidden_size=128, ffn_hidden_size=512,
+                     num_attention_heads=4, num_query_groups=2, kv_channels=128, layernorm_epsilon=1e-6,
+                     apply_layernorm_1p=True, params_dtype=torch.bfloat16, xattn_cond_hidden_ratio=1.0)
+    ec = EngineConfig(cp_size=1, cp_strategy="none", ulysses_overlap_degree=1, fp8_quant=True)
+    torch.manual_seed(31)
+    block = dm.TransformerBlock(mc, ec)
+    g = torch.Generator().manual_seed(31)
+    with torch.no_grad():
+        for name, p_ in block.named_parameters():
+            if p_.dtype == torch.float8_e4m3fn or name.endswith("_scale"):
+                continue
+            if "layernorm" in name or "post_norm" in name:
+                p_.copy_((torch.randn(p_.shape, generator=g) * 0.2).to(p_.dtype))
+            elif name.endswith("layer_norm.weight"):
+                p_.copy_((1.0 + torch.randn(p_.shape, generator=g) * 0.02).to(p_.dtype))
+            elif name.endswith("bias"):
+                p_.copy_((torch.randn(p_.shape, generator=g) * 0.02).to(p_.dtype))
+            else:
+                p_.copy_((torch.randn(p_.shape, generator=g) * (1.0 / math.sqrt(p_.shape[-1]))).to(p_.dtype))
+    for name, sub in block.named_modules():
+        if isinstance(sub, (dm.PerTensorQuantizedFp8Linear, dm.PerChannelQuantizedFp8Linear)):
+            init_fp8_linear(sub, g, input_amax=4.0 if "linear_qkv" in name else 6.0)
+    for name, sub in block.named_modules():       # dit_model.py:621-638
+        if "_xattn" in name:
+            continue
+        if any(k in name for k in ("q_layernorm", "k_layernorm", "self_attn_post_norm", "mlp_post_norm",
+                                   "final_layernorm")):
+            sub.float()
+    block.eval()
+    assert isinstance(block.layers[1].mlp.linear_fc1, dm.PerTensorQuantizedFp8Linear)
+    assert isinstance(block.layers[0].mlp.linear_fc1, torch.nn.Linear)
+    assert isinstance(block.layers[2].mlp.linear_fc1, torch.nn.Linear)
+    H = W = 4
+    frames = 3
+    clip = frames * H * W
+    hidden = mc.hidden_size
+    fx = {"w." + k_: (v_.view(torch.uint8).numpy() if v_.dtype == torch.float8_e4m3fn else pk(v_))
+          for k_, v_ in block.state_dict().items()}
+    fx["clip"] = np.array(clip)
+    fx["dims"] = np.array([3, hidden, 512, 4, 2])       # layers, hidden, ffn, Hq, Hkv
+    inf = InferenceParams(max_batch_size=1, max_sequence_length=4 * clip)
+    for tag, sp, dn, k_chunks, y_index, update, extra in (
+            ("A", 0, 2, [(0, 1), (0, 2)], [50, 41], True, True),
+            ("B", 1, 2, [(0, 2), (1, 3)], [0, 64], True, False)):
+        S = dn * clip
+        hs = torch.randn(S, 1, hidden, generator=g).to(torch.bfloat16)
+        kvs = torch.randn(int(sum(y_index)), hidden, generator=g).to(torch.bfloat16)
+        cond = torch.randn(1, dn, int(hidden * mc.cond_hidden_ratio), generator=g).to(torch.bfloat16)
+        cmap = torch.arange(dn).repeat_interleave(clip).reshape(1, -1).transpose(0, 1).contiguous()
+        rope = rope_for(dm, (sp + dn) * frames, H, W, dn * frames)
+        m = meta(dm, clip, sp, dn, 1, [[s_ * clip, e_ * clip] for s_, e_ in k_chunks], y_index, fwd_extra=extra)
+        inf.update_kv_cache = update
+        per_layer = []
+        hooks = [l_.register_forward_hook(lambda mod, a, o: per_layer.append(o.clone())) for l_ in block.layers]
+        with torch.no_grad():
+            out = block(hs, cond, cmap, kvs, rope, inf, m)
+        for h_ in hooks:
+            h_.remove()
+        assert out.dtype == torch.float32 and len(per_layer) == 3
+        fx.update({f"{tag}.after_layer{i}": pk(t_) for i, t_ in enumerate(per_layer)})
+        fx.update({f"{tag}.hidden_states": pk(hs), f"{tag}.key_value_states": pk(kvs), f"{tag}.condition": pk(cond),
+                   f"{tag}.condition_map": cmap.numpy(), f"{tag}.rope": pk(rope),
+                   f"{tag}.k_range": np.array([[s_ * clip, e_ * clip] for s_, e_ in k_chunks], dtype=np.int32),
+                   f"{tag}.y_index": np.array(y_index), f"{tag}.meta": np.array([sp, dn, int(update), int(extra)]),
+                   f"{tag}.out": out.numpy()})
+    np.savez_compressed(os.path.join(OUT, "transformer_block.npz"), **fx)
+    print("transformer block fixture written")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -707,6 +787,8 @@ if __name__ == "__main__":
         gen_two_blocks()
     if which in ("fp8",):         # run on its own (a process group per scenario)
         gen_fp8()
+    if which in ("block",):       # run on its own
+        gen_block()
     if which in ("gating",):      # run on its own: it monkey-patches Tensor.is_cuda while it runs
         gen_gating()
     if which in ("all", "single"):

@@ -616,6 +616,22 @@ def transformer_layer(w, hs, condition, condition_map, kvs, rope, cache, has_inf
     return bias_modulate_add(m, x1, condition_map, gate_mlp, w["mlp_post_norm.weight"], w["mlp_post_norm.bias"])
 
 
+def transformer_block(layer_weights, final_ln_w, final_ln_b, hs, condition, condition_map, kvs, rope, caches, has_inf,
+                      slice_point, dn, clip, np_q_range, np_k_range, y_index, update_kv_cache,
+                      gated_linear_unit=False, fwd_extra_1st_chunk=False, collect=None):
+    """TransformerBlock.forward, dit_module.py:1413-1441 (pre_process and post_process both True, pp_size 1): the
+    layers in order, each with its own KV cache, then the final LayerNorm (+1p) on the fp32 hidden state. `collect`, if
+    a list, receives the hidden state after every layer."""
+    x = hs
+    for w, cache in zip(layer_weights, caches):
+        x = transformer_layer(w, x, condition, condition_map, kvs, rope, cache, has_inf, slice_point, dn, clip,
+                              np_q_range, np_k_range, y_index, update_kv_cache, gated_linear_unit=gated_linear_unit,
+                              fwd_extra_1st_chunk=fwd_extra_1st_chunk)
+        if collect is not None:
+            collect.append(x)
+    return layer_norm(x, final_ln_w, final_ln_b, 1e-6, zero_centered_gamma=True)
+
+
 # ----------------------------------------------------------------------------------------------- RoPE table
 def rope_table(T_total: int, H: int, W: int, bands: Optional[np.ndarray] = None, keep_last_T: Optional[int] = None):
     """LearnableRotaryEmbeddingCat.get_embed as used at dit_model.py:163-166 (in_pixels=False, dim=128):

@@ -214,3 +214,64 @@ def test_fp8_quant_layer_replays_the_reference(doubles, variant, fused):
     finally:
         D.qkv_proj_norm_rope = D_q
     assert (calls["fused_fp8"] > 0) == (variant == "shared" and fused)
+
+
+def _block_from_golden(T, g, graph=False):
+    from magi_b200.common import EngineConfig, ModelConfig
+    L, hidden, ffn, Hq, Hkv = [int(x) for x in g["dims"]]
+    mc = ModelConfig(num_layers=L, hidden_size=hidden, ffn_hidden_size=ffn, num_attention_heads=Hq,
+                     num_query_groups=Hkv)
+    block = T.high_precision_promote(T.TransformerBlock(mc, EngineConfig(fp8_quant=True, enable_cuda_graph=graph)))
+    sd = {}
+    for name, key in g.weights().items():
+        a = g.raw(key)
+        sd[name] = torch.from_numpy(a.copy()).view(torch.float8_e4m3fn) if a.dtype == np.uint8 else g.torch(key)
+    block.load_state_dict(sd, strict=True)
+    return block.eval(), Hkv
+
+
+def test_transformer_block_replays_the_reference(doubles):
+    """The caller of the layers: the drop-in TransformerBlock (dit_module.py:1373-1441) against the reference's own
+    block run on CPU (tests/golden/transformer_block.npz): three layers with fp8_quant on - layers 0 and 2 bf16, layer 1
+    fp8, as the reference chooses by layer number - and the final fp32 LayerNorm; the reference state dict loads with
+    strict=True under the reference's names (`layers.<i>...`, `final_layernorm`); two forwards through the KV caches.
+    (1) every layer on the REFERENCE's input of that layer (the fixture holds the hidden state after each layer):
+        rel-L2 < 8e-3, and the final norm on the reference's last hidden state: 1e-5;
+    (2) the block end to end: the fp8 layer turns the bf16-ulp differences between two GEMM implementations in its
+        input into e4m3 rounding flips (3 mantissa bits), a ~7x amplification - the numpy oracle itself sits at
+        1.8e-2 from the reference's ATen run here - so the end-to-end bound is 5e-2."""
+    _, T = doubles
+    from magi_b200.common import InferenceParams
+    from magi_b200.fp8_linear import PerTensorQuantizedFp8Linear
+    g = Golden("transformer_block.npz")
+    block, _ = _block_from_golden(T, g)
+    assert [isinstance(l.mlp.linear_fc1, PerTensorQuantizedFp8Linear) for l in block.layers] == [False, True, False]
+    assert block.final_layernorm.weight.dtype == torch.float32
+    clip = int(g["clip"])
+    for mode in ("per_layer", "end_to_end"):
+        inf = InferenceParams(max_batch_size=1, max_sequence_length=4 * clip)
+        for tag in ("A", "B"):
+            sp, dn, upd, extra = [int(x) for x in g[f"{tag}.meta"]]
+            meta = _meta(clip, sp, dn, 1, O.core_q_ranges(clip, dn, 1), g.raw(f"{tag}.k_range"), g[f"{tag}.y_index"],
+                         extra)
+            inf.update_kv_cache = bool(upd)
+            args = (g.torch(f"{tag}.condition"), g.torch(f"{tag}.condition_map"), g.torch(f"{tag}.key_value_states"),
+                    g.torch(f"{tag}.rope"), inf, meta)
+            if mode == "end_to_end":
+                out = block(g.torch(f"{tag}.hidden_states"), *args)
+                assert out.dtype == torch.float32
+                rel, _ = _rel(out, g[f"{tag}.out"])
+                assert rel < 5e-2, (tag, rel)
+                continue
+            for l, layer in enumerate(block.layers):
+                x = g.torch(f"{tag}.hidden_states" if l == 0 else f"{tag}.after_layer{l - 1}")
+                rel, _ = _rel(layer(x, *args), g[f"{tag}.after_layer{l}"])
+                assert rel < 8e-3, (tag, l, rel)
+            with torch.no_grad():
+                normed = block.final_layernorm(g.torch(f"{tag}.after_layer2").float())
+            rel, _ = _rel(normed, g[f"{tag}.out"])
+            assert rel < 1e-5, (tag, rel)
+    # pipeline hooks of the reference interface
+    block.pre_process = False
+    with pytest.raises(AssertionError, match="set_input_tensor"):
+        block(None, None, None, None, None, inf, meta)

@@ -438,3 +438,37 @@ def test_fp8_transformer_layer_matches_reference(variant):
             assert got.shape == ref.shape and rel < 5e-3, (variant, tag, name, rel)
     ref_cache = g[pre + "cache"]
     assert np.abs(cache[:3 * clip] - ref_cache).max() <= 1.6e-2
+
+
+def test_transformer_block_matches_reference():
+    """TransformerBlock (dit_module.py:1373-1441: three layers, the middle one fp8 under fp8_quant, final fp32
+    LayerNorm) through the oracle against the reference's own block run on CPU. Every layer on the reference's input of
+    that layer: rel-L2 < 5e-3; the final norm on the reference's last hidden state: 1e-5; end to end 5e-2 (the fp8
+    layer amplifies the bf16-ulp differences of its input ~7x through e4m3 rounding flips; measured 1.8e-2)."""
+    g = Golden("transformer_block.npz")
+    L = int(g["dims"][0])
+    ws = []
+    for l in range(L):
+        pre = f"w.layers.{l}."
+        ws.append({k[len(pre):]: (g.raw(k) if g.raw(k).dtype == np.uint8 else g[k]) for k in g.files if k.startswith(pre)})
+    fw, fb = g["w.final_layernorm.weight"], g["w.final_layernorm.bias"]
+    clip = int(g["clip"])
+    c_tf = [np.zeros((4 * clip, 2, 256), dtype=np.float32) for _ in range(L)]
+    c_e2e = [np.zeros((4 * clip, 2, 256), dtype=np.float32) for _ in range(L)]
+    for tag in ("A", "B"):
+        sp, dn, upd, extra = [int(x) for x in g[f"{tag}.meta"]]
+        common = (g[f"{tag}.condition"], g.raw(f"{tag}.condition_map"), g[f"{tag}.key_value_states"], g[f"{tag}.rope"])
+        tail = (True, sp, dn, clip, O.core_q_ranges(clip, dn, 1), g.raw(f"{tag}.k_range"), g[f"{tag}.y_index"], bool(upd))
+        for l in range(L):
+            x = g[f"{tag}.hidden_states"] if l == 0 else g[f"{tag}.after_layer{l - 1}"]
+            y = O.transformer_layer(ws[l], x, *common, c_tf[l], *tail, fwd_extra_1st_chunk=bool(extra))
+            ref = g[f"{tag}.after_layer{l}"]
+            rel = np.linalg.norm(y - ref) / np.linalg.norm(ref)
+            assert rel < 5e-3, (tag, l, rel)
+        ref = g[f"{tag}.out"]
+        y = O.layer_norm(g[f"{tag}.after_layer{L - 1}"], fw, fb, 1e-6, True)
+        assert np.linalg.norm(y - ref) / np.linalg.norm(ref) < 1e-5
+        out = O.transformer_block(ws, fw, fb, g[f"{tag}.hidden_states"], *common, c_e2e, *tail,
+                                  fwd_extra_1st_chunk=bool(extra))
+        rel = np.linalg.norm(out - ref) / np.linalg.norm(ref)
+        assert out.shape == ref.shape and rel < 5e-2, (tag, rel)
