@@ -701,8 +701,9 @@ def gen_block():
     init_dist(0, 1, 29593)
     from inference.common import InferenceParams
     from inference.common.config import EngineConfig, ModelConfig
-    mc = ModelConfig(model_name="videodit_ardf", num_layers=3, hidden_size=128, ffn_hidden_size=512,
-                     num_attention_heads=4, num_query_groups=2, kv_channels=128, layernorm_epsilon=1e-6,
+    # hidden 256: the fused gating kernel works on 256-wide groups (every real model is a multiple of it)
+    mc = ModelConfig(model_name="videodit_ardf", num_layers=3, hidden_size=256, ffn_hidden_size=512,
+                     num_attention_heads=2, num_query_groups=2, kv_channels=128, layernorm_epsilon=1e-6,
                      apply_layernorm_1p=True, params_dtype=torch.bfloat16, xattn_cond_hidden_ratio=1.0)
     ec = EngineConfig(cp_size=1, cp_strategy="none", ulysses_overlap_degree=1, fp8_quant=True)
     torch.manual_seed(31)
@@ -740,7 +741,7 @@ def gen_block():
     fx = {"w." + k_: (v_.view(torch.uint8).numpy() if v_.dtype == torch.float8_e4m3fn else pk(v_))
           for k_, v_ in block.state_dict().items()}
     fx["clip"] = np.array(clip)
-    fx["dims"] = np.array([3, hidden, 512, 4, 2])       # layers, hidden, ffn, Hq, Hkv
+    fx["dims"] = np.array([3, hidden, 512, 2, 2])       # layers, hidden, ffn, Hq, Hkv
     inf = InferenceParams(max_batch_size=1, max_sequence_length=4 * clip)
     for tag, sp, dn, k_chunks, y_index, update, extra in (
             ("A", 0, 2, [(0, 1), (0, 2)], [50, 41], True, True),
