@@ -247,7 +247,7 @@ def test_transformer_block_matches_reference_golden():
     reference's own block (tests/golden/transformer_block.npz: three layers, the middle one fp8 under fp8_quant, final
     fp32 LayerNorm): strict state-dict load under the reference's names, two forwards through the KV caches.
     Every layer on the reference's input of that layer: rel-L2 <= 2e-2 (the per-step criterion of SURVEY.md 8(c), as
-    in the single-layer tests); final norm on the reference's last hidden state: 1e-5; end to end 1e-1 (the fp8 layer
+    in the single-layer tests); final norm on the reference's last hidden state: 1e-5; end to end 5e-2 (the fp8 layer
     amplifies bf16-ulp input differences ~7x through e4m3 rounding flips and the final LayerNorm removes the large
     common component of the hidden state - the CPU oracle itself sits at 1.8e-2 from the reference's ATen run). With enable_cuda_graph the layer stack replays from one CUDA graph per forward
     signature and must agree with the eager block."""
@@ -324,9 +324,10 @@ def test_transformer_block_matches_reference_golden():
             assert out_e.dtype == torch.float32 and out_g.dtype == torch.float32
             r, rg = rel(out_e, g[f"{tag}.out"]), rel(out_g, out_e.cpu().numpy())
             print(f"block {tag} end to end: rel-L2 {r:.3e}; graph vs eager {rg:.3e}")
-            assert r <= 1e-1, (tag, r)
+            assert r <= 5e-2, (tag, r)          # measured on the B200: 1.8e-2 / 2.0e-2 (profiles/r02blk_pytest.log)
             # cuBLAS may pick other GEMM algorithms under stream capture, and the fp8 layer amplifies that: same bound
-            assert rg <= 1e-1, tag
+            # (measured: bit-identical)
+            assert rg <= 5e-2, tag
     st = graphed._graphed
     assert st is not None and (st.disabled_reason is not None or (st.captures == 2 and st.replays == 4)), \
         (st.captures, st.replays, st.disabled_reason)
