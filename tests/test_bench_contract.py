@@ -49,3 +49,16 @@ def test_both_arms_name_the_same_config():
     assert "ulysses" in bench.static_config(a, bench.WORKLOADS["cfg2"], 8)["parallelism"]
     a.cp_mode = "ring"
     assert "multimem" in bench.static_config(a, bench.WORKLOADS["cfg2"], 2)["parallelism"]
+
+
+def test_prologue_byte_accounting():
+    """roofline.prologue_hbm: the algorithmic bytes of the layer's one prologue launch at cfg2 - projection outputs in
+    (q, k, v, qx, text [K|V], sin / cos rows), q / packed [K|V] / its cache copy / qx / text [K|V] out."""
+    sys.path.insert(0, ROOT)
+    import bench
+    w = bench.WORKLOADS["cfg2"]
+    S, T = 4 * 9360, 50 + 3 * 512
+    q, kv = S * 24 * 128 * 2, S * 8 * 256 * 2
+    expect = (2 * q + kv + S * 96 * 4 + T * 8 * 256 * 2) + (2 * q + 2 * kv + T * 8 * 256 * 2)
+    assert bench.prologue_bytes(w) == expect
+    assert abs(expect / 1e6 - 1407.6) < 0.1
